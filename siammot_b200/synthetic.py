@@ -1,0 +1,109 @@
+"""Seeded synthetic weights with the reference state-dict layout.
+
+There are no checkpoints offline (all are S3 downloads: /root/reference/readme/model_zoo.md), so
+parity tests and the benchmark run on random weights of the real architecture.  The recipe keeps
+activations O(1) through the 39 DLA convs (He-style gains; FrozenBN gamma < 1 on residual
+branches) and scales the head layers so that scores spread over (0,1) and the EMM regression
+outputs are tens of pixels -- i.e. detections start tracks, tracks move, get suspended and
+resumed, instead of everything sitting at 0.5 as with the default initialisers.
+
+Pure function of (cfg, seed): torch CPU generator, so the same tensors are produced in the
+authoring container and on the GPU box."""
+import math
+
+import torch
+
+DLA34_LEVELS = (1, 1, 1, 2, 2, 1)
+DLA34_CHANNELS = (16, 32, 64, 128, 256, 512)
+
+
+def dla34_layout():
+    """Yield (kind, name, shape) for every DLA-34 parameter/buffer group, in reference order
+    (dla.py:241-313).  kind in {"conv", "bn"}."""
+    ch = DLA34_CHANNELS
+    out = [("conv", "base_layer.0", (ch[0], 3, 7, 7)), ("bn", "base_layer.1", ch[0]),
+           ("conv", "level0.0", (ch[0], ch[0], 3, 3)), ("bn", "level0.1", ch[0]),
+           ("conv", "level1.0", (ch[1], ch[0], 3, 3)), ("bn", "level1.1", ch[1])]
+
+    def block(pre, cin, cout):
+        out.extend([("conv", pre + ".conv1", (cout, cin, 3, 3)), ("bn", pre + ".bn1", cout),
+                    ("conv", pre + ".conv2", (cout, cout, 3, 3)), ("bn", pre + ".bn2", cout)])
+
+    def tree(pre, levels, cin, cout, level_root, root_dim=0):
+        if root_dim == 0:
+            root_dim = 2 * cout
+        if level_root:
+            root_dim += cin
+        if levels == 1:
+            block(pre + ".tree1", cin, cout)
+            block(pre + ".tree2", cout, cout)
+            out.extend([("conv", pre + ".root.conv", (cout, root_dim, 1, 1)), ("bn", pre + ".root.bn", cout)])
+        else:
+            tree(pre + ".tree1", levels - 1, cin, cout, False, 0)
+            tree(pre + ".tree2", levels - 1, cout, cout, False, root_dim + cout)
+        if cin != cout:
+            out.extend([("conv", pre + ".project.0", (cout, cin, 1, 1)), ("bn", pre + ".project.1", cout)])
+
+    for lvl in range(2, 6):
+        tree("level%d" % lvl, DLA34_LEVELS[lvl], ch[lvl - 1], ch[lvl], lvl > 2)
+    return out
+
+
+def make_state_dict(cfg, seed=1):
+    g = torch.Generator().manual_seed(seed)
+
+    def randn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    def rand(*shape):
+        return torch.rand(*shape, generator=g)
+
+    sd = {}
+    for kind, name, shape in dla34_layout():
+        key = "backbone.body." + name
+        if kind == "conv":
+            fan_in = shape[1] * shape[2] * shape[3]
+            sd[key + ".weight"] = randn(*shape, std=math.sqrt(2.0 / fan_in))
+        else:
+            residual_branch = name.endswith("bn2") or ".project" in name
+            sd[key + ".weight"] = (0.6 if residual_branch else 0.9) + 0.1 * rand(shape)
+            sd[key + ".bias"] = randn(shape, std=0.1)
+            sd[key + ".running_mean"] = randn(shape, std=0.1)
+            sd[key + ".running_var"] = 1.0 + 0.1 * rand(shape)
+    C = cfg.MODEL.DLA.BACKBONE_OUT_CHANNELS
+    for i, cin in enumerate(DLA34_CHANNELS[2:], 1):
+        sd["backbone.fpn.fpn_inner%d.weight" % i] = randn(C, cin, 1, 1, std=math.sqrt(1.0 / cin))
+        sd["backbone.fpn.fpn_inner%d.bias" % i] = randn(C, std=0.1)
+        sd["backbone.fpn.fpn_layer%d.weight" % i] = randn(C, C, 3, 3, std=math.sqrt(1.0 / (9 * C)))
+        sd["backbone.fpn.fpn_layer%d.bias" % i] = randn(C, std=0.1)
+    A = len(cfg.MODEL.RPN.ASPECT_RATIOS)
+    sd["rpn.head.conv.weight"] = randn(C, C, 3, 3, std=math.sqrt(2.0 / (9 * C)))
+    sd["rpn.head.conv.bias"] = randn(C, std=0.1)
+    sd["rpn.head.cls_logits.weight"] = randn(A, C, 1, 1, std=0.4 / math.sqrt(C))
+    sd["rpn.head.cls_logits.bias"] = randn(A, std=0.1) - 1.0
+    sd["rpn.head.bbox_pred.weight"] = randn(4 * A, C, 1, 1, std=0.3 / math.sqrt(C))
+    sd["rpn.head.bbox_pred.bias"] = randn(4 * A, std=0.05)
+    H = cfg.MODEL.ROI_BOX_HEAD
+    d_in, rep, ncls = C * H.POOLER_RESOLUTION ** 2, H.MLP_HEAD_DIM, H.NUM_CLASSES
+    pre = "roi_heads.box."
+    sd[pre + "feature_extractor.fc6.weight"] = randn(rep, d_in, std=math.sqrt(2.0 / d_in))
+    sd[pre + "feature_extractor.fc6.bias"] = randn(rep, std=0.1)
+    sd[pre + "feature_extractor.fc7.weight"] = randn(rep, rep, std=math.sqrt(2.0 / rep))
+    sd[pre + "feature_extractor.fc7.bias"] = randn(rep, std=0.1)
+    sd[pre + "predictor.cls_score.weight"] = randn(ncls, rep, std=2.0 / math.sqrt(rep))
+    sd[pre + "predictor.cls_score.bias"] = randn(ncls, std=0.1) + torch.tensor([3.5] + [0.0] * (ncls - 1))
+    nreg = 2 if cfg.MODEL.CLS_AGNOSTIC_BBOX_REG else ncls
+    sd[pre + "predictor.bbox_pred.weight"] = randn(4 * nreg, rep, std=0.5 / math.sqrt(rep))
+    sd[pre + "predictor.bbox_pred.bias"] = randn(4 * nreg, std=0.05)
+    pre = "roi_heads.track.tracker.predictor."
+    for tower in ("cls_tower", "reg_tower"):
+        sd[pre + tower + ".0.weight"] = randn(C, C, 3, 3, std=math.sqrt(2.0 / (9 * C)))
+        sd[pre + tower + ".1.weight"] = 0.9 + 0.2 * rand(C)
+        sd[pre + tower + ".1.bias"] = randn(C, std=0.1)
+    sd[pre + "cls.weight"] = randn(2, C, 3, 3, std=1.5 / math.sqrt(9 * C))
+    sd[pre + "cls.bias"] = torch.tensor([0.0, 1.0])
+    sd[pre + "center.weight"] = randn(1, C, 3, 3, std=1.0 / math.sqrt(9 * C))
+    sd[pre + "center.bias"] = torch.tensor([1.0])
+    sd[pre + "reg.weight"] = randn(4, C, 3, 3, std=6.0 / math.sqrt(9 * C))
+    sd[pre + "reg.bias"] = torch.tensor([30.0, 60.0, 30.0, 60.0])
+    return sd

@@ -1,0 +1,35 @@
+"""Seeded scenarios shared by the golden-vector generator, the oracle tests and the GPU parity tests."""
+import os
+
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
+
+# name -> dict(yaml, overrides (yacs list form), H, W, frames, n_obj, clip_seed, weight_seed, inject)
+SCENARIOS = {
+    # default TAO-style config, natural start / suspend / resume dynamics
+    "emm_256x384": dict(yaml="DLA_34_FPN_EMM.yaml", overrides=[], H=256, W=384, frames=6, n_obj=6,
+                        clip_seed=0, weight_seed=1, inject=None),
+    # MOT17 config: amodal (no clipping anywhere) + short dormancy so tracks expire
+    "emm_amodal_expire_192x320": dict(yaml="DLA_34_FPN_EMM_MOT17.yaml",
+                                      overrides=["MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES", 2,
+                                                 "INFERENCE.USE_GIVEN_DETECTIONS", False],
+                                      H=192, W=320, frames=7, n_obj=5, clip_seed=3, weight_seed=2, inject=None),
+    # BASELINE.json configs[0]: one 720p frame pair (704x1280 after the reference resize rule), 4 injected
+    # tracks (cx, cy, w, h) hitting FPN levels 0,1,2,0
+    "pair_720p_4tracks": dict(yaml="DLA_34_FPN_EMM.yaml", overrides=[], H=704, W=1280, frames=2, n_obj=6,
+                              clip_seed=0, weight_seed=1,
+                              inject=[(200., 300., 60., 150.), (500., 350., 80., 200.),
+                                      (800., 352., 300., 500.), (1100., 400., 40., 100.)]),
+}
+
+
+def inject_boxes(spec):
+    b = torch.tensor(spec, dtype=torch.float32)
+    return torch.stack((b[:, 0] - b[:, 2] / 2, b[:, 1] - b[:, 3] / 2,
+                        b[:, 0] + b[:, 2] / 2, b[:, 1] + b[:, 3] / 2), dim=1)
+
+
+def golden_path(name):
+    return os.path.join(GOLDEN_DIR, name + ".pt")

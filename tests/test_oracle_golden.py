@@ -1,0 +1,72 @@
+"""Pin the CPU oracle (oracle/siammot_oracle.py) against the reference.
+
+The golden vectors were produced by the reference's own modules (tests/golden/make_golden.py).
+Tolerance: both sides are fp32 CPU PyTorch built from the same primitive ops, so they agree to
+rounding; 1e-4 px / 1e-5 score leaves room for a different CPU / oneDNN code path."""
+import pytest
+import torch
+
+from helpers import load_golden, run_oracle_scenario
+from scenarios import SCENARIOS
+
+def _canon(boxes, obj):
+    rows = sorted(range(boxes.shape[0]), key=lambda i: (-float(obj[i]),) + tuple(boxes[i].tolist()))
+    return boxes[rows]
+
+
+BOX_TOL = 1e-4
+SCORE_TOL = 1e-5
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_oracle_matches_reference_golden(name):
+    gold = load_golden(name)["frames"]
+    got = run_oracle_scenario(name)
+    assert len(got) == len(gold)
+    for t, (g, o) in enumerate(zip(gold, got)):
+        assert o["boxes"].shape == g["boxes"].shape, "frame %d: box count" % t
+        assert torch.equal(o["ids"], g["ids"]), "frame %d: ids must be bit-exact" % t
+        assert torch.equal(o["labels"], g["labels"])
+        assert (o["boxes"] - g["boxes"]).abs().max() <= BOX_TOL
+        assert (o["scores"] - g["scores"]).abs().max() <= SCORE_TOL
+        assert o["active"] == g["active"] and o["dormant"] == g["dormant"]
+        # proposals: the order inside a group of EQUAL fp32 objectness is implementation-defined in
+        # the reference (torch.topk); compare after a canonical sort inside such groups
+        props = _canon(o["trace"]["proposals"][:32], g["objectness"])
+        assert (props - _canon(g["props"], g["objectness"])).abs().max() <= BOX_TOL
+        if "track_boxes" in g:
+            tr = o["trace"]["tracks"]
+            assert torch.equal(tr["ids"], g["track_ids"])
+            assert (tr["boxes"] - g["track_boxes"]).abs().max() <= BOX_TOL
+            assert (tr["scores"] - g["track_scores"]).abs().max() <= SCORE_TOL
+
+
+def test_golden_scenarios_exercise_the_state_machine():
+    """The fixtures are only useful if tracks start, persist, go dormant, resume and expire."""
+    g = load_golden("emm_256x384")["frames"]
+    ids_per_frame = [set(f["ids"][f["ids"] >= 0].tolist()) for f in g]
+    assert all(len(s) > 0 for s in ids_per_frame)
+    assert any(ids_per_frame[t] & ids_per_frame[t + 1] for t in range(len(g) - 1)), "no track persisted"
+    assert any(len(f["dormant"]) > 0 for f in g)
+    resumed = any((set(g[t]["dormant"]) & set(g[t + 1]["active"])) for t in range(len(g) - 1))
+    assert resumed, "no dormant track was resumed"
+    e = load_golden("emm_amodal_expire_192x320")["frames"]
+    seen, expired = set(), False
+    for f in e:
+        alive = set(f["active"]) | set(f["dormant"])
+        expired |= bool(seen - alive)
+        seen |= alive
+    assert expired, "no track expired"
+
+
+@pytest.mark.skipif(not __import__("oracle.reference_loader", fromlist=["x"]).available(),
+                    reason="reference tree not present (authoring container only)")
+def test_oracle_matches_live_reference_xcorr():
+    """xcorr.py imports verbatim (pure torch): compare the restatement with it directly."""
+    from oracle import reference_loader
+    reference_loader.load()
+    from siammot.modelling.track_head.EMM.xcorr import xcorr_depthwise as ref_xcorr
+    from oracle.siammot_oracle import xcorr_depthwise
+    torch.manual_seed(0)
+    x, k = torch.randn(5, 16, 30, 30), torch.randn(5, 16, 15, 15)
+    assert torch.equal(ref_xcorr(x, k), xcorr_depthwise(x, k))
