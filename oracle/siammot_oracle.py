@@ -105,14 +105,22 @@ def fpn_forward(P, feats, pre="backbone.fpn"):
 # ----------------------------------------------------------------------------------------------
 # RPN (upstream head + anchors; patched post-processor rpn_patch.py:15-60)
 # ----------------------------------------------------------------------------------------------
-def rpn_forward(P, cfg, feats, img_w, img_h):
-    """Returns proposals (R,4) and objectness (R,), R <= FPN_POST_NMS_TOP_N_TEST."""
+def rpn_head_forward(P, feats):
+    """Upstream SingleConvRPNHead: 3x3 conv + ReLU, 1x1 -> A objectness, 1x1 -> 4A deltas, shared over levels."""
+    logits, deltas = [], []
+    for f in feats:
+        t = F.relu(F.conv2d(f, P["rpn.head.conv.weight"], P["rpn.head.conv.bias"], 1, 1))
+        logits.append(F.conv2d(t, P["rpn.head.cls_logits.weight"], P["rpn.head.cls_logits.bias"]))
+        deltas.append(F.conv2d(t, P["rpn.head.bbox_pred.weight"], P["rpn.head.bbox_pred.bias"]))
+    return logits, deltas
+
+
+def rpn_select(cfg, logits_l, deltas_l, img_w, img_h):
+    """Patched RPNPostProcessor (rpn_patch.py:15-60) + upstream select_over_all_levels.
+    logits_l[i]: (1,A,H,W), deltas_l[i]: (1,4A,H,W).  Returns proposals (R,4), objectness (R,)."""
     R = cfg.MODEL.RPN
     boxes_all, scores_all = [], []
-    for lvl, f in enumerate(feats):
-        t = F.relu(F.conv2d(f, P["rpn.head.conv.weight"], P["rpn.head.conv.bias"], 1, 1))
-        logits = F.conv2d(t, P["rpn.head.cls_logits.weight"], P["rpn.head.cls_logits.bias"])
-        deltas = F.conv2d(t, P["rpn.head.bbox_pred.weight"], P["rpn.head.bbox_pred.bias"])
+    for lvl, (logits, deltas) in enumerate(zip(logits_l, deltas_l)):
         _, A, H, W = logits.shape
         # permute_and_flatten -> order (h, w, a)                         rpn_patch.py:21-24
         logit = logits[0].permute(1, 2, 0).reshape(-1)
@@ -140,6 +148,12 @@ def rpn_forward(P, cfg, feats, img_w, img_h):
     return boxes[inds], scores[inds]
 
 
+def rpn_forward(P, cfg, feats, img_w, img_h):
+    """Returns proposals (R,4) and objectness (R,), R <= FPN_POST_NMS_TOP_N_TEST."""
+    logits, deltas = rpn_head_forward(P, feats)
+    return rpn_select(cfg, logits, deltas, img_w, img_h)
+
+
 # ----------------------------------------------------------------------------------------------
 # box head (box_head.py:23-52, inference.py:46-191)
 # ----------------------------------------------------------------------------------------------
@@ -161,9 +175,8 @@ def pool_rois(feats, boxes, level_boxes, scales, res, sampling, rois=None):
     return out
 
 
-def box_head_forward(P, cfg, feats, boxes, img_w, img_h, ids=None, labels=None):
-    """ROIBoxHead.forward + PostProcessor.  ``ids``/``labels`` given => the boxes are tracks
-    (inference.py:80-103).  Returns dict(boxes, scores, ids, labels)."""
+def box_head_features(P, cfg, feats, boxes):
+    """FPN2MLPFeatureExtractor + FPNPredictor (upstream; box_head.py:46-48): logits (n,ncls), deltas (n,4*ncls)."""
     H = cfg.MODEL.ROI_BOX_HEAD
     pre = "roi_heads.box."
     x = pool_rois(feats, boxes, boxes, H.POOLER_SCALES, H.POOLER_RESOLUTION, H.POOLER_SAMPLING_RATIO)
@@ -172,6 +185,12 @@ def box_head_forward(P, cfg, feats, boxes, img_w, img_h, ids=None, labels=None):
     x = F.relu(F.linear(x, P[pre + "feature_extractor.fc7.weight"], P[pre + "feature_extractor.fc7.bias"]))
     logits = F.linear(x, P[pre + "predictor.cls_score.weight"], P[pre + "predictor.cls_score.bias"])
     deltas = F.linear(x, P[pre + "predictor.bbox_pred.weight"], P[pre + "predictor.bbox_pred.bias"])
+    return logits, deltas
+
+
+def box_post(cfg, logits, deltas, boxes, img_w, img_h, ids=None, labels=None):
+    """PostProcessor.forward + filter_results (inference.py:46-191).  ``ids``/``labels`` given => the
+    boxes are tracks (inference.py:80-103).  Returns dict(boxes, scores, ids, labels)."""
     prob = F.softmax(logits, -1)
     n, ncls = prob.shape
     if cfg.MODEL.CLS_AGNOSTIC_BBOX_REG:
@@ -204,6 +223,12 @@ def box_head_forward(P, cfg, feats, boxes, img_w, img_h, ids=None, labels=None):
         oi += [ij[d][keep], ij[t]]
         ol.append(torch.full((keep.numel() + int(t.sum()),), j, dtype=torch.int64))
     return dict(boxes=torch.cat(ob), scores=torch.cat(os_), ids=torch.cat(oi), labels=torch.cat(ol))
+
+
+def box_head_forward(P, cfg, feats, boxes, img_w, img_h, ids=None, labels=None):
+    """ROIBoxHead.forward at inference (box_head.py:23-52)."""
+    logits, deltas = box_head_features(P, cfg, feats, boxes)
+    return box_post(cfg, logits, deltas, boxes, img_w, img_h, ids, labels)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,207 @@
+// Small NHWC tensor kernels: layout change, 2x2 max-pool, FPN top-down merge, P6 subsample,
+// GroupNorm+ReLU.  All are HBM/latency bound: one thread per 4 channels, 16B/8B vector accesses.
+#include "common.cuh"
+
+namespace smot {
+
+// ---- CHW fp32 image -> NHWC ---------------------------------------------------------------
+template <typename T>
+__global__ void image_to_nhwc_kernel(const float* __restrict__ chw, T* __restrict__ out, int C, int HW, int ld) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  for (int c = 0; c < C; ++c) out[(size_t)p * ld + c] = from_f<T>(chw[(size_t)c * HW + p]);
+  for (int c = C; c < ld; ++c) out[(size_t)p * ld + c] = from_f<T>(0.f);
+}
+
+// ---- MaxPool2d(2,2) --------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out, int batch, int H, int W, int C,
+                                  int in_ld, int out_ld) {
+  const int OH = H / 2, OW = W / 2, C4 = C / 4;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)batch * OH * OW * C4;
+  if (idx >= total) return;
+  int c = (int)(idx % C4) * 4;
+  size_t pix = idx / C4;
+  int ow = (int)(pix % OW);
+  int oh = (int)((pix / OW) % OH);
+  int n = (int)(pix / ((size_t)OW * OH));
+  const T* base = in + (((size_t)n * H + 2 * oh) * W + 2 * ow) * in_ld + c;
+  float4 a = ld4(base), b = ld4(base + in_ld), d = ld4(base + (size_t)W * in_ld), e = ld4(base + (size_t)(W + 1) * in_ld);
+  float4 r = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
+                         fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
+  st4(out + pix * out_ld + c, r);
+}
+
+// ---- lateral += bilinear(top), align_corners=False (ATen upsample_bilinear2d index rule) -----
+template <typename T>
+__global__ void upsample_add_kernel(const T* __restrict__ top, int Ht, int Wt, int top_ld, T* __restrict__ lat, int H,
+                                    int W, int lat_ld, int C) {
+  const int C4 = C / 4;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)H * W * C4) return;
+  int c = (int)(idx % C4) * 4;
+  size_t pix = idx / C4;
+  int x = (int)(pix % W), y = (int)(pix / W);
+  const float sh = (float)Ht / (float)H, sw = (float)Wt / (float)W;
+  float fy = fmaxf(sh * ((float)y + 0.5f) - 0.5f, 0.f);
+  float fx = fmaxf(sw * ((float)x + 0.5f) - 0.5f, 0.f);
+  int y0 = (int)fy, x0 = (int)fx;
+  int y1 = y0 + (y0 < Ht - 1 ? 1 : 0), x1 = x0 + (x0 < Wt - 1 ? 1 : 0);
+  float ly = fy - (float)y0, lx = fx - (float)x0;
+  float hy = 1.f - ly, hx = 1.f - lx;
+  float4 v00 = ld4(top + ((size_t)y0 * Wt + x0) * top_ld + c), v01 = ld4(top + ((size_t)y0 * Wt + x1) * top_ld + c);
+  float4 v10 = ld4(top + ((size_t)y1 * Wt + x0) * top_ld + c), v11 = ld4(top + ((size_t)y1 * Wt + x1) * top_ld + c);
+  T* dst = lat + pix * lat_ld + c;
+  float4 l = ld4(dst);
+  // ATen: w_y0 * (w_x0 * v00 + w_x1 * v01) + w_y1 * (w_x0 * v10 + w_x1 * v11)
+  l.x += hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+  l.y += hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+  l.z += hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
+  l.w += hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+  st4(dst, l);
+}
+
+// ---- out[y][x] = in[2y][2x] ----------------------------------------------------------------
+template <typename T>
+__global__ void subsample2_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C, int in_ld,
+                                  int out_ld) {
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1, C4 = C / 4;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)OH * OW * C4) return;
+  int c = (int)(idx % C4) * 4;
+  size_t pix = idx / C4;
+  int x = (int)(pix % OW), y = (int)(pix / OW);
+  st4(out + pix * out_ld + c, ld4(in + ((size_t)(2 * y) * W + 2 * x) * in_ld + c));
+}
+
+// ---- GroupNorm (+ReLU), in place; one CTA per (sample, group) --------------------------------
+template <typename T>
+__global__ void groupnorm_relu_kernel(T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      int HW, int C, int ld, int groups, float eps, int relu) {
+  const int n = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int cpg = C / groups;
+  T* base = x + (size_t)n * HW * ld + g * cpg;
+  const int cnt = HW * cpg;
+  __shared__ float s_sum[32], s_sq[32];
+  __shared__ float s_mean, s_rstd;
+  // pass 1: mean
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) sum += to_f(base[(size_t)(i / cpg) * ld + (i % cpg)]);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? s_sum[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) s_mean = v / (float)cnt;
+  }
+  __syncthreads();
+  const float mean = s_mean;
+  // pass 2: biased variance around the mean
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    float d = to_f(base[(size_t)(i / cpg) * ld + (i % cpg)]) - mean;
+    sq += d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((threadIdx.x & 31) == 0) s_sq[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? s_sq[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) s_rstd = rsqrtf(v / (float)cnt + eps);
+  }
+  __syncthreads();
+  const float rstd = s_rstd;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int c = i % cpg;
+    T* ptr = base + (size_t)(i / cpg) * ld + c;
+    float y = (to_f(*ptr) - mean) * rstd * gamma[g * cpg + c] + beta[g * cpg + c];
+    if (relu) y = fmaxf(y, 0.f);
+    *ptr = from_f<T>(y);
+  }
+}
+
+static inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace smot
+
+using namespace smot;
+
+extern "C" int smot_image_to_nhwc(const float* chw, void* out, int C, int H, int W, int out_ld, int dtype, void* stream) {
+  SMOT_CHECK_ARG(chw && out && C > 0 && H > 0 && W > 0 && out_ld >= C, "smot_image_to_nhwc: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int HW = H * W;
+  if (dtype == SMOT_F32)
+    image_to_nhwc_kernel<float><<<blocks_for(HW, 256), 256, 0, st>>>(chw, (float*)out, C, HW, out_ld);
+  else if (dtype == SMOT_F16)
+    image_to_nhwc_kernel<__half><<<blocks_for(HW, 256), 256, 0, st>>>(chw, (__half*)out, C, HW, out_ld);
+  else
+    SMOT_CHECK_ARG(false, "smot_image_to_nhwc: bad dtype %d", dtype);
+  SMOT_CHECK_LAUNCH("smot_image_to_nhwc");
+  return SMOT_OK;
+}
+
+extern "C" int smot_maxpool2x2(const void* in, void* out, int batch, int H, int W, int C, int in_ld, int out_ld,
+                               int dtype, void* stream) {
+  SMOT_CHECK_ARG(in && out && batch > 0 && H >= 2 && W >= 2 && C % 4 == 0 && in_ld % 4 == 0 && out_ld % 4 == 0,
+                 "smot_maxpool2x2: bad arguments (C, in_ld, out_ld must be multiples of 4)");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t total = (size_t)batch * (H / 2) * (W / 2) * (C / 4);
+  if (dtype == SMOT_F32)
+    maxpool2x2_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float*)in, (float*)out, batch, H, W, C, in_ld, out_ld);
+  else if (dtype == SMOT_F16)
+    maxpool2x2_kernel<__half><<<blocks_for(total, 256), 256, 0, st>>>((const __half*)in, (__half*)out, batch, H, W, C, in_ld, out_ld);
+  else
+    SMOT_CHECK_ARG(false, "smot_maxpool2x2: bad dtype %d", dtype);
+  SMOT_CHECK_LAUNCH("smot_maxpool2x2");
+  return SMOT_OK;
+}
+
+extern "C" int smot_upsample_add(const void* top, int Ht, int Wt, int top_ld, void* lateral, int H, int W, int lat_ld,
+                                 int C, int dtype, void* stream) {
+  SMOT_CHECK_ARG(top && lateral && Ht > 0 && Wt > 0 && H > 0 && W > 0 && C % 4 == 0 && top_ld % 4 == 0 && lat_ld % 4 == 0,
+                 "smot_upsample_add: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t total = (size_t)H * W * (C / 4);
+  if (dtype == SMOT_F32)
+    upsample_add_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float*)top, Ht, Wt, top_ld, (float*)lateral, H, W, lat_ld, C);
+  else if (dtype == SMOT_F16)
+    upsample_add_kernel<__half><<<blocks_for(total, 256), 256, 0, st>>>((const __half*)top, Ht, Wt, top_ld, (__half*)lateral, H, W, lat_ld, C);
+  else
+    SMOT_CHECK_ARG(false, "smot_upsample_add: bad dtype %d", dtype);
+  SMOT_CHECK_LAUNCH("smot_upsample_add");
+  return SMOT_OK;
+}
+
+extern "C" int smot_subsample2(const void* in, void* out, int H, int W, int C, int in_ld, int out_ld, int dtype,
+                               void* stream) {
+  SMOT_CHECK_ARG(in && out && H > 0 && W > 0 && C % 4 == 0 && in_ld % 4 == 0 && out_ld % 4 == 0, "smot_subsample2: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t total = (size_t)((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / 4);
+  if (dtype == SMOT_F32)
+    subsample2_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float*)in, (float*)out, H, W, C, in_ld, out_ld);
+  else if (dtype == SMOT_F16)
+    subsample2_kernel<__half><<<blocks_for(total, 256), 256, 0, st>>>((const __half*)in, (__half*)out, H, W, C, in_ld, out_ld);
+  else
+    SMOT_CHECK_ARG(false, "smot_subsample2: bad dtype %d", dtype);
+  SMOT_CHECK_LAUNCH("smot_subsample2");
+  return SMOT_OK;
+}
+
+extern "C" int smot_groupnorm_relu(void* x, const float* gamma, const float* beta, int batch, int HW, int C, int ld,
+                                   int groups, float eps, int relu, int dtype, void* stream) {
+  SMOT_CHECK_ARG(x && gamma && beta && batch >= 0 && HW > 0 && groups > 0 && C % groups == 0 && ld >= C,
+                 "smot_groupnorm_relu: bad arguments");
+  if (batch == 0) return SMOT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMOT_F32)
+    groupnorm_relu_kernel<float><<<batch * groups, 256, 0, st>>>((float*)x, gamma, beta, HW, C, ld, groups, eps, relu);
+  else if (dtype == SMOT_F16)
+    groupnorm_relu_kernel<__half><<<batch * groups, 256, 0, st>>>((__half*)x, gamma, beta, HW, C, ld, groups, eps, relu);
+  else
+    SMOT_CHECK_ARG(false, "smot_groupnorm_relu: bad dtype %d", dtype);
+  SMOT_CHECK_LAUNCH("smot_groupnorm_relu");
+  return SMOT_OK;
+}

@@ -1,0 +1,334 @@
+// EMM tracker kernels: depthwise cross-correlation and the fused upsample+decode.
+//
+// smot_xcorr  (xcorr.py:37-45).  NHWC: a lane owns one channel, so every shared/global access of a
+//   warp is a contiguous run of channels.  Per (track, 32-channel group) the S*S search window and
+//   the T*T template are staged once in shared memory; each warp then produces output rows with a
+//   register-blocked row convolution (for each template row u: S window values + T taps in
+//   registers -> O*T FMAs), i.e. ~5 FMAs per shared-memory load, so the kernel is bound by the
+//   FP32 FMA pipe, not by shared memory or HBM (see DESIGN.md for the roofline).
+//
+// smot_emm_decode  (track_core.py:69-76,101-135,184-225).  The reference materialises seven
+//   bicubic x16 maps (55 MB at 30 tracks) and runs ~15 elementwise / reduction kernels over them.
+//   Here nothing is materialised: a CTA upsamples its slice separably (horizontal pass into shared
+//   memory, vertical pass in registers), evaluates the penalised score per pixel and keeps only the
+//   arg-max (packed 64-bit atomicMax: score bits << 32 | ~index, so ties resolve to the first index
+//   like torch.argmax).
+#include "common.cuh"
+
+namespace smot {
+
+// =============================================================================================
+// xcorr
+// =============================================================================================
+template <typename T, int S, int TT>
+__global__ void __launch_bounds__(256) xcorr_kernel(const T* __restrict__ x, const T* __restrict__ k, T* __restrict__ out,
+                                                    int C) {
+  constexpr int O = S - TT + 1;
+  constexpr int CG = 32;
+  extern __shared__ __align__(16) float xc_smem[];
+  float* xs = xc_smem;                // [S*S][CG]
+  float* ks = xc_smem + S * S * CG;   // [TT*TT][CG]
+  const int n = blockIdx.y;
+  const int c0 = blockIdx.x * CG;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const T* xb = x + (size_t)n * S * S * C + c0;
+  const T* kb = k + (size_t)n * TT * TT * C + c0;
+  // stage (4 channels per thread per position, coalesced runs of CG channels)
+  for (int i = threadIdx.x; i < S * S * (CG / 4); i += blockDim.x) {
+    const int pos = i / (CG / 4), q = (i % (CG / 4)) * 4;
+    float4 v = ld4(xb + (size_t)pos * C + q);
+    *reinterpret_cast<float4*>(xs + pos * CG + q) = v;
+  }
+  for (int i = threadIdx.x; i < TT * TT * (CG / 4); i += blockDim.x) {
+    const int pos = i / (CG / 4), q = (i % (CG / 4)) * 4;
+    float4 v = ld4(kb + (size_t)pos * C + q);
+    *reinterpret_cast<float4*>(ks + pos * CG + q) = v;
+  }
+  __syncthreads();
+  T* ob = out + (size_t)n * O * O * C + c0 + lane;
+  for (int i = warp; i < O; i += 8) {
+    float acc[O];
+#pragma unroll
+    for (int j = 0; j < O; ++j) acc[j] = 0.f;
+    for (int u = 0; u < TT; ++u) {
+      float xr[S], kr[TT];
+#pragma unroll
+      for (int j = 0; j < S; ++j) xr[j] = xs[((i + u) * S + j) * CG + lane];
+#pragma unroll
+      for (int v = 0; v < TT; ++v) kr[v] = ks[(u * TT + v) * CG + lane];
+#pragma unroll
+      for (int v = 0; v < TT; ++v)
+#pragma unroll
+        for (int j = 0; j < O; ++j) acc[j] = fmaf(xr[j + v], kr[v], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < O; ++j) ob[(size_t)(i * O + j) * C] = from_f<T>(acc[j]);
+  }
+}
+
+// generic fallback for unusual geometries: one thread per output element
+template <typename T>
+__global__ void xcorr_generic_kernel(const T* __restrict__ x, const T* __restrict__ k, T* __restrict__ out, int n, int C,
+                                     int S, int TT) {
+  const int O = S - TT + 1;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * O * O * C) return;
+  const int c = (int)(idx % C);
+  size_t r = idx / C;
+  const int j = (int)(r % O), i = (int)((r / O) % O), t = (int)(r / ((size_t)O * O));
+  const T* xb = x + (size_t)t * S * S * C + c;
+  const T* kb = k + (size_t)t * TT * TT * C + c;
+  float acc = 0.f;
+  for (int u = 0; u < TT; ++u)
+    for (int v = 0; v < TT; ++v) acc = fmaf(to_f(xb[(size_t)((i + u) * S + j + v) * C]), to_f(kb[(size_t)(u * TT + v) * C]), acc);
+  out[idx] = from_f<T>(acc);
+}
+
+template <typename T, int S, int TT>
+static int launch_xcorr(const void* x, const void* k, void* out, int n, int C, cudaStream_t st) {
+  const size_t smem = (size_t)(S * S + TT * TT) * 32 * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(xcorr_kernel<T, S, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("smot_xcorr: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return SMOT_ERR_CUDA;
+    }
+    attr = true;
+  }
+  xcorr_kernel<T, S, TT><<<dim3(C / 32, n), 256, smem, st>>>((const T*)x, (const T*)k, (T*)out, C);
+  SMOT_CHECK_LAUNCH("smot_xcorr");
+  return SMOT_OK;
+}
+
+// =============================================================================================
+// fused bicubic upsample + decode
+// =============================================================================================
+constexpr int EMM_CH = 7;
+
+struct CubicTap {
+  int idx[4];
+  float w[4];
+};
+
+// ATen upsample_bicubic2d (align_corners=False, A=-0.75): source index, taps clamped to the map
+__device__ __forceinline__ CubicTap cubic_taps(int dst, float scale, int in_size) {
+  const float A = -0.75f;
+  const float src = scale * ((float)dst + 0.5f) - 0.5f;
+  const float fl = floorf(src);
+  const float t = src - fl;
+  const int i0 = (int)fl;
+  CubicTap c;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) c.idx[j] = min(max(i0 - 1 + j, 0), in_size - 1);
+  const float x0 = t + 1.f, x3 = (1.f - t) + 1.f, x2 = 1.f - t;
+  c.w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  c.w[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+  c.w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  c.w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+  return c;
+}
+
+struct DecodeArgs {
+  const float* maps;
+  int map_ld, n, O, up, T;
+  const float* sr;
+  const float* tboxes;
+  const float* hann;  // [O*up]
+  float pad;
+  int use_centerness;
+  float sigma, one_minus_sigma;
+  int img_w, img_h, amodal;
+  int rows_per_cta;
+  unsigned long long* best;  // [n]
+  float* out_boxes;
+  float* out_conf;
+  int* out_valid;
+};
+
+__device__ __forceinline__ float hsum4(const float* v, const float* w) {
+  // ((w0*v0 + w1*v1) + w2*v2) + w3*v3, same association as ATen's interpolate loop
+  return ((w[0] * v[0] + w[1] * v[1]) + w[2] * v[2]) + w[3] * v[3];
+}
+
+struct PixelEval {
+  float score, p1, tlbr[4];
+};
+
+// everything after the upsampled channel values are known (decode_response, track_core.py:101-118)
+__device__ __forceinline__ PixelEval eval_pixel(const float* c, float box_w, float box_h, float win, int use_centerness,
+                                                float sigma, float one_minus_sigma) {
+  PixelEval e;
+  const float m = fmaxf(c[0], c[1]);
+  const float e0 = expf(c[0] - m), e1 = expf(c[1] - m);
+  e.p1 = __fdiv_rn(e1, e0 + e1);
+  float conf = e.p1;
+  if (use_centerness) conf = e.p1 * __fdiv_rn(1.f, 1.f + expf(-c[2]));
+  float sw = __fdiv_rn(c[5] + c[3], box_w), sh = __fdiv_rn(c[6] + c[4], box_h);
+  sw = fmaxf(sw, __fdiv_rn(1.f, sw));
+  sh = fmaxf(sh, __fdiv_rn(1.f, sh));
+  const float pen = expf((-sw * sh + 1.f) * 0.1f);
+  e.score = (conf * pen) * one_minus_sigma + sigma * win;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) e.tlbr[j] = c[3 + j];
+  return e;
+}
+
+__global__ void __launch_bounds__(256) emm_score_kernel(const DecodeArgs a) {
+  extern __shared__ __align__(16) float dec_smem[];
+  const int O = a.O, OW = a.O * a.up;
+  float* maps_s = dec_smem;                 // [O*O][EMM_CH]
+  float* tmp = dec_smem + O * O * EMM_CH;   // [EMM_CH][O][OW] horizontally upsampled
+  const int n = blockIdx.y;
+  const float* mp = a.maps + (size_t)n * O * O * a.map_ld;
+  for (int i = threadIdx.x; i < O * O * EMM_CH; i += blockDim.x) maps_s[i] = mp[(size_t)(i / EMM_CH) * a.map_ld + (i % EMM_CH)];
+  __syncthreads();
+  const float scale = 1.f / (float)a.up;
+  for (int x = threadIdx.x; x < OW; x += blockDim.x) {
+    const CubicTap tx = cubic_taps(x, scale, O);
+    for (int r = 0; r < O; ++r)
+#pragma unroll
+      for (int ch = 0; ch < EMM_CH; ++ch) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = maps_s[(r * O + tx.idx[j]) * EMM_CH + ch];
+        tmp[(ch * O + r) * OW + x] = hsum4(v, tx.w);
+      }
+  }
+  __syncthreads();
+  const float box_w = a.tboxes[n * 4 + 2] - a.tboxes[n * 4 + 0];
+  const float box_h = a.tboxes[n * 4 + 3] - a.tboxes[n * 4 + 1];
+  const int y0 = blockIdx.x * a.rows_per_cta, y1 = min(OW, y0 + a.rows_per_cta);
+  unsigned long long best = 0ull;
+  for (int x = threadIdx.x; x < OW; x += blockDim.x) {
+    const float wx = a.hann[x];
+    for (int y = y0; y < y1; ++y) {
+      const CubicTap ty = cubic_taps(y, scale, O);
+      float c[EMM_CH];
+#pragma unroll
+      for (int ch = 0; ch < EMM_CH; ++ch) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = tmp[(ch * O + ty.idx[j]) * OW + x];
+        c[ch] = hsum4(v, ty.w);
+      }
+      const PixelEval e = eval_pixel(c, box_w, box_h, a.hann[y] * wx, a.use_centerness, a.sigma, a.one_minus_sigma);
+      // scores are >= 0 here (conf, pen, window >= 0), so the raw float bits order like the floats
+      const unsigned idx = (unsigned)(y * OW + x);
+      const unsigned long long key = ((unsigned long long)__float_as_uint(fmaxf(e.score, 0.f)) << 32) |
+                                     (unsigned long long)(0xFFFFFFFFu - idx);
+      best = key > best ? key : best;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(&a.best[n], best);
+}
+
+__global__ void emm_finalize_kernel(const DecodeArgs a) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.n) return;
+  const int O = a.O, OW = a.O * a.up;
+  const unsigned idx = 0xFFFFFFFFu - (unsigned)(a.best[n] & 0xFFFFFFFFull);
+  const int y = (int)(idx / OW), x = (int)(idx % OW);
+  const float scale = 1.f / (float)a.up;
+  const CubicTap tx = cubic_taps(x, scale, O), ty = cubic_taps(y, scale, O);
+  const float* mp = a.maps + (size_t)n * O * O * a.map_ld;
+  float c[EMM_CH];
+  for (int ch = 0; ch < EMM_CH; ++ch) {
+    float rowv[4];
+    for (int i = 0; i < 4; ++i) {
+      float v[4];
+      for (int j = 0; j < 4; ++j) v[j] = mp[(size_t)(ty.idx[i] * O + tx.idx[j]) * a.map_ld + ch];
+      rowv[i] = hsum4(v, tx.w);
+    }
+    c[ch] = hsum4(rowv, ty.w);
+  }
+  const float* tb = a.tboxes + n * 4;
+  const PixelEval e = eval_pixel(c, tb[2] - tb[0], tb[3] - tb[1], a.hann[y] * a.hann[x], a.use_centerness, a.sigma,
+                                 a.one_minus_sigma);
+  // get_locations (track_core.py:184-225): SR box sampled on an (S*up)^2 grid, S = O + T - 1
+  const float* s = a.sr + n * 4;
+  const int s_full = (O + 2 * (a.T / 2)) * a.up;
+  const int border = (a.T / 2) * a.up;
+  const float stride_w = __fdiv_rn(s[2] - s[0], (float)(s_full - 1));
+  const float stride_h = __fdiv_rn(s[3] - s[1], (float)(s_full - 1));
+  const float cx = (s[0] + (float)(border + x) * stride_w) - a.pad;
+  const float cy = (s[1] + (float)(border + y) * stride_h) - a.pad;
+  float x1 = cx - e.tlbr[0], y1 = cy - e.tlbr[1], x2 = cx + e.tlbr[2], y2 = cy + e.tlbr[3];
+  int valid = 1;
+  if (!a.amodal) {
+    x1 = fminf(fmaxf(x1, 0.f), (float)a.img_w - 1.f), y1 = fminf(fmaxf(y1, 0.f), (float)a.img_h - 1.f);
+    x2 = fminf(fmaxf(x2, 0.f), (float)a.img_w - 1.f), y2 = fminf(fmaxf(y2, 0.f), (float)a.img_h - 1.f);
+    valid = (y2 > y1) && (x2 > x1);
+  }
+  reinterpret_cast<float4*>(a.out_boxes)[n] = make_float4(x1, y1, x2, y2);
+  a.out_conf[n] = e.p1;
+  a.out_valid[n] = valid;
+}
+
+}  // namespace smot
+
+using namespace smot;
+
+extern "C" int smot_xcorr(const void* x, const void* k, void* out, int n, int channels, int S, int T, int dtype,
+                          void* stream) {
+  SMOT_CHECK_ARG(n >= 0 && channels > 0 && T >= 1 && S >= T, "smot_xcorr: bad geometry n=%d C=%d S=%d T=%d", n, channels, S, T);
+  if (n == 0) return SMOT_OK;
+  SMOT_CHECK_ARG(x && k && out, "smot_xcorr: null argument");
+  SMOT_CHECK_ARG(dtype == SMOT_F32 || dtype == SMOT_F16, "smot_xcorr: bad dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fast = channels % 32 == 0 && (((uintptr_t)x | (uintptr_t)k) & 15) == 0;
+  if (fast && S == 30 && T == 15)
+    return dtype == SMOT_F32 ? launch_xcorr<float, 30, 15>(x, k, out, n, channels, st)
+                             : launch_xcorr<__half, 30, 15>(x, k, out, n, channels, st);
+  const int O = S - T + 1;
+  const size_t total = (size_t)n * O * O * channels;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (dtype == SMOT_F32)
+    xcorr_generic_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (const float*)k, (float*)out, n, channels, S, T);
+  else
+    xcorr_generic_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, (const __half*)k, (__half*)out, n, channels, S, T);
+  SMOT_CHECK_LAUNCH("smot_xcorr(generic)");
+  return SMOT_OK;
+}
+
+extern "C" int smot_emm_decode(const float* maps, int map_ld, int n, int O, int up, int T, const float* sr,
+                               const float* tboxes, const float* hann, float pad, int use_centerness, double sigma,
+                               int img_w, int img_h, int amodal, float* out_boxes, float* out_conf, int* out_valid,
+                               void* scratch, void* stream) {
+  SMOT_CHECK_ARG(n >= 0 && O >= 1 && up >= 1 && T >= 1 && map_ld >= EMM_CH, "smot_emm_decode: bad arguments");
+  if (n == 0) return SMOT_OK;
+  SMOT_CHECK_ARG(maps && sr && tboxes && hann && out_boxes && out_conf && out_valid && scratch, "smot_emm_decode: null argument");
+  const int OW = O * up;
+  const size_t smem = ((size_t)O * O * EMM_CH + (size_t)EMM_CH * O * OW) * sizeof(float);
+  SMOT_CHECK_ARG(smem <= 200 * 1024, "smot_emm_decode: response map %dx%d (x%d) does not fit shared memory", O, O, up);
+  cudaStream_t st = (cudaStream_t)stream;
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(emm_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("smot_emm_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return SMOT_ERR_CUDA;
+    }
+    attr_bytes = smem;
+  }
+  DecodeArgs a;
+  a.maps = maps, a.map_ld = map_ld, a.n = n, a.O = O, a.up = up, a.T = T, a.sr = sr, a.tboxes = tboxes, a.hann = hann;
+  a.pad = pad, a.use_centerness = use_centerness, a.sigma = (float)sigma, a.one_minus_sigma = (float)(1.0 - sigma), a.img_w = img_w, a.img_h = img_h, a.amodal = amodal;
+  a.rows_per_cta = 32;
+  a.best = (unsigned long long*)scratch;
+  a.out_boxes = out_boxes, a.out_conf = out_conf, a.out_valid = out_valid;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)n * 8, st);
+  if (e != cudaSuccess) {
+    set_error("smot_emm_decode: memset: %s", cudaGetErrorString(e));
+    return SMOT_ERR_CUDA;
+  }
+  emm_score_kernel<<<dim3((OW + a.rows_per_cta - 1) / a.rows_per_cta, n), 256, smem, st>>>(a);
+  SMOT_CHECK_LAUNCH("smot_emm_decode(score)");
+  emm_finalize_kernel<<<(n + 63) / 64, 64, 0, st>>>(a);
+  SMOT_CHECK_LAUNCH("smot_emm_decode(finalize)");
+  return SMOT_OK;
+}

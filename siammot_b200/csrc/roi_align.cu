@@ -1,0 +1,119 @@
+// Legacy (non-aligned) ROIAlign over an FPN pyramid, NHWC, one warp per output bin.
+//
+// Replaces three things of the reference at once:
+//   * maskrcnn_benchmark _C.roi_align_forward (upstream csrc/cuda/ROIAlign_cuda.cu: one thread per
+//     output element, 16 scalar loads each) -- here lanes own 4 channels each, so every corner read
+//     of a warp is one contiguous 16B/8B-per-lane vector load;
+//   * LevelMapper + the per-level nonzero/index_put loop of sr_pool.py:74-89 -- level chosen in-kernel;
+//   * TrackUtils.pad_feature (track_utils.py:87-107), 170 MB of zero-padded copies per frame at 720p --
+//     emulated: coordinates are evaluated in the padded frame exactly as the reference does, and
+//     corner reads that fall into the padding return 0.
+#include "common.cuh"
+
+namespace smot {
+
+struct RoiArgs {
+  smot_pyramid pyr;
+  const float* rois;
+  const float* level_boxes;
+  const int* count;
+  int max_rois, channels, res, sampling;
+};
+
+template <typename T>
+__global__ void roi_align_kernel(const RoiArgs a, T* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bins = a.res * a.res;
+  if (warp >= a.max_rois * bins) return;
+  const int r = warp / bins;
+  const int bin = warp - r * bins;
+  const int ph = bin / a.res, pw = bin - ph * a.res;
+  T* dst = out + (size_t)warp * a.channels;
+  const int n = a.count ? min(*a.count, a.max_rois) : a.max_rois;
+  if (r >= n) {
+    for (int c = lane * 4; c < a.channels; c += 128) st4(dst + c, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
+  // ---- level (LevelMapper: floor(4 + log2(sqrt(area)/224 + 1e-6)), clamp, - k_min)
+  const float* lb = (a.level_boxes ? a.level_boxes : a.rois) + 4 * r;
+  const float area = (lb[2] - lb[0] + 1.f) * (lb[3] - lb[1] + 1.f);
+  float lv = floorf(4.f + log2f(__fdiv_rn(__fsqrt_rn(area), 224.f) + 1e-6f));
+  const float kmin = (float)a.pyr.k_min, kmax = (float)(a.pyr.k_min + a.pyr.num_levels - 1);
+  lv = fminf(fmaxf(lv, kmin), kmax);
+  const int l = (int)lv - a.pyr.k_min;
+
+  const T* __restrict__ feat = reinterpret_cast<const T*>(a.pyr.feat[l]);
+  const int H = a.pyr.H[l], W = a.pyr.W[l], ld = a.pyr.ld[l], pad = a.pyr.pad[l];
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;  // size of the (virtual) padded map
+  const float sc = a.pyr.scale[l];
+  const float* roi = a.rois + 4 * r;
+  const float x1 = roi[0] * sc, y1 = roi[1] * sc, x2 = roi[2] * sc, y2 = roi[3] * sc;
+  const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
+  const float bin_h = __fdiv_rn(rh, (float)a.res), bin_w = __fdiv_rn(rw, (float)a.res);
+  const int gh = a.sampling > 0 ? a.sampling : (int)ceilf(__fdiv_rn(rh, (float)a.res));
+  const int gw = a.sampling > 0 ? a.sampling : (int)ceilf(__fdiv_rn(rw, (float)a.res));
+  const float cnt = (float)(gh * gw);
+
+  for (int c = lane * 4; c < a.channels; c += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int iy = 0; iy < gh; ++iy) {
+      float y = y1 + (float)ph * bin_h + __fdiv_rn(((float)iy + .5f) * bin_h, (float)gh);
+      for (int ix = 0; ix < gw; ++ix) {
+        float x = x1 + (float)pw * bin_w + __fdiv_rn(((float)ix + .5f) * bin_w, (float)gw);
+        if (y < -1.f || y > (float)Hp || x < -1.f || x > (float)Wp) continue;
+        float yy = y <= 0.f ? 0.f : y, xx = x <= 0.f ? 0.f : x;
+        int yl = (int)yy, xl = (int)xx, yh, xh;
+        if (yl >= Hp - 1) { yh = yl = Hp - 1; yy = (float)yl; } else yh = yl + 1;
+        if (xl >= Wp - 1) { xh = xl = Wp - 1; xx = (float)xl; } else xh = xl + 1;
+        const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+        // to the real (unpadded) map; reads inside the padding are zeros
+        const int ryl = yl - pad, ryh = yh - pad, rxl = xl - pad, rxh = xh - pad;
+        const bool oyl = ryl >= 0 && ryl < H, oyh = ryh >= 0 && ryh < H;
+        const bool oxl = rxl >= 0 && rxl < W, oxh = rxh >= 0 && rxh < W;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v1 = (oyl && oxl) ? ld4(feat + ((size_t)ryl * W + rxl) * ld + c) : z;
+        float4 v2 = (oyl && oxh) ? ld4(feat + ((size_t)ryl * W + rxh) * ld + c) : z;
+        float4 v3 = (oyh && oxl) ? ld4(feat + ((size_t)ryh * W + rxl) * ld + c) : z;
+        float4 v4 = (oyh && oxh) ? ld4(feat + ((size_t)ryh * W + rxh) * ld + c) : z;
+        acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+        acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+        acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+        acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+      }
+    }
+    acc.x = __fdiv_rn(acc.x, cnt), acc.y = __fdiv_rn(acc.y, cnt), acc.z = __fdiv_rn(acc.z, cnt), acc.w = __fdiv_rn(acc.w, cnt);
+    st4(dst + c, acc);
+  }
+}
+
+}  // namespace smot
+
+using namespace smot;
+
+extern "C" int smot_roi_align(const smot_pyramid* pyr, const float* rois, const float* level_boxes, const int* count,
+                              int max_rois, int channels, int res, int sampling_ratio, void* out, int dtype,
+                              void* stream) {
+  SMOT_CHECK_ARG(pyr && out && (rois || max_rois == 0), "smot_roi_align: null argument");
+  SMOT_CHECK_ARG(pyr->num_levels >= 1 && pyr->num_levels <= SMOT_MAX_LEVELS, "smot_roi_align: num_levels %d", pyr->num_levels);
+  SMOT_CHECK_ARG(channels > 0 && channels % 4 == 0 && res > 0 && max_rois >= 0, "smot_roi_align: channels must be a multiple of 4");
+  for (int l = 0; l < pyr->num_levels; ++l)
+    SMOT_CHECK_ARG(pyr->feat[l] && pyr->ld[l] % 4 == 0 && pyr->H[l] > 0 && pyr->W[l] > 0 && pyr->pad[l] >= 0,
+                   "smot_roi_align: bad level %d", l);
+  if (max_rois == 0) return SMOT_OK;
+  RoiArgs a;
+  a.pyr = *pyr, a.rois = rois, a.level_boxes = level_boxes, a.count = count;
+  a.max_rois = max_rois, a.channels = channels, a.res = res, a.sampling = sampling_ratio;
+  const long long warps = (long long)max_rois * res * res;
+  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMOT_F32)
+    roi_align_kernel<float><<<blocks, 256, 0, st>>>(a, (float*)out);
+  else if (dtype == SMOT_F16)
+    roi_align_kernel<__half><<<blocks, 256, 0, st>>>(a, (__half*)out);
+  else
+    SMOT_CHECK_ARG(false, "smot_roi_align: bad dtype %d", dtype);
+  SMOT_CHECK_LAUNCH("smot_roi_align");
+  return SMOT_OK;
+}
