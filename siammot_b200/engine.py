@@ -136,7 +136,26 @@ class Engine(object):
         self.hann = torch.hann_window(self.o_res * self.up, dtype=torch.float).to(self.device)
         self.pads = [int(T.PAD_PIXELS / ((2 ** i) * 4)) for i in range(len(T.POOLER_SCALES))]
         self._nms_ws = {}
-        self.profile = None  # optional dict name -> list of (start_event, end_event)
+        self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
+
+    def timed(self, name):
+        """Context manager: when self.timers is a dict, brackets the enclosed launches with CUDA events on
+        the launching stream (bench.py's live per-kernel timing)."""
+        eng = self
+
+        class _T(object):
+            def __enter__(self_inner):
+                if eng.timers is not None:
+                    self_inner.e0 = torch.cuda.Event(enable_timing=True)
+                    self_inner.e1 = torch.cuda.Event(enable_timing=True)
+                    self_inner.e0.record()
+
+            def __exit__(self_inner, *exc):
+                if eng.timers is not None:
+                    self_inner.e1.record()
+                    eng.timers.setdefault(name, []).append((self_inner.e0, self_inner.e1))
+                return False
+        return _T()
 
     # ------------------------------------------------------------------------------------------
     # weights
@@ -383,7 +402,8 @@ class Engine(object):
             image = image[0]
         P = self.plan(image.shape[1], image.shape[2])
         P.img_in.copy_(image, non_blocking=True)
-        P.run()
+        with self.timed("static"):
+            P.run()
         return P
 
     def box_head_eager(self, P, rois, track_labels=None):
@@ -404,9 +424,11 @@ class Engine(object):
         cfg = self.cfg
         T = cfg.MODEL.TRACK_HEAD
         n = mem_boxes.shape[0]
-        srf = ops.roi_align(P.feats, mem_sr, T.POOLER_SCALES, self.s_res, T.POOLER_SAMPLING_RATIO,
-                            level_boxes=mem_boxes, pads=self.pads)
-        resp = ops.xcorr(srf, mem_feat)
+        with self.timed("sr_roi_align"):
+            srf = ops.roi_align(P.feats, mem_sr, T.POOLER_SCALES, self.s_res, T.POOLER_SAMPLING_RATIO,
+                                level_boxes=mem_boxes, pads=self.pads)
+        with self.timed("xcorr"):
+            resp = ops.xcorr(srf, mem_feat)
         O, Cc = self.o_res, self.C
         w, _, _ = self.weights["emm.towers"]
         tower = ops.conv2d(resp, w, pad=1)

@@ -1,0 +1,98 @@
+"""CPU-only checks of the host side: C-ABI library loads and exports every symbol smot.h declares,
+config surface, BoxList semantics, track pool state machine (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    path = __graft_entry__.build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(REPO, "include", "smot.h")).read()
+    names = set(re.findall(r"\b(smot_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 15
+    for n in sorted(names):
+        assert hasattr(lib, n), "libsmot.so does not export %s" % n
+    from siammot_b200 import _lib
+    assert _lib.lib().smot_abi_version() == _lib.ABI_VERSION
+
+
+def test_argument_errors_are_reported_not_crashed():
+    from siammot_b200 import _lib
+    l = _lib.lib()
+    d = _lib.ConvDesc()
+    assert l.smot_conv2d(ctypes.byref(d), None) == 1  # SMOT_ERR_INVALID: null tensors
+    assert b"null" in l.smot_last_error()
+    assert l.smot_sort_nms(None, 4, None, 1, None, 5000, 0.0, 0.5, 10, 0, None, None, None, None, None, None, 0, None) == 1
+
+
+def test_product_does_not_import_the_oracle():
+    for root, _, files in os.walk(os.path.join(REPO, "siammot_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_config_loads_reference_style_yaml_and_overrides():
+    from siammot_b200.config import get_cfg
+    cfg = get_cfg()
+    assert cfg.MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES == 1 and cfg.MODEL.RPN.POST_NMS_TOP_N_TEST == 300
+    cfg.merge_from_file(os.path.join(REPO, "siammot_b200", "configs", "dla34_emm_mot17.yaml"))
+    assert cfg.INPUT.AMODAL is True and cfg.MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES == 30
+    cfg.merge_from_list(["MODEL.TRACK_HEAD.TRACK_THRESH", 0.5, "SOLVER.STEPS", "(1, 2)"])
+    assert cfg.MODEL.TRACK_HEAD.TRACK_THRESH == 0.5 and cfg.SOLVER.STEPS == (1, 2)
+    c2 = cfg.clone()
+    c2.MODEL.TRACK_HEAD.TRACK_THRESH = 0.1
+    assert cfg.MODEL.TRACK_HEAD.TRACK_THRESH == 0.5
+    cfg.freeze()
+    with pytest.raises(AttributeError):
+        cfg.DTYPE = "float16"
+
+
+def test_boxlist_legacy_semantics():
+    from siammot_b200.structures import BoxList, cat_boxlist, remove_small_boxes
+    b = BoxList(torch.tensor([[10., 20., 29., 59.], [-5., -5., 700., 800.], [3., 3., 3., 3.]]), (640, 480))
+    assert b.area().tolist() == [20 * 40, 706 * 806, 1]
+    x = b.convert("xywh")
+    assert x.bbox[0].tolist() == [10., 20., 20., 40.] and torch.equal(x.convert("xyxy").bbox, b.bbox)
+    c = BoxList(b.bbox.clone(), (640, 480)).clip_to_image(remove_empty=True)
+    assert c.bbox.tolist() == [[10., 20., 29., 59.], [0., 0., 639., 479.]]
+    b.add_field("scores", torch.tensor([0.1, 0.2, 0.3]))
+    r = b.resize((1280, 960))
+    assert r.bbox[0].tolist() == [20., 40., 58., 118.] and r.size == (1280, 960)
+    assert len(cat_boxlist([b, b])) == 6 and len(remove_small_boxes(b, 2)) == 2
+    assert len(b[torch.tensor([True, False, True])]) == 2
+
+
+def test_track_pool_state_machine():
+    from siammot_b200.modelling.track_utils import TrackPool, TrackUtils
+    p = TrackPool(max_dormant_frames=2)
+    a, b, c = p.start_track(), p.start_track(), p.start_track()
+    assert (a, b, c) == (0, 1, 2) and p.get_active_ids() == {0, 1, 2}
+    p.increment_frame()
+    p.suspend_track(1)
+    assert p.get_dormant_ids() == {1} and p._dormant_ids[1] == 0
+    with pytest.raises(ValueError):
+        p.suspend_track(1)
+    p.expire_tracks()          # frame 1 - last 0 = 1 < 2: stays
+    assert p.get_dormant_ids() == {1}
+    p.increment_frame()
+    p.expire_tracks()          # 2 - 0 >= 2: expires
+    assert p.get_dormant_ids() == set()
+    with pytest.raises(ValueError):
+        p.resume_track(1)
+    p.suspend_track(2)
+    p.resume_track(2)
+    assert p.get_active_ids() == {0, 2} and p.start_track() == 3
+    p.reset()
+    assert p.start_track() == 0
+    tu = TrackUtils(search_expansion=1.0, min_search_wh=0, pad_pixels=512)
+    sr = tu.search_region(torch.tensor([[100., 100., 159., 249.]]))
+    assert sr.tolist() == [[582., 537., 701., 836.]]
