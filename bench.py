@@ -154,7 +154,6 @@ def kernels_per_frame(h):
     """Kernels of libsmot.so launched per step: static plan (graph replay) + dynamic stage at N=30."""
     from siammot_b200 import _lib
     P = h.eng.plan(H_NET, W_NET)
-    names = {_lib.lib().smot_conv2d: "smot_conv2d"}
     n = 0
     for fn, args, tag in P.steps:
         name = getattr(fn, "__name__", None)

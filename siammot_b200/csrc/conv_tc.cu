@@ -1,11 +1,371 @@
-// tcgen05 / TMA implicit-GEMM convolution (fp16 in, fp32 accumulate in TMEM).  Placeholder until the
-// kernel lands: reports "unsupported" so SMOT_CONV_AUTO uses the SIMT member of the family.
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (fp16 operands, fp32 accumulation in TMEM).
+//
+// GEMM view as in conv_simt.cu: M = output pixels, N = Cout, K = taps * Cin.  One CTA produces a
+// 128 (pixels) x BN (channels) output tile; the 128 pixels are a TILE_W x TILE_H patch of one image
+// (16x8 for feature maps, 128x1 for matrices), so that for filter tap (r,s) the A operand of the
+// tile is ONE 4-D TMA box of the NHWC input at offset (s-pad, r-pad): im2col is never built, and
+// the zero padding of the convolution is TMA's out-of-bounds fill.  K advances over
+// taps x (Cin/64): each step stages a 128x64 A box and a BNx64 weight box (both 128B-swizzled,
+// K-major) in a shared-memory ring fed by one TMA-producer thread; one MMA thread issues
+// 4 x tcgen05.mma (M=128, N=BN, K=16) per step into a TMEM accumulator and releases the ring slot
+// with tcgen05.commit; four epilogue warps read the accumulator with tcgen05.ld, apply
+// scale/bias (+residual) (+ReLU) and store fp16 NHWC with an arbitrary channel pitch (so DLA roots
+// still read their children without a concat).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace smot {
-bool conv2d_tc_supported(const smot_conv_desc*) { return false; }
-int conv2d_tc(const smot_conv_desc*, cudaStream_t) {
-  set_error("smot_conv2d: tcgen05 path not available");
-  return SMOT_ERR_UNSUPPORTED;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;  // fp16 elements = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 192;
+
+struct TcArgs {
+  const float* scale;
+  const float* bias;
+  const __half* res;
+  __half* out;
+  int H, W;          // output (= input, stride 1) spatial size
+  int Cin, Cout, out_ld, res_ld, relu;
+  int taps, KW, pad, cin_chunks;
+  int tiles_w, tiles_h, tile_w, tile_h;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a mis-programmed pipeline must fail the launch, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1u << 26)) {
+      printf("smot conv_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// SM100 shared-memory matrix descriptor: K-major, 128B swizzle, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);  // start address
+  d |= (uint64_t)0 << 16;                            // leading byte offset (unused: one atom along K)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
+  d |= (uint64_t)1 << 46;                            // descriptor version (SM100)
+  d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  // the registers are only valid after wait::ld: tie them to the wait so nothing is scheduled across it
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  using S = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t tc_smem_raw[];
+  // 128B-swizzled tiles need 1024B-aligned bases
+  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * S::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw = t % a.tiles_w;
+  t /= a.tiles_w;
+  const int th = t % a.tiles_h;
+  const int img = t / a.tiles_h;
+  const int w0 = tw * a.tile_w, h0 = th * a.tile_h;
+  const int n0 = blockIdx.y * BN;
+  const int total = a.taps * a.cin_chunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation (whole warp), BN fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int it = 0; it < total; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], (uint32_t)S::STAGE_BYTES);
+        const int tap = it / a.cin_chunks, cc = it - tap * a.cin_chunks;
+        const int r = tap / a.KW, sx = tap - r * a.KW;
+        tma_load_4d(sA + s * S::A_BYTES, &tmA, &full[s], cc * TC_BK, w0 + sx - a.pad, h0 + r - a.pad, img);
+        tma_load_2d(sB + s * S::B_BYTES, &tmB, &full[s], tap * a.Cin + cc * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_f16(TC_BM, BN);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint64_t ad = umma_desc_sw128(sA + s * S::A_BYTES);
+        const uint64_t bd = umma_desc_sw128(sB + s * S::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)  // +32 bytes (2 x 16B units) per K=16 step inside the swizzle atom
+          umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)((it | k) != 0));
+        umma_commit(&empty[s]);  // slot reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+  } else {  // ===== epilogue warps 2..5 =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int oh = h0 + row / a.tile_w, ow = w0 + row % a.tile_w;
+    const bool valid = oh < a.H && ow < a.W;
+    const size_t pix = ((size_t)img * a.H + oh) * a.W + ow;
+    mbar_wait(tmem_full, 0u);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (valid) {
+        const int n = n0 + c0;
+        if (a.scale) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(v[j], __ldg(a.scale + n + j));
+        }
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(v[j], __ldg(a.bias + n + j));
+        }
+        if (a.res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + n);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 rv = __ldg(rp + g);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __half22float2(h2[e]);
+              v[g * 8 + 2 * e] += f.x;
+              v[g * 8 + 2 * e + 1] += f.y;
+            }
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.out_ld + n);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 ov;
+          __half2* h2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+          op[g] = ov;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled get_encode() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+static bool encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("smot_conv2d(tcgen05): cuTensorMapEncodeTiled entry point not available");
+    return false;
+  }
+  uint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("smot_conv2d(tcgen05): cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return false;
+  }
+  return true;
+}
+
+bool conv2d_tc_supported(const smot_conv_desc* d) {
+  if (d->in_dtype != SMOT_F16 || d->out_dtype != SMOT_F16) return false;
+  if (d->stride != 1 || d->KH != d->KW || (d->KH != 1 && d->KH != 3) || d->pad != d->KH / 2) return false;
+  if (d->Cin % TC_BK != 0 || d->Cout % 64 != 0) return false;
+  if (d->in_ld % 8 != 0 || d->out_ld % 8 != 0 || (d->residual && d->res_ld % 8 != 0)) return false;
+  if (((uintptr_t)d->in | (uintptr_t)d->weight | (uintptr_t)d->out | (uintptr_t)d->residual) & 15) return false;
+  if (d->batch < 1 || d->OH != d->H || d->OW != d->W) return false;
+  if ((long long)d->batch * d->H * d->W < 64) return false;  // not worth a 128-row tile
+  return true;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, dim3 grid, cudaStream_t st) {
+  using S = TcSmem<BN, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("smot_conv2d(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return SMOT_ERR_CUDA;
+    }
+    attr = true;
+  }
+  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(tmA, tmB, a);
+  SMOT_CHECK_LAUNCH("smot_conv2d(tcgen05)");
+  return SMOT_OK;
+}
+
+int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
+  TcArgs a;
+  a.scale = d->scale, a.bias = d->bias, a.res = (const __half*)d->residual, a.out = (__half*)d->out;
+  a.H = d->H, a.W = d->W, a.Cin = d->Cin, a.Cout = d->Cout, a.out_ld = d->out_ld, a.res_ld = d->res_ld, a.relu = d->relu;
+  a.taps = d->KH * d->KW, a.KW = d->KW, a.pad = d->pad, a.cin_chunks = d->Cin / TC_BK;
+  if (d->H == 1) {
+    a.tile_w = 128, a.tile_h = 1;
+  } else {
+    a.tile_w = 16, a.tile_h = 8;
+  }
+  a.tiles_w = ceil_div(d->W, a.tile_w), a.tiles_h = ceil_div(d->H, a.tile_h);
+  const long long tiles = (long long)a.tiles_w * a.tiles_h * d->batch;
+  // BN: 128 unless that leaves most SMs idle
+  const int BN = (d->Cout % 128 == 0 && tiles * (d->Cout / 128) >= 148) ? 128 : 64;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
+    uint64_t str[3] = {(uint64_t)d->in_ld * 2, (uint64_t)d->W * d->in_ld * 2, (uint64_t)d->H * d->W * d->in_ld * 2};
+    uint32_t box[4] = {(uint32_t)TC_BK, (uint32_t)a.tile_w, (uint32_t)a.tile_h, 1u};
+    if (!encode_map(&tmA, d->in, 4, dims, str, box)) return SMOT_ERR_CUDA;
+  }
+  {
+    const uint64_t K = (uint64_t)a.taps * d->Cin;
+    uint64_t dims[2] = {K, (uint64_t)d->Cout};
+    uint64_t str[1] = {K * 2};
+    uint32_t box[2] = {(uint32_t)TC_BK, (uint32_t)BN};
+    if (!encode_map(&tmB, d->weight, 2, dims, str, box)) return SMOT_ERR_CUDA;
+  }
+  dim3 grid((unsigned)tiles, (unsigned)(d->Cout / BN));
+  if (BN == 128) return launch_tc<128, 3>(tmA, tmB, a, grid, st);
+  return launch_tc<64, 4>(tmA, tmB, a, grid, st);
+}
+
 }  // namespace smot

@@ -321,3 +321,75 @@ def test_emm_decode_matches_oracle(amodal):
     assert valid.cpu().bool().tolist() == ref_valid.tolist()
     assert (conf.cpu() - ref_conf).abs().max() <= 1e-5
     assert (bb.cpu() - ref_bb).abs().max() <= 1e-3
+
+
+TC_CASES = [
+    # B, Cin, H, W, Cout, k, residual, relu, scale
+    (1, 64, 176, 320, 64, 3, True, True, True),     # level2 block conv: 440 tiles x BN 64
+    (1, 128, 88, 160, 128, 3, True, True, True),    # level3: BN 128 path? (110 tiles x 1 -> BN 64)
+    (1, 256, 44, 80, 256, 3, False, True, True),    # level4, ragged tile rows (44 = 5.5 x 8)
+    (1, 512, 22, 40, 512, 3, True, True, True),     # level5, ragged both ways, K = 4608
+    (1, 448, 88, 160, 128, 1, False, True, True),   # root over a 448-channel concat buffer
+    (1, 128, 11, 20, 128, 3, False, False, False),  # P6-sized map, bias only
+    (30, 128, 16, 16, 256, 3, False, False, False),  # EMM towers at 30 tracks
+    (1, 128, 176, 320, 128, 3, False, True, False),  # RPN conv on P2: BN 128
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv2d_tcgen05_matches_oracle_and_simt(case):
+    """The tcgen05/TMA member of the conv family against torch fp32 on the fp16-rounded operands and
+    against the SIMT member (same operands, fp32 accumulation in both)."""
+    from siammot_b200 import _lib
+    B, Cin, H, W, Cout, k, use_res, relu, use_scale = case
+    g = torch.Generator().manual_seed(Cin + H)
+    dt = torch.float16
+    x = q(torch.randn(B, Cin, H, W, generator=g), dt)
+    w = q(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k), dt)
+    scale = (0.5 + torch.rand(Cout, generator=g)) if use_scale else None
+    bias = torch.randn(Cout, generator=g)
+    res = q(torch.randn(B, Cout, H, W, generator=g), dt) if use_res else None
+    ref = F.conv2d(x, w, None, 1, k // 2)
+    if scale is not None:
+        ref = ref * scale.view(1, -1, 1, 1)
+    ref = ref + bias.view(1, -1, 1, 1)
+    if res is not None:
+        ref = ref + res
+    if relu:
+        ref = F.relu(ref)
+    dx, dw = nhwc(x, dt), ohwi(w, dt)
+    ds, db = (scale.to(DEV) if scale is not None else None), bias.to(DEV)
+    dr = nhwc(res, dt) if res is not None else None
+    out = torch.empty((B, H, W, Cout), dtype=dt, device=DEV)
+    assert ops().conv2d_algo(dx, dw, out, scale=ds, bias=db, residual=dr, pad=k // 2, relu=relu) == _lib.CONV_TCGEN05
+    got_tc = ops().conv2d(dx, dw, ds, db, dr, 1, k // 2, relu, algo=_lib.CONV_TCGEN05)
+    got_simt = ops().conv2d(dx, dw, ds, db, dr, 1, k // 2, relu, algo=_lib.CONV_SIMT)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(got_tc), ref) <= 2e-3
+    assert rel_err(nchw(got_tc), nchw(got_simt)) <= 1e-3
+
+
+def test_conv2d_tcgen05_channel_slices_and_fc():
+    from siammot_b200 import _lib
+    g = torch.Generator().manual_seed(77)
+    dt = torch.float16
+    H, W = 24, 40
+    buf = (torch.randn(1, H, W, 320, generator=g)).to(DEV, dt)
+    w3 = q(torch.randn(64, 128, 3, 3, generator=g) / 34.0, dt)
+    outbuf = torch.zeros(1, H, W, 192, dtype=dt, device=DEV)
+    x_view, o_view = buf[..., 64:192], outbuf[..., 128:192]
+    res_view = buf[..., 256:320]
+    ref = F.relu(F.conv2d(nchw(x_view), w3, None, 1, 1) + nchw(res_view))
+    assert ops().conv2d_algo(x_view, ohwi(w3, dt), o_view, residual=res_view, pad=1, relu=True) == _lib.CONV_TCGEN05
+    ops().conv2d(x_view, ohwi(w3, dt), residual=res_view, pad=1, relu=True, out=o_view)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(o_view), ref) <= 2e-3
+    assert float(outbuf[..., :128].abs().max()) == 0.0
+    for rows in (300, 30, 128):
+        xfc = q(torch.randn(rows, 6272, generator=g), dt)
+        wfc = q(torch.randn(1024, 6272, generator=g) / math.sqrt(6272), dt)
+        bfc = torch.randn(1024, generator=g)
+        reffc = F.relu(F.linear(xfc, wfc, bfc))
+        gotfc = ops().conv2d(xfc.to(DEV, dt).view(1, 1, rows, 6272), wfc.to(DEV, dt).view(1024, 1, 1, 6272), None,
+                             bfc.to(DEV), relu=True, algo=_lib.CONV_TCGEN05)
+        assert rel_err(gotfc.view(rows, 1024).float().cpu(), reffc) <= 2e-3
