@@ -313,7 +313,7 @@ bool conv2d_tc_supported(const smot_conv_desc* d) {
   if (d->in_ld % 8 != 0 || d->out_ld % 8 != 0 || (d->residual && d->res_ld % 8 != 0)) return false;
   if (((uintptr_t)d->in | (uintptr_t)d->weight | (uintptr_t)d->out | (uintptr_t)d->residual) & 15) return false;
   if (d->batch < 1 || d->OH != d->H || d->OW != d->W) return false;
-  if ((long long)d->batch * d->H * d->W < 64) return false;  // not worth a 128-row tile
+  if ((long long)d->batch * d->H * d->W < 16) return false;  // not worth a 128-row tile
   return true;
 }
 
