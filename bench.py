@@ -134,7 +134,8 @@ class Harness(object):
         P = self.eng.run_static(frame_dev)
         self.pool.reset()
         ids = torch.tensor([self.pool.start_track() for _ in range(N_TRACKS)])
-        self.mem = self.model.roi_heads._build_memory(P, self.boxes, ids, torch.ones(N_TRACKS, dtype=torch.int64))
+        self.mem = self.model.roi_heads._build_memory(P, self.boxes.numpy(), ids.numpy(),
+                                                      torch.ones(N_TRACKS, dtype=torch.int64).numpy())
         self.pool.increment_frame()
         self.snapshot = (set(self.pool._active_ids), dict(self.pool._dormant_ids), dict(self.pool._cache),
                          self.pool._max_id, self.pool._frame_idx)

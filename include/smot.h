@@ -149,6 +149,15 @@ int smot_box_decode(const float* head, int head_ld, const float* rois, const int
                     const float* weights4, int img_w, int img_h, int amodal, const int* track_labels,
                     float* out_boxes, float* out_scores, void* stream);
 
+/* ---- solver candidates: detections ++ refined tracks ---------------------------------------------
+ * cat[0..ncap) = detections (as is); cat[ncap + r] = track r with its label's refined box and score
+ *   s = (p_det + 1 + p_trk + 1) / 2   (roi_heads.py:67,76; = p_det + 1 when tracktor)  + active[r]
+ *   (track_solver.py:69), or -1 when valid[r] == 0.  *zero_count (optional) is reset to 0. */
+int smot_track_combine(const float* det_boxes, const float* det_scores, int ncap, const float* dec_boxes,
+                       const float* dec_scores, int ncls, const int* labels, const float* conf, const int* valid,
+                       const float* active, int n, int tracktor, float* cat_boxes, float* cat_scores, int* zero_count,
+                       void* stream);
+
 /* ---- EMM tracker ---------------------------------------------------------------------------------
  * smot_xcorr: depthwise valid cross-correlation (xcorr.py:37-45), NHWC:
  *   out[n][i][j][c] = sum_{u,v<T} x[n][i+u][j+v][c] * k[n][u][v][c],  x: SxS, k: TxT, out: (S-T+1)^2. */

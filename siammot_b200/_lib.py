@@ -39,7 +39,7 @@ _lib = None
 # kernels launched by one call of each entry point (memsets not counted); used for bench.py's gpu_launches
 KERNELS_PER_CALL = {"smot_conv2d": 1, "smot_image_to_nhwc": 1, "smot_maxpool2x2": 1, "smot_upsample_add": 1,
                     "smot_subsample2": 1, "smot_groupnorm_relu": 1, "smot_roi_align": 1, "smot_rpn_select": 3,
-                    "smot_sort_nms": 1, "smot_box_decode": 1, "smot_xcorr": 1, "smot_emm_decode": 2}
+                    "smot_sort_nms": 1, "smot_box_decode": 1, "smot_track_combine": 1, "smot_xcorr": 1, "smot_emm_decode": 2}
 
 
 def _declare(lib):
@@ -58,6 +58,7 @@ def _declare(lib):
         "smot_rpn_select": [C.POINTER(RpnLevel), i, i, i, f, f, i, i, i, i, vp, vp, vp, vp, sz, vp],
         "smot_sort_nms": [vp, i, vp, i, vp, i, f, f, i, i, vp, vp, vp, vp, vp, vp, sz, vp],
         "smot_box_decode": [vp, i, vp, vp, i, i, C.POINTER(C.c_float * 4), i, i, i, vp, vp, vp, vp],
+        "smot_track_combine": [vp, vp, i, vp, vp, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp],
         "smot_xcorr": [vp, vp, vp, i, i, i, i, i, vp],
         "smot_emm_decode": [vp, i, i, i, i, i, vp, vp, vp, f, i, d, i, i, i, vp, vp, vp, vp, vp],
     }

@@ -378,9 +378,50 @@ __global__ void box_decode_kernel(const float* __restrict__ head, int head_ld, c
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// candidate assembly for the solver: detections ++ refined tracks (roi_heads.py:60-84,44; track_solver.py:69)
+// ---------------------------------------------------------------------------------------------
+__global__ void track_combine_kernel(const float* __restrict__ det_boxes, const float* __restrict__ det_scores, int ncap,
+                                     const float* __restrict__ dec_boxes, const float* __restrict__ dec_scores, int ncls,
+                                     const int* __restrict__ labels, const float* __restrict__ conf,
+                                     const int* __restrict__ valid, const float* __restrict__ active, int n, int tracktor,
+                                     float* __restrict__ cat_boxes, float* __restrict__ cat_scores, int* zero_me) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && zero_me) *zero_me = 0;
+  if (i < ncap) {
+    reinterpret_cast<float4*>(cat_boxes)[i] = reinterpret_cast<const float4*>(det_boxes)[i];
+    cat_scores[i] = det_scores[i];
+  } else if (i < ncap + n) {
+    const int r = i - ncap;
+    const int lab = labels[r];
+    const float det_part = dec_scores[(size_t)r * ncls + lab];  // p + 1 (inference.py:103)
+    float s = det_part;
+    if (!tracktor) s = __fdiv_rn(det_part + (conf[r] + 1.f), 2.f);  // roi_heads.py:67,76
+    s = s + active[r];                                              // track_solver.py:69 (active rows +1)
+    reinterpret_cast<float4*>(cat_boxes)[i] = reinterpret_cast<const float4*>(dec_boxes)[(size_t)r * ncls + lab];
+    cat_scores[i] = valid[r] ? s : -1.f;
+  }
+}
+
 }  // namespace smot
 
 using namespace smot;
+
+extern "C" int smot_track_combine(const float* det_boxes, const float* det_scores, int ncap, const float* dec_boxes,
+                                  const float* dec_scores, int ncls, const int* labels, const float* conf, const int* valid,
+                                  const float* active, int n, int tracktor, float* cat_boxes, float* cat_scores,
+                                  int* zero_count, void* stream) {
+  SMOT_CHECK_ARG(ncap >= 0 && n >= 0 && cat_boxes && cat_scores, "smot_track_combine: bad arguments");
+  SMOT_CHECK_ARG(ncap == 0 || (det_boxes && det_scores), "smot_track_combine: null detections");
+  SMOT_CHECK_ARG(n == 0 || (dec_boxes && dec_scores && labels && conf && valid && active && ncls >= 2),
+                 "smot_track_combine: null track arrays");
+  const int total = ncap + n;
+  track_combine_kernel<<<(total + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      det_boxes, det_scores, ncap, dec_boxes, dec_scores, ncls, labels, conf, valid, active, n, tracktor, cat_boxes,
+      cat_scores, zero_count);
+  SMOT_CHECK_LAUNCH("smot_track_combine");
+  return SMOT_OK;
+}
 
 extern "C" size_t smot_sort_nms_workspace(int n_max) {
   if (n_max <= 0) return 0;

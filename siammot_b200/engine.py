@@ -106,6 +106,160 @@ class _Plan(object):
             self.run_eager()
 
 
+class _TrackArena(object):
+    """Buffers shared by every per-n launch plan of one static plan (only one plan runs at a time):
+    device work buffers for up to ``cap`` tracks and two pinned host blocks.  Plans are views."""
+
+    def __init__(self, eng, P, ncap, cap):
+        dev, dt, f32 = eng.device, eng.dtype, torch.float32
+        Cc, S, O = eng.C, eng.s_res, eng.o_res
+        self.cap, self.ncap = cap, ncap
+        tmax = ncap + cap
+        self.inputs = torch.zeros((10 * cap,), dtype=f32, device=dev)
+        self.inputs_host = torch.zeros((10 * cap,), dtype=f32).pin_memory()
+        self.res = torch.zeros((1 + 7 * tmax,), dtype=f32, device=dev)
+        self.cat_boxes = torch.zeros((tmax, 4), dtype=f32, device=dev)
+        self.host = torch.zeros((1 + 7 * tmax + 1 + ncap,), dtype=f32).pin_memory()
+        self.srf = torch.zeros((cap * S * S * Cc,), dtype=dt, device=dev)
+        self.resp = torch.zeros((cap * O * O * Cc,), dtype=dt, device=dev)
+        self.tower = torch.zeros((cap * O * O * 2 * Cc,), dtype=dt, device=dev)
+        self.maps = torch.zeros((cap * O * O * 8,), dtype=f32, device=dev)
+        self.tb = torch.zeros((cap, 4), dtype=f32, device=dev)
+        self.conf = torch.zeros((cap,), dtype=f32, device=dev)
+        self.valid = torch.zeros((cap,), dtype=torch.int32, device=dev)
+        self.scratch = torch.zeros((cap,), dtype=torch.int64, device=dev)
+        self.box = eng._box_buffers(cap)
+        self.staged_mem = None   # the Memory whose inputs currently sit in self.inputs (device)
+        self.done = torch.cuda.Event()
+
+
+class _TrackPlan(object):
+    """Launch list of the track-dependent stage for exactly n tracks in memory (cached per n):
+    SR ROIAlign -> xcorr -> towers+GN -> heads -> fused decode -> box-head refinement -> candidate
+    assembly -> solver NMS, then ONE device->host copy of the result block.  All operands except the
+    template features are views of the shared _TrackArena; the small per-track inputs (search regions,
+    template boxes, labels, active flags) arrive in one host->device copy."""
+
+    def __init__(self, eng, P, n, arena, det=None):
+        dev, dt, cfg = eng.device, eng.dtype, eng.cfg
+        L = lib()
+        self.e, self.P, self.n, self.arena = eng, P, n, arena
+        A = arena
+        det_boxes, det_scores, det_block = det if det is not None else (P.det_boxes, P.det_scores, P.det_block)
+        self.det_block = det_block
+        self.keep_det = (det_boxes, det_scores)
+        ncap = det_boxes.shape[0]
+        assert ncap == A.ncap and n <= A.cap
+        total = ncap + n
+        self.ncap, self.total = ncap, total
+        self.keep, self.steps = [], []
+        f32 = torch.float32
+        # ---- inputs block: sr (4n) | boxes (4n) | labels (n, int32 bits) | active (n)
+        self.inputs = A.inputs[:max(10 * n, 1)]
+        self.inputs_host = A.inputs_host[:max(10 * n, 1)]
+        self.sr = A.inputs[0:4 * n].view(n, 4)
+        self.boxes = A.inputs[4 * n:8 * n].view(n, 4)
+        self.labels = A.inputs[8 * n:9 * n].view(torch.int32)
+        self.active = A.inputs[9 * n:10 * n]
+        # ---- result block: kept_boxes (4t, 16B aligned for float4 stores) | keep_cnt | keep_idx (t) | kept_scores (t) | cat_scores (t)
+        t = max(total, 1)
+        rlen = 1 + 7 * t
+        self.res = A.res[:rlen]
+        self.kept_boxes = self.res[0:4 * t].view(t, 4)
+        self.keep_cnt = self.res[4 * t:4 * t + 1].view(torch.int32)
+        self.keep_idx = self.res[4 * t + 1:5 * t + 1].view(torch.int32)
+        self.kept_scores = self.res[5 * t + 1:6 * t + 1]
+        self.cat_scores = self.res[6 * t + 1:7 * t + 1]
+        self.cat_boxes = A.cat_boxes[:t]
+        self.host_res = A.host[:rlen]
+        self.host_det = A.host[rlen:rlen + 1 + ncap].view(torch.int32)
+        self.done = A.done
+        T = cfg.MODEL.TRACK_HEAD
+        Cc, S, O, Tr = eng.C, eng.s_res, eng.o_res, eng.t_res
+        dc = _lib.dtype_code(dt)
+        self.xcorr_slot = None
+        if n:
+            self.srf = A.srf[:n * S * S * Cc].view(n, S, S, Cc)
+            self.resp = A.resp[:n * O * O * Cc].view(n, O, O, Cc)
+            self.tower = A.tower[:n * O * O * 2 * Cc].view(n, O, O, 2 * Cc)
+            self.maps = A.maps[:n * O * O * 8].view(n, O, O, 8)
+            self.tb, self.conf, self.valid, self.scratch = A.tb[:n], A.conf[:n], A.valid[:n], A.scratch[:n]
+            pyr_pad = ops.make_pyramid(P.feats, T.POOLER_SCALES, eng.pads)
+            self.keep.append(pyr_pad)
+            self.steps.append((L.smot_roi_align, (C.byref(pyr_pad), ops._ptr(self.sr), ops._ptr(self.boxes), None, n, Cc, S,
+                                                  T.POOLER_SAMPLING_RATIO, ops._ptr(self.srf), dc), "sr_roi_align"))
+            self.xcorr_slot = len(self.steps)
+            self.steps.append((L.smot_xcorr, None, "xcorr"))  # args rebuilt per frame (template pointer)
+            self._conv(self.resp, "emm.towers", self.tower, pad=1)
+            self.steps.append((L.smot_groupnorm_relu, (ops._ptr(self.tower), ops._ptr(eng.gn_gamma), ops._ptr(eng.gn_beta), n,
+                                                       O * O, 2 * Cc, 2 * Cc, 2 * cfg.MODEL.GROUP_NORM.NUM_GROUPS,
+                                                       cfg.MODEL.GROUP_NORM.EPSILON, 1, dc), "emm_gn"))
+            self._conv(self.tower[..., :Cc], "emm.clsctr", self.maps[..., 0:3], pad=1)
+            self._conv(self.tower[..., Cc:], "emm.reg", self.maps[..., 3:7], pad=1, relu=True)
+            self.steps.append((L.smot_emm_decode, (ops._ptr(self.maps), 8, n, O, eng.up, Tr, ops._ptr(self.sr), ops._ptr(self.boxes),
+                                                   ops._ptr(eng.hann), float(T.PAD_PIXELS), int(T.EMM.USE_CENTERNESS),
+                                                   float(T.EMM.COSINE_WINDOW_WEIGHT), P.W, P.H, int(cfg.INPUT.AMODAL),
+                                                   ops._ptr(self.tb), ops._ptr(self.conf), ops._ptr(self.valid),
+                                                   ops._ptr(self.scratch)), "emm_decode"))
+            # refinement by the box head (roi_heads.py:60-84)
+            self.box = {k: (v[:n] if k in ("pooled", "dec_boxes", "dec_scores") else (v[:, :, :n] if torch.is_tensor(v) else v))
+                        for k, v in A.box.items()}
+            Q = _Plan(eng, P.H, P.W)
+            Q.feats = P.feats
+            eng._box_steps(Q, self.box, self.tb, None, n, self.labels)
+            self.keep.append(Q)
+            self.steps += Q.steps
+            dec_b, dec_s = self.box["dec_boxes"], self.box["dec_scores"]
+        else:
+            dec_b = dec_s = None
+        self.steps.append((L.smot_track_combine, (ops._ptr(det_boxes), ops._ptr(det_scores), ncap, ops._ptr(dec_b),
+                                                  ops._ptr(dec_s), eng.ncls, ops._ptr(self.labels) if n else None,
+                                                  ops._ptr(self.conf) if n else None, ops._ptr(self.valid) if n else None,
+                                                  ops._ptr(self.active) if n else None, n, int(T.TRACKTOR),
+                                                  ops._ptr(self.cat_boxes), ops._ptr(self.cat_scores), ops._ptr(self.keep_cnt)),
+                           "track_combine"))
+        if total:
+            ws = eng.nms_workspace(total)
+            self.steps.append((L.smot_sort_nms, (ops._ptr(self.cat_boxes), 4, ops._ptr(self.cat_scores), 1, None, total, -0.5, 0.5,
+                                                 total, 0, ops._ptr(self.keep_idx), ops._ptr(self.kept_boxes),
+                                                 ops._ptr(self.kept_scores), None, ops._ptr(self.keep_cnt), ops._ptr(ws),
+                                                 ws.numel()), "solver_nms"))
+
+    @property
+    def staged_mem(self):
+        return self.arena.staged_mem
+
+    @staged_mem.setter
+    def staged_mem(self, m):
+        self.arena.staged_mem = m
+
+    def _conv(self, x, name, out, **kw):
+        w, scale, bias = self.e.weights[name]
+        d = ops.conv_desc(x, w, out, scale, bias, **kw)
+        self.keep.append(d)
+        self.steps.append((lib().smot_conv2d, (C.byref(d),), "conv:" + name))
+
+    def run(self, feat, upload=True):
+        """Launch the stage and wait for its result block (the frame's only device->host sync)."""
+        eng = self.e
+        st = _lib.stream_ptr()
+        if self.n:
+            if upload:
+                self.inputs.copy_(self.inputs_host, non_blocking=True)
+            xargs = (ops._ptr(self.srf), ops._ptr(feat), ops._ptr(self.resp), self.n, eng.C, eng.s_res, eng.t_res,
+                     _lib.dtype_code(eng.dtype))
+        for i, (fn, args, tag) in enumerate(self.steps):
+            if i == self.xcorr_slot:
+                with eng.timed("xcorr"):
+                    check(fn(*xargs, st), tag)
+            else:
+                check(fn(*args, st), tag)
+        self.host_res.copy_(self.res, non_blocking=True)
+        self.host_det.copy_(self.det_block, non_blocking=True)
+        self.done.record()
+        self.done.synchronize()
+
+
 class Engine(object):
     def __init__(self, cfg, device="cuda", dtype=None, use_graph=True):
         if not torch.cuda.is_available():
@@ -136,6 +290,8 @@ class Engine(object):
         self.hann = torch.hann_window(self.o_res * self.up, dtype=torch.float).to(self.device)
         self.pads = [int(T.PAD_PIXELS / ((2 ** i) * 4)) for i in range(len(T.POOLER_SCALES))]
         self._nms_ws = {}
+        self._track_plans = {}
+        self._arenas = {}
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
 
     def timed(self, name):
@@ -218,6 +374,8 @@ class Engine(object):
         Wt["emm.clsctr"] = (_ohwi(wcc, dt, dev), None, _f32(bcc, dev))
         Wt["emm.reg"] = (_ohwi(sd[pre + "reg.weight"], dt, dev), None, _f32(sd[pre + "reg.bias"], dev))
         self.plans.clear()
+        self._track_plans.clear()
+        self._arenas.clear()
 
     # ------------------------------------------------------------------------------------------
     # static plan
@@ -341,8 +499,9 @@ class Engine(object):
         cap = nprop * (ncls - 1)
         P.det_boxes = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
         P.det_scores = torch.zeros((cap,), dtype=torch.float32, device=dev)
-        P.det_labels = torch.zeros((cap,), dtype=torch.int32, device=dev)
-        P.det_count = torch.zeros((1,), dtype=torch.int32, device=dev)
+        P.det_block = torch.zeros((1 + cap,), dtype=torch.int32, device=dev)   # [count | labels]: one D2H
+        P.det_count = P.det_block[0:1]
+        P.det_labels = P.det_block[1:]
         nws = ops.sort_nms_workspace(nprop, dev)
         P.keep.append(nws)
         P.call(lambda st: self._fill_dets(P), (), "det_init")
@@ -443,10 +602,37 @@ class Engine(object):
         return ops.emm_decode(maps, mem_sr, mem_boxes, self.hann, self.up, self.t_res, T.PAD_PIXELS,
                               T.EMM.USE_CENTERNESS, T.EMM.COSINE_WINDOW_WEIGHT, P.W, P.H, cfg.INPUT.AMODAL)
 
-    def templates(self, P, boxes_dev):
+    def templates(self, P, boxes_dev, out=None):
         """EMM.extract_cache feature part (track_core.py:92): ROIAlign T x T on the unpadded pyramid."""
         T = self.cfg.MODEL.TRACK_HEAD
-        return ops.roi_align(P.feats, boxes_dev, T.POOLER_SCALES, self.t_res, T.POOLER_SAMPLING_RATIO)
+        if getattr(P, "pyr_plain", None) is None:
+            P.pyr_plain = ops.make_pyramid(P.feats, T.POOLER_SCALES)
+        return ops.roi_align(P.feats, boxes_dev, T.POOLER_SCALES, self.t_res, T.POOLER_SAMPLING_RATIO, out=out,
+                             pyramid=P.pyr_plain)
+
+    def track_arena(self, P, n, ncap=None):
+        """The shared buffer arena of static plan P, grown (x2) when n exceeds its capacity."""
+        ncap = P.det_boxes.shape[0] if ncap is None else ncap
+        key = (P.H, P.W, ncap)
+        A = self._arenas.get(key)
+        if A is None or A.cap < n:
+            cap = 64 if A is None else A.cap
+            while cap < n:
+                cap *= 2
+            A = self._arenas[key] = _TrackArena(self, P, ncap, cap)
+            for k in [k for k in self._track_plans if k[:2] == (P.H, P.W)]:
+                self._track_plans.pop(k)
+        return A
+
+    def track_plan(self, P, n, det=None):
+        if det is not None:   # external detections: one-off plan over their arrays
+            return _TrackPlan(self, P, n, self.track_arena(P, n, det[0].shape[0]), det=det)
+        A = self.track_arena(P, n)
+        key = (P.H, P.W, n)
+        tp = self._track_plans.get(key)
+        if tp is None:
+            tp = self._track_plans[key] = _TrackPlan(self, P, n, A)
+        return tp
 
     def nms_workspace(self, n):
         n = max(64, 1 << (max(n, 1) - 1).bit_length())

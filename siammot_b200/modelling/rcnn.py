@@ -10,6 +10,7 @@ through :class:`siammot_b200.engine.Engine`; this file is host control flow only
 TrackHead.get_track_memory track_head.py:54-110), restructured so that a frame costs one
 device->host copy.
 """
+import numpy as np
 import torch
 from torch import nn
 
@@ -46,28 +47,41 @@ def _is_frozen_bn_key(key, bn_names):
 
 
 class Memory(object):
-    """Track memory for the next frame: N = active tracks (first) + dormant tracks."""
+    """Track memory for the next frame: N = active tracks (first) + dormant tracks.
+    Host-side arrays are numpy fp32 / int64 (same IEEE arithmetic as the reference's torch ops)."""
 
     def __init__(self, feat, sr, boxes, ids, labels, n_active, device):
         self.feat = feat                  # device (N,T,T,C) activation dtype
-        self.sr = sr                      # cpu (N,4) fp32, padded frame
-        self.boxes = boxes                # cpu (N,4) fp32
-        self.ids = ids                    # list[int]
-        self.labels = labels              # cpu int64 (N,)
+        self.sr = sr                      # np (N,4) fp32, padded frame
+        self.boxes = boxes                # np (N,4) fp32
+        self.ids = ids                    # np int64 (N,)
+        self.labels = labels              # np int64 (N,)
         self.n_active = n_active
-        self.n = boxes.shape[0]
-        if self.n:
-            self.sr_dev = sr.to(device, non_blocking=True)
-            self.boxes_dev = boxes.to(device, non_blocking=True)
-            self.labels_dev = labels.to(torch.int32).to(device, non_blocking=True)
-            act = torch.zeros(self.n, dtype=torch.float32)
-            act[:n_active] = 1.0
-            self.active_dev = act.to(device, non_blocking=True)
+        self.n = int(boxes.shape[0])
+        self.device = device
+
+    def stage(self, tp):
+        """Write sr | boxes | labels | active into the plan's pinned input block."""
+        n = self.n
+        h = tp.inputs_host.numpy()
+        h[0:4 * n] = self.sr.reshape(-1)
+        h[4 * n:8 * n] = self.boxes.reshape(-1)
+        h[8 * n:9 * n].view(np.int32)[:] = self.labels
+        h[9 * n:9 * n + self.n_active] = 1.0
+        h[9 * n + self.n_active:10 * n] = 0.0
+
+    # views used by the generic (plugin / given-detection) path
+    def torch_views(self):
+        dev = self.device
+        return (torch.from_numpy(self.sr).to(dev), torch.from_numpy(self.boxes).to(dev),
+                torch.from_numpy(self.labels.astype(np.int32)).to(dev))
 
 
 @registry.SIAMESE_TRACKER.register("EMM")
 class EMM(nn.Module):
-    """The Explicit Motion Model tracker (track_core.py:14-98) on the engine."""
+    """The Explicit Motion Model tracker (track_core.py:14-98) on the engine.  ``SiamMOT.forward`` runs it
+    through the engine's fused per-N launch plan; ``forward`` / ``extract_cache`` keep the reference's
+    plugin contract for callers that drive the tracker themselves."""
 
     def __init__(self, cfg, track_utils):
         super().__init__()
@@ -76,12 +90,9 @@ class EMM(nn.Module):
         self.predictor = _Holder()
         self.engine = None  # set by SiamMOT
 
-    def track_device(self, plan, mem):
-        return self.engine.emm_track(plan, mem.feat, mem.sr_dev, mem.boxes_dev)
-
     def forward(self, features, boxes, sr, targets=None, template_features=None):
-        """Reference contract: returns ({}, [BoxList], {}) with clipped, non-empty track boxes.
-        ``features`` is the engine plan of the current frame."""
+        """Reference contract: ({}, [BoxList], {}) with clipped, non-empty track boxes.
+        ``features`` is the engine plan of the current frame (see INTEGRATION.md)."""
         dev = self.engine.device
         b, s = boxes[0], sr[0]
         tb, conf, valid = self.engine.emm_track(features, template_features, s.bbox.to(dev).contiguous(),
@@ -120,25 +131,28 @@ class TrackSolver(nn.Module):
         self.start_thresh = start_track_thresh
         self.resume_track_thresh = resume_track_thresh
 
-    def resolve(self, boxes, scores_adj, all_ids, labels, all_track_ids):
-        """Host half of TrackSolver.forward (track_solver.py:71-106) given the NMS survivors, in NMS order.
-        scores_adj still carries the +1 (dormant / refined) and +2 (active) offsets."""
+    def resolve(self, scores_adj, ids, all_track_ids):
+        """Host half of TrackSolver.forward (track_solver.py:71-106) on the NMS survivors (numpy, NMS order).
+        scores_adj still carries the +1 (dormant / refined) and +2 (active) offsets.  Returns the folded
+        scores and the final ids; updates the pool exactly like the reference."""
         pool = self.track_pool
-        _scores = scores_adj.clone()
-        _scores[_scores >= 2.] = _scores[_scores >= 2.] - 2.
-        _scores[_scores >= 1.] = _scores[_scores >= 1.] - 1.
-        _ids = all_ids.clone()
-        start_idxs = ((_ids < 0) & (_scores >= self.start_thresh)).nonzero()
-        inactive_idxs = ((_ids >= 0) & (_scores < self.track_thresh))
+        _scores = scores_adj.astype(np.float32, copy=True)
+        m = _scores >= np.float32(2.)
+        _scores[m] = _scores[m] - np.float32(2.)
+        m = _scores >= np.float32(1.)
+        _scores[m] = _scores[m] - np.float32(1.)
+        _ids = ids.astype(np.int64, copy=True)
+        start_idxs = np.nonzero((_ids < 0) & (_scores >= np.float32(self.start_thresh)))[0]
+        inactive_idxs = (_ids >= 0) & (_scores < np.float32(self.track_thresh))
         nms_track_ids = set(_ids[_ids >= 0].tolist())
         nms_removed_ids = all_track_ids - nms_track_ids
         inactive_ids = set(_ids[inactive_idxs].tolist()) | nms_removed_ids
         dormant_ids = pool.get_dormant_ids()
-        dormant_mask = torch.tensor([int(x) in dormant_ids for x in _ids], dtype=torch.bool)
-        resume_ids = _ids[dormant_mask & (_scores >= self.resume_track_thresh)]
-        for _id in resume_ids.tolist():
-            pool.resume_track(_id)
-        for _idx in start_idxs:
+        if dormant_ids:
+            dormant_mask = np.fromiter((x in dormant_ids for x in _ids.tolist()), dtype=bool, count=_ids.shape[0])
+            for _id in _ids[dormant_mask & (_scores >= np.float32(self.resume_track_thresh))].tolist():
+                pool.resume_track(_id)
+        for _idx in start_idxs.tolist():
             _ids[_idx] = pool.start_track()
         active_ids = pool.get_active_ids()
         for _id in inactive_ids:
@@ -147,7 +161,7 @@ class TrackSolver(nn.Module):
         _ids[inactive_idxs] = -1
         pool.expire_tracks()
         pool.increment_frame()
-        return boxes, _scores, _ids, labels
+        return _scores, _ids
 
 
 class CombinedROIHeads(nn.ModuleDict):
@@ -155,141 +169,143 @@ class CombinedROIHeads(nn.ModuleDict):
         super().__init__(heads)
         self.cfg = cfg
         self.engine = None
+        self._out_host = None
 
     def reset_roi_status(self):
         if self.cfg.MODEL.TRACK_ON:
             self.track.reset_track_pool()
 
-    # -- detections from externally provided boxes (roi_heads.py:26-34)
+    # -- detections from externally provided boxes (roi_heads.py:26-34): box head + per-class NMS, eager
     def _given_detections(self, P, given):
         eng, dev, cfg = self.engine, self.engine.device, self.cfg
+        ncls = eng.ncls
         rois = given.convert("xyxy").bbox.to(dev, torch.float32).contiguous()
         n = rois.shape[0]
-        dec_b, dec_s = eng.box_head_eager(P, rois)
-        ncls = eng.ncls
-        cap = n * (ncls - 1)
+        cap = max(n * (ncls - 1), 1)
         det_boxes = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
         det_scores = torch.full((cap,), -1.0, dtype=torch.float32, device=dev)
-        det_labels = torch.zeros((cap,), dtype=torch.int32, device=dev)
-        det_count = torch.zeros((1,), dtype=torch.int32, device=dev)
-        H = cfg.MODEL.ROI_HEADS
-        for j in range(1, ncls):
-            ops.sort_nms(dec_b[:, j], dec_s[:, j], det_count, n_max=n, min_score=H.SCORE_THRESH, thresh=H.NMS,
-                         max_keep=n, tag=j, out_boxes=det_boxes, out_scores=det_scores, out_tag=det_labels,
-                         workspace=eng.nms_workspace(n), box_stride=4 * ncls, score_stride=ncls)
-        return det_boxes, det_scores, det_labels, det_count
+        det_block = torch.zeros((1 + cap,), dtype=torch.int32, device=dev)
+        if n:
+            dec_b, dec_s = eng.box_head_eager(P, rois)
+            H = cfg.MODEL.ROI_HEADS
+            for j in range(1, ncls):
+                ops.sort_nms(dec_b[:, j], dec_s[:, j], det_block[0:1], n_max=n, min_score=H.SCORE_THRESH, thresh=H.NMS,
+                             max_keep=n, tag=j, out_boxes=det_boxes, out_scores=det_scores, out_tag=det_block[1:],
+                             workspace=eng.nms_workspace(n), box_stride=4 * ncls, score_stride=ncls)
+        return det_boxes, det_scores, det_block
 
     def run_frame(self, P, mem, given_detection=None):
-        """One frame after the static stage.  Returns (BoxList on device, Memory for the next frame)."""
-        eng, dev, cfg = self.engine, self.engine.device, self.cfg
-        pool = self.track.track_pool
-        img_size = (P.W, P.H)
-        if given_detection is None:
-            det_boxes, det_scores, det_labels, det_count = P.det_boxes, P.det_scores, P.det_labels, P.det_count
-        elif len(given_detection[0]) > 0:
-            det_boxes, det_scores, det_labels, det_count = self._given_detections(P, given_detection[0])
-        else:
-            det_boxes = torch.zeros((0, 4), dtype=torch.float32, device=dev)
-            det_scores = torch.zeros((0,), dtype=torch.float32, device=dev)
-            det_labels = torch.zeros((0,), dtype=torch.int32, device=dev)
-            det_count = torch.zeros((1,), dtype=torch.int32, device=dev)
-        ncap = det_boxes.shape[0]
-
+        """One frame after the static stage (CombinedROIHeads.forward roi_heads.py:21-51).
+        Returns (BoxList on the model device, Memory for the next frame)."""
+        eng, cfg = self.engine, self.cfg
         if not cfg.MODEL.TRACK_ON:
             raise NotImplementedError("MODEL.TRACK_ON False")
+        pool = self.track.track_pool
         if mem is None:
             pool.reset()                                                  # track_head.py:39-40
-        n_trk = mem.n if (mem is not None and mem.feat.numel() > 0) else 0
-        if n_trk:
-            tb, conf, valid = self.track.tracker.track_device(P, mem)     # EMM.forward
-            dec_b, dec_s = eng.box_head_eager(P, tb, mem.labels_dev)      # _refine_tracks roi_heads.py:60-84
-            rows = torch.arange(n_trk, device=dev)
-            lab = mem.labels_dev.long()
-            ref_boxes = dec_b[rows, lab]
-            det_part = dec_s[rows, lab]                                   # p + 1   (inference.py:103)
-            if cfg.MODEL.TRACK_HEAD.TRACKTOR:
-                trk_scores = det_part
-            else:
-                trk_scores = (det_part + (conf + 1.)) / 2.                # roi_heads.py:67,76
-            trk_scores = trk_scores + mem.active_dev                      # track_solver.py:69
-            trk_scores = torch.where(valid > 0, trk_scores, torch.full_like(trk_scores, -1.0))
-            cat_boxes = torch.cat([det_boxes, ref_boxes])
-            cat_scores = torch.cat([det_scores, trk_scores])
+        n = mem.n if (mem is not None and mem.feat is not None and mem.feat.numel() > 0) else 0
+        if given_detection is None:
+            tp = eng.track_plan(P, n)
         else:
-            cat_boxes, cat_scores = det_boxes, det_scores
-        total = cat_boxes.shape[0]
-        keep_idx = torch.zeros((max(total, 1),), dtype=torch.int32, device=dev)
-        keep_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
-        if total:
-            ops.sort_nms(cat_boxes, cat_scores, keep_cnt, n_max=total, min_score=-0.5, thresh=0.5, max_keep=total,
-                         out_index=keep_idx, workspace=eng.nms_workspace(total))
-        # ---- the frame's single device->host copy
-        pack = torch.cat([keep_cnt.view(torch.float32), det_count.view(torch.float32), keep_idx.view(torch.float32),
-                          cat_boxes.reshape(-1), cat_scores, det_labels.view(torch.float32)])
-        host = pack.cpu()
-        k = int(host[0:1].view(torch.int32))
-        o = 2
-        h_keep = host[o:o + max(total, 1)].view(torch.int32)[:k].long(); o += max(total, 1)
-        h_boxes = host[o:o + 4 * total].view(total, 4); o += 4 * total
-        h_scores = host[o:o + total]; o += total
-        h_dlabels = host[o:o + ncap].view(torch.int32).long()
+            # external detections replace the RPN/box-head ones: a one-off plan bound to their arrays
+            tp = eng.track_plan(P, n, det=self._given_detections(P, given_detection[0]))
+        upload = bool(n) and tp.staged_mem is not mem
+        if upload:
+            mem.stage(tp)
+            tp.staged_mem = mem
+        tp.run(mem.feat if n else None, upload=upload)
 
-        # ids / labels of every candidate row (detections first, then memory rows)
-        all_ids = torch.full((total,), -1, dtype=torch.int64)
-        all_labels = torch.zeros((total,), dtype=torch.int64)
-        all_labels[:ncap] = h_dlabels
-        if n_trk:
-            all_ids[ncap:] = torch.tensor(mem.ids, dtype=torch.int64)
-            all_labels[ncap:] = mem.labels
-            trk_valid = h_scores[ncap:] > -0.5
-            if not bool(trk_valid.any()):
+        # ---- host: unpack the result block
+        total, ncap = tp.total, tp.ncap
+        t = max(total, 1)
+        hf = tp.host_res.numpy()
+        hi = hf.view(np.int32)
+        k = int(hi[4 * t])
+        keep = hi[4 * t + 1:4 * t + 1 + k]
+        kboxes = hf[0:4 * t].reshape(t, 4)[:k]
+        kscores = hf[5 * t + 1:5 * t + 1 + k]
+        det_labels = tp.host_det.numpy()[1:1 + ncap]
+        is_trk = keep >= ncap
+        ids = np.full((k,), -1, dtype=np.int64)
+        labels = np.zeros((k,), dtype=np.int64)
+        labels[~is_trk] = det_labels[keep[~is_trk]]
+        all_track_ids = set()
+        if n:
+            trk_valid = hf[6 * t + 1 + ncap:6 * t + 1 + total] > -0.5
+            if not trk_valid.any():
                 # roi_heads.py:64-65 returns a bare BoxList here and :44 then evaluates list + BoxList
                 raise TypeError("can only concatenate list (not \"BoxList\") to list")
-            all_track_ids = set(all_ids[ncap:][trk_valid].tolist())
+            all_track_ids = set(mem.ids[trk_valid].tolist())
+            rows = keep[is_trk] - ncap
+            ids[is_trk] = mem.ids[rows]
+            labels[is_trk] = mem.labels[rows]
+        if k == 0:                                                        # track_solver.py:51-52 (early return)
+            scores = np.zeros((0,), dtype=np.float32)
         else:
-            all_track_ids = set()
-
-        if k == 0 and not (h_scores > -0.5).any():                        # track_solver.py:51-52
-            boxes, scores = torch.zeros((0, 4)), torch.zeros((0,))
-            ids, labels = torch.zeros((0,), dtype=torch.int64), torch.zeros((0,), dtype=torch.int64)
-        else:
-            boxes, scores, ids, labels = self.solver.resolve(h_boxes[h_keep], h_scores[h_keep], all_ids[h_keep],
-                                                             all_labels[h_keep], all_track_ids)
+            scores, ids = self.solver.resolve(kscores, ids, all_track_ids)
+        boxes = np.array(kboxes, dtype=np.float32, copy=True)
         new_mem = self._build_memory(P, boxes, ids, labels)
-        result = BoxList(boxes.to(dev, non_blocking=True), img_size, mode="xyxy")
-        result.add_field("scores", scores.to(dev, non_blocking=True))
-        result.add_field("ids", ids.to(dev, non_blocking=True))
-        result.add_field("labels", labels.to(dev, non_blocking=True))
-        return result, new_mem
+        return self._to_boxlist(boxes, scores, ids, labels, (P.W, P.H)), new_mem
+
+    def _to_boxlist(self, boxes, scores, ids, labels, size):
+        """One packed pinned buffer -> one H2D copy; the BoxList fields are views of the device copy."""
+        dev = self.engine.device
+        k = boxes.shape[0]
+        nbytes = 36 * k
+        if self._out_host is None or self._out_host.numel() < nbytes:
+            self._out_host = torch.zeros((max(nbytes, 36 * 256),), dtype=torch.uint8).pin_memory()
+        h = self._out_host.numpy()
+        h[0:8 * k].view(np.int64)[:] = ids
+        h[8 * k:16 * k].view(np.int64)[:] = labels
+        h[16 * k:32 * k].view(np.float32)[:] = boxes.reshape(-1)
+        h[32 * k:36 * k].view(np.float32)[:] = scores
+        d = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=dev)
+        d[:nbytes].copy_(self._out_host[:nbytes], non_blocking=True)
+        out = BoxList(d[16 * k:32 * k].view(torch.float32).view(k, 4), size, mode="xyxy")
+        out.add_field("scores", d[32 * k:36 * k].view(torch.float32))
+        out.add_field("ids", d[0:8 * k].view(torch.int64))
+        out.add_field("labels", d[8 * k:16 * k].view(torch.int64))
+        return out
 
     def _build_memory(self, P, boxes, ids, labels):
-        """TrackHead.get_track_memory (track_head.py:54-110) + EMM.extract_cache (track_core.py:81-98)."""
+        """TrackHead.get_track_memory (track_head.py:54-110) + EMM.extract_cache (track_core.py:81-98).
+        boxes/ids/labels: numpy, solver output order."""
         eng, dev = self.engine, self.engine.device
         pool = self.track.track_pool
         tu = self.track.track_utils
         active_ids = pool.get_active_ids()
-        sel = torch.tensor([int(i) in active_ids for i in ids.tolist()], dtype=torch.bool)
-        a_boxes, a_ids, a_labels = boxes[sel], ids[sel].tolist(), labels[sel]
-        n_act = a_boxes.shape[0]
+        ids_l = ids.tolist()
+        sel = np.fromiter((i in active_ids for i in ids_l), dtype=bool, count=len(ids_l))
+        a_boxes, a_ids, a_labels = boxes[sel], ids[sel], labels[sel]
+        n_act = int(a_ids.shape[0])
         cache = pool.get_cache()
         dormant = [cache[i] for i in pool.get_dormant_ids() if i in cache] if cache else []
-        m_boxes = torch.cat([a_boxes] + [d["box"] for d in dormant]) if dormant else a_boxes
-        a_sr = tu.search_region(a_boxes) if n_act else torch.zeros((0, 4))
-        m_sr = torch.cat([a_sr] + [d["sr"] for d in dormant]) if dormant else a_sr
-        m_ids = a_ids + [d["id"] for d in dormant]
-        m_labels = torch.cat([a_labels] + [d["label"] for d in dormant]) if dormant else a_labels
-        n = m_boxes.shape[0]
+        n = n_act + len(dormant)
+        m_boxes = np.empty((n, 4), dtype=np.float32)
+        m_sr = np.empty((n, 4), dtype=np.float32)
+        m_ids = np.empty((n,), dtype=np.int64)
+        m_labels = np.empty((n,), dtype=np.int64)
+        m_boxes[:n_act], m_ids[:n_act], m_labels[:n_act] = a_boxes, a_ids, a_labels
+        if n_act:
+            m_sr[:n_act] = tu.search_region_np(a_boxes)
+        for j, d in enumerate(dormant):
+            r = n_act + j
+            m_boxes[r], m_sr[r], m_ids[r], m_labels[r] = d[3], d[2], d[4], d[5]
         if n == 0:
-            feat = torch.zeros((0,), device=dev)
-        else:
-            parts = []
-            if n_act:
-                parts.append(eng.templates(P, a_boxes.to(dev).contiguous()))
-            parts += [d["feat"][None] for d in dormant]
-            feat = torch.cat(parts) if len(parts) > 1 else parts[0]
-        mem = Memory(feat, m_sr, m_boxes, m_ids, m_labels, n_act, dev)
-        pool.update_cache({m_ids[r]: dict(feat=feat[r], sr=m_sr[r:r + 1], box=m_boxes[r:r + 1], id=m_ids[r],
-                                          label=m_labels[r:r + 1]) for r in range(n)})
+            return Memory(None, m_sr, m_boxes, m_ids, m_labels, 0, dev)
+        tp = eng.track_plan(P, n)            # next frame's plan: stage its inputs now (boxes are needed on device anyway)
+        mem = Memory(None, m_sr, m_boxes, m_ids, m_labels, n_act, dev)
+        mem.stage(tp)
+        tp.staged_mem = mem
+        tp.inputs.copy_(tp.inputs_host, non_blocking=True)
+        feat = torch.empty((n, eng.t_res, eng.t_res, eng.C), dtype=eng.dtype, device=dev)
+        if n_act:
+            eng.templates(P, tp.boxes[:n_act], out=feat[:n_act])
+        if dormant:
+            feat[n_act:] = torch.stack([d[0][d[1]] for d in dormant])
+        mem.feat = feat
+        pool.update_cache({int(m_ids[r]): (feat, r, m_sr[r].copy(), m_boxes[r].copy(), int(m_ids[r]), int(m_labels[r]))
+                           for r in range(n)})
         return mem
 
 
@@ -356,11 +372,15 @@ class SiamMOT(nn.Module):
         self.roi_heads.reset_roi_status()
 
     def _memory_from_tuple(self, cache):
+        """Accept the reference's (template_features, [sr BoxList], [boxes BoxList]) memory tuple."""
         feats, sr, boxes = cache
         b = boxes[0].to("cpu")
-        n_act = sum(1 for i in b.get_field("ids").tolist() if i in self.roi_heads.track.track_pool.get_active_ids())
-        return Memory(feats, sr[0].bbox.to("cpu").float(), b.bbox.float(), b.get_field("ids").tolist(),
-                      b.get_field("labels").to(torch.int64), n_act, next(self.parameters()).device)
+        ids = b.get_field("ids").to(torch.int64).numpy()
+        active = self.roi_heads.track.track_pool.get_active_ids()
+        n_act = sum(1 for i in ids.tolist() if i in active)
+        dev = next(self.parameters()).device
+        return Memory(feats.to(dev) if feats.numel() else None, sr[0].bbox.to("cpu").float().numpy(), b.bbox.float().numpy(),
+                      ids, b.get_field("labels").to(torch.int64).numpy(), n_act, dev)
 
     @torch.no_grad()
     def forward(self, images, targets=None, given_detection=None):

@@ -26,6 +26,17 @@ class TrackUtils(object):
         h_ext = torch.max((self.min_search_wh - h) / (self.search_expansion * 2.), h * (self.search_expansion / 2.))
         return torch.stack((sr[:, 0] - w_ext, sr[:, 1] - h_ext, sr[:, 2] + w_ext, sr[:, 3] + h_ext), dim=1)
 
+    def search_region_np(self, boxes):
+        """numpy fp32 twin of search_region (identical IEEE operations, lower host overhead)."""
+        import numpy as np
+        sr = boxes + np.float32(self.pad_pixels)
+        w = sr[:, 2] - sr[:, 0] + np.float32(1)
+        h = sr[:, 3] - sr[:, 1] + np.float32(1)
+        se = float(self.search_expansion)
+        w_ext = np.maximum((np.float32(self.min_search_wh) - w) / np.float32(se * 2.), w * np.float32(se / 2.))
+        h_ext = np.maximum((np.float32(self.min_search_wh) - h) / np.float32(se * 2.), h * np.float32(se / 2.))
+        return np.stack((sr[:, 0] - w_ext, sr[:, 1] - h_ext, sr[:, 2] + w_ext, sr[:, 3] + h_ext), axis=1).astype(np.float32)
+
     def update_boxes_in_pad_images(self, boxlists):
         out = []
         for bl in boxlists:

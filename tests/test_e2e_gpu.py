@@ -38,7 +38,8 @@ def run_engine_scenario(name, dtype="float32"):
         pool.reset()
         boxes = inject_boxes(sc["inject"])
         ids = torch.tensor([pool.start_track() for _ in range(len(boxes))])
-        model.flush_memory(model.roi_heads._build_memory(P, boxes, ids, torch.ones(len(boxes), dtype=torch.int64)))
+        model.flush_memory(model.roi_heads._build_memory(P, boxes.numpy(), ids.numpy(),
+                                                               torch.ones(len(boxes), dtype=torch.int64).numpy()))
         pool.increment_frame()
         start = 1
     for t in range(start, sc["frames"]):
