@@ -1,0 +1,163 @@
+// Convolution / fully-connected layers with very few output channels (Cout <= 16): the RPN
+// objectness+delta predictor (15), the EMM cls/center/reg heads (3 / 4) and the box predictor (10).
+// They are bandwidth/latency bound (the weight is tiny, every input element is used Cout times), so a
+// GEMM tile is the wrong shape: here ONE WARP produces PIX consecutive output pixels; its lanes split
+// the input channels (4 per lane, contiguous 8/16-byte loads, 256/512 B per warp per pixel and tap),
+// the weights sit in shared memory as [Cout][K] and are read conflict-free as float4, and the partial
+// sums are combined with a butterfly reduction.  Epilogue: bias / scale, optional ReLU, fp32 or fp16 out.
+#include "common.cuh"
+
+namespace smot {
+
+struct SmallNArgs {
+  const void* in;
+  const void* wt;
+  const float* scale;
+  const float* bias;
+  void* out;
+  int batch, H, W, Cin, in_ld, OH, OW, Cout, out_ld, KH, KW, pad, relu, M, K;
+};
+
+constexpr int SN_PIX = 4;
+constexpr int SN_WARPS = 8;
+
+template <typename TI, typename TO, int COUT>
+__global__ void __launch_bounds__(SN_WARPS * 32) conv_smalln_kernel(const SmallNArgs a) {
+  extern __shared__ __align__(16) float sn_w[];  // [COUT][K] (rows >= a.Cout are zero)
+  const TI* __restrict__ wt = reinterpret_cast<const TI*>(a.wt);
+  for (int i = threadIdx.x; i < COUT * a.K; i += blockDim.x) {
+    const int co = i / a.K;
+    sn_w[i] = co < a.Cout ? to_f(wt[(size_t)co * a.K + (i - co * a.K)]) : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m0 = (blockIdx.x * SN_WARPS + warp) * SN_PIX;
+  if (m0 >= a.M) return;
+  const TI* __restrict__ in = reinterpret_cast<const TI*>(a.in);
+  const TI* base[SN_PIX];
+  int ih0[SN_PIX], iw0[SN_PIX];
+  bool ok[SN_PIX];
+#pragma unroll
+  for (int p = 0; p < SN_PIX; ++p) {
+    const int m = m0 + p;
+    ok[p] = m < a.M;
+    const int mm = ok[p] ? m : m0;
+    const int img = mm / (a.OH * a.OW);
+    const int rem = mm - img * (a.OH * a.OW);
+    const int oh = rem / a.OW;
+    ih0[p] = oh - a.pad;
+    iw0[p] = rem - oh * a.OW - a.pad;
+    base[p] = in + (size_t)img * a.H * a.W * a.in_ld;
+  }
+  float acc[SN_PIX][COUT];
+#pragma unroll
+  for (int p = 0; p < SN_PIX; ++p)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[p][c] = 0.f;
+
+  for (int r = 0; r < a.KH; ++r)
+    for (int s = 0; s < a.KW; ++s) {
+      const int kbase = (r * a.KW + s) * a.Cin;
+      for (int c0 = lane * 4; c0 < a.Cin; c0 += 128) {
+        float4 x[SN_PIX];
+#pragma unroll
+        for (int p = 0; p < SN_PIX; ++p) {
+          const int ih = ih0[p] + r, iw = iw0[p] + s;
+          const bool v = ok[p] && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
+          x[p] = v ? ld4(base[p] + ((size_t)ih * a.W + iw) * a.in_ld + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          const float4 w = *reinterpret_cast<const float4*>(sn_w + (size_t)c * a.K + kbase + c0);
+#pragma unroll
+          for (int p = 0; p < SN_PIX; ++p) {
+            acc[p][c] = fmaf(x[p].x, w.x, acc[p][c]);
+            acc[p][c] = fmaf(x[p].y, w.y, acc[p][c]);
+            acc[p][c] = fmaf(x[p].z, w.z, acc[p][c]);
+            acc[p][c] = fmaf(x[p].w, w.w, acc[p][c]);
+          }
+        }
+      }
+    }
+  // butterfly reduction: afterwards every lane holds the full sums
+#pragma unroll
+  for (int p = 0; p < SN_PIX; ++p)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+      float v = acc[p][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[p][c] = v;
+    }
+  TO* __restrict__ out = reinterpret_cast<TO*>(a.out);
+#pragma unroll
+  for (int p = 0; p < SN_PIX; ++p) {
+    if (!ok[p]) continue;
+    // lane c writes channel c (select without dynamic register indexing)
+    float y = 0.f;
+#pragma unroll
+    for (int c = 0; c < COUT; ++c)
+      if (lane == c) y = acc[p][c];
+    if (lane < a.Cout) {
+      if (a.scale) y = __fmul_rn(y, a.scale[lane]);
+      if (a.bias) y = __fadd_rn(y, a.bias[lane]);
+      if (a.relu) y = fmaxf(y, 0.f);
+      out[(size_t)(m0 + p) * a.out_ld + lane] = from_f<TO>(y);
+    }
+  }
+}
+
+bool conv2d_smalln_supported(const smot_conv_desc* d) {
+  if (d->Cout > 16 || d->stride != 1 || d->residual) return false;
+  if (d->Cin < 64 || d->Cin % 4 != 0 || d->in_ld % 4 != 0 || ((uintptr_t)d->in & 15)) return false;  // lanes split channels
+  if ((size_t)d->KH * d->KW * d->Cin * 16 * sizeof(float) > 96 * 1024) return false;
+  if (d->OH != d->H + 2 * d->pad - d->KH + 1 || d->OW != d->W + 2 * d->pad - d->KW + 1) return false;
+  return true;
+}
+
+template <typename TI, typename TO>
+static int launch_smalln(const SmallNArgs& a, cudaStream_t st) {
+  const int cout_pad = a.Cout <= 4 ? 4 : (a.Cout <= 8 ? 8 : 16);
+  const size_t smem = (size_t)cout_pad * a.K * sizeof(float);
+  const unsigned grid = (unsigned)ceil_div(a.M, SN_PIX * SN_WARPS);
+  cudaError_t e = cudaSuccess;
+#define SMOT_SN_LAUNCH(CO)                                                                                          \
+  do {                                                                                                              \
+    static size_t attr = 0;                                                                                         \
+    if (smem > 48 * 1024 && smem > attr) {                                                                          \
+      e = cudaFuncSetAttribute(conv_smalln_kernel<TI, TO, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      attr = smem;                                                                                                  \
+    }                                                                                                               \
+    if (e == cudaSuccess) conv_smalln_kernel<TI, TO, CO><<<grid, SN_WARPS * 32, smem, st>>>(a);                     \
+  } while (0)
+  if (cout_pad == 4)
+    SMOT_SN_LAUNCH(4);
+  else if (cout_pad == 8)
+    SMOT_SN_LAUNCH(8);
+  else
+    SMOT_SN_LAUNCH(16);
+#undef SMOT_SN_LAUNCH
+  if (e != cudaSuccess) {
+    set_error("smot_conv2d(smalln): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return SMOT_ERR_CUDA;
+  }
+  SMOT_CHECK_LAUNCH("smot_conv2d(smalln)");
+  return SMOT_OK;
+}
+
+int conv2d_smalln(const smot_conv_desc* d, cudaStream_t st) {
+  SmallNArgs a;
+  a.in = d->in, a.wt = d->weight, a.scale = d->scale, a.bias = d->bias, a.out = d->out;
+  a.batch = d->batch, a.H = d->H, a.W = d->W, a.Cin = d->Cin, a.in_ld = d->in_ld, a.OH = d->OH, a.OW = d->OW;
+  a.Cout = d->Cout, a.out_ld = d->out_ld, a.KH = d->KH, a.KW = d->KW, a.pad = d->pad, a.relu = d->relu;
+  a.M = d->batch * d->OH * d->OW;
+  a.K = d->KH * d->KW * d->Cin;
+  if (a.M == 0) return SMOT_OK;
+  if (d->in_dtype == SMOT_F32 && d->out_dtype == SMOT_F32) return launch_smalln<float, float>(a, st);
+  if (d->in_dtype == SMOT_F16 && d->out_dtype == SMOT_F16) return launch_smalln<__half, __half>(a, st);
+  if (d->in_dtype == SMOT_F16 && d->out_dtype == SMOT_F32) return launch_smalln<__half, float>(a, st);
+  set_error("smot_conv2d(smalln): unsupported dtype combination");
+  return SMOT_ERR_UNSUPPORTED;
+}
+
+}  // namespace smot

@@ -36,7 +36,7 @@ struct TcArgs {
   __half* out;
   int H, W;          // output (= input, stride 1) spatial size
   int Cin, Cout, out_ld, res_ld, relu;
-  int taps, KW, pad, cin_chunks;
+  int taps, KW, pad, cin_chunks, stride;
   int tiles_w, tiles_h, tile_w, tile_h;
 };
 
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         mbar_expect_tx(&full[s], (uint32_t)S::STAGE_BYTES);
         const int tap = it / a.cin_chunks, cc = it - tap * a.cin_chunks;
         const int r = tap / a.KW, sx = tap - r * a.KW;
-        tma_load_4d(sA + s * S::A_BYTES, &tmA, &full[s], cc * TC_BK, w0 + sx - a.pad, h0 + r - a.pad, img);
+        tma_load_4d(sA + s * S::A_BYTES, &tmA, &full[s], cc * TC_BK, w0 * a.stride + sx - a.pad, h0 * a.stride + r - a.pad, img);
         tma_load_2d(sB + s * S::B_BYTES, &tmB, &full[s], tap * a.Cin + cc * TC_BK, n0);
       }
     }
@@ -289,13 +289,15 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
 }
 
 static bool encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                       const uint32_t* box) {
+                       const uint32_t* box, const uint32_t* estr_in = nullptr) {
   PFN_cuTensorMapEncodeTiled enc = get_encode();
   if (!enc) {
     set_error("smot_conv2d(tcgen05): cuTensorMapEncodeTiled entry point not available");
     return false;
   }
   uint32_t estr[4] = {1, 1, 1, 1};
+  if (estr_in)
+    for (int i = 0; i < rank; ++i) estr[i] = estr_in[i];
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -308,12 +310,13 @@ static bool encode_map(CUtensorMap* tm, const void* base, int rank, const uint64
 
 bool conv2d_tc_supported(const smot_conv_desc* d) {
   if (d->in_dtype != SMOT_F16 || d->out_dtype != SMOT_F16) return false;
-  if (d->stride != 1 || d->KH != d->KW || (d->KH != 1 && d->KH != 3) || d->pad != d->KH / 2) return false;
+  if (d->KH != d->KW || (d->KH != 1 && d->KH != 3) || d->pad != d->KH / 2) return false;
+  if (d->stride != 1 && !(d->stride == 2 && d->KH == 3 && d->H % 2 == 0 && d->W % 2 == 0 && d->H > 1)) return false;
   if (d->Cin % TC_BK != 0 || d->Cout % 64 != 0) return false;
   if (d->in_ld % 8 != 0 || d->out_ld % 8 != 0 || (d->residual && d->res_ld % 8 != 0)) return false;
   if (((uintptr_t)d->in | (uintptr_t)d->weight | (uintptr_t)d->out | (uintptr_t)d->residual) & 15) return false;
-  if (d->batch < 1 || d->OH != d->H || d->OW != d->W) return false;
-  if ((long long)d->batch * d->H * d->W < 16) return false;  // not worth a 128-row tile
+  if (d->batch < 1 || d->OH != d->H / d->stride || d->OW != d->W / d->stride) return false;
+  if ((long long)d->batch * d->OH * d->OW < 16) return false;  // not worth a 128-row tile
   return true;
 }
 
@@ -337,14 +340,14 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
 int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   TcArgs a;
   a.scale = d->scale, a.bias = d->bias, a.res = (const __half*)d->residual, a.out = (__half*)d->out;
-  a.H = d->H, a.W = d->W, a.Cin = d->Cin, a.Cout = d->Cout, a.out_ld = d->out_ld, a.res_ld = d->res_ld, a.relu = d->relu;
+  a.H = d->OH, a.W = d->OW, a.stride = d->stride, a.Cin = d->Cin, a.Cout = d->Cout, a.out_ld = d->out_ld, a.res_ld = d->res_ld, a.relu = d->relu;
   a.taps = d->KH * d->KW, a.KW = d->KW, a.pad = d->pad, a.cin_chunks = d->Cin / TC_BK;
   if (d->H == 1) {
     a.tile_w = 128, a.tile_h = 1;
   } else {
     a.tile_w = 16, a.tile_h = 8;
   }
-  a.tiles_w = ceil_div(d->W, a.tile_w), a.tiles_h = ceil_div(d->H, a.tile_h);
+  a.tiles_w = ceil_div(d->OW, a.tile_w), a.tiles_h = ceil_div(d->OH, a.tile_h);
   const long long tiles = (long long)a.tiles_w * a.tiles_h * d->batch;
   // BN: 128 unless that leaves most SMs idle
   const int BN = (d->Cout % 128 == 0 && tiles * (d->Cout / 128) >= 148) ? 128 : 64;
@@ -353,8 +356,10 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
     uint64_t str[3] = {(uint64_t)d->in_ld * 2, (uint64_t)d->W * d->in_ld * 2, (uint64_t)d->H * d->W * d->in_ld * 2};
-    uint32_t box[4] = {(uint32_t)TC_BK, (uint32_t)a.tile_w, (uint32_t)a.tile_h, 1u};
-    if (!encode_map(&tmA, d->in, 4, dims, str, box)) return SMOT_ERR_CUDA;
+    // stride-2 convs: the box is traversed with element stride 2 and still lands as tile_w x tile_h pixels
+    uint32_t box[4] = {(uint32_t)TC_BK, (uint32_t)(a.tile_w * d->stride), (uint32_t)(a.tile_h * d->stride), 1u};
+    uint32_t estr[4] = {1u, (uint32_t)d->stride, (uint32_t)d->stride, 1u};
+    if (!encode_map(&tmA, d->in, 4, dims, str, box, estr)) return SMOT_ERR_CUDA;
   }
   {
     const uint64_t K = (uint64_t)a.taps * d->Cin;

@@ -59,10 +59,11 @@ __global__ void __launch_bounds__(SN_THREADS) sort_nms_kernel(SortNmsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
   float4* sbox = reinterpret_cast<float4*>(smem_raw + (size_t)a.np * 8);
+  int* kept_all = reinterpret_cast<int*>(smem_raw + (size_t)a.np * 24);  // sorted row of the k-th survivor
   __shared__ unsigned long long removed[SN_MAX / 64];
   __shared__ unsigned long long diag[64];
   __shared__ int kept_rows[64];
-  __shared__ int s_m, s_kept;
+  __shared__ int s_m, s_kept, s_nk, s_done;
 
   const int prob = blockIdx.x;
   const float* boxes = a.boxes + (size_t)prob * a.in_step * a.box_stride;
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(SN_THREADS) sort_nms_kernel(SortNmsArgs a) {
   int* out_count = a.out_count + prob;
   const int n = a.count ? min(a.count[prob], a.n_max) : a.n_max;
 
-  if (threadIdx.x == 0) s_m = 0, s_kept = 0;
+  if (threadIdx.x == 0) s_m = 0, s_kept = 0, s_done = 0;
   __syncthreads();
   int local = 0;
   for (int i = threadIdx.x; i < a.np; i += blockDim.x) {
@@ -98,25 +99,10 @@ __global__ void __launch_bounds__(SN_THREADS) sort_nms_kernel(SortNmsArgs a) {
   __syncthreads();
 
   const int words = (m + 63) >> 6;
-  const int base = a.append ? *out_count : 0;
-  const int out_off = prob * a.out_step + base;
-  int* out_index = a.out_index ? a.out_index + out_off : nullptr;
-  float* out_boxes = a.out_boxes ? a.out_boxes + (size_t)out_off * 4 : nullptr;
-  float* out_scores = a.out_scores ? a.out_scores + out_off : nullptr;
-  int* out_tag = a.out_tag ? a.out_tag + out_off : nullptr;
-
-  auto emit = [&](int k, int row) {  // k-th survivor is sorted row `row`
-    const unsigned idx = 0xFFFFFFFFu - (unsigned)(keys[row] & 0xFFFFFFFFull);
-    if (out_index) out_index[k] = (int)idx;
-    if (out_boxes) reinterpret_cast<float4*>(out_boxes)[k] = sbox[row];
-    if (out_scores) out_scores[k] = scores[(size_t)idx * a.score_stride];
-    if (out_tag) out_tag[k] = a.tag;
-  };
-
   int kept_total;
   if (a.thresh <= 0.f || a.max_keep <= 0) {
     kept_total = max(min(m, a.max_keep), 0);
-    for (int i = threadIdx.x; i < kept_total; i += blockDim.x) emit(i, i);
+    for (int i = threadIdx.x; i < kept_total; i += blockDim.x) kept_all[i] = i;
   } else {
     // ---- suppression bitmask: mask[i][w] bit b set <=> j = 64w+b > i and IoU(i,j) > thresh
     for (int item = threadIdx.x; item < m * words; item += blockDim.x) {
@@ -125,60 +111,67 @@ __global__ void __launch_bounds__(SN_THREADS) sort_nms_kernel(SortNmsArgs a) {
       if (w >= (i >> 6)) {
         const float4 bi = sbox[i];
         const int j0 = w << 6, j1 = min(m, j0 + 64);
-        for (int j = max(j0, i + 1); j < j1; ++j)
-          if (iou_plus1(bi, sbox[j]) > a.thresh) bits |= 1ull << (j - j0);
+        for (int j = max(j0, i + 1); j < j1; ++j) {
+          const float4 bj = sbox[j];
+          // disjoint boxes have IoU 0: skip the division (same result, most pairs are disjoint)
+          if (fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x) + 1.f > 0.f && fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y) + 1.f > 0.f)
+            if (iou_plus1(bi, bj) > a.thresh) bits |= 1ull << (j - j0);
+        }
       }
       mask[(size_t)i * words + w] = bits;
     }
     __syncthreads();
-    // ---- reduction by warp 0, 64 rows at a time (two memory round trips per chunk)
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      int kept = 0;
-      bool done = false;
-      for (int c = 0; c < words && !done; ++c) {
-        for (int t = lane; t < 64; t += 32) {
-          const int row = (c << 6) + t;
-          diag[t] = row < m ? mask[(size_t)row * words + c] : 0ull;
-        }
-        __syncwarp();
+    // ---- reduction, 64 sorted rows per round: (A) stage the diagonal words, (B) one thread resolves the
+    //      round serially from registers, (C) the whole CTA ORs the survivors' rows into `removed`
+    for (int c = 0; c < words; ++c) {
+      if (threadIdx.x < 64) {
+        const int row = (c << 6) + threadIdx.x;
+        diag[threadIdx.x] = row < m ? mask[(size_t)row * words + c] : 0ull;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
         unsigned long long cur = removed[c];
-        int nk = 0;
-        for (int b = 0; b < 64; ++b) {
-          const int row = (c << 6) + b;
-          if (row >= m) break;
+        int kept = s_kept, nk = 0;
+        const int rows_here = min(64, m - (c << 6));
+        for (int b = 0; b < rows_here && kept + nk < a.max_keep; ++b) {
           if (!((cur >> b) & 1ull)) {
-            if (lane == 0) {
-              kept_rows[nk] = row;
-              emit(kept + nk, row);
-            }
+            kept_rows[nk] = (c << 6) + b;
+            kept_all[kept + nk] = (c << 6) + b;
             ++nk;
             cur |= diag[b];
-            if (kept + nk >= a.max_keep) {
-              done = true;
-              break;
-            }
           }
         }
-        __syncwarp();
-        if (!done) {
-          for (int w = c + 1 + lane; w < words; w += 32) {
-            unsigned long long acc = removed[w];
-            for (int q = 0; q < nk; ++q) acc |= mask[(size_t)kept_rows[q] * words + w];
-            removed[w] = acc;
-          }
-        }
-        kept += nk;
-        __syncwarp();
+        s_nk = nk;
+        s_kept = kept + nk;
+        if (kept + nk >= a.max_keep) s_done = 1;
       }
-      if (lane == 0) s_kept = kept;
+      __syncthreads();
+      if (s_done) break;
+      const int nk = s_nk, nw = words - c - 1;
+      for (int item = threadIdx.x; item < nk * nw; item += blockDim.x) {
+        const int qq = item / nw, w = c + 1 + (item - qq * nw);
+        const unsigned long long v = mask[(size_t)kept_rows[qq] * words + w];
+        if (v) atomicOr(&removed[w], v);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     kept_total = s_kept;
   }
+  __syncthreads();
+  // ---- outputs, all threads
+  const int base = a.append ? *out_count : 0;
+  const int out_off = prob * a.out_step + base;
+  for (int k = threadIdx.x; k < kept_total; k += blockDim.x) {
+    const int row = kept_all[k];
+    const unsigned idx = 0xFFFFFFFFu - (unsigned)(keys[row] & 0xFFFFFFFFull);
+    if (a.out_index) a.out_index[out_off + k] = (int)idx;
+    if (a.out_boxes) reinterpret_cast<float4*>(a.out_boxes)[out_off + k] = sbox[row];
+    if (a.out_scores) a.out_scores[out_off + k] = scores[(size_t)idx * a.score_stride];
+    if (a.out_tag) a.out_tag[out_off + k] = a.tag;
+  }
   // rows [kept, fill_tail) of this problem's output slot are marked invalid (score -1)
-  if (a.fill_tail > 0 && out_scores)
-    for (int i = kept_total + threadIdx.x; i < a.fill_tail - base; i += blockDim.x) out_scores[i] = -1.f;
+  if (a.fill_tail > 0 && a.out_scores)
+    for (int i = kept_total + threadIdx.x; i < a.fill_tail - base; i += blockDim.x) a.out_scores[out_off + i] = -1.f;
   __syncthreads();
   if (threadIdx.x == 0) *out_count = base + kept_total;
 }
@@ -191,10 +184,10 @@ static int next_pow2(int n) {
 
 static int launch_sort_nms(SortNmsArgs& a, int problems, cudaStream_t st) {
   a.np = next_pow2(a.n_max);
-  const size_t smem = (size_t)a.np * 24;
+  const size_t smem = (size_t)a.np * 28;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_MAX * 24);
+    cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_MAX * 28);
     if (e != cudaSuccess) {
       set_error("sort_nms: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return SMOT_ERR_CUDA;
@@ -239,9 +232,16 @@ __global__ void __launch_bounds__(1024) rpn_topk_kernel(const RpnArgs a) {
     __syncthreads();
     const unsigned prefix = s_prefix;
     const unsigned pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned key = float_key(logit_at(i));
-      if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {  // 8 independent loads in flight per thread
+      unsigned key[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        key[u] = i < n ? float_key(logit_at(i)) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * (int)blockDim.x < n && (key[u] & pmask) == prefix) atomicAdd(&hist[(key[u] >> shift) & 0xFFu], 1u);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -264,11 +264,20 @@ __global__ void __launch_bounds__(1024) rpn_topk_kernel(const RpnArgs a) {
   if (threadIdx.x == 0) s_cnt = 0u, s_eqbase = 0u;
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) cand[i] = 0ull;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const unsigned key = float_key(logit_at(i));
-    if (key > T || (all_eq && key == T)) {
-      unsigned pos = atomicAdd(&s_cnt, 1u);
-      cand[pos] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+  for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
+    unsigned key[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      key[u] = i < n ? float_key(logit_at(i)) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < n && (key[u] > T || (all_eq && key[u] == T))) {
+        unsigned pos = atomicAdd(&s_cnt, 1u);
+        cand[pos] = ((unsigned long long)key[u] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+      }
     }
   }
   __syncthreads();

@@ -393,3 +393,51 @@ def test_conv2d_tcgen05_channel_slices_and_fc():
         gotfc = ops().conv2d(xfc.to(DEV, dt).view(1, 1, rows, 6272), wfc.to(DEV, dt).view(1024, 1, 1, 6272), None,
                              bfc.to(DEV), relu=True, algo=_lib.CONV_TCGEN05)
         assert rel_err(gotfc.view(rows, 1024).float().cpu(), reffc) <= 2e-3
+
+
+@pytest.mark.parametrize("case", [(1, 64, 88, 160, 128), (1, 128, 44, 80, 256), (1, 256, 22, 40, 512), (2, 64, 32, 48, 64)])
+def test_conv2d_tcgen05_stride2(case):
+    """3x3 stride-2 convs of the DLA trees through the strided TMA box (elementStrides = 2)."""
+    from siammot_b200 import _lib
+    B, Cin, H, W, Cout = case
+    g = torch.Generator().manual_seed(Cin + W)
+    dt = torch.float16
+    x = q(torch.randn(B, Cin, H, W, generator=g), dt)
+    w = q(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9), dt)
+    scale, bias = 0.5 + torch.rand(Cout, generator=g), torch.randn(Cout, generator=g)
+    ref = F.relu(F.conv2d(x, w, None, 2, 1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    out = torch.empty((B, H // 2, W // 2, Cout), dtype=dt, device=DEV)
+    args = (nhwc(x, dt), ohwi(w, dt), scale.to(DEV), bias.to(DEV), None, 2, 1, True)
+    assert ops().conv2d_algo(args[0], args[1], out, scale=args[2], bias=args[3], stride=2, pad=1, relu=True) == _lib.CONV_TCGEN05
+    got = ops().conv2d(*args, algo=_lib.CONV_TCGEN05)
+    got_simt = ops().conv2d(*args, algo=_lib.CONV_SIMT)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(got), ref) <= 2e-3
+    assert rel_err(nchw(got), nchw(got_simt)) <= 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_conv2d_small_cout_kernel(dtype):
+    """Cout <= 16 layers (warp-per-pixel kernel): EMM heads 3x3 (3 / 4 outputs, input = channel slice of the
+    tower buffer), box predictor FC 1024 -> 10, RPN predictor 1x1 -> 15, all with fp32 outputs."""
+    g = torch.Generator().manual_seed(31)
+    tower = q(torch.randn(7, 256, 16, 16, generator=g), dtype)
+    dtower = nhwc(tower, dtype)
+    maps = torch.zeros(7, 16, 16, 8, dtype=torch.float32, device=DEV)
+    for (lo, hi, cout, off, relu) in ((0, 128, 3, 0, False), (128, 256, 4, 3, True)):
+        w = q(torch.randn(cout, 128, 3, 3, generator=g) / 34.0, dtype)
+        b = torch.randn(cout, generator=g)
+        ref = F.conv2d(tower[:, lo:hi], w, b, 1, 1)
+        ref = F.relu(ref) if relu else ref
+        ops().conv2d(dtower[..., lo:hi], ohwi(w, dtype), None, b.to(DEV), pad=1, relu=relu, out=maps[..., off:off + cout])
+        assert rel_err(nchw(maps[..., off:off + cout]), ref) <= tol(dtype)
+    assert float(maps[..., 7].abs().max()) == 0.0
+    for rows in (300, 30, 1):
+        x = q(torch.randn(rows, 1024, generator=g), dtype)
+        w = q(torch.randn(10, 1024, generator=g) / 32.0, dtype)
+        b = torch.randn(10, generator=g)
+        out = torch.zeros(1, 1, rows, 12, dtype=torch.float32, device=DEV)
+        ops().conv2d(x.to(DEV, dtype).view(1, 1, rows, 1024), w.to(DEV, dtype).view(10, 1, 1, 1024), None, b.to(DEV),
+                     out=out[..., :10])
+        assert rel_err(out[0, 0, :, :10].cpu(), F.linear(x, w, b)) <= tol(dtype)
+        assert float(out[..., 10:].abs().max()) == 0.0
