@@ -161,7 +161,7 @@ def kernels_per_frame(h):
         n += _lib.KERNELS_PER_CALL.get(name, 0) if name else 0
     # dynamic: sr roi_align, xcorr, towers conv, groupnorm, 2 head convs, decode(2), refine(roi_align, 3 conv, decode),
     # solver sort_nms, template roi_align
-    n += 1 + 1 + 1 + 1 + 2 + 2 + 5 + 1 + 1
+    n += 1 + 1 + 1 + 1 + 2 + 2 + 5 + 1 + 3 + 1
     return n
 
 

@@ -38,8 +38,8 @@ _lib = None
 
 # kernels launched by one call of each entry point (memsets not counted); used for bench.py's gpu_launches
 KERNELS_PER_CALL = {"smot_conv2d": 1, "smot_image_to_nhwc": 1, "smot_maxpool2x2": 1, "smot_upsample_add": 1,
-                    "smot_subsample2": 1, "smot_groupnorm_relu": 1, "smot_roi_align": 1, "smot_rpn_select": 3,
-                    "smot_sort_nms": 1, "smot_box_decode": 1, "smot_track_combine": 1, "smot_xcorr": 1, "smot_emm_decode": 2}
+                    "smot_subsample2": 1, "smot_groupnorm_relu": 1, "smot_roi_align": 1, "smot_rpn_select": 7,
+                    "smot_sort_nms": 3, "smot_box_decode": 1, "smot_track_combine": 1, "smot_xcorr": 1, "smot_emm_decode": 2}
 
 
 def _declare(lib):

@@ -1,13 +1,17 @@
 // Device-resident proposal selection, sorting and NMS.
 //
 // The reference does these steps with ~10 tiny ATen kernels plus a device->host copy of the NMS mask
-// and a serial host loop per call (upstream csrc/cuda/nms.cu), seven times per frame.  Here each is
-// one kernel with on-device reduction, so the whole detection stage stays capturable in a CUDA graph.
+// and a serial host loop per call (upstream csrc/cuda/nms.cu), seven times per frame.  Here every step
+// stays on the device (fixed capacities, device-side counts), so the whole detection stage is
+// capturable in a CUDA graph.  A single CTA is far too slow for the O(n^2) / O(n) parts, so each job is
+// split so that the quadratic / linear work spreads over many SMs and only O(n) bookkeeping is serial:
 //
-//   sort_nms_kernel : 64-bit composite keys (score key << 32 | ~index) -> bitonic sort in shared
-//                     memory -> 64-wide bitmask IoU(+1) matrix -> chunked warp reduction.
-//   rpn_topk_kernel : per FPN level, radix select of the top-k objectness logits, sort, anchor
-//                     synthesis + BoxCoder decode + clip  (rpn_patch.py:15-52).
+//   sort + NMS   : nms_sort_kernel   (1 CTA / problem)  64-bit keys (score key << 32 | ~index), bitonic sort
+//                  nms_mask_kernel   (n/64 CTAs / problem) IoU(+1) bitmask, lane = candidate, word = ballot
+//                  nms_reduce_kernel (1 CTA / problem)  64 sorted rows per round: serial resolve + CTA-wide OR
+//   RPN top-k    : rpn_local_topk_kernel (1 CTA / ~10k anchors) exact local top-k by 64-bit radix select
+//                  rpn_merge_kernel      (1 CTA / level) top-k of the local winners, sort, anchor synthesis +
+//                                        BoxCoder decode + clip  (rpn_patch.py:15-52)
 //   box_decode_kernel: softmax + per-class decode + clip + track-row rule (inference.py:58-110).
 #include "common.cuh"
 
@@ -31,9 +35,14 @@ struct SortNmsArgs {
   float* out_scores;
   int* out_tag;
   int* out_count;
-  unsigned long long* mask;  // [n_max][ceil(n_max/64)]
-  // batching (blockIdx.x = problem): element offsets added per problem
-  int in_step, out_step, mask_step;
+  // workspace (per problem p): sorted boxes / original indices / number of candidates / bitmask
+  float4* s_boxes;             // [P][n_max]
+  int* s_index;                // [P][n_max]
+  int* s_m;                    // [P]
+  unsigned long long* mask;    // [P][n_max][words_max], words_max = ceil(n_max / 64)
+  int words_max;
+  // batching (blockIdx = problem): element offsets added per problem
+  int in_step, out_step;
 };
 
 __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int np) {
@@ -55,24 +64,16 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int 
   }
 }
 
-__global__ void __launch_bounds__(SN_THREADS) sort_nms_kernel(SortNmsArgs a) {
+// ---- K1: order the candidates -----------------------------------------------------------------
+__global__ void __launch_bounds__(SN_THREADS) nms_sort_kernel(SortNmsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
-  float4* sbox = reinterpret_cast<float4*>(smem_raw + (size_t)a.np * 8);
-  int* kept_all = reinterpret_cast<int*>(smem_raw + (size_t)a.np * 24);  // sorted row of the k-th survivor
-  __shared__ unsigned long long removed[SN_MAX / 64];
-  __shared__ unsigned long long diag[64];
-  __shared__ int kept_rows[64];
-  __shared__ int s_m, s_kept, s_nk, s_done;
-
+  __shared__ int s_cnt;
   const int prob = blockIdx.x;
   const float* boxes = a.boxes + (size_t)prob * a.in_step * a.box_stride;
   const float* scores = a.scores + (size_t)prob * a.in_step * a.score_stride;
-  unsigned long long* mask = a.mask + (size_t)prob * a.mask_step;
-  int* out_count = a.out_count + prob;
   const int n = a.count ? min(a.count[prob], a.n_max) : a.n_max;
-
-  if (threadIdx.x == 0) s_m = 0, s_kept = 0, s_done = 0;
+  if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   int local = 0;
   for (int i = threadIdx.x; i < a.np; i += blockDim.x) {
@@ -86,47 +87,86 @@ __global__ void __launch_bounds__(SN_THREADS) sort_nms_kernel(SortNmsArgs a) {
     }
     keys[i] = key;
   }
-  if (local) atomicAdd(&s_m, local);
+  if (local) atomicAdd(&s_cnt, local);
   __syncthreads();
   bitonic_sort_desc(keys, a.np);
-  const int m = s_m;
+  const int m = s_cnt;
+  float4* sb = a.s_boxes + (size_t)prob * a.n_max;
+  int* si = a.s_index + (size_t)prob * a.n_max;
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
     const unsigned idx = 0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFull);
     const float* b = boxes + (size_t)idx * a.box_stride;
-    sbox[i] = make_float4(b[0], b[1], b[2], b[3]);
+    sb[i] = make_float4(b[0], b[1], b[2], b[3]);
+    si[i] = (int)idx;
   }
+  if (threadIdx.x == 0) a.s_m[prob] = m;
+}
+
+// ---- K2: suppression bitmask, mask[i][w] bit b set <=> j = 64w+b > i and IoU(i,j) > thresh -------
+//      grid (row blocks of 64, problems); one warp per (i, w) word: lane = candidate j (two rounds of 32)
+__global__ void __launch_bounds__(256) nms_mask_kernel(SortNmsArgs a) {
+  const int prob = blockIdx.y;
+  const int m = a.s_m[prob];
+  const int i0 = blockIdx.x * 64;
+  if (i0 >= m) return;
+  const int words = (m + 63) >> 6;
+  const float4* __restrict__ sb = a.s_boxes + (size_t)prob * a.n_max;
+  unsigned long long* mask = a.mask + (size_t)prob * a.n_max * a.words_max;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int w_lo = i0 >> 6;  // words left of the diagonal block are all zero and never read
+  const int nw = words - w_lo;
+  for (int item = wid; item < 64 * nw; item += 8) {
+    const int i = i0 + item / nw, w = w_lo + item % nw;
+    if (i >= m) break;
+    const float4 bi = sb[i];
+    unsigned lo = 0u, hi = 0u;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int j = (w << 6) + half * 32 + lane;
+      bool hit = false;
+      if (j > i && j < m) {
+        const float4 bj = sb[j];
+        // disjoint boxes have IoU 0: skip the division (same result, most pairs are disjoint)
+        if (fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x) + 1.f > 0.f && fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y) + 1.f > 0.f)
+          hit = iou_plus1(bi, bj) > a.thresh;
+      }
+      const unsigned b = __ballot_sync(0xffffffffu, hit);
+      if (half == 0) lo = b; else hi = b;
+    }
+    if (lane == 0) mask[(size_t)i * a.words_max + w] = ((unsigned long long)hi << 32) | lo;
+  }
+}
+
+// ---- K3: greedy reduction + outputs ------------------------------------------------------------
+__global__ void __launch_bounds__(SN_THREADS) nms_reduce_kernel(SortNmsArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* kept_all = reinterpret_cast<int*>(smem_raw);  // sorted row of the k-th survivor, [np]
+  __shared__ unsigned long long removed[SN_MAX / 64];
+  __shared__ unsigned long long diag[64];
+  __shared__ int kept_rows[64];
+  __shared__ int s_kept, s_nk, s_done;
+  const int prob = blockIdx.x;
+  const float* scores = a.scores + (size_t)prob * a.in_step * a.score_stride;
+  const float4* __restrict__ sb = a.s_boxes + (size_t)prob * a.n_max;
+  const int* __restrict__ si = a.s_index + (size_t)prob * a.n_max;
+  const unsigned long long* mask = a.mask + (size_t)prob * a.n_max * a.words_max;
+  int* out_count = a.out_count + prob;
+  const int m = a.s_m[prob];
+  const int words = (m + 63) >> 6;
+  if (threadIdx.x == 0) s_kept = 0, s_done = 0;
   for (int i = threadIdx.x; i < SN_MAX / 64; i += blockDim.x) removed[i] = 0ull;
   __syncthreads();
-
-  const int words = (m + 63) >> 6;
   int kept_total;
   if (a.thresh <= 0.f || a.max_keep <= 0) {
     kept_total = max(min(m, a.max_keep), 0);
     for (int i = threadIdx.x; i < kept_total; i += blockDim.x) kept_all[i] = i;
   } else {
-    // ---- suppression bitmask: mask[i][w] bit b set <=> j = 64w+b > i and IoU(i,j) > thresh
-    for (int item = threadIdx.x; item < m * words; item += blockDim.x) {
-      const int i = item / words, w = item - i * words;
-      unsigned long long bits = 0ull;
-      if (w >= (i >> 6)) {
-        const float4 bi = sbox[i];
-        const int j0 = w << 6, j1 = min(m, j0 + 64);
-        for (int j = max(j0, i + 1); j < j1; ++j) {
-          const float4 bj = sbox[j];
-          // disjoint boxes have IoU 0: skip the division (same result, most pairs are disjoint)
-          if (fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x) + 1.f > 0.f && fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y) + 1.f > 0.f)
-            if (iou_plus1(bi, bj) > a.thresh) bits |= 1ull << (j - j0);
-        }
-      }
-      mask[(size_t)i * words + w] = bits;
-    }
-    __syncthreads();
-    // ---- reduction, 64 sorted rows per round: (A) stage the diagonal words, (B) one thread resolves the
-    //      round serially from registers, (C) the whole CTA ORs the survivors' rows into `removed`
+    // 64 sorted rows per round: (A) stage the diagonal words, (B) one thread resolves the round serially,
+    // (C) the whole CTA ORs the survivors' rows into `removed`
     for (int c = 0; c < words; ++c) {
       if (threadIdx.x < 64) {
         const int row = (c << 6) + threadIdx.x;
-        diag[threadIdx.x] = row < m ? mask[(size_t)row * words + c] : 0ull;
+        diag[threadIdx.x] = row < m ? mask[(size_t)row * a.words_max + c] : 0ull;
       }
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -150,7 +190,7 @@ __global__ void __launch_bounds__(SN_THREADS) sort_nms_kernel(SortNmsArgs a) {
       const int nk = s_nk, nw = words - c - 1;
       for (int item = threadIdx.x; item < nk * nw; item += blockDim.x) {
         const int qq = item / nw, w = c + 1 + (item - qq * nw);
-        const unsigned long long v = mask[(size_t)kept_rows[qq] * words + w];
+        const unsigned long long v = mask[(size_t)kept_rows[qq] * a.words_max + w];
         if (v) atomicOr(&removed[w], v);
       }
       __syncthreads();
@@ -158,14 +198,13 @@ __global__ void __launch_bounds__(SN_THREADS) sort_nms_kernel(SortNmsArgs a) {
     kept_total = s_kept;
   }
   __syncthreads();
-  // ---- outputs, all threads
   const int base = a.append ? *out_count : 0;
   const int out_off = prob * a.out_step + base;
   for (int k = threadIdx.x; k < kept_total; k += blockDim.x) {
     const int row = kept_all[k];
-    const unsigned idx = 0xFFFFFFFFu - (unsigned)(keys[row] & 0xFFFFFFFFull);
-    if (a.out_index) a.out_index[out_off + k] = (int)idx;
-    if (a.out_boxes) reinterpret_cast<float4*>(a.out_boxes)[out_off + k] = sbox[row];
+    const int idx = si[row];
+    if (a.out_index) a.out_index[out_off + k] = idx;
+    if (a.out_boxes) reinterpret_cast<float4*>(a.out_boxes)[out_off + k] = sb[row];
     if (a.out_scores) a.out_scores[out_off + k] = scores[(size_t)idx * a.score_stride];
     if (a.out_tag) a.out_tag[out_off + k] = a.tag;
   }
@@ -182,132 +221,165 @@ static int next_pow2(int n) {
   return p;
 }
 
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t sort_nms_ws_bytes(int problems, int n_max) {
+  const size_t P = (size_t)problems, n = (size_t)n_max, words = (n + 63) / 64;
+  return align256(P * n * 16) + align256(P * n * 4) + align256(P * 4) + align256(P * n * words * 8);
+}
+
+static void carve_sort_nms_ws(SortNmsArgs& a, void* ws, int problems) {
+  const size_t P = (size_t)problems, n = (size_t)a.n_max;
+  unsigned char* w = (unsigned char*)ws;
+  a.s_boxes = (float4*)w;            w += align256(P * n * 16);
+  a.s_index = (int*)w;               w += align256(P * n * 4);
+  a.s_m = (int*)w;                   w += align256(P * 4);
+  a.mask = (unsigned long long*)w;
+  a.words_max = (a.n_max + 63) / 64;
+}
+
 static int launch_sort_nms(SortNmsArgs& a, int problems, cudaStream_t st) {
   a.np = next_pow2(a.n_max);
-  const size_t smem = (size_t)a.np * 28;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_MAX * 28);
+    cudaError_t e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_MAX * 8);
     if (e != cudaSuccess) {
       set_error("sort_nms: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return SMOT_ERR_CUDA;
     }
     attr_set = true;
   }
-  sort_nms_kernel<<<problems, SN_THREADS, smem, st>>>(a);
-  SMOT_CHECK_LAUNCH("sort_nms");
+  nms_sort_kernel<<<problems, SN_THREADS, (size_t)a.np * 8, st>>>(a);
+  SMOT_CHECK_LAUNCH("sort_nms(sort)");
+  if (a.thresh > 0.f && a.max_keep > 0) {
+    nms_mask_kernel<<<dim3((a.n_max + 63) / 64, problems), 256, 0, st>>>(a);
+    SMOT_CHECK_LAUNCH("sort_nms(mask)");
+  }
+  nms_reduce_kernel<<<problems, SN_THREADS, (size_t)a.np * 4, st>>>(a);
+  SMOT_CHECK_LAUNCH("sort_nms(reduce)");
   return SMOT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // RPN: per-level top-k by objectness logit + decode
 // ---------------------------------------------------------------------------------------------
+constexpr int RPN_CHUNK = 10752;   // anchors per local-top-k CTA (level 0 of a 704x1280 frame = 16 chunks)
+constexpr int RPN_MAX_CHUNKS = 256;
+
 struct RpnArgs {
   smot_rpn_level lv[SMOT_MAX_LEVELS];
   int pre_nms_top_n;  // <= 1024
   float min_size;
   int img_w, img_h, amodal;
-  float* cand_boxes;   // [levels][pre_nms_top_n][4]
-  float* cand_scores;  // [levels][pre_nms_top_n]
-  int* cand_count;     // [levels]
+  int nchunks;
+  int chunk_first[SMOT_MAX_LEVELS + 1];  // chunks of level l are [chunk_first[l], chunk_first[l+1])
+  unsigned long long* local;             // [nchunks][1024] composite keys of the local winners (0 = empty)
+  float* cand_boxes;                     // [levels][pre_nms_top_n][4]
+  float* cand_scores;                    // [levels][pre_nms_top_n]
+  int* cand_count;                       // [levels]
 };
 
-__global__ void __launch_bounds__(1024) rpn_topk_kernel(const RpnArgs a) {
-  const smot_rpn_level& L = a.lv[blockIdx.x];
-  const int n = L.H * L.W * L.A;
-  const int k = min(a.pre_nms_top_n, n);
-  __shared__ unsigned long long cand[1024];
+// Exact top-k of n UNIQUE 64-bit keys by radix select (8 bits per pass, MSB first).  get(i) returns the key of
+// element i (0 for "absent").  The k winners are written to out[0..k) in arbitrary order, out[k..1024) = 0.
+// All threads of the CTA must call this; n, k uniform; k <= 1024.
+template <typename GetKey>
+__device__ void select_topk_u64(GetKey get, int n, int k, unsigned long long* out) {
   __shared__ unsigned hist[256];
-  __shared__ unsigned s_prefix, s_need, s_cnt, s_eqbase, s_numeq;
-  __shared__ unsigned warp_tot[32];
-  const float* __restrict__ head = L.head;
-  auto logit_at = [&](int i) -> float { return head[(size_t)(i / L.A) * L.head_ld + (i % L.A)]; };
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned s_need, s_cnt;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) out[i] = 0ull;
+  if (threadIdx.x == 0) s_prefix = 0ull, s_need = (unsigned)k, s_cnt = 0u;
+  __syncthreads();
+  if (k > 0 && n > 0) {
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      const unsigned long long pmask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+      for (int b0 = 0; b0 < n; b0 += 4 * blockDim.x) {  // block-uniform trip count, 4 loads in flight
+        unsigned long long key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = b0 + u * blockDim.x + threadIdx.x;
+          key[u] = i < n ? get(i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          // warp-aggregated: scores cluster in a few bins, one atomic per distinct bin per warp
+          const bool act = key[u] != 0ull && (key[u] & pmask) == prefix;
+          const unsigned bin = act ? (unsigned)((key[u] >> shift) & 0xFFull) : 0xFFFFFFFFu;
+          const unsigned peers = __match_any_sync(0xffffffffu, bin);
+          if (act && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned need = s_need, cum = 0u;
+        int b = 255;
+        for (; b > 0; --b) {
+          if (cum + hist[b] >= need) break;
+          cum += hist[b];
+        }
+        s_need = need - cum;
+        s_prefix = prefix | ((unsigned long long)b << shift);
+      }
+      __syncthreads();
+      // fewer than k present keys: the threshold collapses to 0 and everything present is taken
+    }
+    const unsigned long long T = s_prefix;  // the k-th largest key (0 if fewer than k keys exist)
+    for (int b0 = 0; b0 < n; b0 += blockDim.x) {
+      const int i = b0 + threadIdx.x;
+      const unsigned long long key = i < n ? get(i) : 0ull;
+      if (key != 0ull && key >= T) {
+        const unsigned pos = atomicAdd(&s_cnt, 1u);
+        if (pos < 1024u) out[pos] = key;
+      }
+    }
+  }
+  __syncthreads();
+}
 
-  // ---- radix select (MSB first, 8 bits per pass) of the k-th largest key
-  if (threadIdx.x == 0) s_prefix = 0u, s_need = (unsigned)k;
-  __syncthreads();
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+__global__ void __launch_bounds__(1024) rpn_local_topk_kernel(const RpnArgs a) {
+  __shared__ unsigned long long win[1024];
+  int lvl = 0;
+  while (lvl + 1 < SMOT_MAX_LEVELS && (int)blockIdx.x >= a.chunk_first[lvl + 1]) ++lvl;
+  const smot_rpn_level& L = a.lv[lvl];
+  const int start = ((int)blockIdx.x - a.chunk_first[lvl]) * RPN_CHUNK;
+  const int count = min(RPN_CHUNK, L.H * L.W * L.A - start);
+  const int k = min(a.pre_nms_top_n, count);
+  const float* __restrict__ head = L.head;
+  const int A = L.A, ld = L.head_ld;
+  auto get = [&](int i) -> unsigned long long {
+    const int g = start + i;  // anchor index within the level: (cell * A + a)
+    const float logit = head[(size_t)(g / A) * ld + (g % A)];
+    return ((unsigned long long)float_key(logit) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)g);
+  };
+  select_topk_u64(get, count, k, win);
+  unsigned long long* dst = a.local + (size_t)blockIdx.x * 1024;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = win[i];
+}
+
+__global__ void __launch_bounds__(1024) rpn_merge_kernel(const RpnArgs a) {
+  __shared__ unsigned long long cand[1024];
+  const int lvl = blockIdx.x;
+  const smot_rpn_level& L = a.lv[lvl];
+  const int c0 = a.chunk_first[lvl], c1 = a.chunk_first[lvl + 1];
+  const int n = (c1 - c0) * 1024;
+  const int total = L.H * L.W * L.A;
+  const int k = min(a.pre_nms_top_n, total);
+  const unsigned long long* __restrict__ src = a.local + (size_t)c0 * 1024;
+  if (c1 - c0 == 1) {
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) cand[i] = src[i];
     __syncthreads();
-    const unsigned prefix = s_prefix;
-    const unsigned pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {  // 8 independent loads in flight per thread
-      unsigned key[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * blockDim.x;
-        key[u] = i < n ? float_key(logit_at(i)) : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (i0 + u * (int)blockDim.x < n && (key[u] & pmask) == prefix) atomicAdd(&hist[(key[u] >> shift) & 0xFFu], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned need = s_need, cum = 0u;
-      int b = 255;
-      for (; b > 0; --b) {
-        if (cum + hist[b] >= need) break;
-        cum += hist[b];
-      }
-      s_need = need - cum;  // still needed among keys sharing the extended prefix
-      s_prefix = prefix | ((unsigned)b << shift);
-      s_numeq = hist[b];    // after the last pass: how many keys equal the k-th key
-    }
-    __syncthreads();
+  } else {
+    select_topk_u64([&](int i) -> unsigned long long { return src[i]; }, n, k, cand);
   }
-  const unsigned T = s_prefix;      // k-th largest key
-  const unsigned need_eq = s_need;  // how many keys == T belong to the top-k
-  const bool all_eq = s_numeq == need_eq;  // no surplus ties: every key == T is taken, order irrelevant
-  // ---- collect: keys > T in any order, keys == T lowest index first
-  if (threadIdx.x == 0) s_cnt = 0u, s_eqbase = 0u;
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) cand[i] = 0ull;
-  __syncthreads();
-  for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
-    unsigned key[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = i0 + u * blockDim.x;
-      key[u] = i < n ? float_key(logit_at(i)) : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = i0 + u * blockDim.x;
-      if (i < n && (key[u] > T || (all_eq && key[u] == T))) {
-        unsigned pos = atomicAdd(&s_cnt, 1u);
-        cand[pos] = ((unsigned long long)key[u] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
-      }
-    }
-  }
-  __syncthreads();
-  const unsigned n_gt = s_cnt;
-  for (int i0 = 0; i0 < n && !all_eq; i0 += blockDim.x) {  // ordered pass over surplus ties (block scan per chunk)
-    const int i = i0 + threadIdx.x;
-    const bool eq = i < n && float_key(logit_at(i)) == T;
-    const unsigned bal = __ballot_sync(0xffffffffu, eq);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) warp_tot[wid] = __popc(bal);
-    __syncthreads();
-    unsigned before = s_eqbase;
-    for (int w = 0; w < wid; ++w) before += warp_tot[w];
-    const unsigned pos = before + __popc(bal & ((1u << lane) - 1u));
-    if (eq && pos < need_eq)
-      cand[n_gt + pos] = ((unsigned long long)T << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned tot = 0u;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += warp_tot[w];
-      s_eqbase += tot;
-    }
-    __syncthreads();
-    if (s_eqbase >= need_eq) break;
-  }
-  __syncthreads();
   bitonic_sort_desc(cand, 1024);
   // ---- decode the k candidates in sorted order
-  float* cb = a.cand_boxes + (size_t)blockIdx.x * a.pre_nms_top_n * 4;
-  float* cs = a.cand_scores + (size_t)blockIdx.x * a.pre_nms_top_n;
+  const float* __restrict__ head = L.head;
+  float* cb = a.cand_boxes + (size_t)lvl * a.pre_nms_top_n * 4;
+  float* cs = a.cand_scores + (size_t)lvl * a.pre_nms_top_n;
   for (int j = threadIdx.x; j < a.pre_nms_top_n; j += blockDim.x) {
     if (j >= k) {
       cs[j] = -1.f;
@@ -339,7 +411,7 @@ __global__ void __launch_bounds__(1024) rpn_topk_kernel(const RpnArgs a) {
     reinterpret_cast<float4*>(cb)[j] = make_float4(x1, y1, x2, y2);
     cs[j] = big ? score : -1.f;
   }
-  if (threadIdx.x == 0) a.cand_count[blockIdx.x] = k;
+  if (threadIdx.x == 0) a.cand_count[lvl] = k;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -434,7 +506,7 @@ extern "C" int smot_track_combine(const float* det_boxes, const float* det_score
 
 extern "C" size_t smot_sort_nms_workspace(int n_max) {
   if (n_max <= 0) return 0;
-  return (size_t)n_max * ((n_max + 63) / 64) * sizeof(unsigned long long);
+  return sort_nms_ws_bytes(1, n_max);
 }
 
 extern "C" int smot_sort_nms(const float* boxes, int box_stride, const float* scores, int score_stride, const int* count,
@@ -445,31 +517,37 @@ extern "C" int smot_sort_nms(const float* boxes, int box_stride, const float* sc
   SMOT_CHECK_ARG(n_max >= 0 && n_max <= SN_MAX, "smot_sort_nms: n_max %d out of range [0,%d]", n_max, SN_MAX);
   if (n_max == 0) return SMOT_OK;
   SMOT_CHECK_ARG(boxes && scores && box_stride >= 4 && score_stride >= 1 && max_keep >= 0, "smot_sort_nms: bad arguments");
-  SMOT_CHECK_ARG(thresh <= 0.f || (workspace && workspace_bytes >= smot_sort_nms_workspace(n_max)),
-                 "smot_sort_nms: workspace too small (%zu < %zu)", workspace_bytes, smot_sort_nms_workspace(n_max));
+  SMOT_CHECK_ARG(workspace && workspace_bytes >= smot_sort_nms_workspace(n_max), "smot_sort_nms: workspace too small (%zu < %zu)",
+                 workspace_bytes, smot_sort_nms_workspace(n_max));
   SortNmsArgs a;
   a.boxes = boxes, a.box_stride = box_stride, a.scores = scores, a.score_stride = score_stride, a.count = count;
   a.n_max = n_max, a.min_score = min_score, a.thresh = thresh, a.max_keep = max_keep, a.tag = tag;
   a.append = 1, a.fill_tail = 0;
   a.out_index = out_index, a.out_boxes = out_boxes, a.out_scores = out_scores, a.out_tag = out_tag, a.out_count = out_count;
-  a.mask = (unsigned long long*)workspace;
-  a.in_step = 0, a.out_step = 0, a.mask_step = 0;
+  a.in_step = 0, a.out_step = 0;
+  carve_sort_nms_ws(a, workspace, 1);
   return launch_sort_nms(a, 1, (cudaStream_t)stream);
 }
 
-static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static int rpn_chunk_count(const smot_rpn_level* levels, int num_levels) {
+  int n = 0;
+  for (int l = 0; l < num_levels; ++l) n += (levels[l].H * levels[l].W * levels[l].A + RPN_CHUNK - 1) / RPN_CHUNK;
+  return n;
+}
 
 extern "C" size_t smot_rpn_select_workspace(int num_levels, int pre_nms_top_n) {
   if (num_levels <= 0 || pre_nms_top_n <= 0) return 0;
   const size_t L = (size_t)num_levels, P = (size_t)pre_nms_top_n;
   size_t b = 0;
-  b += align256(L * P * 16);                 // cand_boxes
-  b += align256(L * P * 4);                  // cand_scores
-  b += align256(L * 4);                      // cand_count
-  b += align256(L * P * 16);                 // kept boxes per level
-  b += align256(L * P * 4);                  // kept scores per level
-  b += align256(L * 4);                      // kept count per level
-  b += align256(L * P * ((P + 63) / 64) * 8);  // nms masks
+  b += align256(L * P * 16);                         // cand_boxes
+  b += align256(L * P * 4);                          // cand_scores
+  b += align256(L * 4);                              // cand_count
+  b += align256(L * P * 16);                         // kept boxes per level
+  b += align256(L * P * 4);                          // kept scores per level
+  b += align256(L * 4);                              // kept count per level
+  b += align256((size_t)RPN_MAX_CHUNKS * 1024 * 8);  // local winners
+  b += sort_nms_ws_bytes(num_levels, pre_nms_top_n); // per-level NMS
+  b += sort_nms_ws_bytes(1, num_levels * pre_nms_top_n);  // cross-level sort
   return b;
 }
 
@@ -487,6 +565,8 @@ extern "C" int smot_rpn_select(const smot_rpn_level* levels, int num_levels, int
     SMOT_CHECK_ARG(levels[l].head && levels[l].A >= 1 && levels[l].A <= SMOT_MAX_ANCHORS && levels[l].H > 0 && levels[l].W > 0 &&
                        levels[l].head_ld >= 5 * levels[l].A,
                    "smot_rpn_select: bad level %d", l);
+  const int nchunks = rpn_chunk_count(levels, num_levels);
+  SMOT_CHECK_ARG(nchunks <= RPN_MAX_CHUNKS, "smot_rpn_select: feature maps too large (%d chunks > %d)", nchunks, RPN_MAX_CHUNKS);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t L = (size_t)num_levels, P = (size_t)pre_nms_top_n;
   unsigned char* w = (unsigned char*)workspace;
@@ -496,28 +576,42 @@ extern "C" int smot_rpn_select(const smot_rpn_level* levels, int num_levels, int
   float* kept_boxes = (float*)w;   w += align256(L * P * 16);
   float* kept_scores = (float*)w;  w += align256(L * P * 4);
   int* kept_count = (int*)w;       w += align256(L * 4);
-  unsigned long long* mask = (unsigned long long*)w;
+  unsigned long long* local = (unsigned long long*)w; w += align256((size_t)RPN_MAX_CHUNKS * 1024 * 8);
+  void* ws_level = w;              w += sort_nms_ws_bytes(num_levels, pre_nms_top_n);
+  void* ws_merge = w;
 
   RpnArgs ra;
-  for (int l = 0; l < num_levels; ++l) ra.lv[l] = levels[l];
+  int nc = 0;
+  for (int l = 0; l < SMOT_MAX_LEVELS; ++l) {
+    ra.chunk_first[l] = nc;
+    if (l < num_levels) {
+      ra.lv[l] = levels[l];
+      nc += (levels[l].H * levels[l].W * levels[l].A + RPN_CHUNK - 1) / RPN_CHUNK;
+    }
+  }
+  ra.chunk_first[SMOT_MAX_LEVELS] = nc;
+  ra.nchunks = nc, ra.local = local;
   ra.pre_nms_top_n = pre_nms_top_n, ra.min_size = min_size, ra.img_w = img_w, ra.img_h = img_h, ra.amodal = amodal;
   ra.cand_boxes = cand_boxes, ra.cand_scores = cand_scores, ra.cand_count = cand_count;
-  rpn_topk_kernel<<<num_levels, 1024, 0, st>>>(ra);
-  SMOT_CHECK_LAUNCH("smot_rpn_select(topk)");
+  cudaError_t e;
+  rpn_local_topk_kernel<<<nc, 1024, 0, st>>>(ra);
+  SMOT_CHECK_LAUNCH("smot_rpn_select(local top-k)");
+  rpn_merge_kernel<<<num_levels, 1024, 0, st>>>(ra);
+  SMOT_CHECK_LAUNCH("smot_rpn_select(merge)");
 
-  // per-level NMS (one CTA per level), survivors into slots of post_nms_top_n rows, tails marked -1
+  // per-level NMS, survivors into slots of post_nms_top_n rows, tails marked -1
   SortNmsArgs a;
   a.boxes = cand_boxes, a.box_stride = 4, a.scores = cand_scores, a.score_stride = 1, a.count = cand_count;
   a.n_max = pre_nms_top_n, a.min_score = -0.5f, a.thresh = nms_thresh, a.max_keep = post_nms_top_n, a.tag = 0;
   a.append = 0, a.fill_tail = post_nms_top_n;
   a.out_index = nullptr, a.out_boxes = kept_boxes, a.out_scores = kept_scores, a.out_tag = nullptr, a.out_count = kept_count;
-  a.mask = mask;
-  a.in_step = pre_nms_top_n, a.out_step = post_nms_top_n, a.mask_step = (int)(P * ((P + 63) / 64));
+  a.in_step = pre_nms_top_n, a.out_step = post_nms_top_n;
+  carve_sort_nms_ws(a, ws_level, num_levels);
   int rc = launch_sort_nms(a, num_levels, st);
   if (rc) return rc;
 
   // cross-level top-k (sort only), level-major order among equal scores
-  cudaError_t e = cudaMemsetAsync(out_count, 0, sizeof(int), st);
+  e = cudaMemsetAsync(out_count, 0, sizeof(int), st);
   if (e != cudaSuccess) {
     set_error("smot_rpn_select: memset failed: %s", cudaGetErrorString(e));
     return SMOT_ERR_CUDA;
@@ -527,7 +621,8 @@ extern "C" int smot_rpn_select(const smot_rpn_level* levels, int num_levels, int
   m.n_max = num_levels * post_nms_top_n, m.min_score = -0.5f, m.thresh = 0.f, m.max_keep = fpn_post_nms_top_n, m.tag = 0;
   m.append = 1, m.fill_tail = 0;
   m.out_index = nullptr, m.out_boxes = out_boxes, m.out_scores = out_scores, m.out_tag = nullptr, m.out_count = out_count;
-  m.mask = nullptr, m.in_step = 0, m.out_step = 0, m.mask_step = 0;
+  m.in_step = 0, m.out_step = 0;
+  carve_sort_nms_ws(m, ws_merge, 1);
   return launch_sort_nms(m, 1, st);
 }
 
