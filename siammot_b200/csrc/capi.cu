@@ -18,6 +18,8 @@ void set_error(const char* fmt, ...) {
 int conv2d_simt(const smot_conv_desc* d, cudaStream_t st);
 int conv2d_tc(const smot_conv_desc* d, cudaStream_t st);
 bool conv2d_tc_supported(const smot_conv_desc* d);
+int conv2d_hires(const smot_conv_desc* d, cudaStream_t st);
+bool conv2d_hires_supported(const smot_conv_desc* d);
 int conv2d_smalln(const smot_conv_desc* d, cudaStream_t st);
 bool conv2d_smalln_supported(const smot_conv_desc* d);
 
@@ -59,6 +61,7 @@ extern "C" int smot_conv2d(const smot_conv_desc* d, void* stream) {
     SMOT_CHECK_ARG(conv2d_tc_supported(d), "smot_conv2d: tcgen05 path does not support this descriptor");
     return conv2d_tc(d, st);
   }
+  if (d->algo == SMOT_CONV_AUTO && conv2d_hires_supported(d)) return conv2d_hires(d, st);  // DLA stem / levels 0-1
   // SIMT family: warp-per-pixel kernel for Cout <= 16, register-tiled implicit GEMM otherwise
   if (d->algo == SMOT_CONV_AUTO && conv2d_smalln_supported(d)) return conv2d_smalln(d, st);
   return conv2d_simt(d, st);

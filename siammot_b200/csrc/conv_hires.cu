@@ -1,0 +1,304 @@
+// High-resolution, low-channel convolutions of the DLA-34 stem (fp16 storage, fp32 accumulation):
+//   base_layer 7x7 3->16, level0 3x3 16->16, level1 3x3/2 16->32, level2.tree1.conv1 3x3/2 32->64
+//   (dla.py:257-260,278-287,34-38).  They hold ~10 % of the FLOPs but ~35 % of the activation bytes: at
+//   704x1280 each reads or writes 14-29 MB and their GEMM N (16..64) and K (147..288) are far too small
+//   for a 128-wide tcgen05 tile, so the bound is HBM, not the tensor pipe.
+// Design: a CTA stages the input halo of an 8x32 (stride 1) or 4x32 (stride 2) output tile ONCE in
+// shared memory (cp.async, zero-fill outside the image = the conv padding) plus the whole weight,
+// every warp then walks the filter taps with warp-level mma.sync.m16n8k16 (A fragments via ldmatrix
+// straight out of the halo, pixel pitch padded by 16 B against bank conflicts), and the fp16 result is
+// staged back through shared memory so global stores are full 16-byte, pixel-contiguous chunks.
+#include "common.cuh"
+
+namespace smot {
+
+struct HiresArgs {
+  const __half* in;
+  const __half* wt;
+  const float* scale;
+  const float* bias;
+  __half* out;
+  int H, W, in_ld, OH, OW, out_ld, relu;
+};
+
+__device__ __forceinline__ uint32_t hs_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(hs_smem(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid) {
+  const int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(hs_smem(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3, pad 1, stride 1|2, CIN in {16,32}, COUT in {16,32,64}
+// ---------------------------------------------------------------------------------------------
+template <int CIN, int COUT, int STRIDE>
+struct Hires3 {
+  static constexpr int TW = 32;
+  static constexpr int TH = STRIDE == 1 ? 8 : 4;
+  static constexpr int MT = STRIDE == 1 ? 2 : 1;  // 16-pixel M tiles per warp (8 warps)
+  static constexpr int IH = (TH - 1) * STRIDE + 3, IW = (TW - 1) * STRIDE + 3;
+  static constexpr int PITCH = CIN * 2 + 16;      // bytes per halo pixel (16 B pad)
+  static constexpr int K = 9 * CIN, KP = K + 8;   // weight row pitch in halves (16 B pad)
+  static constexpr int HALO_BYTES = ((IH * IW * PITCH + 127) / 128) * 128;
+  static constexpr int W_BYTES = COUT * KP * 2;
+  static constexpr int OUT_BYTES = TH * TW * COUT * 2;
+  static constexpr int SMEM = HALO_BYTES + W_BYTES;
+  static_assert(OUT_BYTES <= HALO_BYTES, "output staging reuses the halo region");
+};
+
+template <int CIN, int COUT, int STRIDE>
+__global__ void __launch_bounds__(256) conv3x3_hires_kernel(const HiresArgs a) {
+  using C = Hires3<CIN, COUT, STRIDE>;
+  extern __shared__ __align__(128) unsigned char hs_raw[];
+  unsigned char* halo = hs_raw;
+  __half* wsm = reinterpret_cast<__half*>(hs_raw + C::HALO_BYTES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ox0 = blockIdx.x * C::TW, oy0 = blockIdx.y * C::TH;
+  const int img = blockIdx.z;
+  const __half* in = a.in + (size_t)img * a.H * a.W * a.in_ld;
+  const int ix0 = ox0 * STRIDE - 1, iy0 = oy0 * STRIDE - 1;
+  // ---- stage weights [COUT][K] -> [COUT][KP] and the input halo (zero-filled outside the image)
+  constexpr int WCH = C::K / 8;  // 16-byte chunks per weight row
+  for (int i = tid; i < COUT * WCH; i += 256) {
+    const int n = i / WCH, q = i - n * WCH;
+    cp_async16(wsm + n * C::KP + q * 8, a.wt + (size_t)n * C::K + q * 8, true);
+  }
+  constexpr int PCH = CIN / 8;  // 16-byte chunks per pixel
+  for (int i = tid; i < C::IH * C::IW * PCH; i += 256) {
+    const int p = i / PCH, q = i - p * PCH;
+    const int py = p / C::IW, px = p - py * C::IW;
+    const int gy = iy0 + py, gx = ix0 + px;
+    const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+    const __half* src = ok ? in + ((size_t)gy * a.W + gx) * a.in_ld + q * 8 : in;
+    cp_async16(halo + p * C::PITCH + q * 16, src, ok);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- warp tiling: stride 1: warp = output row, 2 M-tiles; stride 2: warp -> (row, half)
+  const int oy_l = STRIDE == 1 ? warp : (warp >> 1);
+  const int mt0 = STRIDE == 1 ? 0 : (warp & 1);
+  float acc[C::MT][COUT / 8][4];
+#pragma unroll
+  for (int m = 0; m < C::MT; ++m)
+#pragma unroll
+    for (int j = 0; j < COUT / 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
+  // ldmatrix lane roles
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;  // A: matrices (r0-7,k0-7),(r8-15,k0-7),(r0-7,k8-15),(r8-15,k8-15)
+  const int a_kh = lane >> 4;
+  const int b_row = (lane & 7) + ((lane >> 4) & 1) * 8;  // B: matrices (n0-7,k0-7),(n0-7,k8-15),(n8-15,k0-7),(n8-15,k8-15)
+  const int b_kh = (lane >> 3) & 1;
+  const uint32_t halo_s = hs_smem(halo), w_s = hs_smem(wsm);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int kc = 0; kc < CIN / 16; ++kc) {
+        uint32_t af[C::MT][4];
+#pragma unroll
+        for (int m = 0; m < C::MT; ++m) {
+          const int iy = oy_l * STRIDE + r;
+          const int ix = ((mt0 + m) * 16 + a_row) * STRIDE + s;
+          ldmatrix_x4(halo_s + (iy * C::IW + ix) * C::PITCH + kc * 32 + a_kh * 16, af[m][0], af[m][1], af[m][2], af[m][3]);
+        }
+        const int kbase = (r * 3 + s) * CIN + kc * 16;
+#pragma unroll
+        for (int jp = 0; jp < COUT / 16; ++jp) {
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(w_s + ((jp * 16 + b_row) * C::KP + kbase + b_kh * 8) * 2, b0, b1, b2, b3);
+#pragma unroll
+          for (int m = 0; m < C::MT; ++m) {
+            mma_16816(acc[m][jp * 2], af[m], b0, b1);
+            mma_16816(acc[m][jp * 2 + 1], af[m], b2, b3);
+          }
+        }
+      }
+  __syncthreads();  // everyone is done reading the halo: reuse it as the output staging tile
+  __half* ost = reinterpret_cast<__half*>(halo);
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int m = 0; m < C::MT; ++m)
+#pragma unroll
+    for (int j = 0; j < COUT / 8; ++j) {
+      const int n = j * 8 + 2 * t;
+      const float s0 = a.scale ? a.scale[n] : 1.f, s1 = a.scale ? a.scale[n + 1] : 1.f;
+      const float c0 = a.bias ? a.bias[n] : 0.f, c1 = a.bias ? a.bias[n + 1] : 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ox_l = (mt0 + m) * 16 + g + h * 8;
+        float v0 = __fadd_rn(__fmul_rn(acc[m][j][2 * h], s0), c0);
+        float v1 = __fadd_rn(__fmul_rn(acc[m][j][2 * h + 1], s1), c1);
+        if (a.relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+        *reinterpret_cast<__half2*>(ost + (oy_l * C::TW + ox_l) * COUT + n) = __floats2half2_rn(v0, v1);
+      }
+    }
+  __syncthreads();
+  constexpr int OCH = COUT / 8;  // 16-byte chunks per output pixel
+  __half* out = a.out + (size_t)img * a.OH * a.OW * a.out_ld;
+  for (int i = tid; i < C::TH * C::TW * OCH; i += 256) {
+    const int p = i / OCH, q = i - p * OCH;
+    const int py = p / C::TW, px = p - py * C::TW;
+    const int oy = oy0 + py, ox = ox0 + px;
+    if (oy < a.OH && ox < a.OW)
+      *reinterpret_cast<uint4*>(out + ((size_t)oy * a.OW + ox) * a.out_ld + q * 8) =
+          *reinterpret_cast<const uint4*>(ost + p * COUT + q * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem: 7x7, pad 3, stride 1, 3 (stored as 4) -> 16 channels.  K per filter row = 8 pixels x 4 ch = 32
+// (the 8th pixel and the 4th channel meet zero weights), i.e. 14 k-steps of m16n8k16.
+// ---------------------------------------------------------------------------------------------
+constexpr int ST_TW = 32, ST_TH = 8, ST_IH = ST_TH + 6, ST_IW = 40, ST_COUT = 16;
+
+__global__ void __launch_bounds__(256) stem7x7_hires_kernel(const HiresArgs a) {
+  __shared__ __align__(16) __half halo[ST_IH * ST_IW * 4];       // 8 B per pixel
+  __shared__ __align__(16) __half wsm[ST_COUT * 7 * 32];         // [cout][r][(s*4 + c)], zero padded
+  __shared__ __align__(16) __half ost[ST_TH * ST_TW * ST_COUT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ox0 = blockIdx.x * ST_TW, oy0 = blockIdx.y * ST_TH;
+  const __half* in = a.in + (size_t)blockIdx.z * a.H * a.W * a.in_ld;
+  for (int i = tid; i < ST_COUT * 7 * 32; i += 256) {
+    const int n = i / 224, rem = i - n * 224, r = rem / 32, k = rem - r * 32;
+    const int s = k >> 2, c = k & 3;
+    wsm[i] = (s < 7 && c < 3) ? a.wt[((size_t)n * 49 + r * 7 + s) * 3 + c] : __float2half(0.f);
+  }
+  for (int p = tid; p < ST_IH * ST_IW; p += 256) {
+    const int py = p / ST_IW, px = p - py * ST_IW;
+    const int gy = oy0 - 3 + py, gx = ox0 - 3 + px;
+    const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+    cp_async8(halo + p * 4, ok ? in + ((size_t)gy * a.W + gx) * a.in_ld : in, ok);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int g = lane >> 2, t = lane & 3;
+  float acc[2][2][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
+  const uint32_t* hw = reinterpret_cast<const uint32_t*>(halo);  // 2 words per pixel
+  const uint32_t* ww = reinterpret_cast<const uint32_t*>(wsm);   // 16 words per (cout, r)
+#pragma unroll
+  for (int r = 0; r < 7; ++r)
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      uint32_t bf[2][2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int base = ((j * 8 + g) * 7 + r) * 16 + kb * 8 + t;
+        bf[j][0] = ww[base];
+        bf[j][1] = ww[base + 4];
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        // A(row i, k) = halo[(warp + r) row][(m*16 + i) pixel + k/4][k%4]: word index = pixel*2 + k/2
+        const int rowbase = ((warp + r) * ST_IW + m * 16) * 2 + kb * 8 + t;
+        uint32_t af[4];
+        af[0] = hw[rowbase + g * 2];
+        af[1] = hw[rowbase + (g + 8) * 2];
+        af[2] = hw[rowbase + g * 2 + 4];
+        af[3] = hw[rowbase + (g + 8) * 2 + 4];
+        mma_16816(acc[m][0], af, bf[0][0], bf[0][1]);
+        mma_16816(acc[m][1], af, bf[1][0], bf[1][1]);
+      }
+    }
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = j * 8 + 2 * t;
+      const float s0 = a.scale ? a.scale[n] : 1.f, s1 = a.scale ? a.scale[n + 1] : 1.f;
+      const float c0 = a.bias ? a.bias[n] : 0.f, c1 = a.bias ? a.bias[n + 1] : 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ox_l = m * 16 + g + h * 8;
+        float v0 = __fadd_rn(__fmul_rn(acc[m][j][2 * h], s0), c0);
+        float v1 = __fadd_rn(__fmul_rn(acc[m][j][2 * h + 1], s1), c1);
+        if (a.relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+        *reinterpret_cast<__half2*>(ost + (warp * ST_TW + ox_l) * ST_COUT + n) = __floats2half2_rn(v0, v1);
+      }
+    }
+  __syncthreads();
+  __half* out = a.out + (size_t)blockIdx.z * a.OH * a.OW * a.out_ld;
+  for (int i = tid; i < ST_TH * ST_TW * 2; i += 256) {
+    const int p = i >> 1, q = i & 1;
+    const int py = p / ST_TW, px = p - py * ST_TW;
+    const int oy = oy0 + py, ox = ox0 + px;
+    if (oy < a.OH && ox < a.OW)
+      *reinterpret_cast<uint4*>(out + ((size_t)oy * a.OW + ox) * a.out_ld + q * 8) =
+          *reinterpret_cast<const uint4*>(ost + p * ST_COUT + q * 8);
+  }
+}
+
+// ---- dispatch ---------------------------------------------------------------------------------
+static bool common_ok(const smot_conv_desc* d) {
+  return d->in_dtype == SMOT_F16 && d->out_dtype == SMOT_F16 && !d->residual && d->out_ld % 8 == 0 &&
+         (((uintptr_t)d->in | (uintptr_t)d->weight | (uintptr_t)d->out) & 15) == 0;
+}
+
+bool conv2d_hires_supported(const smot_conv_desc* d) {
+  if (!common_ok(d)) return false;
+  if (d->KH == 7 && d->KW == 7 && d->stride == 1 && d->pad == 3 && d->Cin == 3 && d->in_ld == 4 && d->Cout == 16) return true;
+  if (d->KH == 3 && d->KW == 3 && d->pad == 1 && d->in_ld % 8 == 0) {
+    if (d->stride == 1 && d->Cin == 16 && d->Cout == 16) return true;
+    if (d->stride == 2 && d->Cin == 16 && d->Cout == 32 && d->H % 2 == 0 && d->W % 2 == 0) return true;
+    if (d->stride == 2 && d->Cin == 32 && d->Cout == 64 && d->H % 2 == 0 && d->W % 2 == 0) return true;
+  }
+  return false;
+}
+
+template <int CIN, int COUT, int STRIDE>
+static int launch3(const HiresArgs& a, int batch, cudaStream_t st) {
+  using C = Hires3<CIN, COUT, STRIDE>;
+  static bool attr = false;
+  if (!attr && C::SMEM > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_hires_kernel<CIN, COUT, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) {
+      set_error("smot_conv2d(hires): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return SMOT_ERR_CUDA;
+    }
+    attr = true;
+  }
+  dim3 grid(ceil_div(a.OW, C::TW), ceil_div(a.OH, C::TH), batch);
+  conv3x3_hires_kernel<CIN, COUT, STRIDE><<<grid, 256, C::SMEM, st>>>(a);
+  SMOT_CHECK_LAUNCH("smot_conv2d(hires)");
+  return SMOT_OK;
+}
+
+int conv2d_hires(const smot_conv_desc* d, cudaStream_t st) {
+  HiresArgs a;
+  a.in = (const __half*)d->in, a.wt = (const __half*)d->weight, a.scale = d->scale, a.bias = d->bias, a.out = (__half*)d->out;
+  a.H = d->H, a.W = d->W, a.in_ld = d->in_ld, a.OH = d->OH, a.OW = d->OW, a.out_ld = d->out_ld, a.relu = d->relu;
+  if (d->batch == 0) return SMOT_OK;
+  if (d->KH == 7) {
+    dim3 grid(ceil_div(a.OW, ST_TW), ceil_div(a.OH, ST_TH), d->batch);
+    stem7x7_hires_kernel<<<grid, 256, 0, st>>>(a);
+    SMOT_CHECK_LAUNCH("smot_conv2d(stem)");
+    return SMOT_OK;
+  }
+  if (d->Cin == 16 && d->Cout == 16) return launch3<16, 16, 1>(a, d->batch, st);
+  if (d->Cin == 16 && d->Cout == 32) return launch3<16, 32, 2>(a, d->batch, st);
+  return launch3<32, 64, 2>(a, d->batch, st);
+}
+
+}  // namespace smot

@@ -350,6 +350,7 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   a.tiles_w = ceil_div(d->OW, a.tile_w), a.tiles_h = ceil_div(d->OH, a.tile_h);
   const long long tiles = (long long)a.tiles_w * a.tiles_h * d->batch;
   // BN: 128 unless that leaves most SMs idle
+  // measured (profiles/): below one wave of CTAs the kernel is latency-bound per CTA, so more, smaller tiles win
   const int BN = (d->Cout % 128 == 0 && tiles * (d->Cout / 128) >= 148) ? 128 : 64;
 
   CUtensorMap tmA, tmB;

@@ -441,3 +441,38 @@ def test_conv2d_small_cout_kernel(dtype):
                      out=out[..., :10])
         assert rel_err(out[0, 0, :, :10].cpu(), F.linear(x, w, b)) <= tol(dtype)
         assert float(out[..., 10:].abs().max()) == 0.0
+
+
+HIRES_CASES = [
+    # name, Cin, Cout, k, stride, H, W
+    ("stem", 3, 16, 7, 1, 72, 104),
+    ("level0", 16, 16, 3, 1, 72, 104),
+    ("level1", 16, 32, 3, 2, 72, 104),
+    ("level2.tree1.conv1", 32, 64, 3, 2, 36, 52),
+    ("level0_ragged", 16, 16, 3, 1, 13, 37),
+]
+
+
+@pytest.mark.parametrize("case", HIRES_CASES)
+def test_conv2d_hires_kernels(case):
+    """mma.sync halo-tile kernels of the DLA stem / levels 0-1 (fp16): vs torch fp32 and vs the SIMT kernel."""
+    from siammot_b200 import _lib
+    name, Cin, Cout, k, stride, H, W = case
+    g = torch.Generator().manual_seed(len(name) + H)
+    dt = torch.float16
+    x = q(torch.randn(2, Cin, H, W, generator=g), dt)
+    w = q(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k), dt)
+    scale, bias = 0.5 + torch.rand(Cout, generator=g), torch.randn(Cout, generator=g)
+    ref = F.relu(F.conv2d(x, w, None, stride, k // 2) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    if Cin == 3:
+        buf = torch.zeros(2, H, W, 4, dtype=dt, device=DEV)
+        buf[..., :3] = nhwc(x, dt)
+        dx = buf[..., :3]
+    else:
+        dx = nhwc(x, dt)
+    args = (dx, ohwi(w, dt), scale.to(DEV), bias.to(DEV), None, stride, k // 2, True)
+    got = ops().conv2d(*args)                       # AUTO -> hires kernel
+    got_simt = ops().conv2d(*args, algo=_lib.CONV_SIMT)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(got), ref) <= 2e-3
+    assert rel_err(nchw(got), nchw(got_simt)) <= 1e-3
