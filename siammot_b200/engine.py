@@ -239,8 +239,8 @@ class _TrackPlan(object):
         self.keep.append(d)
         self.steps.append((lib().smot_conv2d, (C.byref(d),), "conv:" + name))
 
-    def run(self, feat, upload=True):
-        """Launch the stage and wait for its result block (the frame's only device->host sync)."""
+    def run(self, feat, upload=True, wait=True):
+        """Launch the stage and (wait=True) block on its result block: the frame's only device->host sync."""
         eng = self.e
         st = _lib.stream_ptr()
         if self.n:
@@ -257,6 +257,10 @@ class _TrackPlan(object):
         self.host_res.copy_(self.res, non_blocking=True)
         self.host_det.copy_(self.det_block, non_blocking=True)
         self.done.record()
+        if wait:
+            self.done.synchronize()
+
+    def wait(self):
         self.done.synchronize()
 
 
@@ -427,8 +431,11 @@ class Engine(object):
         B, H, W, Cc, ld = ops._nhwc(x)
         return (ops._ptr(x), ops._ptr(out), B, H, W, Cc, ld, ops._nhwc(out)[4], _lib.dtype_code(x.dtype))
 
-    def plan(self, H, W):
-        key = (H, W)
+    def plan(self, H, W, slot=0):
+        """Static launch plan (+ its buffers and CUDA graph) for one input size.  ``slot`` selects one of
+        several independent copies so that frame t+1 can be in flight while frame t's features are still
+        needed (SiamMOT.forward_clip double-buffers with slots 0/1)."""
+        key = (H, W, slot)
         if key in self.plans:
             return self.plans[key]
         if not self.weights:
@@ -438,6 +445,7 @@ class Engine(object):
                              "(DATALOADER.SIZE_DIVISIBILITY 32) and fails in dla.py:54 otherwise" % (H, W))
         cfg, dev, dt = self.cfg, self.device, self.dtype
         P = _Plan(self, H, W)
+        P.slot = slot
         L = lib()
         dc = _lib.dtype_code(dt)
         # ---- input
@@ -553,13 +561,13 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     # per-frame entry points
     # ------------------------------------------------------------------------------------------
-    def run_static(self, image):
-        """image: (3,H,W) or (1,3,H,W) float tensor (any device).  Runs backbone..detections."""
+    def run_static(self, image, slot=0):
+        """image: (3,H,W) or (1,3,H,W) float tensor (any device).  Enqueues backbone..detections."""
         if image.dim() == 4:
             if image.shape[0] != 1:
                 raise ValueError("one image per forward (track_core.py:75 asserts the same)")
             image = image[0]
-        P = self.plan(image.shape[1], image.shape[2])
+        P = self.plan(image.shape[1], image.shape[2], slot)
         P.img_in.copy_(image, non_blocking=True)
         with self.timed("static"):
             P.run()
@@ -613,14 +621,14 @@ class Engine(object):
     def track_arena(self, P, n, ncap=None):
         """The shared buffer arena of static plan P, grown (x2) when n exceeds its capacity."""
         ncap = P.det_boxes.shape[0] if ncap is None else ncap
-        key = (P.H, P.W, ncap)
+        key = (P.H, P.W, getattr(P, "slot", 0), ncap)
         A = self._arenas.get(key)
         if A is None or A.cap < n:
             cap = 64 if A is None else A.cap
             while cap < n:
                 cap *= 2
             A = self._arenas[key] = _TrackArena(self, P, ncap, cap)
-            for k in [k for k in self._track_plans if k[:2] == (P.H, P.W)]:
+            for k in [k for k in self._track_plans if k[:3] == (P.H, P.W, getattr(P, "slot", 0))]:
                 self._track_plans.pop(k)
         return A
 
@@ -628,7 +636,7 @@ class Engine(object):
         if det is not None:   # external detections: one-off plan over their arrays
             return _TrackPlan(self, P, n, self.track_arena(P, n, det[0].shape[0]), det=det)
         A = self.track_arena(P, n)
-        key = (P.H, P.W, n)
+        key = (P.H, P.W, getattr(P, "slot", 0), n)
         tp = self._track_plans.get(key)
         if tp is None:
             tp = self._track_plans[key] = _TrackPlan(self, P, n, A)

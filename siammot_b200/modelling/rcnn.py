@@ -197,6 +197,10 @@ class CombinedROIHeads(nn.ModuleDict):
     def run_frame(self, P, mem, given_detection=None):
         """One frame after the static stage (CombinedROIHeads.forward roi_heads.py:21-51).
         Returns (BoxList on the model device, Memory for the next frame)."""
+        return self.finish_frame(self.launch_frame(P, mem, given_detection))
+
+    def launch_frame(self, P, mem, given_detection=None):
+        """Enqueue the track-dependent stage of a frame (no host wait).  Returns a pending-frame token."""
         eng, cfg = self.engine, self.cfg
         if not cfg.MODEL.TRACK_ON:
             raise NotImplementedError("MODEL.TRACK_ON False")
@@ -213,8 +217,14 @@ class CombinedROIHeads(nn.ModuleDict):
         if upload:
             mem.stage(tp)
             tp.staged_mem = mem
-        tp.run(mem.feat if n else None, upload=upload)
+        tp.run(mem.feat if n else None, upload=upload, wait=False)
+        return (P, tp, mem, n)
 
+    def finish_frame(self, pending, next_P=None):
+        """Wait for the frame's result block, resolve ids on the host, build the next-frame memory.
+        next_P: the static plan the NEXT frame will run on (clip pipelining); defaults to this frame's."""
+        P, tp, mem, n = pending
+        tp.wait()
         # ---- host: unpack the result block
         total, ncap = tp.total, tp.ncap
         t = max(total, 1)
@@ -244,7 +254,7 @@ class CombinedROIHeads(nn.ModuleDict):
         else:
             scores, ids = self.solver.resolve(kscores, ids, all_track_ids)
         boxes = np.array(kboxes, dtype=np.float32, copy=True)
-        new_mem = self._build_memory(P, boxes, ids, labels)
+        new_mem = self._build_memory(P, boxes, ids, labels, next_P)
         return self._to_boxlist(boxes, scores, ids, labels, (P.W, P.H)), new_mem
 
     def _to_boxlist(self, boxes, scores, ids, labels, size):
@@ -267,7 +277,7 @@ class CombinedROIHeads(nn.ModuleDict):
         out.add_field("labels", d[8 * k:16 * k].view(torch.int64))
         return out
 
-    def _build_memory(self, P, boxes, ids, labels):
+    def _build_memory(self, P, boxes, ids, labels, next_P=None):
         """TrackHead.get_track_memory (track_head.py:54-110) + EMM.extract_cache (track_core.py:81-98).
         boxes/ids/labels: numpy, solver output order."""
         eng, dev = self.engine, self.engine.device
@@ -293,7 +303,8 @@ class CombinedROIHeads(nn.ModuleDict):
             m_boxes[r], m_sr[r], m_ids[r], m_labels[r] = d[3], d[2], d[4], d[5]
         if n == 0:
             return Memory(None, m_sr, m_boxes, m_ids, m_labels, 0, dev)
-        tp = eng.track_plan(P, n)            # next frame's plan: stage its inputs now (boxes are needed on device anyway)
+        # next frame's plan: stage its inputs now (the boxes are needed on the device anyway)
+        tp = eng.track_plan(next_P if next_P is not None else P, n)
         mem = Memory(None, m_sr, m_boxes, m_ids, m_labels, n_act, dev)
         mem.stage(tp)
         tp.staged_mem = mem
@@ -394,6 +405,36 @@ class SiamMOT(nn.Module):
         self._mem = mem
         self.track_memory = mem
         return [result]
+
+
+def _forward_clip(self, frames, before_frame=None):
+    """Process consecutive frames of ONE video with the frame-independent stage of frame t+1 enqueued while
+    the host resolves frame t (double-buffered static plans).  Results are identical to calling the model
+    frame by frame; this is the throughput API (the reference has INFERENCE.CLIP_LEN but processes one
+    frame per forward, defaults.py:96, track_core.py:75).  frames: sequence / tensor of (3,H,W) frames.
+    before_frame(t): optional hook called right before frame t's tracker stage is enqueued."""
+    if self.training:
+        raise NotImplementedError("siammot_b200 is an inference engine: call .eval()")
+    eng = self.engine()
+    n_frames = len(frames)
+    results = []
+    with torch.no_grad():
+        P_next = eng.run_static(frames[0], 0) if n_frames else None
+        for t in range(n_frames):
+            P = P_next
+            if before_frame is not None:
+                before_frame(t)
+            pending = self.roi_heads.launch_frame(P, self._mem)
+            if t + 1 < n_frames:
+                P_next = eng.run_static(frames[t + 1], (t + 1) & 1)
+            result, mem = self.roi_heads.finish_frame(pending, next_P=P_next)
+            self._mem = mem
+            self.track_memory = mem
+            results.append(result)
+    return results
+
+
+SiamMOT.forward_clip = _forward_clip
 
 
 def build_siammot(cfg):

@@ -101,3 +101,17 @@ def test_engine_fp16_tracks_close_to_reference():
     assert abs(len(g0["ids"]) - len(o0["ids"])) <= max(3, len(g0["ids"]) // 10)
     same = int((g0["ids"][:n] == o0["ids"][:n]).sum())
     assert same >= 0.8 * n
+
+
+def test_forward_clip_equals_frame_by_frame():
+    """The pipelined clip API (double-buffered static plans) must give exactly the per-frame results."""
+    name = "emm_256x384"
+    cfg, model, clip = build_model(name, "float32")
+    model.reset_siammot_status()
+    ref = [model(f.to("cuda"))[0] for f in clip]
+    model.reset_siammot_status()
+    got = model.forward_clip([f.to("cuda") for f in clip])
+    assert len(got) == len(ref)
+    for a, b in zip(ref, got):
+        assert torch.equal(a.bbox, b.bbox) and torch.equal(a.get_field("ids"), b.get_field("ids"))
+        assert torch.equal(a.get_field("scores"), b.get_field("scores"))
