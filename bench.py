@@ -264,11 +264,11 @@ def run_ours(args):
         "e2e": {"value": round(world * args.steps / (e2e_ms * 1e-3), 2), "unit": "frames/s",
                 "h2d_bytes_per_step": 3 * H_NET * W_NET * 4, "d2h_bytes_per_step": int(d2h / args.steps)},
         "gpu_launches": kernels_per_frame(h) * args.steps,
-        "roofline": {"kernel": "xcorr_kernel (smot_xcorr)", "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak,
+        "roofline": {"kernel": "xcorr_mma_kernel (smot_xcorr)" if args.dtype == "float16" else "xcorr_kernel (smot_xcorr)", "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak,
                      "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
                      "algorithmic_bytes": xc_bytes, "us_per_launch": round(xc_ms * 1e3, 2),
                      "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650 GB/s",
-                     "note": "41.7 FLOP/B: FP32-FMA-bound unless reformulated (SURVEY.md hard part 2)"},
+                     "note": "fp16: banded-Toeplitz mma.sync form (bound by staging/latency); fp32: FMA form, 41.7 FLOP/B"},
         "stage_ms": {"static_graph": round(sum(static) / max(len(static), 1), 4)},
         "clocks": clocks,
     }

@@ -20,49 +20,179 @@ namespace smot {
 // =============================================================================================
 // xcorr
 // =============================================================================================
+// Staging keeps the search window in its storage type (fp16 windows cost half the shared memory, so three
+// CTAs fit per SM) and the template in fp32.  grid = (C/32, tracks, 2): blockIdx.z selects output rows
+// [8z, 8z+8) -> a CTA stages only the O/2 + T - 1 window rows it needs; warp w owns output row 8z + w.
 template <typename T, int S, int TT>
 __global__ void __launch_bounds__(256) xcorr_kernel(const T* __restrict__ x, const T* __restrict__ k, T* __restrict__ out,
                                                     int C) {
   constexpr int O = S - TT + 1;
   constexpr int CG = 32;
-  extern __shared__ __align__(16) float xc_smem[];
-  float* xs = xc_smem;                // [S*S][CG]
-  float* ks = xc_smem + S * S * CG;   // [TT*TT][CG]
-  const int n = blockIdx.y;
-  const int c0 = blockIdx.x * CG;
+  constexpr int RH = O / 2;            // output rows per CTA
+  constexpr int XR = RH + TT - 1;      // window rows per CTA
+  static_assert(O % 2 == 0 && RH <= 8, "row split assumes <= 8 rows per CTA (one per warp)");
+  extern __shared__ __align__(16) unsigned char xc_raw[];
+  T* xs = reinterpret_cast<T*>(xc_raw);                                           // [XR*S][CG]
+  float* ks = reinterpret_cast<float*>(xc_raw + ((XR * S * CG * sizeof(T) + 15) / 16) * 16);  // [TT*TT][CG]
+  const int n = blockIdx.y, c0 = blockIdx.x * CG, r0 = blockIdx.z * RH;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const T* xb = x + (size_t)n * S * S * C + c0;
+  const T* xb = x + ((size_t)n * S * S + (size_t)r0 * S) * C + c0;
   const T* kb = k + (size_t)n * TT * TT * C + c0;
-  // stage (4 channels per thread per position, coalesced runs of CG channels)
-  for (int i = threadIdx.x; i < S * S * (CG / 4); i += blockDim.x) {
-    const int pos = i / (CG / 4), q = (i % (CG / 4)) * 4;
-    float4 v = ld4(xb + (size_t)pos * C + q);
-    *reinterpret_cast<float4*>(xs + pos * CG + q) = v;
+  constexpr int VEC = 16 / sizeof(T);  // elements per 16-byte chunk
+  for (int i = threadIdx.x; i < XR * S * (CG / VEC); i += blockDim.x) {
+    const int pos = i / (CG / VEC), q = (i % (CG / VEC)) * VEC;
+    *reinterpret_cast<uint4*>(xs + pos * CG + q) = *reinterpret_cast<const uint4*>(xb + (size_t)pos * C + q);
   }
   for (int i = threadIdx.x; i < TT * TT * (CG / 4); i += blockDim.x) {
     const int pos = i / (CG / 4), q = (i % (CG / 4)) * 4;
-    float4 v = ld4(kb + (size_t)pos * C + q);
-    *reinterpret_cast<float4*>(ks + pos * CG + q) = v;
+    *reinterpret_cast<float4*>(ks + pos * CG + q) = ld4(kb + (size_t)pos * C + q);
   }
   __syncthreads();
-  T* ob = out + (size_t)n * O * O * C + c0 + lane;
-  for (int i = warp; i < O; i += 8) {
-    float acc[O];
+  if (warp >= RH) return;
+  const int i = warp;  // local output row
+  float acc[O];
 #pragma unroll
-    for (int j = 0; j < O; ++j) acc[j] = 0.f;
-    for (int u = 0; u < TT; ++u) {
-      float xr[S], kr[TT];
+  for (int j = 0; j < O; ++j) acc[j] = 0.f;
+  for (int u = 0; u < TT; ++u) {
+    float xr[S], kr[TT];
 #pragma unroll
-      for (int j = 0; j < S; ++j) xr[j] = xs[((i + u) * S + j) * CG + lane];
+    for (int j = 0; j < S; ++j) xr[j] = to_f(xs[((i + u) * S + j) * CG + lane]);
 #pragma unroll
-      for (int v = 0; v < TT; ++v) kr[v] = ks[(u * TT + v) * CG + lane];
+    for (int v = 0; v < TT; ++v) kr[v] = ks[(u * TT + v) * CG + lane];
 #pragma unroll
-      for (int v = 0; v < TT; ++v)
+    for (int v = 0; v < TT; ++v)
 #pragma unroll
-        for (int j = 0; j < O; ++j) acc[j] = fmaf(xr[j + v], kr[v], acc[j]);
+      for (int j = 0; j < O; ++j) acc[j] = fmaf(xr[j + v], kr[v], acc[j]);
+  }
+  T* ob = out + ((size_t)n * O * O + (size_t)(r0 + i) * O) * C + c0 + lane;
+#pragma unroll
+  for (int j = 0; j < O; ++j) ob[(size_t)j * C] = from_f<T>(acc[j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core form of the depthwise correlation (fp16 storage, fp32 accumulation).
+// For one (track, channel):  Out(16x16) = sum_u X[u:u+16, 0:32) * B_u,  B_u[m][j] = K[u][m-j] (banded
+// Toeplitz of template row u, zero outside 0 <= m-j < 15): 15 x (2 k-steps x 2 n-tiles) mma.sync.m16n8k16,
+// ~2.1x redundant MACs on a pipe >10x faster than the FP32 FMAs -> the kernel becomes bound by staging.
+// A fragments come by ldmatrix from a per-channel transposed copy of the window (xT[c][row][col], row pitch
+// 80 B: conflict-free); B fragments are single 32-bit shared loads from two zero-padded copies of the
+// template row (one shifted by an element so odd offsets stay 4-byte aligned).
+// ---------------------------------------------------------------------------------------------
+constexpr int XM_CG = 16;                 // channels per CTA
+constexpr int XM_WARPS = 16;              // one channel per warp: the per-channel chain (template rows -> 60 dependent MMAs) runs 16-wide
+constexpr int XM_PITCH = 40;              // halves per window row in xT (30 data + zero pad; 80 B)
+constexpr int XM_KZ = 48;                 // halves per zero-padded template-row copy
+constexpr int XM_CSTRIDE = 30 * XM_PITCH + 8;  // halves between channel planes of xT (604 words: 8 banks apart mod 32)
+constexpr int XM_ILP = 8;                 // 16-byte window loads in flight per thread while staging
+
+__device__ __forceinline__ void xm_ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void xm_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(XM_WARPS * 32) xcorr_mma_kernel(const __half* __restrict__ x, const __half* __restrict__ k,
+                                                                 __half* __restrict__ out, int C) {
+  constexpr int S = 30, TT = 15, O = 16;
+  extern __shared__ __align__(16) unsigned char xm_raw[];
+  __half* xT = reinterpret_cast<__half*>(xm_raw);                                   // [CG][CSTRIDE]    38656 B
+  __half* kraw = xT + XM_CG * XM_CSTRIDE;                                         // [T*T][CG]         7200 B
+  __half (*kz)[TT][2][XM_KZ] = reinterpret_cast<__half (*)[TT][2][XM_KZ]>(kraw + TT * TT * XM_CG);  // 11520 B
+  __half* ost = reinterpret_cast<__half*>(kz) + XM_WARPS * TT * 2 * XM_KZ;          // [O*O][CG]         8192 B
+  const int n = blockIdx.y, c0 = blockIdx.x * XM_CG;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // zero the pad columns of xT and the padded template rows
+  for (int i = tid; i < XM_CG * S * (XM_PITCH - S); i += blockDim.x) {
+    const int r = i / (XM_PITCH - S), cpad = i - r * (XM_PITCH - S);
+    xT[(r / S) * XM_CSTRIDE + (r % S) * XM_PITCH + S + cpad] = __float2half(0.f);
+  }
+  for (int i = tid; i < XM_WARPS * TT * 2 * XM_KZ / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(&kz[0][0][0][0])[i] = 0u;
+  // stage the window transposed: 16-byte global reads (8 channels of one position) issued in batches of
+  // XM_ILP so that several are in flight per thread, then 2-byte scattered stores (channel stride padded
+  // to XM_CSTRIDE halves: the 8 channels of a chunk land in 8 different banks)
+  const __half* xb = x + (size_t)n * S * S * C + c0;
+  constexpr int XM_ITEMS = S * S * (XM_CG / 8);
+  for (int b0 = 0; b0 < XM_ITEMS; b0 += XM_ILP * XM_WARPS * 32) {
+    uint4 v[XM_ILP];
+#pragma unroll
+    for (int u = 0; u < XM_ILP; ++u) {
+      const int i = b0 + u * XM_WARPS * 32 + tid;
+      if (i < XM_ITEMS) v[u] = *reinterpret_cast<const uint4*>(xb + (size_t)(i / (XM_CG / 8)) * C + (i % (XM_CG / 8)) * 8);
     }
 #pragma unroll
-    for (int j = 0; j < O; ++j) ob[(size_t)(i * O + j) * C] = from_f<T>(acc[j]);
+    for (int u = 0; u < XM_ILP; ++u) {
+      const int i = b0 + u * XM_WARPS * 32 + tid;
+      if (i < XM_ITEMS) {
+        const int pos = i / (XM_CG / 8), q = i % (XM_CG / 8);
+        const __half* h = reinterpret_cast<const __half*>(&v[u]);
+        const int row = pos / S, col = pos - row * S;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xT[(q * 8 + e) * XM_CSTRIDE + row * XM_PITCH + col] = h[e];
+      }
+    }
+  }
+  const __half* kb = k + (size_t)n * TT * TT * C + c0;
+  for (int i = tid; i < TT * TT * (XM_CG / 8); i += blockDim.x) {
+    const int pos = i / (XM_CG / 8), q = i % (XM_CG / 8);
+    *reinterpret_cast<uint4*>(kraw + pos * XM_CG + q * 8) = *reinterpret_cast<const uint4*>(kb + (size_t)pos * C + q * 8);
+  }
+  __syncthreads();
+  const int g = lane >> 2, t = lane & 3;
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
+  const int par = g & 1;
+  const uint32_t xT_s = (uint32_t)__cvta_generic_to_shared(xT);
+  for (int cc = 0; cc < XM_CG / XM_WARPS; ++cc) {
+    const int c = warp * (XM_CG / XM_WARPS) + cc;
+    // template rows of channel c into the two zero-padded copies: kz[u][0][16+v] = kz[u][1][15+v] = K[u][v]
+    for (int i = lane; i < TT * TT; i += 32) {
+      const int u = i / TT, v = i - u * TT;
+      const __half val = kraw[i * XM_CG + c];
+      kz[warp][u][0][16 + v] = val;
+      kz[warp][u][1][15 + v] = val;
+    }
+    __syncwarp();
+    float acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    const uint32_t xc_s = xT_s + (uint32_t)(c * XM_CSTRIDE * 2);
+#pragma unroll 3
+    for (int u = 0; u < TT; ++u) {
+      const uint32_t* kzw = reinterpret_cast<const uint32_t*>(&kz[warp][u][par][0]);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t af[4];
+        xm_ldmatrix_x4(xc_s + (uint32_t)(((u + a_row) * XM_PITCH + ks * 16 + a_kh * 8) * 2), af[0], af[1], af[2], af[3]);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int d0 = 16 * ks + 2 * t - 8 * nt - g;  // B[k = 16ks+2t (+1)][n = 8nt+g] = K[u][d0 (+1)]
+          const int w = (16 + d0 - par) >> 1;
+          xm_mma(acc[nt], af, kzw[w], kzw[w + 4]);
+        }
+      }
+    }
+    // D fragment -> staging tile [pos][channel]
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = g + 8 * h, j = nt * 8 + 2 * t;
+        ost[(i * O + j) * XM_CG + c] = __float2half_rn(acc[nt][2 * h]);
+        ost[(i * O + j + 1) * XM_CG + c] = __float2half_rn(acc[nt][2 * h + 1]);
+      }
+    __syncwarp();
+  }
+  __syncthreads();
+  __half* ob = out + (size_t)n * O * O * C + c0;
+  for (int i = tid; i < O * O * (XM_CG / 8); i += blockDim.x) {
+    const int pos = i / (XM_CG / 8), q = i % (XM_CG / 8);
+    *reinterpret_cast<uint4*>(ob + (size_t)pos * C + q * 8) = *reinterpret_cast<const uint4*>(ost + pos * XM_CG + q * 8);
   }
 }
 
@@ -86,7 +216,8 @@ __global__ void xcorr_generic_kernel(const T* __restrict__ x, const T* __restric
 
 template <typename T, int S, int TT>
 static int launch_xcorr(const void* x, const void* k, void* out, int n, int C, cudaStream_t st) {
-  const size_t smem = (size_t)(S * S + TT * TT) * 32 * sizeof(float);
+  constexpr int XR = (S - TT + 1) / 2 + TT - 1;
+  const size_t smem = ((size_t)XR * S * 32 * sizeof(T) + 15) / 16 * 16 + (size_t)TT * TT * 32 * sizeof(float);
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(xcorr_kernel<T, S, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -96,7 +227,7 @@ static int launch_xcorr(const void* x, const void* k, void* out, int n, int C, c
     }
     attr = true;
   }
-  xcorr_kernel<T, S, TT><<<dim3(C / 32, n), 256, smem, st>>>((const T*)x, (const T*)k, (T*)out, C);
+  xcorr_kernel<T, S, TT><<<dim3(C / 32, n, 2), 256, smem, st>>>((const T*)x, (const T*)k, (T*)out, C);
   SMOT_CHECK_LAUNCH("smot_xcorr");
   return SMOT_OK;
 }
@@ -280,6 +411,22 @@ extern "C" int smot_xcorr(const void* x, const void* k, void* out, int n, int ch
   SMOT_CHECK_ARG(x && k && out, "smot_xcorr: null argument");
   SMOT_CHECK_ARG(dtype == SMOT_F32 || dtype == SMOT_F16, "smot_xcorr: bad dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMOT_F16 && S == 30 && T == 15 && channels % XM_CG == 0 &&
+      (((uintptr_t)x | (uintptr_t)k | (uintptr_t)out) & 15) == 0) {
+    constexpr int XM_SMEM = (XM_CG * XM_CSTRIDE + 15 * 15 * XM_CG + XM_WARPS * 15 * 2 * XM_KZ + 16 * 16 * XM_CG) * 2;
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(xcorr_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XM_SMEM);
+      if (e != cudaSuccess) {
+        set_error("smot_xcorr: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return SMOT_ERR_CUDA;
+      }
+      attr = true;
+    }
+    xcorr_mma_kernel<<<dim3(channels / XM_CG, n), XM_WARPS * 32, XM_SMEM, st>>>((const __half*)x, (const __half*)k, (__half*)out, channels);
+    SMOT_CHECK_LAUNCH("smot_xcorr(mma)");
+    return SMOT_OK;
+  }
   const bool fast = channels % 32 == 0 && (((uintptr_t)x | (uintptr_t)k) & 15) == 0;
   if (fast && S == 30 && T == 15)
     return dtype == SMOT_F32 ? launch_xcorr<float, 30, 15>(x, k, out, n, channels, st)
