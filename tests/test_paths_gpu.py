@@ -1,0 +1,121 @@
+"""GPU parity of the less-travelled branches of the path against the CPU oracle (fp32 arithmetic):
+public detections (roi_heads.py:26-34), CrowdHuman-density track counts (BASELINE configs[2]: 80 tracks),
+the TRACKTOR scoring switch (roi_heads.py:72-76) and the reference's failure mode when every track is lost."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import scenario_cfg
+from siammot_b200.synthetic import make_state_dict
+from siammot_b200.synth_clip import make_clip
+
+pytestmark = pytest.mark.gpu
+BOX_TOL, SCORE_TOL = 1e-3, 1e-3
+
+
+def _pair(cfg, seed=1):
+    from oracle.siammot_oracle import OracleSiamMOT
+    from siammot_b200.modelling import build_siammot
+    sd = make_state_dict(cfg, seed)
+    model = build_siammot(cfg)
+    model.load_state_dict(sd, strict=False)
+    return model.to("cuda").eval(), OracleSiamMOT(cfg, sd)
+
+
+def _check(got, ref, t):
+    assert got.bbox.shape[0] == ref["boxes"].shape[0], "frame %d: %d vs %d boxes" % (t, got.bbox.shape[0], ref["boxes"].shape[0])
+    assert torch.equal(got.get_field("ids").cpu(), ref["ids"]), "frame %d ids" % t
+    assert torch.equal(got.get_field("labels").cpu(), ref["labels"])
+    if got.bbox.shape[0] == 0:
+        return
+    assert float((got.bbox.cpu() - ref["boxes"]).abs().max()) <= BOX_TOL
+    assert float((got.get_field("scores").cpu() - ref["scores"]).abs().max()) <= SCORE_TOL
+
+
+def test_given_detections_match_oracle():
+    from siammot_b200.structures import BoxList
+    cfg = scenario_cfg("emm_amodal_expire_192x320")
+    model, orc = _pair(cfg, 2)
+    clip = make_clip(4, 192, 320, 5, 3)
+    g = torch.Generator().manual_seed(4)
+    model.reset_siammot_status()
+    orc.reset()
+    for t in range(4):
+        n = 0 if t == 2 else 24                       # one frame with no public detections at all
+        xy = torch.rand(n, 2, generator=g) * torch.tensor([250., 120.])
+        wh = torch.rand(n, 2, generator=g) * torch.tensor([50., 60.]) + 10
+        boxes = torch.cat([xy, xy + wh], 1)
+        bl = BoxList(boxes.clone(), (320, 192), mode="xyxy")
+        bl.add_field("labels", torch.ones(n, dtype=torch.int64))
+        bl.add_field("scores", torch.ones(n))
+        bl.add_field("ids", torch.full((n,), -1, dtype=torch.int64))
+        got = model(clip[t].to("cuda"), given_detection=[bl])[0]
+        if n:
+            given = dict(boxes=boxes, ids=torch.full((n,), -1, dtype=torch.int64), labels=torch.ones(n, dtype=torch.int64))
+        else:
+            given = dict(boxes=torch.zeros((0, 4)), scores=torch.zeros((0,)), ids=torch.zeros((0,), dtype=torch.int64),
+                         labels=torch.zeros((0,), dtype=torch.int64))
+        ref = orc.forward(clip[t], given_detection=given)
+        _check(got, ref, t)
+
+
+def test_eighty_tracks_match_oracle():
+    """80 tracks in memory (CrowdHuman density, BASELINE configs[2]) seeded on a 384x640 frame pair."""
+    from oracle.siammot_oracle import build_memory
+    cfg = scenario_cfg("emm_256x384")
+    model, orc = _pair(cfg, 1)
+    clip = make_clip(2, 384, 640, 6, 7)
+    g = torch.Generator().manual_seed(9)
+    n = 80
+    c = torch.rand(n, 2, generator=g) * torch.tensor([560., 300.]) + torch.tensor([40., 40.])
+    wh = torch.rand(n, 2, generator=g) * torch.tensor([60., 120.]) + torch.tensor([12., 24.])
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
+    labels = torch.ones(n, dtype=torch.int64)
+    # engine
+    eng = model.engine()
+    P = eng.run_static(clip[0].to("cuda"))
+    pool = model.roi_heads.track.track_pool
+    pool.reset()
+    ids = torch.tensor([pool.start_track() for _ in range(n)])
+    model.flush_memory(model.roi_heads._build_memory(P, boxes.numpy(), ids.numpy(), labels.numpy()))
+    pool.increment_frame()
+    got = model(clip[1].to("cuda"))[0]
+    # oracle
+    feats = orc.features(clip[0])
+    orc.pool.reset()
+    oids = torch.tensor([orc.pool.start() for _ in range(n)])
+    orc.memory = build_memory(orc.P, cfg, orc.pool, feats, dict(boxes=boxes, scores=torch.full((n,), 0.9), ids=oids, labels=labels))
+    orc.pool.frame += 1
+    ref = orc.forward(clip[1])
+    assert int((ref["ids"] >= 0).sum()) >= 20
+    _check(got, ref, 1)
+
+
+def test_tracktor_switch_matches_oracle():
+    cfg = scenario_cfg("emm_256x384")
+    cfg.MODEL.TRACK_HEAD.TRACKTOR = True
+    model, orc = _pair(cfg, 1)
+    clip = make_clip(3, 256, 384, 6, 0)
+    model.reset_siammot_status()
+    orc.reset()
+    for t in range(3):
+        _check(model(clip[t].to("cuda"))[0], orc.forward(clip[t]), t)
+
+
+def test_all_tracks_lost_raises_like_the_reference():
+    """roi_heads.py:64-65 returns a bare BoxList when every propagated track is clipped away and :44 then fails
+    on list + BoxList; the engine reproduces the TypeError instead of silently continuing."""
+    cfg = scenario_cfg("emm_256x384")
+    model, _ = _pair(cfg, 1)
+    clip = make_clip(2, 256, 384, 6, 0)
+    eng = model.engine()
+    P = eng.run_static(clip[0].to("cuda"))
+    pool = model.roi_heads.track.track_pool
+    pool.reset()
+    # a template far outside the frame: the decoded box is clipped to an empty one
+    boxes = np.array([[3000., 3000., 3050., 3100.]], dtype=np.float32)
+    ids = np.array([pool.start_track()], dtype=np.int64)
+    model.flush_memory(model.roi_heads._build_memory(P, boxes, ids, np.ones(1, dtype=np.int64)))
+    pool.increment_frame()
+    with pytest.raises(TypeError):
+        model(clip[1].to("cuda"))
