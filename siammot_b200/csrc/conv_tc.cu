@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -370,8 +371,12 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
     if (!encode_map(&tmB, d->weight, 2, dims, str, box)) return SMOT_ERR_CUDA;
   }
   dim3 grid((unsigned)tiles, (unsigned)(d->Cout / BN));
-  if (BN == 128) return launch_tc<128, 3>(tmA, tmB, a, grid, st);
-  return launch_tc<64, 4>(tmA, tmB, a, grid, st);
+  // many short tiles: 2-stage rings let 4 CTAs share an SM, so one CTA's prologue / epilogue overlaps the
+  // main loops of the others (same bytes in flight per SM as 2 CTAs x 4 stages)
+  const char* force = getenv("SMOT_TC_STAGES");
+  const bool shallow = force ? atoi(force) == 2 : (tiles * (d->Cout / BN) >= 296 && a.taps * a.cin_chunks <= 36);
+  if (BN == 128) return shallow ? launch_tc<128, 2>(tmA, tmB, a, grid, st) : launch_tc<128, 3>(tmA, tmB, a, grid, st);
+  return shallow ? launch_tc<64, 2>(tmA, tmB, a, grid, st) : launch_tc<64, 4>(tmA, tmB, a, grid, st);
 }
 
 }  // namespace smot
