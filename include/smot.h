@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SMOT_ABI_VERSION 1
+#define SMOT_ABI_VERSION 2
 
 enum { SMOT_OK = 0, SMOT_ERR_INVALID = 1, SMOT_ERR_CUDA = 2, SMOT_ERR_UNSUPPORTED = 3 };
 enum { SMOT_F32 = 0, SMOT_F16 = 1 };
@@ -70,7 +70,13 @@ typedef struct {
   int in_dtype;  /* SMOT_F32 | SMOT_F16: dtype of in, weight, residual */
   int out_dtype; /* SMOT_F32 | SMOT_F16 */
   int algo;      /* SMOT_CONV_* */
+  /* optional scratch for split-K (tcgen05 path, few output tiles x long K): fp32 partial tiles + per-tile
+   * arrival counters.  The counter region (first SMOT_CONV_WS_COUNTER_BYTES bytes) must be zero before the
+   * first use and is left zero by every call; calls sharing a workspace must be stream-ordered. */
+  void* workspace;
+  size_t workspace_bytes;
 } smot_conv_desc;
+#define SMOT_CONV_WS_COUNTER_BYTES 65536
 int smot_conv2d(const smot_conv_desc* d, void* stream);
 /* Which kernel family SMOT_CONV_AUTO would pick for this descriptor (SMOT_CONV_SIMT / _TCGEN05). */
 int smot_conv2d_algo(const smot_conv_desc* d);

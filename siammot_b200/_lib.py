@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libsmot.so")
 F32, F16 = 0, 1
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
 MAX_LEVELS, MAX_ANCHORS = 5, 16
-ABI_VERSION = 1
+ABI_VERSION = 2
+CONV_WS_COUNTER_BYTES = 65536
 
 
 class ConvDesc(C.Structure):
@@ -20,7 +21,8 @@ class ConvDesc(C.Structure):
                 ("batch", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("in_ld", C.c_int),
                 ("OH", C.c_int), ("OW", C.c_int), ("Cout", C.c_int), ("out_ld", C.c_int), ("res_ld", C.c_int),
                 ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
-                ("relu", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int), ("algo", C.c_int)]
+                ("relu", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int), ("algo", C.c_int),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 class Pyramid(C.Structure):

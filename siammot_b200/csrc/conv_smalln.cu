@@ -107,6 +107,62 @@ __global__ void __launch_bounds__(SN_WARPS * 32) conv_smalln_kernel(const SmallN
   }
 }
 
+// Few output pixels (box predictor on <= 300 ROIs, refinement on the tracks): staging the whole weight in
+// shared memory per CTA would dominate, so each warp streams the weight rows it needs straight from L2
+// (one warp per output pixel, lanes split the input channels, Cout accumulators per lane).
+template <typename TI, typename TO, int COUT>
+__global__ void __launch_bounds__(128) conv_smalln_direct_kernel(const SmallNArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (m >= a.M) return;
+  const TI* __restrict__ in = reinterpret_cast<const TI*>(a.in);
+  const TI* __restrict__ wt = reinterpret_cast<const TI*>(a.wt);
+  const int img = m / (a.OH * a.OW);
+  const int rem = m - img * (a.OH * a.OW);
+  const int oh = rem / a.OW, ow = rem - oh * a.OW;
+  const TI* base = in + (size_t)img * a.H * a.W * a.in_ld;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  for (int r = 0; r < a.KH; ++r)
+    for (int s = 0; s < a.KW; ++s) {
+      const int ih = oh - a.pad + r, iw = ow - a.pad + s;
+      if (ih < 0 || ih >= a.H || iw < 0 || iw >= a.W) continue;
+      const TI* px = base + ((size_t)ih * a.W + iw) * a.in_ld;
+      const int kbase = (r * a.KW + s) * a.Cin;
+      for (int c0 = lane * 4; c0 < a.Cin; c0 += 128) {
+        const float4 x = ld4(px + c0);
+        float4 w[COUT];  // unconditional loads (rows past Cout re-read the last row) so all are in flight together
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) w[c] = ld4(wt + (size_t)min(c, a.Cout - 1) * a.K + kbase + c0);
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          acc[c] = fmaf(x.x, w[c].x, acc[c]);
+          acc[c] = fmaf(x.y, w[c].y, acc[c]);
+          acc[c] = fmaf(x.z, w[c].z, acc[c]);
+          acc[c] = fmaf(x.w, w[c].w, acc[c]);
+        }
+      }
+    }
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) {
+    float v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[c] = v;
+  }
+  float y = 0.f;
+#pragma unroll
+  for (int c = 0; c < COUT; ++c)
+    if (lane == c) y = acc[c];
+  if (lane < a.Cout) {
+    if (a.scale) y = __fmul_rn(y, a.scale[lane]);
+    if (a.bias) y = __fadd_rn(y, a.bias[lane]);
+    if (a.relu) y = fmaxf(y, 0.f);
+    reinterpret_cast<TO*>(a.out)[(size_t)m * a.out_ld + lane] = from_f<TO>(y);
+  }
+}
+
 bool conv2d_smalln_supported(const smot_conv_desc* d) {
   if (d->Cout > 16 || d->stride != 1 || d->residual) return false;
   if (d->Cin < 64 || d->Cin % 4 != 0 || d->in_ld % 4 != 0 || ((uintptr_t)d->in & 15)) return false;  // lanes split channels
@@ -118,6 +174,17 @@ bool conv2d_smalln_supported(const smot_conv_desc* d) {
 template <typename TI, typename TO>
 static int launch_smalln(const SmallNArgs& a, cudaStream_t st) {
   const int cout_pad = a.Cout <= 4 ? 4 : (a.Cout <= 8 ? 8 : 16);
+  if (a.M <= 1024 && ((uintptr_t)a.wt & 15) == 0 && a.K % 4 == 0) {
+    const unsigned g = (unsigned)ceil_div(a.M, 4);
+    if (cout_pad == 4)
+      conv_smalln_direct_kernel<TI, TO, 4><<<g, 128, 0, st>>>(a);
+    else if (cout_pad == 8)
+      conv_smalln_direct_kernel<TI, TO, 8><<<g, 128, 0, st>>>(a);
+    else
+      conv_smalln_direct_kernel<TI, TO, 16><<<g, 128, 0, st>>>(a);
+    SMOT_CHECK_LAUNCH("smot_conv2d(smalln direct)");
+    return SMOT_OK;
+  }
   const size_t smem = (size_t)cout_pad * a.K * sizeof(float);
   const unsigned grid = (unsigned)ceil_div(a.M, SN_PIX * SN_WARPS);
   cudaError_t e = cudaSuccess;

@@ -39,6 +39,11 @@ struct TcArgs {
   int Cin, Cout, out_ld, res_ld, relu;
   int taps, KW, pad, cin_chunks, stride;
   int tiles_w, tiles_h, tile_w, tile_h;
+  // split-K (gridDim.z > 1): fp32 partial tiles [z][tile][128][Cout] and one arrival counter per output tile
+  int splits, chunks_per_split, num_tiles;
+  float* partial;
+  unsigned* counters;
+  unsigned long long* dbg;  // developer timing probe (SMOT_TC_DEBUG): 8 timestamps of CTA (0,0,0), else null
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -82,6 +87,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
       ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(i)                                                                                   \
+  do {                                                                                                \
+    if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) a.dbg[i] = gtimer();          \
+  } while (0)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -137,7 +151,7 @@ struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 8 /*scale, bias*/;
 };
 
 template <int BN, int STAGES>
@@ -154,8 +168,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   uint64_t* empty = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint32_t* tmem_slot_aux = tmem_slot + 1;
+  float* s_scale = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);  // [BN] scale, then [BN] bias
+  float* s_bias = s_scale + BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TC_STAMP(0);
   // tile coordinates
   int t = blockIdx.x;
   const int tw = t % a.tiles_w;
@@ -164,7 +182,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const int img = t / a.tiles_h;
   const int w0 = tw * a.tile_w, h0 = th * a.tile_h;
   const int n0 = blockIdx.y * BN;
-  const int total = a.taps * a.cin_chunks;
+  const int all_chunks = a.taps * a.cin_chunks;
+  const int it0 = (int)blockIdx.z * a.chunks_per_split;                 // this CTA's K range [it0, it0 + total)
+  const int total = min(a.chunks_per_split, all_chunks - it0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -184,6 +204,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
@@ -192,7 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_expect_tx(&full[s], (uint32_t)S::STAGE_BYTES);
-        const int tap = it / a.cin_chunks, cc = it - tap * a.cin_chunks;
+        const int tap = (it0 + it) / a.cin_chunks, cc = (it0 + it) - tap * a.cin_chunks;
         const int r = tap / a.KW, sx = tap - r * a.KW;
         tma_load_4d(sA + s * S::A_BYTES, &tmA, &full[s], cc * TC_BK, w0 * a.stride + sx - a.pad, h0 * a.stride + r - a.pad, img);
         tma_load_2d(sB + s * S::B_BYTES, &tmB, &full[s], tap * a.Cin + cc * TC_BK, n0);
@@ -205,6 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(&full[s], ph);
+        if (it == 0) TC_STAMP(2);
         tc_fence_after();
         const uint64_t ad = umma_desc_sw128(sA + s * S::A_BYTES);
         const uint64_t bd = umma_desc_sw128(sB + s * S::B_BYTES);
@@ -221,54 +243,114 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int oh = h0 + row / a.tile_w, ow = w0 + row % a.tile_w;
     const bool valid = oh < a.H && ow < a.W;
     const size_t pix = ((size_t)img * a.H + oh) * a.W + ow;
-    mbar_wait(tmem_full, 0u);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (valid) {
-        const int n = n0 + c0;
-        if (a.scale) {
+    // while the main loop runs: park this N-tile's scale / bias in shared memory (read as float4 broadcasts later)
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      s_scale[i] = a.scale ? __ldg(a.scale + n0 + i) : 1.f;
+      s_bias[i] = a.bias ? __ldg(a.bias + n0 + i) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    auto finish = [&](float* v, int c0) {  // scale / bias / residual / ReLU / fp16 store of 32 channels
+      const int n = n0 + c0;
+      if (a.scale) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(v[j], __ldg(a.scale + n + j));
+        for (int g = 0; g < 8; ++g) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * g);
+          v[4 * g] = __fmul_rn(v[4 * g], sc.x), v[4 * g + 1] = __fmul_rn(v[4 * g + 1], sc.y);
+          v[4 * g + 2] = __fmul_rn(v[4 * g + 2], sc.z), v[4 * g + 3] = __fmul_rn(v[4 * g + 3], sc.w);
         }
-        if (a.bias) {
+      }
+      if (a.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(v[j], __ldg(a.bias + n + j));
+        for (int g = 0; g < 8; ++g) {
+          const float4 bi = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
+          v[4 * g] = __fadd_rn(v[4 * g], bi.x), v[4 * g + 1] = __fadd_rn(v[4 * g + 1], bi.y);
+          v[4 * g + 2] = __fadd_rn(v[4 * g + 2], bi.z), v[4 * g + 3] = __fadd_rn(v[4 * g + 3], bi.w);
         }
-        if (a.res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + n);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 rv = __ldg(rp + g);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f = __half22float2(h2[e]);
-              v[g * 8 + 2 * e] += f.x;
-              v[g * 8 + 2 * e + 1] += f.y;
-            }
-          }
-        }
-        if (a.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.out_ld + n);
+      }
+      if (a.res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + n);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint4 ov;
-          __half2* h2 = reinterpret_cast<__half2*>(&ov);
+          uint4 rv = __ldg(rp + g);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-          op[g] = ov;
+          for (int e = 0; e < 4; ++e) {
+            float2 f = __half22float2(h2[e]);
+            v[g * 8 + 2 * e] += f.x;
+            v[g * 8 + 2 * e + 1] += f.y;
+          }
         }
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.out_ld + n);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 ov;
+        __half2* h2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+        op[g] = ov;
+      }
+    };
+    mbar_wait(tmem_full, 0u);
+    if (warp == 2 && lane == 0) TC_STAMP(3);
+    tc_fence_after();
+    if (a.splits == 1) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (valid) finish(v, c0);
+      }
+    } else {
+      // ---- split-K: park the fp32 partial tile, the last CTA of this output tile reduces in split order
+      const int tile_id = (int)blockIdx.x;
+      float* mine = a.partial + (((size_t)blockIdx.z * a.num_tiles + tile_id) * TC_BM + row) * a.Cout + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) reinterpret_cast<float4*>(mine + c0)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+      if (warp == 2 && lane == 0) {
+        const unsigned prev = atomicAdd(a.counters + (size_t)tile_id * gridDim.y + blockIdx.y, 1u);
+        *tmem_slot_aux = prev;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*tmem_slot_aux == (unsigned)(a.splits - 1)) {
+        __threadfence();
+        if (valid) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int z = 0; z < a.splits; ++z) {
+              const float4* src = reinterpret_cast<const float4*>(
+                  a.partial + (((size_t)z * a.num_tiles + tile_id) * TC_BM + row) * a.Cout + n0 + c0);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 p = __ldcg(src + g);
+                v[4 * g] += p.x, v[4 * g + 1] += p.y, v[4 * g + 2] += p.z, v[4 * g + 3] += p.w;
+              }
+            }
+            finish(v, c0);
+          }
+        }
+        if (warp == 2 && lane == 0) a.counters[(size_t)tile_id * gridDim.y + blockIdx.y] = 0u;  // self-resetting
       }
     }
   }
+  if (warp == 2 && lane == 0) TC_STAMP(4);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(5);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
@@ -352,7 +434,12 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   const long long tiles = (long long)a.tiles_w * a.tiles_h * d->batch;
   // BN: 128 unless that leaves most SMs idle
   // measured (profiles/): below one wave of CTAs the kernel is latency-bound per CTA, so more, smaller tiles win
-  const int BN = (d->Cout % 128 == 0 && tiles * (d->Cout / 128) >= 148) ? 128 : 64;
+  // One tcgen05.mma costs ~160 cycles whatever its N (measured: the dependent accumulate chain, not TMA, paces the
+  // main loop), so the widest N that still leaves ~100 CTAs wins.
+  int BN = 64;
+  if (d->Cout % 256 == 0 && tiles * (d->Cout / 256) >= 96) BN = 256;
+  else if (d->Cout % 128 == 0 && tiles * (d->Cout / 128) >= 96) BN = 128;
+  if (const char* fbn = getenv("SMOT_TC_BN")) BN = (atoi(fbn) == 256 && d->Cout % 256 == 0) ? 256 : ((atoi(fbn) >= 128 && d->Cout % 128 == 0) ? 128 : 64);  // developer override
 
   CUtensorMap tmA, tmB;
   {
@@ -370,12 +457,38 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
     uint32_t box[2] = {(uint32_t)TC_BK, (uint32_t)BN};
     if (!encode_map(&tmB, d->weight, 2, dims, str, box)) return SMOT_ERR_CUDA;
   }
-  dim3 grid((unsigned)tiles, (unsigned)(d->Cout / BN));
+  // split-K: few output tiles with a long K loop leave most SMs idle and each CTA latency-bound
+  const int all_chunks = a.taps * a.cin_chunks;
+  const long long ctas = tiles * (d->Cout / BN);
+  int splits = 1;
+  // measured (profiles/): only worth it when a single wave would leave > 80 % of the SMs idle (fc6 on the tracks)
+  if (d->workspace && ctas <= 24 && all_chunks >= 32) {
+    splits = (int)(296 / ctas);
+    if (splits > 8) splits = 8;
+    if (splits > all_chunks / 6) splits = all_chunks / 6;
+    const size_t need = (size_t)SMOT_CONV_WS_COUNTER_BYTES + (size_t)splits * tiles * TC_BM * d->Cout * sizeof(float);
+    if (splits < 2 || need > d->workspace_bytes || (size_t)ctas * sizeof(unsigned) > SMOT_CONV_WS_COUNTER_BYTES) splits = 1;
+  }
+  a.splits = splits;
+  a.chunks_per_split = (all_chunks + splits - 1) / splits;
+  a.splits = (all_chunks + a.chunks_per_split - 1) / a.chunks_per_split;  // no empty split
+  a.num_tiles = (int)tiles;
+  {
+    const char* dbg = getenv("SMOT_TC_DEBUG");  // hex device pointer to 8 x u64
+    a.dbg = dbg ? (unsigned long long*)strtoull(dbg, nullptr, 16) : nullptr;
+  }
+  a.counters = (unsigned*)d->workspace;
+  a.partial = d->workspace ? (float*)((char*)d->workspace + SMOT_CONV_WS_COUNTER_BYTES) : nullptr;
+  dim3 grid((unsigned)tiles, (unsigned)(d->Cout / BN), (unsigned)a.splits);
   // many short tiles: 2-stage rings let 4 CTAs share an SM, so one CTA's prologue / epilogue overlaps the
   // main loops of the others (same bytes in flight per SM as 2 CTAs x 4 stages)
   const char* force = getenv("SMOT_TC_STAGES");
   const bool shallow = force ? atoi(force) == 2 : (tiles * (d->Cout / BN) >= 296 && a.taps * a.cin_chunks <= 36);
+  // at most one CTA per SM: nothing else hides the ~1 us TMA round trip, so run an 8-deep ring (192 KB)
+  const bool deep = force ? atoi(force) == 8 : ((long long)grid.x * grid.y * grid.z <= 148 && all_chunks >= 8);
+  if (BN == 256) return launch_tc<256, 3>(tmA, tmB, a, grid, st);  // 48 KB stages, 1 CTA / SM
   if (BN == 128) return shallow ? launch_tc<128, 2>(tmA, tmB, a, grid, st) : launch_tc<128, 3>(tmA, tmB, a, grid, st);
+  if (deep) return launch_tc<64, 8>(tmA, tmB, a, grid, st);
   return shallow ? launch_tc<64, 2>(tmA, tmB, a, grid, st) : launch_tc<64, 4>(tmA, tmB, a, grid, st);
 }
 

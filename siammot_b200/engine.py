@@ -79,7 +79,7 @@ class _Plan(object):
 
     def conv(self, x, name, out, residual=None, stride=1, pad=0, relu=False):
         w, scale, bias = self.e.weights[name]
-        d = ops.conv_desc(x, w, out, scale, bias, residual, stride, pad, relu)
+        d = ops.conv_desc(x, w, out, scale, bias, residual, stride, pad, relu, workspace=self.e.conv_ws)
         self.keep.append(d)
         self.steps.append((lib().smot_conv2d, (C.byref(d),), "conv:" + name))
         return out
@@ -235,7 +235,7 @@ class _TrackPlan(object):
 
     def _conv(self, x, name, out, **kw):
         w, scale, bias = self.e.weights[name]
-        d = ops.conv_desc(x, w, out, scale, bias, **kw)
+        d = ops.conv_desc(x, w, out, scale, bias, workspace=self.e.conv_ws, **kw)
         self.keep.append(d)
         self.steps.append((lib().smot_conv2d, (C.byref(d),), "conv:" + name))
 
@@ -294,6 +294,7 @@ class Engine(object):
         self.hann = torch.hann_window(self.o_res * self.up, dtype=torch.float).to(self.device)
         self.pads = [int(T.PAD_PIXELS / ((2 ** i) * 4)) for i in range(len(T.POOLER_SCALES))]
         self._nms_ws = {}
+        self.conv_ws = ops.conv_workspace(self.device)  # shared by every conv (all launches are stream-ordered)
         self._track_plans = {}
         self._arenas = {}
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()

@@ -39,7 +39,13 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def conv_desc(x, weight, out, scale=None, bias=None, residual=None, stride=1, pad=0, relu=False, algo=_lib.CONV_AUTO):
+def conv_workspace(device, nbytes=48 << 20):
+    """Zeroed scratch for split-K convolutions (fp32 partial tiles + self-resetting arrival counters)."""
+    return torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+
+
+def conv_desc(x, weight, out, scale=None, bias=None, residual=None, stride=1, pad=0, relu=False, algo=_lib.CONV_AUTO,
+              workspace=None):
     """Build the smot_conv_desc for out = act(conv(x, weight)*scale + bias + residual)."""
     _require_cuda(x, weight, out, scale, bias, residual)
     B, H, W, Cin, in_ld = _nhwc(x)
@@ -64,20 +70,22 @@ def conv_desc(x, weight, out, scale=None, bias=None, residual=None, stride=1, pa
     d.KH, d.KW, d.stride, d.pad = weight.shape[1], weight.shape[2], stride, pad
     d.relu = int(bool(relu))
     d.in_dtype, d.out_dtype, d.algo = dtype_code(x.dtype), dtype_code(out.dtype), algo
+    d.workspace = workspace.data_ptr() if workspace is not None else None
+    d.workspace_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
     if Bo != B:
         raise ValueError("batch mismatch")
     return d
 
 
 def conv2d(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0, relu=False, out=None, out_dtype=None,
-           algo=_lib.CONV_AUTO):
+           algo=_lib.CONV_AUTO, workspace=None):
     B, H, W, _, _ = _nhwc(x)
     KH, KW = weight.shape[1], weight.shape[2]
     OH = (H + 2 * pad - KH) // stride + 1
     OW = (W + 2 * pad - KW) // stride + 1
     if out is None:
         out = torch.empty((B, OH, OW, weight.shape[0]), dtype=out_dtype or x.dtype, device=x.device)
-    d = conv_desc(x, weight, out, scale, bias, residual, stride, pad, relu, algo)
+    d = conv_desc(x, weight, out, scale, bias, residual, stride, pad, relu, algo, workspace)
     check(lib().smot_conv2d(C.byref(d), stream_ptr()), "smot_conv2d")
     return out
 

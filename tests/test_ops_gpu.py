@@ -476,3 +476,36 @@ def test_conv2d_hires_kernels(case):
     torch.cuda.synchronize()
     assert rel_err(nchw(got), ref) <= 2e-3
     assert rel_err(nchw(got), nchw(got_simt)) <= 1e-3
+
+
+def test_conv2d_tcgen05_split_k():
+    """Few-tile / long-K layers (level5 convs, fc6) with the split-K workspace: fp32 partial tiles are reduced in
+    split order by the last CTA of each output tile; counters must be left zero (call twice, then inspect)."""
+    from siammot_b200 import _lib
+    g = torch.Generator().manual_seed(123)
+    dt = torch.float16
+    ws = ops().conv_workspace(DEV)
+    # level5 3x3: 9 tiles x 8 n-tiles x K = 4608
+    x = q(torch.randn(1, 512, 22, 40, generator=g), dt)
+    w = q(torch.randn(512, 512, 3, 3, generator=g) / math.sqrt(512 * 9), dt)
+    res = q(torch.randn(1, 512, 22, 40, generator=g), dt)
+    scale, bias = 0.5 + torch.rand(512, generator=g), torch.randn(512, generator=g)
+    ref = F.relu(F.conv2d(x, w, None, 1, 1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1) + res)
+    args = (nhwc(x, dt), ohwi(w, dt), scale.to(DEV), bias.to(DEV), nhwc(res, dt), 1, 1, True)
+    for _ in range(2):
+        got = ops().conv2d(*args, algo=_lib.CONV_TCGEN05, workspace=ws)
+        torch.cuda.synchronize()
+        assert rel_err(nchw(got), ref) <= 2e-3
+    plain = ops().conv2d(*args, algo=_lib.CONV_TCGEN05)
+    assert rel_err(nchw(got), nchw(plain)) <= 1e-3
+    # fc6 for 300 and 30 rows
+    for rows in (300, 30):
+        xfc = q(torch.randn(rows, 6272, generator=g), dt)
+        wfc = q(torch.randn(1024, 6272, generator=g) / math.sqrt(6272), dt)
+        bfc = torch.randn(1024, generator=g)
+        reffc = F.relu(F.linear(xfc, wfc, bfc))
+        gotfc = ops().conv2d(xfc.to(DEV, dt).view(1, 1, rows, 6272), wfc.to(DEV, dt).view(1024, 1, 1, 6272), None,
+                             bfc.to(DEV), relu=True, algo=_lib.CONV_TCGEN05, workspace=ws)
+        assert rel_err(gotfc.view(rows, 1024).float().cpu(), reffc) <= 2e-3
+    torch.cuda.synchronize()
+    assert int(ws[:_lib.CONV_WS_COUNTER_BYTES].view(torch.int32).abs().sum()) == 0
