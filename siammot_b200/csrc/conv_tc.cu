@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         if (valid) finish(v, c0);
       }
     } else {
-      // ---- split-K: park the fp32 partial tile, the last CTA of this output tile reduces in split order
+      // ---- split-K: park the raw fp32 partial tile [split][tile][128][Cout]; splitk_reduce_kernel finishes the layer
       const int tile_id = (int)blockIdx.x;
       float* mine = a.partial + (((size_t)blockIdx.z * a.num_tiles + tile_id) * TC_BM + row) * a.Cout + n0;
 #pragma unroll 1
@@ -315,35 +315,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
         for (int g = 0; g < 8; ++g) reinterpret_cast<float4*>(mine + c0)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-      }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-      if (warp == 2 && lane == 0) {
-        const unsigned prev = atomicAdd(a.counters + (size_t)tile_id * gridDim.y + blockIdx.y, 1u);
-        *tmem_slot_aux = prev;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (*tmem_slot_aux == (unsigned)(a.splits - 1)) {
-        __threadfence();
-        if (valid) {
-#pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            for (int z = 0; z < a.splits; ++z) {
-              const float4* src = reinterpret_cast<const float4*>(
-                  a.partial + (((size_t)z * a.num_tiles + tile_id) * TC_BM + row) * a.Cout + n0 + c0);
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 p = __ldcg(src + g);
-                v[4 * g] += p.x, v[4 * g + 1] += p.y, v[4 * g + 2] += p.z, v[4 * g + 3] += p.w;
-              }
-            }
-            finish(v, c0);
-          }
-        }
-        if (warp == 2 && lane == 0) a.counters[(size_t)tile_id * gridDim.y + blockIdx.y] = 0u;  // self-resetting
       }
     }
   }
@@ -355,6 +326,46 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
   }
+}
+
+// Deterministic split-K finish: out[pixel][n] = act((sum_z partial[z]) * scale + bias + residual), summed in split order.
+// One thread per 4 output channels of one pixel; tiles map back to pixels exactly as in conv_tc_kernel.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcArgs a) {
+  const int c4 = a.Cout / 4;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)a.num_tiles * TC_BM * c4;
+  if (idx >= total) return;
+  const int n = (int)(idx % c4) * 4;
+  const size_t rowg = idx / c4;  // tile * 128 + row
+  const int row = (int)(rowg % TC_BM);
+  int t = (int)(rowg / TC_BM);
+  const int tw = t % a.tiles_w;
+  t /= a.tiles_w;
+  const int th = t % a.tiles_h;
+  const int img = t / a.tiles_h;
+  const int oh = th * a.tile_h + row / a.tile_w, ow = tw * a.tile_w + row % a.tile_w;
+  if (oh >= a.H || ow >= a.W) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < a.splits; ++z) {
+    const float4 p = *reinterpret_cast<const float4*>(a.partial + ((size_t)z * a.num_tiles * TC_BM + rowg) * a.Cout + n);
+    acc.x += p.x, acc.y += p.y, acc.z += p.z, acc.w += p.w;
+  }
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (a.scale) v[j] = __fmul_rn(v[j], a.scale[n + j]);
+    if (a.bias) v[j] = __fadd_rn(v[j], a.bias[n + j]);
+  }
+  const size_t pix = ((size_t)img * a.H + oh) * a.W + ow;
+  if (a.res) {
+    const float4 r = ld4(a.res + pix * a.res_ld + n);
+    v[0] += r.x, v[1] += r.y, v[2] += r.z, v[3] += r.w;
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  st4(a.out + pix * a.out_ld + n, make_float4(v[0], v[1], v[2], v[3]));
 }
 
 // ---- host side ------------------------------------------------------------------------------
@@ -434,13 +445,26 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   const long long tiles = (long long)a.tiles_w * a.tiles_h * d->batch;
   // BN: 128 unless that leaves most SMs idle
   // measured (profiles/): below one wave of CTAs the kernel is latency-bound per CTA, so more, smaller tiles win
-  // One tcgen05.mma costs ~160 cycles whatever its N (measured: the dependent accumulate chain, not TMA, paces the
-  // main loop), so the widest N that still leaves ~100 CTAs wins.
+  // Measured (tools/probe_tc.py, tools/bench_conv.py): the main loop advances ~0.35 us per 64-deep k-chunk whatever
+  // BN is (64..256), how deep the ring is and how many CTAs share the SM -- the four M128/K16 MMAs of a chunk pace it,
+  // not TMA.  Hence: (a) the widest N that still leaves ~100 CTAs; (b) layers with only a handful of output tiles
+  // (levels 4-5, FC layers) take the widest BN AND split K over up to 8 CTAs, finished by splitk_reduce_kernel.
+  const int all_chunks = a.taps * a.cin_chunks;
   int BN = 64;
   if (d->Cout % 256 == 0 && tiles * (d->Cout / 256) >= 96) BN = 256;
   else if (d->Cout % 128 == 0 && tiles * (d->Cout / 128) >= 96) BN = 128;
-  if (const char* fbn = getenv("SMOT_TC_BN")) BN = (atoi(fbn) == 256 && d->Cout % 256 == 0) ? 256 : ((atoi(fbn) >= 128 && d->Cout % 128 == 0) ? 128 : 64);  // developer override
-
+  int splits = 1;
+  {
+    const int bw = d->Cout % 256 == 0 ? 256 : (d->Cout % 128 == 0 ? 128 : 64);
+    const long long cw = tiles * (d->Cout / bw);
+    if (d->workspace && cw <= 40 && all_chunks >= 16 && !getenv("SMOT_TC_NOSPLIT")) {
+      int sp = (int)(148 / cw);
+      if (sp > 8) sp = 8;
+      if (sp > all_chunks / 4) sp = all_chunks / 4;
+      const size_t need = (size_t)SMOT_CONV_WS_COUNTER_BYTES + (size_t)sp * tiles * TC_BM * d->Cout * sizeof(float);
+      if (sp >= 2 && need <= d->workspace_bytes) splits = sp, BN = bw;
+    }
+  }
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
@@ -456,18 +480,6 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
     uint64_t str[1] = {K * 2};
     uint32_t box[2] = {(uint32_t)TC_BK, (uint32_t)BN};
     if (!encode_map(&tmB, d->weight, 2, dims, str, box)) return SMOT_ERR_CUDA;
-  }
-  // split-K: few output tiles with a long K loop leave most SMs idle and each CTA latency-bound
-  const int all_chunks = a.taps * a.cin_chunks;
-  const long long ctas = tiles * (d->Cout / BN);
-  int splits = 1;
-  // measured (profiles/): only worth it when a single wave would leave > 80 % of the SMs idle (fc6 on the tracks)
-  if (d->workspace && ctas <= 24 && all_chunks >= 32) {
-    splits = (int)(296 / ctas);
-    if (splits > 8) splits = 8;
-    if (splits > all_chunks / 6) splits = all_chunks / 6;
-    const size_t need = (size_t)SMOT_CONV_WS_COUNTER_BYTES + (size_t)splits * tiles * TC_BM * d->Cout * sizeof(float);
-    if (splits < 2 || need > d->workspace_bytes || (size_t)ctas * sizeof(unsigned) > SMOT_CONV_WS_COUNTER_BYTES) splits = 1;
   }
   a.splits = splits;
   a.chunks_per_split = (all_chunks + splits - 1) / splits;
@@ -486,10 +498,16 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   const bool shallow = force ? atoi(force) == 2 : (tiles * (d->Cout / BN) >= 296 && a.taps * a.cin_chunks <= 36);
   // at most one CTA per SM: nothing else hides the ~1 us TMA round trip, so run an 8-deep ring (192 KB)
   const bool deep = force ? atoi(force) == 8 : ((long long)grid.x * grid.y * grid.z <= 148 && all_chunks >= 8);
-  if (BN == 256) return launch_tc<256, 3>(tmA, tmB, a, grid, st);  // 48 KB stages, 1 CTA / SM
-  if (BN == 128) return shallow ? launch_tc<128, 2>(tmA, tmB, a, grid, st) : launch_tc<128, 3>(tmA, tmB, a, grid, st);
-  if (deep) return launch_tc<64, 8>(tmA, tmB, a, grid, st);
-  return shallow ? launch_tc<64, 2>(tmA, tmB, a, grid, st) : launch_tc<64, 4>(tmA, tmB, a, grid, st);
+  int rc;
+  if (BN == 256) rc = launch_tc<256, 3>(tmA, tmB, a, grid, st);  // 48 KB stages, 1 CTA / SM
+  else if (BN == 128) rc = shallow ? launch_tc<128, 2>(tmA, tmB, a, grid, st) : launch_tc<128, 3>(tmA, tmB, a, grid, st);
+  else if (deep) rc = launch_tc<64, 8>(tmA, tmB, a, grid, st);
+  else rc = shallow ? launch_tc<64, 2>(tmA, tmB, a, grid, st) : launch_tc<64, 4>(tmA, tmB, a, grid, st);
+  if (rc != SMOT_OK || a.splits == 1) return rc;
+  const size_t total_out = (size_t)a.num_tiles * TC_BM * (d->Cout / 4);
+  splitk_reduce_kernel<<<(unsigned)((total_out + 255) / 256), 256, 0, st>>>(a);
+  SMOT_CHECK_LAUNCH("smot_conv2d(split-K reduce)");
+  return SMOT_OK;
 }
 
 }  // namespace smot
