@@ -18,7 +18,7 @@ def t_us(row):
 
 
 idx = [i for i, r in enumerate(rows) if "image_to_nhwc" in r["Kernel Name"]]
-a, b = idx[1], idx[2]
+a, b = (idx[1], idx[2]) if len(idx) > 2 else (idx[0], idx[1])
 tot = 0
 agg = collections.defaultdict(lambda: [0, 0.0])
 for r in rows[a:b]:
