@@ -73,17 +73,28 @@ __global__ void __launch_bounds__(256) xcorr_kernel(const T* __restrict__ x, con
 // Tensor-core form of the depthwise correlation (fp16 storage, fp32 accumulation).
 // For one (track, channel):  Out(16x16) = sum_u X[u:u+16, 0:32) * B_u,  B_u[m][j] = K[u][m-j] (banded
 // Toeplitz of template row u, zero outside 0 <= m-j < 15): 15 x (2 k-steps x 2 n-tiles) mma.sync.m16n8k16,
-// ~2.1x redundant MACs on a pipe >10x faster than the FP32 FMAs -> the kernel becomes bound by staging.
-// A fragments come by ldmatrix from a per-channel transposed copy of the window (xT[c][row][col], row pitch
-// 80 B: conflict-free); B fragments are single 32-bit shared loads from two zero-padded copies of the
-// template row (one shifted by an element so odd offsets stay 4-byte aligned).
+// ~2.1x redundant MACs on a pipe >10x faster than the FP32 FMAs -> the kernel is bound by staging, so the
+// staging is what is organised carefully:
+//  * one CTA = 16 channels of one track, one warp per channel in the MMA phase;
+//  * window: a warp copies one (window row, 8-channel group) per step, lane = column: 16-byte global loads
+//    (all issued before the first store), 2-byte transposing stores into per-channel planes
+//    xT[c][row][col] (row pitch 80 B -> ldmatrix and the stores are bank-conflict free);
+//  * template: staged the same way straight into TWO zero-padded copies of every template row
+//    (kz[c][u][p][32]: K[u][v] at half 8 - p + v), so that a B fragment register (K[u][d], K[u][d+1]) is ONE
+//    aligned 32-bit load for even and odd d alike.  With d0 = 2t - g the four MMAs of a (u) step need only the
+//    words at d0, d0+8, d0+16: the operands at d0-8 and d0+24 are structurally zero (15 taps);
+//  * results leave through the (dead) first 512 B of the warp's own window plane, packed half2, and are
+//    written with 16-byte stores.
 // ---------------------------------------------------------------------------------------------
 constexpr int XM_CG = 16;                 // channels per CTA
-constexpr int XM_WARPS = 16;              // one channel per warp: the per-channel chain (template rows -> 60 dependent MMAs) runs 16-wide
-constexpr int XM_PITCH = 40;              // halves per window row in xT (30 data + zero pad; 80 B)
-constexpr int XM_KZ = 48;                 // halves per zero-padded template-row copy
-constexpr int XM_CSTRIDE = 30 * XM_PITCH + 8;  // halves between channel planes of xT (604 words: 8 banks apart mod 32)
-constexpr int XM_ILP = 8;                 // 16-byte window loads in flight per thread while staging
+constexpr int XM_WARPS = 16;              // one channel per warp
+constexpr int XM_PITCH = 40;              // halves per window row in xT (30 data + 2 zero + pad; 80 B)
+constexpr int XM_CSTRIDE = 30 * XM_PITCH + 8;  // halves between channel planes of xT (2416 B, 16-byte multiple)
+constexpr int XM_KROW = 32;               // halves per zero-padded template-row copy
+constexpr int XM_KPLANE = 15 * 2 * XM_KROW;    // halves per channel in kz
+constexpr int XM_SMEM = (XM_CG * XM_CSTRIDE + XM_CG * XM_KPLANE) * 2;
+static_assert(XM_CG == XM_WARPS, "the MMA phase maps one channel to one warp");
+static_assert((XM_CG * XM_CSTRIDE * 2) % 16 == 0 && (XM_CSTRIDE * 2) % 16 == 0, "16-byte alignment of the planes");
 
 __device__ __forceinline__ void xm_ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -99,100 +110,105 @@ __device__ __forceinline__ void xm_mma(float* c, const uint32_t* a, uint32_t b0,
 __global__ void __launch_bounds__(XM_WARPS * 32) xcorr_mma_kernel(const __half* __restrict__ x, const __half* __restrict__ k,
                                                                  __half* __restrict__ out, int C) {
   constexpr int S = 30, TT = 15, O = 16;
+  constexpr int XSTEPS = (S * 2 + XM_WARPS - 1) / XM_WARPS;    // (window row, channel half) pairs per warp
+  constexpr int KSTEPS = (TT * 2 + XM_WARPS - 1) / XM_WARPS;   // (template row, channel half) pairs per warp
   extern __shared__ __align__(16) unsigned char xm_raw[];
-  __half* xT = reinterpret_cast<__half*>(xm_raw);                                   // [CG][CSTRIDE]    38656 B
-  __half* kraw = xT + XM_CG * XM_CSTRIDE;                                         // [T*T][CG]         7200 B
-  __half (*kz)[TT][2][XM_KZ] = reinterpret_cast<__half (*)[TT][2][XM_KZ]>(kraw + TT * TT * XM_CG);  // 11520 B
-  __half* ost = reinterpret_cast<__half*>(kz) + XM_WARPS * TT * 2 * XM_KZ;          // [O*O][CG]         8192 B
+  __half* xT = reinterpret_cast<__half*>(xm_raw);     // [CG][CSTRIDE]
+  __half* kz = xT + XM_CG * XM_CSTRIDE;             // [CG][TT][2][KROW]
   const int n = blockIdx.y, c0 = blockIdx.x * XM_CG;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // zero the pad columns of xT and the padded template rows
-  for (int i = tid; i < XM_CG * S * (XM_PITCH - S); i += blockDim.x) {
-    const int r = i / (XM_PITCH - S), cpad = i - r * (XM_PITCH - S);
-    xT[(r / S) * XM_CSTRIDE + (r % S) * XM_PITCH + S + cpad] = __float2half(0.f);
-  }
-  for (int i = tid; i < XM_WARPS * TT * 2 * XM_KZ / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(&kz[0][0][0][0])[i] = 0u;
-  // stage the window transposed: 16-byte global reads (8 channels of one position) issued in batches of
-  // XM_ILP so that several are in flight per thread, then 2-byte scattered stores (channel stride padded
-  // to XM_CSTRIDE halves: the 8 channels of a chunk land in 8 different banks)
+  // ---- global loads first (in flight while the zero fill runs)
   const __half* xb = x + (size_t)n * S * S * C + c0;
-  constexpr int XM_ITEMS = S * S * (XM_CG / 8);
-  for (int b0 = 0; b0 < XM_ITEMS; b0 += XM_ILP * XM_WARPS * 32) {
-    uint4 v[XM_ILP];
+  const __half* kb = k + (size_t)n * TT * TT * C + c0;
+  uint4 xv[XSTEPS], kv[KSTEPS];
 #pragma unroll
-    for (int u = 0; u < XM_ILP; ++u) {
-      const int i = b0 + u * XM_WARPS * 32 + tid;
-      if (i < XM_ITEMS) v[u] = *reinterpret_cast<const uint4*>(xb + (size_t)(i / (XM_CG / 8)) * C + (i % (XM_CG / 8)) * 8);
+  for (int it = 0; it < XSTEPS; ++it) {
+    const int idx = it * XM_WARPS + warp, r = idx >> 1, q = idx & 1;
+    if (idx < S * 2 && lane < S) xv[it] = *reinterpret_cast<const uint4*>(xb + (size_t)(r * S + lane) * C + q * 8);
+  }
+#pragma unroll
+  for (int it = 0; it < KSTEPS; ++it) {
+    const int idx = it * XM_WARPS + warp, u = idx >> 1, q = idx & 1;
+    if (idx < TT * 2 && lane < TT) kv[it] = *reinterpret_cast<const uint4*>(kb + (size_t)(u * TT + lane) * C + q * 8);
+  }
+  // ---- zero fill: the padded template rows entirely, columns 30/31 of every window row
+  {
+    uint4* kz4 = reinterpret_cast<uint4*>(kz);
+    for (int i = tid; i < XM_CG * XM_KPLANE / 8; i += XM_WARPS * 32) kz4[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < XM_CG * S) {
+      const int c = tid / S, r = tid - c * S;
+      *reinterpret_cast<uint32_t*>(xT + c * XM_CSTRIDE + r * XM_PITCH + S) = 0u;
     }
+  }
+  // ---- transposing stores of the window
 #pragma unroll
-    for (int u = 0; u < XM_ILP; ++u) {
-      const int i = b0 + u * XM_WARPS * 32 + tid;
-      if (i < XM_ITEMS) {
-        const int pos = i / (XM_CG / 8), q = i % (XM_CG / 8);
-        const __half* h = reinterpret_cast<const __half*>(&v[u]);
-        const int row = pos / S, col = pos - row * S;
+  for (int it = 0; it < XSTEPS; ++it) {
+    const int idx = it * XM_WARPS + warp, r = idx >> 1, q = idx & 1;
+    if (idx < S * 2 && lane < S) {
+      const __half* h = reinterpret_cast<const __half*>(&xv[it]);
+      __half* dst = xT + (q * 8) * XM_CSTRIDE + r * XM_PITCH + lane;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) xT[(q * 8 + e) * XM_CSTRIDE + row * XM_PITCH + col] = h[e];
+      for (int e = 0; e < 8; ++e) dst[e * XM_CSTRIDE] = h[e];
+    }
+  }
+  __syncthreads();  // template zero fill complete before the template values land
+#pragma unroll
+  for (int it = 0; it < KSTEPS; ++it) {
+    const int idx = it * XM_WARPS + warp, u = idx >> 1, q = idx & 1;
+    if (idx < TT * 2 && lane < TT) {
+      const __half* h = reinterpret_cast<const __half*>(&kv[it]);
+      __half* dst = kz + (q * 8) * XM_KPLANE + u * 2 * XM_KROW + 8 + lane;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dst[e * XM_KPLANE] = h[e];                  // copy 0: K[u][v] at half 8 + v
+        dst[e * XM_KPLANE + XM_KROW - 1] = h[e];    // copy 1: K[u][v] at half 7 + v
       }
     }
   }
-  const __half* kb = k + (size_t)n * TT * TT * C + c0;
-  for (int i = tid; i < TT * TT * (XM_CG / 8); i += blockDim.x) {
-    const int pos = i / (XM_CG / 8), q = i % (XM_CG / 8);
-    *reinterpret_cast<uint4*>(kraw + pos * XM_CG + q * 8) = *reinterpret_cast<const uint4*>(kb + (size_t)pos * C + q * 8);
-  }
   __syncthreads();
+  // ---- MMA phase: warp = channel
   const int g = lane >> 2, t = lane & 3;
   const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
   const int par = g & 1;
-  const uint32_t xT_s = (uint32_t)__cvta_generic_to_shared(xT);
-  for (int cc = 0; cc < XM_CG / XM_WARPS; ++cc) {
-    const int c = warp * (XM_CG / XM_WARPS) + cc;
-    // template rows of channel c into the two zero-padded copies: kz[u][0][16+v] = kz[u][1][15+v] = K[u][v]
-    for (int i = lane; i < TT * TT; i += 32) {
-      const int u = i / TT, v = i - u * TT;
-      const __half val = kraw[i * XM_CG + c];
-      kz[warp][u][0][16 + v] = val;
-      kz[warp][u][1][15 + v] = val;
+  const int c = warp;
+  const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(xT + c * XM_CSTRIDE + a_row * XM_PITCH + a_kh * 8);
+  // word (8 - par + d0) / 2 of copy `par`, d0 = 2t - g in [-7, 6]
+  const uint32_t* kzw = reinterpret_cast<const uint32_t*>(kz + c * XM_KPLANE + par * XM_KROW) + ((8 + 2 * t - g - par) >> 1);
+  float acc[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll 5
+  for (int u = 0; u < TT; ++u) {
+    const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];  // K[u][d0 + {0,8,16} (+1)]
+    uint32_t af[4];
+    // B[k][n] = K[u][k - n]; register b0 holds k = 16ks + 2t (+1), b1 the same + 8; n = 8nt + g
+    xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2), af[0], af[1], af[2], af[3]);             // window cols 0..15
+    xm_mma(acc[0], af, k0, k8);      // nt 0: d = d0, d0 + 8
+    xm_mma(acc[1], af, 0u, k0);      // nt 1: d = d0 - 8 (no tap), d0
+    xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2 + 32), af[0], af[1], af[2], af[3]);        // window cols 16..31
+    xm_mma(acc[0], af, k16, 0u);     // nt 0: d = d0 + 16, d0 + 24 (no tap)
+    xm_mma(acc[1], af, k8, k16);     // nt 1: d = d0 + 8, d0 + 16
+  }
+  // ---- D fragments -> the warp's own (now dead) window plane as [O*O] halves, then 16-byte stores
+  __syncwarp();
+  {
+    __half2* ost = reinterpret_cast<__half2*>(xT + c * XM_CSTRIDE);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      ost[g * 8 + nt * 4 + t] = __floats2half2_rn(acc[nt][0], acc[nt][1]);
+      ost[(g + 8) * 8 + nt * 4 + t] = __floats2half2_rn(acc[nt][2], acc[nt][3]);
     }
-    __syncwarp();
-    float acc[2][4];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-    const uint32_t xc_s = xT_s + (uint32_t)(c * XM_CSTRIDE * 2);
-#pragma unroll 3
-    for (int u = 0; u < TT; ++u) {
-      const uint32_t* kzw = reinterpret_cast<const uint32_t*>(&kz[warp][u][par][0]);
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        uint32_t af[4];
-        xm_ldmatrix_x4(xc_s + (uint32_t)(((u + a_row) * XM_PITCH + ks * 16 + a_kh * 8) * 2), af[0], af[1], af[2], af[3]);
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          const int d0 = 16 * ks + 2 * t - 8 * nt - g;  // B[k = 16ks+2t (+1)][n = 8nt+g] = K[u][d0 (+1)]
-          const int w = (16 + d0 - par) >> 1;
-          xm_mma(acc[nt], af, kzw[w], kzw[w + 4]);
-        }
-      }
-    }
-    // D fragment -> staging tile [pos][channel]
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = g + 8 * h, j = nt * 8 + 2 * t;
-        ost[(i * O + j) * XM_CG + c] = __float2half_rn(acc[nt][2 * h]);
-        ost[(i * O + j + 1) * XM_CG + c] = __float2half_rn(acc[nt][2 * h + 1]);
-      }
-    __syncwarp();
   }
   __syncthreads();
-  __half* ob = out + (size_t)n * O * O * C + c0;
-  for (int i = tid; i < O * O * (XM_CG / 8); i += blockDim.x) {
-    const int pos = i / (XM_CG / 8), q = i % (XM_CG / 8);
-    *reinterpret_cast<uint4*>(ob + (size_t)pos * C + q * 8) = *reinterpret_cast<const uint4*>(ost + pos * XM_CG + q * 8);
+  {
+    const int q = warp & 1, pos = (warp >> 1) * 32 + lane;   // 256 positions x 2 channel halves = 512 threads
+    const __half* src = xT + (q * 8) * XM_CSTRIDE + pos;
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = src[e * XM_CSTRIDE];
+    *reinterpret_cast<uint4*>(out + ((size_t)n * O * O + pos) * C + c0 + q * 8) = *reinterpret_cast<const uint4*>(h);
   }
 }
 
@@ -413,7 +429,6 @@ extern "C" int smot_xcorr(const void* x, const void* k, void* out, int n, int ch
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SMOT_F16 && S == 30 && T == 15 && channels % XM_CG == 0 &&
       (((uintptr_t)x | (uintptr_t)k | (uintptr_t)out) & 15) == 0) {
-    constexpr int XM_SMEM = (XM_CG * XM_CSTRIDE + 15 * 15 * XM_CG + XM_WARPS * 15 * 2 * XM_KZ + 16 * 16 * XM_CG) * 2;
     static bool attr = false;
     if (!attr) {
       cudaError_t e = cudaFuncSetAttribute(xcorr_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XM_SMEM);

@@ -3,15 +3,20 @@
 // The reference does these steps with ~10 tiny ATen kernels plus a device->host copy of the NMS mask
 // and a serial host loop per call (upstream csrc/cuda/nms.cu), seven times per frame.  Here every step
 // stays on the device (fixed capacities, device-side counts), so the whole detection stage is
-// capturable in a CUDA graph.  A single CTA is far too slow for the O(n^2) / O(n) parts, so each job is
-// split so that the quadratic / linear work spreads over many SMs and only O(n) bookkeeping is serial:
+// capturable in a CUDA graph.  Every job is latency bound, so each is split so that the quadratic / linear
+// work spreads over many SMs, all repeated passes run out of shared memory, and only O(n) bookkeeping is
+// serial:
 //
 //   sort + NMS   : nms_sort_kernel   (1 CTA / problem)  64-bit keys (score key << 32 | ~index), bitonic sort
-//                  nms_mask_kernel   (n/64 CTAs / problem) IoU(+1) bitmask, lane = candidate, word = ballot
-//                  nms_reduce_kernel (1 CTA / problem)  64 sorted rows per round: serial resolve + CTA-wide OR
-//   RPN top-k    : rpn_local_topk_kernel (1 CTA / ~10k anchors) exact local top-k by 64-bit radix select
+//                                    (or a stable compaction when the rows already arrive in order)
+//                  nms_mask_kernel   (one 64-thread CTA per 64x64 tile of the upper triangle) IoU(+1) bitmask
+//                  nms_reduce_kernel (1 CTA / problem)  bitmask staged in shared memory; 64 sorted rows per round:
+//                                    branch-free serial resolve by one thread + CTA-wide OR of the survivors' rows
+//   RPN top-k    : rpn_local_topk_kernel (1 CTA / ~10k anchors) keys staged once in shared memory, exact local
+//                                        top-k by radix select (11-bit digits, parallel threshold search)
 //                  rpn_merge_kernel      (1 CTA / level) top-k of the local winners, sort, anchor synthesis +
 //                                        BoxCoder decode + clip  (rpn_patch.py:15-52)
+//                  rpn_final_kernel      cross-level top-n by rank (each level is already sorted)
 //   box_decode_kernel: softmax + per-class decode + clip + track-row rule (inference.py:58-110).
 #include "common.cuh"
 
@@ -19,6 +24,7 @@ namespace smot {
 
 constexpr int SN_THREADS = 1024;
 constexpr int SN_MAX = 4096;
+constexpr int SN_CACHE_BYTES = 192 * 1024;  // largest bitmask nms_reduce_kernel stages in shared memory
 constexpr float BBOX_XFORM_CLIP = 4.135166556742356f;  // log(1000/16)
 
 struct SortNmsArgs {
@@ -30,6 +36,8 @@ struct SortNmsArgs {
   int n_max, np;  // np = power of two >= n_max
   float min_score, thresh;
   int max_keep, tag, append, fill_tail;
+  int presorted;    // rows arrive in (score desc, index asc) order: nms_sort_kernel only drops rows <= min_score
+  int cache_pitch;  // > 0: nms_reduce_kernel stages the bitmask in shared memory with this row pitch (words)
   int* out_index;
   float* out_boxes;
   float* out_scores;
@@ -45,18 +53,17 @@ struct SortNmsArgs {
   int in_step, out_step;
 };
 
+// one compare-exchange pair per thread and stage
 __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int np) {
   for (int k = 2; k <= np; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < np; i += blockDim.x) {
-        int ixj = i ^ j;
-        if (ixj > i) {
-          unsigned long long a = keys[i], b = keys[ixj];
-          bool desc = (i & k) == 0;
-          if (desc ? (a < b) : (a > b)) {
-            keys[i] = b;
-            keys[ixj] = a;
-          }
+      for (int t = threadIdx.x; t < (np >> 1); t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
+        const unsigned long long a = keys[i], b = keys[p];
+        const bool desc = (i & k) == 0;
+        if (desc ? (a < b) : (a > b)) {
+          keys[i] = b;
+          keys[p] = a;
         }
       }
       __syncthreads();
@@ -69,10 +76,42 @@ __global__ void __launch_bounds__(SN_THREADS) nms_sort_kernel(SortNmsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
   __shared__ int s_cnt;
+  __shared__ int wcnt[SN_THREADS / 32];
   const int prob = blockIdx.x;
   const float* boxes = a.boxes + (size_t)prob * a.in_step * a.box_stride;
   const float* scores = a.scores + (size_t)prob * a.in_step * a.score_stride;
   const int n = a.count ? min(a.count[prob], a.n_max) : a.n_max;
+  float4* sb = a.s_boxes + (size_t)prob * a.n_max;
+  int* si = a.s_index + (size_t)prob * a.n_max;
+  if (a.presorted) {
+    // stable compaction of the rows with score > min_score
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int base = 0;
+    for (int i0 = 0; i0 < n; i0 += SN_THREADS) {  // block-uniform trip count
+      const int i = i0 + threadIdx.x;
+      const bool valid = i < n && scores[(size_t)i * a.score_stride] > a.min_score;
+      const unsigned bal = __ballot_sync(0xffffffffu, valid);
+      if (lane == 0) wcnt[warp] = __popc(bal);
+      __syncthreads();
+      int before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < SN_THREADS / 32; ++w) {
+        const int c = wcnt[w];
+        total += c;
+        before += w < warp ? c : 0;
+      }
+      if (valid) {
+        const int pos = base + before + __popc(bal & ((1u << lane) - 1u));
+        const float* b = boxes + (size_t)i * a.box_stride;
+        sb[pos] = make_float4(b[0], b[1], b[2], b[3]);
+        si[pos] = i;
+      }
+      base += total;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) a.s_m[prob] = base;
+    return;
+  }
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   int local = 0;
@@ -91,8 +130,6 @@ __global__ void __launch_bounds__(SN_THREADS) nms_sort_kernel(SortNmsArgs a) {
   __syncthreads();
   bitonic_sort_desc(keys, a.np);
   const int m = s_cnt;
-  float4* sb = a.s_boxes + (size_t)prob * a.n_max;
-  int* si = a.s_index + (size_t)prob * a.n_max;
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
     const unsigned idx = 0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFull);
     const float* b = boxes + (size_t)idx * a.box_stride;
@@ -103,98 +140,111 @@ __global__ void __launch_bounds__(SN_THREADS) nms_sort_kernel(SortNmsArgs a) {
 }
 
 // ---- K2: suppression bitmask, mask[i][w] bit b set <=> j = 64w+b > i and IoU(i,j) > thresh -------
-//      grid (row blocks of 64, problems); one warp per (i, w) word: lane = candidate j (two rounds of 32)
-__global__ void __launch_bounds__(256) nms_mask_kernel(SortNmsArgs a) {
-  const int prob = blockIdx.y;
+//      grid (column block w, row block, problem), upper triangle only; thread = row i of the tile, the 64
+//      column boxes are broadcast from shared memory.  Words left of the diagonal are never written or read.
+__global__ void __launch_bounds__(64) nms_mask_kernel(SortNmsArgs a) {
+  __shared__ float4 cbox[64];
+  const int cb = blockIdx.x, rb = blockIdx.y, prob = blockIdx.z;
+  if (cb < rb) return;
   const int m = a.s_m[prob];
-  const int i0 = blockIdx.x * 64;
-  if (i0 >= m) return;
-  const int words = (m + 63) >> 6;
+  if ((cb << 6) >= m) return;
   const float4* __restrict__ sb = a.s_boxes + (size_t)prob * a.n_max;
-  unsigned long long* mask = a.mask + (size_t)prob * a.n_max * a.words_max;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int w_lo = i0 >> 6;  // words left of the diagonal block are all zero and never read
-  const int nw = words - w_lo;
-  for (int item = wid; item < 64 * nw; item += 8) {
-    const int i = i0 + item / nw, w = w_lo + item % nw;
-    if (i >= m) break;
-    const float4 bi = sb[i];
-    unsigned lo = 0u, hi = 0u;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int j = (w << 6) + half * 32 + lane;
-      bool hit = false;
-      if (j > i && j < m) {
-        const float4 bj = sb[j];
-        // disjoint boxes have IoU 0: skip the division (same result, most pairs are disjoint)
-        if (fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x) + 1.f > 0.f && fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y) + 1.f > 0.f)
-          hit = iou_plus1(bi, bj) > a.thresh;
-      }
-      const unsigned b = __ballot_sync(0xffffffffu, hit);
-      if (half == 0) lo = b; else hi = b;
-    }
-    if (lane == 0) mask[(size_t)i * a.words_max + w] = ((unsigned long long)hi << 32) | lo;
+  const int j0 = cb << 6, i = (rb << 6) + threadIdx.x;
+  cbox[threadIdx.x] = j0 + threadIdx.x < m ? sb[j0 + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  if (i >= m) return;
+  const float4 bi = sb[i];
+  const int jn = min(64, m - j0);
+  const int jb = cb == rb ? (int)threadIdx.x + 1 : 0;  // j > i
+  unsigned long long word = 0ull;
+  for (int b = jb; b < jn; ++b) {
+    const float4 bj = cbox[b];
+    // disjoint boxes have IoU 0: skip the division (same result, most pairs are disjoint)
+    if (fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x) + 1.f > 0.f && fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y) + 1.f > 0.f)
+      if (iou_plus1(bi, bj) > a.thresh) word |= 1ull << b;
   }
+  a.mask[((size_t)prob * a.n_max + i) * a.words_max + cb] = word;
 }
 
 // ---- K3: greedy reduction + outputs ------------------------------------------------------------
 __global__ void __launch_bounds__(SN_THREADS) nms_reduce_kernel(SortNmsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* kept_all = reinterpret_cast<int*>(smem_raw);  // sorted row of the k-th survivor, [np]
+  unsigned long long* cache = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)a.np * 4);
   __shared__ unsigned long long removed[SN_MAX / 64];
-  __shared__ unsigned long long diag[64];
-  __shared__ int kept_rows[64];
-  __shared__ int s_kept, s_nk, s_done;
+  __shared__ unsigned long long s_km;
+  __shared__ int s_kept, s_base, s_done;
   const int prob = blockIdx.x;
   const float* scores = a.scores + (size_t)prob * a.in_step * a.score_stride;
   const float4* __restrict__ sb = a.s_boxes + (size_t)prob * a.n_max;
   const int* __restrict__ si = a.s_index + (size_t)prob * a.n_max;
-  const unsigned long long* mask = a.mask + (size_t)prob * a.n_max * a.words_max;
+  const unsigned long long* gmask = a.mask + (size_t)prob * a.n_max * a.words_max;
   int* out_count = a.out_count + prob;
   const int m = a.s_m[prob];
   const int words = (m + 63) >> 6;
   if (threadIdx.x == 0) s_kept = 0, s_done = 0;
   for (int i = threadIdx.x; i < SN_MAX / 64; i += blockDim.x) removed[i] = 0ull;
-  __syncthreads();
   int kept_total;
   if (a.thresh <= 0.f || a.max_keep <= 0) {
+    __syncthreads();
     kept_total = max(min(m, a.max_keep), 0);
     for (int i = threadIdx.x; i < kept_total; i += blockDim.x) kept_all[i] = i;
   } else {
-    // 64 sorted rows per round: (A) stage the diagonal words, (B) one thread resolves the round serially,
-    // (C) the whole CTA ORs the survivors' rows into `removed`
+    // the upper triangle of the bitmask goes to shared memory once (when it fits): the rounds below are a
+    // dependent chain and must not wait for global loads
+    const unsigned long long* M = gmask;
+    int pitch = a.words_max;
+    if (a.cache_pitch > 0) {
+      for (int idx = threadIdx.x; idx < m * words; idx += blockDim.x) {
+        const int row = idx / words, w = idx - row * words;
+        if (w >= (row >> 6)) cache[row * a.cache_pitch + w] = gmask[(size_t)row * a.words_max + w];
+      }
+      M = cache;
+      pitch = a.cache_pitch;
+    }
+    __syncthreads();
+    // 64 sorted rows per round: (A) one thread resolves the round serially from the diagonal words (branch-free:
+    // the 64 loads do not depend on the chain), (B) the whole CTA ORs the survivors' rows into `removed`
     for (int c = 0; c < words; ++c) {
-      if (threadIdx.x < 64) {
-        const int row = (c << 6) + threadIdx.x;
-        diag[threadIdx.x] = row < m ? mask[(size_t)row * a.words_max + c] : 0ull;
-      }
-      __syncthreads();
       if (threadIdx.x == 0) {
-        unsigned long long cur = removed[c];
-        int kept = s_kept, nk = 0;
+        const unsigned long long* d = M + (size_t)(c << 6) * pitch + c;
         const int rows_here = min(64, m - (c << 6));
-        for (int b = 0; b < rows_here && kept + nk < a.max_keep; ++b) {
-          if (!((cur >> b) & 1ull)) {
-            kept_rows[nk] = (c << 6) + b;
-            kept_all[kept + nk] = (c << 6) + b;
-            ++nk;
-            cur |= diag[b];
-          }
+        unsigned long long cur = removed[c], km = 0ull;
+#pragma unroll 16
+        for (int b = 0; b < 64; ++b) {
+          const unsigned long long dv = b < rows_here ? d[(size_t)b * pitch] : 0ull;
+          const unsigned long long bit = 1ull << b;
+          const bool keep = (cur & bit) == 0ull;
+          cur |= keep ? dv : 0ull;
+          km |= keep ? bit : 0ull;
         }
-        s_nk = nk;
+        if (rows_here < 64) km &= (1ull << rows_here) - 1ull;
+        const int kept = s_kept, room = a.max_keep - kept;
+        int nk = __popcll(km);
+        if (nk >= room) {
+          for (; nk > room; --nk) km &= ~(1ull << (63 - __clzll((long long)km)));
+          s_done = 1;
+        }
+        s_km = km;
+        s_base = kept;
         s_kept = kept + nk;
-        if (kept + nk >= a.max_keep) s_done = 1;
       }
       __syncthreads();
+      const unsigned long long km = s_km;
+      if (threadIdx.x < 64 && ((km >> threadIdx.x) & 1ull))
+        kept_all[s_base + __popcll(km & ((1ull << threadIdx.x) - 1ull))] = (c << 6) + threadIdx.x;
       if (s_done) break;
-      const int nk = s_nk, nw = words - c - 1;
-      for (int item = threadIdx.x; item < nk * nw; item += blockDim.x) {
-        const int qq = item / nw, w = c + 1 + (item - qq * nw);
-        const unsigned long long v = mask[(size_t)kept_rows[qq] * a.words_max + w];
-        if (v) atomicOr(&removed[w], v);
+      const int nw = words - c - 1;
+      for (int item = threadIdx.x; item < 64 * nw; item += blockDim.x) {
+        const int b = item & 63, w = c + 1 + (item >> 6);
+        if ((km >> b) & 1ull) {
+          const unsigned long long v = M[(size_t)((c << 6) + b) * pitch + w];
+          if (v) atomicOr(&removed[w], v);
+        }
       }
       __syncthreads();
     }
+    __syncthreads();
     kept_total = s_kept;
   }
   __syncthreads();
@@ -243,19 +293,27 @@ static int launch_sort_nms(SortNmsArgs& a, int problems, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_MAX * 8);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_MAX * 4 + SN_CACHE_BYTES);
     if (e != cudaSuccess) {
       set_error("sort_nms: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return SMOT_ERR_CUDA;
     }
     attr_set = true;
   }
-  nms_sort_kernel<<<problems, SN_THREADS, (size_t)a.np * 8, st>>>(a);
+  nms_sort_kernel<<<problems, SN_THREADS, a.presorted ? 0 : (size_t)a.np * 8, st>>>(a);
   SMOT_CHECK_LAUNCH("sort_nms(sort)");
-  if (a.thresh > 0.f && a.max_keep > 0) {
-    nms_mask_kernel<<<dim3((a.n_max + 63) / 64, problems), 256, 0, st>>>(a);
+  const bool suppress = a.thresh > 0.f && a.max_keep > 0;
+  a.cache_pitch = 0;
+  size_t cache_bytes = 0;
+  if (suppress) {
+    const int blocks = (a.n_max + 63) / 64;
+    nms_mask_kernel<<<dim3(blocks, blocks, problems), 64, 0, st>>>(a);
     SMOT_CHECK_LAUNCH("sort_nms(mask)");
+    const int pitch = a.words_max | 1;  // odd pitch: a column of 64-bit words spreads over all banks
+    if ((size_t)a.n_max * pitch * 8 <= (size_t)SN_CACHE_BYTES) a.cache_pitch = pitch, cache_bytes = (size_t)a.n_max * pitch * 8;
   }
-  nms_reduce_kernel<<<problems, SN_THREADS, (size_t)a.np * 4, st>>>(a);
+  nms_reduce_kernel<<<problems, SN_THREADS, (size_t)a.np * 4 + cache_bytes, st>>>(a);
   SMOT_CHECK_LAUNCH("sort_nms(reduce)");
   return SMOT_OK;
 }
@@ -265,72 +323,106 @@ static int launch_sort_nms(SortNmsArgs& a, int problems, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 constexpr int RPN_CHUNK = 10752;   // anchors per local-top-k CTA (level 0 of a 704x1280 frame = 16 chunks)
 constexpr int RPN_MAX_CHUNKS = 256;
+constexpr int RPN_IDX_BITS = 22;   // anchors per level < 4M
+constexpr int RPN_KEY_BITS = 32 + RPN_IDX_BITS;
+constexpr unsigned long long RPN_IDX_MASK = (1ull << RPN_IDX_BITS) - 1ull;
+constexpr int RPN_MERGE_SMEM_KEYS = 20 * 1024;  // local winners rpn_merge_kernel stages in shared memory (160 KB)
 
 struct RpnArgs {
   smot_rpn_level lv[SMOT_MAX_LEVELS];
+  int num_levels;
   int pre_nms_top_n;  // <= 1024
+  int post_nms_top_n, final_top_n;
   float min_size;
   int img_w, img_h, amodal;
   int nchunks;
   int chunk_first[SMOT_MAX_LEVELS + 1];  // chunks of level l are [chunk_first[l], chunk_first[l+1])
+  int merge_in_smem;                     // every level's local winners fit RPN_MERGE_SMEM_KEYS
   unsigned long long* local;             // [nchunks][1024] composite keys of the local winners (0 = empty)
   float* cand_boxes;                     // [levels][pre_nms_top_n][4]
   float* cand_scores;                    // [levels][pre_nms_top_n]
   int* cand_count;                       // [levels]
+  const float* kept_boxes;               // [levels][post_nms_top_n][4]  per-level NMS survivors, score order
+  const float* kept_scores;              // [levels][post_nms_top_n]
+  const int* kept_count;                 // [levels]
+  float* out_boxes;
+  float* out_scores;
+  int* out_count;
 };
 
-// Exact top-k of n UNIQUE 64-bit keys by radix select (8 bits per pass, MSB first).  get(i) returns the key of
-// element i (0 for "absent").  The k winners are written to out[0..k) in arbitrary order, out[k..1024) = 0.
-// All threads of the CTA must call this; n, k uniform; k <= 1024.
-template <typename GetKey>
-__device__ void select_topk_u64(GetKey get, int n, int k, unsigned long long* out) {
-  __shared__ unsigned hist[256];
+// composite key: (objectness logit as monotone u32) << 22 | (2^22 - 1 - anchor index in the level): unique, and
+// descending key order = (logit desc, anchor index asc)
+__device__ __forceinline__ unsigned long long rpn_key(float logit, int g) {
+  return ((unsigned long long)float_key(logit) << RPN_IDX_BITS) | (RPN_IDX_MASK - (unsigned long long)g);
+}
+
+// Exact top-k of n UNIQUE keys of RPN_KEY_BITS bits by radix select (11-bit digits, MSB first); keys[] (shared or
+// global memory) holds 0 for "absent".  The k winners go to out[0..k) in arbitrary order, out[k..1024) = 0.
+// All threads of the CTA (1024) must call this; n, k uniform; k <= 1024.
+__device__ void select_topk_u64(const unsigned long long* keys, int n, int k, unsigned long long* out) {
+  constexpr int DIGIT = 11, BINS = 1 << DIGIT;
+  __shared__ unsigned hist[BINS];
+  __shared__ unsigned wsum[32];
   __shared__ unsigned long long s_prefix;
-  __shared__ unsigned s_need, s_cnt;
+  __shared__ unsigned s_need, s_cnt, s_active;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) out[i] = 0ull;
-  if (threadIdx.x == 0) s_prefix = 0ull, s_need = (unsigned)k, s_cnt = 0u;
+  if (threadIdx.x == 0) s_prefix = 0ull, s_need = (unsigned)k, s_cnt = 0u, s_active = (unsigned)n;
   __syncthreads();
   if (k > 0 && n > 0) {
-    for (int pass = 0; pass < 8; ++pass) {
-      const int shift = 56 - 8 * pass;
-      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+    for (int hi = RPN_KEY_BITS; hi > 0;) {
+      const int width = hi < DIGIT ? hi : DIGIT, shift = hi - width;
+      for (int i = threadIdx.x; i < BINS; i += blockDim.x) hist[i] = 0u;
       __syncthreads();
       const unsigned long long prefix = s_prefix;
-      const unsigned long long pmask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-      for (int b0 = 0; b0 < n; b0 += 4 * blockDim.x) {  // block-uniform trip count, 4 loads in flight
-        unsigned long long key[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = b0 + u * blockDim.x + threadIdx.x;
-          key[u] = i < n ? get(i) : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          // warp-aggregated: scores cluster in a few bins, one atomic per distinct bin per warp
-          const bool act = key[u] != 0ull && (key[u] & pmask) == prefix;
-          const unsigned bin = act ? (unsigned)((key[u] >> shift) & 0xFFull) : 0xFFFFFFFFu;
-          const unsigned peers = __match_any_sync(0xffffffffu, bin);
-          if (act && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+      const unsigned long long pmask = hi >= 64 ? 0ull : (~0ull << hi);
+      const unsigned dmask = (1u << width) - 1u;
+      // many candidates in few bins (first pass, or heavy ties): one atomic per distinct bin per warp
+      const bool aggregate = s_active > 4096u;
+      for (int b0 = 0; b0 < n; b0 += blockDim.x) {  // block-uniform trip count
+        const int i = b0 + threadIdx.x;
+        const unsigned long long key = i < n ? keys[i] : 0ull;
+        const bool act = key != 0ull && (key & pmask) == prefix;
+        const unsigned bin = (unsigned)(key >> shift) & dmask;
+        if (aggregate) {
+          const unsigned peers = __match_any_sync(0xffffffffu, act ? bin : 0xFFFFFFFFu);
+          if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+        } else if (act) {
+          atomicAdd(&hist[bin], 1u);
         }
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        unsigned need = s_need, cum = 0u;
-        int b = 255;
-        for (; b > 0; --b) {
-          if (cum + hist[b] >= need) break;
-          cum += hist[b];
+      // parallel threshold search: thread t owns bins 2t, 2t+1; E = number of keys in bins above 2t+1
+      {
+        const unsigned h0 = hist[2 * threadIdx.x], h1 = hist[2 * threadIdx.x + 1], s = h0 + h1;
+        unsigned v = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned u = __shfl_down_sync(0xffffffffu, v, o);
+          if (lane + o < 32) v += u;
         }
-        s_need = need - cum;
-        s_prefix = prefix | ((unsigned long long)b << shift);
+        if (lane == 0) wsum[warp] = v;
+        __syncthreads();
+        unsigned E = v - s;
+        for (int w = warp + 1; w < 32; ++w) E += wsum[w];
+        const unsigned need = s_need;
+        __syncthreads();  // everyone has read s_need before the owner of the threshold bin rewrites it
+        if (E < need && need <= E + h1) {
+          s_need = need - E, s_active = h1;
+          s_prefix = prefix | ((unsigned long long)(2 * threadIdx.x + 1) << shift);
+        } else if (E + h1 < need && need <= E + s) {
+          s_need = need - E - h1, s_active = h0;
+          s_prefix = prefix | ((unsigned long long)(2 * threadIdx.x) << shift);
+        }
+        // fewer than `need` keys present: no bin qualifies, the digit stays 0 and everything present is taken
       }
       __syncthreads();
-      // fewer than k present keys: the threshold collapses to 0 and everything present is taken
+      hi = shift;
     }
     const unsigned long long T = s_prefix;  // the k-th largest key (0 if fewer than k keys exist)
     for (int b0 = 0; b0 < n; b0 += blockDim.x) {
       const int i = b0 + threadIdx.x;
-      const unsigned long long key = i < n ? get(i) : 0ull;
+      const unsigned long long key = i < n ? keys[i] : 0ull;
       if (key != 0ull && key >= T) {
         const unsigned pos = atomicAdd(&s_cnt, 1u);
         if (pos < 1024u) out[pos] = key;
@@ -341,6 +433,8 @@ __device__ void select_topk_u64(GetKey get, int n, int k, unsigned long long* ou
 }
 
 __global__ void __launch_bounds__(1024) rpn_local_topk_kernel(const RpnArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);  // [RPN_CHUNK]
   __shared__ unsigned long long win[1024];
   int lvl = 0;
   while (lvl + 1 < SMOT_MAX_LEVELS && (int)blockIdx.x >= a.chunk_first[lvl + 1]) ++lvl;
@@ -350,17 +444,18 @@ __global__ void __launch_bounds__(1024) rpn_local_topk_kernel(const RpnArgs a) {
   const int k = min(a.pre_nms_top_n, count);
   const float* __restrict__ head = L.head;
   const int A = L.A, ld = L.head_ld;
-  auto get = [&](int i) -> unsigned long long {
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
     const int g = start + i;  // anchor index within the level: (cell * A + a)
-    const float logit = head[(size_t)(g / A) * ld + (g % A)];
-    return ((unsigned long long)float_key(logit) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)g);
-  };
-  select_topk_u64(get, count, k, win);
+    keys[i] = rpn_key(head[(size_t)(g / A) * ld + (g % A)], g);
+  }
+  __syncthreads();
+  select_topk_u64(keys, count, k, win);
   unsigned long long* dst = a.local + (size_t)blockIdx.x * 1024;
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = win[i];
 }
 
 __global__ void __launch_bounds__(1024) rpn_merge_kernel(const RpnArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned long long cand[1024];
   const int lvl = blockIdx.x;
   const smot_rpn_level& L = a.lv[lvl];
@@ -372,8 +467,13 @@ __global__ void __launch_bounds__(1024) rpn_merge_kernel(const RpnArgs a) {
   if (c1 - c0 == 1) {
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) cand[i] = src[i];
     __syncthreads();
+  } else if (a.merge_in_smem) {
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = src[i];
+    __syncthreads();
+    select_topk_u64(keys, n, k, cand);
   } else {
-    select_topk_u64([&](int i) -> unsigned long long { return src[i]; }, n, k, cand);
+    select_topk_u64(src, n, k, cand);
   }
   bitonic_sort_desc(cand, 1024);
   // ---- decode the k candidates in sorted order
@@ -385,7 +485,7 @@ __global__ void __launch_bounds__(1024) rpn_merge_kernel(const RpnArgs a) {
       cs[j] = -1.f;
       continue;
     }
-    const int i = (int)(0xFFFFFFFFu - (unsigned)(cand[j] & 0xFFFFFFFFull));
+    const int i = (int)(RPN_IDX_MASK - (cand[j] & RPN_IDX_MASK));
     const int cell = i / L.A, an = i - cell * L.A;
     const int y = cell / L.W, x = cell - y * L.W;
     const float* row = head + (size_t)cell * L.head_ld;
@@ -412,6 +512,40 @@ __global__ void __launch_bounds__(1024) rpn_merge_kernel(const RpnArgs a) {
     cs[j] = big ? score : -1.f;
   }
   if (threadIdx.x == 0) a.cand_count[lvl] = k;
+}
+
+// Cross-level top-n (upstream select_over_all_levels at test time: topk of the concatenated objectness).  Every
+// level's survivors are already in (score desc, position asc) order, so the global rank of a row is its own
+// position plus, per other level, the number of rows that precede it: rows of lower levels win ties (the order
+// topk sees in the level-major concatenation).  No sort, no CTA-wide synchronisation.
+__global__ void __launch_bounds__(256) rpn_final_kernel(const RpnArgs a) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int P = a.post_nms_top_n;
+  if (e == 0) {
+    int total = 0;
+    for (int l = 0; l < a.num_levels; ++l) total += min(a.kept_count[l], P);
+    *a.out_count = min(total, a.final_top_n);
+  }
+  if (e >= a.num_levels * P) return;
+  const int l = e / P, p = e - l * P;
+  if (p >= min(a.kept_count[l], P)) return;
+  const float s = a.kept_scores[e];
+  int rank = p;
+  for (int o = 0; o < a.num_levels; ++o) {
+    if (o == l) continue;
+    const float* so = a.kept_scores + (size_t)o * P;
+    int lo = 0, hi = min(a.kept_count[o], P);  // first position in level o that does NOT precede (l, p)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const float v = so[mid];
+      if (o < l ? v >= s : v > s) lo = mid + 1; else hi = mid;
+    }
+    rank += lo;
+  }
+  if (rank < a.final_top_n) {
+    reinterpret_cast<float4*>(a.out_boxes)[rank] = reinterpret_cast<const float4*>(a.kept_boxes)[e];
+    a.out_scores[rank] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -522,7 +656,7 @@ extern "C" int smot_sort_nms(const float* boxes, int box_stride, const float* sc
   SortNmsArgs a;
   a.boxes = boxes, a.box_stride = box_stride, a.scores = scores, a.score_stride = score_stride, a.count = count;
   a.n_max = n_max, a.min_score = min_score, a.thresh = thresh, a.max_keep = max_keep, a.tag = tag;
-  a.append = 1, a.fill_tail = 0;
+  a.append = 1, a.fill_tail = 0, a.presorted = 0;
   a.out_index = out_index, a.out_boxes = out_boxes, a.out_scores = out_scores, a.out_tag = out_tag, a.out_count = out_count;
   a.in_step = 0, a.out_step = 0;
   carve_sort_nms_ws(a, workspace, 1);
@@ -547,7 +681,6 @@ extern "C" size_t smot_rpn_select_workspace(int num_levels, int pre_nms_top_n) {
   b += align256(L * 4);                              // kept count per level
   b += align256((size_t)RPN_MAX_CHUNKS * 1024 * 8);  // local winners
   b += sort_nms_ws_bytes(num_levels, pre_nms_top_n); // per-level NMS
-  b += sort_nms_ws_bytes(1, num_levels * pre_nms_top_n);  // cross-level sort
   return b;
 }
 
@@ -563,7 +696,8 @@ extern "C" int smot_rpn_select(const smot_rpn_level* levels, int num_levels, int
   SMOT_CHECK_ARG(workspace_bytes >= smot_rpn_select_workspace(num_levels, pre_nms_top_n), "smot_rpn_select: workspace too small");
   for (int l = 0; l < num_levels; ++l)
     SMOT_CHECK_ARG(levels[l].head && levels[l].A >= 1 && levels[l].A <= SMOT_MAX_ANCHORS && levels[l].H > 0 && levels[l].W > 0 &&
-                       levels[l].head_ld >= 5 * levels[l].A,
+                       levels[l].head_ld >= 5 * levels[l].A &&
+                       (long long)levels[l].H * levels[l].W * levels[l].A <= (long long)RPN_IDX_MASK,
                    "smot_rpn_select: bad level %d", l);
   const int nchunks = rpn_chunk_count(levels, num_levels);
   SMOT_CHECK_ARG(nchunks <= RPN_MAX_CHUNKS, "smot_rpn_select: feature maps too large (%d chunks > %d)", nchunks, RPN_MAX_CHUNKS);
@@ -577,53 +711,59 @@ extern "C" int smot_rpn_select(const smot_rpn_level* levels, int num_levels, int
   float* kept_scores = (float*)w;  w += align256(L * P * 4);
   int* kept_count = (int*)w;       w += align256(L * 4);
   unsigned long long* local = (unsigned long long*)w; w += align256((size_t)RPN_MAX_CHUNKS * 1024 * 8);
-  void* ws_level = w;              w += sort_nms_ws_bytes(num_levels, pre_nms_top_n);
-  void* ws_merge = w;
+  void* ws_level = w;
 
   RpnArgs ra;
-  int nc = 0;
+  int nc = 0, widest = 0;
   for (int l = 0; l < SMOT_MAX_LEVELS; ++l) {
     ra.chunk_first[l] = nc;
     if (l < num_levels) {
       ra.lv[l] = levels[l];
-      nc += (levels[l].H * levels[l].W * levels[l].A + RPN_CHUNK - 1) / RPN_CHUNK;
+      const int c = (levels[l].H * levels[l].W * levels[l].A + RPN_CHUNK - 1) / RPN_CHUNK;
+      nc += c;
+      widest = c > widest ? c : widest;
     }
   }
   ra.chunk_first[SMOT_MAX_LEVELS] = nc;
+  ra.num_levels = num_levels;
   ra.nchunks = nc, ra.local = local;
-  ra.pre_nms_top_n = pre_nms_top_n, ra.min_size = min_size, ra.img_w = img_w, ra.img_h = img_h, ra.amodal = amodal;
+  ra.merge_in_smem = widest * 1024 <= RPN_MERGE_SMEM_KEYS;
+  ra.pre_nms_top_n = pre_nms_top_n, ra.post_nms_top_n = post_nms_top_n, ra.final_top_n = fpn_post_nms_top_n;
+  ra.min_size = min_size, ra.img_w = img_w, ra.img_h = img_h, ra.amodal = amodal;
   ra.cand_boxes = cand_boxes, ra.cand_scores = cand_scores, ra.cand_count = cand_count;
-  cudaError_t e;
-  rpn_local_topk_kernel<<<nc, 1024, 0, st>>>(ra);
+  ra.kept_boxes = kept_boxes, ra.kept_scores = kept_scores, ra.kept_count = kept_count;
+  ra.out_boxes = out_boxes, ra.out_scores = out_scores, ra.out_count = out_count;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(rpn_local_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RPN_CHUNK * 8);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(rpn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RPN_MERGE_SMEM_KEYS * 8);
+    if (e != cudaSuccess) {
+      set_error("smot_rpn_select: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return SMOT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  rpn_local_topk_kernel<<<nc, 1024, RPN_CHUNK * 8, st>>>(ra);
   SMOT_CHECK_LAUNCH("smot_rpn_select(local top-k)");
-  rpn_merge_kernel<<<num_levels, 1024, 0, st>>>(ra);
+  rpn_merge_kernel<<<num_levels, 1024, ra.merge_in_smem && widest > 1 ? (size_t)widest * 1024 * 8 : 0, st>>>(ra);
   SMOT_CHECK_LAUNCH("smot_rpn_select(merge)");
 
-  // per-level NMS, survivors into slots of post_nms_top_n rows, tails marked -1
+  // per-level NMS (the candidates are already in score order), survivors into slots of post_nms_top_n rows
   SortNmsArgs a;
   a.boxes = cand_boxes, a.box_stride = 4, a.scores = cand_scores, a.score_stride = 1, a.count = cand_count;
   a.n_max = pre_nms_top_n, a.min_score = -0.5f, a.thresh = nms_thresh, a.max_keep = post_nms_top_n, a.tag = 0;
-  a.append = 0, a.fill_tail = post_nms_top_n;
+  a.append = 0, a.fill_tail = post_nms_top_n, a.presorted = 1;
   a.out_index = nullptr, a.out_boxes = kept_boxes, a.out_scores = kept_scores, a.out_tag = nullptr, a.out_count = kept_count;
   a.in_step = pre_nms_top_n, a.out_step = post_nms_top_n;
   carve_sort_nms_ws(a, ws_level, num_levels);
   int rc = launch_sort_nms(a, num_levels, st);
   if (rc) return rc;
 
-  // cross-level top-k (sort only), level-major order among equal scores
-  e = cudaMemsetAsync(out_count, 0, sizeof(int), st);
-  if (e != cudaSuccess) {
-    set_error("smot_rpn_select: memset failed: %s", cudaGetErrorString(e));
-    return SMOT_ERR_CUDA;
-  }
-  SortNmsArgs m;
-  m.boxes = kept_boxes, m.box_stride = 4, m.scores = kept_scores, m.score_stride = 1, m.count = nullptr;
-  m.n_max = num_levels * post_nms_top_n, m.min_score = -0.5f, m.thresh = 0.f, m.max_keep = fpn_post_nms_top_n, m.tag = 0;
-  m.append = 1, m.fill_tail = 0;
-  m.out_index = nullptr, m.out_boxes = out_boxes, m.out_scores = out_scores, m.out_tag = nullptr, m.out_count = out_count;
-  m.in_step = 0, m.out_step = 0;
-  carve_sort_nms_ws(m, ws_merge, 1);
-  return launch_sort_nms(m, 1, st);
+  // cross-level top-n
+  rpn_final_kernel<<<(num_levels * post_nms_top_n + 255) / 256, 256, 0, st>>>(ra);
+  SMOT_CHECK_LAUNCH("smot_rpn_select(final)");
+  return SMOT_OK;
 }
 
 extern "C" int smot_box_decode(const float* head, int head_ld, const float* rois, const int* count, int n_max, int ncls,

@@ -222,17 +222,19 @@ def _rpn_cfg(amodal=False):
     return cfg
 
 
-@pytest.mark.parametrize("amodal", [False, True])
-def test_rpn_select_matches_oracle(amodal):
+# 192x320: one or two chunks per level; 704x1280: 16 chunks merged out of shared memory; 1056x1920: 36 chunks, merged
+# from global memory
+@pytest.mark.parametrize("amodal,size", [(False, (192, 320)), (True, (192, 320)), (False, (704, 1280)), (False, (1056, 1920))])
+def test_rpn_select_matches_oracle(amodal, size):
     cfg = _rpn_cfg(amodal)
     g = torch.Generator().manual_seed(21)
-    img_h, img_w, A = 192, 320, 3
+    (img_h, img_w), A = size, 3
     logits, deltas, heads = [], [], []
     for lvl in range(5):
         h, w = math.ceil(img_h / (4 << lvl)), math.ceil(img_w / (4 << lvl))
         lg = torch.randn(1, A, h, w, generator=g) * 2
-        if lvl == 0:
-            lg.view(-1)[::7] = 1.25  # many exactly tied logits straddling the top-k cut
+        if lvl == 0:  # many exactly tied logits straddling the top-1000 cut (about 500 above, n/7 tied)
+            lg.view(-1)[::7] = lg.view(-1).sort(descending=True).values[600]
         dl = torch.randn(1, 4 * A, h, w, generator=g) * 0.5
         logits.append(lg)
         deltas.append(dl)
