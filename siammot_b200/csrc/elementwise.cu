@@ -123,6 +123,67 @@ __global__ void groupnorm_relu_kernel(T* __restrict__ x, const float* __restrict
   }
 }
 
+// Register-resident variant for 4 channels per group and HW <= 256 (the EMM towers: 16x16 maps, 32 groups of 4):
+// one CTA per (sample, slab of 32 channels = 8 groups); thread = (pixel phase tid/8, group tid%8) keeps its
+// <= 8 pixels x 4 channels in registers, so the tensor is read once and written once; the two-pass variance
+// (mean first, then squared deviations) is kept.
+template <typename T>
+__global__ void __launch_bounds__(256) groupnorm4_relu_kernel(T* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, int HW, int C, int ld,
+                                                             float eps, int relu) {
+  constexpr int ITERS = 8;
+  const int slabs = C / 32;
+  const int n = blockIdx.x / slabs, c0 = (blockIdx.x % slabs) * 32;
+  const int q = threadIdx.x & 7, pr = threadIdx.x >> 3, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  T* base = x + (size_t)n * HW * ld + c0 + q * 4;
+  __shared__ float part[8][8];
+  float4 v[ITERS];
+  float sum = 0.f;
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int px = pr + it * 32;
+    v[it] = px < HW ? ld4(base + (size_t)px * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sum += (v[it].x + v[it].y) + (v[it].z + v[it].w);
+  }
+  const float inv = 1.f / (float)(HW * 4);
+  // group total: lanes q, q+8, q+16, q+24 of every warp, then the 8 warps
+  auto group_total = [&](float t) -> float {
+    t += __shfl_xor_sync(0xffffffffu, t, 8);
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
+    __syncthreads();  // previous use of part[] is over
+    if (lane < 8) part[warp][lane] = t;
+    __syncthreads();
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += part[w][q];
+    return r;
+  };
+  const float mean = group_total(sum) * inv;
+  float sq = 0.f;
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    if (pr + it * 32 < HW) {
+      const float dx = v[it].x - mean, dy = v[it].y - mean, dz = v[it].z - mean, dw = v[it].w - mean;
+      sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  const float rstd = rsqrtf(group_total(sq) * inv + eps);
+  const float4 gm = *reinterpret_cast<const float4*>(gamma + c0 + q * 4), bt = *reinterpret_cast<const float4*>(beta + c0 + q * 4);
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int px = pr + it * 32;
+    if (px < HW) {
+      float4 y;
+      y.x = (v[it].x - mean) * rstd * gm.x + bt.x;
+      y.y = (v[it].y - mean) * rstd * gm.y + bt.y;
+      y.z = (v[it].z - mean) * rstd * gm.z + bt.z;
+      y.w = (v[it].w - mean) * rstd * gm.w + bt.w;
+      if (relu) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);
+      st4(base + (size_t)px * ld, y);
+    }
+  }
+}
+
 static inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace smot
@@ -196,7 +257,14 @@ extern "C" int smot_groupnorm_relu(void* x, const float* gamma, const float* bet
                  "smot_groupnorm_relu: bad arguments");
   if (batch == 0) return SMOT_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == SMOT_F32)
+  const size_t esz = dtype == SMOT_F16 ? 2 : 4;
+  const bool fast = C == groups * 4 && C % 32 == 0 && HW <= 256 && ((uintptr_t)x % (4 * esz)) == 0 && ld % 4 == 0 &&
+                    ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0;
+  if (fast && dtype == SMOT_F32)
+    groupnorm4_relu_kernel<float><<<batch * (C / 32), 256, 0, st>>>((float*)x, gamma, beta, HW, C, ld, eps, relu);
+  else if (fast && dtype == SMOT_F16)
+    groupnorm4_relu_kernel<__half><<<batch * (C / 32), 256, 0, st>>>((__half*)x, gamma, beta, HW, C, ld, eps, relu);
+  else if (dtype == SMOT_F32)
     groupnorm_relu_kernel<float><<<batch * groups, 256, 0, st>>>((float*)x, gamma, beta, HW, C, ld, groups, eps, relu);
   else if (dtype == SMOT_F16)
     groupnorm_relu_kernel<__half><<<batch * groups, 256, 0, st>>>((__half*)x, gamma, beta, HW, C, ld, groups, eps, relu);

@@ -286,7 +286,7 @@ struct DecodeArgs {
   int use_centerness;
   float sigma, one_minus_sigma;
   int img_w, img_h, amodal;
-  int rows_per_cta;
+  int rows_per_cta, rows_max;
   unsigned long long* best;  // [n]
   float* out_boxes;
   float* out_conf;
@@ -321,31 +321,36 @@ __device__ __forceinline__ PixelEval eval_pixel(const float* c, float box_w, flo
   return e;
 }
 
+// grid (row bands, tracks): a CTA scores rows [y0, y1) of the upsampled map.  It upsamples horizontally only the
+// source rows its band touches (rows_per_cta / up + 4 at most), so the staging buffer is a few tens of KB and
+// several CTAs share an SM; the arithmetic per pixel is unchanged.
 __global__ void __launch_bounds__(256) emm_score_kernel(const DecodeArgs a) {
   extern __shared__ __align__(16) float dec_smem[];
   const int O = a.O, OW = a.O * a.up;
   float* maps_s = dec_smem;                 // [O*O][EMM_CH]
-  float* tmp = dec_smem + O * O * EMM_CH;   // [EMM_CH][O][OW] horizontally upsampled
+  float* tmp = dec_smem + O * O * EMM_CH;   // [EMM_CH][rows_max][OW] horizontally upsampled rows r_lo..r_hi
   const int n = blockIdx.y;
-  const float* mp = a.maps + (size_t)n * O * O * a.map_ld;
-  for (int i = threadIdx.x; i < O * O * EMM_CH; i += blockDim.x) maps_s[i] = mp[(size_t)(i / EMM_CH) * a.map_ld + (i % EMM_CH)];
-  __syncthreads();
   const float scale = 1.f / (float)a.up;
+  const int y0 = blockIdx.x * a.rows_per_cta, y1 = min(OW, y0 + a.rows_per_cta);
+  const int r_lo = cubic_taps(y0, scale, O).idx[0], r_hi = cubic_taps(y1 - 1, scale, O).idx[3];  // <= rows_max rows
+  const float* mp = a.maps + (size_t)n * O * O * a.map_ld;
+  for (int i = threadIdx.x + r_lo * O * EMM_CH; i < (r_hi + 1) * O * EMM_CH; i += blockDim.x)
+    maps_s[i] = mp[(size_t)(i / EMM_CH) * a.map_ld + (i % EMM_CH)];
+  __syncthreads();
   for (int x = threadIdx.x; x < OW; x += blockDim.x) {
     const CubicTap tx = cubic_taps(x, scale, O);
-    for (int r = 0; r < O; ++r)
+    for (int r = r_lo; r <= r_hi; ++r)
 #pragma unroll
       for (int ch = 0; ch < EMM_CH; ++ch) {
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = maps_s[(r * O + tx.idx[j]) * EMM_CH + ch];
-        tmp[(ch * O + r) * OW + x] = hsum4(v, tx.w);
+        tmp[(ch * a.rows_max + (r - r_lo)) * OW + x] = hsum4(v, tx.w);
       }
   }
   __syncthreads();
   const float box_w = a.tboxes[n * 4 + 2] - a.tboxes[n * 4 + 0];
   const float box_h = a.tboxes[n * 4 + 3] - a.tboxes[n * 4 + 1];
-  const int y0 = blockIdx.x * a.rows_per_cta, y1 = min(OW, y0 + a.rows_per_cta);
   unsigned long long best = 0ull;
   for (int x = threadIdx.x; x < OW; x += blockDim.x) {
     const float wx = a.hann[x];
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(256) emm_score_kernel(const DecodeArgs a) {
       for (int ch = 0; ch < EMM_CH; ++ch) {
         float v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = tmp[(ch * O + ty.idx[j]) * OW + x];
+        for (int j = 0; j < 4; ++j) v[j] = tmp[(ch * a.rows_max + (ty.idx[j] - r_lo)) * OW + x];
         c[ch] = hsum4(v, ty.w);
       }
       const PixelEval e = eval_pixel(c, box_w, box_h, a.hann[y] * wx, a.use_centerness, a.sigma, a.one_minus_sigma);
@@ -465,7 +470,9 @@ extern "C" int smot_emm_decode(const float* maps, int map_ld, int n, int O, int 
   if (n == 0) return SMOT_OK;
   SMOT_CHECK_ARG(maps && sr && tboxes && hann && out_boxes && out_conf && out_valid && scratch, "smot_emm_decode: null argument");
   const int OW = O * up;
-  const size_t smem = ((size_t)O * O * EMM_CH + (size_t)EMM_CH * O * OW) * sizeof(float);
+  const int rows_per_cta = up;                        // one source-row period per band
+  const int rows_max = min(O, rows_per_cta / up + 4);  // source rows a band can touch (4 taps)
+  const size_t smem = ((size_t)O * O * EMM_CH + (size_t)EMM_CH * rows_max * OW) * sizeof(float);
   SMOT_CHECK_ARG(smem <= 200 * 1024, "smot_emm_decode: response map %dx%d (x%d) does not fit shared memory", O, O, up);
   cudaStream_t st = (cudaStream_t)stream;
   static size_t attr_bytes = 0;
@@ -480,7 +487,7 @@ extern "C" int smot_emm_decode(const float* maps, int map_ld, int n, int O, int 
   DecodeArgs a;
   a.maps = maps, a.map_ld = map_ld, a.n = n, a.O = O, a.up = up, a.T = T, a.sr = sr, a.tboxes = tboxes, a.hann = hann;
   a.pad = pad, a.use_centerness = use_centerness, a.sigma = (float)sigma, a.one_minus_sigma = (float)(1.0 - sigma), a.img_w = img_w, a.img_h = img_h, a.amodal = amodal;
-  a.rows_per_cta = 32;
+  a.rows_per_cta = rows_per_cta, a.rows_max = rows_max;
   a.best = (unsigned long long*)scratch;
   a.out_boxes = out_boxes, a.out_conf = out_conf, a.out_valid = out_valid;
   cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)n * 8, st);

@@ -71,6 +71,8 @@ class _Plan(object):
         self.graph = None
         self.dev = engine.device
         self.dtype = engine.dtype
+        self.ws = engine.conv_ws      # split-K scratch of the stream this plan runs on
+        self.static_done = None       # event recorded after the plan when it runs on the side stream (forward_clip)
 
     def new(self, H, W, Cc, dtype=None, B=1):
         t = torch.zeros((B, H, W, Cc), dtype=dtype or self.dtype, device=self.dev)
@@ -79,7 +81,7 @@ class _Plan(object):
 
     def conv(self, x, name, out, residual=None, stride=1, pad=0, relu=False):
         w, scale, bias = self.e.weights[name]
-        d = ops.conv_desc(x, w, out, scale, bias, residual, stride, pad, relu, workspace=self.e.conv_ws)
+        d = ops.conv_desc(x, w, out, scale, bias, residual, stride, pad, relu, workspace=self.ws)
         self.keep.append(d)
         self.steps.append((lib().smot_conv2d, (C.byref(d),), "conv:" + name))
         return out
@@ -235,7 +237,7 @@ class _TrackPlan(object):
 
     def _conv(self, x, name, out, **kw):
         w, scale, bias = self.e.weights[name]
-        d = ops.conv_desc(x, w, out, scale, bias, workspace=self.e.conv_ws, **kw)
+        d = ops.conv_desc(x, w, out, scale, bias, workspace=self.e.conv_ws_track, **kw)
         self.keep.append(d)
         self.steps.append((lib().smot_conv2d, (C.byref(d),), "conv:" + name))
 
@@ -294,7 +296,11 @@ class Engine(object):
         self.hann = torch.hann_window(self.o_res * self.up, dtype=torch.float).to(self.device)
         self.pads = [int(T.PAD_PIXELS / ((2 ** i) * 4)) for i in range(len(T.POOLER_SCALES))]
         self._nms_ws = {}
-        self.conv_ws = ops.conv_workspace(self.device)  # shared by every conv (all launches are stream-ordered)
+        # split-K scratch: one for the frame-independent stage, one for the track stage -- forward_clip runs the two
+        # stages of consecutive frames on different streams, launches within a stage are stream-ordered
+        self.conv_ws = ops.conv_workspace(self.device)
+        self.conv_ws_track = ops.conv_workspace(self.device)
+        self._side = None
         self._track_plans = {}
         self._arenas = {}
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
@@ -562,8 +568,14 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     # per-frame entry points
     # ------------------------------------------------------------------------------------------
+    def side_stream(self):
+        """The stream forward_clip runs the frame-independent stage on (created on first use)."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def run_static(self, image, slot=0):
-        """image: (3,H,W) or (1,3,H,W) float tensor (any device).  Enqueues backbone..detections."""
+        """image: (3,H,W) or (1,3,H,W) float tensor (any device).  Enqueues backbone..detections on the current stream."""
         if image.dim() == 4:
             if image.shape[0] != 1:
                 raise ValueError("one image per forward (track_core.py:75 asserts the same)")
@@ -580,6 +592,7 @@ class Engine(object):
         n = rois.shape[0]
         B = self._box_buffers(n)
         Q = _Plan(self, P.H, P.W)
+        Q.ws = self.conv_ws_track
         Q.feats = P.feats
         self._box_steps(Q, B, rois, None, n, track_labels)
         Q.keep.append(B)

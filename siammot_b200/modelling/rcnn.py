@@ -408,29 +408,52 @@ class SiamMOT(nn.Module):
 
 
 def _forward_clip(self, frames, before_frame=None):
-    """Process consecutive frames of ONE video with the frame-independent stage of frame t+1 enqueued while
-    the host resolves frame t (double-buffered static plans).  Results are identical to calling the model
-    frame by frame; this is the throughput API (the reference has INFERENCE.CLIP_LEN but processes one
-    frame per forward, defaults.py:96, track_core.py:75).  frames: sequence / tensor of (3,H,W) frames.
+    """Process consecutive frames of ONE video as a two-stage pipeline: the frame-independent stage (backbone ..
+    detections, double-buffered static plans) of frame t+1 runs on a side stream while the track stage of frame t
+    runs on the current stream and the host resolves ids.  Results are identical to calling the model frame by
+    frame; this is the throughput API (the reference has INFERENCE.CLIP_LEN but processes one frame per forward,
+    defaults.py:96, track_core.py:75).  frames: sequence / tensor of (3,H,W) frames.
     before_frame(t): optional hook called right before frame t's tracker stage is enqueued."""
     if self.training:
         raise NotImplementedError("siammot_b200 is an inference engine: call .eval()")
     eng = self.engine()
     n_frames = len(frames)
     results = []
+    if not n_frames:
+        return results
+    cur = torch.cuda.current_stream(eng.device)
+    side = eng.side_stream()
+    side.wait_stream(cur)          # the frames (and anything else already enqueued) are visible to the side stream
+    slot_free = [None, None]       # event: every reader of the slot's buffers (track stage, template pooling) is enqueued-complete
+
+    def static(t):
+        with torch.cuda.stream(side):
+            if slot_free[t & 1] is not None:
+                side.wait_event(slot_free[t & 1])
+            P = eng.run_static(frames[t], t & 1)
+            if P.static_done is None:
+                P.static_done = torch.cuda.Event()
+            P.static_done.record(side)
+        return P
+
     with torch.no_grad():
-        P_next = eng.run_static(frames[0], 0) if n_frames else None
+        P_next = static(0)
         for t in range(n_frames):
             P = P_next
             if before_frame is not None:
                 before_frame(t)
+            cur.wait_event(P.static_done)
             pending = self.roi_heads.launch_frame(P, self._mem)
             if t + 1 < n_frames:
-                P_next = eng.run_static(frames[t + 1], (t + 1) & 1)
+                P_next = static(t + 1)
             result, mem = self.roi_heads.finish_frame(pending, next_P=P_next)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            slot_free[t & 1] = ev
             self._mem = mem
             self.track_memory = mem
             results.append(result)
+        cur.wait_stream(side)
     return results
 
 

@@ -145,6 +145,13 @@ def test_small_tensor_kernels(dtype):
     refz = F.relu(F.group_norm(z, 32, gamma, beta, 1e-5))
     gotz = ops().groupnorm_relu_(nhwc(z, dtype), gamma.to(DEV), beta.to(DEV), 32, 1e-5, True)
     assert rel_err(nchw(gotz), refz) <= max(tol(dtype), 1e-4)
+    # register-resident kernel with a partial pixel loop (9x7 map), generic kernel (8 channels per group; 20x20 map)
+    for shape, groups in (((2, 64, 9, 7), 16), ((2, 64, 16, 16), 8), ((1, 32, 20, 20), 8)):
+        z = q(torch.randn(*shape, generator=g), dtype) * 1.5 - 0.3
+        gamma, beta = 0.5 + torch.rand(shape[1], generator=g), torch.randn(shape[1], generator=g)
+        refz = F.relu(F.group_norm(z, groups, gamma, beta, 1e-5))
+        gotz = ops().groupnorm_relu_(nhwc(z, dtype), gamma.to(DEV), beta.to(DEV), groups, 1e-5, True)
+        assert rel_err(nchw(gotz), refz) <= max(tol(dtype), 1e-4)
     img = torch.randn(3, 19, 23, generator=g)
     got_img = ops().image_to_nhwc(img.to(DEV), dtype)
     assert torch.equal(got_img.float().cpu()[0].permute(2, 0, 1), q(img, dtype))
