@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SMOT_ABI_VERSION 2
+#define SMOT_ABI_VERSION 3
 
 enum { SMOT_OK = 0, SMOT_ERR_INVALID = 1, SMOT_ERR_CUDA = 2, SMOT_ERR_UNSUPPORTED = 3 };
 enum { SMOT_F32 = 0, SMOT_F16 = 1 };
@@ -179,6 +179,28 @@ int smot_xcorr(const void* x, const void* k, void* out, int n, int channels, int
 int smot_emm_decode(const float* maps, int map_ld, int n, int O, int up, int T, const float* sr, const float* tboxes,
                     const float* hann, float pad, int use_centerness, double sigma, int img_w, int img_h, int amodal,
                     float* out_boxes, float* out_conf, int* out_valid, void* scratch, void* stream);
+
+/* ---- test-time frame preprocessing ---------------------------------
+ * Replaces, for one decoded RGB uint8 HWC frame, the reference's CPU chain demos/demo_inference.py:74-82 ->
+ * build_augmentation.py:52-66 (is_train=False): torchvision F.resize on a PIL image with the size from
+ * ImageResize.get_size (image_augmentation.py:21-50) -> ToTensor -> maskrcnn_benchmark Normalize(mean, std,
+ * to_bgr255).  Results are bit-identical to that chain (Pillow's 8-bit resampling is integer arithmetic).
+ *
+ * smot_resample_ksize / smot_resample_coeffs: HOST helpers restating Pillow libImaging/Resample.c
+ *   precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter over the whole axis: bounds[out][2] =
+ *   (first source index, tap count), kk[out][ksize] = 22-bit fixed-point weights.  The caller copies both to the
+ *   device once per (in_size, out_size).
+ * smot_resample_h_u8: horizontal pass, uint8 [H][W][3] (row pitch in bytes) -> uint8 [H][OW][3]; only needed when
+ *   OW != W (Pillow skips the pass otherwise).
+ * smot_resample_v_normalize: vertical pass (bounds == NULL: height unchanged, no pass) fused with ToTensor and
+ *   Normalize: uint8 [H][W][3] -> float32 [3][OH][W] = ((v/255)[*255 and BGR order if to_bgr255] - mean) / std,
+ *   every step one IEEE fp32 operation as in the torch chain.  mean3 / std3: HOST float[3], output-channel order. */
+int smot_resample_ksize(int in_size, int out_size);
+int smot_resample_coeffs(int in_size, int out_size, int* bounds, int* kk);
+int smot_resample_h_u8(const void* in, int in_pitch, int H, int W, const int* bounds, const int* kk, int ksize, int OW,
+                       void* out, int out_pitch, void* stream);
+int smot_resample_v_normalize(const void* in, int in_pitch, int H, int W, const int* bounds, const int* kk, int ksize,
+                              int OH, const float* mean3, const float* std3, int to_bgr255, float* out_chw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libsmot.so")
 F32, F16 = 0, 1
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
 MAX_LEVELS, MAX_ANCHORS = 5, 16
-ABI_VERSION = 2
+ABI_VERSION = 3
 CONV_WS_COUNTER_BYTES = 65536
 
 
@@ -40,8 +40,9 @@ _lib = None
 
 # kernels launched by one call of each entry point (memsets not counted); used for bench.py's gpu_launches
 KERNELS_PER_CALL = {"smot_conv2d": 1, "smot_image_to_nhwc": 1, "smot_maxpool2x2": 1, "smot_upsample_add": 1,
-                    "smot_subsample2": 1, "smot_groupnorm_relu": 1, "smot_roi_align": 1, "smot_rpn_select": 7,
-                    "smot_sort_nms": 3, "smot_box_decode": 1, "smot_track_combine": 1, "smot_xcorr": 1, "smot_emm_decode": 2}
+                    "smot_subsample2": 1, "smot_groupnorm_relu": 1, "smot_roi_align": 1, "smot_rpn_select": 6,
+                    "smot_sort_nms": 3, "smot_box_decode": 1, "smot_track_combine": 1, "smot_xcorr": 1, "smot_emm_decode": 2,
+                    "smot_resample_h_u8": 1, "smot_resample_v_normalize": 1}
 
 
 def _declare(lib):
@@ -63,6 +64,9 @@ def _declare(lib):
         "smot_track_combine": [vp, vp, i, vp, vp, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp],
         "smot_xcorr": [vp, vp, vp, i, i, i, i, i, vp],
         "smot_emm_decode": [vp, i, i, i, i, i, vp, vp, vp, f, i, d, i, i, i, vp, vp, vp, vp, vp],
+        "smot_resample_coeffs": [i, i, vp, vp],
+        "smot_resample_h_u8": [vp, i, i, i, vp, vp, i, i, vp, i, vp],
+        "smot_resample_v_normalize": [vp, i, i, i, vp, vp, i, i, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), i, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -72,6 +76,8 @@ def _declare(lib):
     lib.smot_rpn_select_workspace.restype = sz
     lib.smot_sort_nms_workspace.argtypes = [i]
     lib.smot_sort_nms_workspace.restype = sz
+    lib.smot_resample_ksize.argtypes = [i, i]
+    lib.smot_resample_ksize.restype = i
 
 
 def lib():

@@ -301,6 +301,7 @@ class Engine(object):
         self.conv_ws = ops.conv_workspace(self.device)
         self.conv_ws_track = ops.conv_workspace(self.device)
         self._side = None
+        self._pre = None
         self._track_plans = {}
         self._arenas = {}
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
@@ -582,6 +583,25 @@ class Engine(object):
             image = image[0]
         P = self.plan(image.shape[1], image.shape[2], slot)
         P.img_in.copy_(image, non_blocking=True)
+        with self.timed("static"):
+            P.run()
+        return P
+
+    def preprocessor(self):
+        if self._pre is None:
+            from .preprocess import FramePreprocessor
+            self._pre = FramePreprocessor(self.cfg, self.device)
+        return self._pre
+
+    def run_static_raw(self, frame, slot=0):
+        """frame: decoded RGB uint8 (H0, W0, 3) frame (host or device).  The reference's test transform (resize to
+        the cfg's test size, ToTensor, Normalize) runs on the device straight into the plan's input buffer, then the
+        frame-independent stage is enqueued as in run_static."""
+        pre = self.preprocessor()
+        oh, ow = pre.output_size(frame.shape[0], frame.shape[1])
+        P = self.plan(oh, ow, slot)
+        with self.timed("preprocess"):
+            pre.into(frame, P.img_in)
         with self.timed("static"):
             P.run()
         return P

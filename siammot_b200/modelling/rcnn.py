@@ -400,11 +400,20 @@ class SiamMOT(nn.Module):
         eng = self.engine()
         if hasattr(images, "tensors"):
             images = images.tensors
-        P = eng.run_static(images)
+        if _is_raw_frame(images):
+            # decoded RGB uint8 HWC frame: the test transform (demo_inference.py:74-82) runs on the device; boxes come
+            # back in resized-frame pixels exactly as if the caller had applied the transform (demo_inference.py:108)
+            P = eng.run_static_raw(images)
+        else:
+            P = eng.run_static(images)
         result, mem = self.roi_heads.run_frame(P, self._mem, given_detection)
         self._mem = mem
         self.track_memory = mem
         return [result]
+
+
+def _is_raw_frame(x):
+    return (isinstance(x, np.ndarray) and x.dtype == np.uint8) or (torch.is_tensor(x) and x.dtype == torch.uint8)
 
 
 def _forward_clip(self, frames, before_frame=None):
@@ -412,7 +421,8 @@ def _forward_clip(self, frames, before_frame=None):
     detections, double-buffered static plans) of frame t+1 runs on a side stream while the track stage of frame t
     runs on the current stream and the host resolves ids.  Results are identical to calling the model frame by
     frame; this is the throughput API (the reference has INFERENCE.CLIP_LEN but processes one frame per forward,
-    defaults.py:96, track_core.py:75).  frames: sequence / tensor of (3,H,W) frames.
+    defaults.py:96, track_core.py:75).  frames: sequence / tensor of normalised (3,H,W) frames or of decoded
+    uint8 (H,W,3) RGB frames (preprocessed on the device).
     before_frame(t): optional hook called right before frame t's tracker stage is enqueued."""
     if self.training:
         raise NotImplementedError("siammot_b200 is an inference engine: call .eval()")
@@ -430,7 +440,7 @@ def _forward_clip(self, frames, before_frame=None):
         with torch.cuda.stream(side):
             if slot_free[t & 1] is not None:
                 side.wait_event(slot_free[t & 1])
-            P = eng.run_static(frames[t], t & 1)
+            P = eng.run_static_raw(frames[t], t & 1) if _is_raw_frame(frames[t]) else eng.run_static(frames[t], t & 1)
             if P.static_done is None:
                 P.static_done = torch.cuda.Event()
             P.static_done.record(side)

@@ -33,3 +33,12 @@ def make_clip(n_frames, height, width, n_obj=6, seed=0):
             f[:, y0:y1, x0:x1] = 1.5 * math.copysign(1.0, float(tex[k, 0, 0, 0])) + 0.5 * patch
         frames.append(f)
     return torch.stack(frames)
+
+
+def make_clip_u8(n_frames, height, width, n_obj=6, seed=0, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """The same clip as decoded video: RGB uint8 (T, H, W, 3) frames whose ToTensor + Normalize(mean, std) image is
+    make_clip's frame up to 8-bit quantisation (input of the raw-frame path, siammot_b200/preprocess.py)."""
+    f = make_clip(n_frames, height, width, n_obj, seed)
+    m = torch.tensor(mean, dtype=torch.float32)[None, :, None, None]
+    s = torch.tensor(std, dtype=torch.float32)[None, :, None, None]
+    return ((f * s + m).clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
