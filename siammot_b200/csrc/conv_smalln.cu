@@ -163,6 +163,135 @@ __global__ void __launch_bounds__(128) conv_smalln_direct_kernel(const SmallNArg
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp16 storage: the same layers on the tensor cores (mma.sync.m16n8k16, fp32 accumulation), WITHOUT shared
+// memory or barriers.  A warp owns 16 output pixels x 8*NT output channels.  The MMA contraction index is
+// permuted so that every fragment register pair is part of ONE 16-byte global load: within a 32-channel chunk
+// thread (g, t) loads channels [8t, 8t+8) of pixel g (and g+8) and of weight row n = g (and g+8), and uses
+// halves {0,1 | 2,3} as the (k = 2t.. | k = 2t+8..) slots of a first k-step and halves {4,5 | 6,7} of a second:
+// A and B agree on the permutation, so the sum is unchanged.  Zero padding = predicated loads.
+// The 8 warps of a CTA are WM pixel groups x WK slices of the K loop (partial sums meet in shared memory), which
+// keeps >= ~1000 warps busy from the 56k-pixel RPN map down to the 30-row refinement FC.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sn_mma(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <typename TO, int NT>
+__global__ void __launch_bounds__(256) conv_smalln_mma_kernel(const SmallNArgs a, int WM, int WK) {
+  __shared__ float red[8][32][NT * 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = warp % WM, wk = warp / WM;
+  const int m0 = (blockIdx.x * WM + wm) * 16;
+  const __half* __restrict__ in = reinterpret_cast<const __half*>(a.in);
+  const __half* __restrict__ wt = reinterpret_cast<const __half*>(a.wt);
+  // the two pixel rows of this thread's A fragments
+  const __half* base[2];
+  int ih0[2], iw0[2];
+  bool ok[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int m = m0 + g + 8 * h;
+    ok[h] = m < a.M;
+    const int mm = ok[h] ? m : 0;
+    const int img = mm / (a.OH * a.OW), rem = mm - img * (a.OH * a.OW), oh = rem / a.OW;
+    ih0[h] = oh - a.pad, iw0[h] = rem - oh * a.OW - a.pad;
+    base[h] = in + (size_t)img * a.H * a.W * a.in_ld + t * 8;
+  }
+  const __half* wrow[NT];
+  bool wok[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    wok[nt] = nt * 8 + g < a.Cout;
+    wrow[nt] = wt + (size_t)(wok[nt] ? nt * 8 + g : 0) * a.K + t * 8;
+  }
+  float acc[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+  const int cpc = a.Cin >> 5, chunks = a.KH * a.KW * cpc;   // 32-channel chunks per tap / in total
+  const int per = (chunks + WK - 1) / WK;
+  const int q0 = wk * per, q1 = min(chunks, q0 + per);
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  constexpr int UN = 4;  // chunks whose loads are in flight together
+  for (int qb = q0; qb < q1; qb += UN) {
+    uint4 av[UN][2], bv[UN][NT];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int q = qb + u;
+      const bool live = q < q1;
+      const int tap = live ? q / cpc : 0, cc = live ? q - tap * cpc : 0;
+      const int r = tap / a.KW, sx = tap - r * a.KW;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ih = ih0[h] + r, iw = iw0[h] + sx;
+        const bool v = live && ok[h] && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
+        av[u][h] = v ? *reinterpret_cast<const uint4*>(base[h] + ((size_t)ih * a.W + iw) * a.in_ld + cc * 32) : zero;
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        bv[u][nt] = (live && wok[nt]) ? *reinterpret_cast<const uint4*>(wrow[nt] + (size_t)tap * a.Cin + cc * 32) : zero;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        sn_mma(acc[nt], av[u][0].x, av[u][1].x, av[u][0].y, av[u][1].y, bv[u][nt].x, bv[u][nt].y);
+        sn_mma(acc[nt], av[u][0].z, av[u][1].z, av[u][0].w, av[u][1].w, bv[u][nt].z, bv[u][nt].w);
+      }
+  }
+  if (WK > 1) {  // partial sums of the K slices meet in shared memory; slice 0 finishes the tile
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[warp][lane][nt * 4 + e] = acc[nt][e];
+    __syncthreads();
+    if (wk != 0) return;
+    for (int k = 1; k < WK; ++k)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] += red[k * WM + wm][lane][nt * 4 + e];
+  }
+  TO* __restrict__ out = reinterpret_cast<TO*>(a.out);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = nt * 8 + 2 * t + (e & 1), h = e >> 1;   // D fragment: rows g / g+8, columns 2t / 2t+1
+      if (ok[h] && n < a.Cout) {
+        float y = acc[nt][e];
+        if (a.scale) y = __fmul_rn(y, a.scale[n]);
+        if (a.bias) y = __fadd_rn(y, a.bias[n]);
+        if (a.relu) y = fmaxf(y, 0.f);
+        out[(size_t)(m0 + g + 8 * h) * a.out_ld + n] = from_f<TO>(y);
+      }
+    }
+}
+
+static bool smalln_mma_ok(const smot_conv_desc* d) {
+  return d->in_dtype == SMOT_F16 && d->Cin % 32 == 0 && d->in_ld % 8 == 0 && (((uintptr_t)d->in | (uintptr_t)d->weight) & 15) == 0 &&
+         ((size_t)d->KH * d->KW * d->Cin) % 8 == 0;
+}
+
+template <typename TO>
+static int launch_smalln_mma(const SmallNArgs& a, cudaStream_t st) {
+  const int mtiles = ceil_div(a.M, 16), chunks = a.KH * a.KW * (a.Cin / 32);
+  int WK = 1;
+  while (WK < 8 && (long long)mtiles * WK < 1184 && chunks / (WK * 2) >= 2) WK *= 2;   // ~8 warps per SM, >= 2 chunks per slice
+  const int WM = 8 / WK;
+  const unsigned grid = (unsigned)ceil_div(mtiles, WM);
+  if (a.Cout <= 8)
+    conv_smalln_mma_kernel<TO, 1><<<grid, 256, 0, st>>>(a, WM, WK);
+  else
+    conv_smalln_mma_kernel<TO, 2><<<grid, 256, 0, st>>>(a, WM, WK);
+  SMOT_CHECK_LAUNCH("smot_conv2d(smalln mma)");
+  return SMOT_OK;
+}
+
 bool conv2d_smalln_supported(const smot_conv_desc* d) {
   if (d->Cout > 16 || d->stride != 1 || d->residual) return false;
   if (d->Cin < 64 || d->Cin % 4 != 0 || d->in_ld % 4 != 0 || ((uintptr_t)d->in & 15)) return false;  // lanes split channels
@@ -220,6 +349,7 @@ int conv2d_smalln(const smot_conv_desc* d, cudaStream_t st) {
   a.M = d->batch * d->OH * d->OW;
   a.K = d->KH * d->KW * d->Cin;
   if (a.M == 0) return SMOT_OK;
+  if (smalln_mma_ok(d)) return d->out_dtype == SMOT_F16 ? launch_smalln_mma<__half>(a, st) : launch_smalln_mma<float>(a, st);
   if (d->in_dtype == SMOT_F32 && d->out_dtype == SMOT_F32) return launch_smalln<float, float>(a, st);
   if (d->in_dtype == SMOT_F16 && d->out_dtype == SMOT_F16) return launch_smalln<__half, __half>(a, st);
   if (d->in_dtype == SMOT_F16 && d->out_dtype == SMOT_F32) return launch_smalln<__half, float>(a, st);

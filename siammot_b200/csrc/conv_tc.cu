@@ -494,15 +494,24 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   dim3 grid((unsigned)tiles, (unsigned)(d->Cout / BN), (unsigned)a.splits);
   // many short tiles: 2-stage rings let 4 CTAs share an SM, so one CTA's prologue / epilogue overlaps the
   // main loops of the others (same bytes in flight per SM as 2 CTAs x 4 stages)
-  const char* force = getenv("SMOT_TC_STAGES");
-  const bool shallow = force ? atoi(force) == 2 : (tiles * (d->Cout / BN) >= 296 && a.taps * a.cin_chunks <= 36);
-  // at most one CTA per SM: nothing else hides the ~1 us TMA round trip, so run an 8-deep ring (192 KB)
-  const bool deep = force ? atoi(force) == 8 : ((long long)grid.x * grid.y * grid.z <= 148 && all_chunks >= 8);
+  const char* force = getenv("SMOT_TC_STAGES");  // developer override: ring depth
+  const int fs = force ? atoi(force) : 0;
+  const int my_chunks = a.chunks_per_split;
+  const bool shallow = fs ? fs == 2 : (tiles * (d->Cout / BN) >= 296 && all_chunks <= 36);
+  // at most one CTA per SM: nothing else hides the ~1 us TMA round trip (the loop then advances `ring depth` chunks
+  // per round trip), so use the whole shared memory for the ring: 8 x 24 KB, 6 x 32 KB, 4 x 48 KB
+  const bool solo = (long long)grid.x * grid.y * grid.z <= 148;
+  const bool deep = fs ? fs >= 6 : (solo && my_chunks >= 6);
   int rc;
-  if (BN == 256) rc = launch_tc<256, 3>(tmA, tmB, a, grid, st);  // 48 KB stages, 1 CTA / SM
-  else if (BN == 128) rc = shallow ? launch_tc<128, 2>(tmA, tmB, a, grid, st) : launch_tc<128, 3>(tmA, tmB, a, grid, st);
-  else if (deep) rc = launch_tc<64, 8>(tmA, tmB, a, grid, st);
-  else rc = shallow ? launch_tc<64, 2>(tmA, tmB, a, grid, st) : launch_tc<64, 4>(tmA, tmB, a, grid, st);
+  if (BN == 256)
+    rc = (fs ? fs >= 4 : (solo && my_chunks >= 4)) ? launch_tc<256, 4>(tmA, tmB, a, grid, st) : launch_tc<256, 3>(tmA, tmB, a, grid, st);
+  else if (BN == 128)
+    rc = shallow ? launch_tc<128, 2>(tmA, tmB, a, grid, st)
+                 : (deep ? launch_tc<128, 6>(tmA, tmB, a, grid, st) : launch_tc<128, 3>(tmA, tmB, a, grid, st));
+  else if (deep)
+    rc = launch_tc<64, 8>(tmA, tmB, a, grid, st);
+  else
+    rc = shallow ? launch_tc<64, 2>(tmA, tmB, a, grid, st) : launch_tc<64, 4>(tmA, tmB, a, grid, st);
   if (rc != SMOT_OK || a.splits == 1) return rc;
   const size_t total_out = (size_t)a.num_tiles * TC_BM * (d->Cout / 4);
   splitk_reduce_kernel<<<(unsigned)((total_out + 255) / 256), 256, 0, st>>>(a);

@@ -24,7 +24,7 @@ namespace smot {
 
 constexpr int SN_THREADS = 1024;
 constexpr int SN_MAX = 4096;
-constexpr int SN_CACHE_BYTES = 192 * 1024;  // largest bitmask nms_reduce_kernel stages in shared memory
+constexpr int SN_CACHE_BYTES = 176 * 1024;  // largest bitmask nms_reduce_kernel stages in shared memory
 constexpr float BBOX_XFORM_CLIP = 4.135166556742356f;  // log(1000/16)
 
 struct SortNmsArgs {
@@ -48,6 +48,7 @@ struct SortNmsArgs {
   int* s_index;                // [P][n_max]
   int* s_m;                    // [P]
   unsigned long long* mask;    // [P][n_max][words_max], words_max = ceil(n_max / 64)
+  unsigned long long* diag_t;  // [P][n_max] transposed diagonal blocks: bit b of row i <=> row 64*(i/64)+b < i suppresses i
   int words_max;
   // batching (blockIdx = problem): element offsets added per problem
   int in_step, out_step;
@@ -142,6 +143,8 @@ __global__ void __launch_bounds__(SN_THREADS) nms_sort_kernel(SortNmsArgs a) {
 // ---- K2: suppression bitmask, mask[i][w] bit b set <=> j = 64w+b > i and IoU(i,j) > thresh -------
 //      grid (column block w, row block, problem), upper triangle only; thread = row i of the tile, the 64
 //      column boxes are broadcast from shared memory.  Words left of the diagonal are never written or read.
+//      Diagonal tiles also emit the transposed word diag_t[i] (bit b <=> row 64*(i/64)+b < i suppresses i; the
+//      IoU test is symmetric bit for bit), which lets nms_reduce_kernel resolve a 64-row block in parallel.
 __global__ void __launch_bounds__(64) nms_mask_kernel(SortNmsArgs a) {
   __shared__ float4 cbox[64];
   const int cb = blockIdx.x, rb = blockIdx.y, prob = blockIdx.z;
@@ -155,26 +158,32 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(SortNmsArgs a) {
   if (i >= m) return;
   const float4 bi = sb[i];
   const int jn = min(64, m - j0);
-  const int jb = cb == rb ? (int)threadIdx.x + 1 : 0;  // j > i
-  unsigned long long word = 0ull;
-  for (int b = jb; b < jn; ++b) {
+  const bool diag = cb == rb;
+  unsigned long long word = 0ull, tword = 0ull;
+  for (int b = 0; b < jn; ++b) {
+    if (diag && b == (int)threadIdx.x) continue;
     const float4 bj = cbox[b];
     // disjoint boxes have IoU 0: skip the division (same result, most pairs are disjoint)
     if (fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x) + 1.f > 0.f && fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y) + 1.f > 0.f)
-      if (iou_plus1(bi, bj) > a.thresh) word |= 1ull << b;
+      if (iou_plus1(bi, bj) > a.thresh) {
+        if (!diag || b > (int)threadIdx.x) word |= 1ull << b; else tword |= 1ull << b;
+      }
   }
   a.mask[((size_t)prob * a.n_max + i) * a.words_max + cb] = word;
+  if (diag) a.diag_t[(size_t)prob * a.n_max + i] = tword;
 }
 
 // ---- K3: greedy reduction + outputs ------------------------------------------------------------
 __global__ void __launch_bounds__(SN_THREADS) nms_reduce_kernel(SortNmsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int* kept_all = reinterpret_cast<int*>(smem_raw);  // sorted row of the k-th survivor, [np]
-  unsigned long long* cache = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)a.np * 4);
+  int* kept_all = reinterpret_cast<int*>(smem_raw);                                        // sorted row of the k-th survivor, [np]
+  unsigned long long* dT = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)a.np * 4);  // transposed diagonal words, [np]
+  unsigned long long* cache = dT + a.np;                                                   // staged bitmask (cache_pitch > 0)
   __shared__ unsigned long long removed[SN_MAX / 64];
   __shared__ unsigned long long s_km;
   __shared__ int s_kept, s_base, s_done;
   const int prob = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* scores = a.scores + (size_t)prob * a.in_step * a.score_stride;
   const float4* __restrict__ sb = a.s_boxes + (size_t)prob * a.n_max;
   const int* __restrict__ si = a.s_index + (size_t)prob * a.n_max;
@@ -190,57 +199,64 @@ __global__ void __launch_bounds__(SN_THREADS) nms_reduce_kernel(SortNmsArgs a) {
     kept_total = max(min(m, a.max_keep), 0);
     for (int i = threadIdx.x; i < kept_total; i += blockDim.x) kept_all[i] = i;
   } else {
-    // the upper triangle of the bitmask goes to shared memory once (when it fits): the rounds below are a
+    // everything the rounds below touch goes to shared memory first (the bitmask when it fits): the rounds are a
     // dependent chain and must not wait for global loads
+    for (int i = threadIdx.x; i < m; i += blockDim.x) dT[i] = a.diag_t[(size_t)prob * a.n_max + i];
     const unsigned long long* M = gmask;
     int pitch = a.words_max;
     if (a.cache_pitch > 0) {
       for (int idx = threadIdx.x; idx < m * words; idx += blockDim.x) {
         const int row = idx / words, w = idx - row * words;
-        if (w >= (row >> 6)) cache[row * a.cache_pitch + w] = gmask[(size_t)row * a.words_max + w];
+        if (w > (row >> 6)) cache[row * a.cache_pitch + w] = gmask[(size_t)row * a.words_max + w];
       }
       M = cache;
       pitch = a.cache_pitch;
     }
     __syncthreads();
-    // 64 sorted rows per round: (A) one thread resolves the round serially from the diagonal words (branch-free:
-    // the 64 loads do not depend on the chain), (B) the whole CTA ORs the survivors' rows into `removed`
+    // 64 sorted rows per round.  (A) warp 0 resolves the block by fixed-point iteration: a row whose in-block
+    // suppressors are all removed is kept, a row with a kept suppressor is removed; the lowest undecided row always
+    // decides, so this is the greedy result, in (dependency depth) steps instead of 64.  (B) warp w ORs the
+    // survivors' rows of bitmask word c+1+w into `removed` (no atomics: one warp per word).
     for (int c = 0; c < words; ++c) {
-      if (threadIdx.x == 0) {
-        const unsigned long long* d = M + (size_t)(c << 6) * pitch + c;
+      if (warp == 0) {
         const int rows_here = min(64, m - (c << 6));
-        unsigned long long cur = removed[c], km = 0ull;
-#pragma unroll 16
-        for (int b = 0; b < 64; ++b) {
-          const unsigned long long dv = b < rows_here ? d[(size_t)b * pitch] : 0ull;
-          const unsigned long long bit = 1ull << b;
-          const bool keep = (cur & bit) == 0ull;
-          cur |= keep ? dv : 0ull;
-          km |= keep ? bit : 0ull;
+        const unsigned long long vm = rows_here == 64 ? ~0ull : ((1ull << rows_here) - 1ull);
+        unsigned long long rem = removed[c] & vm, kept = 0ull, und = vm & ~rem;
+        const unsigned long long sup0 = lane < rows_here ? dT[(c << 6) + lane] : 0ull;
+        const unsigned long long sup1 = lane + 32 < rows_here ? dT[(c << 6) + 32 + lane] : 0ull;
+        while (und) {
+          const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
+          const bool r0 = u0 && (sup0 & kept), r1 = u1 && (sup1 & kept);
+          const bool k0 = u0 && !r0 && (sup0 & ~rem) == 0ull, k1 = u1 && !r1 && (sup1 & ~rem) == 0ull;
+          const unsigned long long nk = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
+          const unsigned long long nr = (unsigned long long)__ballot_sync(0xffffffffu, r0) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, r1) << 32);
+          kept |= nk, rem |= nr, und &= ~(nk | nr);
         }
-        if (rows_here < 64) km &= (1ull << rows_here) - 1ull;
-        const int kept = s_kept, room = a.max_keep - kept;
-        int nk = __popcll(km);
-        if (nk >= room) {
-          for (; nk > room; --nk) km &= ~(1ull << (63 - __clzll((long long)km)));
-          s_done = 1;
+        if (lane == 0) {
+          const int base = s_kept, room = a.max_keep - base;
+          int nk = __popcll(kept);
+          if (nk >= room) {
+            for (; nk > room; --nk) kept &= ~(1ull << (63 - __clzll((long long)kept)));
+            s_done = 1;
+          }
+          s_km = kept;
+          s_base = base;
+          s_kept = base + nk;
         }
-        s_km = km;
-        s_base = kept;
-        s_kept = kept + nk;
       }
       __syncthreads();
       const unsigned long long km = s_km;
       if (threadIdx.x < 64 && ((km >> threadIdx.x) & 1ull))
         kept_all[s_base + __popcll(km & ((1ull << threadIdx.x) - 1ull))] = (c << 6) + threadIdx.x;
       if (s_done) break;
-      const int nw = words - c - 1;
-      for (int item = threadIdx.x; item < 64 * nw; item += blockDim.x) {
-        const int b = item & 63, w = c + 1 + (item >> 6);
-        if ((km >> b) & 1ull) {
-          const unsigned long long v = M[(size_t)((c << 6) + b) * pitch + w];
-          if (v) atomicOr(&removed[w], v);
-        }
+      for (int w = c + 1 + warp; w < words; w += SN_THREADS / 32) {
+        unsigned long long v = 0ull;
+        if ((km >> lane) & 1ull) v = M[(size_t)((c << 6) + lane) * pitch + w];
+        if ((km >> (lane + 32)) & 1ull) v |= M[(size_t)((c << 6) + 32 + lane) * pitch + w];
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v), hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+        if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
       }
       __syncthreads();
     }
@@ -275,7 +291,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static size_t sort_nms_ws_bytes(int problems, int n_max) {
   const size_t P = (size_t)problems, n = (size_t)n_max, words = (n + 63) / 64;
-  return align256(P * n * 16) + align256(P * n * 4) + align256(P * 4) + align256(P * n * words * 8);
+  return align256(P * n * 16) + align256(P * n * 4) + align256(P * 4) + align256(P * n * 8) + align256(P * n * words * 8);
 }
 
 static void carve_sort_nms_ws(SortNmsArgs& a, void* ws, int problems) {
@@ -284,6 +300,7 @@ static void carve_sort_nms_ws(SortNmsArgs& a, void* ws, int problems) {
   a.s_boxes = (float4*)w;            w += align256(P * n * 16);
   a.s_index = (int*)w;               w += align256(P * n * 4);
   a.s_m = (int*)w;                   w += align256(P * 4);
+  a.diag_t = (unsigned long long*)w; w += align256(P * n * 8);
   a.mask = (unsigned long long*)w;
   a.words_max = (a.n_max + 63) / 64;
 }
@@ -294,7 +311,7 @@ static int launch_sort_nms(SortNmsArgs& a, int problems, cudaStream_t st) {
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_MAX * 8);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_MAX * 4 + SN_CACHE_BYTES);
+      e = cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_MAX * 12 + SN_CACHE_BYTES);
     if (e != cudaSuccess) {
       set_error("sort_nms: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return SMOT_ERR_CUDA;
@@ -313,7 +330,7 @@ static int launch_sort_nms(SortNmsArgs& a, int problems, cudaStream_t st) {
     const int pitch = a.words_max | 1;  // odd pitch: a column of 64-bit words spreads over all banks
     if ((size_t)a.n_max * pitch * 8 <= (size_t)SN_CACHE_BYTES) a.cache_pitch = pitch, cache_bytes = (size_t)a.n_max * pitch * 8;
   }
-  nms_reduce_kernel<<<problems, SN_THREADS, (size_t)a.np * 4 + cache_bytes, st>>>(a);
+  nms_reduce_kernel<<<problems, SN_THREADS, (size_t)a.np * 12 + cache_bytes, st>>>(a);
   SMOT_CHECK_LAUNCH("sort_nms(reduce)");
   return SMOT_OK;
 }

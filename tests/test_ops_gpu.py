@@ -450,6 +450,22 @@ def test_conv2d_small_cout_kernel(dtype):
                      out=out[..., :10])
         assert rel_err(out[0, 0, :, :10].cpu(), F.linear(x, w, b)) <= tol(dtype)
         assert float(out[..., 10:].abs().max()) == 0.0
+    # RPN predictor: 1x1, 128 -> 15 (objectness + deltas), fp32 head with pitch 16; ragged pixel counts, batch 2
+    for (B, H, W) in ((1, 22, 40), (1, 11, 20), (2, 5, 7), (1, 44, 80)):
+        x = q(torch.randn(B, 128, H, W, generator=g), dtype)
+        w = q(torch.randn(15, 128, 1, 1, generator=g) / 11.0, dtype)
+        b = torch.randn(15, generator=g)
+        head = torch.zeros(B, H, W, 16, dtype=torch.float32, device=DEV)
+        ops().conv2d(nhwc(x, dtype), ohwi(w, dtype), None, b.to(DEV), out=head[..., :15])
+        assert rel_err(nchw(head[..., :15]), F.conv2d(x, w, b)) <= tol(dtype)
+        assert float(head[..., 15].abs().max()) == 0.0
+    # fp16 output with scale + bias + ReLU (the generic epilogue)
+    x = q(torch.randn(2, 64, 9, 13, generator=g), dtype)
+    w = q(torch.randn(8, 64, 3, 3, generator=g) / 24.0, dtype)
+    sc, b = torch.rand(8, generator=g) + 0.5, torch.randn(8, generator=g)
+    ref = F.relu(F.conv2d(x, w, None, 1, 1) * sc[None, :, None, None] + b[None, :, None, None])
+    got = ops().conv2d(nhwc(x, dtype), ohwi(w, dtype), sc.to(DEV), b.to(DEV), pad=1, relu=True)
+    assert rel_err(nchw(got), ref) <= tol(dtype)
 
 
 HIRES_CASES = [
