@@ -57,7 +57,7 @@ def test_model_accepts_raw_frames():
     cfg.DTYPE = "float32"
     cfg.INPUT.MIN_SIZE_TEST, cfg.INPUT.MAX_SIZE_TEST = 192, 320   # 200x334 frames -> 192x320 network input
     sd = make_state_dict(cfg, 1)
-    frames = make_clip_u8(3, 200, 334, 4, 5, cfg.INPUT.PIXEL_MEAN, cfg.INPUT.PIXEL_STD)
+    frames = make_clip_u8(3, 200, 334, 4, 7, cfg.INPUT.PIXEL_MEAN, cfg.INPUT.PIXEL_STD)   # seed 7: tracks start in frame 0
     assert opp.preprocess(frames[0].numpy(), cfg).shape == (3, 192, 320)
 
     def run(kind):
