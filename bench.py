@@ -158,7 +158,7 @@ def kernels_per_frame(h):
     from siammot_b200 import _lib
     P = h.eng.plan(H_NET, W_NET)
     n = 0
-    for fn, args, tag in P.steps:
+    for fn, args, tag, _branch in P.steps:
         name = getattr(fn, "__name__", None)
         n += _lib.KERNELS_PER_CALL.get(name, 0) if name else 0
     # dynamic: sr roi_align, xcorr, towers conv, groupnorm, 2 head convs, decode(2), refine(roi_align, 3 conv, decode),

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace smot {
@@ -26,6 +28,16 @@ bool conv2d_smalln_supported(const smot_conv_desc* d);
 }  // namespace smot
 
 using namespace smot;
+
+namespace smot {
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SMOT_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+}  // namespace smot
 
 extern "C" int smot_abi_version(void) { return SMOT_ABI_VERSION; }
 extern "C" const char* smot_last_error(void) { return g_err; }

@@ -30,6 +30,29 @@ void set_error(const char* fmt, ...);
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------
+// The detection stage is ~110 short kernels in one CUDA graph; at 5-15 us each, the drain -> launch -> prologue
+// gap between consecutive kernels is a large share of the frame.  Kernels launched through launch_pdl() may begin
+// while their predecessor in the stream is still running: they do everything that does not touch the predecessor's
+// data first (barrier init, TMEM allocation, staging constant weights), then pdl_wait() blocks until the predecessor
+// has completed and its writes are visible.  pdl_launch_dependents() at the top lets the NEXT kernel start the same
+// way once every CTA of this grid is running.  Both are no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // capi.cu: on unless SMOT_PDL=0
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- storage-type <-> float -------------------------------------------------------------
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }

@@ -72,11 +72,13 @@ __global__ void __launch_bounds__(256) conv3x3_hires_kernel(const HiresArgs a) {
   const __half* in = a.in + (size_t)img * a.H * a.W * a.in_ld;
   const int ix0 = ox0 * STRIDE - 1, iy0 = oy0 * STRIDE - 1;
   // ---- stage weights [COUT][K] -> [COUT][KP] and the input halo (zero-filled outside the image)
+  pdl_launch_dependents();
   constexpr int WCH = C::K / 8;  // 16-byte chunks per weight row
   for (int i = tid; i < COUT * WCH; i += 256) {
     const int n = i / WCH, q = i - n * WCH;
     cp_async16(wsm + n * C::KP + q * 8, a.wt + (size_t)n * C::K + q * 8, true);
   }
+  pdl_wait();  // the weights are constants; the input belongs to the previous kernel
   constexpr int PCH = CIN / 8;  // 16-byte chunks per pixel
   for (int i = tid; i < C::IH * C::IW * PCH; i += 256) {
     const int p = i / PCH, q = i - p * PCH;
@@ -175,11 +177,13 @@ __global__ void __launch_bounds__(256) stem7x7_hires_kernel(const HiresArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ox0 = blockIdx.x * ST_TW, oy0 = blockIdx.y * ST_TH;
   const __half* in = a.in + (size_t)blockIdx.z * a.H * a.W * a.in_ld;
+  pdl_launch_dependents();
   for (int i = tid; i < ST_COUT * 7 * 32; i += 256) {
     const int n = i / 224, rem = i - n * 224, r = rem / 32, k = rem - r * 32;
     const int s = k >> 2, c = k & 3;
     wsm[i] = (s < 7 && c < 3) ? a.wt[((size_t)n * 49 + r * 7 + s) * 3 + c] : __float2half(0.f);
   }
+  pdl_wait();
   for (int p = tid; p < ST_IH * ST_IW; p += 256) {
     const int py = p / ST_IW, px = p - py * ST_IW;
     const int gy = oy0 - 3 + py, gx = ox0 - 3 + px;
@@ -280,7 +284,7 @@ static int launch3(const HiresArgs& a, int batch, cudaStream_t st) {
     attr = true;
   }
   dim3 grid(ceil_div(a.OW, C::TW), ceil_div(a.OH, C::TH), batch);
-  conv3x3_hires_kernel<CIN, COUT, STRIDE><<<grid, 256, C::SMEM, st>>>(a);
+  launch_pdl(conv3x3_hires_kernel<CIN, COUT, STRIDE>, grid, dim3(256), C::SMEM, st, a);
   SMOT_CHECK_LAUNCH("smot_conv2d(hires)");
   return SMOT_OK;
 }
@@ -292,7 +296,7 @@ int conv2d_hires(const smot_conv_desc* d, cudaStream_t st) {
   if (d->batch == 0) return SMOT_OK;
   if (d->KH == 7) {
     dim3 grid(ceil_div(a.OW, ST_TW), ceil_div(a.OH, ST_TH), d->batch);
-    stem7x7_hires_kernel<<<grid, 256, 0, st>>>(a);
+    launch_pdl(stem7x7_hires_kernel, grid, dim3(256), 0, st, a);
     SMOT_CHECK_LAUNCH("smot_conv2d(stem)");
     return SMOT_OK;
   }

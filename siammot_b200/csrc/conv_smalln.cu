@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(256) conv_smalln_mma_kernel(const SmallNArgs a
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int wm = warp % WM, wk = warp / WM;
   const int m0 = (blockIdx.x * WM + wm) * 16;
+  pdl_launch_dependents();
+  pdl_wait();
   const __half* __restrict__ in = reinterpret_cast<const __half*>(a.in);
   const __half* __restrict__ wt = reinterpret_cast<const __half*>(a.wt);
   // the two pixel rows of this thread's A fragments
@@ -285,9 +287,9 @@ static int launch_smalln_mma(const SmallNArgs& a, cudaStream_t st) {
   const int WM = 8 / WK;
   const unsigned grid = (unsigned)ceil_div(mtiles, WM);
   if (a.Cout <= 8)
-    conv_smalln_mma_kernel<TO, 1><<<grid, 256, 0, st>>>(a, WM, WK);
+    launch_pdl(conv_smalln_mma_kernel<TO, 1>, dim3(grid), dim3(256), 0, st, a, WM, WK);
   else
-    conv_smalln_mma_kernel<TO, 2><<<grid, 256, 0, st>>>(a, WM, WK);
+    launch_pdl(conv_smalln_mma_kernel<TO, 2>, dim3(grid), dim3(256), 0, st, a, WM, WK);
   SMOT_CHECK_LAUNCH("smot_conv2d(smalln mma)");
   return SMOT_OK;
 }

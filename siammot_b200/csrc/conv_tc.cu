@@ -146,98 +146,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int BN, int STAGES>
-struct TcSmem {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
-  static constexpr int B_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 8 /*scale, bias*/;
-};
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                             const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-  using S = TcSmem<BN, STAGES>;
-  extern __shared__ uint8_t tc_smem_raw[];
-  // 128B-swizzled tiles need 1024B-aligned bases
-  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * S::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
-  uint32_t* tmem_slot_aux = tmem_slot + 1;
-  float* s_scale = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);  // [BN] scale, then [BN] bias
-  float* s_bias = s_scale + BN;
-
+// ---- epilogue warps 2..5: TMEM -> scale / bias (+residual) (+ReLU) -> fp16 NHWC, or the raw fp32 partial tile when K is split
+template <int BN>
+__device__ __forceinline__ void tc_epilogue(const TcArgs& a, uint32_t tmem_base, float* s_scale, float* s_bias, uint64_t* tmem_full,
+                                            int img, int h0, int w0, int n0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) TC_STAMP(0);
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tw = t % a.tiles_w;
-  t /= a.tiles_w;
-  const int th = t % a.tiles_h;
-  const int img = t / a.tiles_h;
-  const int w0 = tw * a.tile_w, h0 = th * a.tile_h;
-  const int n0 = blockIdx.y * BN;
-  const int all_chunks = a.taps * a.cin_chunks;
-  const int it0 = (int)blockIdx.z * a.chunks_per_split;                 // this CTA's K range [it0, it0 + total)
-  const int total = min(a.chunks_per_split, all_chunks - it0);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    mbar_init(tmem_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {  // TMEM allocation (whole warp), BN fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) TC_STAMP(1);
-
-  if (warp == 0) {
-    if (lane == 0) {  // ===== TMA producer =====
-      for (int it = 0; it < total; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        mbar_expect_tx(&full[s], (uint32_t)S::STAGE_BYTES);
-        const int tap = (it0 + it) / a.cin_chunks, cc = (it0 + it) - tap * a.cin_chunks;
-        const int r = tap / a.KW, sx = tap - r * a.KW;
-        tma_load_4d(sA + s * S::A_BYTES, &tmA, &full[s], cc * TC_BK, w0 * a.stride + sx - a.pad, h0 * a.stride + r - a.pad, img);
-        tma_load_2d(sB + s * S::B_BYTES, &tmB, &full[s], tap * a.Cin + cc * TC_BK, n0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_f16(TC_BM, BN);
-      for (int it = 0; it < total; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&full[s], ph);
-        if (it == 0) TC_STAMP(2);
-        tc_fence_after();
-        const uint64_t ad = umma_desc_sw128(sA + s * S::A_BYTES);
-        const uint64_t bd = umma_desc_sw128(sB + s * S::B_BYTES);
-#pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)  // +32 bytes (2 x 16B units) per K=16 step inside the swizzle atom
-          umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)((it | k) != 0));
-        umma_commit(&empty[s]);  // slot reusable once these MMAs have read it
-      }
-      umma_commit(tmem_full);    // accumulator complete
-    }
-  } else {  // ===== epilogue warps 2..5 =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int oh = h0 + row / a.tile_w, ow = w0 + row % a.tile_w;
@@ -318,6 +231,103 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       }
     }
   }
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 8 /*scale, bias*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  using S = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t tc_smem_raw[];
+  // 128B-swizzled tiles need 1024B-aligned bases
+  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * S::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint32_t* tmem_slot_aux = tmem_slot + 1;
+  float* s_scale = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);  // [BN] scale, then [BN] bias
+  float* s_bias = s_scale + BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) TC_STAMP(0);
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw = t % a.tiles_w;
+  t /= a.tiles_w;
+  const int th = t % a.tiles_h;
+  const int img = t / a.tiles_h;
+  const int w0 = tw * a.tile_w, h0 = th * a.tile_h;
+  const int n0 = blockIdx.y * BN;
+  const int all_chunks = a.taps * a.cin_chunks;
+  const int it0 = (int)blockIdx.z * a.chunks_per_split;                 // this CTA's K range [it0, it0 + total)
+  const int total = min(a.chunks_per_split, all_chunks - it0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation (whole warp), BN fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel; its outputs are read (and buffers rewritten) from here on
+  if (threadIdx.x == 0) TC_STAMP(1);
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int it = 0; it < total; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], (uint32_t)S::STAGE_BYTES);
+        const int tap = (it0 + it) / a.cin_chunks, cc = (it0 + it) - tap * a.cin_chunks;
+        const int r = tap / a.KW, sx = tap - r * a.KW;
+        tma_load_4d(sA + s * S::A_BYTES, &tmA, &full[s], cc * TC_BK, w0 * a.stride + sx - a.pad, h0 * a.stride + r - a.pad, img);
+        tma_load_2d(sB + s * S::B_BYTES, &tmB, &full[s], tap * a.Cin + cc * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_f16(TC_BM, BN);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        if (it == 0) TC_STAMP(2);
+        tc_fence_after();
+        const uint64_t ad = umma_desc_sw128(sA + s * S::A_BYTES);
+        const uint64_t bd = umma_desc_sw128(sB + s * S::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)  // +32 bytes (2 x 16B units) per K=16 step inside the swizzle atom
+          umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)((it | k) != 0));
+        umma_commit(&empty[s]);  // slot reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+  } else {  // ===== epilogue warps 2..5 =====
+    tc_epilogue<BN>(a, tmem_base, s_scale, s_bias, tmem_full, img, h0, w0, n0);
+  }
   if (warp == 2 && lane == 0) TC_STAMP(4);
   tc_fence_before();
   __syncthreads();
@@ -328,9 +338,150 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3x3 / stride 1 with a shared-memory resident input halo.
+// conv_tc_kernel re-reads the A operand once per filter tap: 9 x 16 KB per 64-channel chunk and CTA.  Measured,
+// those layers sit at the L2 -> SM throughput cap (~11.5 TB/s over all SMs, profiles/conv_layers_r01_*.txt), not at
+// the tensor pipe.  Here the (8+2) x (16+2) pixel halo of an 8 x 16 output tile is loaded ONCE per channel chunk
+// (one 4-D TMA box, PW pixels per patch row, 128B-swizzled, zero fill = conv padding) and the nine taps are nine
+// shifted views of it: row m = y*8 + x of tap (r, s) is patch pixel (y + r, x + s), i.e. the UMMA descriptor starts
+// (r*PW + s) * 128 B into the patch and steps PW * 128 B between its 8-row groups.  Only the weights still stream per
+// tap (their own ring).  K order: channel chunk outermost, taps inside.
+// ---------------------------------------------------------------------------------------------
+constexpr int HALO_TW = 8, HALO_TH = 16, HALO_SA = 2;
+
+template <int BN, int PW, int SB>
+struct HaloSmem {
+  static constexpr int A_BOX_BYTES = (HALO_TH + 2) * PW * TC_BK * 2;              // bytes one TMA patch delivers
+  static constexpr int A_BYTES = ((A_BOX_BYTES + 1023) / 1024) * 1024;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int RING = HALO_SA * A_BYTES + SB * B_BYTES;
+  static constexpr int TOTAL = RING + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 8 /*scale, bias*/;
+  static_assert((2 * HALO_SA + 2 * SB + 2) * 8 <= 256, "barrier block");
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_rows(const void* smem, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN, int PW, int SB>
+__global__ void __launch_bounds__(TC_THREADS) conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB, const TcArgs a,
+                                                                  const int bo_mode) {
+  using S = HaloSmem<BN, PW, SB>;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + HALO_SA * S::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::RING);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + HALO_SA;
+  uint64_t* fullB = emptyA + HALO_SA;
+  uint64_t* emptyB = fullB + SB;
+  uint64_t* tmem_full = emptyB + SB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_scale = reinterpret_cast<float*>(smem + S::RING + 256);
+  float* s_bias = s_scale + BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  int t = blockIdx.x;
+  const int tw = t % a.tiles_w;
+  t /= a.tiles_w;
+  const int th = t % a.tiles_h;
+  const int img = t / a.tiles_h;
+  const int w0 = tw * HALO_TW, h0 = th * HALO_TH;
+  const int n0 = blockIdx.y * BN;
+  const int cc0 = (int)blockIdx.z * a.chunks_per_split;                  // this CTA's channel chunks [cc0, cc0 + ncc)
+  const int ncc = min(a.chunks_per_split, a.cin_chunks - cc0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < HALO_SA; ++i) mbar_init(&fullA[i], 1), mbar_init(&emptyA[i], 1);
+    for (int i = 0; i < SB; ++i) mbar_init(&fullB[i], 1), mbar_init(&emptyB[i], 1);
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  // developer probes (timing only, results are garbage): 256 = no MMAs, 512 = no weight loads, 1024 = no patch loads
+  const bool no_mma = bo_mode & 256, no_b = bo_mode & 512, no_a = bo_mode & 1024;
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer: one halo patch per channel chunk, one weight tile per tap =====
+      int ib = 0;
+      for (int ic = 0; ic < ncc; ++ic) {
+        const int sa = ic % HALO_SA;
+        if (!no_a) {
+          mbar_wait(&emptyA[sa], ((uint32_t)(ic / HALO_SA) & 1u) ^ 1u);
+          mbar_expect_tx(&fullA[sa], (uint32_t)S::A_BOX_BYTES);
+          tma_load_4d(sA + sa * S::A_BYTES, &tmA, &fullA[sa], (cc0 + ic) * TC_BK, w0 - 1, h0 - 1, img);
+        }
+        for (int tap = 0; tap < 9 && !no_b; ++tap, ++ib) {
+          const int sb = ib % SB;
+          mbar_wait(&emptyB[sb], ((uint32_t)(ib / SB) & 1u) ^ 1u);
+          mbar_expect_tx(&fullB[sb], (uint32_t)S::B_BYTES);
+          tma_load_2d(sB + sb * S::B_BYTES, &tmB, &fullB[sb], tap * a.Cin + (cc0 + ic) * TC_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_f16(TC_BM, BN);
+      int ib = 0;
+      for (int ic = 0; ic < ncc; ++ic) {
+        const int sa = ic % HALO_SA;
+        if (!no_a) mbar_wait(&fullA[sa], (uint32_t)(ic / HALO_SA) & 1u);
+        const uint8_t* patch = sA + sa * S::A_BYTES;
+        for (int tap = 0; tap < 9; ++tap, ++ib) {
+          const int sb = ib % SB;
+          if (!no_b) mbar_wait(&fullB[sb], (uint32_t)(ib / SB) & 1u);
+          tc_fence_after();
+          const int r = tap / 3, sx = tap - 3 * r;
+          const uint32_t first_row = (uint32_t)(r * PW + sx);   // patch pixel of output row 0 for this tap
+          const uint64_t ad = umma_desc_sw128_rows(patch + first_row * 128u, (uint32_t)PW * 128u, (bo_mode & 1) ? first_row : 0u);
+          const uint64_t bd = umma_desc_sw128(sB + sb * S::B_BYTES);
+          if (!no_mma) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+              umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)((ic | tap | k) != 0));
+          }
+          if (!no_b) umma_commit(&emptyB[sb]);
+        }
+        if (!no_a) umma_commit(&emptyA[sa]);   // all nine taps of this patch have been read
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    tc_epilogue<BN>(a, tmem_base, s_scale, s_bias, tmem_full, img, h0, w0, n0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
 // Deterministic split-K finish: out[pixel][n] = act((sum_z partial[z]) * scale + bias + residual), summed in split order.
 // One thread per 4 output channels of one pixel; tiles map back to pixels exactly as in conv_tc_kernel.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c4 = a.Cout / 4;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)a.num_tiles * TC_BM * c4;
@@ -426,12 +577,97 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
     }
     attr = true;
   }
-  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(tmA, tmB, a);
+  launch_pdl(conv_tc_kernel<BN, STAGES>, grid, dim3(TC_THREADS), S::TOTAL, st, tmA, tmB, a);
   SMOT_CHECK_LAUNCH("smot_conv2d(tcgen05)");
   return SMOT_OK;
 }
 
+template <int BN, int PW, int SB>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, dim3 grid, int bo_mode, cudaStream_t st) {
+  using S = HaloSmem<BN, PW, SB>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<BN, PW, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("smot_conv2d(tcgen05 halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return SMOT_ERR_CUDA;
+    }
+    attr = true;
+  }
+  launch_pdl(conv3x3_halo_kernel<BN, PW, SB>, grid, dim3(TC_THREADS), S::TOTAL, st, tmA, tmB, a, bo_mode);
+  SMOT_CHECK_LAUNCH("smot_conv2d(tcgen05 halo)");
+  return SMOT_OK;
+}
+
+static int halo_mode() {  // developer switch SMOT_TC_HALO: 0 = off, 16 / 10 = patch width, +100 = descriptor base offset mode
+  const char* e = getenv("SMOT_TC_HALO");
+  return e ? atoi(e) : 0;
+}
+
+static int conv2d_tc_halo(const smot_conv_desc* d, int mode, cudaStream_t st) {
+  TcArgs a;
+  a.scale = d->scale, a.bias = d->bias, a.res = (const __half*)d->residual, a.out = (__half*)d->out;
+  a.H = d->OH, a.W = d->OW, a.stride = 1, a.Cin = d->Cin, a.Cout = d->Cout, a.out_ld = d->out_ld, a.res_ld = d->res_ld, a.relu = d->relu;
+  a.taps = 9, a.KW = 3, a.pad = 1, a.cin_chunks = d->Cin / TC_BK;
+  a.tile_w = HALO_TW, a.tile_h = HALO_TH;
+  a.tiles_w = ceil_div(d->OW, HALO_TW), a.tiles_h = ceil_div(d->OH, HALO_TH);
+  const long long tiles = (long long)a.tiles_w * a.tiles_h * d->batch;
+  const int pw = mode % 100;
+  int bo_mode = (mode / 100) & 1;
+  if (const char* e = getenv("SMOT_TC_PROBE")) bo_mode |= atoi(e);
+  int BN = 64;
+  if (d->Cout % 256 == 0 && tiles * (d->Cout / 256) >= 96) BN = 256;
+  else if (d->Cout % 128 == 0 && tiles * (d->Cout / 128) >= 96) BN = 128;
+  int splits = 1;
+  {
+    const int bw = d->Cout % 256 == 0 ? 256 : (d->Cout % 128 == 0 ? 128 : 64);
+    const long long cw = tiles * (d->Cout / bw);
+    if (d->workspace && cw <= 40 && a.cin_chunks >= 2 && !getenv("SMOT_TC_NOSPLIT")) {
+      int sp = (int)(148 / cw);
+      if (sp > 8) sp = 8;
+      if (sp > a.cin_chunks) sp = a.cin_chunks;
+      const size_t need = (size_t)SMOT_CONV_WS_COUNTER_BYTES + (size_t)sp * tiles * TC_BM * d->Cout * sizeof(float);
+      if (sp >= 2 && need <= d->workspace_bytes) splits = sp, BN = bw;
+    }
+  }
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
+    uint64_t str[3] = {(uint64_t)d->in_ld * 2, (uint64_t)d->W * d->in_ld * 2, (uint64_t)d->H * d->W * d->in_ld * 2};
+    uint32_t box[4] = {(uint32_t)TC_BK, (uint32_t)pw, (uint32_t)(HALO_TH + 2), 1u};
+    if (!encode_map(&tmA, d->in, 4, dims, str, box)) return SMOT_ERR_CUDA;
+  }
+  {
+    const uint64_t K = (uint64_t)9 * d->Cin;
+    uint64_t dims[2] = {K, (uint64_t)d->Cout};
+    uint64_t str[1] = {K * 2};
+    uint32_t box[2] = {(uint32_t)TC_BK, (uint32_t)BN};
+    if (!encode_map(&tmB, d->weight, 2, dims, str, box)) return SMOT_ERR_CUDA;
+  }
+  a.chunks_per_split = (a.cin_chunks + splits - 1) / splits;
+  a.splits = (a.cin_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
+  a.num_tiles = (int)tiles;
+  a.dbg = nullptr;
+  a.counters = (unsigned*)d->workspace;
+  a.partial = d->workspace ? (float*)((char*)d->workspace + SMOT_CONV_WS_COUNTER_BYTES) : nullptr;
+  dim3 grid((unsigned)tiles, (unsigned)(d->Cout / BN), (unsigned)a.splits);
+  const bool crowded = (long long)grid.x * grid.y * grid.z > 148;   // several CTAs per SM: shallow weight ring, 2 CTAs / SM
+  int rc;
+#define SMOT_HALO(BN_, SB_) (pw == 10 ? launch_halo<BN_, 10, SB_>(tmA, tmB, a, grid, bo_mode, st) : launch_halo<BN_, 16, SB_>(tmA, tmB, a, grid, bo_mode, st))
+  if (BN == 256) rc = SMOT_HALO(256, 4);
+  else if (BN == 128) rc = crowded ? SMOT_HALO(128, 2) : SMOT_HALO(128, 6);
+  else rc = crowded ? SMOT_HALO(64, 4) : SMOT_HALO(64, 8);
+#undef SMOT_HALO
+  if (rc != SMOT_OK || a.splits == 1) return rc;
+  const size_t total_out = (size_t)a.num_tiles * TC_BM * (d->Cout / 4);
+  launch_pdl(splitk_reduce_kernel, dim3((unsigned)((total_out + 255) / 256)), dim3(256), 0, st, a);
+  SMOT_CHECK_LAUNCH("smot_conv2d(split-K reduce)");
+  return SMOT_OK;
+}
+
 int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
+  if (d->KH == 3 && d->stride == 1 && d->H > 1 && (halo_mode() % 100 == 16 || halo_mode() % 100 == 10))
+    return conv2d_tc_halo(d, halo_mode(), st);
   TcArgs a;
   a.scale = d->scale, a.bias = d->bias, a.res = (const __half*)d->residual, a.out = (__half*)d->out;
   a.H = d->OH, a.W = d->OW, a.stride = d->stride, a.Cin = d->Cin, a.Cout = d->Cout, a.out_ld = d->out_ld, a.res_ld = d->res_ld, a.relu = d->relu;
@@ -514,7 +750,7 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
     rc = shallow ? launch_tc<64, 2>(tmA, tmB, a, grid, st) : launch_tc<64, 4>(tmA, tmB, a, grid, st);
   if (rc != SMOT_OK || a.splits == 1) return rc;
   const size_t total_out = (size_t)a.num_tiles * TC_BM * (d->Cout / 4);
-  splitk_reduce_kernel<<<(unsigned)((total_out + 255) / 256), 256, 0, st>>>(a);
+  launch_pdl(splitk_reduce_kernel, dim3((unsigned)((total_out + 255) / 256)), dim3(256), 0, st, a);
   SMOT_CHECK_LAUNCH("smot_conv2d(split-K reduce)");
   return SMOT_OK;
 }

@@ -7,6 +7,8 @@ namespace smot {
 // ---- CHW fp32 image -> NHWC ---------------------------------------------------------------
 template <typename T>
 __global__ void image_to_nhwc_kernel(const float* __restrict__ chw, T* __restrict__ out, int C, int HW, int ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   for (int c = 0; c < C; ++c) out[(size_t)p * ld + c] = from_f<T>(chw[(size_t)c * HW + p]);
@@ -17,6 +19,8 @@ __global__ void image_to_nhwc_kernel(const float* __restrict__ chw, T* __restric
 template <typename T>
 __global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out, int batch, int H, int W, int C,
                                   int in_ld, int out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int OH = H / 2, OW = W / 2, C4 = C / 4;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)batch * OH * OW * C4;
@@ -37,6 +41,8 @@ __global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out,
 template <typename T>
 __global__ void upsample_add_kernel(const T* __restrict__ top, int Ht, int Wt, int top_ld, T* __restrict__ lat, int H,
                                     int W, int lat_ld, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C4 = C / 4;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)H * W * C4) return;
@@ -66,6 +72,8 @@ __global__ void upsample_add_kernel(const T* __restrict__ top, int Ht, int Wt, i
 template <typename T>
 __global__ void subsample2_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C, int in_ld,
                                   int out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1, C4 = C / 4;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)OH * OW * C4) return;
@@ -195,9 +203,9 @@ extern "C" int smot_image_to_nhwc(const float* chw, void* out, int C, int H, int
   cudaStream_t st = (cudaStream_t)stream;
   int HW = H * W;
   if (dtype == SMOT_F32)
-    image_to_nhwc_kernel<float><<<blocks_for(HW, 256), 256, 0, st>>>(chw, (float*)out, C, HW, out_ld);
+    launch_pdl(image_to_nhwc_kernel<float>, dim3(blocks_for(HW, 256)), dim3(256), 0, st, chw, (float*)out, C, HW, out_ld);
   else if (dtype == SMOT_F16)
-    image_to_nhwc_kernel<__half><<<blocks_for(HW, 256), 256, 0, st>>>(chw, (__half*)out, C, HW, out_ld);
+    launch_pdl(image_to_nhwc_kernel<__half>, dim3(blocks_for(HW, 256)), dim3(256), 0, st, chw, (__half*)out, C, HW, out_ld);
   else
     SMOT_CHECK_ARG(false, "smot_image_to_nhwc: bad dtype %d", dtype);
   SMOT_CHECK_LAUNCH("smot_image_to_nhwc");
@@ -211,9 +219,9 @@ extern "C" int smot_maxpool2x2(const void* in, void* out, int batch, int H, int 
   cudaStream_t st = (cudaStream_t)stream;
   size_t total = (size_t)batch * (H / 2) * (W / 2) * (C / 4);
   if (dtype == SMOT_F32)
-    maxpool2x2_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float*)in, (float*)out, batch, H, W, C, in_ld, out_ld);
+    launch_pdl(maxpool2x2_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const float*)in, (float*)out, batch, H, W, C, in_ld, out_ld);
   else if (dtype == SMOT_F16)
-    maxpool2x2_kernel<__half><<<blocks_for(total, 256), 256, 0, st>>>((const __half*)in, (__half*)out, batch, H, W, C, in_ld, out_ld);
+    launch_pdl(maxpool2x2_kernel<__half>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const __half*)in, (__half*)out, batch, H, W, C, in_ld, out_ld);
   else
     SMOT_CHECK_ARG(false, "smot_maxpool2x2: bad dtype %d", dtype);
   SMOT_CHECK_LAUNCH("smot_maxpool2x2");
@@ -227,9 +235,9 @@ extern "C" int smot_upsample_add(const void* top, int Ht, int Wt, int top_ld, vo
   cudaStream_t st = (cudaStream_t)stream;
   size_t total = (size_t)H * W * (C / 4);
   if (dtype == SMOT_F32)
-    upsample_add_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float*)top, Ht, Wt, top_ld, (float*)lateral, H, W, lat_ld, C);
+    launch_pdl(upsample_add_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const float*)top, Ht, Wt, top_ld, (float*)lateral, H, W, lat_ld, C);
   else if (dtype == SMOT_F16)
-    upsample_add_kernel<__half><<<blocks_for(total, 256), 256, 0, st>>>((const __half*)top, Ht, Wt, top_ld, (__half*)lateral, H, W, lat_ld, C);
+    launch_pdl(upsample_add_kernel<__half>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const __half*)top, Ht, Wt, top_ld, (__half*)lateral, H, W, lat_ld, C);
   else
     SMOT_CHECK_ARG(false, "smot_upsample_add: bad dtype %d", dtype);
   SMOT_CHECK_LAUNCH("smot_upsample_add");
@@ -242,9 +250,9 @@ extern "C" int smot_subsample2(const void* in, void* out, int H, int W, int C, i
   cudaStream_t st = (cudaStream_t)stream;
   size_t total = (size_t)((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / 4);
   if (dtype == SMOT_F32)
-    subsample2_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float*)in, (float*)out, H, W, C, in_ld, out_ld);
+    launch_pdl(subsample2_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const float*)in, (float*)out, H, W, C, in_ld, out_ld);
   else if (dtype == SMOT_F16)
-    subsample2_kernel<__half><<<blocks_for(total, 256), 256, 0, st>>>((const __half*)in, (__half*)out, H, W, C, in_ld, out_ld);
+    launch_pdl(subsample2_kernel<__half>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const __half*)in, (__half*)out, H, W, C, in_ld, out_ld);
   else
     SMOT_CHECK_ARG(false, "smot_subsample2: bad dtype %d", dtype);
   SMOT_CHECK_LAUNCH("smot_subsample2");

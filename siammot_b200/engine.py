@@ -73,6 +73,7 @@ class _Plan(object):
         self.dtype = engine.dtype
         self.ws = engine.conv_ws      # split-K scratch of the stream this plan runs on
         self.static_done = None       # event recorded after the plan when it runs on the side stream (forward_clip)
+        self.branch = None            # while building: steps appended go to this parallel branch (None = main line)
 
     def new(self, H, W, Cc, dtype=None, B=1):
         t = torch.zeros((B, H, W, Cc), dtype=dtype or self.dtype, device=self.dev)
@@ -81,18 +82,42 @@ class _Plan(object):
 
     def conv(self, x, name, out, residual=None, stride=1, pad=0, relu=False):
         w, scale, bias = self.e.weights[name]
-        d = ops.conv_desc(x, w, out, scale, bias, residual, stride, pad, relu, workspace=self.ws)
+        ws = self.ws if self.branch is None else self.e.branch_ws(self.branch)
+        d = ops.conv_desc(x, w, out, scale, bias, residual, stride, pad, relu, workspace=ws)
         self.keep.append(d)
-        self.steps.append((lib().smot_conv2d, (C.byref(d),), "conv:" + name))
+        self.steps.append((lib().smot_conv2d, (C.byref(d),), "conv:" + name, self.branch))
         return out
 
     def call(self, fn, args, tag):
-        self.steps.append((fn, args, tag))
+        self.steps.append((fn, args, tag, self.branch))
+
+    # Independent layers (the FPN laterals, the per-level FPN-output -> RPN chains) are enqueued on parallel branches:
+    # fork(n) .. join() become parallel paths of the CUDA graph (streams in eager mode), so the small-level kernels
+    # (<= 30 CTAs, mostly fixed launch / prologue / epilogue cost) run under the big P2 ones instead of after them.
+    def fork(self, n):
+        self.steps.append(("fork", n, None, None))
+
+    def join(self):
+        self.branch = None
+        self.steps.append(("join", None, None, None))
 
     def run_eager(self):
-        st = _lib.stream_ptr()
-        for fn, args, tag in self.steps:
-            check(fn(*args, st), tag)
+        main = torch.cuda.current_stream(self.dev)
+        st = C.c_void_p(main.cuda_stream)
+        active = []
+        for fn, args, tag, branch in self.steps:
+            if fn == "fork":
+                active = self.e.branch_streams(args)
+                for b in active:
+                    b.wait_stream(main)
+            elif fn == "join":
+                for b in active:
+                    main.wait_stream(b)
+                active = []
+            elif branch is None:
+                check(fn(*args, st), tag)
+            else:
+                check(fn(*args, C.c_void_p(active[branch].cuda_stream)), tag)
 
     def run(self):
         if self.e.use_graph:
@@ -302,6 +327,8 @@ class Engine(object):
         self.conv_ws_track = ops.conv_workspace(self.device)
         self._side = None
         self._pre = None
+        self._branch_ws = []
+        self._branch_streams = []
         self._track_plans = {}
         self._arenas = {}
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
@@ -472,30 +499,40 @@ class Engine(object):
         body = [x2, x3, x4, x5]
         # ---- FPN (fpn_patch.py:29-61)
         Cc = self.C
-        feats = [None] * 5
-        last = None
-        for i in range(4, 0, -1):
-            f = body[i - 1]
-            inner = P.conv(f, "fpn.fpn_inner%d" % i, P.new(f.shape[1], f.shape[2], Cc))
-            if last is not None:
-                P.call(L.smot_upsample_add, (ops._ptr(last), last.shape[1], last.shape[2], Cc, ops._ptr(inner),
-                                             inner.shape[1], inner.shape[2], Cc, Cc, dc), "upsample_add%d" % i)
-            feats[i - 1] = P.conv(inner, "fpn.fpn_layer%d" % i, P.new(f.shape[1], f.shape[2], Cc), pad=1)
-            last = inner
-        p5 = feats[3]
-        feats[4] = P.new((p5.shape[1] - 1) // 2 + 1, (p5.shape[2] - 1) // 2 + 1, Cc)
-        P.call(L.smot_subsample2, (ops._ptr(p5), ops._ptr(feats[4]), p5.shape[1], p5.shape[2], Cc, Cc, Cc, dc), "p6")
-        P.feats = feats
-        # ---- RPN head + selection
         R = cfg.MODEL.RPN
         A = self.n_anchor
         hld = ((5 * A + 3) // 4) * 4
-        heads = []
-        for l, f in enumerate(feats):
+        feats, heads, inner = [None] * 5, [None] * 5, [None] * 4
+        P.fork(4)                                   # the four lateral 1x1 convs are independent
+        for i in range(4, 0, -1):
+            f = body[i - 1]
+            P.branch = 4 - i
+            inner[i - 1] = P.conv(f, "fpn.fpn_inner%d" % i, P.new(f.shape[1], f.shape[2], Cc))
+        P.join()
+        for i in range(3, 0, -1):                   # top-down pathway: sequential
+            last, cur = inner[i], inner[i - 1]
+            P.call(L.smot_upsample_add, (ops._ptr(last), last.shape[1], last.shape[2], Cc, ops._ptr(cur),
+                                         cur.shape[1], cur.shape[2], Cc, Cc, dc), "upsample_add%d" % (i + 1))
+
+        def rpn_head(l):
+            f = feats[l]
             t = P.conv(f, "rpn.conv", P.new(f.shape[1], f.shape[2], Cc), pad=1, relu=True)
-            hbuf = P.new(f.shape[1], f.shape[2], hld, dtype=torch.float32)
-            P.conv(t, "rpn.pred", hbuf[..., :5 * A])
-            heads.append(hbuf)
+            heads[l] = P.new(f.shape[1], f.shape[2], hld, dtype=torch.float32)
+            P.conv(t, "rpn.pred", heads[l][..., :5 * A])
+
+        P.fork(4)                                   # per level: FPN output conv -> RPN conv -> RPN predictor
+        for l in range(4):
+            P.branch = l
+            feats[l] = P.conv(inner[l], "fpn.fpn_layer%d" % (l + 1), P.new(inner[l].shape[1], inner[l].shape[2], Cc), pad=1)
+            rpn_head(l)
+            if l == 3:                              # P6 = stride-2 subsample of P5 (fpn_patch.py:57-59), same branch
+                p5 = feats[3]
+                feats[4] = P.new((p5.shape[1] - 1) // 2 + 1, (p5.shape[2] - 1) // 2 + 1, Cc)
+                P.call(L.smot_subsample2, (ops._ptr(p5), ops._ptr(feats[4]), p5.shape[1], p5.shape[2], Cc, Cc, Cc, dc), "p6")
+                rpn_head(4)
+        P.join()
+        P.feats = feats
+        # ---- RPN selection
         P.rpn_levels = ops.rpn_levels(heads, R.ANCHOR_STRIDE, self.cells)
         P.keep.append(P.rpn_levels)
         nprop = R.FPN_POST_NMS_TOP_N_TEST
@@ -569,6 +606,17 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     # per-frame entry points
     # ------------------------------------------------------------------------------------------
+    def branch_ws(self, b):
+        """Split-K scratch of parallel branch b (concurrent convolutions must not share one)."""
+        while len(self._branch_ws) <= b:
+            self._branch_ws.append(ops.conv_workspace(self.device))
+        return self._branch_ws[b]
+
+    def branch_streams(self, n):
+        while len(self._branch_streams) < n:
+            self._branch_streams.append(torch.cuda.Stream(device=self.device))
+        return self._branch_streams[:n]
+
     def side_stream(self):
         """The stream forward_clip runs the frame-independent stage on (created on first use)."""
         if self._side is None:

@@ -503,6 +503,27 @@ def test_conv2d_hires_kernels(case):
     assert rel_err(nchw(got), nchw(got_simt)) <= 1e-3
 
 
+@pytest.mark.parametrize("mode", ["16", "10"])
+def test_conv2d_tcgen05_halo_variant(mode, monkeypatch):
+    """Developer variant of the 3x3 tcgen05 kernel (SMOT_TC_HALO): the input halo of an 8x16 tile stays in shared
+    memory and the nine taps are shifted UMMA descriptors over it (patch rows of 16 or 10 pixels).  Same results."""
+    from siammot_b200 import _lib
+    monkeypatch.setenv("SMOT_TC_HALO", mode)
+    g = torch.Generator().manual_seed(int(mode))
+    dt = torch.float16
+    ws = ops().conv_workspace(DEV)
+    for (B, Cin, H, W, Cout, use_ws) in ((1, 128, 88, 160, 128, False), (1, 64, 37, 53, 64, False), (3, 128, 16, 16, 256, False),
+                                         (1, 512, 22, 40, 512, True)):
+        x = q(torch.randn(B, Cin, H, W, generator=g), dt)
+        w = q(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9), dt)
+        res = q(torch.randn(B, Cout, H, W, generator=g), dt)
+        scale, bias = 0.5 + torch.rand(Cout, generator=g), torch.randn(Cout, generator=g)
+        ref = F.relu(F.conv2d(x, w, None, 1, 1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1) + res)
+        got = ops().conv2d(nhwc(x, dt), ohwi(w, dt), scale.to(DEV), bias.to(DEV), nhwc(res, dt), 1, 1, True,
+                           algo=_lib.CONV_TCGEN05, workspace=ws if use_ws else None)
+        assert rel_err(nchw(got), ref) <= 2e-3
+
+
 def test_conv2d_tcgen05_split_k():
     """Few-tile / long-K layers (level5 convs, fc6) with the split-K workspace: fp32 partial tiles are reduced in
     split order by the last CTA of each output tile; counters must be left zero (call twice, then inspect)."""

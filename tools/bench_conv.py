@@ -21,6 +21,8 @@ LAYERS = [  # name, B, Cin, H, W, Cout, k, stride
     ("towers 30", 30, 128, 16, 16, 256, 3, 1),
 ]
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+if os.environ.get("SMOT_LAYERS"):   # comma-separated substrings of layer names
+    LAYERS = [l for l in LAYERS if any(k in l[0] for k in os.environ["SMOT_LAYERS"].split(","))]
 for name, B, Cin, H, W, Cout, k, s in LAYERS:
     x = torch.randn(B, H, W, Cin, device=dev).to(dt)
     w = (torch.randn(Cout, k, k, Cin, device=dev) / math.sqrt(Cin * k * k)).to(dt)
