@@ -232,10 +232,11 @@ class _TrackPlan(object):
             self.box = {k: (v[:n] if k in ("pooled", "dec_boxes", "dec_scores") else (v[:, :, :n] if torch.is_tensor(v) else v))
                         for k, v in A.box.items()}
             Q = _Plan(eng, P.H, P.W)
+            Q.ws = eng.conv_ws_track   # this stage may run while the other stream executes the next frame's static stage
             Q.feats = P.feats
             eng._box_steps(Q, self.box, self.tb, None, n, self.labels)
             self.keep.append(Q)
-            self.steps += Q.steps
+            self.steps += [st[:3] for st in Q.steps]
             dec_b, dec_s = self.box["dec_boxes"], self.box["dec_scores"]
         else:
             dec_b = dec_s = None
