@@ -148,6 +148,7 @@ class _TrackArena(object):
         self.cat_boxes = torch.zeros((tmax, 4), dtype=f32, device=dev)
         self.host = torch.zeros((1 + 7 * tmax + 1 + ncap,), dtype=f32).pin_memory()
         self.srf = torch.zeros((cap * S * S * Cc,), dtype=dt, device=dev)
+        self.tmpl = torch.zeros((cap * eng.t_res * eng.t_res * Cc,), dtype=dt, device=dev)   # the frame's templates (fixed address)
         self.resp = torch.zeros((cap * O * O * Cc,), dtype=dt, device=dev)
         self.tower = torch.zeros((cap * O * O * 2 * Cc,), dtype=dt, device=dev)
         self.maps = torch.zeros((cap * O * O * 8,), dtype=f32, device=dev)
@@ -180,6 +181,8 @@ class _TrackPlan(object):
         total = ncap + n
         self.ncap, self.total = ncap, total
         self.keep, self.steps = [], []
+        self.graph, self.warm = None, False
+        self.det_is_static = det is None   # one-off plans over external detections are not worth capturing
         f32 = torch.float32
         # ---- inputs block: sr (4n) | boxes (4n) | labels (n, int32 bits) | active (n)
         self.inputs = A.inputs[:max(10 * n, 1)]
@@ -207,6 +210,7 @@ class _TrackPlan(object):
         self.xcorr_slot = None
         if n:
             self.srf = A.srf[:n * S * S * Cc].view(n, S, S, Cc)
+            self.tmpl = A.tmpl[:n * Tr * Tr * Cc].view(n, Tr, Tr, Cc)
             self.resp = A.resp[:n * O * O * Cc].view(n, O, O, Cc)
             self.tower = A.tower[:n * O * O * 2 * Cc].view(n, O, O, 2 * Cc)
             self.maps = A.maps[:n * O * O * 8].view(n, O, O, 8)
@@ -216,7 +220,7 @@ class _TrackPlan(object):
             self.steps.append((L.smot_roi_align, (C.byref(pyr_pad), ops._ptr(self.sr), ops._ptr(self.boxes), None, n, Cc, S,
                                                   T.POOLER_SAMPLING_RATIO, ops._ptr(self.srf), dc), "sr_roi_align"))
             self.xcorr_slot = len(self.steps)
-            self.steps.append((L.smot_xcorr, None, "xcorr"))  # args rebuilt per frame (template pointer)
+            self.steps.append((L.smot_xcorr, (ops._ptr(self.srf), ops._ptr(self.tmpl), ops._ptr(self.resp), n, Cc, S, Tr, dc), "xcorr"))
             self._conv(self.resp, "emm.towers", self.tower, pad=1)
             self.steps.append((L.smot_groupnorm_relu, (ops._ptr(self.tower), ops._ptr(eng.gn_gamma), ops._ptr(eng.gn_beta), n,
                                                        O * O, 2 * Cc, 2 * Cc, 2 * cfg.MODEL.GROUP_NORM.NUM_GROUPS,
@@ -267,23 +271,41 @@ class _TrackPlan(object):
         self.keep.append(d)
         self.steps.append((lib().smot_conv2d, (C.byref(d),), "conv:" + name))
 
-    def run(self, feat, upload=True, wait=True):
-        """Launch the stage and (wait=True) block on its result block: the frame's only device->host sync."""
+    def _enqueue(self):
+        """The whole stage on the current stream: inputs H2D, kernels, result block D2H (all addresses fixed)."""
         eng = self.e
         st = _lib.stream_ptr()
         if self.n:
-            if upload:
-                self.inputs.copy_(self.inputs_host, non_blocking=True)
-            xargs = (ops._ptr(self.srf), ops._ptr(feat), ops._ptr(self.resp), self.n, eng.C, eng.s_res, eng.t_res,
-                     _lib.dtype_code(eng.dtype))
+            self.inputs.copy_(self.inputs_host, non_blocking=True)
         for i, (fn, args, tag) in enumerate(self.steps):
-            if i == self.xcorr_slot:
+            if i == self.xcorr_slot and eng.time_kernels:
                 with eng.timed("xcorr"):
-                    check(fn(*xargs, st), tag)
+                    check(fn(*args, st), tag)
             else:
                 check(fn(*args, st), tag)
         self.host_res.copy_(self.res, non_blocking=True)
         self.host_det.copy_(self.det_block, non_blocking=True)
+
+    def run(self, feat, upload=True, wait=True):
+        """Launch the stage and (wait=True) block on its result block: the frame's only device->host sync.
+        The launch list is replayed as a CUDA graph from its second use on (the first use runs it eagerly, which also
+        sets kernel attributes); the template features are copied to the plan's fixed buffer first."""
+        eng = self.e
+        if self.n and feat.data_ptr() != self.tmpl.data_ptr():
+            self.tmpl.copy_(feat.view(self.tmpl.shape), non_blocking=True)
+        if eng.use_graph and not (eng.timers is not None and eng.time_kernels) and self.det_is_static:
+            if self.graph is None and self.warm:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue()
+                self.graph = g
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._enqueue()
+                self.warm = True
+        else:
+            self._enqueue()
         self.done.record()
         if wait:
             self.done.synchronize()
@@ -333,6 +355,7 @@ class Engine(object):
         self._track_plans = {}
         self._arenas = {}
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
+        self.time_kernels = False  # also bracket single kernels of the track stage (forces its eager path)
 
     def timed(self, name):
         """Context manager: when self.timers is a dict, brackets the enclosed launches with CUDA events on
