@@ -686,9 +686,10 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   // not TMA.  Hence: (a) the widest N that still leaves ~100 CTAs; (b) layers with only a handful of output tiles
   // (levels 4-5, FC layers) take the widest BN AND split K over up to 8 CTAs, finished by splitk_reduce_kernel.
   const int all_chunks = a.taps * a.cin_chunks;
+  static const int min_ctas = getenv("SMOT_TC_MINCTAS") ? atoi(getenv("SMOT_TC_MINCTAS")) : 96;   // developer override
   int BN = 64;
-  if (d->Cout % 256 == 0 && tiles * (d->Cout / 256) >= 96) BN = 256;
-  else if (d->Cout % 128 == 0 && tiles * (d->Cout / 128) >= 96) BN = 128;
+  if (d->Cout % 256 == 0 && tiles * (d->Cout / 256) >= min_ctas) BN = 256;
+  else if (d->Cout % 128 == 0 && tiles * (d->Cout / 128) >= min_ctas) BN = 128;
   int splits = 1;
   {
     const int bw = d->Cout % 256 == 0 ? 256 : (d->Cout % 128 == 0 ? 128 : 64);

@@ -10,8 +10,8 @@ import torch
 import bench
 
 h = bench.Harness("float16", torch.device("cuda", 0))
-frames = bench.make_frames(bench.N_FRAMES).to("cuda")
-h.prime(frames[0])
+frames = bench.make_frames_u8(bench.N_FRAMES, h.cfg).pin_memory()   # decoded uint8 frames: the e2e arm's input
+h.prime(h.eng.preprocessor()(frames[0]))
 for i in range(40):
     h.step(frames[i % 32])
 torch.cuda.synchronize()
