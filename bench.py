@@ -178,6 +178,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     h = Harness(args.dtype, device)
+    h.model.results_on_host = True   # results are consumed on the host (as demo / inferencer do): CPU BoxLists straight from the solver
     frames_u8 = make_frames_u8(N_FRAMES, h.cfg).pin_memory()                   # host, pinned: the e2e arm's input
     pre = h.eng.preprocessor()
     frames_dev = torch.stack([pre(frames_u8[i]) for i in range(N_FRAMES)])    # normalised 3x704x1280, resident in HBM
@@ -219,7 +220,7 @@ def run_ours(args):
         nbytes = 0
         for i in range(args.steps):
             h.restore()
-            out = h.model(src[(args.warmup + i) % N_FRAMES])[0].to("cpu")   # H2D inside forward, D2H of the result
+            out = h.model(src[(args.warmup + i) % N_FRAMES])[0].to("cpu")   # H2D inside forward; results arrive on the host
             nbytes += out.bbox.numel() * 4 + sum(out.get_field(f).numel() * out.get_field(f).element_size() for f in out.fields())
         torch.cuda.synchronize()
         return time.perf_counter() - t0, nbytes
@@ -289,10 +290,13 @@ def run_ours(args):
                    "parallelism": "1 stream per GPU x %d" % world, "cuda_graph": True,
                    "api": "value: model.forward_clip on normalised frames resident in HBM (frame t+1's detection stage runs on a "
                           "side stream under frame t's track stage and host solver); e2e: model(frame) per decoded RGB uint8 "
-                          "720p frame in pinned host memory, test transform (resize 720->704, ToTensor, Normalize) on the device",
+                          "720p frame in pinned host memory, test transform (resize 720->704, ToTensor, Normalize) on the device; "
+                          "model.results_on_host = True (CPU BoxLists from the packed result block the engine copies D2H)",
                    "baseline_note": "17 FPS = README.md:22 'a single modern GPU', unnamed hardware"},
         "e2e": {"value": round(world * args.steps / (e2e_ms * 1e-3), 2), "unit": "frames/s",
-                "h2d_bytes_per_step": 3 * H_SRC * W_SRC, "d2h_bytes_per_step": int(d2h / args.steps),
+                "h2d_bytes_per_step": 3 * H_SRC * W_SRC + tp.inputs.numel() * 4,
+                "d2h_bytes_per_step": (tp.host_res.numel() + tp.host_det.numel()) * 4,
+                "result_bytes_per_step": int(d2h / args.steps),
                 "float32_chw_host_input": {"value": round(world * args.steps / (e2e_float_ms * 1e-3), 2), "unit": "frames/s",
                                            "h2d_bytes_per_step": 3 * H_NET * W_NET * 4,
                                            "note": "same loop with the reference's calling convention (frame already resized + "

@@ -170,6 +170,7 @@ class CombinedROIHeads(nn.ModuleDict):
         self.cfg = cfg
         self.engine = None
         self._out_host = None
+        self.results_on_host = False   # True: forward returns CPU BoxLists (what demo / inferencer convert to anyway)
 
     def reset_roi_status(self):
         if self.cfg.MODEL.TRACK_ON:
@@ -258,9 +259,18 @@ class CombinedROIHeads(nn.ModuleDict):
         return self._to_boxlist(boxes, scores, ids, labels, (P.W, P.H)), new_mem
 
     def _to_boxlist(self, boxes, scores, ids, labels, size):
-        """One packed pinned buffer -> one H2D copy; the BoxList fields are views of the device copy."""
+        """One packed pinned buffer -> one H2D copy; the BoxList fields are views of the device copy.
+        With ``results_on_host`` (result egress) the BoxList is built from the host arrays the solver
+        just produced -- no H2D here and no D2H + sync in the caller's ``.to('cpu')`` (inferencer.py:65-67)."""
         dev = self.engine.device
         k = boxes.shape[0]
+        if self.results_on_host:
+            # copies: the inputs may be views of the pinned result block, which the next frame overwrites
+            out = BoxList(torch.from_numpy(np.array(boxes, dtype=np.float32, copy=True).reshape(k, 4)), size, mode="xyxy")
+            out.add_field("scores", torch.from_numpy(np.array(scores, dtype=np.float32, copy=True)))
+            out.add_field("ids", torch.from_numpy(np.array(ids, dtype=np.int64, copy=True)))
+            out.add_field("labels", torch.from_numpy(np.array(labels, dtype=np.int64, copy=True)))
+            return out
         nbytes = 36 * k
         if self._out_host is None or self._out_host.numel() < nbytes:
             self._out_host = torch.zeros((max(nbytes, 36 * 256),), dtype=torch.uint8).pin_memory()
@@ -372,6 +382,17 @@ class SiamMOT(nn.Module):
         r = super()._apply(fn, *a, **k)
         self._engine_stale = True
         return r
+
+    @property
+    def results_on_host(self):
+        """True: forward / forward_clip return CPU BoxLists built straight from the solver's host arrays (the reference's
+        callers move every result to the CPU anyway: demo_inference.py:107, inferencer.py:65).  Default False = the
+        reference contract (BoxList on the model's device)."""
+        return self.roi_heads.results_on_host
+
+    @results_on_host.setter
+    def results_on_host(self, v):
+        self.roi_heads.results_on_host = bool(v)
 
     # ---- reference API
     def flush_memory(self, cache=None):

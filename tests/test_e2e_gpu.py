@@ -115,3 +115,19 @@ def test_forward_clip_equals_frame_by_frame():
     for a, b in zip(ref, got):
         assert torch.equal(a.bbox, b.bbox) and torch.equal(a.get_field("ids"), b.get_field("ids"))
         assert torch.equal(a.get_field("scores"), b.get_field("scores"))
+
+
+def test_results_on_host_are_the_same_results():
+    """Egress option: CPU BoxLists built from the solver's host arrays equal the device ones."""
+    name = "emm_256x384"
+    outs = []
+    for host in (False, True):
+        cfg, model, clip = build_model(name, "float32")
+        model.results_on_host = host
+        model.reset_siammot_status()
+        res = [model(clip[t].to("cuda"))[0] for t in range(SCENARIOS[name]["frames"])]
+        assert all(r.bbox.device.type == ("cpu" if host else "cuda") for r in res)
+        outs.append(res)
+    for a, b in zip(*outs):
+        assert torch.equal(a.bbox.cpu(), b.bbox) and torch.equal(a.get_field("scores").cpu(), b.get_field("scores"))
+        assert torch.equal(a.get_field("ids").cpu(), b.get_field("ids")) and torch.equal(a.get_field("labels").cpu(), b.get_field("labels"))
