@@ -70,9 +70,9 @@ typedef struct {
   int in_dtype;  /* SMOT_F32 | SMOT_F16: dtype of in, weight, residual */
   int out_dtype; /* SMOT_F32 | SMOT_F16 */
   int algo;      /* SMOT_CONV_* */
-  /* optional scratch for split-K (tcgen05 path, few output tiles x long K): fp32 partial tiles + per-tile
-   * arrival counters.  The counter region (first SMOT_CONV_WS_COUNTER_BYTES bytes) must be zero before the
-   * first use and is left zero by every call; calls sharing a workspace must be stream-ordered. */
+  /* optional scratch for split-K (tcgen05 path, few output tiles x long K): fp32 partial tiles, summed in split
+   * order by a second kernel.  The first SMOT_CONV_WS_COUNTER_BYTES bytes are reserved (never written); calls
+   * sharing a workspace must be stream-ordered -- concurrent streams need one workspace each. */
   void* workspace;
   size_t workspace_bytes;
 } smot_conv_desc;

@@ -39,10 +39,9 @@ struct TcArgs {
   int Cin, Cout, out_ld, res_ld, relu;
   int taps, KW, pad, cin_chunks, stride;
   int tiles_w, tiles_h, tile_w, tile_h;
-  // split-K (gridDim.z > 1): fp32 partial tiles [z][tile][128][Cout] and one arrival counter per output tile
+  // split-K (gridDim.z > 1): fp32 partial tiles [z][tile][128][Cout], summed by splitk_reduce_kernel
   int splits, chunks_per_split, num_tiles;
   float* partial;
-  unsigned* counters;
   unsigned long long* dbg;  // developer timing probe (SMOT_TC_DEBUG): 8 timestamps of CTA (0,0,0), else null
 };
 
@@ -254,7 +253,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   uint64_t* empty = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
-  uint32_t* tmem_slot_aux = tmem_slot + 1;
   float* s_scale = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);  // [BN] scale, then [BN] bias
   float* s_bias = s_scale + BN;
 
@@ -648,7 +646,6 @@ static int conv2d_tc_halo(const smot_conv_desc* d, int mode, cudaStream_t st) {
   a.splits = (a.cin_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
   a.num_tiles = (int)tiles;
   a.dbg = nullptr;
-  a.counters = (unsigned*)d->workspace;
   a.partial = d->workspace ? (float*)((char*)d->workspace + SMOT_CONV_WS_COUNTER_BYTES) : nullptr;
   dim3 grid((unsigned)tiles, (unsigned)(d->Cout / BN), (unsigned)a.splits);
   const bool crowded = (long long)grid.x * grid.y * grid.z > 148;   // several CTAs per SM: shallow weight ring, 2 CTAs / SM
@@ -679,12 +676,10 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   }
   a.tiles_w = ceil_div(d->OW, a.tile_w), a.tiles_h = ceil_div(d->OH, a.tile_h);
   const long long tiles = (long long)a.tiles_w * a.tiles_h * d->batch;
-  // BN: 128 unless that leaves most SMs idle
-  // measured (profiles/): below one wave of CTAs the kernel is latency-bound per CTA, so more, smaller tiles win
-  // Measured (tools/probe_tc.py, tools/bench_conv.py): the main loop advances ~0.35 us per 64-deep k-chunk whatever
-  // BN is (64..256), how deep the ring is and how many CTAs share the SM -- the four M128/K16 MMAs of a chunk pace it,
-  // not TMA.  Hence: (a) the widest N that still leaves ~100 CTAs; (b) layers with only a handful of output tiles
-  // (levels 4-5, FC layers) take the widest BN AND split K over up to 8 CTAs, finished by splitk_reduce_kernel.
+  // Tile shape.  Measured (profiles/conv_probe_r01.txt): the k-steps issue at the tensor-pipe floor, but two thirds of a layer
+  // is per-kernel / per-CTA fixed cost (launch, TMEM allocation, epilogue).  Hence: (a) the widest N that still leaves ~100
+  // CTAs; (b) layers with only a handful of output tiles (levels 4-5, FC layers) take the widest BN AND split K over up
+  // to 8 CTAs, finished by splitk_reduce_kernel (not splitting, or splitting less, measured slower).
   const int all_chunks = a.taps * a.cin_chunks;
   static const int min_ctas = getenv("SMOT_TC_MINCTAS") ? atoi(getenv("SMOT_TC_MINCTAS")) : 96;   // developer override
   int BN = 64;
@@ -726,7 +721,6 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
     const char* dbg = getenv("SMOT_TC_DEBUG");  // hex device pointer to 8 x u64
     a.dbg = dbg ? (unsigned long long*)strtoull(dbg, nullptr, 16) : nullptr;
   }
-  a.counters = (unsigned*)d->workspace;
   a.partial = d->workspace ? (float*)((char*)d->workspace + SMOT_CONV_WS_COUNTER_BYTES) : nullptr;
   dim3 grid((unsigned)tiles, (unsigned)(d->Cout / BN), (unsigned)a.splits);
   // many short tiles: 2-stage rings let 4 CTAs share an SM, so one CTA's prologue / epilogue overlaps the

@@ -318,7 +318,9 @@ static int launch_sort_nms(SortNmsArgs& a, int problems, cudaStream_t st) {
     }
     attr_set = true;
   }
-  nms_sort_kernel<<<problems, SN_THREADS, a.presorted ? 0 : (size_t)a.np * 8, st>>>(a);
+  // the bitonic network has np/2 compare-exchanges per stage: a smaller CTA makes its ~50 barriers cheaper
+  const int sort_threads = a.presorted ? SN_THREADS : (a.np / 2 < 128 ? 128 : (a.np / 2 > SN_THREADS ? SN_THREADS : a.np / 2));
+  nms_sort_kernel<<<problems, sort_threads, a.presorted ? 0 : (size_t)a.np * 8, st>>>(a);
   SMOT_CHECK_LAUNCH("sort_nms(sort)");
   const bool suppress = a.thresh > 0.f && a.max_keep > 0;
   a.cache_pitch = 0;
@@ -435,6 +437,9 @@ __device__ void select_topk_u64(const unsigned long long* keys, int n, int k, un
       }
       __syncthreads();
       hi = shift;
+      // every key left in the threshold bin is needed: the prefix (lower digits 0) already is the threshold.  Typical after
+      // the logit digits -- the index digits only matter when equal logits straddle the cut.
+      if (s_need == s_active) break;
     }
     const unsigned long long T = s_prefix;  // the k-th largest key (0 if fewer than k keys exist)
     for (int b0 = 0; b0 < n; b0 += blockDim.x) {
