@@ -37,6 +37,29 @@ __global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out,
   st4(out + pix * out_ld + c, r);
 }
 
+// fp16, 8 channels (16 bytes) per thread: the max of fp16 values is exact in fp16, so no conversion at all
+__global__ void maxpool2x2_h8_kernel(const __half* __restrict__ in, __half* __restrict__ out, int batch, int H, int W, int C,
+                                     int in_ld, int out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int OH = H / 2, OW = W / 2, C8 = C / 8;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)batch * OH * OW * C8) return;
+  const int c = (int)(idx % C8) * 8;
+  const size_t pix = idx / C8;
+  const int ow = (int)(pix % OW), oh = (int)((pix / OW) % OH), n = (int)(pix / ((size_t)OW * OH));
+  const __half* base = in + (((size_t)n * H + 2 * oh) * W + 2 * ow) * in_ld + c;
+  uint4 a = *reinterpret_cast<const uint4*>(base), b = *reinterpret_cast<const uint4*>(base + in_ld);
+  uint4 d = *reinterpret_cast<const uint4*>(base + (size_t)W * in_ld), e = *reinterpret_cast<const uint4*>(base + (size_t)(W + 1) * in_ld);
+  uint4 r;
+  const __half2 *pa = reinterpret_cast<const __half2*>(&a), *pb = reinterpret_cast<const __half2*>(&b);
+  const __half2 *pd = reinterpret_cast<const __half2*>(&d), *pe = reinterpret_cast<const __half2*>(&e);
+  __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(__hmax2(pa[i], pb[i]), __hmax2(pd[i], pe[i]));
+  *reinterpret_cast<uint4*>(out + pix * out_ld + c) = r;
+}
+
 // ---- lateral += bilinear(top), align_corners=False (ATen upsample_bilinear2d index rule) -----
 template <typename T>
 __global__ void upsample_add_kernel(const T* __restrict__ top, int Ht, int Wt, int top_ld, T* __restrict__ lat, int H,
@@ -66,6 +89,45 @@ __global__ void upsample_add_kernel(const T* __restrict__ top, int Ht, int Wt, i
   l.z += hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
   l.w += hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
   st4(dst, l);
+}
+
+// fp16, 8 channels per thread; same arithmetic per channel as upsample_add_kernel
+__global__ void upsample_add_h8_kernel(const __half* __restrict__ top, int Ht, int Wt, int top_ld, __half* __restrict__ lat, int H,
+                                       int W, int lat_ld, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C8 = C / 8;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)H * W * C8) return;
+  const int c = (int)(idx % C8) * 8;
+  const size_t pix = idx / C8;
+  const int x = (int)(pix % W), y = (int)(pix / W);
+  const float sh = (float)Ht / (float)H, sw = (float)Wt / (float)W;
+  const float fy = fmaxf(sh * ((float)y + 0.5f) - 0.5f, 0.f);
+  const float fx = fmaxf(sw * ((float)x + 0.5f) - 0.5f, 0.f);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < Ht - 1 ? 1 : 0), x1 = x0 + (x0 < Wt - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const uint4 q00 = *reinterpret_cast<const uint4*>(top + ((size_t)y0 * Wt + x0) * top_ld + c);
+  const uint4 q01 = *reinterpret_cast<const uint4*>(top + ((size_t)y0 * Wt + x1) * top_ld + c);
+  const uint4 q10 = *reinterpret_cast<const uint4*>(top + ((size_t)y1 * Wt + x0) * top_ld + c);
+  const uint4 q11 = *reinterpret_cast<const uint4*>(top + ((size_t)y1 * Wt + x1) * top_ld + c);
+  __half* dst = lat + pix * lat_ld + c;
+  uint4 ql = *reinterpret_cast<const uint4*>(dst);
+  const __half2 *p00 = reinterpret_cast<const __half2*>(&q00), *p01 = reinterpret_cast<const __half2*>(&q01);
+  const __half2 *p10 = reinterpret_cast<const __half2*>(&q10), *p11 = reinterpret_cast<const __half2*>(&q11);
+  __half2* pl = reinterpret_cast<__half2*>(&ql);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v00 = __half22float2(p00[i]), v01 = __half22float2(p01[i]), v10 = __half22float2(p10[i]), v11 = __half22float2(p11[i]);
+    float2 l = __half22float2(pl[i]);
+    // ATen: w_y0 * (w_x0 * v00 + w_x1 * v01) + w_y1 * (w_x0 * v10 + w_x1 * v11)
+    l.x += hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+    l.y += hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+    pl[i] = __floats2half2_rn(l.x, l.y);
+  }
+  *reinterpret_cast<uint4*>(dst) = ql;
 }
 
 // ---- out[y][x] = in[2y][2x] ----------------------------------------------------------------
@@ -220,6 +282,8 @@ extern "C" int smot_maxpool2x2(const void* in, void* out, int batch, int H, int 
   size_t total = (size_t)batch * (H / 2) * (W / 2) * (C / 4);
   if (dtype == SMOT_F32)
     launch_pdl(maxpool2x2_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const float*)in, (float*)out, batch, H, W, C, in_ld, out_ld);
+  else if (dtype == SMOT_F16 && C % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0)
+    launch_pdl(maxpool2x2_h8_kernel, dim3(blocks_for(total / 2, 256)), dim3(256), 0, st, (const __half*)in, (__half*)out, batch, H, W, C, in_ld, out_ld);
   else if (dtype == SMOT_F16)
     launch_pdl(maxpool2x2_kernel<__half>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const __half*)in, (__half*)out, batch, H, W, C, in_ld, out_ld);
   else
@@ -236,6 +300,8 @@ extern "C" int smot_upsample_add(const void* top, int Ht, int Wt, int top_ld, vo
   size_t total = (size_t)H * W * (C / 4);
   if (dtype == SMOT_F32)
     launch_pdl(upsample_add_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const float*)top, Ht, Wt, top_ld, (float*)lateral, H, W, lat_ld, C);
+  else if (dtype == SMOT_F16 && C % 8 == 0 && top_ld % 8 == 0 && lat_ld % 8 == 0 && (((uintptr_t)top | (uintptr_t)lateral) & 15) == 0)
+    launch_pdl(upsample_add_h8_kernel, dim3(blocks_for(total / 2, 256)), dim3(256), 0, st, (const __half*)top, Ht, Wt, top_ld, (__half*)lateral, H, W, lat_ld, C);
   else if (dtype == SMOT_F16)
     launch_pdl(upsample_add_kernel<__half>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const __half*)top, Ht, Wt, top_ld, (__half*)lateral, H, W, lat_ld, C);
   else
