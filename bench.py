@@ -5,6 +5,8 @@ A "step" is one frame through the per-frame hot path (backbone -> FPN -> RPN -> 
 30 tracks in memory -> refinement -> solver -> next-frame memory) on the BASELINE.json configs[1]
 workload: 1280x720 synthetic video, i.e. a 3x704x1280 network input after the reference's own resize
 rule (image_augmentation.py:21-42), DLA-34-FPN + EMM, fp16 storage / fp32 accumulation.
+`value`: model.forward_clip over normalised frames resident in HBM; `e2e`: model(frame) per decoded uint8 frame in
+pinned host memory (H2D, test transform on the device, hot path, packed result D2H inside the timed region).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype float16|float32]
   python bench.py --impl reference ...     # the reference path on the host CPU (oracle port)

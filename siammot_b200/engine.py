@@ -8,9 +8,11 @@ This is the B200-native replacement for everything beneath ``SiamMOT.forward``
   ride in the conv epilogues;
 * the frame-independent stage (backbone -> FPN -> RPN head -> proposal selection -> box head ->
   per-class NMS) is a fixed list of C-ABI launches with device-side counts, captured once into a
-  CUDA graph and replayed per frame;
+  CUDA graph (independent layers as parallel branches) and replayed per frame;
 * the track-dependent stage (search-region ROIAlign with virtual padding -> xcorr -> EMM towers ->
-  fused decode -> box-head refinement -> solver NMS) is launched eagerly with N = tracks in memory;
+  fused decode -> box-head refinement -> solver NMS) is a launch list per N = tracks in memory, replayed as a
+  CUDA graph from its second use;
+* decoded uint8 frames are resized / normalised on the device (preprocess.py), bit-identically to the CPU transform;
 * exactly one device->host copy per frame (the solver needs ids on the host, track_solver.py:62-106),
   against >= 10 hidden syncs in the reference.
 
