@@ -30,6 +30,25 @@ void set_error(const char* fmt, ...);
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Opt `kernel` into `bytes` of dynamic shared memory.  The attribute is per device and a process may drive several
+// GPUs, so the largest grant is remembered per device (one static table per call site = per kernel instance).
+constexpr int SMOT_MAX_DEVICES = 64;
+#define SMOT_ENSURE_SMEM(kernel, bytes, what)                                                                            \
+  do {                                                                                                                   \
+    static int granted__[::smot::SMOT_MAX_DEVICES];                                                                      \
+    int dev__ = 0;                                                                                                       \
+    cudaGetDevice(&dev__);                                                                                               \
+    const int want__ = (int)(bytes);                                                                                     \
+    if (dev__ >= 0 && dev__ < ::smot::SMOT_MAX_DEVICES && want__ > 48 * 1024 && granted__[dev__] < want__) {             \
+      cudaError_t e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want__);               \
+      if (e__ != cudaSuccess) {                                                                                          \
+        ::smot::set_error("%s: cudaFuncSetAttribute(%d bytes): %s", what, want__, cudaGetErrorString(e__));              \
+        return SMOT_ERR_CUDA;                                                                                            \
+      }                                                                                                                  \
+      granted__[dev__] = want__;                                                                                         \
+    }                                                                                                                    \
+  } while (0)
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------
 // The detection stage is ~110 short kernels in one CUDA graph; at 5-15 us each, the drain -> launch -> prologue
 // gap between consecutive kernels is a large share of the frame.  Kernels launched through launch_pdl() may begin

@@ -274,15 +274,7 @@ bool conv2d_hires_supported(const smot_conv_desc* d) {
 template <int CIN, int COUT, int STRIDE>
 static int launch3(const HiresArgs& a, int batch, cudaStream_t st) {
   using C = Hires3<CIN, COUT, STRIDE>;
-  static bool attr = false;
-  if (!attr && C::SMEM > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_hires_kernel<CIN, COUT, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-    if (e != cudaSuccess) {
-      set_error("smot_conv2d(hires): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return SMOT_ERR_CUDA;
-    }
-    attr = true;
-  }
+  SMOT_ENSURE_SMEM((conv3x3_hires_kernel<CIN, COUT, STRIDE>), C::SMEM, "smot_conv2d(hires)");
   dim3 grid(ceil_div(a.OW, C::TW), ceil_div(a.OH, C::TH), batch);
   launch_pdl(conv3x3_hires_kernel<CIN, COUT, STRIDE>, grid, dim3(256), C::SMEM, st, a);
   SMOT_CHECK_LAUNCH("smot_conv2d(hires)");

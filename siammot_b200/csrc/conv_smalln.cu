@@ -318,15 +318,10 @@ static int launch_smalln(const SmallNArgs& a, cudaStream_t st) {
   }
   const size_t smem = (size_t)cout_pad * a.K * sizeof(float);
   const unsigned grid = (unsigned)ceil_div(a.M, SN_PIX * SN_WARPS);
-  cudaError_t e = cudaSuccess;
-#define SMOT_SN_LAUNCH(CO)                                                                                          \
-  do {                                                                                                              \
-    static size_t attr = 0;                                                                                         \
-    if (smem > 48 * 1024 && smem > attr) {                                                                          \
-      e = cudaFuncSetAttribute(conv_smalln_kernel<TI, TO, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      attr = smem;                                                                                                  \
-    }                                                                                                               \
-    if (e == cudaSuccess) conv_smalln_kernel<TI, TO, CO><<<grid, SN_WARPS * 32, smem, st>>>(a);                     \
+#define SMOT_SN_LAUNCH(CO)                                                                       \
+  do {                                                                                           \
+    SMOT_ENSURE_SMEM((conv_smalln_kernel<TI, TO, CO>), smem, "smot_conv2d(smalln)");             \
+    conv_smalln_kernel<TI, TO, CO><<<grid, SN_WARPS * 32, smem, st>>>(a);                        \
   } while (0)
   if (cout_pad == 4)
     SMOT_SN_LAUNCH(4);
@@ -335,10 +330,6 @@ static int launch_smalln(const SmallNArgs& a, cudaStream_t st) {
   else
     SMOT_SN_LAUNCH(16);
 #undef SMOT_SN_LAUNCH
-  if (e != cudaSuccess) {
-    set_error("smot_conv2d(smalln): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    return SMOT_ERR_CUDA;
-  }
   SMOT_CHECK_LAUNCH("smot_conv2d(smalln)");
   return SMOT_OK;
 }

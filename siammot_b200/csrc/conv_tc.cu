@@ -566,15 +566,7 @@ bool conv2d_tc_supported(const smot_conv_desc* d) {
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, dim3 grid, cudaStream_t st) {
   using S = TcSmem<BN, STAGES>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-    if (e != cudaSuccess) {
-      set_error("smot_conv2d(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return SMOT_ERR_CUDA;
-    }
-    attr = true;
-  }
+  SMOT_ENSURE_SMEM((conv_tc_kernel<BN, STAGES>), S::TOTAL, "smot_conv2d(tcgen05)");
   launch_pdl(conv_tc_kernel<BN, STAGES>, grid, dim3(TC_THREADS), S::TOTAL, st, tmA, tmB, a);
   SMOT_CHECK_LAUNCH("smot_conv2d(tcgen05)");
   return SMOT_OK;
@@ -583,15 +575,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
 template <int BN, int PW, int SB>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, dim3 grid, int bo_mode, cudaStream_t st) {
   using S = HaloSmem<BN, PW, SB>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<BN, PW, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-    if (e != cudaSuccess) {
-      set_error("smot_conv2d(tcgen05 halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return SMOT_ERR_CUDA;
-    }
-    attr = true;
-  }
+  SMOT_ENSURE_SMEM((conv3x3_halo_kernel<BN, PW, SB>), S::TOTAL, "smot_conv2d(tcgen05 halo)");
   launch_pdl(conv3x3_halo_kernel<BN, PW, SB>, grid, dim3(TC_THREADS), S::TOTAL, st, tmA, tmB, a, bo_mode);
   SMOT_CHECK_LAUNCH("smot_conv2d(tcgen05 halo)");
   return SMOT_OK;

@@ -234,15 +234,7 @@ template <typename T, int S, int TT>
 static int launch_xcorr(const void* x, const void* k, void* out, int n, int C, cudaStream_t st) {
   constexpr int XR = (S - TT + 1) / 2 + TT - 1;
   const size_t smem = ((size_t)XR * S * 32 * sizeof(T) + 15) / 16 * 16 + (size_t)TT * TT * 32 * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(xcorr_kernel<T, S, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("smot_xcorr: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return SMOT_ERR_CUDA;
-    }
-    attr = true;
-  }
+  SMOT_ENSURE_SMEM((xcorr_kernel<T, S, TT>), smem, "smot_xcorr");
   xcorr_kernel<T, S, TT><<<dim3(C / 32, n, 2), 256, smem, st>>>((const T*)x, (const T*)k, (T*)out, C);
   SMOT_CHECK_LAUNCH("smot_xcorr");
   return SMOT_OK;
@@ -434,15 +426,7 @@ extern "C" int smot_xcorr(const void* x, const void* k, void* out, int n, int ch
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SMOT_F16 && S == 30 && T == 15 && channels % XM_CG == 0 &&
       (((uintptr_t)x | (uintptr_t)k | (uintptr_t)out) & 15) == 0) {
-    static bool attr = false;
-    if (!attr) {
-      cudaError_t e = cudaFuncSetAttribute(xcorr_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XM_SMEM);
-      if (e != cudaSuccess) {
-        set_error("smot_xcorr: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        return SMOT_ERR_CUDA;
-      }
-      attr = true;
-    }
+    SMOT_ENSURE_SMEM(xcorr_mma_kernel, XM_SMEM, "smot_xcorr(mma)");
     xcorr_mma_kernel<<<dim3(channels / XM_CG, n), XM_WARPS * 32, XM_SMEM, st>>>((const __half*)x, (const __half*)k, (__half*)out, channels);
     SMOT_CHECK_LAUNCH("smot_xcorr(mma)");
     return SMOT_OK;
@@ -475,15 +459,7 @@ extern "C" int smot_emm_decode(const float* maps, int map_ld, int n, int O, int 
   const size_t smem = ((size_t)O * O * EMM_CH + (size_t)EMM_CH * rows_max * OW) * sizeof(float);
   SMOT_CHECK_ARG(smem <= 200 * 1024, "smot_emm_decode: response map %dx%d (x%d) does not fit shared memory", O, O, up);
   cudaStream_t st = (cudaStream_t)stream;
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(emm_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("smot_emm_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return SMOT_ERR_CUDA;
-    }
-    attr_bytes = smem;
-  }
+  SMOT_ENSURE_SMEM(emm_score_kernel, smem, "smot_emm_decode");
   DecodeArgs a;
   a.maps = maps, a.map_ld = map_ld, a.n = n, a.O = O, a.up = up, a.T = T, a.sr = sr, a.tboxes = tboxes, a.hann = hann;
   a.pad = pad, a.use_centerness = use_centerness, a.sigma = (float)sigma, a.one_minus_sigma = (float)(1.0 - sigma), a.img_w = img_w, a.img_h = img_h, a.amodal = amodal;

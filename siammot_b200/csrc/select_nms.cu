@@ -307,17 +307,8 @@ static void carve_sort_nms_ws(SortNmsArgs& a, void* ws, int problems) {
 
 static int launch_sort_nms(SortNmsArgs& a, int problems, cudaStream_t st) {
   a.np = next_pow2(a.n_max);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_MAX * 8);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_MAX * 12 + SN_CACHE_BYTES);
-    if (e != cudaSuccess) {
-      set_error("sort_nms: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      return SMOT_ERR_CUDA;
-    }
-    attr_set = true;
-  }
+  SMOT_ENSURE_SMEM(nms_sort_kernel, SN_MAX * 8, "sort_nms(sort)");
+  SMOT_ENSURE_SMEM(nms_reduce_kernel, SN_MAX * 12 + SN_CACHE_BYTES, "sort_nms(reduce)");
   // the bitonic network has np/2 compare-exchanges per stage: a smaller CTA makes its ~50 barriers cheaper
   const int sort_threads = a.presorted ? SN_THREADS : (a.np / 2 < 128 ? 128 : (a.np / 2 > SN_THREADS ? SN_THREADS : a.np / 2));
   nms_sort_kernel<<<problems, sort_threads, a.presorted ? 0 : (size_t)a.np * 8, st>>>(a);
@@ -755,17 +746,8 @@ extern "C" int smot_rpn_select(const smot_rpn_level* levels, int num_levels, int
   ra.cand_boxes = cand_boxes, ra.cand_scores = cand_scores, ra.cand_count = cand_count;
   ra.kept_boxes = kept_boxes, ra.kept_scores = kept_scores, ra.kept_count = kept_count;
   ra.out_boxes = out_boxes, ra.out_scores = out_scores, ra.out_count = out_count;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rpn_local_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RPN_CHUNK * 8);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(rpn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RPN_MERGE_SMEM_KEYS * 8);
-    if (e != cudaSuccess) {
-      set_error("smot_rpn_select: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      return SMOT_ERR_CUDA;
-    }
-    attr_set = true;
-  }
+  SMOT_ENSURE_SMEM(rpn_local_topk_kernel, RPN_CHUNK * 8, "smot_rpn_select(local top-k)");
+  SMOT_ENSURE_SMEM(rpn_merge_kernel, RPN_MERGE_SMEM_KEYS * 8, "smot_rpn_select(merge)");
   rpn_local_topk_kernel<<<nc, 1024, RPN_CHUNK * 8, st>>>(ra);
   SMOT_CHECK_LAUNCH("smot_rpn_select(local top-k)");
   rpn_merge_kernel<<<num_levels, 1024, ra.merge_in_smem && widest > 1 ? (size_t)widest * 1024 * 8 : 0, st>>>(ra);
