@@ -96,3 +96,68 @@ def test_track_pool_state_machine():
     tu = TrackUtils(search_expansion=1.0, min_search_wh=0, pad_pixels=512)
     sr = tu.search_region(torch.tensor([[100., 100., 159., 249.]]))
     assert sr.tolist() == [[582., 537., 701., 836.]]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_host_solver_matches_oracle_on_random_sequences(seed):
+    """The product's host half of the solver (numpy, NMS survivors in, ids out) and its TrackPool against the oracle's
+    TrackSolver.forward restatement over 40 random frames: ids, folded scores and the pool state (active set, dormant
+    table incl. insertion order, id counter) must agree exactly every frame."""
+    import numpy as np
+    from oracle import prims
+    from oracle.siammot_oracle import PoolState, solver_forward
+    from siammot_b200.config import get_cfg
+    from siammot_b200.modelling.rcnn import TrackSolver
+    from siammot_b200.modelling.track_utils import TrackPool
+    cfg = get_cfg()
+    T = cfg.MODEL.TRACK_HEAD
+    T.MAX_DORMANT_FRAMES = 3
+    g = torch.Generator().manual_seed(seed)
+    pool_o = PoolState(T.MAX_DORMANT_FRAMES)
+    pool_p = TrackPool(max_dormant_frames=T.MAX_DORMANT_FRAMES)
+    solver = TrackSolver(pool_p, T.TRACK_THRESH, T.START_TRACK_THRESH, T.RESUME_TRACK_THRESH)
+    started = 0
+    for t in range(40):
+        # candidates: fresh detections (id -1, score in (0.05, 1)) + one row per track in memory (active and dormant,
+        # score = refined average in [1, 2)); boxes cluster so that NMS removes some rows, tracks included
+        known = sorted(pool_o.active) + list(pool_o.dormant.keys())
+        n_det = int(torch.randint(3, 12, (1,), generator=g))
+        ctr = torch.rand(n_det + len(known), 2, generator=g) * 60 + torch.randint(0, 3, (n_det + len(known), 1), generator=g) * 200
+        wh = torch.rand(n_det + len(known), 2, generator=g) * 20 + 50
+        boxes = torch.cat([ctr, ctr + wh], 1)
+        scores = torch.cat([torch.rand(n_det, generator=g) * 0.95 + 0.05, 1.0 + torch.rand(len(known), generator=g)])
+        if len(known):   # exact ties between a detection and a track row, and scores straddling the thresholds
+            scores[n_det] = 1.0 + scores[0]
+        ids = torch.tensor([-1] * n_det + known, dtype=torch.int64)
+        labels = torch.ones(n_det + len(known), dtype=torch.int64)
+        det = dict(boxes=boxes, scores=scores.clone(), ids=ids.clone(), labels=labels)
+        ref = solver_forward(cfg, pool_o, det)
+        # the product path: active +1 and NMS happen on the device (track_combine / sort_nms kernels); emulate them with the
+        # same primitives, then the host half under test
+        active = pool_p.get_active_ids()
+        adj = scores + torch.tensor([1.0 if int(i) in active else 0.0 for i in ids])
+        keep = prims.nms_legacy(boxes, adj, 0.5)
+        all_track_ids = set(ids[ids >= 0].tolist())
+        sc, out_ids = solver.resolve(adj[keep].numpy(), ids[keep].numpy(), all_track_ids)
+        assert out_ids.tolist() == ref["ids"].tolist(), "frame %d" % t
+        assert np.array_equal(sc, ref["scores"].numpy()), "frame %d" % t
+        assert pool_p.get_active_ids() == pool_o.active and list(pool_p._dormant_ids.items()) == list(pool_o.dormant.items())
+        assert pool_p._max_id + 1 == pool_o.next_id and pool_p._frame_idx == pool_o.frame
+        started = pool_o.next_id
+    assert started > 10 and len(pool_o.dormant) + len(pool_o.active) > 0
+
+
+def test_search_region_numpy_twin_is_bit_exact():
+    """TrackUtils.search_region_np (the per-frame host path) against the torch method and the oracle restatement."""
+    import numpy as np
+    from oracle.siammot_oracle import search_region
+    from siammot_b200.modelling.track_utils import TrackUtils
+    g = torch.Generator().manual_seed(4)
+    for exp, min_wh in ((1.0, 0), (1.0, 120), (4.0, 0)):
+        tu = TrackUtils(search_expansion=exp, min_search_wh=min_wh, pad_pixels=512)
+        xy = torch.rand(200, 2, generator=g) * 1200 - 100
+        wh = torch.rand(200, 2, generator=g) * 400 + 1
+        boxes = torch.cat([xy, xy + wh], 1)
+        ref = search_region(boxes, 512, exp, min_wh)
+        assert torch.equal(tu.search_region(boxes), ref)
+        assert np.array_equal(tu.search_region_np(boxes.numpy()), ref.numpy())
