@@ -64,3 +64,19 @@ def test_library_coefficients_match_oracle(n_in, n_out):
     assert L.smot_resample_coeffs(n_in, n_out, bounds.ctypes.data_as(C.c_void_p), kk.ctypes.data_as(C.c_void_p)) == 0
     rb, rk = opp.precompute_coeffs(n_in, n_out)
     assert ks == rk.shape[1] and np.array_equal(rb, bounds) and np.array_equal(rk, kk)
+
+
+def test_oracle_matches_committed_golden_vectors():
+    """tests/golden/preprocess.npz was written by Pillow / torchvision themselves (make_preprocess_golden.py): the oracle
+    must reproduce it bit for bit whatever Pillow is installed where the tests run."""
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    from make_preprocess_golden import CASES, frame
+    gold = np.load(os.path.join(here, "preprocess.npz"))
+    for (seed, h, w, oh, ow, mean, std, bgr) in CASES:
+        img = frame(seed, h, w)
+        resized = opp.pil_resize_bilinear(img, oh, ow)
+        assert np.array_equal(resized, gold["resized_%d" % seed])
+        assert np.array_equal(opp.normalize(resized, mean, std, bgr).numpy(), gold["tensor_%d" % seed])
