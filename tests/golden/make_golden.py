@@ -22,7 +22,7 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
 from oracle import reference_loader  # noqa: E402
-from scenarios import SCENARIOS, golden_path, inject_boxes  # noqa: E402
+from scenarios import GIVEN_SCENARIOS, SCENARIOS, given_boxes, golden_path, inject_boxes  # noqa: E402
 from siammot_b200.synthetic import make_state_dict  # noqa: E402
 from siammot_b200.synth_clip import make_clip  # noqa: E402
 
@@ -89,6 +89,30 @@ def run(name):
     torch.save(dict(scenario=name, spec=sc, torch=torch.__version__, frames=frames), golden_path(name))
 
 
+def run_given(name):
+    """Public-detection path: model(frame, given_detection=[BoxList]) every frame (roi_heads.py:26-34)."""
+    sc = GIVEN_SCENARIOS[name]
+    cfg, model = build_reference(sc)
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    clip = make_clip(sc["frames"], sc["H"], sc["W"], sc["n_obj"], sc["clip_seed"])
+    model.reset_siammot_status()
+    frames = []
+    with torch.no_grad():
+        for t, boxes in enumerate(given_boxes(sc)):
+            n = boxes.shape[0]
+            bl = BoxList(boxes.clone(), (sc["W"], sc["H"]), mode="xyxy")
+            bl.add_field("labels", torch.ones(n, dtype=torch.int64))
+            bl.add_field("scores", torch.ones(n))
+            bl.add_field("ids", torch.full((n,), -1, dtype=torch.int64))
+            out = model(clip[t], given_detection=[bl])[0]
+            pool = model.roi_heads.track.track_pool
+            frames.append(dict(boxes=out.bbox.clone(), scores=out.get_field("scores").clone(), ids=out.get_field("ids").clone(),
+                               labels=out.get_field("labels").clone(), active=sorted(pool._active_ids),
+                               dormant=sorted(pool._dormant_ids.keys())))
+            print(name, "frame", t, "given", n, "boxes", len(out), "tracked", int((frames[-1]["ids"] >= 0).sum()))
+    torch.save(dict(scenario=name, spec=sc, torch=torch.__version__, frames=frames), golden_path(name))
+
+
 if __name__ == "__main__":
-    for n in (sys.argv[1:] or list(SCENARIOS)):
-        run(n)
+    for n in (sys.argv[1:] or list(SCENARIOS) + list(GIVEN_SCENARIOS)):
+        (run_given if n in GIVEN_SCENARIOS else run)(n)

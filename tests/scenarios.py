@@ -25,6 +25,30 @@ SCENARIOS = {
 }
 
 
+# public-detection path: the reference is fed `given_detection` every frame (roi_heads.py:26-34);
+# oracle-only fixtures (the engine's given-detection path is checked against the oracle in tests/test_paths_gpu.py)
+GIVEN_SCENARIOS = {
+    "given_det_192x320": dict(yaml="DLA_34_FPN_EMM_MOT17.yaml",
+                              # thresholds lowered so that tracks start / persist / lapse on random public boxes
+                              overrides=["MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES", 2, "INFERENCE.USE_GIVEN_DETECTIONS", False,
+                                         "MODEL.TRACK_HEAD.START_TRACK_THRESH", 0.12, "MODEL.TRACK_HEAD.TRACK_THRESH", 0.06,
+                                         "MODEL.TRACK_HEAD.RESUME_TRACK_THRESH", 0.09],
+                              H=192, W=320, frames=5, n_obj=5, clip_seed=3, weight_seed=2, inject=None,
+                              det_seed=4, det_per_frame=(24, 24, 0, 24, 30)),   # frame 2: no public detections at all
+}
+
+
+def given_boxes(sc):
+    """The public detections of every frame of a GIVEN_SCENARIOS entry (seeded)."""
+    g = torch.Generator().manual_seed(sc["det_seed"])
+    out = []
+    for n in sc["det_per_frame"]:
+        xy = torch.rand(n, 2, generator=g) * torch.tensor([sc["W"] * 0.78, sc["H"] * 0.62])
+        wh = torch.rand(n, 2, generator=g) * torch.tensor([50., 60.]) + 10
+        out.append(torch.cat([xy, xy + wh], 1))
+    return out
+
+
 def inject_boxes(spec):
     b = torch.tensor(spec, dtype=torch.float32)
     return torch.stack((b[:, 0] - b[:, 2] / 2, b[:, 1] - b[:, 3] / 2,

@@ -70,3 +70,39 @@ def test_oracle_matches_live_reference_xcorr():
     torch.manual_seed(0)
     x, k = torch.randn(5, 16, 30, 30), torch.randn(5, 16, 15, 15)
     assert torch.equal(ref_xcorr(x, k), xcorr_depthwise(x, k))
+
+
+def test_oracle_matches_reference_golden_with_given_detections():
+    """Public-detection path (roi_heads.py:26-34): the reference was fed `given_detection` every frame, one frame with an
+    empty list (tests/golden/make_golden.py run_given)."""
+    from helpers import CONFIG_DIR, YAML_MAP
+    from oracle.siammot_oracle import OracleSiamMOT
+    from scenarios import GIVEN_SCENARIOS, given_boxes
+    from siammot_b200.config import get_cfg
+    from siammot_b200.synth_clip import make_clip
+    from siammot_b200.synthetic import make_state_dict
+    import os
+    name = "given_det_192x320"
+    sc = GIVEN_SCENARIOS[name]
+    cfg = get_cfg()
+    cfg.merge_from_file(os.path.join(CONFIG_DIR, YAML_MAP[sc["yaml"]]))
+    cfg.merge_from_list(sc["overrides"])
+    gold = load_golden(name)["frames"]
+    orc = OracleSiamMOT(cfg, make_state_dict(cfg, sc["weight_seed"]))
+    orc.reset()
+    clip = make_clip(sc["frames"], sc["H"], sc["W"], sc["n_obj"], sc["clip_seed"])
+    tracked = 0
+    for t, (boxes, g) in enumerate(zip(given_boxes(sc), gold)):
+        n = boxes.shape[0]
+        given = dict(boxes=boxes, scores=torch.ones(n), ids=torch.full((n,), -1, dtype=torch.int64),
+                     labels=torch.ones(n, dtype=torch.int64))
+        o = orc.forward(clip[t], given_detection=given)
+        assert o["boxes"].shape == g["boxes"].shape, "frame %d: box count" % t
+        assert torch.equal(o["ids"], g["ids"]), "frame %d: ids must be bit-exact" % t
+        assert torch.equal(o["labels"], g["labels"])
+        if o["boxes"].numel():
+            assert (o["boxes"] - g["boxes"]).abs().max() <= BOX_TOL
+            assert (o["scores"] - g["scores"]).abs().max() <= SCORE_TOL
+        assert sorted(orc.pool.active) == g["active"] and sorted(orc.pool.dormant.keys()) == g["dormant"]
+        tracked += int((g["ids"] >= 0).sum())
+    assert tracked >= 10

@@ -59,6 +59,36 @@ def test_given_detections_match_oracle():
         _check(got, ref, t)
 
 
+def test_given_detections_with_tracks_match_reference_golden():
+    """The public-detection scenario whose expected outputs come from the reference itself
+    (tests/golden/given_det_192x320.pt): tracks start, persist through a frame without detections, and lapse."""
+    from helpers import load_golden
+    from scenarios import GIVEN_SCENARIOS, given_boxes
+    from siammot_b200.config import get_cfg
+    from siammot_b200.structures import BoxList
+    from helpers import CONFIG_DIR, YAML_MAP
+    import os
+    sc = GIVEN_SCENARIOS["given_det_192x320"]
+    cfg = get_cfg()
+    cfg.merge_from_file(os.path.join(CONFIG_DIR, YAML_MAP[sc["yaml"]]))
+    cfg.merge_from_list(sc["overrides"])
+    cfg.DTYPE = "float32"
+    model, _ = _pair(cfg, sc["weight_seed"])
+    gold = load_golden("given_det_192x320")["frames"]
+    clip = make_clip(sc["frames"], sc["H"], sc["W"], sc["n_obj"], sc["clip_seed"])
+    model.reset_siammot_status()
+    for t, (boxes, g) in enumerate(zip(given_boxes(sc), gold)):
+        n = boxes.shape[0]
+        bl = BoxList(boxes.clone(), (sc["W"], sc["H"]), mode="xyxy")
+        bl.add_field("labels", torch.ones(n, dtype=torch.int64))
+        bl.add_field("scores", torch.ones(n))
+        bl.add_field("ids", torch.full((n,), -1, dtype=torch.int64))
+        got = model(clip[t].to("cuda"), given_detection=[bl])[0]
+        _check(got, g, t)
+        pool = model.roi_heads.track.track_pool
+        assert sorted(pool.get_active_ids()) == g["active"] and sorted(pool._dormant_ids.keys()) == g["dormant"]
+
+
 def test_eighty_tracks_match_oracle():
     """80 tracks in memory (CrowdHuman density, BASELINE configs[2]) seeded on a 384x640 frame pair."""
     from oracle.siammot_oracle import build_memory
