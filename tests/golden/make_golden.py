@@ -22,7 +22,7 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
 from oracle import reference_loader  # noqa: E402
-from scenarios import GIVEN_SCENARIOS, SCENARIOS, given_boxes, golden_path, inject_boxes  # noqa: E402
+from scenarios import GIVEN_SCENARIOS, ORACLE_SCENARIOS, SCENARIOS, given_boxes, golden_path, inject_boxes  # noqa: E402
 from siammot_b200.synthetic import make_state_dict  # noqa: E402
 from siammot_b200.synth_clip import make_clip  # noqa: E402
 
@@ -41,7 +41,7 @@ def build_reference(sc):
 
 
 def run(name):
-    sc = SCENARIOS[name]
+    sc = SCENARIOS.get(name) or ORACLE_SCENARIOS[name]
     cfg, model = build_reference(sc)
     from maskrcnn_benchmark.structures.bounding_box import BoxList
     clip = make_clip(sc["frames"], sc["H"], sc["W"], sc["n_obj"], sc["clip_seed"])
@@ -114,5 +114,5 @@ def run_given(name):
 
 
 if __name__ == "__main__":
-    for n in (sys.argv[1:] or list(SCENARIOS) + list(GIVEN_SCENARIOS)):
+    for n in (sys.argv[1:] or list(SCENARIOS) + list(ORACLE_SCENARIOS) + list(GIVEN_SCENARIOS)):
         (run_given if n in GIVEN_SCENARIOS else run)(n)

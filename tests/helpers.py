@@ -2,7 +2,7 @@ import os
 
 import torch
 
-from scenarios import SCENARIOS, golden_path, inject_boxes
+from scenarios import ORACLE_SCENARIOS, SCENARIOS, golden_path, inject_boxes
 from siammot_b200.config import get_cfg
 from siammot_b200.synthetic import make_state_dict
 from siammot_b200.synth_clip import make_clip
@@ -11,8 +11,12 @@ CONFIG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
 YAML_MAP = {"DLA_34_FPN_EMM.yaml": "dla34_emm.yaml", "DLA_34_FPN_EMM_MOT17.yaml": "dla34_emm_mot17.yaml"}
 
 
+def _spec(name):
+    return SCENARIOS.get(name) or ORACLE_SCENARIOS[name]
+
+
 def scenario_cfg(name):
-    sc = SCENARIOS[name]
+    sc = _spec(name)
     cfg = get_cfg()
     cfg.merge_from_file(os.path.join(CONFIG_DIR, YAML_MAP[sc["yaml"]]))
     cfg.merge_from_list(sc["overrides"])
@@ -20,7 +24,7 @@ def scenario_cfg(name):
 
 
 def scenario_inputs(name):
-    sc = SCENARIOS[name]
+    sc = _spec(name)
     cfg = scenario_cfg(name)
     return cfg, make_state_dict(cfg, sc["weight_seed"]), make_clip(sc["frames"], sc["H"], sc["W"], sc["n_obj"], sc["clip_seed"])
 
@@ -32,7 +36,7 @@ def load_golden(name):
 def run_oracle_scenario(name):
     """Run the CPU oracle over a scenario; returns list of per-frame dicts (+ trace)."""
     from oracle.siammot_oracle import OracleSiamMOT, build_memory
-    sc = SCENARIOS[name]
+    sc = _spec(name)
     cfg, sd, clip = scenario_inputs(name)
     orc = OracleSiamMOT(cfg, sd)
     orc.reset()

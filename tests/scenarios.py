@@ -38,6 +38,19 @@ GIVEN_SCENARIOS = {
 }
 
 
+# further reference-generated fixtures that pin the ORACLE only (CPU tests); the engine is compared with the oracle on the
+# same switches in tests/test_paths_gpu.py
+ORACLE_SCENARIOS = {
+    # two foreground classes (the reference's person_vehicle models): per-class NMS, labels carried by tracks
+    "emm_3class_192x320": dict(yaml="DLA_34_FPN_EMM.yaml", overrides=["MODEL.ROI_BOX_HEAD.NUM_CLASSES", 3],
+                               H=192, W=320, frames=5, n_obj=5, clip_seed=5, weight_seed=3, inject=None),
+    # TRACKTOR scoring switch (roi_heads.py:72-76) + centerness off (track_core.py:106-108)
+    "emm_tracktor_nocenter_256x384": dict(yaml="DLA_34_FPN_EMM.yaml",
+                                          overrides=["MODEL.TRACK_HEAD.TRACKTOR", True, "MODEL.TRACK_HEAD.EMM.USE_CENTERNESS", False],
+                                          H=256, W=384, frames=5, n_obj=6, clip_seed=0, weight_seed=1, inject=None),
+}
+
+
 def given_boxes(sc):
     """The public detections of every frame of a GIVEN_SCENARIOS entry (seeded)."""
     g = torch.Generator().manual_seed(sc["det_seed"])

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from helpers import load_golden, scenario_cfg, scenario_inputs
-from scenarios import SCENARIOS, inject_boxes
+from scenarios import ORACLE_SCENARIOS, SCENARIOS, inject_boxes
 
 pytestmark = pytest.mark.gpu
 
@@ -27,7 +27,7 @@ def build_model(name, dtype="float32"):
 
 
 def run_engine_scenario(name, dtype="float32"):
-    sc = SCENARIOS[name]
+    sc = SCENARIOS.get(name) or ORACLE_SCENARIOS[name]
     cfg, model, clip = build_model(name, dtype)
     model.reset_siammot_status()
     out, start = [], 0
@@ -53,6 +53,23 @@ def run_engine_scenario(name, dtype="float32"):
 
 @pytest.mark.parametrize("name", list(SCENARIOS))
 def test_engine_fp32_matches_reference_golden(name):
+    gold = load_golden(name)["frames"]
+    got = run_engine_scenario(name, "float32")
+    assert len(got) == len(gold)
+    for t, (g, o) in enumerate(zip(gold, got)):
+        assert o["boxes"].shape == g["boxes"].shape, "frame %d: %d boxes vs %d" % (t, o["boxes"].shape[0], g["boxes"].shape[0])
+        assert torch.equal(o["ids"], g["ids"]), "frame %d: track ids differ" % t
+        assert torch.equal(o["labels"], g["labels"])
+        assert float((o["boxes"] - g["boxes"]).abs().max()) <= BOX_TOL, "frame %d boxes" % t
+        assert float((o["scores"] - g["scores"]).abs().max()) <= SCORE_TOL, "frame %d scores" % t
+        assert o["active"] == g["active"] and o["dormant"] == g["dormant"]
+
+
+@pytest.mark.xfail(strict=False, reason="fixtures added after this round's GPU budget was spent: the oracle is pinned to them on "
+                                       "the CPU (tests/test_oracle_golden.py); the engine's first GPU run on them is pending")
+@pytest.mark.parametrize("name", list(ORACLE_SCENARIOS))
+def test_engine_fp32_matches_reference_golden_more_switches(name):
+    """Two foreground classes; TRACKTOR scoring + centerness off -- expected outputs from the reference itself."""
     gold = load_golden(name)["frames"]
     got = run_engine_scenario(name, "float32")
     assert len(got) == len(gold)

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from helpers import load_golden, run_oracle_scenario
-from scenarios import SCENARIOS
+from scenarios import ORACLE_SCENARIOS, SCENARIOS
 
 def _canon(boxes, obj):
     rows = sorted(range(boxes.shape[0]), key=lambda i: (-float(obj[i]),) + tuple(boxes[i].tolist()))
@@ -18,7 +18,7 @@ BOX_TOL = 1e-4
 SCORE_TOL = 1e-5
 
 
-@pytest.mark.parametrize("name", list(SCENARIOS))
+@pytest.mark.parametrize("name", list(SCENARIOS) + list(ORACLE_SCENARIOS))
 def test_oracle_matches_reference_golden(name):
     gold = load_golden(name)["frames"]
     got = run_oracle_scenario(name)
