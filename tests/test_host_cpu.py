@@ -40,6 +40,33 @@ def test_product_does_not_import_the_oracle():
                 assert "import oracle" not in src and "from oracle" not in src, f
 
 
+def test_no_undefined_names_in_host_code():
+    """The GPU-side host paths cannot run in a container without a GPU; at least no name in them is unbound."""
+    import sys
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import lint_names
+    bad = [(os.path.relpath(f, REPO), line, name) for f in lint_names.default_files() for line, name in lint_names.undefined_names(f)]
+    assert not bad, bad
+
+
+def test_bench_workloads_resolve_to_the_stated_network_sizes():
+    """bench.py's --workload table: the cfg overrides give exactly the network input size the workload text states."""
+    import sys
+    sys.path.insert(0, REPO)
+    import bench
+    from siammot_b200.preprocess import get_size
+    try:
+        for name, w in bench.WORKLOADS.items():
+            bench.select_workload(name)
+            cfg = bench.build_cfg("float16")
+            h, wd = w["src"]
+            assert get_size(wd, h, cfg.INPUT.MIN_SIZE_TEST, cfg.INPUT.MAX_SIZE_TEST, cfg.DATALOADER.SIZE_DIVISIBILITY) == w["net"]
+            assert bench.track_table().shape == (w["tracks"], 4)
+            assert "%dx%d" % w["net"] in w["text"] and str(w["tracks"]) in w["text"]
+    finally:
+        bench.select_workload("720p30")
+
+
 def test_config_loads_reference_style_yaml_and_overrides():
     from siammot_b200.config import get_cfg
     cfg = get_cfg()
