@@ -8,7 +8,8 @@ from siammot_b200.synthetic import make_state_dict
 from siammot_b200.synth_clip import make_clip
 
 CONFIG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "siammot_b200", "configs")
-YAML_MAP = {"DLA_34_FPN_EMM.yaml": "dla34_emm.yaml", "DLA_34_FPN_EMM_MOT17.yaml": "dla34_emm_mot17.yaml"}
+YAML_MAP = {"DLA_34_FPN_EMM.yaml": "dla34_emm.yaml", "DLA_34_FPN_EMM_MOT17.yaml": "dla34_emm_mot17.yaml",
+            "DLA_34_FPN_EMM_AOT.yaml": "dla34_emm_aot.yaml"}
 
 
 def _spec(name):

@@ -48,6 +48,13 @@ ORACLE_SCENARIOS = {
     "emm_tracktor_nocenter_256x384": dict(yaml="DLA_34_FPN_EMM.yaml",
                                           overrides=["MODEL.TRACK_HEAD.TRACKTOR", True, "MODEL.TRACK_HEAD.EMM.USE_CENTERNESS", False],
                                           H=256, W=384, frames=5, n_obj=6, clip_seed=0, weight_seed=1, inject=None),
+    # AOT geometry: 7x7 templates, search region r = 5 (35x35 windows, 29x29 responses, x16 ->
+    # 464x464 score maps), PAD_PIXELS 256, anchors 6..96, centerness off, cosine-window weight 0.1; thresholds lowered so that
+    # tracks start / lapse / resume on random weights (the shipped 0.95 / 0.6 start nothing)
+    "emm_aot_geometry_256x384": dict(yaml="DLA_34_FPN_EMM_AOT.yaml",
+                                     overrides=["MODEL.TRACK_HEAD.START_TRACK_THRESH", 0.45, "MODEL.TRACK_HEAD.TRACK_THRESH", 0.35,
+                                                "MODEL.TRACK_HEAD.RESUME_TRACK_THRESH", 0.4, "MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES", 3],
+                                     H=256, W=384, frames=6, n_obj=6, clip_seed=0, weight_seed=3, inject=None),
 }
 
 

@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
                                        "the CPU (tests/test_oracle_golden.py); the engine's first GPU run on them is pending")
 @pytest.mark.parametrize("name", list(ORACLE_SCENARIOS))
 def test_engine_fp32_matches_reference_golden_more_switches(name):
-    """Two foreground classes; TRACKTOR scoring + centerness off -- expected outputs from the reference itself."""
+    """Two foreground classes; TRACKTOR scoring + centerness off; the AOT geometry (7x7 templates, 35x35 search windows,
+    29x29 responses, PAD_PIXELS 256) -- expected outputs from the reference itself."""
     gold = load_golden(name)["frames"]
     got = run_engine_scenario(name, "float32")
     assert len(got) == len(gold)
