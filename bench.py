@@ -360,7 +360,7 @@ def run_ours(args):
                                            "note": "same loop with the reference's calling convention (frame already resized + "
                                                    "normalised on the host)"}},
         "gpu_launches": kernels_per_frame(h) * args.steps,
-        "roofline": {"kernel": "xcorr_mma_kernel (smot_xcorr)" if args.dtype == "float16" else "xcorr_kernel (smot_xcorr)", "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak,
+        "roofline": {"kernel": getattr(tp, "xcorr_kernel", "smot_xcorr"), "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak,
                      "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
                      "algorithmic_bytes": xc_bytes, "us_per_launch": round(xc_ms * 1e3, 2),
                      "timing": "10 CUDA-event brackets of 20 back-to-back launches of the frame's smot_xcorr call, right after the timed "

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SMOT_ABI_VERSION 3
+#define SMOT_ABI_VERSION 4
 
 enum { SMOT_OK = 0, SMOT_ERR_INVALID = 1, SMOT_ERR_CUDA = 2, SMOT_ERR_UNSUPPORTED = 3 };
 enum { SMOT_F32 = 0, SMOT_F16 = 1 };
@@ -168,6 +168,20 @@ int smot_track_combine(const float* det_boxes, const float* det_scores, int ncap
  * smot_xcorr: depthwise valid cross-correlation (xcorr.py:37-45), NHWC:
  *   out[n][i][j][c] = sum_{u,v<T} x[n][i+u][j+v][c] * k[n][u][v][c],  x: SxS, k: TxT, out: (S-T+1)^2. */
 int smot_xcorr(const void* x, const void* k, void* out, int n, int channels, int S, int T, int dtype, void* stream);
+
+/* smot_roi_align_planar + smot_xcorr_planar: the same two operations with the search windows exchanged CHANNEL-PLANAR
+ * (fp16 correlation, S = 30, T = 15 only): window element (roi r, channel c, row i, column j) lives at
+ *   x_planar[(r * channels + c) * SMOT_XCORR_PLANE + i * SMOT_XCORR_ROW_PITCH + j]
+ * and columns 30 / 31 of every row must be zero (smot_roi_align_planar never writes them: zero-fill the buffer once).
+ * smot_roi_align_planar has smot_roi_align's semantics and arithmetic for any res <= 32 / row_pitch / plane_pitch and
+ * both dtypes; smot_xcorr_planar produces exactly smot_xcorr's fp16 output ([n][16][16][channels], NHWC) from planar
+ * windows and NHWC templates.  channels % 16 == 0.  Both honour programmatic dependent launch (SMOT_PDL). */
+#define SMOT_XCORR_ROW_PITCH 40
+#define SMOT_XCORR_PLANE 1208
+int smot_roi_align_planar(const smot_pyramid* pyr, const float* rois, const float* level_boxes, const int* count,
+                          int max_rois, int channels, int res, int sampling_ratio, void* out, int row_pitch,
+                          int plane_pitch, int dtype, void* stream);
+int smot_xcorr_planar(const void* x_planar, const void* k, void* out, int n, int channels, void* stream);
 
 /* smot_emm_decode: fused bicubic x`up` upsampling (track_core.py:69-71) + get_locations (:184-225) +
  * decode_response (:101-135) + clip/validity of wrap_results_to_boxlist (:165-181).

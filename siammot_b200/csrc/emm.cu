@@ -212,6 +212,163 @@ __global__ void __launch_bounds__(XM_WARPS * 32) xcorr_mma_kernel(const __half* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Planar-input form of the tensor-core correlation (developer switch SMOT_XCORR_PLANAR).
+//
+// ncu on xcorr_mma_kernel (profiles/ncu_xcorr_mma_r01_v12_raw.csv) puts the time in the window staging, not in the MMAs:
+// 21.6 k global load requests touching 25 sectors each (a warp gathers 30 x 16 B at a 256-byte stride; every sector is
+// requested twice), long-scoreboard + LSU-throttle stalls on 60 % of the issue slots, tensor pipe at 17 % of its rate.
+// Here the search windows arrive CHANNEL-PLANAR from smot_roi_align_planar -- per (track, channel) a plane of
+// XM_CSTRIDE halves with rows XM_PITCH apart, i.e. exactly the shared-memory image the MMA phase reads -- so the window
+// staging of a CTA is four bulk async copies (cp.async.bulk, 38 656 B, complete_tx on one mbarrier) issued by a
+// dedicated warp: no per-thread loads, no transposing stores, full-line L2 reads.  Columns 30 / 31 of every window row
+// are zero in the producer's buffer (they meet structurally-zero B rows, but 0 x NaN must not happen).
+//
+// Programmatic dependent launch: everything that does not depend on the predecessor -- barrier init, zero fill and
+// staging of the templates (written to HBM before the predecessor even started) -- runs before griddepcontrol.wait and
+// overlaps the tail of the ROIAlign; the copy warp waits, then issues the bulk copies.  The MMA phase and the result
+// path are those of xcorr_mma_kernel, instruction for instruction, so the outputs are bit-identical.
+// ---------------------------------------------------------------------------------------------
+constexpr int XP_THREADS = (XM_WARPS + 1) * 32;                 // 16 MMA warps + 1 copy warp
+constexpr int XP_BAR_OFF = XM_SMEM;                             // mbarrier behind the two staging areas
+constexpr int XP_SMEM = XM_SMEM + 16;
+constexpr int XP_COPIES = 4;                                    // bulk copies per CTA (4 channel planes each)
+static_assert(XM_SMEM % 8 == 0, "mbarrier alignment");
+static_assert(XM_CG % XP_COPIES == 0 && ((XM_CG / XP_COPIES) * XM_CSTRIDE * 2) % 16 == 0, "bulk copy size must be a 16-byte multiple");
+
+__device__ __forceinline__ void xp_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void xp_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool xp_mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void xp_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(XP_THREADS) xcorr_planar_kernel(const __half* __restrict__ xp, const __half* __restrict__ k,
+                                                                  __half* __restrict__ out, int C) {
+  constexpr int S = 30, TT = 15, O = 16;
+  constexpr int KSTEPS = (TT * 2 + XM_WARPS - 1) / XM_WARPS;   // (template row, channel half) pairs per warp
+  static_assert(S * XM_PITCH + 8 == XM_CSTRIDE, "plane = 30 rows of XM_PITCH halves + 8");
+  extern __shared__ __align__(128) unsigned char xp_raw[];
+  __half* xT = reinterpret_cast<__half*>(xp_raw);     // [CG][CSTRIDE]: filled by the bulk copies
+  __half* kz = xT + XM_CG * XM_CSTRIDE;             // [CG][TT][2][KROW]
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(xp_raw + XP_BAR_OFF);
+  const int n = blockIdx.y, c0 = blockIdx.x * XM_CG;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool copy_warp = warp == XM_WARPS;
+  pdl_launch_dependents();
+  // ---- prologue (independent of the predecessor's output)
+  const __half* kb = k + (size_t)n * TT * TT * C + c0;
+  uint4 kv[KSTEPS];
+  if (!copy_warp) {
+#pragma unroll
+    for (int it = 0; it < KSTEPS; ++it) {
+      const int idx = it * XM_WARPS + warp, u = idx >> 1, q = idx & 1;
+      if (idx < TT * 2 && lane < TT) kv[it] = *reinterpret_cast<const uint4*>(kb + (size_t)(u * TT + lane) * C + q * 8);
+    }
+    uint4* kz4 = reinterpret_cast<uint4*>(kz);
+    for (int i = tid; i < XM_CG * XM_KPLANE / 8; i += XM_WARPS * 32) kz4[i] = make_uint4(0u, 0u, 0u, 0u);
+  } else if (lane == 0) {
+    xp_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();  // template zero fill complete; the mbarrier is initialised for every thread
+  if (copy_warp) {
+    // ---- window: wait for the producer of the planes, then 4 bulk copies onto one mbarrier
+    pdl_wait();
+    if (lane == 0) {
+      constexpr uint32_t BYTES = (XM_CG / XP_COPIES) * XM_CSTRIDE * 2;
+      const __half* src = xp + ((size_t)n * C + c0) * XM_CSTRIDE;
+      xp_mbar_expect_tx(bar, BYTES * XP_COPIES);
+#pragma unroll
+      for (int i = 0; i < XP_COPIES; ++i)
+        xp_bulk_g2s((uint32_t)__cvta_generic_to_shared(xT) + i * BYTES, reinterpret_cast<const unsigned char*>(src) + (size_t)i * BYTES,
+                    BYTES, bar);
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < KSTEPS; ++it) {
+      const int idx = it * XM_WARPS + warp, u = idx >> 1, q = idx & 1;
+      if (idx < TT * 2 && lane < TT) {
+        const __half* h = reinterpret_cast<const __half*>(&kv[it]);
+        __half* dst = kz + (q * 8) * XM_KPLANE + u * 2 * XM_KROW + 8 + lane;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          dst[e * XM_KPLANE] = h[e];                  // copy 0: K[u][v] at half 8 + v
+          dst[e * XM_KPLANE + XM_KROW - 1] = h[e];    // copy 1: K[u][v] at half 7 + v
+        }
+      }
+    }
+    pdl_wait();  // the result stores below must not pass the predecessor either (back-to-back launches share `out`)
+  }
+  __syncthreads();  // templates staged
+  float acc[2][4];
+  const int g = lane >> 2, t = lane & 3;
+  const int c = warp;
+  if (!copy_warp) {
+    // bounded wait for the windows: a mis-programmed copy must fail the launch, never hang the GPU
+    for (uint32_t spin = 0; !xp_mbar_try_wait(bar, 0); ++spin) {
+      if (spin > (1u << 24)) {
+        printf("smot xcorr_planar: bulk copy wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, tid);
+        __trap();
+      }
+    }
+    // ---- MMA phase: warp = channel (identical to xcorr_mma_kernel)
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
+    const int par = g & 1;
+    const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(xT + c * XM_CSTRIDE + a_row * XM_PITCH + a_kh * 8);
+    const uint32_t* kzw = reinterpret_cast<const uint32_t*>(kz + c * XM_KPLANE + par * XM_KROW) + ((8 + 2 * t - g - par) >> 1);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll 5
+    for (int u = 0; u < TT; ++u) {
+      const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
+      uint32_t af[4];
+      xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2), af[0], af[1], af[2], af[3]);
+      xm_mma(acc[0], af, k0, k8);
+      xm_mma(acc[1], af, 0u, k0);
+      xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2 + 32), af[0], af[1], af[2], af[3]);
+      xm_mma(acc[0], af, k16, 0u);
+      xm_mma(acc[1], af, k8, k16);
+    }
+    // ---- D fragments -> the warp's own (now dead) window plane as [O*O] halves
+    __syncwarp();
+    __half2* ost = reinterpret_cast<__half2*>(xT + c * XM_CSTRIDE);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      ost[g * 8 + nt * 4 + t] = __floats2half2_rn(acc[nt][0], acc[nt][1]);
+      ost[(g + 8) * 8 + nt * 4 + t] = __floats2half2_rn(acc[nt][2], acc[nt][3]);
+    }
+  }
+  __syncthreads();
+  if (!copy_warp) {
+    const int q = warp & 1, pos = (warp >> 1) * 32 + lane;   // 256 positions x 2 channel halves = 512 threads
+    const __half* src = xT + (q * 8) * XM_CSTRIDE + pos;
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = src[e * XM_CSTRIDE];
+    *reinterpret_cast<uint4*>(out + ((size_t)n * O * O + pos) * C + c0 + q * 8) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
 // generic fallback for unusual geometries: one thread per output element
 template <typename T>
 __global__ void xcorr_generic_kernel(const T* __restrict__ x, const T* __restrict__ k, T* __restrict__ out, int n, int C,
@@ -443,6 +600,24 @@ extern "C" int smot_xcorr(const void* x, const void* k, void* out, int n, int ch
   else
     xcorr_generic_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, (const __half*)k, (__half*)out, n, channels, S, T);
   SMOT_CHECK_LAUNCH("smot_xcorr(generic)");
+  return SMOT_OK;
+}
+
+extern "C" int smot_xcorr_planar(const void* x_planar, const void* k, void* out, int n, int channels, void* stream) {
+  SMOT_CHECK_ARG(n >= 0 && channels > 0 && channels % XM_CG == 0, "smot_xcorr_planar: bad geometry n=%d C=%d (C must be a multiple of %d)",
+                 n, channels, XM_CG);
+  if (n == 0) return SMOT_OK;
+  SMOT_CHECK_ARG(x_planar && k && out, "smot_xcorr_planar: null argument");
+  SMOT_CHECK_ARG((((uintptr_t)x_planar | (uintptr_t)k | (uintptr_t)out) & 15) == 0, "smot_xcorr_planar: operands must be 16-byte aligned");
+  static_assert(XM_CSTRIDE == SMOT_XCORR_PLANE && XM_PITCH == SMOT_XCORR_ROW_PITCH, "smot.h states the plane layout");
+  SMOT_ENSURE_SMEM(xcorr_planar_kernel, XP_SMEM, "smot_xcorr_planar");
+  cudaError_t e = launch_pdl(xcorr_planar_kernel, dim3(channels / XM_CG, n), dim3(XP_THREADS), XP_SMEM, (cudaStream_t)stream,
+                             (const __half*)x_planar, (const __half*)k, (__half*)out, channels);
+  if (e != cudaSuccess) {
+    set_error("smot_xcorr_planar: launch failed: %s", cudaGetErrorString(e));
+    return SMOT_ERR_CUDA;
+  }
+  SMOT_CHECK_LAUNCH("smot_xcorr_planar");
   return SMOT_OK;
 }
 

@@ -88,9 +88,138 @@ __global__ void roi_align_kernel(const RoiArgs a, T* __restrict__ out) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Channel-planar variant: out[(roi * C + c) * plane_pitch + ph * row_pitch + pw].
+//
+// Producer side of smot_xcorr_planar: the EMM correlation runs per (track, channel) on the tensor cores with the window
+// COLUMN as the contraction index, i.e. it wants every channel's res x res window as a dense 2-D plane.  Writing the
+// search windows in that layout here (row pitch 40 halves, plane 1208 halves = exactly the shared-memory image the MMA
+// phase reads) turns the consumer's staging -- 16-byte gathers at a 256-byte stride and 2-byte transposing stores --
+// into one bulk copy per CTA.  The columns res .. row_pitch-1 are never written: the caller zero-fills the buffer once.
+//
+// grid (res rows, rois): a CTA produces one window row for all channels.  Its 8 warps compute the row's bins with the
+// same arithmetic (operation for operation) as roi_align_kernel -- lanes own 4 channels, corner reads are contiguous
+// 8/16-byte-per-lane loads -- and park the values in a shared-memory tile [C][res]; the tile is then written out as one
+// contiguous run per channel.  (The bin arithmetic is restated rather than shared with roi_align_kernel so that the
+// validated kernel stays byte-identical; unify once this variant has been through the GPU tests.)
+// ---------------------------------------------------------------------------------------------
+constexpr int RAP_TP = 33;  // tile pitch in elements: odd -> the 4-channels-per-lane stores are at most 2-way conflicted
+
+template <typename T>
+__global__ void __launch_bounds__(256) roi_align_planar_kernel(const RoiArgs a, T* __restrict__ out, int row_pitch,
+                                                               int plane_pitch) {
+  extern __shared__ __align__(16) unsigned char rap_raw[];
+  T* tile = reinterpret_cast<T*>(rap_raw);  // [channels][RAP_TP]
+  pdl_launch_dependents();                  // the correlation kernel may start its (input-independent) prologue now
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ph = blockIdx.x, r = blockIdx.y;
+  const int n = a.count ? min(*a.count, a.max_rois) : a.max_rois;
+  T* dst = out + (size_t)r * a.channels * plane_pitch + (size_t)ph * row_pitch;
+  if (r >= n) {  // rows past the count are zero, as in roi_align_kernel
+    for (int i = threadIdx.x; i < a.channels * a.res; i += blockDim.x) {
+      const int c = i / a.res, pw = i - c * a.res;
+      dst[(size_t)c * plane_pitch + pw] = from_f<T>(0.f);
+    }
+    return;
+  }
+  const float* lb = (a.level_boxes ? a.level_boxes : a.rois) + 4 * r;
+  const float area = (lb[2] - lb[0] + 1.f) * (lb[3] - lb[1] + 1.f);
+  float lv = floorf(4.f + log2f(__fdiv_rn(__fsqrt_rn(area), 224.f) + 1e-6f));
+  const float kmin = (float)a.pyr.k_min, kmax = (float)(a.pyr.k_min + a.pyr.num_levels - 1);
+  lv = fminf(fmaxf(lv, kmin), kmax);
+  const int l = (int)lv - a.pyr.k_min;
+
+  const T* __restrict__ feat = reinterpret_cast<const T*>(a.pyr.feat[l]);
+  const int H = a.pyr.H[l], W = a.pyr.W[l], ld = a.pyr.ld[l], pad = a.pyr.pad[l];
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const float sc = a.pyr.scale[l];
+  const float* roi = a.rois + 4 * r;
+  const float x1 = roi[0] * sc, y1 = roi[1] * sc, x2 = roi[2] * sc, y2 = roi[3] * sc;
+  const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
+  const float bin_h = __fdiv_rn(rh, (float)a.res), bin_w = __fdiv_rn(rw, (float)a.res);
+  const int gh = a.sampling > 0 ? a.sampling : (int)ceilf(__fdiv_rn(rh, (float)a.res));
+  const int gw = a.sampling > 0 ? a.sampling : (int)ceilf(__fdiv_rn(rw, (float)a.res));
+  const float cnt = (float)(gh * gw);
+
+  for (int pw = wid; pw < a.res; pw += 8) {
+    for (int c = lane * 4; c < a.channels; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int iy = 0; iy < gh; ++iy) {
+        float y = y1 + (float)ph * bin_h + __fdiv_rn(((float)iy + .5f) * bin_h, (float)gh);
+        for (int ix = 0; ix < gw; ++ix) {
+          float x = x1 + (float)pw * bin_w + __fdiv_rn(((float)ix + .5f) * bin_w, (float)gw);
+          if (y < -1.f || y > (float)Hp || x < -1.f || x > (float)Wp) continue;
+          float yy = y <= 0.f ? 0.f : y, xx = x <= 0.f ? 0.f : x;
+          int yl = (int)yy, xl = (int)xx, yh, xh;
+          if (yl >= Hp - 1) { yh = yl = Hp - 1; yy = (float)yl; } else yh = yl + 1;
+          if (xl >= Wp - 1) { xh = xl = Wp - 1; xx = (float)xl; } else xh = xl + 1;
+          const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+          const int ryl = yl - pad, ryh = yh - pad, rxl = xl - pad, rxh = xh - pad;
+          const bool oyl = ryl >= 0 && ryl < H, oyh = ryh >= 0 && ryh < H;
+          const bool oxl = rxl >= 0 && rxl < W, oxh = rxh >= 0 && rxh < W;
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 v1 = (oyl && oxl) ? ld4(feat + ((size_t)ryl * W + rxl) * ld + c) : z;
+          float4 v2 = (oyl && oxh) ? ld4(feat + ((size_t)ryl * W + rxh) * ld + c) : z;
+          float4 v3 = (oyh && oxl) ? ld4(feat + ((size_t)ryh * W + rxl) * ld + c) : z;
+          float4 v4 = (oyh && oxh) ? ld4(feat + ((size_t)ryh * W + rxh) * ld + c) : z;
+          acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+          acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+          acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+          acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+        }
+      }
+      T* tp = tile + (size_t)c * RAP_TP + pw;
+      tp[0] = from_f<T>(__fdiv_rn(acc.x, cnt));
+      tp[RAP_TP] = from_f<T>(__fdiv_rn(acc.y, cnt));
+      tp[2 * RAP_TP] = from_f<T>(__fdiv_rn(acc.z, cnt));
+      tp[3 * RAP_TP] = from_f<T>(__fdiv_rn(acc.w, cnt));
+    }
+  }
+  __syncthreads();
+  // one contiguous run of `res` elements per channel
+  for (int i = threadIdx.x; i < a.channels * a.res; i += blockDim.x) {
+    const int c = i / a.res, pw = i - c * a.res;
+    dst[(size_t)c * plane_pitch + pw] = tile[(size_t)c * RAP_TP + pw];
+  }
+}
+
 }  // namespace smot
 
 using namespace smot;
+
+extern "C" int smot_roi_align_planar(const smot_pyramid* pyr, const float* rois, const float* level_boxes, const int* count,
+                                     int max_rois, int channels, int res, int sampling_ratio, void* out, int row_pitch,
+                                     int plane_pitch, int dtype, void* stream) {
+  SMOT_CHECK_ARG(pyr && out && (rois || max_rois == 0), "smot_roi_align_planar: null argument");
+  SMOT_CHECK_ARG(pyr->num_levels >= 1 && pyr->num_levels <= SMOT_MAX_LEVELS, "smot_roi_align_planar: num_levels %d", pyr->num_levels);
+  SMOT_CHECK_ARG(channels > 0 && channels % 4 == 0 && res > 0 && res < RAP_TP && max_rois >= 0,
+                 "smot_roi_align_planar: channels must be a multiple of 4 and res <= %d", RAP_TP - 1);
+  SMOT_CHECK_ARG(row_pitch >= res && (long long)plane_pitch >= (long long)(res - 1) * row_pitch + res,
+                 "smot_roi_align_planar: pitches %d / %d too small for res %d", row_pitch, plane_pitch, res);
+  for (int l = 0; l < pyr->num_levels; ++l)
+    SMOT_CHECK_ARG(pyr->feat[l] && pyr->ld[l] % 4 == 0 && pyr->H[l] > 0 && pyr->W[l] > 0 && pyr->pad[l] >= 0,
+                   "smot_roi_align_planar: bad level %d", l);
+  if (max_rois == 0) return SMOT_OK;
+  RoiArgs a;
+  a.pyr = *pyr, a.rois = rois, a.level_boxes = level_boxes, a.count = count;
+  a.max_rois = max_rois, a.channels = channels, a.res = res, a.sampling = sampling_ratio;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid((unsigned)res, (unsigned)max_rois);
+  if (dtype == SMOT_F32) {
+    const size_t smem = (size_t)channels * RAP_TP * sizeof(float);
+    SMOT_ENSURE_SMEM(roi_align_planar_kernel<float>, smem, "smot_roi_align_planar");
+    roi_align_planar_kernel<float><<<grid, 256, smem, st>>>(a, (float*)out, row_pitch, plane_pitch);
+  } else if (dtype == SMOT_F16) {
+    const size_t smem = (size_t)channels * RAP_TP * sizeof(__half);
+    SMOT_ENSURE_SMEM(roi_align_planar_kernel<__half>, smem, "smot_roi_align_planar");
+    roi_align_planar_kernel<__half><<<grid, 256, smem, st>>>(a, (__half*)out, row_pitch, plane_pitch);
+  } else {
+    SMOT_CHECK_ARG(false, "smot_roi_align_planar: bad dtype %d", dtype);
+  }
+  SMOT_CHECK_LAUNCH("smot_roi_align_planar");
+  return SMOT_OK;
+}
 
 extern "C" int smot_roi_align(const smot_pyramid* pyr, const float* rois, const float* level_boxes, const int* count,
                               int max_rois, int channels, int res, int sampling_ratio, void* out, int dtype,

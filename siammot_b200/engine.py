@@ -21,6 +21,7 @@ a few single-element glue ops on tiny tensors.  No CPU fallback exists.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -150,6 +151,8 @@ class _TrackArena(object):
         self.cat_boxes = torch.zeros((tmax, 4), dtype=f32, device=dev)
         self.host = torch.zeros((1 + 7 * tmax + 1 + ncap,), dtype=f32).pin_memory()
         self.srf = torch.zeros((cap * S * S * Cc,), dtype=dt, device=dev)
+        # channel-planar search windows (developer switch SMOT_XCORR_PLANAR): zero-filled once, the pad columns stay zero
+        self.srp = torch.zeros((cap * Cc * _lib.XCORR_PLANE,), dtype=dt, device=dev) if eng.xcorr_planar_ok() else None
         self.tmpl = torch.zeros((cap * eng.t_res * eng.t_res * Cc,), dtype=dt, device=dev)   # the frame's templates (fixed address)
         self.resp = torch.zeros((cap * O * O * Cc,), dtype=dt, device=dev)
         self.tower = torch.zeros((cap * O * O * 2 * Cc,), dtype=dt, device=dev)
@@ -219,10 +222,22 @@ class _TrackPlan(object):
             self.tb, self.conf, self.valid, self.scratch = A.tb[:n], A.conf[:n], A.valid[:n], A.scratch[:n]
             pyr_pad = ops.make_pyramid(P.feats, T.POOLER_SCALES, eng.pads)
             self.keep.append(pyr_pad)
-            self.steps.append((L.smot_roi_align, (C.byref(pyr_pad), ops._ptr(self.sr), ops._ptr(self.boxes), None, n, Cc, S,
-                                                  T.POOLER_SAMPLING_RATIO, ops._ptr(self.srf), dc), "sr_roi_align"))
-            self.xcorr_slot = len(self.steps)
-            self.steps.append((L.smot_xcorr, (ops._ptr(self.srf), ops._ptr(self.tmpl), ops._ptr(self.resp), n, Cc, S, Tr, dc), "xcorr"))
+            self.xcorr_kernel = "xcorr_mma_kernel (smot_xcorr)" if dt == torch.float16 else "xcorr_kernel (smot_xcorr)"
+            if A.srp is not None:
+                # search windows exchanged channel-planar: the correlation stages them with bulk copies
+                self.srp = A.srp[:n * Cc * _lib.XCORR_PLANE].view(n, Cc, _lib.XCORR_PLANE)
+                self.steps.append((L.smot_roi_align_planar, (C.byref(pyr_pad), ops._ptr(self.sr), ops._ptr(self.boxes), None, n, Cc,
+                                                             S, T.POOLER_SAMPLING_RATIO, ops._ptr(self.srp), _lib.XCORR_ROW_PITCH,
+                                                             _lib.XCORR_PLANE, dc), "sr_roi_align"))
+                self.xcorr_slot = len(self.steps)
+                self.steps.append((L.smot_xcorr_planar, (ops._ptr(self.srp), ops._ptr(self.tmpl), ops._ptr(self.resp), n, Cc), "xcorr"))
+                self.xcorr_kernel = "xcorr_planar_kernel (smot_xcorr_planar)"
+            else:
+                self.steps.append((L.smot_roi_align, (C.byref(pyr_pad), ops._ptr(self.sr), ops._ptr(self.boxes), None, n, Cc, S,
+                                                      T.POOLER_SAMPLING_RATIO, ops._ptr(self.srf), dc), "sr_roi_align"))
+                self.xcorr_slot = len(self.steps)
+                self.steps.append((L.smot_xcorr, (ops._ptr(self.srf), ops._ptr(self.tmpl), ops._ptr(self.resp), n, Cc, S, Tr, dc),
+                                   "xcorr"))
             self._conv(self.resp, "emm.towers", self.tower, pad=1)
             self.steps.append((L.smot_groupnorm_relu, (ops._ptr(self.tower), ops._ptr(eng.gn_gamma), ops._ptr(eng.gn_beta), n,
                                                        O * O, 2 * Cc, 2 * Cc, 2 * cfg.MODEL.GROUP_NORM.NUM_GROUPS,
@@ -356,8 +371,16 @@ class Engine(object):
         self._branch_streams = []
         self._track_plans = {}
         self._arenas = {}
+        # developer switch: exchange the EMM search windows channel-planar (smot_roi_align_planar ->
+        # smot_xcorr_planar).  Off by default until it has been through the GPU tests.
+        self.xcorr_planar = os.environ.get("SMOT_XCORR_PLANAR", "0") == "1"
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
         self.time_kernels = False  # also bracket single kernels of the track stage (forces its eager path)
+
+    def xcorr_planar_ok(self):
+        """The planar exchange applies to the fp16 correlation at the TAO geometry (S = 30, T = 15) with C % 16 == 0."""
+        return (self.xcorr_planar and self.dtype == torch.float16 and self.s_res == 30 and self.t_res == 15
+                and self.C % 16 == 0)
 
     def timed(self, name):
         """Context manager: when self.timers is a dict, brackets the enclosed launches with CUDA events on
@@ -699,11 +722,18 @@ class Engine(object):
         cfg = self.cfg
         T = cfg.MODEL.TRACK_HEAD
         n = mem_boxes.shape[0]
-        with self.timed("sr_roi_align"):
-            srf = ops.roi_align(P.feats, mem_sr, T.POOLER_SCALES, self.s_res, T.POOLER_SAMPLING_RATIO,
-                                level_boxes=mem_boxes, pads=self.pads)
-        with self.timed("xcorr"):
-            resp = ops.xcorr(srf, mem_feat)
+        if self.xcorr_planar_ok():
+            with self.timed("sr_roi_align"):
+                srp = ops.roi_align_planar(P.feats, mem_sr, T.POOLER_SCALES, self.s_res, T.POOLER_SAMPLING_RATIO,
+                                           level_boxes=mem_boxes, pads=self.pads)
+            with self.timed("xcorr"):
+                resp = ops.xcorr_planar(srp, mem_feat.contiguous())
+        else:
+            with self.timed("sr_roi_align"):
+                srf = ops.roi_align(P.feats, mem_sr, T.POOLER_SCALES, self.s_res, T.POOLER_SAMPLING_RATIO,
+                                    level_boxes=mem_boxes, pads=self.pads)
+            with self.timed("xcorr"):
+                resp = ops.xcorr(srf, mem_feat)
         O, Cc = self.o_res, self.C
         w, _, _ = self.weights["emm.towers"]
         tower = ops.conv2d(resp, w, pad=1)

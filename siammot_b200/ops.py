@@ -244,6 +244,39 @@ def xcorr(x, k, out=None):
     return out
 
 
+def roi_align_planar(feats, rois, scales, res, sampling, level_boxes=None, pads=None, count=None, out=None, pyramid=None,
+                     row_pitch=_lib.XCORR_ROW_PITCH, plane_pitch=_lib.XCORR_PLANE):
+    """smot_roi_align with a channel-planar result: returns (n, C, plane_pitch) in the feature dtype; window element
+    (i, j) of channel c sits at [roi, c, i * row_pitch + j].  Elements outside the res x res windows are left as they are
+    (zeros when the buffer is allocated here)."""
+    _require_cuda(rois, level_boxes, count, *feats)
+    n = rois.shape[0]
+    Cc = feats[0].shape[3]
+    if out is None:
+        out = torch.zeros((n, Cc, plane_pitch), dtype=feats[0].dtype, device=feats[0].device)
+    if n == 0:
+        return out
+    p = pyramid or make_pyramid(feats, scales, pads)
+    assert rois.dtype == torch.float32 and rois.is_contiguous() and out.is_contiguous()
+    assert level_boxes is None or (level_boxes.dtype == torch.float32 and level_boxes.is_contiguous())
+    check(lib().smot_roi_align_planar(C.byref(p), _ptr(rois), _ptr(level_boxes), _ptr(count), n, Cc, res, sampling, _ptr(out),
+                                      row_pitch, plane_pitch, dtype_code(feats[0].dtype), stream_ptr()), "smot_roi_align_planar")
+    return out
+
+
+def xcorr_planar(x_planar, k, out=None):
+    """x_planar (n, C, XCORR_PLANE) fp16 channel-planar 30x30 windows (row pitch XCORR_ROW_PITCH, columns 30/31 zero),
+    k (n,15,15,C) NHWC fp16 -> (n,16,16,C) NHWC: the output of xcorr() on the same windows, bit for bit."""
+    _require_cuda(x_planar, k)
+    n, Cc, plane = x_planar.shape
+    assert plane == _lib.XCORR_PLANE and x_planar.dtype == torch.float16 and k.dtype == torch.float16
+    assert x_planar.is_contiguous() and k.is_contiguous() and tuple(k.shape) == (n, 15, 15, Cc)
+    if out is None:
+        out = torch.empty((n, 16, 16, Cc), dtype=torch.float16, device=k.device)
+    check(lib().smot_xcorr_planar(_ptr(x_planar), _ptr(k), _ptr(out), n, Cc, stream_ptr()), "smot_xcorr_planar")
+    return out
+
+
 def emm_decode(maps, sr, tboxes, hann, up, T, pad, use_centerness, sigma, img_w, img_h, amodal):
     """maps: fp32 (n,O,O,ld>=7).  Returns boxes (n,4), conf (n,), valid (n,) int32."""
     _require_cuda(maps, sr, tboxes, hann)
