@@ -36,21 +36,28 @@ N_FRAMES = 32                 # distinct frames resident in HBM: 32 x 10.8 MB = 
 METRIC = "tracker FPS @720p (DLA34-FPN+EMM, 30 tracks)"
 WORKLOAD = "720p synthetic clip -> 3x704x1280, DLA-34-FPN + EMM, 30 active tracks, 1 frame per step"
 CFG_OVERRIDES = []
+CFG_YAML = "dla34_emm.yaml"
 
 # BASELINE.json configs: the default (configs[1]) is what the metric is quoted on; the others are selectable for reporting
 WORKLOADS = {
-    "720p30": dict(src=(720, 1280), net=(704, 1280), tracks=30, opts=[],
+    "720p30": dict(src=(720, 1280), net=(704, 1280), tracks=30, opts=[], yaml="dla34_emm.yaml",
                    metric=METRIC, text=WORKLOAD),
+    # configs[4]: the same clip on the upstream R-50-FPN body (256-channel FPN / RPN / box head / EMM)
+    "r50_720p30": dict(src=(720, 1280), net=(704, 1280), tracks=30, opts=[], yaml="r50_emm.yaml",
+                       metric="tracker FPS @720p (R50-FPN+EMM, 30 tracks)",
+                       text="720p synthetic clip -> 3x704x1280, R-50-FPN + EMM (256 channels), 30 active tracks, 1 frame per step"),
     # configs[2]: native 1080p input (INPUT.MIN/MAX_SIZE_TEST 1080/1920 -> 3x1056x1920), 80 tracks
     "1080p80": dict(src=(1080, 1920), net=(1056, 1920), tracks=80, opts=["INPUT.MIN_SIZE_TEST", 1080, "INPUT.MAX_SIZE_TEST", 1920],
+                    yaml="dla34_emm.yaml",
                     metric="tracker FPS @1080p (DLA34-FPN+EMM, 80 tracks)",
                     text="1080p synthetic clip -> 3x1056x1920, DLA-34-FPN + EMM (search region r=2), 80 active tracks, 1 frame per step"),
 }
 
 
 def select_workload(name):
-    global H_NET, W_NET, H_SRC, W_SRC, N_TRACKS, METRIC, WORKLOAD, CFG_OVERRIDES
+    global H_NET, W_NET, H_SRC, W_SRC, N_TRACKS, METRIC, WORKLOAD, CFG_OVERRIDES, CFG_YAML
     w = WORKLOADS[name]
+    CFG_YAML = w["yaml"]
     (H_SRC, W_SRC), (H_NET, W_NET), N_TRACKS = w["src"], w["net"], w["tracks"]
     METRIC, WORKLOAD, CFG_OVERRIDES = w["metric"], w["text"], w["opts"]
 
@@ -58,7 +65,7 @@ def select_workload(name):
 def build_cfg(dtype):
     from siammot_b200.config import get_cfg
     cfg = get_cfg()
-    cfg.merge_from_file(os.path.join(REPO, "siammot_b200", "configs", "dla34_emm.yaml"))
+    cfg.merge_from_file(os.path.join(REPO, "siammot_b200", "configs", CFG_YAML))
     if CFG_OVERRIDES:
         cfg.merge_from_list(list(CFG_OVERRIDES))
     cfg.DTYPE = dtype
@@ -453,7 +460,8 @@ def main():
     ap.add_argument("--dtype", default="float16", choices=["float16", "float32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="720p30", choices=sorted(WORKLOADS),
-                    help="720p30 = BASELINE.json configs[1] (the metric's configuration, default); 1080p80 = configs[2]")
+                    help="720p30 = BASELINE.json configs[1] (the metric's configuration, default); 1080p80 = configs[2]; "
+                         "r50_720p30 = configs[4]")
     args = ap.parse_args()
     select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

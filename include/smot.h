@@ -87,6 +87,10 @@ int smot_image_to_nhwc(const float* chw, void* out, int C, int H, int W, int out
 /* nn.MaxPool2d(2,2) of DlaTree.downsample (dla.py:216,227). out is (H/2)x(W/2). */
 int smot_maxpool2x2(const void* in, void* out, int batch, int H, int W, int C, int in_ld, int out_ld, int dtype,
                     void* stream);
+/* F.max_pool2d(x, kernel_size=3, stride=2, padding=1) of the ResNet stem (upstream maskrcnn_benchmark
+ * modeling/backbone/resnet.py BaseStem.forward; the "R-50-FPN" body).  out is ((H-1)/2+1) x ((W-1)/2+1). */
+int smot_maxpool3x3s2(const void* in, void* out, int batch, int H, int W, int C, int in_ld, int out_ld, int dtype,
+                      void* stream);
 /* lateral += bilinear_resize(top -> HxW, align_corners=False)   (fpn_patch.py:49-51). */
 int smot_upsample_add(const void* top, int Ht, int Wt, int top_ld, void* lateral, int H, int W, int lat_ld, int C,
                       int dtype, void* stream);

@@ -85,6 +85,32 @@ def dla34_forward(P, x, pre="backbone.body"):
     return [x2, x3, x4, x5]
 
 
+R50_BLOCKS = (3, 4, 6, 3)
+
+
+def resnet50_forward(P, x, pre="backbone.body", stride_in_1x1=True):
+    """Upstream maskrcnn_benchmark ResNet.forward for "R-50-FPN" (modeling/backbone/resnet.py; un-vendored, restated):
+    stem = 7x7/2 conv + FrozenBN + ReLU + 3x3/2 max-pool (pad 1); four stages of bottleneck blocks
+    1x1 (stride here when STRIDE_IN_1X1) -> 3x3 -> 1x1, FrozenBN after each, ReLU after the first two and after the
+    residual add; the first block of a stage projects the identity with a strided 1x1 + FrozenBN.  Returns C2..C5."""
+    x = _conv_bn(P, x, pre + ".stem.conv1", pre + ".stem.bn1", 2, 3, relu=True)
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    outs = []
+    for li, nb in enumerate(R50_BLOCKS):
+        for b in range(nb):
+            blk = "%s.layer%d.%d" % (pre, li + 1, b)
+            stride = 2 if (b == 0 and li > 0) else 1
+            s1, s3 = (stride, 1) if stride_in_1x1 else (1, stride)
+            identity = x
+            if (blk + ".downsample.0.weight") in P:
+                identity = _conv_bn(P, x, blk + ".downsample.0", blk + ".downsample.1", stride, 0)
+            y = _conv_bn(P, x, blk + ".conv1", blk + ".bn1", s1, 0, relu=True)
+            y = _conv_bn(P, y, blk + ".conv2", blk + ".bn2", s3, 1, relu=True)
+            x = _conv_bn(P, y, blk + ".conv3", blk + ".bn3", 1, 0, relu=True, residual=identity)
+        outs.append(x)
+    return outs
+
+
 def fpn_forward(P, feats, pre="backbone.fpn"):
     """Patched FPN.forward (fpn_patch.py:29-61): bilinear resize-to-lateral-size top-down,
     LastLevelMaxPool = stride-2 subsample for P6."""
@@ -451,6 +477,11 @@ class OracleSiamMOT(object):
     def features(self, image):
         if image.dim() == 3:
             image = image[None]
+        body = self.cfg.MODEL.BACKBONE.CONV_BODY
+        if body == "R-50-FPN":
+            return fpn_forward(self.P, resnet50_forward(self.P, image.to(torch.float32),
+                                                        stride_in_1x1=self.cfg.MODEL.RESNETS.STRIDE_IN_1X1))
+        assert body == "DLA-34-FPN", body
         return fpn_forward(self.P, dla34_forward(self.P, image.to(torch.float32)))
 
     @torch.no_grad()

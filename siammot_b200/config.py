@@ -102,7 +102,10 @@ _DEFAULTS = {
         "BACKBONE": {"CONV_BODY": "DLA-34-FPN", "FREEZE_CONV_BODY_AT": 2},
         "FPN": {"USE_GN": False, "USE_RELU": False},
         "GROUP_NORM": {"DIM_PER_GP": -1, "NUM_GROUPS": 32, "EPSILON": 1e-5},
-        "RESNETS": {"BACKBONE_OUT_CHANNELS": 1024},
+        # upstream maskrcnn_benchmark defaults (the "R-50-FPN" body of BASELINE.json configs[4])
+        "RESNETS": {"NUM_GROUPS": 1, "WIDTH_PER_GROUP": 64, "STRIDE_IN_1X1": True, "TRANS_FUNC": "BottleneckWithFixedBatchNorm",
+                    "STEM_FUNC": "StemWithFixedBatchNorm", "RES5_DILATION": 1, "BACKBONE_OUT_CHANNELS": 1024,
+                    "RES2_OUT_CHANNELS": 256, "STEM_OUT_CHANNELS": 64, "STAGE_WITH_DCN": (False, False, False, False)},
         "DLA": {"DLA_STAGE2_OUT_CHANNELS": 64, "DLA_STAGE3_OUT_CHANNELS": 128, "DLA_STAGE4_OUT_CHANNELS": 256,
                 "DLA_STAGE5_OUT_CHANNELS": 512, "BACKBONE_OUT_CHANNELS": 128,
                 "STAGE_WITH_DCN": (False, False, False, False, False, False)},

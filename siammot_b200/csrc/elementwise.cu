@@ -60,6 +60,35 @@ __global__ void maxpool2x2_h8_kernel(const __half* __restrict__ in, __half* __re
   *reinterpret_cast<uint4*>(out + pix * out_ld + c) = r;
 }
 
+// ---- max_pool2d(kernel 3, stride 2, padding 1): the ResNet stem pool (upstream resnet.py BaseStem.forward) --------
+// Padding is "-inf" (taps outside the map do not take part), OH = (H - 1) / 2 + 1.  One thread = 4 channels of one
+// output pixel; the max of storage-type values is exact, so fp16 maps go through float only as a container.
+template <typename T>
+__global__ void maxpool3x3s2_kernel(const T* __restrict__ in, T* __restrict__ out, int batch, int H, int W, int C,
+                                    int in_ld, int out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1, C4 = C / 4;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)batch * OH * OW * C4) return;
+  const int c = (int)(idx % C4) * 4;
+  const size_t pix = idx / C4;
+  const int ow = (int)(pix % OW), oh = (int)((pix / OW) % OH), n = (int)(pix / ((size_t)OW * OH));
+  const float ninf = -__int_as_float(0x7f800000);
+  float4 r = make_float4(ninf, ninf, ninf, ninf);
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int y = 2 * oh + dy;
+    if (y < 0 || y >= H) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int x = 2 * ow + dx;
+      if (x < 0 || x >= W) continue;
+      const float4 v = ld4(in + (((size_t)n * H + y) * W + x) * in_ld + c);
+      r.x = fmaxf(r.x, v.x), r.y = fmaxf(r.y, v.y), r.z = fmaxf(r.z, v.z), r.w = fmaxf(r.w, v.w);
+    }
+  }
+  st4(out + pix * out_ld + c, r);
+}
+
 // ---- lateral += bilinear(top), align_corners=False (ATen upsample_bilinear2d index rule) -----
 template <typename T>
 __global__ void upsample_add_kernel(const T* __restrict__ top, int Ht, int Wt, int top_ld, T* __restrict__ lat, int H,
@@ -289,6 +318,22 @@ extern "C" int smot_maxpool2x2(const void* in, void* out, int batch, int H, int 
   else
     SMOT_CHECK_ARG(false, "smot_maxpool2x2: bad dtype %d", dtype);
   SMOT_CHECK_LAUNCH("smot_maxpool2x2");
+  return SMOT_OK;
+}
+
+extern "C" int smot_maxpool3x3s2(const void* in, void* out, int batch, int H, int W, int C, int in_ld, int out_ld,
+                                 int dtype, void* stream) {
+  SMOT_CHECK_ARG(in && out && batch > 0 && H >= 1 && W >= 1 && C > 0 && C % 4 == 0 && in_ld % 4 == 0 && out_ld % 4 == 0,
+                 "smot_maxpool3x3s2: bad arguments (C, in_ld, out_ld must be multiples of 4)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)batch * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / 4);
+  if (dtype == SMOT_F32)
+    launch_pdl(maxpool3x3s2_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const float*)in, (float*)out, batch, H, W, C, in_ld, out_ld);
+  else if (dtype == SMOT_F16)
+    launch_pdl(maxpool3x3s2_kernel<__half>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const __half*)in, (__half*)out, batch, H, W, C, in_ld, out_ld);
+  else
+    SMOT_CHECK_ARG(false, "smot_maxpool3x3s2: bad dtype %d", dtype);
+  SMOT_CHECK_LAUNCH("smot_maxpool3x3s2");
   return SMOT_OK;
 }
 

@@ -344,10 +344,18 @@ class Engine(object):
         self.use_graph = use_graph
         self.weights = {}
         self.plans = {}
-        self.C = cfg.MODEL.DLA.BACKBONE_OUT_CHANNELS
+        from .synthetic import backbone_channels, is_resnet
+        if cfg.MODEL.BACKBONE.CONV_BODY not in ("DLA-34-FPN", "R-50-FPN"):
+            raise NotImplementedError("body %s: DLA-34-FPN (SURVEY.md section 8) and R-50-FPN (BASELINE.json configs[4]) are "
+                                      "implemented" % cfg.MODEL.BACKBONE.CONV_BODY)
+        self.resnet = is_resnet(cfg)
+        if self.resnet:
+            R = cfg.MODEL.RESNETS
+            if (R.NUM_GROUPS != 1 or R.RES5_DILATION != 1 or any(R.STAGE_WITH_DCN) or R.STEM_FUNC != "StemWithFixedBatchNorm"
+                    or R.TRANS_FUNC != "BottleneckWithFixedBatchNorm"):
+                raise NotImplementedError("R-50-FPN: only the plain FrozenBN bottleneck body (no groups / dilation / DCN)")
+        self.C = backbone_channels(cfg)[1]
         self.ncls = cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES
-        if cfg.MODEL.BACKBONE.CONV_BODY != "DLA-34-FPN":
-            raise NotImplementedError("only the DLA-34-FPN body is implemented (SURVEY.md section 8)")
         if cfg.MODEL.CLS_AGNOSTIC_BBOX_REG:
             raise NotImplementedError("CLS_AGNOSTIC_BBOX_REG")
         R = cfg.MODEL.RPN
@@ -421,7 +429,7 @@ class Engine(object):
                 conv = k[:-len(".weight")]
                 leaf = conv.rsplit(".", 1)[1]
                 parent = conv.rsplit(".", 1)[0]
-                if leaf in ("conv1", "conv2"):
+                if leaf in ("conv1", "conv2", "conv3"):
                     bnn = parent + ".bn" + leaf[-1]
                 elif leaf == "conv":
                     bnn = parent + ".bn"
@@ -511,6 +519,48 @@ class Engine(object):
         self._tree(P, name + ".tree1", x, 1, cin, cout, stride, False, out=t1)
         return self._tree(P, name + ".tree2", t1, 1, cout, cout, 1, False, out=out, rootbuf=rootbuf)
 
+    def _resnet_body(self, P, img):
+        """Upstream maskrcnn_benchmark ResNet-50 (modeling/backbone/resnet.py, "R-50-FPN") as launches: stem 7x7/2 + FrozenBN +
+        ReLU, 3x3/2 max-pool, four stages of bottleneck blocks (1x1 -> 3x3 -> 1x1, FrozenBN / ReLU / residual in the conv
+        epilogues).  With STRIDE_IN_1X1 the strided 1x1 convs of a stage's first block (conv1 and the identity projection) read
+        only the even pixels: the input is subsampled once (smot_subsample2) and both run as plain GEMMs on the tensor cores.
+        Returns [C2, C3, C4, C5]."""
+        L = lib()
+        cfg = self.cfg
+        R = cfg.MODEL.RESNETS
+        dc = _lib.dtype_code(self.dtype)
+        H, W = img.shape[1], img.shape[2]
+        stem = R.STEM_OUT_CHANNELS
+        H2, W2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        x = P.conv(img[..., :3], "body.stem.conv1", P.new(H2, W2, stem), stride=2, pad=3, relu=True)
+        H4, W4 = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
+        pooled = P.new(H4, W4, stem)
+        P.call(L.smot_maxpool3x3s2, self._pool_args(x, pooled), "stem_pool")
+        x, cin = pooled, stem
+        outs = []
+        from .synthetic import R50_BLOCKS
+        for li, nb in enumerate(R50_BLOCKS):
+            mid, cout = R.NUM_GROUPS * R.WIDTH_PER_GROUP * 2 ** li, R.RES2_OUT_CHANNELS * 2 ** li
+            for b in range(nb):
+                name = "body.layer%d.%d" % (li + 1, b)
+                stride = 2 if (b == 0 and li > 0) else 1
+                s1, s3 = (stride, 1) if R.STRIDE_IN_1X1 else (1, stride)
+                h, w = x.shape[1], x.shape[2]
+                ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+                xs = x
+                if stride == 2:   # the even pixels, once, for every strided 1x1 of the block
+                    xs = P.new(ho, wo, cin)
+                    P.call(L.smot_subsample2, (ops._ptr(x), ops._ptr(xs), h, w, cin, ops._nhwc(x)[4], cin, dc), "sub2:" + name)
+                identity = x
+                if cin != cout:
+                    identity = P.conv(xs, name + ".downsample.0", P.new(ho, wo, cout))
+                a = P.conv(xs if s1 == 2 else x, name + ".conv1", P.new(ho if s1 == 2 else h, wo if s1 == 2 else w, mid), relu=True)
+                bmap = P.conv(a, name + ".conv2", P.new(ho, wo, mid), stride=s3, pad=1, relu=True)
+                x = P.conv(bmap, name + ".conv3", P.new(ho, wo, cout), residual=identity, relu=True)
+                cin = cout
+            outs.append(x)
+        return outs
+
     def _pool_args(self, x, out):
         B, H, W, Cc, ld = ops._nhwc(x)
         return (ops._ptr(x), ops._ptr(out), B, H, W, Cc, ld, ops._nhwc(out)[4], _lib.dtype_code(x.dtype))
@@ -536,16 +586,19 @@ class Engine(object):
         P.img_in = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
         img = P.new(H, W, 4)
         P.call(L.smot_image_to_nhwc, (ops._ptr(P.img_in), ops._ptr(img), 3, H, W, 4, dc), "image_to_nhwc")
-        # ---- DLA-34 body (dla.py:289-304)
-        ch = (16, 32, 64, 128, 256, 512)
-        x = P.conv(img[..., :3], "body.base_layer.0", P.new(H, W, ch[0]), pad=3, relu=True)
-        x = P.conv(x, "body.level0.0", P.new(H, W, ch[0]), pad=1, relu=True)
-        x = P.conv(x, "body.level1.0", P.new(H // 2, W // 2, ch[1]), stride=2, pad=1, relu=True)
-        x2 = self._tree(P, "level2", x, 1, ch[1], ch[2], 2, False)
-        x3 = self._tree(P, "level3", x2, 2, ch[2], ch[3], 2, True)
-        x4 = self._tree(P, "level4", x3, 2, ch[3], ch[4], 2, True)
-        x5 = self._tree(P, "level5", x4, 1, ch[4], ch[5], 2, True)
-        body = [x2, x3, x4, x5]
+        if self.resnet:
+            body = self._resnet_body(P, img)
+        else:
+            # ---- DLA-34 body (dla.py:289-304)
+            ch = (16, 32, 64, 128, 256, 512)
+            x = P.conv(img[..., :3], "body.base_layer.0", P.new(H, W, ch[0]), pad=3, relu=True)
+            x = P.conv(x, "body.level0.0", P.new(H, W, ch[0]), pad=1, relu=True)
+            x = P.conv(x, "body.level1.0", P.new(H // 2, W // 2, ch[1]), stride=2, pad=1, relu=True)
+            x2 = self._tree(P, "level2", x, 1, ch[1], ch[2], 2, False)
+            x3 = self._tree(P, "level3", x2, 2, ch[2], ch[3], 2, True)
+            x4 = self._tree(P, "level4", x3, 2, ch[3], ch[4], 2, True)
+            x5 = self._tree(P, "level5", x4, 1, ch[4], ch[5], 2, True)
+            body = [x2, x3, x4, x5]
         # ---- FPN (fpn_patch.py:29-61)
         Cc = self.C
         R = cfg.MODEL.RPN

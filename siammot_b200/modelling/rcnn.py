@@ -17,7 +17,7 @@ from torch import nn
 from .. import ops
 from ..engine import Engine, cell_anchors
 from ..structures import BoxList
-from ..synthetic import dla34_layout, make_state_dict
+from ..synthetic import backbone_channels, body_layout, make_state_dict
 from . import registry
 from .track_utils import build_track_utils
 
@@ -335,9 +335,9 @@ class SiamMOT(nn.Module):
         super().__init__()
         self.cfg = cfg
         # ---- parameter tree with the reference's names; values: seeded synthetic init (no checkpoints offline)
-        bn_names = set("backbone.body." + n for kind, n, _ in dla34_layout() if kind == "bn")
+        bn_names = set("backbone.body." + n for kind, n, _ in body_layout(cfg) if kind == "bn")
         self.backbone = _Holder()
-        self.backbone.out_channels = cfg.MODEL.DLA.BACKBONE_OUT_CHANNELS
+        self.backbone.out_channels = backbone_channels(cfg)[1]
         self.rpn = _Holder()
         track_utils, track_pool = build_track_utils(cfg)
         tracker = registry.SIAMESE_TRACKER[cfg.MODEL.TRACK_HEAD.MODEL](cfg, track_utils)

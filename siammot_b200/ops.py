@@ -113,6 +113,17 @@ def maxpool2x2(x, out=None):
     return out
 
 
+def maxpool3x3s2(x, out=None):
+    """F.max_pool2d(x, 3, 2, 1) on an NHWC map (the ResNet stem pool)."""
+    _require_cuda(x)
+    B, H, W, Cc, ld = _nhwc(x)
+    if out is None:
+        out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), dtype=x.dtype, device=x.device)
+    check(lib().smot_maxpool3x3s2(_ptr(x), _ptr(out), B, H, W, Cc, ld, _nhwc(out)[4], dtype_code(x.dtype), stream_ptr()),
+          "smot_maxpool3x3s2")
+    return out
+
+
 def upsample_add_(lateral, top):
     _require_cuda(lateral, top)
     _, H, W, Cc, lld = _nhwc(lateral)

@@ -49,6 +49,53 @@ def dla34_layout():
     return out
 
 
+R50_BLOCKS = (3, 4, 6, 3)
+
+
+def resnet50_layout(blocks=R50_BLOCKS, stem=64, res2=256, width=64):
+    """(kind, name, shape) of every ResNet-50 body parameter group in upstream module order (maskrcnn_benchmark
+    modeling/backbone/resnet.py: stem, then per block downsample / conv1..3), stride on the first 1x1."""
+    out = [("conv", "stem.conv1", (stem, 3, 7, 7)), ("bn", "stem.bn1", stem)]
+    cin = stem
+    for li, nb in enumerate(blocks):
+        mid, cout = width * 2 ** li, res2 * 2 ** li
+        for b in range(nb):
+            pre = "layer%d.%d" % (li + 1, b)
+            if cin != cout:
+                out.extend([("conv", pre + ".downsample.0", (cout, cin, 1, 1)), ("bn", pre + ".downsample.1", cout)])
+            out.extend([("conv", pre + ".conv1", (mid, cin, 1, 1)), ("bn", pre + ".bn1", mid),
+                        ("conv", pre + ".conv2", (mid, mid, 3, 3)), ("bn", pre + ".bn2", mid),
+                        ("conv", pre + ".conv3", (cout, mid, 1, 1)), ("bn", pre + ".bn3", cout)])
+            cin = cout
+    return out
+
+
+def is_resnet(cfg):
+    return cfg.MODEL.BACKBONE.CONV_BODY.startswith("R-")
+
+
+def body_layout(cfg):
+    """Layout of the configured body: DLA-34 (dla.py) or ResNet-50 (upstream resnet.py)."""
+    body = cfg.MODEL.BACKBONE.CONV_BODY
+    if body == "DLA-34-FPN":
+        return dla34_layout()
+    if body == "R-50-FPN":
+        R = cfg.MODEL.RESNETS
+        return resnet50_layout(R50_BLOCKS, R.STEM_OUT_CHANNELS, R.RES2_OUT_CHANNELS, R.NUM_GROUPS * R.WIDTH_PER_GROUP)
+    raise NotImplementedError("body %s (DLA-34-FPN and R-50-FPN are implemented)" % body)
+
+
+def backbone_channels(cfg):
+    """(FPN input channels per stage, FPN output channels) -- backbone_ext.py:17-23 / upstream build_resnet_fpn_backbone;
+    the EMM head takes the same output width (feature_extractor.py:47-52)."""
+    if is_resnet(cfg):
+        c2 = cfg.MODEL.RESNETS.RES2_OUT_CHANNELS
+        return (c2, c2 * 2, c2 * 4, c2 * 8), cfg.MODEL.RESNETS.BACKBONE_OUT_CHANNELS
+    D = cfg.MODEL.DLA
+    return ((D.DLA_STAGE2_OUT_CHANNELS, D.DLA_STAGE3_OUT_CHANNELS, D.DLA_STAGE4_OUT_CHANNELS, D.DLA_STAGE5_OUT_CHANNELS),
+            D.BACKBONE_OUT_CHANNELS)
+
+
 def make_state_dict(cfg, seed=1):
     g = torch.Generator().manual_seed(seed)
 
@@ -59,19 +106,21 @@ def make_state_dict(cfg, seed=1):
         return torch.rand(*shape, generator=g)
 
     sd = {}
-    for kind, name, shape in dla34_layout():
+    resnet = is_resnet(cfg)
+    for kind, name, shape in body_layout(cfg):
         key = "backbone.body." + name
         if kind == "conv":
             fan_in = shape[1] * shape[2] * shape[3]
             sd[key + ".weight"] = randn(*shape, std=math.sqrt(2.0 / fan_in))
         else:
-            residual_branch = name.endswith("bn2") or ".project" in name
+            # the branch that is added to the identity gets a smaller gain so that activations stay O(1) with depth
+            residual_branch = (name.endswith("bn3") or ".downsample" in name) if resnet else (name.endswith("bn2") or ".project" in name)
             sd[key + ".weight"] = (0.6 if residual_branch else 0.9) + 0.1 * rand(shape)
             sd[key + ".bias"] = randn(shape, std=0.1)
             sd[key + ".running_mean"] = randn(shape, std=0.1)
             sd[key + ".running_var"] = 1.0 + 0.1 * rand(shape)
-    C = cfg.MODEL.DLA.BACKBONE_OUT_CHANNELS
-    for i, cin in enumerate(DLA34_CHANNELS[2:], 1):
+    stage_channels, C = backbone_channels(cfg)
+    for i, cin in enumerate(stage_channels, 1):
         sd["backbone.fpn.fpn_inner%d.weight" % i] = randn(C, cin, 1, 1, std=math.sqrt(1.0 / cin))
         sd["backbone.fpn.fpn_inner%d.bias" % i] = randn(C, std=0.1)
         sd["backbone.fpn.fpn_layer%d.weight" % i] = randn(C, C, 3, 3, std=math.sqrt(1.0 / (9 * C)))

@@ -55,6 +55,13 @@ ORACLE_SCENARIOS = {
                                      overrides=["MODEL.TRACK_HEAD.START_TRACK_THRESH", 0.45, "MODEL.TRACK_HEAD.TRACK_THRESH", 0.35,
                                                 "MODEL.TRACK_HEAD.RESUME_TRACK_THRESH", 0.4, "MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES", 3],
                                      H=256, W=384, frames=6, n_obj=6, clip_seed=0, weight_seed=3, inject=None),
+    # BASELINE.json configs[4]: upstream maskrcnn_benchmark "R-50-FPN" body (stride on the first 1x1), 256-channel FPN / RPN / box
+    # head / EMM.  The body is NOT reference code (un-vendored upstream, restated in oracle/shim/.../backbone/resnet.py and
+    # cross-checked against torchvision in tests/test_oracle_resnet.py): this fixture pins everything SiamMOT-authored around it
+    "emm_r50_192x320": dict(yaml="DLA_34_FPN_EMM.yaml",
+                            overrides=["MODEL.BACKBONE.CONV_BODY", "R-50-FPN", "MODEL.RESNETS.BACKBONE_OUT_CHANNELS", 256,
+                                       "MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES", 3],
+                            H=192, W=320, frames=5, n_obj=5, clip_seed=5, weight_seed=4, inject=None),
 }
 
 

@@ -188,3 +188,26 @@ def test_search_region_numpy_twin_is_bit_exact():
         ref = search_region(boxes, 512, exp, min_wh)
         assert torch.equal(tu.search_region(boxes), ref)
         assert np.array_equal(tu.search_region_np(boxes.numpy()), ref.numpy())
+
+
+@pytest.mark.parametrize("name", ["emm_256x384", "emm_r50_192x320"])
+def test_state_dict_layout_equals_the_reference_module_tree(name):
+    """build_siammot(cfg).state_dict() has exactly the keys and shapes of the reference's SiamMOT (DLA-34-FPN and the upstream
+    R-50-FPN body), so DetectronCheckpointer-style checkpoints load unchanged.  Needs the reference tree (authoring container)."""
+    import sys
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from oracle import reference_loader
+    if not reference_loader.available():
+        pytest.skip("reference tree not present")
+    from helpers import scenario_cfg
+    from scenarios import ORACLE_SCENARIOS, SCENARIOS
+    from siammot_b200.modelling import build_siammot
+    sc = SCENARIOS.get(name) or ORACLE_SCENARIOS[name]
+    cfg0, build = reference_loader.load()
+    rcfg = cfg0.clone()
+    rcfg.merge_from_file(os.path.join(reference_loader.REFERENCE_ROOT, "configs", "dla", sc["yaml"]))
+    rcfg.merge_from_list(sc["overrides"])
+    rcfg.MODEL.DEVICE = "cpu"
+    ref = {k: tuple(v.shape) for k, v in build(rcfg).state_dict().items()}
+    ours = {k: tuple(v.shape) for k, v in build_siammot(scenario_cfg(name)).state_dict().items()}
+    assert ours == ref
