@@ -168,6 +168,17 @@ int smot_track_combine(const float* det_boxes, const float* det_scores, int ncap
                        const float* active, int n, int tracktor, float* cat_boxes, float* cat_scores, int* zero_count,
                        void* stream);
 
+/* smot_track_combine_grouped: the same for more than one foreground class, where the reference's order matters: its box
+ * head returns the refined tracks grouped by class (filter_results, inference.py:145-191) and _refine_tracks adds the EMM
+ * scores taken BEFORE that regrouping position by position (roi_heads.py:67,76).  With V = valid tracks in memory order and
+ * G = V stably sorted by label: cat[ncap + g] = box / detection score of track G[g], EMM score of V[g]; perm[g] = G[g]
+ * (memory row) for g < |V|, and cat_scores = -1, perm = -1 for the unused tail.  Identical to smot_track_combine (up to
+ * the compaction of invalid rows) when every track has the same label. */
+int smot_track_combine_grouped(const float* det_boxes, const float* det_scores, int ncap, const float* dec_boxes,
+                               const float* dec_scores, int ncls, const int* labels, const float* conf, const int* valid,
+                               const float* active, int n, int tracktor, float* cat_boxes, float* cat_scores,
+                               int* zero_count, int* perm, void* stream);
+
 /* ---- EMM tracker ---------------------------------------------------------------------------------
  * smot_xcorr: depthwise valid cross-correlation (xcorr.py:37-45), NHWC:
  *   out[n][i][j][c] = sum_{u,v<T} x[n][i+u][j+v][c] * k[n][u][v][c],  x: SxS, k: TxT, out: (S-T+1)^2. */

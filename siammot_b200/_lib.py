@@ -42,7 +42,7 @@ _lib = None
 # kernels launched by one call of each entry point (memsets not counted); used for bench.py's gpu_launches
 KERNELS_PER_CALL = {"smot_conv2d": 1, "smot_image_to_nhwc": 1, "smot_maxpool2x2": 1, "smot_maxpool3x3s2": 1, "smot_upsample_add": 1,
                     "smot_subsample2": 1, "smot_groupnorm_relu": 1, "smot_roi_align": 1, "smot_rpn_select": 6,
-                    "smot_sort_nms": 3, "smot_box_decode": 1, "smot_track_combine": 1, "smot_xcorr": 1, "smot_emm_decode": 2,
+                    "smot_sort_nms": 3, "smot_box_decode": 1, "smot_track_combine": 1, "smot_track_combine_grouped": 1, "smot_xcorr": 1, "smot_emm_decode": 2,
                     "smot_roi_align_planar": 1, "smot_xcorr_planar": 1,
                     "smot_resample_h_u8": 1, "smot_resample_v_normalize": 1}
 
@@ -65,6 +65,7 @@ def _declare(lib):
         "smot_sort_nms": [vp, i, vp, i, vp, i, f, f, i, i, vp, vp, vp, vp, vp, vp, sz, vp],
         "smot_box_decode": [vp, i, vp, vp, i, i, C.POINTER(C.c_float * 4), i, i, i, vp, vp, vp, vp],
         "smot_track_combine": [vp, vp, i, vp, vp, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp],
+        "smot_track_combine_grouped": [vp, vp, i, vp, vp, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp],
         "smot_xcorr": [vp, vp, vp, i, i, i, i, i, vp],
         "smot_roi_align_planar": [C.POINTER(Pyramid), vp, vp, vp, i, i, i, i, vp, i, i, i, vp],
         "smot_xcorr_planar": [vp, vp, vp, i, i, vp],

@@ -631,9 +631,75 @@ __global__ void track_combine_kernel(const float* __restrict__ det_boxes, const 
   }
 }
 
+// Multi-class form (NUM_CLASSES > 2).  The reference's box head returns the refined tracks GROUPED BY CLASS (filter_results
+// loops over the classes, inference.py:145-191), while _refine_tracks took the EMM scores before the box head ran
+// (roi_heads.py:67) and adds them position by position (:76).  With one foreground class both orders coincide; with more,
+// position g of the class-grouped list carries box / id / label / detection score of track G[g] but the EMM score of V[g],
+// where V = the valid tracks in memory order and G = V stably sorted by label.  Replicated here exactly (it decides scores,
+// hence ids): the thread of valid track r finds g = its rank in G and the row src = V[g], writes candidate ncap + g and
+// perm[g] = r (the host maps solver survivors back to memory rows through perm); positions >= |V| get score -1, perm -1.
+// O(n) work per thread, n = tracks in memory (tens).
+__global__ void track_combine_grouped_kernel(const float* __restrict__ det_boxes, const float* __restrict__ det_scores, int ncap,
+                                             const float* __restrict__ dec_boxes, const float* __restrict__ dec_scores, int ncls,
+                                             const int* __restrict__ labels, const float* __restrict__ conf,
+                                             const int* __restrict__ valid, const float* __restrict__ active, int n, int tracktor,
+                                             float* __restrict__ cat_boxes, float* __restrict__ cat_scores, int* zero_me,
+                                             int* __restrict__ perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && zero_me) *zero_me = 0;
+  if (i < ncap) {
+    reinterpret_cast<float4*>(cat_boxes)[i] = reinterpret_cast<const float4*>(det_boxes)[i];
+    cat_scores[i] = det_scores[i];
+    return;
+  }
+  if (i >= ncap + n) return;
+  const int r = i - ncap;
+  int m = 0;  // |V|
+  for (int q = 0; q < n; ++q) m += valid[q] ? 1 : 0;
+  if (r >= m) {  // unused tail position r
+    reinterpret_cast<float4*>(cat_boxes)[ncap + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cat_scores[ncap + r] = -1.f;
+    perm[r] = -1;
+  }
+  if (!valid[r]) return;
+  const int lab = labels[r];
+  int g = 0;
+  for (int q = 0; q < n; ++q)
+    if (valid[q] && (labels[q] < lab || (labels[q] == lab && q < r))) ++g;
+  int src = -1, cnt = 0;
+  for (int q = 0; q < n; ++q)
+    if (valid[q]) {
+      if (cnt == g) { src = q; break; }
+      ++cnt;
+    }
+  const float det_part = dec_scores[(size_t)r * ncls + lab];          // p + 1 (inference.py:103)
+  float s = det_part;
+  if (!tracktor) s = __fdiv_rn(det_part + (conf[src] + 1.f), 2.f);    // roi_heads.py:67,76: the score of V[g], not of G[g]
+  s = s + active[r];                                                  // track_solver.py:69
+  reinterpret_cast<float4*>(cat_boxes)[ncap + g] = reinterpret_cast<const float4*>(dec_boxes)[(size_t)r * ncls + lab];
+  cat_scores[ncap + g] = s;
+  perm[g] = r;
+}
+
 }  // namespace smot
 
 using namespace smot;
+
+extern "C" int smot_track_combine_grouped(const float* det_boxes, const float* det_scores, int ncap, const float* dec_boxes,
+                                          const float* dec_scores, int ncls, const int* labels, const float* conf,
+                                          const int* valid, const float* active, int n, int tracktor, float* cat_boxes,
+                                          float* cat_scores, int* zero_count, int* perm, void* stream) {
+  SMOT_CHECK_ARG(ncap >= 0 && n >= 0 && cat_boxes && cat_scores, "smot_track_combine_grouped: bad arguments");
+  SMOT_CHECK_ARG(ncap == 0 || (det_boxes && det_scores), "smot_track_combine_grouped: null detections");
+  SMOT_CHECK_ARG(n == 0 || (dec_boxes && dec_scores && labels && conf && valid && active && perm && ncls >= 2),
+                 "smot_track_combine_grouped: null track arrays");
+  const int total = ncap + n;
+  track_combine_grouped_kernel<<<(total + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      det_boxes, det_scores, ncap, dec_boxes, dec_scores, ncls, labels, conf, valid, active, n, tracktor, cat_boxes,
+      cat_scores, zero_count, perm);
+  SMOT_CHECK_LAUNCH("smot_track_combine_grouped");
+  return SMOT_OK;
+}
 
 extern "C" int smot_track_combine(const float* det_boxes, const float* det_scores, int ncap, const float* dec_boxes,
                                   const float* dec_scores, int ncls, const int* labels, const float* conf, const int* valid,

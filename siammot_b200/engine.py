@@ -147,9 +147,9 @@ class _TrackArena(object):
         tmax = ncap + cap
         self.inputs = torch.zeros((10 * cap,), dtype=f32, device=dev)
         self.inputs_host = torch.zeros((10 * cap,), dtype=f32).pin_memory()
-        self.res = torch.zeros((1 + 7 * tmax,), dtype=f32, device=dev)
+        self.res = torch.zeros((1 + 7 * tmax + cap,), dtype=f32, device=dev)
         self.cat_boxes = torch.zeros((tmax, 4), dtype=f32, device=dev)
-        self.host = torch.zeros((1 + 7 * tmax + 1 + ncap,), dtype=f32).pin_memory()
+        self.host = torch.zeros((1 + 7 * tmax + cap + 1 + ncap,), dtype=f32).pin_memory()
         self.srf = torch.zeros((cap * S * S * Cc,), dtype=dt, device=dev)
         # channel-planar search windows (developer switch SMOT_XCORR_PLANAR): zero-filled once, the pad columns stay zero
         self.srp = torch.zeros((cap * Cc * _lib.XCORR_PLANE,), dtype=dt, device=dev) if eng.xcorr_planar_ok() else None
@@ -197,14 +197,17 @@ class _TrackPlan(object):
         self.labels = A.inputs[8 * n:9 * n].view(torch.int32)
         self.active = A.inputs[9 * n:10 * n]
         # ---- result block: kept_boxes (4t, 16B aligned for float4 stores) | keep_cnt | keep_idx (t) | kept_scores (t) | cat_scores (t)
+        #      [| perm (n): candidate position -> memory row, only with more than one foreground class]
         t = max(total, 1)
-        rlen = 1 + 7 * t
+        self.grouped = bool(n) and eng.ncls > 2
+        rlen = 1 + 7 * t + (n if self.grouped else 0)
         self.res = A.res[:rlen]
         self.kept_boxes = self.res[0:4 * t].view(t, 4)
         self.keep_cnt = self.res[4 * t:4 * t + 1].view(torch.int32)
         self.keep_idx = self.res[4 * t + 1:5 * t + 1].view(torch.int32)
         self.kept_scores = self.res[5 * t + 1:6 * t + 1]
         self.cat_scores = self.res[6 * t + 1:7 * t + 1]
+        self.perm = self.res[7 * t + 1:7 * t + 1 + n].view(torch.int32) if self.grouped else None
         self.cat_boxes = A.cat_boxes[:t]
         self.host_res = A.host[:rlen]
         self.host_det = A.host[rlen:rlen + 1 + ncap].view(torch.int32)
@@ -261,12 +264,20 @@ class _TrackPlan(object):
             dec_b, dec_s = self.box["dec_boxes"], self.box["dec_scores"]
         else:
             dec_b = dec_s = None
-        self.steps.append((L.smot_track_combine, (ops._ptr(det_boxes), ops._ptr(det_scores), ncap, ops._ptr(dec_b),
-                                                  ops._ptr(dec_s), eng.ncls, ops._ptr(self.labels) if n else None,
-                                                  ops._ptr(self.conf) if n else None, ops._ptr(self.valid) if n else None,
-                                                  ops._ptr(self.active) if n else None, n, int(T.TRACKTOR),
-                                                  ops._ptr(self.cat_boxes), ops._ptr(self.cat_scores), ops._ptr(self.keep_cnt)),
-                           "track_combine"))
+        if self.grouped:
+            # several foreground classes: the reference's class-grouped order / position-paired scores (roi_heads.py:60-84)
+            self.steps.append((L.smot_track_combine_grouped, (ops._ptr(det_boxes), ops._ptr(det_scores), ncap, ops._ptr(dec_b),
+                                                              ops._ptr(dec_s), eng.ncls, ops._ptr(self.labels), ops._ptr(self.conf),
+                                                              ops._ptr(self.valid), ops._ptr(self.active), n, int(T.TRACKTOR),
+                                                              ops._ptr(self.cat_boxes), ops._ptr(self.cat_scores),
+                                                              ops._ptr(self.keep_cnt), ops._ptr(self.perm)), "track_combine"))
+        else:
+            self.steps.append((L.smot_track_combine, (ops._ptr(det_boxes), ops._ptr(det_scores), ncap, ops._ptr(dec_b),
+                                                      ops._ptr(dec_s), eng.ncls, ops._ptr(self.labels) if n else None,
+                                                      ops._ptr(self.conf) if n else None, ops._ptr(self.valid) if n else None,
+                                                      ops._ptr(self.active) if n else None, n, int(T.TRACKTOR),
+                                                      ops._ptr(self.cat_boxes), ops._ptr(self.cat_scores), ops._ptr(self.keep_cnt)),
+                               "track_combine"))
         if total:
             ws = eng.nms_workspace(total)
             self.steps.append((L.smot_sort_nms, (ops._ptr(self.cat_boxes), 4, ops._ptr(self.cat_scores), 1, None, total, -0.5, 0.5,

@@ -242,12 +242,22 @@ class CombinedROIHeads(nn.ModuleDict):
         labels[~is_trk] = det_labels[keep[~is_trk]]
         all_track_ids = set()
         if n:
-            trk_valid = hf[6 * t + 1 + ncap:6 * t + 1 + total] > -0.5
-            if not trk_valid.any():
+            if tp.grouped:
+                # several foreground classes: candidate position g holds memory row perm[g] (class-grouped order of the
+                # reference's box head, inference.py:145-191); -1 marks the unused tail
+                perm = hi[7 * t + 1:7 * t + 1 + n]
+                valid_rows = perm[perm >= 0]
+                any_valid = valid_rows.size > 0
+                rows = perm[keep[is_trk] - ncap]
+            else:
+                trk_valid = hf[6 * t + 1 + ncap:6 * t + 1 + total] > -0.5
+                any_valid = trk_valid.any()
+                valid_rows = trk_valid
+                rows = keep[is_trk] - ncap
+            if not any_valid:
                 # roi_heads.py:64-65 returns a bare BoxList here and :44 then evaluates list + BoxList
                 raise TypeError("can only concatenate list (not \"BoxList\") to list")
-            all_track_ids = set(mem.ids[trk_valid].tolist())
-            rows = keep[is_trk] - ncap
+            all_track_ids = set(mem.ids[valid_rows].tolist())
             ids[is_trk] = mem.ids[rows]
             labels[is_trk] = mem.labels[rows]
         if k == 0:                                                        # track_solver.py:51-52 (early return)

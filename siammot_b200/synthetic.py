@@ -114,8 +114,9 @@ def make_state_dict(cfg, seed=1):
             sd[key + ".weight"] = randn(*shape, std=math.sqrt(2.0 / fan_in))
         else:
             # the branch that is added to the identity gets a smaller gain so that activations stay O(1) with depth
-            residual_branch = (name.endswith("bn3") or ".downsample" in name) if resnet else (name.endswith("bn2") or ".project" in name)
-            sd[key + ".weight"] = (0.6 if residual_branch else 0.9) + 0.1 * rand(shape)
+            # (16 bottleneck blocks in the ResNet: a much smaller gain than for DLA's 8 basic blocks)
+            residual_branch = name.endswith("bn3") if resnet else (name.endswith("bn2") or ".project" in name)
+            sd[key + ".weight"] = ((0.25 if resnet else 0.6) if residual_branch else 0.9) + 0.1 * rand(shape)
             sd[key + ".bias"] = randn(shape, std=0.1)
             sd[key + ".running_mean"] = randn(shape, std=0.1)
             sd[key + ".running_var"] = 1.0 + 0.1 * rand(shape)

@@ -61,7 +61,7 @@ ORACLE_SCENARIOS = {
     "emm_r50_192x320": dict(yaml="DLA_34_FPN_EMM.yaml",
                             overrides=["MODEL.BACKBONE.CONV_BODY", "R-50-FPN", "MODEL.RESNETS.BACKBONE_OUT_CHANNELS", 256,
                                        "MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES", 3],
-                            H=192, W=320, frames=5, n_obj=5, clip_seed=5, weight_seed=4, inject=None),
+                            H=192, W=320, frames=5, n_obj=5, clip_seed=5, weight_seed=11, inject=None),
 }
 
 

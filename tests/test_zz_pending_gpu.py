@@ -120,3 +120,42 @@ def test_engine_planar_switch_changes_nothing(monkeypatch):
         for a, b in zip(ref, got):
             assert torch.equal(a.bbox, b.bbox) and torch.equal(a.get_field("scores"), b.get_field("scores"))
             assert torch.equal(a.get_field("ids"), b.get_field("ids"))
+
+
+@pytest.mark.xfail(strict=False, reason="smot_track_combine_grouped (several foreground classes) was written after this round's GPU "
+                                       "budget was spent; its specification is pinned on the CPU against the reference golden "
+                                       "(tests/test_engine_emulated_cpu.py); first GPU run pending")
+def test_track_combine_grouped_matches_its_cpu_specification():
+    """The CUDA kernel against tests/cabi_emulator.py's restatement of roi_heads.py:60-84 over class-grouped tracks."""
+    import ctypes as C
+
+    import numpy as np
+
+    import cabi_emulator as ce
+    from siammot_b200 import _lib
+    spec = ce.FakeLib()
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+
+    def p(t):
+        return C.c_void_p(t.data_ptr())
+
+    for trial in range(40):
+        n, ncap, ncls = int(rng.integers(1, 90)), int(rng.integers(0, 40)), int(rng.integers(3, 6))
+        tracktor = int(rng.integers(0, 2))
+        host = dict(det_boxes=torch.rand(max(ncap, 1), 4), det_scores=torch.rand(max(ncap, 1)), dec_boxes=torch.rand(n, ncls, 4),
+                    dec_scores=torch.rand(n, ncls), labels=torch.tensor(rng.integers(1, ncls, n), dtype=torch.int32),
+                    conf=torch.rand(n), valid=torch.tensor(rng.integers(0, 2, n), dtype=torch.int32),
+                    active=torch.tensor(rng.integers(0, 2, n), dtype=torch.float32))
+        out_h = dict(cb=torch.full((ncap + n, 4), 9.), cs=torch.full((ncap + n,), 9.), zc=torch.tensor([5], dtype=torch.int32),
+                     perm=torch.full((n,), 7, dtype=torch.int32))
+        dev = {k: v.cuda() for k, v in host.items()}
+        out_d = {k: v.cuda() for k, v in out_h.items()}
+        for src, out, fn in ((host, out_h, spec.smot_track_combine_grouped), (dev, out_d, L.smot_track_combine_grouped)):
+            rc = fn(p(src["det_boxes"]), p(src["det_scores"]), ncap, p(src["dec_boxes"]), p(src["dec_scores"]), ncls, p(src["labels"]),
+                    p(src["conf"]), p(src["valid"]), p(src["active"]), n, tracktor, p(out["cb"]), p(out["cs"]), p(out["zc"]),
+                    p(out["perm"]), None)
+            assert rc == 0
+        torch.cuda.synchronize()
+        for k in out_h:
+            assert torch.equal(out_d[k].cpu(), out_h[k]), (trial, k)
