@@ -305,6 +305,18 @@ class FakeLib(object):
             _view(_a(out), n, O, O, Cc, Cc).copy_(y.permute(0, 2, 3, 1))
         return 0
 
+    def smot_xcorr_planar(self, xp, k, out, n, Cc, st):
+        self._count("smot_xcorr_planar")
+        from siammot_b200 import _lib
+        if n:
+            S, T, O, RP, PL = 30, 15, 16, _lib.XCORR_ROW_PITCH, _lib.XCORR_PLANE
+            planes = _f32(xp, n * Cc * PL).view(n, Cc, PL)
+            rows = planes[:, :, :S * RP].view(n, Cc, S, RP)
+            assert float(rows[..., S:S + 2].abs().max()) == 0.0, "columns 30/31 of the planar windows must be zero"
+            y = orc.xcorr_depthwise(rows[..., :S], _view(_a(k), n, T, T, Cc, Cc).permute(0, 3, 1, 2))
+            _view(_a(out), n, O, O, Cc, Cc).copy_(y.permute(0, 2, 3, 1))
+        return 0
+
     def smot_emm_decode(self, maps, map_ld, n, O, up, T, sr, tboxes, hann, pad, use_centerness, sigma, img_w, img_h, amodal,
                         out_boxes, out_conf, out_valid, scratch, st):
         self._count("smot_emm_decode")
@@ -338,7 +350,7 @@ class _Event(object):
         pass
 
     def elapsed_time(self, other):
-        return 0.0
+        return 1.0   # ms: any positive number -- timings taken under the emulation are meaningless
 
 
 class _Stream(object):
@@ -384,4 +396,27 @@ def install(monkeypatch):
         return self._engine
 
     monkeypatch.setattr(rcnn.SiamMOT, "engine", host_engine)
+    return fake
+
+
+def install_for_bench(monkeypatch):
+    """install() + what bench.py touches beyond the model: device placement and the device-side test transform (emulated by
+    the oracle's restatement of the reference transform)."""
+    from oracle import preprocess as opp
+    from siammot_b200 import preprocess
+    fake = install(monkeypatch)
+    orig_init = preprocess.FramePreprocessor.__init__
+
+    def init(self, cfg, device="cuda"):
+        orig_init(self, cfg, device)
+        self._cfg = cfg
+
+    def into(self, frame, out):
+        out.copy_(opp.preprocess(frame.numpy() if torch.is_tensor(frame) else frame, self._cfg))
+        return out
+
+    monkeypatch.setattr(preprocess.FramePreprocessor, "__init__", init)
+    monkeypatch.setattr(preprocess.FramePreprocessor, "into", into)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a: None)
+    monkeypatch.setattr(torch.nn.Module, "to", lambda self, *a, **k: self)
     return fake

@@ -84,3 +84,14 @@ def test_emulated_forward_clip_equals_golden(monkeypatch):
     """The clip API's bookkeeping (double-buffered plans, next_P for the memory) on the host."""
     got, _ = _run("emm_amodal_expire_192x320", monkeypatch, clip_api=True)
     _compare(load_golden("emm_amodal_expire_192x320")["frames"], got)
+
+
+def test_emulated_planar_window_exchange_wiring(monkeypatch):
+    """Host wiring of the SMOT_XCORR_PLANAR switch (arena buffer, the two planar calls in the track plan): same goldens.
+    The emulation is fp32, so the dtype condition of the switch is lifted for this test only."""
+    from siammot_b200 import engine
+    monkeypatch.setattr(engine.Engine, "xcorr_planar_ok", lambda self: self.xcorr_planar and self.s_res == 30 and self.t_res == 15)
+    got, fake = _run("emm_256x384", monkeypatch, env={"SMOT_XCORR_PLANAR": "1"})
+    _compare(load_golden("emm_256x384")["frames"], got)
+    assert fake.calls.get("smot_xcorr_planar", 0) > 0 and fake.calls.get("smot_roi_align_planar", 0) > 0
+    assert fake.calls.get("smot_xcorr", 0) == 0
