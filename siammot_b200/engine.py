@@ -76,6 +76,8 @@ class _Plan(object):
         self.dtype = engine.dtype
         self.ws = engine.conv_ws      # split-K scratch of the stream this plan runs on
         self.static_done = None       # event recorded after the plan when it runs on the side stream (forward_clip)
+        self.backbone_done = None     # three-stage clip mode: event after part 0
+        self.part_graphs = [None, None]
         self.branch = None            # while building: steps appended go to this parallel branch (None = main line)
 
     def new(self, H, W, Cc, dtype=None, B=1):
@@ -104,11 +106,19 @@ class _Plan(object):
         self.branch = None
         self.steps.append(("join", None, None, None))
 
-    def run_eager(self):
+    def split_index(self):
+        """First step of the detection tail (RPN selection .. per-class NMS): everything before it is the backbone / FPN /
+        RPN-head part, whose kernels fill the GPU; the tail is a serial chain of small kernels."""
+        for i, (_fn, _args, tag, _branch) in enumerate(self.steps):
+            if tag == "rpn_select":
+                return i
+        raise RuntimeError("static plan without an rpn_select step")
+
+    def run_eager(self, lo=0, hi=None):
         main = torch.cuda.current_stream(self.dev)
         st = C.c_void_p(main.cuda_stream)
         active = []
-        for fn, args, tag, branch in self.steps:
+        for fn, args, tag, branch in self.steps[lo:hi]:
             if fn == "fork":
                 active = self.e.branch_streams(args)
                 for b in active:
@@ -134,6 +144,23 @@ class _Plan(object):
             self.graph.replay()
         else:
             self.run_eager()
+
+    def run_part(self, part):
+        """Run one half of the plan on the current stream (part 0: image .. RPN heads, part 1: proposal selection ..
+        detections), each half its own CUDA graph -- SiamMOT.forward_clip's three-stage mode runs the halves of
+        consecutive frames on different streams."""
+        k = self.split_index()
+        lo, hi = (0, k) if part == 0 else (k, len(self.steps))
+        if not self.e.use_graph:
+            return self.run_eager(lo, hi)
+        if self.part_graphs[part] is None:
+            self.run_eager(lo, hi)  # warm-up on live data (the other half has run): sets function attributes
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run_eager(lo, hi)
+            self.part_graphs[part] = g
+        self.part_graphs[part].replay()
 
 
 class _TrackArena(object):
@@ -384,7 +411,15 @@ class Engine(object):
         # stages of consecutive frames on different streams, launches within a stage are stream-ordered
         self.conv_ws = ops.conv_workspace(self.device)
         self.conv_ws_track = ops.conv_workspace(self.device)
+        # the detection tail (box-head FCs) has its own: in forward_clip's three-stage mode it runs on a third stream while
+        # the next frame's backbone uses conv_ws
+        self.conv_ws_det = ops.conv_workspace(self.device)
         self._side = None
+        self._tail = None
+        # developer switches of SiamMOT.forward_clip: SMOT_CLIP_SPLIT=1 runs the detection tail of frame t
+        # on a third stream under the backbone of frame t+1; SMOT_CLIP_SLOTS = number of static-plan copies (2 or 3)
+        self.clip_split = os.environ.get("SMOT_CLIP_SPLIT", "0") == "1"
+        self.clip_slots = max(2, min(4, int(os.environ.get("SMOT_CLIP_SLOTS", "2"))))
         self._pre = None
         self._branch_ws = []
         self._branch_streams = []
@@ -659,6 +694,7 @@ class Engine(object):
                                    ops._ptr(P.props), ops._ptr(P.prop_scores), ops._ptr(P.prop_count), ops._ptr(ws),
                                    ws.numel()), "rpn_select")
         # ---- box head on the proposals (box_head.py:46-51, inference.py:46-191)
+        P.ws = self.conv_ws_det   # split-K scratch of the detection tail (see Engine.__init__)
         P.box = self._box_buffers(nprop)
         self._box_steps(P, P.box, P.props, P.prop_count, nprop, None)
         ncls = self.ncls
@@ -736,8 +772,15 @@ class Engine(object):
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
 
-    def run_static(self, image, slot=0):
-        """image: (3,H,W) or (1,3,H,W) float tensor (any device).  Enqueues backbone..detections on the current stream."""
+    def tail_stream(self):
+        """Three-stage clip mode: the stream of the detection tail."""
+        if self._tail is None:
+            self._tail = torch.cuda.Stream(device=self.device)
+        return self._tail
+
+    def run_static(self, image, slot=0, part=None):
+        """image: (3,H,W) or (1,3,H,W) float tensor (any device).  Enqueues backbone..detections on the current stream.
+        part=0: only the input copy and the backbone / FPN / RPN-head half (the detection tail follows with run_tail)."""
         if image.dim() == 4:
             if image.shape[0] != 1:
                 raise ValueError("one image per forward (track_core.py:75 asserts the same)")
@@ -745,7 +788,13 @@ class Engine(object):
         P = self.plan(image.shape[1], image.shape[2], slot)
         P.img_in.copy_(image, non_blocking=True)
         with self.timed("static"):
-            P.run()
+            P.run() if part is None else P.run_part(part)
+        return P
+
+    def run_tail(self, P):
+        """The detection tail (proposal selection, box head, per-class NMS) of a plan whose part 0 has been enqueued."""
+        with self.timed("static_tail"):
+            P.run_part(1)
         return P
 
     def preprocessor(self):
@@ -754,7 +803,7 @@ class Engine(object):
             self._pre = FramePreprocessor(self.cfg, self.device)
         return self._pre
 
-    def run_static_raw(self, frame, slot=0):
+    def run_static_raw(self, frame, slot=0, part=None):
         """frame: decoded RGB uint8 (H0, W0, 3) frame (host or device).  The reference's test transform (resize to
         the cfg's test size, ToTensor, Normalize) runs on the device straight into the plan's input buffer, then the
         frame-independent stage is enqueued as in run_static."""
@@ -764,7 +813,7 @@ class Engine(object):
         with self.timed("preprocess"):
             pre.into(frame, P.img_in)
         with self.timed("static"):
-            P.run()
+            P.run() if part is None else P.run_part(part)
         return P
 
     def box_head_eager(self, P, rois, track_labels=None):
@@ -819,6 +868,11 @@ class Engine(object):
             P.pyr_plain = ops.make_pyramid(P.feats, T.POOLER_SCALES)
         return ops.roi_align(P.feats, boxes_dev, T.POOLER_SCALES, self.t_res, T.POOLER_SAMPLING_RATIO, out=out,
                              pyramid=P.pyr_plain)
+
+    def gather_templates(self, feat, first, sources):
+        """feat[first + j] = sources[j][0][sources[j][1]]: the cached templates of dormant tracks (rows of earlier frames'
+        template tensors, track_head.py:77-97) appended behind the active tracks' templates.  Device-side, current stream."""
+        feat[first:] = torch.stack([t[r] for t, r in sources])
 
     def track_arena(self, P, n, ncap=None):
         """The shared buffer arena of static plan P, grown (x2) when n exceeds its capacity."""

@@ -333,7 +333,7 @@ class CombinedROIHeads(nn.ModuleDict):
         if n_act:
             eng.templates(P, tp.boxes[:n_act], out=feat[:n_act])
         if dormant:
-            feat[n_act:] = torch.stack([d[0][d[1]] for d in dormant])
+            eng.gather_templates(feat, n_act, [(d[0], d[1]) for d in dormant])
         mem.feat = feat
         pool.update_cache({int(m_ids[r]): (feat, r, m_sr[r].copy(), m_boxes[r].copy(), int(m_ids[r]), int(m_labels[r]))
                            for r in range(n)})
@@ -462,6 +462,8 @@ def _forward_clip(self, frames, before_frame=None):
     results = []
     if not n_frames:
         return results
+    if eng.clip_split:
+        return _forward_clip_three_stage(self, eng, frames, before_frame)
     cur = torch.cuda.current_stream(eng.device)
     side = eng.side_stream()
     side.wait_stream(cur)          # the frames (and anything else already enqueued) are visible to the side stream
@@ -495,6 +497,74 @@ def _forward_clip(self, frames, before_frame=None):
             self.track_memory = mem
             results.append(result)
         cur.wait_stream(side)
+    return results
+
+
+def _forward_clip_three_stage(self, eng, frames, before_frame=None):
+    """forward_clip with the frame-independent stage cut in two (developer switch SMOT_CLIP_SPLIT=1):
+
+      stream A   B(t): input copy / test transform, backbone, FPN, RPN heads   -- the kernels that fill the GPU
+      stream D   D(t): proposal selection, box head, per-class NMS             -- a serial chain of small kernels
+      caller's   T(t): track stage, then the host solver H(t) and the next-frame memory
+
+    Dependencies: D(t) after B(t); T(t) after D(t) and H(t-1); B(t + K) after T(t) and H(t)'s template pooling (slot reuse,
+    K = SMOT_CLIP_SLOTS static-plan copies).  So D(t) and T(t) run under B(t+1) (.. B(t+K-1)), and the per-frame period is
+    max(B, T + H) instead of B + D.  The three stages use disjoint split-K scratch (conv_ws / conv_ws_det / conv_ws_track)
+    and per-slot buffers; every cross-stream edge is an event recorded BEFORE the wait on it is enqueued.
+    Results are identical to frame-by-frame calls."""
+    n_frames = len(frames)
+    K = eng.clip_slots
+    results = []
+    cur = torch.cuda.current_stream(eng.device)
+    sA, sD = eng.side_stream(), eng.tail_stream()
+    sA.wait_stream(cur)            # the frames (and anything else already enqueued) are visible to the worker streams
+    sD.wait_stream(cur)
+    slot_free = [None] * K         # event: every reader of the slot's buffers (D, T, template pooling) is enqueued-complete
+    plans = {}
+
+    def backbone(t):
+        s = t % K
+        with torch.cuda.stream(sA):
+            if slot_free[s] is not None:
+                sA.wait_event(slot_free[s])
+            P = (eng.run_static_raw(frames[t], s, part=0) if _is_raw_frame(frames[t]) else eng.run_static(frames[t], s, part=0))
+            if P.backbone_done is None:
+                P.backbone_done = torch.cuda.Event()
+            P.backbone_done.record(sA)
+        plans[t] = P
+
+    def detect(t):
+        P = plans[t]
+        with torch.cuda.stream(sD):
+            sD.wait_event(P.backbone_done)
+            eng.run_tail(P)
+            if P.static_done is None:
+                P.static_done = torch.cuda.Event()
+            P.static_done.record(sD)
+
+    with torch.no_grad():
+        for t in range(min(K - 1, n_frames)):
+            backbone(t)
+        detect(0)
+        for t in range(n_frames):
+            P = plans.pop(t)
+            if before_frame is not None:
+                before_frame(t)
+            cur.wait_event(P.static_done)          # D(t) complete (hence B(t))
+            pending = self.roi_heads.launch_frame(P, self._mem)
+            if t + K - 1 < n_frames:
+                backbone(t + K - 1)                # slot of frame t-1: its slot_free event was recorded in iteration t-1
+            if t + 1 < n_frames:
+                detect(t + 1)
+            result, mem = self.roi_heads.finish_frame(pending, next_P=plans.get(t + 1))
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            slot_free[t % K] = ev
+            self._mem = mem
+            self.track_memory = mem
+            results.append(result)
+        cur.wait_stream(sA)
+        cur.wait_stream(sD)
     return results
 
 

@@ -95,3 +95,13 @@ def test_emulated_planar_window_exchange_wiring(monkeypatch):
     _compare(load_golden("emm_256x384")["frames"], got)
     assert fake.calls.get("smot_xcorr_planar", 0) > 0 and fake.calls.get("smot_roi_align_planar", 0) > 0
     assert fake.calls.get("smot_xcorr", 0) == 0
+
+
+@pytest.mark.parametrize("slots", ["2", "3"])
+def test_emulated_three_stage_clip_equals_golden(slots, monkeypatch):
+    """SMOT_CLIP_SPLIT=1: the static plan cut at the proposal selection, K plan copies -- same results (this checks the
+    bookkeeping: plan slices, slot rotation, next_P; the stream / event ordering can only be exercised on a GPU)."""
+    env = {"SMOT_CLIP_SPLIT": "1", "SMOT_CLIP_SLOTS": slots}
+    for name in ("emm_amodal_expire_192x320", "emm_256x384"):
+        got, fake = _run(name, monkeypatch, clip_api=True, env=env)
+        _compare(load_golden(name)["frames"], got)

@@ -26,3 +26,42 @@ def test_backbone_and_fpn_wiring_matches_oracle(name, monkeypatch):
         assert got.shape == want.shape, (l, got.shape, want.shape)
         err = float((got - want).abs().max() / want.abs().max())
         assert err <= 1e-4, "FPN level %d: relative error %g" % (l, err)
+
+
+def test_concurrent_stages_use_disjoint_split_k_scratch(monkeypatch):
+    """forward_clip runs the backbone half of frame t+1, the detection tail of frame t and the track stage of frame t on three
+    streams (SMOT_CLIP_SPLIT) -- or the first two on one and the third on another (default).  The emulated convs do not touch
+    the split-K scratch, so tests/stream_sim.py cannot see a conflict there: check the assignment itself."""
+    import cabi_emulator
+    from siammot_b200 import engine
+    cabi_emulator.install(monkeypatch)          # the track plan's arena also creates events / pinned blocks
+    cfg, sd, clip = scenario_inputs("emm_amodal_expire_192x320")
+    cfg.DTYPE = "float32"
+    eng = engine.Engine(cfg, device="cpu", use_graph=False)
+    eng.load_state_dict(sd)
+    P = eng.plan(clip[0].shape[1], clip[0].shape[2])
+    k = P.split_index()
+
+    def scratch(steps):
+        out = set()
+        for st in steps:
+            if getattr(st[0], "__name__", None) == "smot_conv2d":
+                out.add(st[1][0]._obj.workspace)
+        return out
+
+    backbone, tail = scratch(P.steps[:k]), scratch(P.steps[k:])
+    tp = eng.track_plan(P, 5)
+    track = scratch(tp.steps)
+    allowed_backbone = {eng.conv_ws.data_ptr()} | {w.data_ptr() for w in eng._branch_ws}
+    assert backbone <= allowed_backbone and len(backbone) >= 2      # main line + parallel branches
+    assert tail == {eng.conv_ws_det.data_ptr()}
+    assert track == {eng.conv_ws_track.data_ptr()}
+    assert not (backbone & tail) and not (backbone & track) and not (tail & track)
+    # parallel branches of one fork never share scratch with each other or with the main line
+    per_branch = {}
+    for fn, args, tag, branch in P.steps[:k]:
+        if getattr(fn, "__name__", None) == "smot_conv2d" and branch is not None:
+            per_branch.setdefault(branch, set()).add(args[0]._obj.workspace)
+    assert all(len(v) == 1 for v in per_branch.values())
+    assert len({next(iter(v)) for v in per_branch.values()}) == len(per_branch)
+    assert eng.conv_ws.data_ptr() not in {next(iter(v)) for v in per_branch.values()}

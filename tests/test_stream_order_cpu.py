@@ -1,0 +1,108 @@
+"""Stream / event ordering of the engine's host orchestration under adversarial (but CUDA-legal) schedules, without a GPU
+(tests/stream_sim.py): per-frame calls, the two-stream clip pipeline and the three-stage clip pipeline must reproduce the
+reference golden whatever the interleaving; a deliberately removed edge must NOT (the detector detects)."""
+import pytest
+import torch
+
+import stream_sim
+from helpers import load_golden, scenario_inputs
+from test_engine_emulated_cpu import _compare
+
+POLICIES = ["lazy", "eager", "workers_eager", "default_eager", ("random", 1), ("random", 2), ("random", 3)]
+NAME = "emm_amodal_expire_192x320"
+
+
+def _run_sim(monkeypatch, policy, mode, env=None, sabotage=None):
+    from siammot_b200.modelling import build_siammot
+    for k, v in (env or {}).items():
+        monkeypatch.setenv(k, v)
+    sim, fake = stream_sim.install(monkeypatch, policy)
+    if sabotage:
+        sabotage(monkeypatch)
+    cfg, sd, clip = scenario_inputs(NAME)
+    cfg.DTYPE = "float32"
+    model = build_siammot(cfg)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    model.results_on_host = True
+    model.reset_siammot_status()
+    pool = model.roi_heads.track.track_pool
+    frames = list(clip)
+    states = []
+    sim.active = True
+    try:
+        if mode == "frame":
+            results = []
+            for f in frames:
+                results.append(model(f)[0])
+                states.append((sorted(pool.get_active_ids()), sorted(pool._dormant_ids)))
+        else:
+            results = model.forward_clip(frames, before_frame=lambda t: states.append((sorted(pool.get_active_ids()), sorted(pool._dormant_ids))))
+            states = states[1:] + [(sorted(pool.get_active_ids()), sorted(pool._dormant_ids))]
+        sim.sync_all()
+    finally:
+        sim.active = False
+    assert sim.executed > 100
+    return [dict(boxes=r.bbox, scores=r.get_field("scores"), ids=r.get_field("ids"), labels=r.get_field("labels"), active=a, dormant=d)
+            for r, (a, d) in zip(results, states)]
+
+
+@pytest.mark.parametrize("policy", POLICIES, ids=str)
+def test_per_frame_and_two_stream_clip_are_schedule_independent(policy, monkeypatch):
+    gold = load_golden(NAME)["frames"]
+    _compare(gold, _run_sim(monkeypatch, policy, "frame"))
+    _compare(gold, _run_sim(monkeypatch, policy, "clip"))
+
+
+@pytest.mark.parametrize("slots", ["2", "3"])
+@pytest.mark.parametrize("policy", POLICIES, ids=str)
+def test_three_stage_clip_is_schedule_independent(policy, slots, monkeypatch):
+    gold = load_golden(NAME)["frames"]
+    _compare(gold, _run_sim(monkeypatch, policy, "clip", env={"SMOT_CLIP_SPLIT": "1", "SMOT_CLIP_SLOTS": slots}))
+
+
+def _differs(gold, got):
+    try:
+        _compare(gold, got)
+    except AssertionError:
+        return True
+    return False
+
+
+def test_the_detector_detects_a_missing_edge(monkeypatch):
+    """Remove one edge at a time from the three-stage pipeline: some legal schedule must then break the results."""
+    gold = load_golden(NAME)["frames"]
+    env = {"SMOT_CLIP_SPLIT": "1", "SMOT_CLIP_SLOTS": "2"}
+
+    def no_wait_on(attr):
+        # Stream.wait_event ignores the events stored under P.<attr> (B -> D edge, or D -> T edge)
+        def sabotage(mp):
+            orig = stream_sim.VStream.wait_event
+
+            def wait_event(self, ev):
+                if getattr(ev, "_tag", None) == attr:
+                    return
+                orig(self, ev)
+            mp.setattr(stream_sim.VStream, "wait_event", wait_event)
+            from siammot_b200 import engine
+            orig_setattr = engine._Plan.__setattr__
+
+            def tagging_setattr(self, name, value):
+                if name == attr and value is not None:
+                    value._tag = attr
+                orig_setattr(self, name, value)
+            mp.setattr(engine._Plan, "__setattr__", tagging_setattr)
+        return sabotage
+
+    for attr in ("backbone_done", "static_done"):
+        broken = False
+        for policy in POLICIES:
+            with pytest.MonkeyPatch.context() as mp:
+                try:
+                    got = _run_sim(mp, policy, "clip", env=env, sabotage=no_wait_on(attr))
+                    broken = broken or _differs(gold, got)
+                except Exception:
+                    broken = True
+            if broken:
+                break
+        assert broken, "removing the %s edge went unnoticed under every schedule" % attr
