@@ -381,9 +381,151 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_frames=2)
+    if world == 1 and args.experimental == "subprocess":
+        # Paths that are built and host-verified but have not been through a GPU run yet are measured for
+        # information in a CHILD process after everything above is final: a crash, a CUDA error or a hang there cannot cost
+        # the line (the child is killed at the timeout).
+        out["experimental"] = experimental_subprocess(args)
+    elif world == 1 and args.experimental == "inproc":
+        def bail():
+            out["experimental"] = {"error": "watchdog: the experimental arms did not return within %d s" % EXPERIMENTAL_TIMEOUT_S}
+            print(json.dumps(out))
+            sys.stdout.flush()
+            os._exit(0)
+        dog = threading.Timer(EXPERIMENTAL_TIMEOUT_S, bail)
+        dog.daemon = True
+        dog.start()
+        try:
+            out["experimental"] = experimental_arms(h, args, frames_dev, frames_u8, hook, ntrk, tp, hbm_peak, xc_bytes)
+        except BaseException as exc:   # noqa: B902 -- a CUDA error surfaces as RuntimeError; keep the line whatever it is
+            out["experimental"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        dog.cancel()
     print(json.dumps(out))
     if distributed:
         dist.destroy_process_group()
+
+
+EXPERIMENTAL_TIMEOUT_S = 150
+
+
+def experimental_subprocess(args):
+    cmd = [sys.executable, os.path.abspath(__file__), "--experimental", "child", "--steps", str(args.steps), "--warmup", str(args.warmup),
+           "--dtype", args.dtype, "--workload", args.workload]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=EXPERIMENTAL_TIMEOUT_S)
+    except subprocess.TimeoutExpired:
+        return {"error": "child process killed after %d s" % EXPERIMENTAL_TIMEOUT_S}
+    except Exception as exc:
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
+    for line in reversed(r.stdout.strip().splitlines()):
+        try:
+            return json.loads(line)
+        except ValueError:
+            continue
+    return {"error": "child exited with code %d: %s" % (r.returncode, r.stderr.strip()[-300:])}
+
+
+def run_experimental_child(args):
+    """`bench.py --experimental child`: own process, own model; prints one JSON object (the "experimental" entry)."""
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    h = Harness(args.dtype, device)
+    h.model.results_on_host = True
+    frames_u8 = make_frames_u8(N_FRAMES, h.cfg).pin_memory()
+    pre = h.eng.preprocessor()
+    frames_dev = torch.stack([pre(frames_u8[i]) for i in range(N_FRAMES)])
+    h.prime(frames_dev[0])
+    hook = lambda t: h.restore()
+    h.model.forward_clip([frames_dev[i % N_FRAMES] for i in range(max(args.warmup, 4))], before_frame=hook)
+    torch.cuda.synchronize()
+    tp = h.eng.track_plan(h.eng.plan(H_NET, W_NET), N_TRACKS)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    esz = 2 if args.dtype == "float16" else 4
+    xc_bytes = N_TRACKS * h.eng.C * (30 * 30 + 15 * 15 + 16 * 16) * esz
+    print(json.dumps(experimental_arms(h, args, frames_dev, frames_u8, hook, None, tp, float(peaks.get("hbm_gbs", 6650.0)), xc_bytes)))
+
+
+def experimental_arms(h, args, frames_dev, frames_u8, hook, ntrk_ref, tp, hbm_peak, xc_bytes):
+    """Measured for information only; none of this feeds `value` / `e2e` / `roofline`.
+    (1) forward_clip as a three-stage pipeline (Engine.clip_split, K = 2 and 3 plan copies): same clip, same memory, must track
+        exactly the boxes the two-stream pipeline tracked.
+    (2) the channel-planar search-window exchange: smot_roi_align_planar / smot_xcorr_planar on the last frame's own track
+        inputs, compared bit for bit with the default kernels' outputs, then timed like the roofline kernel."""
+    from siammot_b200 import _lib, ops
+    from siammot_b200._lib import check, stream_ptr
+    eng = h.eng
+    res = {}
+    steps = min(args.steps, 100)
+    seq = [frames_dev[(args.warmup + i) % N_FRAMES] for i in range(steps)]
+    seq_h = [frames_u8[(args.warmup + i) % N_FRAMES] for i in range(steps)]
+    ref_trk = None
+    for K in (2, 3):
+        key = "three_stage_clip_k%d" % K
+        try:
+            eng.clip_split, eng.clip_slots = True, K
+            h.model.forward_clip([frames_dev[i % N_FRAMES] for i in range(max(args.warmup, 4))], before_frame=hook)
+            torch.cuda.synchronize()
+            if ref_trk is None:   # the two-stream pipeline on exactly this (possibly shorter) sequence
+                eng.clip_split = False
+                ref_trk = sum(int((r.get_field("ids") >= 0).sum()) for r in h.model.forward_clip(seq, before_frame=hook))
+                eng.clip_split = True
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = h.model.forward_clip(seq, before_frame=hook)
+            e1.record()
+            torch.cuda.synchronize()
+            n1 = sum(int((r.get_field("ids") >= 0).sum()) for r in out)
+            h.model.forward_clip(seq_h[:4], before_frame=hook)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = h.model.forward_clip(seq_h, before_frame=hook)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            n2 = sum(int((r.get_field("ids") >= 0).sum()) for r in out)
+            res[key] = {"value": round(steps / (e0.elapsed_time(e1) * 1e-3), 2), "e2e": round(steps / dt, 2), "unit": "frames/s",
+                        "steps": steps, "same_tracks_as_two_stream": bool(n1 == ref_trk and n2 == ref_trk)}
+        except Exception as exc:
+            res[key] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            break
+        finally:
+            eng.clip_split, eng.clip_slots = False, 2
+    try:
+        T = h.cfg.MODEL.TRACK_HEAD
+        P = tp.P
+        if eng.s_res != 30 or eng.t_res != 15:
+            raise RuntimeError("planar exchange: S=30, T=15 only")
+        srf = ops.roi_align(P.feats, tp.sr, T.POOLER_SCALES, eng.s_res, T.POOLER_SAMPLING_RATIO, level_boxes=tp.boxes, pads=eng.pads)
+        srp = ops.roi_align_planar(P.feats, tp.sr, T.POOLER_SCALES, eng.s_res, T.POOLER_SAMPLING_RATIO, level_boxes=tp.boxes,
+                                   pads=eng.pads)
+        n, Cc = srf.shape[0], srf.shape[3]
+        rows = srp[:, :, :30 * _lib.XCORR_ROW_PITCH].reshape(n, Cc, 30, _lib.XCORR_ROW_PITCH)
+        same_windows = bool(torch.equal(rows[..., :30].permute(0, 2, 3, 1), srf)) and float(rows[..., 30:32].abs().max()) == 0.0
+        tmpl = tp.tmpl.contiguous()
+        ref = ops.xcorr(srf, tmpl)
+        got = ops.xcorr_planar(srp, tmpl)
+        same_out = bool(torch.equal(ref, got))
+        L = _lib.lib()
+        ev = []
+        for i in range(13):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                check(L.smot_xcorr_planar(ops._ptr(srp), ops._ptr(tmpl), ops._ptr(got), n, Cc, stream_ptr()), "xcorr_planar")
+            b.record()
+            ev.append((a, b))
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) / 20 for a, b in ev[3:]) / max(len(ev) - 3, 1)
+        gbs = xc_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        res["xcorr_planar"] = {"windows_equal_default": same_windows, "output_equal_default": same_out,
+                               "us_per_launch": round(ms * 1e3, 2), "achieved_gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 4),
+                               "algorithmic_bytes": xc_bytes}
+    except Exception as exc:
+        res["xcorr_planar"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    return res
 
 
 # --------------------------------------------------------------------------------------------------
@@ -459,6 +601,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="float16", choices=["float16", "float32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--experimental", default="subprocess", choices=["subprocess", "inproc", "off", "child"],
+                    help="information-only arms for paths that have not had a GPU run yet: in a child process after the line is "
+                         "final (default), in this process under a watchdog (tests), or not at all; 'child' is the child's mode")
     ap.add_argument("--workload", default="720p30", choices=sorted(WORKLOADS),
                     help="720p30 = BASELINE.json configs[1] (the metric's configuration, default); 1080p80 = configs[2]; "
                          "r50_720p30 = configs[4]")
@@ -467,6 +612,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.experimental == "child":
+        run_experimental_child(args)
     else:
         run_ours(args)
 

@@ -280,7 +280,9 @@ def xcorr_planar(x_planar, k, out=None):
     k (n,15,15,C) NHWC fp16 -> (n,16,16,C) NHWC: the output of xcorr() on the same windows, bit for bit."""
     _require_cuda(x_planar, k)
     n, Cc, plane = x_planar.shape
-    assert plane == _lib.XCORR_PLANE and x_planar.dtype == torch.float16 and k.dtype == torch.float16
+    if x_planar.dtype != torch.float16 or k.dtype != torch.float16:
+        raise TypeError("smot_xcorr_planar is the fp16 tensor-core correlation (got %s / %s)" % (x_planar.dtype, k.dtype))
+    assert plane == _lib.XCORR_PLANE
     assert x_planar.is_contiguous() and k.is_contiguous() and tuple(k.shape) == (n, 15, 15, Cc)
     if out is None:
         out = torch.empty((n, 16, 16, Cc), dtype=torch.float16, device=k.device)

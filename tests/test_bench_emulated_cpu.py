@@ -7,13 +7,24 @@ import io
 import json
 import sys
 
+import torch
+
 import cabi_emulator
 
 
 def test_bench_gpu_arm_control_flow_and_json_contract(monkeypatch):
     cabi_emulator.install_for_bench(monkeypatch)
     import bench
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "3", "--dtype", "float32", "--no-cpu-baseline"])
+    from siammot_b200 import _lib, ops
+
+    def xcorr_planar_any_dtype(x_planar, k, out=None):   # the emulation is fp32: lift the wrapper's fp16 requirement
+        n, Cc, _ = x_planar.shape
+        out = torch.empty((n, 16, 16, Cc), dtype=k.dtype) if out is None else out
+        _lib.check(_lib.lib().smot_xcorr_planar(ops._ptr(x_planar), ops._ptr(k), ops._ptr(out), n, Cc, None))
+        return out
+    monkeypatch.setattr(ops, "xcorr_planar", xcorr_planar_any_dtype)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "3", "--dtype", "float32", "--no-cpu-baseline",
+                                      "--experimental", "inproc"])
     buf = io.StringIO()
     try:
         with contextlib.redirect_stdout(buf):
@@ -33,3 +44,25 @@ def test_bench_gpu_arm_control_flow_and_json_contract(monkeypatch):
     r = line["roofline"]
     assert r["bound"] == "hbm" and r["algorithmic_bytes"] == 30 * 128 * 1381 * 4 and 0 < r["frac"]
     assert line["gpu_launches"] > 0
+    # the information-only arms: three-stage clip (K = 2, 3) tracks what the two-stream clip tracks; the planar exchange
+    # reproduces the default kernels' windows and responses
+    ex = line["experimental"]
+    for k in ("three_stage_clip_k2", "three_stage_clip_k3"):
+        assert ex[k].get("same_tracks_as_two_stream") is True, ex[k]
+    assert ex["xcorr_planar"].get("windows_equal_default") is True and ex["xcorr_planar"].get("output_equal_default") is True, ex["xcorr_planar"]
+
+
+def test_bench_experimental_child_mode(monkeypatch):
+    """`bench.py --experimental child` (what the default run launches as a subprocess once its own line is final)."""
+    cabi_emulator.install_for_bench(monkeypatch)
+    import bench
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "3", "--dtype", "float32", "--experimental", "child"])
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            bench.main()
+    finally:
+        bench.select_workload("720p30")
+    ex = json.loads(buf.getvalue().strip().splitlines()[-1])
+    assert ex["three_stage_clip_k2"]["same_tracks_as_two_stream"] is True and ex["three_stage_clip_k3"]["same_tracks_as_two_stream"] is True
+    assert "xcorr_planar" in ex        # fp32 here: the wrapper refuses (TypeError recorded), fp16 on the GPU

@@ -23,23 +23,23 @@ for K in 2 3; do
   SMOT_CLIP_SPLIT=1 SMOT_CLIP_SLOTS=$K timeout 300 python -m pytest tests/test_e2e_gpu.py tests/test_preprocess_gpu.py -m gpu -q \
       -k "forward_clip or raw_frames" > "$OUT/pytest_clip_split_k$K.txt" 2>&1
   echo "rc=$?" >> "$OUT/pytest_clip_split_k$K.txt"
-  SMOT_CLIP_SPLIT=1 SMOT_CLIP_SLOTS=$K timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu-baseline \
+  SMOT_CLIP_SPLIT=1 SMOT_CLIP_SLOTS=$K timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --experimental off \
       > "$OUT/bench_clip_split_k$K.json" 2> "$OUT/bench_clip_split_k$K.err"
 done
 timeout 400 python bench.py --steps 200 --warmup 10 > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
-SMOT_XCORR_PLANAR=1 timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu-baseline > "$OUT/bench_planar.json" 2> "$OUT/bench_planar.err"
-timeout 400 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --workload 1080p80 > "$OUT/bench_1080p80.json" 2> "$OUT/bench_1080p80.err"
-timeout 400 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --workload r50_720p30 > "$OUT/bench_r50.json" 2> "$OUT/bench_r50.err"
+SMOT_XCORR_PLANAR=1 timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --experimental off > "$OUT/bench_planar.json" 2> "$OUT/bench_planar.err"
+timeout 400 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --experimental off --workload 1080p80 > "$OUT/bench_1080p80.json" 2> "$OUT/bench_1080p80.err"
+timeout 400 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --experimental off --workload r50_720p30 > "$OUT/bench_r50.json" 2> "$OUT/bench_r50.err"
 # launch lists (cold-cache, serialised: compare shares), default and planar
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file "$OUT/launches_default.csv" \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_default.log" 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --experimental off > "$OUT/ncu_default.log" 2>&1
 SMOT_XCORR_PLANAR=1 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file "$OUT/launches_planar.csv" \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_planar.log" 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --experimental off > "$OUT/ncu_planar.log" 2>&1
 # one full capture of each roofline-kernel candidate
 SMOT_XCORR_PLANAR=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:xcorr_planar_kernel -c 1 -s 3 \
-    -o "$OUT/xcorr_planar" -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_xcorr_planar.log" 2>&1
+    -o "$OUT/xcorr_planar" -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --experimental off > "$OUT/ncu_xcorr_planar.log" 2>&1
 SMOT_XCORR_PLANAR=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:roi_align_planar_kernel -c 1 -s 3 \
-    -o "$OUT/roi_align_planar" -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_roi_align_planar.log" 2>&1
+    -o "$OUT/roi_align_planar" -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --experimental off > "$OUT/ncu_roi_align_planar.log" 2>&1
 for f in "$OUT"/launches_*.csv; do python tools/launch_report.py "$f" > "${f%.csv}_summary.txt" 2>&1; done
 tail -n 3 "$OUT"/pytest_validated.txt "$OUT"/pytest_pending.txt "$OUT"/smoke.txt
 tail -n 2 "$OUT"/pytest_clip_split_k*.txt
