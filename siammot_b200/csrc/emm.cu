@@ -322,11 +322,17 @@ __global__ void __launch_bounds__(XP_THREADS) xcorr_planar_kernel(const __half* 
   const int g = lane >> 2, t = lane & 3;
   const int c = warp;
   if (!copy_warp) {
-    // bounded wait for the windows: a mis-programmed copy must fail the launch, never hang the GPU
+    // bounded wait for the windows (wall clock, 2 s): a mis-programmed copy must fail the launch, never hang the GPU
+    unsigned long long t_start = 0;
     for (uint32_t spin = 0; !xp_mbar_try_wait(bar, 0); ++spin) {
-      if (spin > (1u << 24)) {
-        printf("smot xcorr_planar: bulk copy wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, tid);
-        __trap();
+      if ((spin & 255u) == 255u) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t_start == 0) t_start = now;
+        if (now - t_start > 2000000000ull) {
+          printf("smot xcorr_planar: bulk copy wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, tid);
+          __trap();
+        }
       }
     }
     // ---- MMA phase: warp = channel (identical to xcorr_mma_kernel)
