@@ -159,3 +159,60 @@ def test_track_combine_grouped_matches_its_cpu_specification():
         torch.cuda.synchronize()
         for k in out_h:
             assert torch.equal(out_d[k].cpu(), out_h[k]), (trial, k)
+
+
+PENDING_R50 = pytest.mark.xfail(strict=False, reason="the R-50-FPN body (engine wiring, smot_maxpool3x3s2) was written after this "
+                                                     "round's GPU budget was spent; host wiring pinned on the CPU, first GPU run pending")
+
+
+@PENDING_R50
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_maxpool3x3s2_matches_torch(dtype):
+    import torch.nn.functional as F
+    from siammot_b200 import ops
+    from test_ops_gpu import DEV, nchw, nhwc, q
+    g = torch.Generator().manual_seed(5)
+    for shape in ((1, 64, 352, 640), (2, 8, 7, 9), (1, 16, 1, 5)):
+        x = q(torch.randn(*shape, generator=g), dtype)
+        ref = F.max_pool2d(x, 3, 2, 1)
+        got = ops.maxpool3x3s2(nhwc(x, dtype))
+        assert torch.equal(nchw(got), ref), shape            # a max of storage-type values is exact
+    # channel-slice operands (pitch > channels) on both sides
+    x = q(torch.randn(1, 24, 10, 12, generator=g), dtype)
+    wide_in = nhwc(x, dtype)
+    wide_out = torch.zeros((1, 5, 6, 32), dtype=dtype, device=DEV)
+    ops.maxpool3x3s2(wide_in[..., 8:24], out=wide_out[..., 4:20])
+    assert torch.equal(nchw(wide_out[..., 4:20]), F.max_pool2d(x[:, 8:24], 3, 2, 1))
+    assert float(wide_out[..., :4].abs().max()) == 0.0 and float(wide_out[..., 20:].abs().max()) == 0.0
+
+
+@PENDING_R50
+def test_r50_body_features_match_oracle_fp32_and_fp16():
+    """FPN maps of the R-50-FPN plan against the oracle (fp32: summation-order tolerance; fp16 storage: 2e-2 of the map's scale
+    through 53 convolutions)."""
+    from oracle.siammot_oracle import OracleSiamMOT
+    from test_e2e_gpu import build_model
+    for dtype, tol_ in (("float32", 1e-4), ("float16", 2e-2)):
+        cfg, model, clip = build_model("emm_r50_192x320", dtype)
+        eng = model.engine()
+        P = eng.run_static(clip[0].to("cuda"))
+        torch.cuda.synchronize()
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        ref = OracleSiamMOT(cfg, sd).features(clip[0])
+        for l, (got, want) in enumerate(zip(P.feats, ref)):
+            got = got.permute(0, 3, 1, 2).float().cpu()
+            assert got.shape == want.shape
+            err = float((got - want).abs().max() / want.abs().max())
+            assert err <= tol_, "%s FPN level %d: relative error %g" % (dtype, l, err)
+
+
+@PENDING_R50
+def test_r50_fp16_tracks_close_to_reference():
+    from test_e2e_gpu import run_engine_scenario
+    name = "emm_r50_192x320"
+    gold = load_golden(name)["frames"]
+    got = run_engine_scenario(name, "float16")
+    g0, o0 = gold[0], got[0]
+    n = min(len(g0["ids"]), len(o0["ids"]))
+    assert abs(len(g0["ids"]) - len(o0["ids"])) <= max(3, len(g0["ids"]) // 10)
+    assert int((g0["ids"][:n] == o0["ids"][:n]).sum()) >= 0.8 * n
