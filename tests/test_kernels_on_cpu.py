@@ -1,0 +1,100 @@
+"""Source text of the simple kernels written without GPU access, executed on the host (tests/cpu_cuda/shim.h: a block's threads
+are OS threads, __syncthreads is a barrier) and compared with the oracle / the C-ABI emulator's specification:
+roi_align_planar_kernel<float>, maxpool3x3s2_kernel<float>, track_combine_grouped_kernel.  The tensor-core / bulk-copy kernel
+(xcorr_planar_kernel) cannot be run this way and stays GPU-only."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "cpu_cuda"))
+
+
+@pytest.fixture(scope="module")
+def cpu_kernels():
+    import build as cpu_build
+    return C.CDLL(cpu_build.build())
+
+
+def p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+@pytest.mark.parametrize("res,row_pitch,plane", [(30, 40, 1208), (15, 16, 240)])
+def test_roi_align_planar_kernel_source_matches_oracle(cpu_kernels, res, row_pitch, plane):
+    from oracle import siammot_oracle as orc
+    from siammot_b200._lib import Pyramid
+    g = torch.Generator().manual_seed(3)
+    Cc, H, W = 136, 24, 40                 # two channel passes per lane (c += 128) and a ragged last one
+    feats = [torch.randn(1, Cc, H >> i, W >> i, generator=g) for i in range(4)]
+    nhwc = [f.permute(0, 2, 3, 1).contiguous() for f in feats]
+    boxes = torch.tensor([[10., 20., 60., 90.], [-30., -20., 40., 50.], [5., 5., 150., 90.], [100., 30., 158., 95.], [70., 10., 71., 11.]])
+    pad = 64
+    sr = orc.search_region(boxes, pad, 1.0, 0)
+    pads = [int(pad / ((2 ** i) * 4)) for i in range(4)]
+    pyr = Pyramid()
+    pyr.num_levels, pyr.k_min = 4, 2
+    for l in range(4):
+        pyr.feat[l], pyr.H[l], pyr.W[l], pyr.ld[l] = nhwc[l].data_ptr(), H >> l, W >> l, Cc
+        pyr.scale[l], pyr.pad[l] = 0.25 / (2 ** l), pads[l]
+    n = boxes.shape[0]
+    count = torch.tensor([4], dtype=torch.int32)      # the last roi is past the device-side count: zero rows
+    out = torch.full((n, Cc, plane), 7.0)
+    cpu_kernels.cpu_roi_align_planar(C.byref(pyr), p(sr), p(boxes), p(count), n, Cc, res, 2, p(out), row_pitch, plane)
+    ref = orc.pool_rois(orc.pad_features(feats, pad), boxes[:4], boxes[:4], (0.25, 0.125, 0.0625, 0.03125), res, 2, rois=sr[:4])
+    # the GPU-validated NHWC kernel through the same shim: same arithmetic, so the two kernels must agree exactly (this also
+    # validates the shim on a kernel whose GPU behaviour is known)
+    nhwc_out = torch.full((n, res, res, Cc), 7.0)
+    cpu_kernels.cpu_roi_align(C.byref(pyr), p(sr), p(boxes), p(count), n, Cc, res, 2, p(nhwc_out))
+    assert float((nhwc_out[:4].permute(0, 3, 1, 2) - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    assert torch.equal(out[:, :, :res * row_pitch].reshape(n, Cc, res, row_pitch)[..., :res], nhwc_out.permute(0, 3, 1, 2))
+    rows = out[:, :, :res * row_pitch].reshape(n, Cc, res, row_pitch)
+    got = rows[..., :res]
+    assert float((got[:4] - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    assert float(got[4].abs().max()) == 0.0                                   # past the count
+    assert float((rows[..., res:] - 7.0).abs().max()) == 0.0                  # pad columns never written
+    assert float((out[:, :, res * row_pitch:] - 7.0).abs().max()) == 0.0 if plane > res * row_pitch else True
+
+
+def test_maxpool3x3s2_kernel_source_matches_torch(cpu_kernels):
+    g = torch.Generator().manual_seed(4)
+    for B, Cc, H, W in ((1, 8, 13, 18), (2, 4, 6, 5), (1, 12, 1, 7)):
+        x = torch.randn(B, Cc, H, W, generator=g)
+        ref = F.max_pool2d(x, 3, 2, 1)
+        xin = torch.zeros(B, H, W, Cc + 4)
+        xin[..., 4:] = x.permute(0, 2, 3, 1)
+        out = torch.full((B, ref.shape[2], ref.shape[3], Cc + 8), 7.0)
+        cpu_kernels.cpu_maxpool3x3s2(C.c_void_p(xin.data_ptr() + 16), C.c_void_p(out.data_ptr() + 16), B, H, W, Cc, Cc + 4, Cc + 8)
+        assert torch.equal(out[..., 4:4 + Cc].permute(0, 3, 1, 2), ref)
+        assert float((out[..., :4] - 7.0).abs().max()) == 0.0 and float((out[..., 4 + Cc:] - 7.0).abs().max()) == 0.0
+
+
+def test_track_combine_grouped_kernel_source_matches_specification(cpu_kernels):
+    import cabi_emulator as ce
+    spec = ce.FakeLib()
+    rng = np.random.default_rng(1)
+    for trial in range(60):
+        n, ncap, ncls = int(rng.integers(1, 70)), int(rng.integers(0, 40)), int(rng.integers(3, 6))
+        tracktor = int(rng.integers(0, 2))
+        src = dict(det_boxes=torch.rand(max(ncap, 1), 4), det_scores=torch.rand(max(ncap, 1)), dec_boxes=torch.rand(n, ncls, 4),
+                   dec_scores=torch.rand(n, ncls), labels=torch.tensor(rng.integers(1, ncls, n), dtype=torch.int32),
+                   conf=torch.rand(n), valid=torch.tensor(rng.integers(0, 2, n), dtype=torch.int32),
+                   active=torch.tensor(rng.integers(0, 2, n), dtype=torch.float32))
+        outs = []
+        for which in ("spec", "kernel"):
+            o = dict(cb=torch.full((ncap + n, 4), 9.), cs=torch.full((ncap + n,), 9.), zc=torch.tensor([5], dtype=torch.int32),
+                     perm=torch.full((n,), 7, dtype=torch.int32))
+            args = (p(src["det_boxes"]), p(src["det_scores"]), ncap, p(src["dec_boxes"]), p(src["dec_scores"]), ncls, p(src["labels"]),
+                    p(src["conf"]), p(src["valid"]), p(src["active"]), n, tracktor, p(o["cb"]), p(o["cs"]), p(o["zc"]), p(o["perm"]))
+            if which == "spec":
+                spec.smot_track_combine_grouped(*args, None)
+            else:
+                cpu_kernels.cpu_track_combine_grouped(*args)
+            outs.append(o)
+        for k in outs[0]:
+            assert torch.equal(outs[0][k], outs[1][k]), (trial, k)
