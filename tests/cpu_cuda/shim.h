@@ -17,10 +17,20 @@
 #include <thread>
 #include <vector>
 
+#ifdef SHIM_WITH_CUDA_FP16
+// kernels that use __half / uint4: CUDA's own host-compilable vector and fp16 headers (plain g++ takes them)
+#include <vector_types.h>
+#include <vector_functions.h>
+#include <cuda_fp16.h>
+#undef __forceinline__
+#undef __launch_bounds__
+#undef __align__
+#else
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+#endif
 
 static thread_local uint3 cpu_threadIdx, cpu_blockIdx;
 static uint3 cpu_blockDim, cpu_gridDim;
@@ -30,12 +40,14 @@ static std::barrier<>* cpu_barrier = nullptr;
 #define blockDim cpu_blockDim
 #define gridDim cpu_gridDim
 
+#ifndef SHIM_WITH_CUDA_FP16
 #define __global__
 #define __device__
 #define __host__
+#define __shared__
+#endif
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__
 #define __align__(n) alignas(n)
 static inline void __syncthreads() { cpu_barrier->arrive_and_wait(); }
 static inline float __fdiv_rn(float a, float b) { return a / b; }

@@ -98,3 +98,40 @@ def test_track_combine_grouped_kernel_source_matches_specification(cpu_kernels):
             outs.append(o)
         for k in outs[0]:
             assert torch.equal(outs[0][k], outs[1][k]), (trial, k)
+
+
+@pytest.fixture(scope="module")
+def cpu_xcorr():
+    import build as cpu_build
+    if not os.path.exists(os.path.join(cpu_build.CUDA_INCLUDE, "cuda_fp16.h")):
+        pytest.skip("CUDA headers not found (cuda_fp16.h is compiled in host mode)")
+    return C.CDLL(cpu_build.build_xcorr())
+
+
+@pytest.mark.parametrize("n,Cc", [(2, 32), (1, 16)])
+def test_xcorr_kernels_source_under_ptx_emulation(cpu_xcorr, n, Cc):
+    """csrc/emm.cu's tensor-core correlation kernels, source text, with ldmatrix / mma.sync / mbarrier / cp.async.bulk emulated
+    on the host (tests/cpu_cuda/shim_tc.h).  xcorr_mma_kernel is validated on the B200: its agreement with the oracle here
+    validates the emulation.  xcorr_planar_kernel (written without GPU access: bulk-copy staging from channel-planar windows,
+    17th warp, mbarrier) must then reproduce xcorr_mma_kernel's output bit for bit."""
+    from oracle import siammot_oracle as orc
+    from siammot_b200 import _lib
+    g = torch.Generator().manual_seed(n * 100 + Cc)
+    x = torch.randn(n, Cc, 30, 30, generator=g).half()
+    k = (torch.randn(n, Cc, 15, 15, generator=g) / 15.).half()
+    ref = orc.xcorr_depthwise(x.float(), k.float())
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    k_nhwc = k.permute(0, 2, 3, 1).contiguous()
+    out_mma = torch.zeros(n, 16, 16, Cc, dtype=torch.float16)
+    cpu_xcorr.cpu_xcorr_mma(p(x_nhwc), p(k_nhwc), p(out_mma), n, Cc)
+    err = float((out_mma.permute(0, 3, 1, 2).float() - ref).abs().max() / ref.abs().max())
+    assert err <= 2e-3, "emulated xcorr_mma_kernel vs oracle: %g" % err
+    PL, RP = _lib.XCORR_PLANE, _lib.XCORR_ROW_PITCH
+    assert cpu_xcorr.cpu_xcorr_plane_halves() == PL
+    xp = torch.full((n, Cc, PL), 77.0, dtype=torch.float16)                    # never-read halves hold garbage
+    rows = xp[:, :, :30 * RP].view(n, Cc, 30, RP)
+    rows[..., :30] = x
+    rows[..., 30:32] = 0.0                                                     # the producer's zero columns
+    out_planar = torch.zeros(n, 16, 16, Cc, dtype=torch.float16)
+    cpu_xcorr.cpu_xcorr_planar(p(xp), p(k_nhwc), p(out_planar), n, Cc)
+    assert torch.equal(out_planar, out_mma)
