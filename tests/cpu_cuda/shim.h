@@ -68,6 +68,23 @@ template <typename T> inline T from_f(float v);
 template <> inline float from_f<float>(float v) { return v; }
 inline float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 inline void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+#ifdef SHIM_WITH_CUDA_FP16
+inline float to_f(__half v) { return __half2float(v); }
+template <> inline __half from_f<__half>(float v) { return __float2half_rn(v); }
+inline float4 ld4(const __half* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  float2 a = __half22float2(*reinterpret_cast<__half2*>(&r.x));
+  float2 b = __half22float2(*reinterpret_cast<__half2*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+inline void st4(__half* p, float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+#endif
 }  // namespace smot
 
 // run `body` for every thread of every block

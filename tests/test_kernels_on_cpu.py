@@ -135,3 +135,38 @@ def test_xcorr_kernels_source_under_ptx_emulation(cpu_xcorr, n, Cc):
     out_planar = torch.zeros(n, 16, 16, Cc, dtype=torch.float16)
     cpu_xcorr.cpu_xcorr_planar(p(xp), p(k_nhwc), p(out_planar), n, Cc)
     assert torch.equal(out_planar, out_mma)
+
+
+def test_fp16_instantiations_of_the_simple_kernels(cpu_xcorr):
+    """The fp16 instantiations the fp16 engine actually launches: planar ROIAlign == the validated NHWC kernel bit for bit,
+    3x3/2 max-pool == torch."""
+    from oracle import siammot_oracle as orc
+    from siammot_b200 import _lib
+    from siammot_b200._lib import Pyramid
+    g = torch.Generator().manual_seed(9)
+    Cc, H, W = 32, 24, 40
+    feats = [torch.randn(1, Cc, H >> i, W >> i, generator=g).half() for i in range(4)]
+    nhwc = [f.permute(0, 2, 3, 1).contiguous() for f in feats]
+    boxes = torch.tensor([[10., 20., 60., 90.], [-30., -20., 40., 50.], [100., 30., 158., 95.]])
+    pad = 64
+    sr = orc.search_region(boxes, pad, 1.0, 0)
+    pyr = Pyramid()
+    pyr.num_levels, pyr.k_min = 4, 2
+    for l in range(4):
+        pyr.feat[l], pyr.H[l], pyr.W[l], pyr.ld[l] = nhwc[l].data_ptr(), H >> l, W >> l, Cc
+        pyr.scale[l], pyr.pad[l] = 0.25 / (2 ** l), int(pad / ((2 ** l) * 4))
+    n, res, RP, PL = 3, 30, _lib.XCORR_ROW_PITCH, _lib.XCORR_PLANE
+    ref = torch.zeros(n, res, res, Cc, dtype=torch.float16)
+    cpu_xcorr.cpu_roi_align_h(C.byref(pyr), p(sr), p(boxes), None, n, Cc, res, 2, p(ref))
+    want = orc.pool_rois(orc.pad_features([f.float() for f in feats], pad), boxes, boxes, (0.25, 0.125, 0.0625, 0.03125), res, 2, rois=sr)
+    assert float((ref.permute(0, 3, 1, 2).float() - want).abs().max()) <= 2e-3 * float(want.abs().max())
+    planes = torch.zeros(n, Cc, PL, dtype=torch.float16)
+    cpu_xcorr.cpu_roi_align_planar_h(C.byref(pyr), p(sr), p(boxes), None, n, Cc, res, 2, p(planes), RP, PL)
+    rows = planes[:, :, :res * RP].view(n, Cc, res, RP)
+    assert torch.equal(rows[..., :res], ref.permute(0, 3, 1, 2))
+    assert float(rows[..., res:].abs().max()) == 0.0 and float(planes[:, :, res * RP:].abs().max()) == 0.0
+    x = torch.randn(1, 8, 9, 14, generator=g).half()
+    out = torch.zeros(1, 5, 7, 8, dtype=torch.float16)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()       # keep it alive across the call
+    cpu_xcorr.cpu_maxpool3x3s2_h(p(x_nhwc), p(out), 1, 9, 14, 8, 8, 8)
+    assert torch.equal(out.permute(0, 3, 1, 2), F.max_pool2d(x.float(), 3, 2, 1).half())
