@@ -509,20 +509,23 @@ def experimental_arms(h, args, frames_dev, frames_u8, hook, ntrk_ref, tp, hbm_pe
         got = ops.xcorr_planar(srp, tmpl)
         same_out = bool(torch.equal(ref, got))
         L = _lib.lib()
-        ev = []
-        for i in range(13):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(20):
-                check(L.smot_xcorr_planar(ops._ptr(srp), ops._ptr(tmpl), ops._ptr(got), n, Cc, stream_ptr()), "xcorr_planar")
-            b.record()
-            ev.append((a, b))
-        torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) / 20 for a, b in ev[3:]) / max(len(ev) - 3, 1)
-        gbs = xc_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        res["xcorr_planar"] = {"windows_equal_default": same_windows, "output_equal_default": same_out,
-                               "us_per_launch": round(ms * 1e3, 2), "achieved_gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 4),
-                               "algorithmic_bytes": xc_bytes}
+        res["xcorr_planar"] = {"windows_equal_default": same_windows, "output_equal_default": same_out, "algorithmic_bytes": xc_bytes}
+        for mode, key in ((0, "mma_phase_of_default_kernel"), (1, "trimmed_mma_phase")):
+            trim = ops.xcorr_planar(srp, tmpl, mma_mode=mode)
+            close = float((trim.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-6))
+            ev = []
+            for i in range(13):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(20):
+                    check(L.smot_xcorr_planar_mode(ops._ptr(srp), ops._ptr(tmpl), ops._ptr(got), n, Cc, mode, stream_ptr()), "xcorr_planar")
+                b.record()
+                ev.append((a, b))
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) / 20 for a, b in ev[3:]) / max(len(ev) - 3, 1)
+            gbs = xc_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            res["xcorr_planar"][key] = {"us_per_launch": round(ms * 1e3, 2), "achieved_gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 4),
+                                        "max_rel_diff_vs_default": round(close, 6)}
     except Exception as exc:
         res["xcorr_planar"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     return res

@@ -197,6 +197,10 @@ int smot_roi_align_planar(const smot_pyramid* pyr, const float* rois, const floa
                           int max_rois, int channels, int res, int sampling_ratio, void* out, int row_pitch,
                           int plane_pitch, int dtype, void* stream);
 int smot_xcorr_planar(const void* x_planar, const void* k, void* out, int n, int channels, void* stream);
+/* The same with the MMA phase chosen explicitly: 0 = xcorr_mma_kernel's (bit-identical to smot_xcorr), 1 = trimmed (m16n8k8 on
+ * the live operand halves, fragments shared between template rows u and u+8; equal to fp16 rounding).  smot_xcorr_planar
+ * takes 1 when the environment has SMOT_XCORR_PLANAR=2, else 0. */
+int smot_xcorr_planar_mode(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode, void* stream);
 
 /* smot_emm_decode: fused bicubic x`up` upsampling (track_core.py:69-71) + get_locations (:184-225) +
  * decode_response (:101-135) + clip/validity of wrap_results_to_boxlist (:165-181).

@@ -13,6 +13,8 @@
 //   memory, vertical pass in registers), evaluates the penalised score per pixel and keeps only the
 //   arg-max (packed 64-bit atomicMax: score bits << 32 | ~index, so ties resolve to the first index
 //   like torch.argmax).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace smot {
@@ -212,6 +214,15 @@ __global__ void __launch_bounds__(XM_WARPS * 32) xcorr_mma_kernel(const __half* 
   }
 }
 
+__device__ __forceinline__ void xm_ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void xm_mma_k8(float* c, uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(b0));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Planar-input form of the tensor-core correlation (developer switch SMOT_XCORR_PLANAR).
 //
@@ -259,6 +270,15 @@ __device__ __forceinline__ void xp_bulk_g2s(uint32_t dst, const void* src, uint3
                : "memory");
 }
 
+// MMA_MODE 0: the MMA phase of xcorr_mma_kernel, instruction for instruction (bit-identical results).
+// MMA_MODE 1 (SMOT_XCORR_PLANAR=2): the same contraction with the structurally-zero work removed --
+//   * of the four m16n8k16 per template row, two have an all-zero B half (taps d0-8 and d0+24 do not exist): they become
+//     m16n8k8 on the live half (window columns 8..15 for output columns 8..15, 16..23 for output columns 0..7): 3 instead of
+//     4 k16-equivalents per row, -25 % tensor work;
+//   * template rows u and u+8 read window rows u..u+15 and u+8..u+23: the second block of the first is the first block of
+//     the second, so the pair costs ldmatrix x4 + x2 per column half instead of 2 x4 (-25 % shared-memory wavefronts).
+//   The accumulation order differs from mode 0 (fp32 rounding), so the results agree to fp16 rounding, not bit for bit.
+template <int MMA_MODE>
 __global__ void __launch_bounds__(XP_THREADS) xcorr_planar_kernel(const __half* __restrict__ xp, const __half* __restrict__ k,
                                                                   __half* __restrict__ out, int C) {
   constexpr int S = 30, TT = 15, O = 16;
@@ -344,16 +364,47 @@ __global__ void __launch_bounds__(XP_THREADS) xcorr_planar_kernel(const __half* 
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    if constexpr (MMA_MODE == 0) {
 #pragma unroll 5
-    for (int u = 0; u < TT; ++u) {
-      const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
-      uint32_t af[4];
-      xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2), af[0], af[1], af[2], af[3]);
-      xm_mma(acc[0], af, k0, k8);
-      xm_mma(acc[1], af, 0u, k0);
-      xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2 + 32), af[0], af[1], af[2], af[3]);
-      xm_mma(acc[0], af, k16, 0u);
-      xm_mma(acc[1], af, k8, k16);
+      for (int u = 0; u < TT; ++u) {
+        const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
+        uint32_t af[4];
+        xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2), af[0], af[1], af[2], af[3]);
+        xm_mma(acc[0], af, k0, k8);
+        xm_mma(acc[1], af, 0u, k0);
+        xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2 + 32), af[0], af[1], af[2], af[3]);
+        xm_mma(acc[0], af, k16, 0u);
+        xm_mma(acc[1], af, k8, k16);
+      }
+    } else {
+      // one template row: window rows [u, u+16) as fragments lo (cols 0..15) / hi (cols 16..31)
+      auto row_step = [&](const uint32_t* lo, const uint32_t* hi, int u) {
+        const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
+        xm_mma(acc[0], lo, k0, k8);              // out cols 0..7  <- window cols 0..15
+        xm_mma_k8(acc[1], lo[2], lo[3], k0);     // out cols 8..15 <- window cols 8..15   (cols 0..7 meet no tap)
+        xm_mma_k8(acc[0], hi[0], hi[1], k16);    // out cols 0..7  <- window cols 16..23  (cols 24..31 meet no tap)
+        xm_mma(acc[1], hi, k8, k16);             // out cols 8..15 <- window cols 16..31
+      };
+      // lanes 0..15 address the x2 loads: rows (lane & 7) + 16 of the pair's 24-row span, column half (lane >> 3) & 1
+      const uint32_t a_x2 = (uint32_t)__cvta_generic_to_shared(xT + c * XM_CSTRIDE + ((lane & 7) + 16) * XM_PITCH + ((lane >> 3) & 1) * 8);
+#pragma unroll
+      for (int u = 0; u < 7; ++u) {
+        uint32_t lo[4], hi[4], lo2[4], hi2[4];
+        xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2), lo[0], lo[1], lo[2], lo[3]);
+        xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2 + 32), hi[0], hi[1], hi[2], hi[3]);
+        // rows u+8..u+15 are the second row block of the fragments above; rows u+16..u+23 are new
+        lo2[0] = lo[1], lo2[2] = lo[3], hi2[0] = hi[1], hi2[2] = hi[3];
+        xm_ldmatrix_x2(a_x2 + (uint32_t)(u * XM_PITCH * 2), lo2[1], lo2[3]);
+        xm_ldmatrix_x2(a_x2 + (uint32_t)(u * XM_PITCH * 2 + 32), hi2[1], hi2[3]);
+        row_step(lo, hi, u);
+        row_step(lo2, hi2, u + 8);
+      }
+      {
+        uint32_t lo[4], hi[4];
+        xm_ldmatrix_x4(a_s + (uint32_t)(7 * XM_PITCH * 2), lo[0], lo[1], lo[2], lo[3]);
+        xm_ldmatrix_x4(a_s + (uint32_t)(7 * XM_PITCH * 2 + 32), hi[0], hi[1], hi[2], hi[3]);
+        row_step(lo, hi, 7);
+      }
     }
     // ---- D fragments -> the warp's own (now dead) window plane as [O*O] halves
     __syncwarp();
@@ -609,16 +660,38 @@ extern "C" int smot_xcorr(const void* x, const void* k, void* out, int n, int ch
   return SMOT_OK;
 }
 
+// developer switch: SMOT_XCORR_PLANAR=2 selects the trimmed MMA phase (read once)
+static bool xcorr_planar_trimmed() {
+  static const bool on = [] {
+    const char* e = getenv("SMOT_XCORR_PLANAR");
+    return e && e[0] == '2';
+  }();
+  return on;
+}
+
 extern "C" int smot_xcorr_planar(const void* x_planar, const void* k, void* out, int n, int channels, void* stream) {
+  return smot_xcorr_planar_mode(x_planar, k, out, n, channels, xcorr_planar_trimmed() ? 1 : 0, stream);
+}
+
+extern "C" int smot_xcorr_planar_mode(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode,
+                                      void* stream) {
+  SMOT_CHECK_ARG(mma_mode == 0 || mma_mode == 1, "smot_xcorr_planar: mma_mode %d", mma_mode);
   SMOT_CHECK_ARG(n >= 0 && channels > 0 && channels % XM_CG == 0, "smot_xcorr_planar: bad geometry n=%d C=%d (C must be a multiple of %d)",
                  n, channels, XM_CG);
   if (n == 0) return SMOT_OK;
   SMOT_CHECK_ARG(x_planar && k && out, "smot_xcorr_planar: null argument");
   SMOT_CHECK_ARG((((uintptr_t)x_planar | (uintptr_t)k | (uintptr_t)out) & 15) == 0, "smot_xcorr_planar: operands must be 16-byte aligned");
   static_assert(XM_CSTRIDE == SMOT_XCORR_PLANE && XM_PITCH == SMOT_XCORR_ROW_PITCH, "smot.h states the plane layout");
-  SMOT_ENSURE_SMEM(xcorr_planar_kernel, XP_SMEM, "smot_xcorr_planar");
-  cudaError_t e = launch_pdl(xcorr_planar_kernel, dim3(channels / XM_CG, n), dim3(XP_THREADS), XP_SMEM, (cudaStream_t)stream,
-                             (const __half*)x_planar, (const __half*)k, (__half*)out, channels);
+  cudaError_t e;
+  if (mma_mode == 1) {
+    SMOT_ENSURE_SMEM(xcorr_planar_kernel<1>, XP_SMEM, "smot_xcorr_planar");
+    e = launch_pdl(xcorr_planar_kernel<1>, dim3(channels / XM_CG, n), dim3(XP_THREADS), XP_SMEM, (cudaStream_t)stream,
+                   (const __half*)x_planar, (const __half*)k, (__half*)out, channels);
+  } else {
+    SMOT_ENSURE_SMEM(xcorr_planar_kernel<0>, XP_SMEM, "smot_xcorr_planar");
+    e = launch_pdl(xcorr_planar_kernel<0>, dim3(channels / XM_CG, n), dim3(XP_THREADS), XP_SMEM, (cudaStream_t)stream,
+                   (const __half*)x_planar, (const __half*)k, (__half*)out, channels);
+  }
   if (e != cudaSuccess) {
     set_error("smot_xcorr_planar: launch failed: %s", cudaGetErrorString(e));
     return SMOT_ERR_CUDA;

@@ -427,7 +427,7 @@ class Engine(object):
         self._arenas = {}
         # developer switch: exchange the EMM search windows channel-planar (smot_roi_align_planar ->
         # smot_xcorr_planar).  Off by default until it has been through the GPU tests.
-        self.xcorr_planar = os.environ.get("SMOT_XCORR_PLANAR", "0") == "1"
+        self.xcorr_planar = os.environ.get("SMOT_XCORR_PLANAR", "0") in ("1", "2")   # 2: + trimmed MMA phase (libsmot reads it)
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
         self.time_kernels = False  # also bracket single kernels of the track stage (forces its eager path)
 

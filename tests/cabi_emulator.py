@@ -317,6 +317,9 @@ class FakeLib(object):
             _view(_a(out), n, O, O, Cc, Cc).copy_(y.permute(0, 2, 3, 1))
         return 0
 
+    def smot_xcorr_planar_mode(self, xp, k, out, n, Cc, mma_mode, st):
+        return self.smot_xcorr_planar(xp, k, out, n, Cc, st)
+
     def smot_emm_decode(self, maps, map_ld, n, O, up, T, sr, tboxes, hann, pad, use_centerness, sigma, img_w, img_h, amodal,
                         out_boxes, out_conf, out_valid, scratch, st):
         self._count("smot_emm_decode")

@@ -50,6 +50,38 @@ inline void xm_ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& 
   r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3];
 }
 
+// ldmatrix .x2: lanes 0..7 / 8..15 give the row addresses of matrices 0 / 1 (the other lanes' addresses are ignored)
+inline void xm_ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  CpuWarp& w = cpu_my_warp();
+  const int lane = threadIdx.x & 31;
+  w.addr[lane] = addr;
+  w.bar->arrive_and_wait();
+  uint32_t r[2];
+  for (int i = 0; i < 2; ++i)
+    std::memcpy(&r[i], cpu_dynamic_smem + w.addr[i * 8 + (lane >> 2)] + (lane & 3) * 4, 4);
+  w.bar->arrive_and_wait();
+  r0 = r[0], r1 = r[1];
+}
+
+// mma.m16n8k8: a0 (g, 2t..) a1 (g+8, 2t..); b0 (k = 2t.., n = g); c as for k16
+inline void xm_mma_k8(float* c, uint32_t a0, uint32_t a1, uint32_t b0) {
+  CpuWarp& w = cpu_my_warp();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  w.a[lane][0] = a0, w.a[lane][1] = a1, w.b[lane][0] = b0;
+  w.bar->arrive_and_wait();
+  auto A = [&](int r, int k) { return cpu_h2f(w.a[(r & 7) * 4 + (k >> 1)][r >= 8 ? 1 : 0], k & 1); };
+  auto B = [&](int k, int n) { return cpu_h2f(w.b[n * 4 + (k >> 1)][0], k & 1); };
+  float d[4];
+  for (int e = 0; e < 4; ++e) {
+    const int r = g + (e >= 2 ? 8 : 0), n = 2 * t + (e & 1);
+    float acc = c[e];
+    for (int k = 0; k < 8; ++k) acc += A(r, k) * B(k, n);
+    d[e] = acc;
+  }
+  w.bar->arrive_and_wait();
+  for (int e = 0; e < 4; ++e) c[e] = d[e];
+}
+
 inline void xm_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   CpuWarp& w = cpu_my_warp();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;

@@ -17,7 +17,7 @@ def test_bench_gpu_arm_control_flow_and_json_contract(monkeypatch):
     import bench
     from siammot_b200 import _lib, ops
 
-    def xcorr_planar_any_dtype(x_planar, k, out=None):   # the emulation is fp32: lift the wrapper's fp16 requirement
+    def xcorr_planar_any_dtype(x_planar, k, out=None, mma_mode=None):   # the emulation is fp32: lift the wrapper's fp16 requirement
         n, Cc, _ = x_planar.shape
         out = torch.empty((n, 16, 16, Cc), dtype=k.dtype) if out is None else out
         _lib.check(_lib.lib().smot_xcorr_planar(ops._ptr(x_planar), ops._ptr(k), ops._ptr(out), n, Cc, None))

@@ -133,8 +133,17 @@ def test_xcorr_kernels_source_under_ptx_emulation(cpu_xcorr, n, Cc):
     rows[..., :30] = x
     rows[..., 30:32] = 0.0                                                     # the producer's zero columns
     out_planar = torch.zeros(n, 16, 16, Cc, dtype=torch.float16)
-    cpu_xcorr.cpu_xcorr_planar(p(xp), p(k_nhwc), p(out_planar), n, Cc)
+    cpu_xcorr.cpu_xcorr_planar(p(xp), p(k_nhwc), p(out_planar), n, Cc, 0)
     assert torch.equal(out_planar, out_mma)
+    # MMA_MODE 1 (SMOT_XCORR_PLANAR=2): m16n8k8 on the live halves, fragments shared between template rows u and u+8 --
+    # another accumulation order, so equality holds to fp16 rounding: the oracle bar, and at most one fp16 ulp from mode 0
+    out_trim = torch.zeros(n, 16, 16, Cc, dtype=torch.float16)
+    cpu_xcorr.cpu_xcorr_planar(p(xp), p(k_nhwc), p(out_trim), n, Cc, 1)
+    err = float((out_trim.permute(0, 3, 1, 2).float() - ref).abs().max() / ref.abs().max())
+    assert err <= 2e-3, "emulated trimmed planar kernel vs oracle: %g" % err
+    d = (out_trim.float() - out_mma.float()).abs()
+    assert float((d / out_mma.float().abs().clamp_min(2e-2)).max()) <= 1.1e-3      # one fp16 ulp (2^-10) of the larger values
+    assert float((d > 0).float().mean()) < 0.05                                    # and rare
 
 
 def test_fp16_instantiations_of_the_simple_kernels(cpu_xcorr):

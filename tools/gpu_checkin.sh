@@ -28,6 +28,7 @@ for K in 2 3; do
 done
 timeout 400 python bench.py --steps 200 --warmup 10 > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
 SMOT_XCORR_PLANAR=1 timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --experimental off > "$OUT/bench_planar.json" 2> "$OUT/bench_planar.err"
+SMOT_XCORR_PLANAR=2 timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --experimental off > "$OUT/bench_planar_trimmed.json" 2> "$OUT/bench_planar_trimmed.err"
 timeout 400 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --experimental off --workload 1080p80 > "$OUT/bench_1080p80.json" 2> "$OUT/bench_1080p80.err"
 timeout 400 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --experimental off --workload r50_720p30 > "$OUT/bench_r50.json" 2> "$OUT/bench_r50.err"
 # launch lists (cold-cache, serialised: compare shares), default and planar
