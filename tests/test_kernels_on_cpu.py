@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(HERE, "cpu_cuda"))
 
 @pytest.fixture(scope="module")
 def cpu_kernels():
-    import build as cpu_build
+    import cpu_cuda_build as cpu_build
     return C.CDLL(cpu_build.build())
 
 
@@ -102,7 +102,7 @@ def test_track_combine_grouped_kernel_source_matches_specification(cpu_kernels):
 
 @pytest.fixture(scope="module")
 def cpu_xcorr():
-    import build as cpu_build
+    import cpu_cuda_build as cpu_build
     if not os.path.exists(os.path.join(cpu_build.CUDA_INCLUDE, "cuda_fp16.h")):
         pytest.skip("CUDA headers not found (cuda_fp16.h is compiled in host mode)")
     return C.CDLL(cpu_build.build_xcorr())
