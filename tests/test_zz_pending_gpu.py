@@ -220,3 +220,30 @@ def test_r50_fp16_tracks_close_to_reference():
     n = min(len(g0["ids"]), len(o0["ids"]))
     assert abs(len(g0["ids"]) - len(o0["ids"])) <= max(3, len(g0["ids"]) // 10)
     assert int((g0["ids"][:n] == o0["ids"][:n]).sum()) >= 0.8 * n
+
+
+@pytest.mark.xfail(strict=False, reason="forward_clip's three-stage mode (SMOT_CLIP_SPLIT) was written after this round's GPU budget "
+                                       "was spent; results and stream ordering are pinned on the CPU (tests/test_engine_emulated_cpu.py, "
+                                       "tests/test_stream_order_cpu.py); first GPU run pending")
+@pytest.mark.parametrize("slots", ["2", "3"])
+def test_three_stage_clip_equals_frame_by_frame(slots, monkeypatch):
+    """SMOT_CLIP_SPLIT=1: backbone half of frame t+1 / detection tail of frame t / track stage of frame t on three streams,
+    K plan copies, one CUDA graph per half -- exactly the per-frame results, twice in a row (graph capture, then replay)."""
+    from test_e2e_gpu import build_model
+    name = "emm_256x384"
+    monkeypatch.setenv("SMOT_CLIP_SPLIT", "0")
+    cfg, model, clip = build_model(name, "float32")
+    model.reset_siammot_status()
+    ref = [model(f.to("cuda"))[0] for f in clip]
+    monkeypatch.setenv("SMOT_CLIP_SPLIT", "1")
+    monkeypatch.setenv("SMOT_CLIP_SLOTS", slots)
+    cfg, model, clip = build_model(name, "float32")
+    assert model.engine().clip_split and model.engine().clip_slots == int(slots)
+    for _ in range(2):
+        model.reset_siammot_status()
+        got = model.forward_clip([f.to("cuda") for f in clip])
+        torch.cuda.synchronize()
+        assert len(got) == len(ref)
+        for a, b in zip(ref, got):
+            assert torch.equal(a.bbox, b.bbox) and torch.equal(a.get_field("ids"), b.get_field("ids"))
+            assert torch.equal(a.get_field("scores"), b.get_field("scores"))
