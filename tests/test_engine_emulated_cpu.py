@@ -105,3 +105,50 @@ def test_emulated_three_stage_clip_equals_golden(slots, monkeypatch):
     for name in ("emm_amodal_expire_192x320", "emm_256x384"):
         got, fake = _run(name, monkeypatch, clip_api=True, env=env)
         _compare(load_golden(name)["frames"], got)
+
+
+def _plugin_contract_check(model, cfg, sd, clip, to_dev=lambda t: t):
+    """EMM.extract_cache / EMM.forward (the SIAMESE_TRACKER plugin contract, track_core.py:28-98) against the oracle."""
+    from oracle import siammot_oracle as orc
+    from siammot_b200.structures import BoxList
+    T = cfg.MODEL.TRACK_HEAD
+    H, W = clip[0].shape[1], clip[0].shape[2]
+    eng = model.engine()
+    tracker = model.roi_heads.track.tracker
+    boxes = inject_boxes([(60., 80., 40., 90.), (150., 100., 70., 120.), (250., 90., 100., 160.), (300., 150., 30., 60.)])
+    ids = torch.tensor([0, 1, 2, 3])
+    labels = torch.ones(4, dtype=torch.int64)
+    det = BoxList(to_dev(boxes.clone()), (W, H), "xyxy")
+    det.add_field("ids", to_dev(ids))
+    det.add_field("labels", to_dev(labels))
+    det.add_field("scores", to_dev(torch.full((4,), 0.9)))
+    P0 = eng.run_static(to_dev(clip[0]))
+    x, sr, dets = tracker.extract_cache(P0, det)
+    o = orc.OracleSiamMOT(cfg, sd)
+    feats0 = o.features(clip[0])
+    ref_x = orc.pool_rois(feats0, boxes, boxes, T.POOLER_SCALES, T.POOLER_RESOLUTION, T.POOLER_SAMPLING_RATIO)
+    ref_sr = orc.search_region(boxes, T.PAD_PIXELS, T.SEARCH_REGION - 1.0, T.MINIMUM_SREACH_REGION)
+    assert tuple(x.shape) == (4, T.POOLER_RESOLUTION, T.POOLER_RESOLUTION, eng.C)
+    assert float((x.permute(0, 3, 1, 2).float().cpu() - ref_x).abs().max()) <= 2e-5 * float(ref_x.abs().max())
+    assert len(sr) == 1 and torch.equal(sr[0].bbox.cpu(), ref_sr) and tuple(sr[0].size) == (W + 2 * T.PAD_PIXELS, H + 2 * T.PAD_PIXELS)
+    assert dets[0] is det
+    # next frame: propagate the four tracks
+    P1 = eng.run_static(to_dev(clip[1]))
+    extra, out, losses = tracker(P1, [det], sr, template_features=x)
+    assert extra == {} and losses == {} and len(out) == 1
+    ref = orc.emm_forward(o.P, cfg, o.features(clip[1]), dict(feat=ref_x, sr=ref_sr, boxes=boxes, ids=ids, labels=labels), W, H)
+    got = out[0]
+    assert torch.equal(got.get_field("ids").cpu(), ref["ids"]) and torch.equal(got.get_field("labels").cpu(), ref["labels"])
+    assert float((got.bbox.cpu() - ref["boxes"]).abs().max()) <= BOX_TOL
+    assert float((got.get_field("scores").cpu() - ref["scores"]).abs().max()) <= SCORE_TOL
+
+
+def test_emulated_tracker_plugin_contract(monkeypatch):
+    from siammot_b200.modelling import build_siammot
+    cabi_emulator.install(monkeypatch)
+    cfg, sd, clip = scenario_inputs("emm_256x384")
+    cfg.DTYPE = "float32"
+    model = build_siammot(cfg)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    _plugin_contract_check(model, cfg, sd, clip)
