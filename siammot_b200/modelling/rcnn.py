@@ -420,8 +420,21 @@ class SiamMOT(nn.Module):
         ids = b.get_field("ids").to(torch.int64).numpy()
         active = self.roi_heads.track.track_pool.get_active_ids()
         n_act = sum(1 for i in ids.tolist() if i in active)
-        dev = next(self.parameters()).device
-        return Memory(feats.to(dev) if feats.numel() else None, sr[0].bbox.to("cpu").float().numpy(), b.bbox.float().numpy(),
+        eng = self.engine()
+        dev = eng.device
+        if feats.numel():
+            T, Cc = eng.t_res, eng.C
+            if feats.dim() == 4 and tuple(feats.shape[1:]) == (Cc, T, T) and Cc != T:
+                feats = feats.permute(0, 2, 3, 1)            # the reference's NCHW templates (track_core.py:92) -> NHWC
+            elif feats.dim() != 4 or tuple(feats.shape[1:]) != (T, T, Cc):
+                raise ValueError("template features must be (N, %d, %d, %d) [reference layout] or (N, %d, %d, %d) [engine layout], got %s"
+                                 % (Cc, T, T, T, T, Cc, tuple(feats.shape)))
+            if feats.shape[0] != b.bbox.shape[0]:
+                raise ValueError("%d template features for %d boxes" % (feats.shape[0], b.bbox.shape[0]))
+            feats = feats.to(device=dev, dtype=eng.dtype).contiguous()
+        else:
+            feats = None
+        return Memory(feats, sr[0].bbox.to("cpu").float().numpy(), b.bbox.float().numpy(),
                       ids, b.get_field("labels").to(torch.int64).numpy(), n_act, dev)
 
     @torch.no_grad()

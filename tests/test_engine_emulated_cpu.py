@@ -152,3 +152,44 @@ def test_emulated_tracker_plugin_contract(monkeypatch):
     model.load_state_dict(sd, strict=False)
     model.eval()
     _plugin_contract_check(model, cfg, sd, clip)
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_emulated_flush_memory_accepts_the_reference_memory_tuple(layout, monkeypatch):
+    """SiamMOT.flush_memory(cache) with the reference's (template_features, [sr], [boxes]) tuple (rcnn.py:34, track_head.py:54-110),
+    templates in the reference's NCHW layout or in the engine's NHWC one: the next frame must come out exactly as in the normal
+    flow, where the engine carries its own memory object."""
+    from siammot_b200.modelling import build_siammot
+    from siammot_b200.structures import BoxList
+    cabi_emulator.install(monkeypatch)
+    name = "emm_256x384"
+    cfg, sd, clip = scenario_inputs(name)
+    cfg.DTYPE = "float32"
+
+    def fresh():
+        m = build_siammot(cfg)
+        m.load_state_dict(sd, strict=False)
+        m.eval()
+        m.reset_siammot_status()
+        return m
+
+    ref_model = fresh()
+    ref = [ref_model(clip[t])[0] for t in range(3)]
+    model = fresh()
+    for t in range(2):
+        model(clip[t])
+    mem = model.track_memory                       # the engine's own memory after frame 1
+    feats = mem.feat.permute(0, 3, 1, 2).contiguous() if layout == "nchw" else mem.feat
+    W, H = clip[0].shape[2], clip[0].shape[1]
+    pad = cfg.MODEL.TRACK_HEAD.PAD_PIXELS
+    sr = BoxList(torch.from_numpy(mem.sr.copy()), (W + 2 * pad, H + 2 * pad), "xyxy")
+    boxes = BoxList(torch.from_numpy(mem.boxes.copy()), (W, H), "xyxy")
+    boxes.add_field("ids", torch.from_numpy(mem.ids.copy()))
+    boxes.add_field("labels", torch.from_numpy(mem.labels.copy()))
+    model.flush_memory((feats, [sr], [boxes]))
+    got = model(clip[2])[0]
+    assert len(got) == len(ref[2]) and int((ref[2].get_field("ids") >= 0).sum()) > 0
+    assert torch.equal(got.bbox, ref[2].bbox) and torch.equal(got.get_field("ids"), ref[2].get_field("ids"))
+    assert torch.equal(got.get_field("scores"), ref[2].get_field("scores"))
+    with pytest.raises(ValueError):
+        model.flush_memory((feats[:, :3], [sr], [boxes]))
