@@ -70,6 +70,18 @@ class Memory(object):
         h[9 * n:9 * n + self.n_active] = 1.0
         h[9 * n + self.n_active:10 * n] = 0.0
 
+    def as_reference_tuple(self, image_size, pad_pixels):
+        """The same memory in the reference's form -- (template_features (N,C,T,T), [sr BoxList], [boxes BoxList with ids /
+        labels]) as TrackHead.get_track_memory returns it (track_head.py:54-110) -- for callers that inspect or store
+        ``model.track_memory`` the reference way; ``flush_memory`` accepts it back."""
+        W, H = image_size
+        feats = self.feat.permute(0, 3, 1, 2) if self.feat is not None else torch.zeros((0,))
+        sr = BoxList(torch.from_numpy(self.sr.copy()), (int(W + 2 * pad_pixels), int(H + 2 * pad_pixels)), "xyxy")
+        boxes = BoxList(torch.from_numpy(self.boxes.copy()), (W, H), "xyxy")
+        boxes.add_field("ids", torch.from_numpy(self.ids.copy()))
+        boxes.add_field("labels", torch.from_numpy(self.labels.copy()))
+        return feats, [sr], [boxes]
+
     # views used by the generic (plugin / given-detection) path
     def torch_views(self):
         dev = self.device

@@ -160,7 +160,6 @@ def test_emulated_flush_memory_accepts_the_reference_memory_tuple(layout, monkey
     templates in the reference's NCHW layout or in the engine's NHWC one: the next frame must come out exactly as in the normal
     flow, where the engine carries its own memory object."""
     from siammot_b200.modelling import build_siammot
-    from siammot_b200.structures import BoxList
     cabi_emulator.install(monkeypatch)
     name = "emm_256x384"
     cfg, sd, clip = scenario_inputs(name)
@@ -179,13 +178,12 @@ def test_emulated_flush_memory_accepts_the_reference_memory_tuple(layout, monkey
     for t in range(2):
         model(clip[t])
     mem = model.track_memory                       # the engine's own memory after frame 1
-    feats = mem.feat.permute(0, 3, 1, 2).contiguous() if layout == "nchw" else mem.feat
     W, H = clip[0].shape[2], clip[0].shape[1]
-    pad = cfg.MODEL.TRACK_HEAD.PAD_PIXELS
-    sr = BoxList(torch.from_numpy(mem.sr.copy()), (W + 2 * pad, H + 2 * pad), "xyxy")
-    boxes = BoxList(torch.from_numpy(mem.boxes.copy()), (W, H), "xyxy")
-    boxes.add_field("ids", torch.from_numpy(mem.ids.copy()))
-    boxes.add_field("labels", torch.from_numpy(mem.labels.copy()))
+    feats, sr_l, boxes_l = mem.as_reference_tuple((W, H), cfg.MODEL.TRACK_HEAD.PAD_PIXELS)
+    sr, boxes = sr_l[0], boxes_l[0]
+    assert tuple(feats.shape[1:]) == (128, 15, 15) and tuple(sr.size) == (W + 1024, H + 1024)
+    if layout == "nhwc":
+        feats = mem.feat
     model.flush_memory((feats, [sr], [boxes]))
     got = model(clip[2])[0]
     assert len(got) == len(ref[2]) and int((ref[2].get_field("ids") >= 0).sum()) > 0
