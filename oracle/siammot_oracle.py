@@ -47,9 +47,20 @@ def _basic_block(P, pre, x, stride, residual=None):
     return _conv_bn(P, y, pre + ".conv2", pre + ".bn2", 1, 1, relu=True, residual=residual)
 
 
-def _tree(P, pre, x, levels, cin, cout, stride, level_root, children=None):
+def _bottleneck_block(P, pre, x, stride, residual=None):
+    """DlaBottleneck.forward (dla.py:81-101), cardinality 1 / base width 64: 1x1 -> 3x3 (stride) -> 1x1, + residual, ReLU."""
+    if residual is None:
+        residual = x
+    y = _conv_bn(P, x, pre + ".conv1", pre + ".bn1", 1, 0, relu=True)
+    y = _conv_bn(P, y, pre + ".conv2", pre + ".bn2", stride, 1, relu=True)
+    return _conv_bn(P, y, pre + ".conv3", pre + ".bn3", 1, 0, relu=True, residual=residual)
+
+
+def _tree(P, pre, x, levels, cin, cout, stride, level_root, children=None, block=None, root_residual=False):
     """DlaTree.forward (dla.py:225-238).  The ``residual`` argument of the reference is always
-    overwritten at dla.py:228, so it is not a parameter here."""
+    overwritten at dla.py:228, so it is not a parameter here.  ``block``: _basic_block (DLA-34) or _bottleneck_block;
+    ``root_residual``: DlaRoot adds its first input (dla.py:185-186; DLA-102 / 169)."""
+    block = block or _basic_block
     children = [] if children is None else children
     bottom = F.max_pool2d(x, stride, stride) if stride > 1 else x
     if cin != cout:
@@ -59,13 +70,31 @@ def _tree(P, pre, x, levels, cin, cout, stride, level_root, children=None):
     if level_root:
         children.append(bottom)
     if levels == 1:
-        x1 = _basic_block(P, pre + ".tree1", x, stride, residual)
-        x2 = _basic_block(P, pre + ".tree2", x1, 1)
+        x1 = block(P, pre + ".tree1", x, stride, residual)
+        x2 = block(P, pre + ".tree2", x1, 1)
         cat = torch.cat([x2, x1] + children, 1)           # DlaRoot.forward dla.py:181-189
-        return _conv_bn(P, cat, pre + ".root.conv", pre + ".root.bn", relu=True)
-    x1 = _tree(P, pre + ".tree1", x, levels - 1, cin, cout, stride, False)
+        return _conv_bn(P, cat, pre + ".root.conv", pre + ".root.bn", relu=True, residual=x2 if root_residual else None)
+    x1 = _tree(P, pre + ".tree1", x, levels - 1, cin, cout, stride, False, None, block, root_residual)
     children.append(x1)
-    return _tree(P, pre + ".tree2", x1, levels - 1, cout, cout, 1, False, children)
+    return _tree(P, pre + ".tree2", x1, levels - 1, cout, cout, 1, False, children, block, root_residual)
+
+
+def dla_forward(P, x, arch, pre="backbone.body"):
+    """DLA.forward (dla.py:289-304) for the plain members of the family (dla.py:307-372): levels / channels / block /
+    residual_root from siammot_b200.synthetic.DLA_ARCHS (the table is data about the reference, shared with the test inputs)."""
+    from siammot_b200.synthetic import DLA_ARCHS
+    A = DLA_ARCHS[arch]
+    ch, lv = A["channels"], A["levels"]
+    block = _bottleneck_block if A["block"] == "bottleneck" else _basic_block
+    x = _conv_bn(P, x, pre + ".base_layer.0", pre + ".base_layer.1", 1, 3, relu=True)
+    for name, n, stride in (("level0", lv[0], 1), ("level1", lv[1], 2)):      # _make_conv_level dla.py:278-287
+        for i in range(n):
+            x = _conv_bn(P, x, "%s.%s.%d" % (pre, name, 3 * i), "%s.%s.%d" % (pre, name, 3 * i + 1), stride if i == 0 else 1, 1, relu=True)
+    outs = []
+    for lvl in range(2, 6):
+        x = _tree(P, "%s.level%d" % (pre, lvl), x, lv[lvl], ch[lvl - 1], ch[lvl], 2, lvl > 2, None, block, A["residual_root"])
+        outs.append(x)
+    return outs
 
 
 DLA34_LEVELS = (1, 1, 1, 2, 2, 1)
@@ -481,8 +510,9 @@ class OracleSiamMOT(object):
         if body == "R-50-FPN":
             return fpn_forward(self.P, resnet50_forward(self.P, image.to(torch.float32),
                                                         stride_in_1x1=self.cfg.MODEL.RESNETS.STRIDE_IN_1X1))
-        assert body == "DLA-34-FPN", body
-        return fpn_forward(self.P, dla34_forward(self.P, image.to(torch.float32)))
+        if body == "DLA-34-FPN":
+            return fpn_forward(self.P, dla34_forward(self.P, image.to(torch.float32)))
+        return fpn_forward(self.P, dla_forward(self.P, image.to(torch.float32), body))
 
     @torch.no_grad()
     def forward(self, image, given_detection=None):

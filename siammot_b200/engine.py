@@ -383,9 +383,12 @@ class Engine(object):
         self.weights = {}
         self.plans = {}
         from .synthetic import backbone_channels, is_resnet
-        if cfg.MODEL.BACKBONE.CONV_BODY not in ("DLA-34-FPN", "R-50-FPN"):
-            raise NotImplementedError("body %s: DLA-34-FPN (SURVEY.md section 8) and R-50-FPN (BASELINE.json configs[4]) are "
-                                      "implemented" % cfg.MODEL.BACKBONE.CONV_BODY)
+        from .synthetic import DLA_ARCHS
+        if cfg.MODEL.BACKBONE.CONV_BODY not in DLA_ARCHS and cfg.MODEL.BACKBONE.CONV_BODY != "R-50-FPN":
+            raise NotImplementedError("body %s: implemented are %s (dla.py:307-372; DLA-34-FPN is the SURVEY.md section 8 path) and "
+                                      "R-50-FPN (BASELINE.json configs[4])" % (cfg.MODEL.BACKBONE.CONV_BODY, ", ".join(sorted(DLA_ARCHS))))
+        if cfg.MODEL.BACKBONE.CONV_BODY in DLA_ARCHS and any(cfg.MODEL.DLA.STAGE_WITH_DCN):
+            raise NotImplementedError("MODEL.DLA.STAGE_WITH_DCN (deformable convolutions)")
         self.resnet = is_resnet(cfg)
         if self.resnet:
             R = cfg.MODEL.RESNETS
@@ -565,6 +568,77 @@ class Engine(object):
         self._tree(P, name + ".tree1", x, 1, cin, cout, stride, False, out=t1)
         return self._tree(P, name + ".tree2", t1, 1, cout, cout, 1, False, out=out, rootbuf=rootbuf)
 
+    def _tree_general(self, P, name, x, levels, cin, cout, stride, level_root, bottleneck, root_residual, out=None, rootbuf=None,
+                      off=None):
+        """DlaTree of any depth with either block type (the DLA family beyond DLA-34: dla.py:316-372), concat-free.
+        The innermost tree2 of a nest owns the root (dla.py:209-210); its input [x2 | x1 | bottom? | x1 of every enclosing
+        tree, outermost first] (dla.py:229-237) is ONE buffer allocated where the nest starts: every producer writes its
+        channel slice in place.  ``rootbuf`` / ``off``: that buffer and its next free channel when this call is the tree2 chain
+        of an enclosing tree.  As in _tree, the ``project`` of a tree whose tree1 is itself a tree is dead code (dla.py:228)."""
+        _, H, W, _ = x.shape
+        Ho, Wo = H // stride, W // stride
+        if rootbuf is None:
+            total = 2 * cout + (cin if level_root else 0) + (levels - 1) * cout
+            rootbuf = P.new(Ho, Wo, total)
+            off = 2 * cout
+        else:
+            assert not level_root and stride == 1
+        bottom = x
+        if level_root:
+            assert stride > 1, "level_root trees of the DLA family down-sample"
+            bottom = rootbuf[..., off:off + cin]
+            P.call(lib().smot_maxpool2x2, self._pool_args(x, bottom), "maxpool:" + name)
+            off += cin
+        elif stride > 1 and levels == 1:
+            bottom = P.new(Ho, Wo, cin)
+            P.call(lib().smot_maxpool2x2, self._pool_args(x, bottom), "maxpool:" + name)
+        if levels > 1:
+            t1 = rootbuf[..., off:off + cout]
+            self._tree_general(P, name + ".tree1", x, levels - 1, cin, cout, stride, False, bottleneck, root_residual, out=t1)
+            return self._tree_general(P, name + ".tree2", t1, levels - 1, cout, cout, 1, False, bottleneck, root_residual,
+                                      out=out, rootbuf=rootbuf, off=off + cout)
+        assert off == rootbuf.shape[3], (name, off, rootbuf.shape)
+        if cin != cout:
+            residual = P.new(Ho, Wo, cout)
+            P.conv(bottom, "body." + name + ".project.0", residual)
+        else:
+            residual = bottom
+        x2v, x1v = rootbuf[..., 0:cout], rootbuf[..., cout:2 * cout]
+
+        def block(pre, inp, outv, s, res):
+            if bottleneck:                                     # DlaBottleneck (dla.py:63-101): mid = out / 2
+                mid = cout // 2
+                a = P.conv(inp, pre + ".conv1", P.new(inp.shape[1], inp.shape[2], mid), relu=True)
+                b = P.conv(a, pre + ".conv2", P.new(Ho, Wo, mid), stride=s, pad=1, relu=True)
+                P.conv(b, pre + ".conv3", outv, residual=res, relu=True)
+            else:                                              # DlaBasic (dla.py:30-57)
+                a = P.conv(inp, pre + ".conv1", P.new(Ho, Wo, cout), stride=s, pad=1, relu=True)
+                P.conv(a, pre + ".conv2", outv, residual=res, pad=1, relu=True)
+        block("body." + name + ".tree1", x, x1v, stride, residual)
+        block("body." + name + ".tree2", x1v, x2v, 1, x1v)
+        if out is None:
+            out = P.new(Ho, Wo, cout)
+        P.conv(rootbuf, "body." + name + ".root.conv", out, residual=x2v if root_residual else None, relu=True)
+        return out
+
+    def _dla_body_general(self, P, img):
+        """DLA.forward (dla.py:289-304) for the family members other than DLA-34 (whose hand-laid plan is _tree)."""
+        from .synthetic import DLA_ARCHS
+        A = DLA_ARCHS[self.cfg.MODEL.BACKBONE.CONV_BODY]
+        ch, lv = A["channels"], A["levels"]
+        H, W = img.shape[1], img.shape[2]
+        x = P.conv(img[..., :3], "body.base_layer.0", P.new(H, W, ch[0]), pad=3, relu=True)
+        for name, n, stride, c in (("level0", lv[0], 1, ch[0]), ("level1", lv[1], 2, ch[1])):
+            for i in range(n):
+                s_ = stride if i == 0 else 1
+                x = P.conv(x, "body.%s.%d" % (name, 3 * i), P.new(x.shape[1] // s_, x.shape[2] // s_, c), stride=s_, pad=1, relu=True)
+        outs = []
+        for lvl in range(2, 6):
+            x = self._tree_general(P, "level%d" % lvl, x, lv[lvl], ch[lvl - 1], ch[lvl], 2, lvl > 2, A["block"] == "bottleneck",
+                                   A["residual_root"])
+            outs.append(x)
+        return outs
+
     def _resnet_body(self, P, img):
         """Upstream maskrcnn_benchmark ResNet-50 (modeling/backbone/resnet.py, "R-50-FPN") as launches: stem 7x7/2 + FrozenBN +
         ReLU, 3x3/2 max-pool, four stages of bottleneck blocks (1x1 -> 3x3 -> 1x1, FrozenBN / ReLU / residual in the conv
@@ -634,6 +708,8 @@ class Engine(object):
         P.call(L.smot_image_to_nhwc, (ops._ptr(P.img_in), ops._ptr(img), 3, H, W, 4, dc), "image_to_nhwc")
         if self.resnet:
             body = self._resnet_body(P, img)
+        elif cfg.MODEL.BACKBONE.CONV_BODY != "DLA-34-FPN":
+            body = self._dla_body_general(P, img)
         else:
             # ---- DLA-34 body (dla.py:289-304)
             ch = (16, 32, 64, 128, 256, 512)

@@ -49,6 +49,61 @@ def dla34_layout():
     return out
 
 
+# The plain (non-grouped, non-DCN) members of the reference's DLA family (dla.py:307-372): tree depths per level, channels,
+# block type, residual roots.  "DLA-46-XC" / "DLA-60-RES2NET" use grouped / Res2Net blocks and are not covered.
+DLA_ARCHS = {
+    "DLA-34-FPN": dict(levels=(1, 1, 1, 2, 2, 1), channels=(16, 32, 64, 128, 256, 512), block="basic", residual_root=False),
+    "DLA-46-C-FPN": dict(levels=(1, 1, 1, 2, 2, 1), channels=(16, 32, 64, 64, 128, 256), block="bottleneck", residual_root=False),
+    "DLA-60-FPN": dict(levels=(1, 1, 1, 2, 3, 1), channels=(16, 32, 128, 256, 512, 1024), block="bottleneck", residual_root=False),
+    "DLA-102-FPN": dict(levels=(1, 1, 1, 3, 4, 1), channels=(16, 32, 128, 256, 512, 1024), block="bottleneck", residual_root=True),
+    "DLA-169-FPN": dict(levels=(1, 1, 2, 3, 5, 1), channels=(16, 32, 128, 256, 512, 1024), block="bottleneck", residual_root=True),
+}
+
+
+def dla_layout(arch):
+    """(kind, name, shape) of every parameter group of a DLA body in the reference's module order (dla.py:241-304): DlaTree
+    registers tree1, tree2, then root (levels == 1), then project; DlaBottleneck has mid = out / 2 channels (dla.py:63-96)."""
+    A = DLA_ARCHS[arch]
+    ch, levels, bottleneck = A["channels"], A["levels"], A["block"] == "bottleneck"
+    out = [("conv", "base_layer.0", (ch[0], 3, 7, 7)), ("bn", "base_layer.1", ch[0])]
+
+    def conv_level(name, cin, cout, convs):
+        for i in range(convs):
+            out.extend([("conv", "%s.%d" % (name, 3 * i), (cout, cin, 3, 3)), ("bn", "%s.%d" % (name, 3 * i + 1), cout)])
+            cin = cout
+    conv_level("level0", ch[0], ch[0], levels[0])
+    conv_level("level1", ch[0], ch[1], levels[1])
+
+    def block(pre, cin, cout):
+        if bottleneck:
+            mid = cout // 2
+            out.extend([("conv", pre + ".conv1", (mid, cin, 1, 1)), ("bn", pre + ".bn1", mid),
+                        ("conv", pre + ".conv2", (mid, mid, 3, 3)), ("bn", pre + ".bn2", mid),
+                        ("conv", pre + ".conv3", (cout, mid, 1, 1)), ("bn", pre + ".bn3", cout)])
+        else:
+            out.extend([("conv", pre + ".conv1", (cout, cin, 3, 3)), ("bn", pre + ".bn1", cout),
+                        ("conv", pre + ".conv2", (cout, cout, 3, 3)), ("bn", pre + ".bn2", cout)])
+
+    def tree(pre, lv, cin, cout, level_root, root_dim=0):
+        if root_dim == 0:
+            root_dim = 2 * cout
+        if level_root:
+            root_dim += cin
+        if lv == 1:
+            block(pre + ".tree1", cin, cout)
+            block(pre + ".tree2", cout, cout)
+            out.extend([("conv", pre + ".root.conv", (cout, root_dim, 1, 1)), ("bn", pre + ".root.bn", cout)])
+        else:
+            tree(pre + ".tree1", lv - 1, cin, cout, False, 0)
+            tree(pre + ".tree2", lv - 1, cout, cout, False, root_dim + cout)
+        if cin != cout:
+            out.extend([("conv", pre + ".project.0", (cout, cin, 1, 1)), ("bn", pre + ".project.1", cout)])
+
+    for lvl in range(2, 6):
+        tree("level%d" % lvl, levels[lvl], ch[lvl - 1], ch[lvl], lvl > 2)
+    return out
+
+
 R50_BLOCKS = (3, 4, 6, 3)
 
 
@@ -79,10 +134,12 @@ def body_layout(cfg):
     body = cfg.MODEL.BACKBONE.CONV_BODY
     if body == "DLA-34-FPN":
         return dla34_layout()
+    if body in DLA_ARCHS:
+        return dla_layout(body)
     if body == "R-50-FPN":
         R = cfg.MODEL.RESNETS
         return resnet50_layout(R50_BLOCKS, R.STEM_OUT_CHANNELS, R.RES2_OUT_CHANNELS, R.NUM_GROUPS * R.WIDTH_PER_GROUP)
-    raise NotImplementedError("body %s (DLA-34-FPN and R-50-FPN are implemented)" % body)
+    raise NotImplementedError("body %s (implemented: %s, R-50-FPN)" % (body, ", ".join(sorted(DLA_ARCHS))))
 
 
 def backbone_channels(cfg):
@@ -115,8 +172,14 @@ def make_state_dict(cfg, seed=1):
         else:
             # the branch that is added to the identity gets a smaller gain so that activations stay O(1) with depth
             # (16 bottleneck blocks in the ResNet: a much smaller gain than for DLA's 8 basic blocks)
-            residual_branch = name.endswith("bn3") if resnet else (name.endswith("bn2") or ".project" in name)
-            sd[key + ".weight"] = ((0.25 if resnet else 0.6) if residual_branch else 0.9) + 0.1 * rand(shape)
+            arch = DLA_ARCHS.get(cfg.MODEL.BACKBONE.CONV_BODY, {})
+            bottleneck = resnet or arch.get("block") == "bottleneck"
+            residual_branch = (name.endswith("bn3") or (".project" in name and not resnet)) if bottleneck else \
+                (name.endswith("bn2") or ".project" in name)
+            gain = ((0.25 if bottleneck else 0.6) if residual_branch else 0.9)
+            if arch.get("residual_root") and name.endswith("root.bn"):
+                gain = 0.4                                  # DlaRoot adds its first input (dla.py:185-186): damp the conv branch
+            sd[key + ".weight"] = gain + 0.1 * rand(shape)
             sd[key + ".bias"] = randn(shape, std=0.1)
             sd[key + ".running_mean"] = randn(shape, std=0.1)
             sd[key + ".running_var"] = 1.0 + 0.1 * rand(shape)

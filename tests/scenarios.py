@@ -62,6 +62,15 @@ ORACLE_SCENARIOS = {
                             overrides=["MODEL.BACKBONE.CONV_BODY", "R-50-FPN", "MODEL.RESNETS.BACKBONE_OUT_CHANNELS", 256,
                                        "MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES", 3],
                             H=192, W=320, frames=5, n_obj=5, clip_seed=5, weight_seed=11, inject=None),
+    # a deeper member of the reference's DLA family (dla.py:353-360): DLA-102 -- bottleneck blocks, trees three and four levels
+    # deep, residual roots.  (MODEL.WEIGHT must name an existing path: for every body but DLA-34 the reference's own lookup of
+    # the ImageNet URL raises KeyError -- dla.py:387-405 map "DLA-102-FPN" to 'dla_102' while model_urls has 'dla102'.)
+    "emm_dla102_192x320": dict(yaml="DLA_34_FPN_EMM.yaml",
+                               overrides=["MODEL.BACKBONE.CONV_BODY", "DLA-102-FPN", "MODEL.DLA.DLA_STAGE2_OUT_CHANNELS", 128,
+                                          "MODEL.DLA.DLA_STAGE3_OUT_CHANNELS", 256, "MODEL.DLA.DLA_STAGE4_OUT_CHANNELS", 512,
+                                          "MODEL.DLA.DLA_STAGE5_OUT_CHANNELS", 1024, "MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES", 3,
+                                          "MODEL.WEIGHT", "/dev/null"],
+                               H=192, W=320, frames=5, n_obj=5, clip_seed=5, weight_seed=32, inject=None),
 }
 
 

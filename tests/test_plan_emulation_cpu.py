@@ -65,3 +65,55 @@ def test_concurrent_stages_use_disjoint_split_k_scratch(monkeypatch):
     assert all(len(v) == 1 for v in per_branch.values())
     assert len({next(iter(v)) for v in per_branch.values()}) == len(per_branch)
     assert eng.conv_ws.data_ptr() not in {next(iter(v)) for v in per_branch.values()}
+
+
+DLA_FAMILY = {"DLA-46-C-FPN": (64, 64, 128, 256), "DLA-60-FPN": (128, 256, 512, 1024), "DLA-102-FPN": (128, 256, 512, 1024),
+              "DLA-169-FPN": (128, 256, 512, 1024)}
+
+
+@pytest.mark.parametrize("arch", sorted(DLA_FAMILY) + ["DLA-34-FPN"])
+def test_dla_family_wiring_matches_oracle(arch, monkeypatch):
+    """The general concat-free DlaTree plan (bottleneck blocks, nests up to five deep, residual roots, level-2 nests) against
+    the oracle, which tests/test_oracle_dla_family_cpu.py pins to the reference's own dla.py modules.  DLA-34 through the same
+    general builder must equal its hand-laid (GPU-validated) plan's result too."""
+    import os
+    from helpers import CONFIG_DIR
+    from oracle.siammot_oracle import OracleSiamMOT
+    from siammot_b200.config import get_cfg
+    from siammot_b200.synthetic import make_state_dict
+    cfg = get_cfg()
+    cfg.merge_from_file(os.path.join(CONFIG_DIR, "dla34_emm.yaml"))
+    stages = DLA_FAMILY.get(arch, (64, 128, 256, 512))
+    cfg.merge_from_list(["MODEL.BACKBONE.CONV_BODY", arch, "MODEL.DLA.DLA_STAGE2_OUT_CHANNELS", stages[0],
+                         "MODEL.DLA.DLA_STAGE3_OUT_CHANNELS", stages[1], "MODEL.DLA.DLA_STAGE4_OUT_CHANNELS", stages[2],
+                         "MODEL.DLA.DLA_STAGE5_OUT_CHANNELS", stages[3]])
+    cfg.DTYPE = "float32"
+    sd = make_state_dict(cfg, 3)
+    eng = build_engine_on_host(cfg, sd, monkeypatch)
+    if arch == "DLA-34-FPN":                       # force the general builder for the validated architecture
+        P = engine_plan_with_general_builder(eng, 64, 96)
+    else:
+        P = eng.plan(64, 96)
+    image = torch.randn(3, 64, 96, generator=torch.Generator().manual_seed(2))
+    assert run_backbone(P, image) >= 40
+    ref = OracleSiamMOT(cfg, sd).features(image)
+    for l, (got, want) in enumerate(zip(P.feats, ref)):
+        got = got.permute(0, 3, 1, 2)
+        assert got.shape == want.shape
+        err = float((got - want).abs().max() / want.abs().max())
+        assert err <= 1e-4, "%s FPN level %d: relative error %g" % (arch, l, err)
+
+
+def engine_plan_with_general_builder(eng, H, W):
+    """plan() with DLA-34 routed through _dla_body_general instead of the hand-laid _tree."""
+    import types
+    orig_tree = eng._tree
+
+    def via_general(self, P, name, x, levels, cin, cout, stride, level_root, out=None, rootbuf=None):
+        assert rootbuf is None
+        return self._tree_general(P, name, x, levels, cin, cout, stride, level_root, False, False, out=out)
+    eng._tree = types.MethodType(via_general, eng)
+    try:
+        return eng.plan(H, W)
+    finally:
+        eng._tree = orig_tree
