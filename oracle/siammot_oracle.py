@@ -117,7 +117,7 @@ def dla34_forward(P, x, pre="backbone.body"):
 R50_BLOCKS = (3, 4, 6, 3)
 
 
-def resnet50_forward(P, x, pre="backbone.body", stride_in_1x1=True):
+def resnet50_forward(P, x, pre="backbone.body", stride_in_1x1=True, blocks=R50_BLOCKS):
     """Upstream maskrcnn_benchmark ResNet.forward for "R-50-FPN" (modeling/backbone/resnet.py; un-vendored, restated):
     stem = 7x7/2 conv + FrozenBN + ReLU + 3x3/2 max-pool (pad 1); four stages of bottleneck blocks
     1x1 (stride here when STRIDE_IN_1X1) -> 3x3 -> 1x1, FrozenBN after each, ReLU after the first two and after the
@@ -125,7 +125,7 @@ def resnet50_forward(P, x, pre="backbone.body", stride_in_1x1=True):
     x = _conv_bn(P, x, pre + ".stem.conv1", pre + ".stem.bn1", 2, 3, relu=True)
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     outs = []
-    for li, nb in enumerate(R50_BLOCKS):
+    for li, nb in enumerate(blocks):
         for b in range(nb):
             blk = "%s.layer%d.%d" % (pre, li + 1, b)
             stride = 2 if (b == 0 and li > 0) else 1
@@ -507,9 +507,10 @@ class OracleSiamMOT(object):
         if image.dim() == 3:
             image = image[None]
         body = self.cfg.MODEL.BACKBONE.CONV_BODY
-        if body == "R-50-FPN":
+        if body in ("R-50-FPN", "R-101-FPN"):
             return fpn_forward(self.P, resnet50_forward(self.P, image.to(torch.float32),
-                                                        stride_in_1x1=self.cfg.MODEL.RESNETS.STRIDE_IN_1X1))
+                                                        stride_in_1x1=self.cfg.MODEL.RESNETS.STRIDE_IN_1X1,
+                                                        blocks=(3, 4, 23, 3) if body == "R-101-FPN" else R50_BLOCKS))
         if body == "DLA-34-FPN":
             return fpn_forward(self.P, dla34_forward(self.P, image.to(torch.float32)))
         return fpn_forward(self.P, dla_forward(self.P, image.to(torch.float32), body))

@@ -383,10 +383,11 @@ class Engine(object):
         self.weights = {}
         self.plans = {}
         from .synthetic import backbone_channels, is_resnet
-        from .synthetic import DLA_ARCHS
-        if cfg.MODEL.BACKBONE.CONV_BODY not in DLA_ARCHS and cfg.MODEL.BACKBONE.CONV_BODY != "R-50-FPN":
+        from .synthetic import DLA_ARCHS, RESNET_BLOCKS
+        if cfg.MODEL.BACKBONE.CONV_BODY not in DLA_ARCHS and cfg.MODEL.BACKBONE.CONV_BODY not in RESNET_BLOCKS:
             raise NotImplementedError("body %s: implemented are %s (dla.py:307-372; DLA-34-FPN is the SURVEY.md section 8 path) and "
-                                      "R-50-FPN (BASELINE.json configs[4])" % (cfg.MODEL.BACKBONE.CONV_BODY, ", ".join(sorted(DLA_ARCHS))))
+                                      "%s (upstream resnet.py; R-50-FPN is BASELINE.json configs[4])"
+                                      % (cfg.MODEL.BACKBONE.CONV_BODY, ", ".join(sorted(DLA_ARCHS)), ", ".join(sorted(RESNET_BLOCKS))))
         if cfg.MODEL.BACKBONE.CONV_BODY in DLA_ARCHS and any(cfg.MODEL.DLA.STAGE_WITH_DCN):
             raise NotImplementedError("MODEL.DLA.STAGE_WITH_DCN (deformable convolutions)")
         self.resnet = is_resnet(cfg)
@@ -394,7 +395,7 @@ class Engine(object):
             R = cfg.MODEL.RESNETS
             if (R.NUM_GROUPS != 1 or R.RES5_DILATION != 1 or any(R.STAGE_WITH_DCN) or R.STEM_FUNC != "StemWithFixedBatchNorm"
                     or R.TRANS_FUNC != "BottleneckWithFixedBatchNorm"):
-                raise NotImplementedError("R-50-FPN: only the plain FrozenBN bottleneck body (no groups / dilation / DCN)")
+                raise NotImplementedError("ResNet bodies: only the plain FrozenBN bottleneck form (no groups / dilation / DCN)")
         self.C = backbone_channels(cfg)[1]
         self.ncls = cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES
         if cfg.MODEL.CLS_AGNOSTIC_BBOX_REG:
@@ -658,8 +659,8 @@ class Engine(object):
         P.call(L.smot_maxpool3x3s2, self._pool_args(x, pooled), "stem_pool")
         x, cin = pooled, stem
         outs = []
-        from .synthetic import R50_BLOCKS
-        for li, nb in enumerate(R50_BLOCKS):
+        from .synthetic import RESNET_BLOCKS
+        for li, nb in enumerate(RESNET_BLOCKS[cfg.MODEL.BACKBONE.CONV_BODY]):
             mid, cout = R.NUM_GROUPS * R.WIDTH_PER_GROUP * 2 ** li, R.RES2_OUT_CHANNELS * 2 ** li
             for b in range(nb):
                 name = "body.layer%d.%d" % (li + 1, b)

@@ -105,6 +105,7 @@ def dla_layout(arch):
 
 
 R50_BLOCKS = (3, 4, 6, 3)
+RESNET_BLOCKS = {"R-50-FPN": R50_BLOCKS, "R-101-FPN": (3, 4, 23, 3)}   # upstream resnet.py stage specs (FPN variants, stages 2..5)
 
 
 def resnet50_layout(blocks=R50_BLOCKS, stem=64, res2=256, width=64):
@@ -136,10 +137,10 @@ def body_layout(cfg):
         return dla34_layout()
     if body in DLA_ARCHS:
         return dla_layout(body)
-    if body == "R-50-FPN":
+    if body in RESNET_BLOCKS:
         R = cfg.MODEL.RESNETS
-        return resnet50_layout(R50_BLOCKS, R.STEM_OUT_CHANNELS, R.RES2_OUT_CHANNELS, R.NUM_GROUPS * R.WIDTH_PER_GROUP)
-    raise NotImplementedError("body %s (implemented: %s, R-50-FPN)" % (body, ", ".join(sorted(DLA_ARCHS))))
+        return resnet50_layout(RESNET_BLOCKS[body], R.STEM_OUT_CHANNELS, R.RES2_OUT_CHANNELS, R.NUM_GROUPS * R.WIDTH_PER_GROUP)
+    raise NotImplementedError("body %s (implemented: %s)" % (body, ", ".join(sorted(DLA_ARCHS) + sorted(RESNET_BLOCKS))))
 
 
 def backbone_channels(cfg):

@@ -117,3 +117,24 @@ def engine_plan_with_general_builder(eng, H, W):
         return eng.plan(H, W)
     finally:
         eng._tree = orig_tree
+
+
+def test_r101_wiring_matches_oracle(monkeypatch):
+    """upstream "R-101-FPN" (stage specs 3, 4, 23, 3) through the same bottleneck plan."""
+    import os
+    from helpers import CONFIG_DIR
+    from oracle.siammot_oracle import OracleSiamMOT
+    from siammot_b200.config import get_cfg
+    from siammot_b200.synthetic import make_state_dict
+    cfg = get_cfg()
+    cfg.merge_from_file(os.path.join(CONFIG_DIR, "r50_emm.yaml"))
+    cfg.merge_from_list(["MODEL.BACKBONE.CONV_BODY", "R-101-FPN"])
+    cfg.DTYPE = "float32"
+    sd = make_state_dict(cfg, 2)
+    eng = build_engine_on_host(cfg, sd, monkeypatch)
+    P = eng.plan(64, 96)
+    image = torch.randn(3, 64, 96, generator=torch.Generator().manual_seed(5))
+    assert run_backbone(P, image) >= 100
+    for l, (got, want) in enumerate(zip(P.feats, OracleSiamMOT(cfg, sd).features(image))):
+        err = float((got.permute(0, 3, 1, 2) - want).abs().max() / want.abs().max())
+        assert err <= 1e-4, "R-101 FPN level %d: relative error %g" % (l, err)
