@@ -472,14 +472,16 @@ def _is_raw_frame(x):
     return (isinstance(x, np.ndarray) and x.dtype == np.uint8) or (torch.is_tensor(x) and x.dtype == torch.uint8)
 
 
-def _forward_clip(self, frames, before_frame=None):
+def _forward_clip(self, frames, before_frame=None, given_detections=None):
     """Process consecutive frames of ONE video as a two-stage pipeline: the frame-independent stage (backbone ..
     detections, double-buffered static plans) of frame t+1 runs on a side stream while the track stage of frame t
     runs on the current stream and the host resolves ids.  Results are identical to calling the model frame by
     frame; this is the throughput API (the reference has INFERENCE.CLIP_LEN but processes one frame per forward,
     defaults.py:96, track_core.py:75).  frames: sequence / tensor of normalised (3,H,W) frames or of decoded
     uint8 (H,W,3) RGB frames (preprocessed on the device).
-    before_frame(t): optional hook called right before frame t's tracker stage is enqueued."""
+    before_frame(t): optional hook called right before frame t's tracker stage is enqueued.
+    given_detections: optional per-frame list of public detections, each what ``forward(..., given_detection=)`` takes (a
+    one-element list holding a BoxList, roi_heads.py:26-34; inferencer.py:47-54), or None for a frame without any."""
     if self.training:
         raise NotImplementedError("siammot_b200 is an inference engine: call .eval()")
     eng = self.engine()
@@ -487,8 +489,10 @@ def _forward_clip(self, frames, before_frame=None):
     results = []
     if not n_frames:
         return results
+    if given_detections is not None and len(given_detections) != n_frames:
+        raise ValueError("given_detections: %d entries for %d frames" % (len(given_detections), n_frames))
     if eng.clip_split:
-        return _forward_clip_three_stage(self, eng, frames, before_frame)
+        return _forward_clip_three_stage(self, eng, frames, before_frame, given_detections)
     cur = torch.cuda.current_stream(eng.device)
     side = eng.side_stream()
     side.wait_stream(cur)          # the frames (and anything else already enqueued) are visible to the side stream
@@ -511,7 +515,7 @@ def _forward_clip(self, frames, before_frame=None):
             if before_frame is not None:
                 before_frame(t)
             cur.wait_event(P.static_done)
-            pending = self.roi_heads.launch_frame(P, self._mem)
+            pending = self.roi_heads.launch_frame(P, self._mem, given_detections[t] if given_detections is not None else None)
             if t + 1 < n_frames:
                 P_next = static(t + 1)
             result, mem = self.roi_heads.finish_frame(pending, next_P=P_next)
@@ -525,7 +529,7 @@ def _forward_clip(self, frames, before_frame=None):
     return results
 
 
-def _forward_clip_three_stage(self, eng, frames, before_frame=None):
+def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detections=None):
     """forward_clip with the frame-independent stage cut in two (developer switch SMOT_CLIP_SPLIT=1):
 
       stream A   B(t): input copy / test transform, backbone, FPN, RPN heads   -- the kernels that fill the GPU
@@ -576,7 +580,7 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None):
             if before_frame is not None:
                 before_frame(t)
             cur.wait_event(P.static_done)          # D(t) complete (hence B(t))
-            pending = self.roi_heads.launch_frame(P, self._mem)
+            pending = self.roi_heads.launch_frame(P, self._mem, given_detections[t] if given_detections is not None else None)
             if t + K - 1 < n_frames:
                 backbone(t + K - 1)                # slot of frame t-1: its slot_free event was recorded in iteration t-1
             if t + 1 < n_frames:

@@ -104,6 +104,7 @@ class Sim(object):
         self.host_mode = True       # False while a queued operation executes (its own tensor ops run directly)
         self.active = False         # interception of tensor ops only while the model runs
         self.executed = 0
+        self.keepalive = []
 
     def current(self):
         return self.stack[-1]
@@ -214,6 +215,20 @@ def install(monkeypatch, policy):
         return wrapper
     for method in ("copy_", "fill_", "zero_"):
         monkeypatch.setattr(torch.Tensor, method, queued(method))
+    # The CUDA caching allocator hands a freed block only to later work of the same stream, so a temporary may die on the
+    # host while kernels that use it are still queued.  Host memory has no such guarantee: keep every buffer allocated while
+    # the model runs alive until the simulation has drained.
+    def keeping(name):
+        orig = getattr(torch, name)
+
+        def wrapper(*a, **k):
+            t = orig(*a, **k)
+            if sim.active and sim.host_mode:
+                sim.keepalive.append(t)
+            return t
+        return wrapper
+    for name in ("zeros", "empty", "full"):
+        monkeypatch.setattr(torch, name, keeping(name))
     orig_gather = engine.Engine.gather_templates
 
     def gather(self, feat, first, sources):

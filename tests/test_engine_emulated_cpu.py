@@ -191,3 +191,54 @@ def test_emulated_flush_memory_accepts_the_reference_memory_tuple(layout, monkey
     assert torch.equal(got.get_field("scores"), ref[2].get_field("scores"))
     with pytest.raises(ValueError):
         model.flush_memory((feats[:, :3], [sr], [boxes]))
+
+
+def _given_scenario():
+    import os
+    from helpers import CONFIG_DIR, YAML_MAP
+    from scenarios import GIVEN_SCENARIOS, given_boxes
+    from siammot_b200.config import get_cfg
+    from siammot_b200.structures import BoxList
+    from siammot_b200.synth_clip import make_clip
+    from siammot_b200.synthetic import make_state_dict
+    sc = GIVEN_SCENARIOS["given_det_192x320"]
+    cfg = get_cfg()
+    cfg.merge_from_file(os.path.join(CONFIG_DIR, YAML_MAP[sc["yaml"]]))
+    cfg.merge_from_list(sc["overrides"])
+    cfg.DTYPE = "float32"
+    clip = make_clip(sc["frames"], sc["H"], sc["W"], sc["n_obj"], sc["clip_seed"])
+    given = []
+    for boxes in given_boxes(sc):
+        n = boxes.shape[0]
+        bl = BoxList(boxes.clone(), (sc["W"], sc["H"]), mode="xyxy")
+        bl.add_field("labels", torch.ones(n, dtype=torch.int64))
+        bl.add_field("scores", torch.ones(n))
+        bl.add_field("ids", torch.full((n,), -1, dtype=torch.int64))
+        given.append([bl])
+    return cfg, make_state_dict(cfg, sc["weight_seed"]), clip, given
+
+
+@pytest.mark.parametrize("mode", ["frame", "clip", "clip3"])
+def test_emulated_public_detections_match_reference_golden(mode, monkeypatch):
+    """given_detection every frame (one frame with none at all) -- per-frame calls and the clip API's given_detections."""
+    from siammot_b200.modelling import build_siammot
+    if mode == "clip3":
+        monkeypatch.setenv("SMOT_CLIP_SPLIT", "1")
+    cabi_emulator.install(monkeypatch)
+    cfg, sd, clip, given = _given_scenario()
+    model = build_siammot(cfg)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    model.reset_siammot_status()
+    gold = load_golden("given_det_192x320")["frames"]
+    if mode == "frame":
+        results = [model(clip[t], given_detection=given[t])[0] for t in range(len(gold))]
+    else:
+        results = model.forward_clip([clip[t] for t in range(len(gold))], given_detections=given)
+    for t, (r, g) in enumerate(zip(results, gold)):
+        assert r.bbox.shape == g["boxes"].shape, "frame %d" % t
+        assert torch.equal(r.get_field("ids"), g["ids"]) and torch.equal(r.get_field("labels"), g["labels"]), "frame %d" % t
+        if g["boxes"].numel():
+            assert float((r.bbox - g["boxes"]).abs().max()) <= BOX_TOL and float((r.get_field("scores") - g["scores"]).abs().max()) <= SCORE_TOL
+    pool = model.roi_heads.track.track_pool
+    assert sorted(pool.get_active_ids()) == gold[-1]["active"] and sorted(pool._dormant_ids) == gold[-1]["dormant"]

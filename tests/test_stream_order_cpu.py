@@ -106,3 +106,31 @@ def test_the_detector_detects_a_missing_edge(monkeypatch):
             if broken:
                 break
         assert broken, "removing the %s edge went unnoticed under every schedule" % attr
+
+
+@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("policy", ["lazy", "workers_eager", ("random", 4)], ids=str)
+def test_public_detection_clip_is_schedule_independent(policy, split, monkeypatch):
+    """forward_clip(frames, given_detections=...): the per-frame box head over external boxes runs on the caller's stream between
+    the detection stage and the track stage of the same frame."""
+    from siammot_b200.modelling import build_siammot
+    from test_engine_emulated_cpu import BOX_TOL, _given_scenario
+    monkeypatch.setenv("SMOT_CLIP_SPLIT", split)
+    sim, fake = stream_sim.install(monkeypatch, policy)
+    cfg, sd, clip, given = _given_scenario()
+    model = build_siammot(cfg)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    model.results_on_host = True
+    model.reset_siammot_status()
+    gold = load_golden("given_det_192x320")["frames"]
+    sim.active = True
+    try:
+        results = model.forward_clip([clip[t] for t in range(len(gold))], given_detections=given)
+        sim.sync_all()
+    finally:
+        sim.active = False
+    for t, (r, g) in enumerate(zip(results, gold)):
+        assert r.bbox.shape == g["boxes"].shape and torch.equal(r.get_field("ids"), g["ids"]), "frame %d" % t
+        if g["boxes"].numel():
+            assert float((r.bbox - g["boxes"]).abs().max()) <= BOX_TOL

@@ -169,6 +169,25 @@ def test_tracker_plugin_contract_on_the_gpu(dtype):
     _plugin_contract_check(model, cfg, sd, clip, to_dev=lambda t: t.to("cuda"))
 
 
+@pytest.mark.xfail(strict=False, reason="forward_clip(given_detections=...) was added after this round's GPU budget was spent; "
+                                       "pinned on the CPU against the reference golden (tests/test_engine_emulated_cpu.py)")
+def test_public_detection_clip_equals_reference_golden():
+    from test_engine_emulated_cpu import BOX_TOL, _given_scenario
+    from siammot_b200.modelling import build_siammot
+    cfg, sd, clip, given = _given_scenario()
+    model = build_siammot(cfg)
+    model.load_state_dict(sd, strict=False)
+    model = model.to("cuda").eval()
+    model.reset_siammot_status()
+    gold = load_golden("given_det_192x320")["frames"]
+    given = [[g[0].to("cuda")] for g in given]
+    results = model.forward_clip([clip[t].to("cuda") for t in range(len(gold))], given_detections=given)
+    for t, (r, g) in enumerate(zip(results, gold)):
+        assert r.bbox.shape == g["boxes"].shape and torch.equal(r.get_field("ids").cpu(), g["ids"]), "frame %d" % t
+        if g["boxes"].numel():
+            assert float((r.bbox.cpu() - g["boxes"]).abs().max()) <= BOX_TOL
+
+
 # (kept last: the only pending cases that launch a kernel with asynchronous copies for the first time)
 # ---- channel-planar search-window exchange (developer switch SMOT_XCORR_PLANAR) -------------------
 PENDING_PLANAR = pytest.mark.xfail(strict=False, reason="smot_roi_align_planar / smot_xcorr_planar were written after this round's "
