@@ -398,8 +398,6 @@ class Engine(object):
                 raise NotImplementedError("ResNet bodies: only the plain FrozenBN bottleneck form (no groups / dilation / DCN)")
         self.C = backbone_channels(cfg)[1]
         self.ncls = cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES
-        if cfg.MODEL.CLS_AGNOSTIC_BBOX_REG:
-            raise NotImplementedError("CLS_AGNOSTIC_BBOX_REG")
         R = cfg.MODEL.RPN
         self.cells = [cell_anchors(st, (sz,), R.ASPECT_RATIOS) for st, sz in zip(R.ANCHOR_STRIDE, R.ANCHOR_SIZES)]
         self.n_anchor = self.cells[0].shape[0]
@@ -507,8 +505,13 @@ class Engine(object):
         w7 = sd[pre + "feature_extractor.fc7.weight"].float()
         Wt["box.fc7"] = (w7.reshape(w7.shape[0], 1, 1, w7.shape[1]).contiguous().to(dev, dt), None,
                          _f32(sd[pre + "feature_extractor.fc7.bias"], dev))
-        wc = torch.cat([sd[pre + "predictor.cls_score.weight"], sd[pre + "predictor.bbox_pred.weight"]], 0).float()
-        bc = torch.cat([sd[pre + "predictor.cls_score.bias"], sd[pre + "predictor.bbox_pred.bias"]], 0)
+        wb, bb = sd[pre + "predictor.bbox_pred.weight"], sd[pre + "predictor.bbox_pred.bias"]
+        if self.cfg.MODEL.CLS_AGNOSTIC_BBOX_REG:
+            # the predictor has two regressors and every class uses the last one (inference.py:66-72: box_regression[:, -4:],
+            # decoded once and repeated per class): replicate that row block per class in the fused GEMM -- same numbers
+            wb, bb = wb[-4:].repeat(self.ncls, 1), bb[-4:].repeat(self.ncls)
+        wc = torch.cat([sd[pre + "predictor.cls_score.weight"], wb], 0).float()
+        bc = torch.cat([sd[pre + "predictor.cls_score.bias"], bb], 0)
         Wt["box.pred"] = (wc.reshape(wc.shape[0], 1, 1, wc.shape[1]).contiguous().to(dev, dt), None, _f32(bc, dev))
         pre = "roi_heads.track.tracker.predictor."
         wt = torch.cat([sd[pre + "cls_tower.0.weight"], sd[pre + "reg_tower.0.weight"]], 0)

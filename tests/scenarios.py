@@ -71,6 +71,10 @@ ORACLE_SCENARIOS = {
                                           "MODEL.DLA.DLA_STAGE5_OUT_CHANNELS", 1024, "MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES", 3,
                                           "MODEL.WEIGHT", "/dev/null"],
                                H=192, W=320, frames=5, n_obj=5, clip_seed=5, weight_seed=32, inject=None),
+    # class-agnostic box regression (upstream MODEL.CLS_AGNOSTIC_BBOX_REG; inference.py:66-72) with two foreground classes
+    "emm_cls_agnostic_192x320": dict(yaml="DLA_34_FPN_EMM.yaml",
+                                     overrides=["MODEL.ROI_BOX_HEAD.NUM_CLASSES", 3, "MODEL.CLS_AGNOSTIC_BBOX_REG", True],
+                                     H=192, W=320, frames=5, n_obj=5, clip_seed=5, weight_seed=3, inject=None),
 }
 
 
