@@ -242,3 +242,41 @@ def test_emulated_public_detections_match_reference_golden(mode, monkeypatch):
             assert float((r.bbox - g["boxes"]).abs().max()) <= BOX_TOL and float((r.get_field("scores") - g["scores"]).abs().max()) <= SCORE_TOL
     pool = model.roi_heads.track.track_pool
     assert sorted(pool.get_active_ids()) == gold[-1]["active"] and sorted(pool._dormant_ids) == gold[-1]["dormant"]
+
+
+def test_emulated_reset_between_videos_and_resolution_change(monkeypatch):
+    """reset_siammot_status() between videos (inferencer.py:157-159): ids restart, results repeat exactly; a video of another
+    resolution gets its own launch plan and arena and leaves the first one's results unchanged when it comes back."""
+    from siammot_b200.modelling import build_siammot
+    from siammot_b200.synth_clip import make_clip
+    cabi_emulator.install(monkeypatch)
+    cfg, sd, clip = scenario_inputs("emm_amodal_expire_192x320")
+    cfg.DTYPE = "float32"
+    model = build_siammot(cfg)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+
+    def run(frames):
+        model.reset_siammot_status()
+        return [model(f)[0] for f in frames]
+
+    a = run(clip[:4])
+    other = make_clip(3, 128, 224, 4, 11)
+    b = run(other)
+    assert all(r.size == (224, 128) for r in b)
+    a2 = run(clip[:4])
+    assert max(int(r.get_field("ids").max()) for r in a if len(r)) >= 0
+    for x, y in zip(a, a2):
+        assert torch.equal(x.bbox, y.bbox) and torch.equal(x.get_field("ids"), y.get_field("ids"))
+        assert torch.equal(x.get_field("scores"), y.get_field("scores"))
+    # 4-D batch-of-one input and an object with .tensors (ImageList) are the same call
+    model.reset_siammot_status()
+    r4 = model(clip[0][None])[0]
+
+    class ImageListLike(object):
+        tensors = clip[0][None]
+    model.reset_siammot_status()
+    rl = model(ImageListLike())[0]
+    assert torch.equal(r4.bbox, a[0].bbox) and torch.equal(rl.bbox, a[0].bbox)
+    with pytest.raises(ValueError):
+        model(torch.zeros(2, 3, 192, 320))
