@@ -346,6 +346,8 @@ class _TrackPlan(object):
         The launch list is replayed as a CUDA graph from its second use on (the first use runs it eagerly, which also
         sets kernel attributes); the template features are copied to the plan's fixed buffer first."""
         eng = self.e
+        if eng.nvtx:
+            torch.cuda.nvtx.range_push("smot/track_stage")
         if self.n and feat.data_ptr() != self.tmpl.data_ptr():
             self.tmpl.copy_(feat.view(self.tmpl.shape), non_blocking=True)
         if eng.use_graph and not (eng.timers is not None and eng.time_kernels) and self.det_is_static:
@@ -362,6 +364,8 @@ class _TrackPlan(object):
         else:
             self._enqueue()
         self.done.record()
+        if eng.nvtx:
+            torch.cuda.nvtx.range_pop()
         if wait:
             self.done.synchronize()
 
@@ -429,6 +433,7 @@ class Engine(object):
         self._arenas = {}
         # developer switch: exchange the EMM search windows channel-planar (smot_roi_align_planar ->
         # smot_xcorr_planar).  Off by default until it has been through the GPU tests.
+        self.nvtx = os.environ.get("SMOT_NVTX", "0") == "1"
         self.xcorr_planar = os.environ.get("SMOT_XCORR_PLANAR", "0") in ("1", "2")   # 2: + trimmed MMA phase (libsmot reads it)
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
         self.time_kernels = False  # also bracket single kernels of the track stage (forces its eager path)
@@ -440,11 +445,14 @@ class Engine(object):
 
     def timed(self, name):
         """Context manager: when self.timers is a dict, brackets the enclosed launches with CUDA events on
-        the launching stream (bench.py's live per-kernel timing)."""
+        the launching stream (bench.py's live per-kernel timing); with SMOT_NVTX=1 also an NVTX range "smot/<name>"
+        (stages: preprocess, static, static_tail, track_stage, next_memory) for `ncu --nvtx --nvtx-include`."""
         eng = self
 
         class _T(object):
             def __enter__(self_inner):
+                if eng.nvtx:
+                    torch.cuda.nvtx.range_push("smot/" + name)
                 if eng.timers is not None:
                     self_inner.e0 = torch.cuda.Event(enable_timing=True)
                     self_inner.e1 = torch.cuda.Event(enable_timing=True)
@@ -454,6 +462,8 @@ class Engine(object):
                 if eng.timers is not None:
                     self_inner.e1.record()
                     eng.timers.setdefault(name, []).append((self_inner.e0, self_inner.e1))
+                if eng.nvtx:
+                    torch.cuda.nvtx.range_pop()
                 return False
         return _T()
 

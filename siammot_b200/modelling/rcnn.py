@@ -277,7 +277,8 @@ class CombinedROIHeads(nn.ModuleDict):
         else:
             scores, ids = self.solver.resolve(kscores, ids, all_track_ids)
         boxes = np.array(kboxes, dtype=np.float32, copy=True)
-        new_mem = self._build_memory(P, boxes, ids, labels, next_P)
+        with self.engine.timed("next_memory"):
+            new_mem = self._build_memory(P, boxes, ids, labels, next_P)
         return self._to_boxlist(boxes, scores, ids, labels, (P.W, P.H)), new_mem
 
     def _to_boxlist(self, boxes, scores, ids, labels, size):

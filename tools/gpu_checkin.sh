@@ -41,6 +41,10 @@ SMOT_XCORR_PLANAR=1 timeout 400 ncu --set full --clock-control none --import-sou
     -o "$OUT/xcorr_planar" -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --experimental off > "$OUT/ncu_xcorr_planar.log" 2>&1
 SMOT_XCORR_PLANAR=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:roi_align_planar_kernel -c 1 -s 3 \
     -o "$OUT/roi_align_planar" -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --experimental off > "$OUT/ncu_roi_align_planar.log" 2>&1
+# memcheck over the kernels that have never run on a GPU (small cases; the sanitizer is 10-50x slower)
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_pending_gpu.py -m gpu -q --runxfail -x \
+    -k "maxpool3x3s2 or track_combine_grouped or roi_align_planar or (xcorr_planar and 3-32)" > "$OUT/sanitizer_memcheck.txt" 2>&1
+echo "memcheck rc=$?" >> "$OUT/sanitizer_memcheck.txt"
 for f in "$OUT"/launches_*.csv; do python tools/launch_report.py "$f" > "${f%.csv}_summary.txt" 2>&1; done
 tail -n 3 "$OUT"/pytest_validated.txt "$OUT"/pytest_pending.txt "$OUT"/smoke.txt
 tail -n 2 "$OUT"/pytest_clip_split_k*.txt
