@@ -509,23 +509,56 @@ def experimental_arms(h, args, frames_dev, frames_u8, hook, ntrk_ref, tp, hbm_pe
         got = ops.xcorr_planar(srp, tmpl)
         same_out = bool(torch.equal(ref, got))
         L = _lib.lib()
-        res["xcorr_planar"] = {"windows_equal_default": same_windows, "output_equal_default": same_out, "algorithmic_bytes": xc_bytes}
+        res["xcorr_planar"] = {"windows_equal_default": same_windows, "output_equal_default": same_out, "algorithmic_bytes": xc_bytes,
+                               "timing": "20 launches per CUDA-event bracket, 10 brackets after 3 warm-up ones; 'graph': the 20 launches "
+                                         "replayed as one CUDA graph (a ~4 us kernel is otherwise paced by the ~8 us Python/ctypes "
+                                         "launch loop, which is also what times the default kernel in `roofline`)"}
+
+        def time_launches(launch):
+            out = {}
+            for how in ("eager", "graph"):
+                try:
+                    if how == "graph":
+                        side = torch.cuda.Stream()
+                        side.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(side):
+                            launch()                         # function attributes are set outside the capture
+                        torch.cuda.current_stream().wait_stream(side)
+                        torch.cuda.synchronize()
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            for _ in range(20):
+                                launch()
+                        run = g.replay
+                    else:
+                        def run():
+                            for _ in range(20):
+                                launch()
+                    ev = []
+                    for i in range(13):
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        run()
+                        b.record()
+                        ev.append((a, b))
+                    torch.cuda.synchronize()
+                    ms = sum(a.elapsed_time(b) / 20 for a, b in ev[3:]) / max(len(ev) - 3, 1)
+                    gbs = xc_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+                    out[how] = {"us_per_launch": round(ms * 1e3, 2), "achieved_gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)}
+                except Exception as exc:
+                    out[how] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            return out
+
+        dflt = torch.empty_like(ref)
+        res["xcorr_planar"]["default_kernel"] = time_launches(
+            lambda: check(L.smot_xcorr(ops._ptr(srf), ops._ptr(tmpl), ops._ptr(dflt), n, Cc, 30, 15, _lib.F16, stream_ptr()), "xcorr"))
         for mode, key in ((0, "mma_phase_of_default_kernel"), (1, "trimmed_mma_phase")):
             trim = ops.xcorr_planar(srp, tmpl, mma_mode=mode)
             close = float((trim.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-6))
-            ev = []
-            for i in range(13):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(20):
-                    check(L.smot_xcorr_planar_mode(ops._ptr(srp), ops._ptr(tmpl), ops._ptr(got), n, Cc, mode, stream_ptr()), "xcorr_planar")
-                b.record()
-                ev.append((a, b))
-            torch.cuda.synchronize()
-            ms = sum(a.elapsed_time(b) / 20 for a, b in ev[3:]) / max(len(ev) - 3, 1)
-            gbs = xc_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-            res["xcorr_planar"][key] = {"us_per_launch": round(ms * 1e3, 2), "achieved_gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 4),
-                                        "max_rel_diff_vs_default": round(close, 6)}
+            t = time_launches(lambda: check(L.smot_xcorr_planar_mode(ops._ptr(srp), ops._ptr(tmpl), ops._ptr(got), n, Cc, mode,
+                                                                     stream_ptr()), "xcorr_planar"))
+            t["max_rel_diff_vs_default"] = round(close, 6)
+            res["xcorr_planar"][key] = t
     except Exception as exc:
         res["xcorr_planar"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     return res

@@ -369,6 +369,13 @@ class _Stream(object):
         pass
 
 
+class _Graph(object):
+    """torch.cuda.CUDAGraph stand-in: "capture" runs the launches once, replay does nothing (timings are meaningless here)."""
+
+    def replay(self):
+        pass
+
+
 def install(monkeypatch):
     """Route the product's libsmot calls to FakeLib and neutralise the CUDA runtime objects.  Returns the FakeLib."""
     from siammot_b200 import _lib, engine, ops, preprocess
@@ -385,6 +392,8 @@ def install(monkeypatch):
     monkeypatch.setattr(torch.cuda, "Stream", _Stream)
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", _Graph)
+    monkeypatch.setattr(torch.cuda, "graph", lambda g, *a, **k: contextlib.nullcontext())
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
 
     def host_engine(self):

@@ -50,6 +50,8 @@ def test_bench_gpu_arm_control_flow_and_json_contract(monkeypatch):
     for k in ("three_stage_clip_k2", "three_stage_clip_k3"):
         assert ex[k].get("same_tracks_as_two_stream") is True, ex[k]
     assert ex["xcorr_planar"].get("windows_equal_default") is True and ex["xcorr_planar"].get("output_equal_default") is True, ex["xcorr_planar"]
+    for k in ("default_kernel", "mma_phase_of_default_kernel", "trimmed_mma_phase"):
+        assert "us_per_launch" in ex["xcorr_planar"][k]["eager"] and "us_per_launch" in ex["xcorr_planar"][k]["graph"], ex["xcorr_planar"][k]
 
 
 def test_bench_experimental_child_mode(monkeypatch):
