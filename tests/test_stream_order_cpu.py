@@ -134,3 +134,30 @@ def test_public_detection_clip_is_schedule_independent(policy, split, monkeypatc
         assert r.bbox.shape == g["boxes"].shape and torch.equal(r.get_field("ids"), g["ids"]), "frame %d" % t
         if g["boxes"].numel():
             assert float((r.bbox - g["boxes"]).abs().max()) <= BOX_TOL
+
+
+@pytest.mark.parametrize("policy", ["lazy", "workers_eager", ("random", 6)], ids=str)
+def test_device_resident_results_are_schedule_independent(policy, monkeypatch):
+    """results_on_host = False (the reference contract): every frame's BoxList fields are views of a device block filled by an
+    asynchronous copy from ONE pinned buffer that the next frame rewrites -- the copy must have run before that rewrite."""
+    from siammot_b200.modelling import build_siammot
+    gold = load_golden(NAME)["frames"]
+    for mode in ("frame", "clip"):
+        with pytest.MonkeyPatch.context() as mp:
+            sim, fake = stream_sim.install(mp, policy)
+            cfg, sd, clip = scenario_inputs(NAME)
+            cfg.DTYPE = "float32"
+            model = build_siammot(cfg)
+            model.load_state_dict(sd, strict=False)
+            model.eval()
+            model.reset_siammot_status()
+            sim.active = True
+            try:
+                res = [model(f)[0] for f in clip] if mode == "frame" else model.forward_clip(list(clip))
+                sim.sync_all()
+            finally:
+                sim.active = False
+            for t, (r, g) in enumerate(zip(res, gold)):
+                assert r.bbox.shape == g["boxes"].shape and torch.equal(r.get_field("ids"), g["ids"]), (mode, t)
+                if g["boxes"].numel():
+                    assert float((r.bbox - g["boxes"]).abs().max()) <= 1e-3, (mode, t)
