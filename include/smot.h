@@ -91,6 +91,13 @@ int smot_maxpool2x2(const void* in, void* out, int batch, int H, int W, int C, i
  * modeling/backbone/resnet.py BaseStem.forward; the "R-50-FPN" body).  out is ((H-1)/2+1) x ((W-1)/2+1). */
 int smot_maxpool3x3s2(const void* in, void* out, int batch, int H, int W, int C, int in_ld, int out_ld, int dtype,
                       void* stream);
+/* The gather of a deformable 3x3 convolution (DCN v1; upstream layers/dcn DeformConv reached through DFConv2d at
+ * siammot/modelling/backbone/dla.py:74-78, MODEL.DLA.STAGE_WITH_DCN): cols[oy][ox][k*C + c] = bilinear sample of input channel c
+ * at (oy*stride - 1 + i + dy, ox*stride - 1 + j + dx), k = 3i + j, (dy, dx) = offsets[oy][ox][2k], [2k+1] (fp32, from the regular
+ * offset conv); zero outside the map.  The deformable conv itself is then smot_conv2d (1x1) over the 9*C columns with the 3x3
+ * weight [Cout][3][3][C] read as [Cout][9*C].  3x3, pad 1, stride 1 or 2, dilation 1. */
+int smot_deform_im2col3x3(const void* in, const float* offsets, void* cols, int H, int W, int C, int in_ld, int off_ld, int OH,
+                          int OW, int out_ld, int stride, int dtype, void* stream);
 /* lateral += bilinear_resize(top -> HxW, align_corners=False)   (fpn_patch.py:49-51). */
 int smot_upsample_add(const void* top, int Ht, int Wt, int top_ld, void* lateral, int H, int W, int lat_ld, int C,
                       int dtype, void* stream);

@@ -47,12 +47,50 @@ def _basic_block(P, pre, x, stride, residual=None):
     return _conv_bn(P, y, pre + ".conv2", pre + ".bn2", 1, 1, relu=True, residual=residual)
 
 
+def deform_conv3x3(x, offset, weight, stride):
+    """DCN v1 (upstream layers/dcn DeformConv, reached through DFConv2d at dla.py:74-78), 3x3 / pad 1, restated from the published
+    operator: output pixel (oy, ox), tap k = 3i + j samples the input at (oy*stride - 1 + i + dy, ox*stride - 1 + j + dx) with
+    (dy, dx) = offset channels (2k, 2k+1), bilinearly, corners outside the map contributing zero.  Cross-checked against
+    torchvision.ops.deform_conv2d in tests/test_oracle_dla_family_cpu.py."""
+    B, C, H, W = x.shape
+    assert B == 1
+    OH, OW = offset.shape[2], offset.shape[3]
+    oy = torch.arange(OH, dtype=torch.float32).view(OH, 1) * stride - 1
+    ox = torch.arange(OW, dtype=torch.float32).view(1, OW) * stride - 1
+    cols = []
+    img = x[0]
+    for k in range(9):
+        i, j = divmod(k, 3)
+        yy = oy + i + offset[0, 2 * k]
+        xx = ox + j + offset[0, 2 * k + 1]
+        inside = (yy > -1) & (yy < H) & (xx > -1) & (xx < W)
+        y0, x0 = torch.floor(yy), torch.floor(xx)
+        ly, lx = yy - y0, xx - x0
+        acc = torch.zeros((C, OH, OW))
+        for dy_, dx_, wgt in ((0, 0, (1 - ly) * (1 - lx)), (0, 1, (1 - ly) * lx), (1, 0, ly * (1 - lx)), (1, 1, ly * lx)):
+            yi, xi = (y0 + dy_).long(), (x0 + dx_).long()
+            ok = inside & (yi >= 0) & (yi < H) & (xi >= 0) & (xi < W)
+            v = img[:, yi.clamp(0, H - 1), xi.clamp(0, W - 1)]
+            acc = acc + v * (wgt * ok)[None]
+        cols.append(acc)
+    col = torch.stack(cols, 1)                                   # (C, 9, OH, OW)
+    return torch.einsum("ock,ckhw->ohw", weight.reshape(weight.shape[0], C, 9), col)[None]
+
+
 def _bottleneck_block(P, pre, x, stride, residual=None):
-    """DlaBottleneck.forward (dla.py:81-101), cardinality 1 / base width 64: 1x1 -> 3x3 (stride) -> 1x1, + residual, ReLU."""
+    """DlaBottleneck.forward (dla.py:81-101), cardinality 1 / base width 64: 1x1 -> 3x3 (stride) -> 1x1, + residual, ReLU.
+    With MODEL.DLA.STAGE_WITH_DCN the 3x3 is upstream's DFConv2d (dla.py:74-78): offsets from a regular 3x3 conv with bias."""
     if residual is None:
         residual = x
     y = _conv_bn(P, x, pre + ".conv1", pre + ".bn1", 1, 0, relu=True)
-    y = _conv_bn(P, y, pre + ".conv2", pre + ".bn2", stride, 1, relu=True)
+    if (pre + ".conv2.offset.weight") in P:
+        off = F.conv2d(y, P[pre + ".conv2.offset.weight"], P[pre + ".conv2.offset.bias"], stride, 1)
+        y = deform_conv3x3(y, off, P[pre + ".conv2.conv.weight"], stride)
+        scale, bias = prims.frozen_bn_scale_bias(P[pre + ".bn2.weight"], P[pre + ".bn2.bias"], P[pre + ".bn2.running_mean"],
+                                                 P[pre + ".bn2.running_var"])
+        y = F.relu(y * scale.reshape(1, -1, 1, 1) + bias.reshape(1, -1, 1, 1))
+    else:
+        y = _conv_bn(P, y, pre + ".conv2", pre + ".bn2", stride, 1, relu=True)
     return _conv_bn(P, y, pre + ".conv3", pre + ".bn3", 1, 0, relu=True, residual=residual)
 
 

@@ -40,7 +40,7 @@ class RpnLevel(C.Structure):
 _lib = None
 
 # kernels launched by one call of each entry point (memsets not counted); used for bench.py's gpu_launches
-KERNELS_PER_CALL = {"smot_conv2d": 1, "smot_image_to_nhwc": 1, "smot_maxpool2x2": 1, "smot_maxpool3x3s2": 1, "smot_upsample_add": 1,
+KERNELS_PER_CALL = {"smot_conv2d": 1, "smot_image_to_nhwc": 1, "smot_maxpool2x2": 1, "smot_maxpool3x3s2": 1, "smot_deform_im2col3x3": 1, "smot_upsample_add": 1,
                     "smot_subsample2": 1, "smot_groupnorm_relu": 1, "smot_roi_align": 1, "smot_rpn_select": 6,
                     "smot_sort_nms": 3, "smot_box_decode": 1, "smot_track_combine": 1, "smot_track_combine_grouped": 1, "smot_xcorr": 1, "smot_emm_decode": 2,
                     "smot_roi_align_planar": 1, "smot_xcorr_planar": 1, "smot_xcorr_planar_mode": 1,
@@ -57,6 +57,7 @@ def _declare(lib):
         "smot_image_to_nhwc": [vp, vp, i, i, i, i, i, vp],
         "smot_maxpool2x2": [vp, vp, i, i, i, i, i, i, i, vp],
         "smot_maxpool3x3s2": [vp, vp, i, i, i, i, i, i, i, vp],
+        "smot_deform_im2col3x3": [vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp],
         "smot_upsample_add": [vp, i, i, i, vp, i, i, i, i, i, vp],
         "smot_subsample2": [vp, vp, i, i, i, i, i, i, vp],
         "smot_groupnorm_relu": [vp, vp, vp, i, i, i, i, i, f, i, i, vp],

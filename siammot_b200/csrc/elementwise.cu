@@ -89,6 +89,46 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ in, T* __restrict__ ou
   st4(out + pix * out_ld + c, r);
 }
 
+// ---- deformable 3x3 sampling (DCN v1: upstream layers/dcn deform_im2col, reached through DFConv2d at dla.py:74-78) ----
+// cols[oy][ox][k*C + c] = bilinear sample of channel c at (oy*stride - 1 + i + dy, ox*stride - 1 + j + dx), k = 3i + j,
+// (dy, dx) = offsets[oy][ox][2k], [2k+1]; a sample position outside (-1, H) x (-1, W) is zero and so is every corner outside
+// the map.  The deformable convolution is then a plain GEMM over the 9*C "channels" of `cols` (smot_conv2d, 1x1) with the
+// 3x3 weight viewed as [Cout][9*C] -- the gather is the only part that is not a dense contraction.
+// One thread = 4 channels of one (pixel, tap); corner reads of neighbouring threads are contiguous.
+template <typename T>
+__global__ void deform_im2col3x3_kernel(const T* __restrict__ in, const float* __restrict__ off, T* __restrict__ cols, int H, int W,
+                                        int C, int in_ld, int off_ld, int OH, int OW, int out_ld, int stride) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C4 = C / 4;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)OH * OW * 9 * C4) return;
+  const int c = (int)(idx % C4) * 4;
+  size_t r = idx / C4;
+  const int k = (int)(r % 9);
+  const size_t pix = r / 9;
+  const int ox = (int)(pix % OW), oy = (int)(pix / OW);
+  const float* o = off + pix * off_ld + 2 * k;
+  const float y = (float)(oy * stride - 1 + k / 3) + o[0];
+  const float x = (float)(ox * stride - 1 + k % 3) + o[1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (y > -1.f && y < (float)H && x > -1.f && x < (float)W) {
+    const float yf = floorf(y), xf = floorf(x);
+    const int y0 = (int)yf, x0 = (int)xf;
+    const float ly = y - yf, lx = x - xf, hy = 1.f - ly, hx = 1.f - lx;
+    const float w[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yi = y0 + (q >> 1), xi = x0 + (q & 1);
+      if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+        const float4 v = ld4(in + ((size_t)yi * W + xi) * in_ld + c);
+        acc.x += w[q] * v.x, acc.y += w[q] * v.y, acc.z += w[q] * v.z, acc.w += w[q] * v.w;
+      }
+    }
+  }
+  st4(cols + pix * out_ld + (size_t)k * C + c, acc);
+}
+
 // ---- lateral += bilinear(top), align_corners=False (ATen upsample_bilinear2d index rule) -----
 template <typename T>
 __global__ void upsample_add_kernel(const T* __restrict__ top, int Ht, int Wt, int top_ld, T* __restrict__ lat, int H,
@@ -334,6 +374,24 @@ extern "C" int smot_maxpool3x3s2(const void* in, void* out, int batch, int H, in
   else
     SMOT_CHECK_ARG(false, "smot_maxpool3x3s2: bad dtype %d", dtype);
   SMOT_CHECK_LAUNCH("smot_maxpool3x3s2");
+  return SMOT_OK;
+}
+
+extern "C" int smot_deform_im2col3x3(const void* in, const float* offsets, void* cols, int H, int W, int C, int in_ld, int off_ld,
+                                     int OH, int OW, int out_ld, int stride, int dtype, void* stream) {
+  SMOT_CHECK_ARG(in && offsets && cols && H > 0 && W > 0 && C > 0 && C % 4 == 0 && in_ld % 4 == 0 && out_ld % 4 == 0 && off_ld >= 18,
+                 "smot_deform_im2col3x3: bad arguments (C, in_ld, out_ld multiples of 4; off_ld >= 18)");
+  SMOT_CHECK_ARG((stride == 1 || stride == 2) && OH == (H - 1) / stride + 1 && OW == (W - 1) / stride + 1 && out_ld >= 9 * C,
+                 "smot_deform_im2col3x3: geometry (3x3, pad 1, stride %d: %dx%d -> %dx%d, out_ld %d)", stride, H, W, OH, OW, out_ld);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)OH * OW * 9 * (C / 4);
+  if (dtype == SMOT_F32)
+    launch_pdl(deform_im2col3x3_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const float*)in, offsets, (float*)cols, H, W, C, in_ld, off_ld, OH, OW, out_ld, stride);
+  else if (dtype == SMOT_F16)
+    launch_pdl(deform_im2col3x3_kernel<__half>, dim3(blocks_for(total, 256)), dim3(256), 0, st, (const __half*)in, offsets, (__half*)cols, H, W, C, in_ld, off_ld, OH, OW, out_ld, stride);
+  else
+    SMOT_CHECK_ARG(false, "smot_deform_im2col3x3: bad dtype %d", dtype);
+  SMOT_CHECK_LAUNCH("smot_deform_im2col3x3");
   return SMOT_OK;
 }
 

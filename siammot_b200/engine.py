@@ -392,8 +392,6 @@ class Engine(object):
             raise NotImplementedError("body %s: implemented are %s (dla.py:307-372; DLA-34-FPN is the SURVEY.md section 8 path) and "
                                       "%s (upstream resnet.py; R-50-FPN is BASELINE.json configs[4])"
                                       % (cfg.MODEL.BACKBONE.CONV_BODY, ", ".join(sorted(DLA_ARCHS)), ", ".join(sorted(RESNET_BLOCKS))))
-        if cfg.MODEL.BACKBONE.CONV_BODY in DLA_ARCHS and any(cfg.MODEL.DLA.STAGE_WITH_DCN):
-            raise NotImplementedError("MODEL.DLA.STAGE_WITH_DCN (deformable convolutions)")
         self.resnet = is_resnet(cfg)
         if self.resnet:
             R = cfg.MODEL.RESNETS
@@ -487,6 +485,17 @@ class Engine(object):
                 conv = k[:-len(".weight")]
                 leaf = conv.rsplit(".", 1)[1]
                 parent = conv.rsplit(".", 1)[0]
+                if conv.endswith(".conv2.offset"):
+                    # DFConv2d's offset predictor (MODEL.DLA.STAGE_WITH_DCN): a regular 3x3 conv with bias, no FrozenBN
+                    Wt[conv[len("backbone."):]] = (_ohwi(sd[k], dt, dev), None, _f32(sd[conv + ".bias"], dev))
+                    continue
+                if conv.endswith(".conv2.conv"):
+                    # ... and its deformable conv: the 3x3 weight read as [Cout][9*Cin] over the sampled columns, then bn2
+                    blk = conv[:-len(".conv2.conv")]
+                    s_, b_ = bn(blk + ".bn2")
+                    w = _ohwi(sd[k], dt, dev)
+                    Wt[conv[len("backbone."):]] = (w.reshape(w.shape[0], 1, 1, -1).contiguous(), s_, b_)
+                    continue
                 if leaf in ("conv1", "conv2", "conv3"):
                     bnn = parent + ".bn" + leaf[-1]
                 elif leaf == "conv":
@@ -583,7 +592,7 @@ class Engine(object):
         return self._tree(P, name + ".tree2", t1, 1, cout, cout, 1, False, out=out, rootbuf=rootbuf)
 
     def _tree_general(self, P, name, x, levels, cin, cout, stride, level_root, bottleneck, root_residual, out=None, rootbuf=None,
-                      off=None):
+                      off=None, with_dcn=False):
         """DlaTree of any depth with either block type (the DLA family beyond DLA-34: dla.py:316-372), concat-free.
         The innermost tree2 of a nest owns the root (dla.py:209-210); its input [x2 | x1 | bottom? | x1 of every enclosing
         tree, outermost first] (dla.py:229-237) is ONE buffer allocated where the nest starts: every producer writes its
@@ -608,9 +617,10 @@ class Engine(object):
             P.call(lib().smot_maxpool2x2, self._pool_args(x, bottom), "maxpool:" + name)
         if levels > 1:
             t1 = rootbuf[..., off:off + cout]
-            self._tree_general(P, name + ".tree1", x, levels - 1, cin, cout, stride, False, bottleneck, root_residual, out=t1)
+            self._tree_general(P, name + ".tree1", x, levels - 1, cin, cout, stride, False, bottleneck, root_residual, out=t1,
+                               with_dcn=with_dcn)
             return self._tree_general(P, name + ".tree2", t1, levels - 1, cout, cout, 1, False, bottleneck, root_residual,
-                                      out=out, rootbuf=rootbuf, off=off + cout)
+                                      out=out, rootbuf=rootbuf, off=off + cout, with_dcn=with_dcn)
         assert off == rootbuf.shape[3], (name, off, rootbuf.shape)
         if cin != cout:
             residual = P.new(Ho, Wo, cout)
@@ -623,7 +633,18 @@ class Engine(object):
             if bottleneck:                                     # DlaBottleneck (dla.py:63-101): mid = out / 2
                 mid = cout // 2
                 a = P.conv(inp, pre + ".conv1", P.new(inp.shape[1], inp.shape[2], mid), relu=True)
-                b = P.conv(a, pre + ".conv2", P.new(Ho, Wo, mid), stride=s, pad=1, relu=True)
+                if with_dcn and bottleneck:
+                    # DFConv2d (dla.py:74-78): offsets from a regular 3x3 conv (fp32), bilinear gather of the 9 taps, then the
+                    # deformable conv proper as a GEMM over the 9*mid gathered columns (+ bn2 + ReLU in its epilogue)
+                    offs = P.new(Ho, Wo, 20, dtype=torch.float32)
+                    P.conv(a, pre + ".conv2.offset", offs[..., :18], stride=s, pad=1)
+                    cols = P.new(Ho, Wo, 9 * mid)
+                    P.call(lib().smot_deform_im2col3x3, (ops._ptr(a), ops._ptr(offs), ops._ptr(cols), a.shape[1], a.shape[2], mid,
+                                                          ops._nhwc(a)[4], 20, Ho, Wo, 9 * mid, s, _lib.dtype_code(self.dtype)),
+                           "deform_im2col:" + pre)
+                    b = P.conv(cols, pre + ".conv2.conv", P.new(Ho, Wo, mid), relu=True)
+                else:
+                    b = P.conv(a, pre + ".conv2", P.new(Ho, Wo, mid), stride=s, pad=1, relu=True)
                 P.conv(b, pre + ".conv3", outv, residual=res, relu=True)
             else:                                              # DlaBasic (dla.py:30-57)
                 a = P.conv(inp, pre + ".conv1", P.new(Ho, Wo, cout), stride=s, pad=1, relu=True)
@@ -649,7 +670,7 @@ class Engine(object):
         outs = []
         for lvl in range(2, 6):
             x = self._tree_general(P, "level%d" % lvl, x, lv[lvl], ch[lvl - 1], ch[lvl], 2, lvl > 2, A["block"] == "bottleneck",
-                                   A["residual_root"])
+                                   A["residual_root"], with_dcn=bool(self.cfg.MODEL.DLA.STAGE_WITH_DCN[lvl]))
             outs.append(x)
         return outs
 

@@ -124,6 +124,19 @@ def maxpool3x3s2(x, out=None):
     return out
 
 
+def deform_im2col3x3(x, offsets, stride=1, out=None):
+    """x (1,H,W,C) NHWC, offsets fp32 (1,OH,OW,>=18) -> columns (1,OH,OW,9*C) of a deformable 3x3 / pad 1 convolution."""
+    _require_cuda(x, offsets)
+    B, H, W, Cc, ld = _nhwc(x)
+    Bo, OH, OW, _, old = _nhwc(offsets)
+    assert B == 1 and Bo == 1 and offsets.dtype == torch.float32
+    if out is None:
+        out = torch.empty((1, OH, OW, 9 * Cc), dtype=x.dtype, device=x.device)
+    check(lib().smot_deform_im2col3x3(_ptr(x), _ptr(offsets), _ptr(out), H, W, Cc, ld, old, OH, OW, _nhwc(out)[4], stride,
+                                      dtype_code(x.dtype), stream_ptr()), "smot_deform_im2col3x3")
+    return out
+
+
 def upsample_add_(lateral, top):
     _require_cuda(lateral, top)
     _, H, W, Cc, lld = _nhwc(lateral)

@@ -60,9 +60,11 @@ DLA_ARCHS = {
 }
 
 
-def dla_layout(arch):
+def dla_layout(arch, dcn=(False,) * 6):
     """(kind, name, shape) of every parameter group of a DLA body in the reference's module order (dla.py:241-304): DlaTree
-    registers tree1, tree2, then root (levels == 1), then project; DlaBottleneck has mid = out / 2 channels (dla.py:63-96)."""
+    registers tree1, tree2, then root (levels == 1), then project; DlaBottleneck has mid = out / 2 channels (dla.py:63-96).
+    dcn[level]: MODEL.DLA.STAGE_WITH_DCN -- the bottlenecks' 3x3 becomes upstream's DFConv2d (dla.py:74-78): kind "convb"
+    (conv with bias) for its offset predictor, then the deformable conv's weight.  DlaBasic ignores the flag (dla.py:33 **_)."""
     A = DLA_ARCHS[arch]
     ch, levels, bottleneck = A["channels"], A["levels"], A["block"] == "bottleneck"
     out = [("conv", "base_layer.0", (ch[0], 3, 7, 7)), ("bn", "base_layer.1", ch[0])]
@@ -74,33 +76,37 @@ def dla_layout(arch):
     conv_level("level0", ch[0], ch[0], levels[0])
     conv_level("level1", ch[0], ch[1], levels[1])
 
-    def block(pre, cin, cout):
+    def block(pre, cin, cout, with_dcn=False):
         if bottleneck:
             mid = cout // 2
-            out.extend([("conv", pre + ".conv1", (mid, cin, 1, 1)), ("bn", pre + ".bn1", mid),
-                        ("conv", pre + ".conv2", (mid, mid, 3, 3)), ("bn", pre + ".bn2", mid),
+            out.extend([("conv", pre + ".conv1", (mid, cin, 1, 1)), ("bn", pre + ".bn1", mid)])
+            if with_dcn:
+                out.extend([("convb", pre + ".conv2.offset", (18, mid, 3, 3)), ("conv", pre + ".conv2.conv", (mid, mid, 3, 3))])
+            else:
+                out.append(("conv", pre + ".conv2", (mid, mid, 3, 3)))
+            out.extend([("bn", pre + ".bn2", mid),
                         ("conv", pre + ".conv3", (cout, mid, 1, 1)), ("bn", pre + ".bn3", cout)])
         else:
             out.extend([("conv", pre + ".conv1", (cout, cin, 3, 3)), ("bn", pre + ".bn1", cout),
                         ("conv", pre + ".conv2", (cout, cout, 3, 3)), ("bn", pre + ".bn2", cout)])
 
-    def tree(pre, lv, cin, cout, level_root, root_dim=0):
+    def tree(pre, lv, cin, cout, level_root, with_dcn, root_dim=0):
         if root_dim == 0:
             root_dim = 2 * cout
         if level_root:
             root_dim += cin
         if lv == 1:
-            block(pre + ".tree1", cin, cout)
-            block(pre + ".tree2", cout, cout)
+            block(pre + ".tree1", cin, cout, with_dcn)
+            block(pre + ".tree2", cout, cout, with_dcn)
             out.extend([("conv", pre + ".root.conv", (cout, root_dim, 1, 1)), ("bn", pre + ".root.bn", cout)])
         else:
-            tree(pre + ".tree1", lv - 1, cin, cout, False, 0)
-            tree(pre + ".tree2", lv - 1, cout, cout, False, root_dim + cout)
+            tree(pre + ".tree1", lv - 1, cin, cout, False, with_dcn, 0)
+            tree(pre + ".tree2", lv - 1, cout, cout, False, with_dcn, root_dim + cout)
         if cin != cout:
             out.extend([("conv", pre + ".project.0", (cout, cin, 1, 1)), ("bn", pre + ".project.1", cout)])
 
     for lvl in range(2, 6):
-        tree("level%d" % lvl, levels[lvl], ch[lvl - 1], ch[lvl], lvl > 2)
+        tree("level%d" % lvl, levels[lvl], ch[lvl - 1], ch[lvl], lvl > 2, bool(dcn[lvl]) and bottleneck)
     return out
 
 
@@ -136,7 +142,7 @@ def body_layout(cfg):
     if body == "DLA-34-FPN":
         return dla34_layout()
     if body in DLA_ARCHS:
-        return dla_layout(body)
+        return dla_layout(body, tuple(cfg.MODEL.DLA.STAGE_WITH_DCN))
     if body in RESNET_BLOCKS:
         R = cfg.MODEL.RESNETS
         return resnet50_layout(RESNET_BLOCKS[body], R.STEM_OUT_CHANNELS, R.RES2_OUT_CHANNELS, R.NUM_GROUPS * R.WIDTH_PER_GROUP)
@@ -170,6 +176,10 @@ def make_state_dict(cfg, seed=1):
         if kind == "conv":
             fan_in = shape[1] * shape[2] * shape[3]
             sd[key + ".weight"] = randn(*shape, std=math.sqrt(2.0 / fan_in))
+        elif kind == "convb":   # DFConv2d's offset predictor: offsets of a fraction of a pixel up to ~2 px
+            fan_in = shape[1] * shape[2] * shape[3]
+            sd[key + ".weight"] = randn(*shape, std=0.7 / math.sqrt(fan_in))
+            sd[key + ".bias"] = randn(shape[0], std=0.3)
         else:
             # the branch that is added to the identity gets a smaller gain so that activations stay O(1) with depth
             # (16 bottleneck blocks in the ResNet: a much smaller gain than for DLA's 8 basic blocks)

@@ -43,6 +43,27 @@ def _rows(p, n, width, stride):
     return _f32(p, (n - 1) * stride + width).as_strided((n, width), (stride, 1))
 
 
+def deform_columns(inp, off, cols, H, W, Cc, ild, oild, OH, OW, old, stride):
+    """Specification of smot_deform_im2col3x3 (DCN v1 sampling) on host pointers, vectorised."""
+    x = _view(inp, 1, H, W, Cc, ild)[0]                       # (H, W, C)
+    o = _view(off, 1, OH, OW, 18, oild)[0]                    # (OH, OW, 18)
+    out = _view(cols, 1, OH, OW, 9 * Cc, old)[0]
+    oy = torch.arange(OH, dtype=torch.float32).view(OH, 1) * stride - 1
+    ox = torch.arange(OW, dtype=torch.float32).view(1, OW) * stride - 1
+    for k in range(9):
+        i, j = divmod(k, 3)
+        yy, xx = oy + i + o[..., 2 * k], ox + j + o[..., 2 * k + 1]
+        inside = (yy > -1) & (yy < H) & (xx > -1) & (xx < W)
+        y0, x0 = torch.floor(yy), torch.floor(xx)
+        ly, lx = yy - y0, xx - x0
+        acc = torch.zeros((OH, OW, Cc))
+        for dy_, dx_, wgt in ((0, 0, (1 - ly) * (1 - lx)), (0, 1, (1 - ly) * lx), (1, 0, ly * (1 - lx)), (1, 1, ly * lx)):
+            yi, xi = (y0 + dy_).long(), (x0 + dx_).long()
+            ok = inside & (yi >= 0) & (yi < H) & (xi >= 0) & (xi < W)
+            acc = acc + x[yi.clamp(0, H - 1), xi.clamp(0, W - 1)] * (wgt * ok)[..., None]
+        out[..., k * Cc:(k + 1) * Cc] = acc
+
+
 class FakeLib(object):
     """Entry points of include/smot.h, fp32 only, on host pointers.  Every method returns SMOT_OK (0)."""
 
@@ -107,6 +128,11 @@ class FakeLib(object):
 
     def smot_maxpool3x3s2(self, *a):
         return self._pool("smot_maxpool3x3s2", *a)
+
+    def smot_deform_im2col3x3(self, inp, off, cols, H, W, Cc, ild, oild, OH, OW, old, stride, dt, st):
+        self._count("smot_deform_im2col3x3")
+        deform_columns(_a(inp), _a(off), _a(cols), H, W, Cc, ild, oild, OH, OW, old, stride)
+        return 0
 
     def smot_subsample2(self, inp, out, H, W, Cc, ild, old, dt, st):
         self._count("smot_subsample2")

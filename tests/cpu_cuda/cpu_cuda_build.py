@@ -37,6 +37,7 @@ def generate():
              _function_text(roi, r"__global__ void __launch_bounds__\(256\) roi_align_planar_kernel")
              .replace("extern __shared__ __align__(16) unsigned char rap_raw[];", "unsigned char* rap_raw = cpu_dynamic_smem;"),
              _function_text(elt, r"__global__ void maxpool3x3s2_kernel"),
+             _function_text(elt, r"__global__ void deform_im2col3x3_kernel"),
              _function_text(sel, r"__global__ void track_combine_grouped_kernel"),
              "}  // namespace smot", """
 using namespace smot;
@@ -58,6 +59,12 @@ extern "C" void cpu_roi_align(const smot_pyramid* pyr, const float* rois, const 
 extern "C" void cpu_maxpool3x3s2(const float* in, float* out, int batch, int H, int W, int C, int in_ld, int out_ld) {
   const size_t total = (size_t)batch * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / 4);
   cpu_launch(dim3((unsigned)((total + 63) / 64)), dim3(64), [&] { maxpool3x3s2_kernel<float>(in, out, batch, H, W, C, in_ld, out_ld); });
+}
+extern "C" void cpu_deform_im2col3x3(const float* in, const float* off, float* cols, int H, int W, int C, int in_ld, int off_ld,
+                                     int OH, int OW, int out_ld, int stride) {
+  const size_t total = (size_t)OH * OW * 9 * (C / 4);
+  cpu_launch(dim3((unsigned)((total + 63) / 64)), dim3(64),
+             [&] { deform_im2col3x3_kernel<float>(in, off, cols, H, W, C, in_ld, off_ld, OH, OW, out_ld, stride); });
 }
 extern "C" void cpu_track_combine_grouped(const float* det_boxes, const float* det_scores, int ncap, const float* dec_boxes,
                                           const float* dec_scores, int ncls, const int* labels, const float* conf, const int* valid,
@@ -117,7 +124,15 @@ def generate_xcorr():
               _function_text(roi, r"__global__ void roi_align_kernel"),
               _function_text(roi, r"__global__ void __launch_bounds__\(256\) roi_align_planar_kernel")
               .replace("extern __shared__ __align__(16) unsigned char rap_raw[];", "unsigned char* rap_raw = cpu_dynamic_smem;"),
-              _function_text(elt, r"__global__ void maxpool3x3s2_kernel"), "}  // namespace smot", """
+              _function_text(elt, r"__global__ void maxpool3x3s2_kernel"),
+              _function_text(elt, r"__global__ void deform_im2col3x3_kernel"), "}  // namespace smot", """
+extern "C" void cpu_deform_im2col3x3_h(const void* in, const float* off, void* cols, int H, int W, int C, int in_ld, int off_ld,
+                                       int OH, int OW, int out_ld, int stride) {
+  const size_t total = (size_t)OH * OW * 9 * (C / 4);
+  cpu_launch(dim3((unsigned)((total + 63) / 64)), dim3(64), [&] {
+    smot::deform_im2col3x3_kernel<__half>((const __half*)in, off, (__half*)cols, H, W, C, in_ld, off_ld, OH, OW, out_ld, stride);
+  });
+}
 extern "C" void cpu_roi_align_h(const smot_pyramid* pyr, const float* rois, const float* level_boxes, const int* count, int max_rois,
                                 int channels, int res, int sampling, void* out) {
   smot::RoiArgs a;

@@ -8,7 +8,7 @@ backbone + FPN part with torch CPU ops, reading and writing the very pointers th
 with the oracle then checks the wiring itself (tests/test_plan_emulation_cpu.py); the kernels are checked on the GPU.
 
 Interpreted entry points: smot_image_to_nhwc, smot_conv2d, smot_maxpool2x2, smot_maxpool3x3s2, smot_subsample2,
-smot_upsample_add.  Interpretation stops at the first call outside that set (the RPN selection)."""
+smot_upsample_add, smot_deform_im2col3x3.  Interpretation stops at the first call outside that set (the RPN selection)."""
 import ctypes as C
 
 import torch
@@ -77,6 +77,10 @@ def run_backbone(plan, image):
             inp, out, H, W, Cc, ild, old, dt = [_p(a) for a in args]
             y = _view(inp, 1, H, W, Cc, ild)[:, ::2, ::2]
             _view(out, 1, y.shape[1], y.shape[2], Cc, old).copy_(y)
+        elif name == "smot_deform_im2col3x3":
+            from cabi_emulator import deform_columns
+            inp, off, cols, H, W, Cc, ild, oild, OH, OW, old, stride, dt = [_p(a) for a in args]
+            deform_columns(inp, off, cols, H, W, Cc, ild, oild, OH, OW, old, stride)
         elif name == "smot_upsample_add":
             top, Ht, Wt, tld, lat, H, W, lld, Cc, dt = [_p(a) for a in args]
             t = _view(top, 1, Ht, Wt, Cc, tld).permute(0, 3, 1, 2)

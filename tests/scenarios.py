@@ -71,6 +71,17 @@ ORACLE_SCENARIOS = {
                                           "MODEL.DLA.DLA_STAGE5_OUT_CHANNELS", 1024, "MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES", 3,
                                           "MODEL.WEIGHT", "/dev/null"],
                                H=192, W=320, frames=5, n_obj=5, clip_seed=5, weight_seed=32, inject=None),
+    # deformable stages (MODEL.DLA.STAGE_WITH_DCN, dla.py:74-78; the reference's "-DCN" models deform levels 3..5): DLA-60 whose
+    # bottleneck 3x3 convs there are upstream's DFConv2d.  DFConv2d / DeformConv are NOT reference code (un-vendored upstream,
+    # restated in oracle/shim/maskrcnn_benchmark/layers over torchvision.ops.deform_conv2d; the oracle's own restatement of
+    # the operator is cross-checked against torchvision in tests/test_oracle_dla_family_cpu.py)
+    "emm_dla60_dcn_192x320": dict(yaml="DLA_34_FPN_EMM.yaml",
+                                  overrides=["MODEL.BACKBONE.CONV_BODY", "DLA-60-FPN",
+                                             "MODEL.DLA.STAGE_WITH_DCN", (False, False, False, True, True, True),
+                                             "MODEL.DLA.DLA_STAGE2_OUT_CHANNELS", 128, "MODEL.DLA.DLA_STAGE3_OUT_CHANNELS", 256,
+                                             "MODEL.DLA.DLA_STAGE4_OUT_CHANNELS", 512, "MODEL.DLA.DLA_STAGE5_OUT_CHANNELS", 1024,
+                                             "MODEL.TRACK_HEAD.MAX_DORMANT_FRAMES", 3, "MODEL.WEIGHT", "/dev/null"],
+                                  H=192, W=320, frames=5, n_obj=5, clip_seed=5, weight_seed=6, inject=None),
     # class-agnostic box regression (upstream MODEL.CLS_AGNOSTIC_BBOX_REG; inference.py:66-72) with two foreground classes
     "emm_cls_agnostic_192x320": dict(yaml="DLA_34_FPN_EMM.yaml",
                                      overrides=["MODEL.ROI_BOX_HEAD.NUM_CLASSES", 3, "MODEL.CLS_AGNOSTIC_BBOX_REG", True],

@@ -190,7 +190,7 @@ def test_search_region_numpy_twin_is_bit_exact():
         assert np.array_equal(tu.search_region_np(boxes.numpy()), ref.numpy())
 
 
-@pytest.mark.parametrize("name", ["emm_256x384", "emm_r50_192x320", "emm_dla102_192x320"])
+@pytest.mark.parametrize("name", ["emm_256x384", "emm_r50_192x320", "emm_dla102_192x320", "emm_dla60_dcn_192x320"])
 def test_state_dict_layout_equals_the_reference_module_tree(name):
     """build_siammot(cfg).state_dict() has exactly the keys and shapes of the reference's SiamMOT (DLA-34-FPN and the upstream
     R-50-FPN body), so DetectronCheckpointer-style checkpoints load unchanged.  Needs the reference tree (authoring container)."""

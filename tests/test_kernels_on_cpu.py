@@ -179,3 +179,29 @@ def test_fp16_instantiations_of_the_simple_kernels(cpu_xcorr):
     x_nhwc = x.permute(0, 2, 3, 1).contiguous()       # keep it alive across the call
     cpu_xcorr.cpu_maxpool3x3s2_h(p(x_nhwc), p(out), 1, 9, 14, 8, 8, 8)
     assert torch.equal(out.permute(0, 3, 1, 2), F.max_pool2d(x.float(), 3, 2, 1).half())
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_deform_im2col_kernel_source_matches_torchvision(cpu_kernels, cpu_xcorr, stride):
+    """deform_im2col3x3_kernel (DCN v1 sampling) + a GEMM over its columns == torchvision.ops.deform_conv2d; fp32 and fp16
+    instantiations; channel pitches wider than the channel counts."""
+    from torchvision.ops import deform_conv2d
+    g = torch.Generator().manual_seed(stride)
+    Cc, H, W = 8, 11, 14
+    OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
+    x = torch.randn(1, Cc, H, W, generator=g)
+    w = torch.randn(6, Cc, 3, 3, generator=g)
+    off = torch.randn(1, 18, OH, OW, generator=g) * 2.0
+    ref = deform_conv2d(x, off, w, None, stride=stride, padding=1)
+    off_nhwc = torch.zeros(1, OH, OW, 20)
+    off_nhwc[..., :18] = off.permute(0, 2, 3, 1)
+    for dtype, fn, tol_ in ((torch.float32, cpu_kernels.cpu_deform_im2col3x3, 1e-5), (torch.float16, cpu_xcorr.cpu_deform_im2col3x3_h, 4e-3)):
+        xin = torch.zeros(1, H, W, Cc + 4, dtype=dtype)
+        xin[..., :Cc] = x.permute(0, 2, 3, 1).to(dtype)
+        cols = torch.full((1, OH, OW, 9 * Cc + 4), 7.0, dtype=dtype)
+        fn(p(xin), p(off_nhwc), p(cols), H, W, Cc, Cc + 4, 20, OH, OW, 9 * Cc + 4, stride)
+        assert float((cols[..., 9 * Cc:].float() - 7.0).abs().max()) == 0.0
+        wq = w.permute(0, 2, 3, 1).reshape(6, 9 * Cc).to(dtype).float()            # [Cout][(tap, channel)], the engine's GEMM view
+        got = torch.einsum("hwk,ok->ohw", cols[0, :, :, :9 * Cc].float(), wq)[None]
+        want = ref if dtype == torch.float32 else deform_conv2d(x.half().float(), off, w.half().float(), None, stride=stride, padding=1)
+        assert float((got - want).abs().max()) <= tol_ * float(want.abs().max())

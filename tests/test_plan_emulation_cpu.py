@@ -71,7 +71,7 @@ DLA_FAMILY = {"DLA-46-C-FPN": (64, 64, 128, 256), "DLA-60-FPN": (128, 256, 512, 
               "DLA-169-FPN": (128, 256, 512, 1024)}
 
 
-@pytest.mark.parametrize("arch", sorted(DLA_FAMILY) + ["DLA-34-FPN"])
+@pytest.mark.parametrize("arch", sorted(DLA_FAMILY) + ["DLA-34-FPN", "DLA-60-FPN+DCN", "DLA-102-FPN+DCN"])
 def test_dla_family_wiring_matches_oracle(arch, monkeypatch):
     """The general concat-free DlaTree plan (bottleneck blocks, nests up to five deep, residual roots, level-2 nests) against
     the oracle, which tests/test_oracle_dla_family_cpu.py pins to the reference's own dla.py modules.  DLA-34 through the same
@@ -83,6 +83,9 @@ def test_dla_family_wiring_matches_oracle(arch, monkeypatch):
     from siammot_b200.synthetic import make_state_dict
     cfg = get_cfg()
     cfg.merge_from_file(os.path.join(CONFIG_DIR, "dla34_emm.yaml"))
+    if arch.endswith("+DCN"):                      # MODEL.DLA.STAGE_WITH_DCN on levels 3..5 (the reference's "-DCN" models)
+        arch = arch[:-4]
+        cfg.merge_from_list(["MODEL.DLA.STAGE_WITH_DCN", (False, False, False, True, True, True)])
     stages = DLA_FAMILY.get(arch, (64, 128, 256, 512))
     cfg.merge_from_list(["MODEL.BACKBONE.CONV_BODY", arch, "MODEL.DLA.DLA_STAGE2_OUT_CHANNELS", stages[0],
                          "MODEL.DLA.DLA_STAGE3_OUT_CHANNELS", stages[1], "MODEL.DLA.DLA_STAGE4_OUT_CHANNELS", stages[2],
