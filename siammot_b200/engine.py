@@ -533,14 +533,15 @@ class Engine(object):
         bc = torch.cat([sd[pre + "predictor.cls_score.bias"], bb], 0)
         Wt["box.pred"] = (wc.reshape(wc.shape[0], 1, 1, wc.shape[1]).contiguous().to(dev, dt), None, _f32(bc, dev))
         pre = "roi_heads.track.tracker.predictor."
-        wt = torch.cat([sd[pre + "cls_tower.0.weight"], sd[pre + "reg_tower.0.weight"]], 0)
-        Wt["emm.towers"] = (_ohwi(wt, dt, dev), None, None)
-        self.gn_gamma = _f32(torch.cat([sd[pre + "cls_tower.1.weight"], sd[pre + "reg_tower.1.weight"]]), dev)
-        self.gn_beta = _f32(torch.cat([sd[pre + "cls_tower.1.bias"], sd[pre + "reg_tower.1.bias"]]), dev)
-        wcc = torch.cat([sd[pre + "cls.weight"], sd[pre + "center.weight"]], 0)
-        bcc = torch.cat([sd[pre + "cls.bias"], sd[pre + "center.bias"]], 0)
-        Wt["emm.clsctr"] = (_ohwi(wcc, dt, dev), None, _f32(bcc, dev))
-        Wt["emm.reg"] = (_ohwi(sd[pre + "reg.weight"], dt, dev), None, _f32(sd[pre + "reg.bias"], dev))
+        if self.cfg.MODEL.TRACK_ON:                  # a detector-only model (MODEL.TRACK_ON False, roi_heads.py:92) has no track head
+            wt = torch.cat([sd[pre + "cls_tower.0.weight"], sd[pre + "reg_tower.0.weight"]], 0)
+            Wt["emm.towers"] = (_ohwi(wt, dt, dev), None, None)
+            self.gn_gamma = _f32(torch.cat([sd[pre + "cls_tower.1.weight"], sd[pre + "reg_tower.1.weight"]]), dev)
+            self.gn_beta = _f32(torch.cat([sd[pre + "cls_tower.1.bias"], sd[pre + "reg_tower.1.bias"]]), dev)
+            wcc = torch.cat([sd[pre + "cls.weight"], sd[pre + "center.weight"]], 0)
+            bcc = torch.cat([sd[pre + "cls.bias"], sd[pre + "center.bias"]], 0)
+            Wt["emm.clsctr"] = (_ohwi(wcc, dt, dev), None, _f32(bcc, dev))
+            Wt["emm.reg"] = (_ohwi(sd[pre + "reg.weight"], dt, dev), None, _f32(sd[pre + "reg.bias"], dev))
         self.plans.clear()
         self._track_plans.clear()
         self._arenas.clear()

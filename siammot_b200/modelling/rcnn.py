@@ -216,7 +216,7 @@ class CombinedROIHeads(nn.ModuleDict):
         """Enqueue the track-dependent stage of a frame (no host wait).  Returns a pending-frame token."""
         eng, cfg = self.engine, self.cfg
         if not cfg.MODEL.TRACK_ON:
-            raise NotImplementedError("MODEL.TRACK_ON False")
+            return self._launch_detections_only(P, given_detection)
         pool = self.track.track_pool
         if mem is None:
             pool.reset()                                                  # track_head.py:39-40
@@ -233,9 +233,39 @@ class CombinedROIHeads(nn.ModuleDict):
         tp.run(mem.feat if n else None, upload=upload, wait=False)
         return (P, tp, mem, n)
 
+    # -- MODEL.TRACK_ON False: the model is the detector alone (roi_heads.py:36 skips track head and solver; rcnn.py:57-61)
+    def _launch_detections_only(self, P, given_detection):
+        eng = self.engine
+        det_boxes, det_scores, det_block = (self._given_detections(P, given_detection[0]) if given_detection is not None
+                                            else (P.det_boxes, P.det_scores, P.det_block))
+        cap = det_boxes.shape[0]
+        host = getattr(P, "det_host", None)
+        if host is None or host.numel() < 6 * cap + 1:
+            host = P.det_host = torch.zeros((6 * cap + 1,), dtype=torch.float32).pin_memory()
+            P.det_done = torch.cuda.Event()
+        host[0:4 * cap].view(cap, 4).copy_(det_boxes, non_blocking=True)
+        host[4 * cap:5 * cap].copy_(det_scores, non_blocking=True)
+        host[5 * cap:6 * cap + 1].view(torch.int32).copy_(det_block, non_blocking=True)
+        P.det_done.record()
+        return (P, None, cap, (det_boxes, det_scores, det_block))     # the arrays stay alive until the copies have run
+
+    def _finish_detections_only(self, pending):
+        P, _, cap, _keep = pending
+        P.det_done.synchronize()
+        h = P.det_host.numpy()
+        blk = h[5 * cap:6 * cap + 1].view(np.int32)
+        k = int(blk[0])
+        boxes = np.array(h[0:4 * cap].reshape(cap, 4)[:k], dtype=np.float32, copy=True)
+        scores = np.array(h[4 * cap:4 * cap + k], dtype=np.float32, copy=True)
+        labels = blk[1:1 + k].astype(np.int64)
+        ids = np.full((k,), -1, dtype=np.int64)                         # inference.py:90: detections carry id -1
+        return self._to_boxlist(boxes, scores, ids, labels, (P.W, P.H)), None
+
     def finish_frame(self, pending, next_P=None):
         """Wait for the frame's result block, resolve ids on the host, build the next-frame memory.
         next_P: the static plan the NEXT frame will run on (clip pipelining); defaults to this frame's."""
+        if pending[1] is None:
+            return self._finish_detections_only(pending)
         P, tp, mem, n = pending
         tp.wait()
         # ---- host: unpack the result block
@@ -362,14 +392,18 @@ class SiamMOT(nn.Module):
         self.backbone = _Holder()
         self.backbone.out_channels = backbone_channels(cfg)[1]
         self.rpn = _Holder()
-        track_utils, track_pool = build_track_utils(cfg)
-        tracker = registry.SIAMESE_TRACKER[cfg.MODEL.TRACK_HEAD.MODEL](cfg, track_utils)
-        sampler = registry.TRACKER_SAMPLER.get(cfg.MODEL.TRACK_HEAD.MODEL, lambda c, t: None)(cfg, track_utils)
-        T = cfg.MODEL.TRACK_HEAD
-        heads = [("box", _Holder()), ("track", TrackHead(tracker, sampler, track_utils, track_pool)),
-                 ("solver", TrackSolver(track_pool, T.TRACK_THRESH, T.START_TRACK_THRESH, T.RESUME_TRACK_THRESH))]
+        heads = [("box", _Holder())]
+        if cfg.MODEL.TRACK_ON:                        # build_roi_heads (roi_heads.py:87-100): track head + solver only when tracking
+            track_utils, track_pool = build_track_utils(cfg)
+            tracker = registry.SIAMESE_TRACKER[cfg.MODEL.TRACK_HEAD.MODEL](cfg, track_utils)
+            sampler = registry.TRACKER_SAMPLER.get(cfg.MODEL.TRACK_HEAD.MODEL, lambda c, t: None)(cfg, track_utils)
+            T = cfg.MODEL.TRACK_HEAD
+            heads += [("track", TrackHead(tracker, sampler, track_utils, track_pool)),
+                      ("solver", TrackSolver(track_pool, T.TRACK_THRESH, T.START_TRACK_THRESH, T.RESUME_TRACK_THRESH))]
         self.roi_heads = CombinedROIHeads(cfg, heads)
         for key, val in make_state_dict(cfg, seed=0).items():
+            if not cfg.MODEL.TRACK_ON and key.startswith("roi_heads.track."):
+                continue
             _attach(self, key, val, as_buffer=_is_frozen_bn_key(key, bn_names))
         R = cfg.MODEL.RPN
         for i, (st, sz) in enumerate(zip(R.ANCHOR_STRIDE, R.ANCHOR_SIZES)):
@@ -392,7 +426,8 @@ class SiamMOT(nn.Module):
             self._engine.load_state_dict(self.state_dict())
             self._engine_stale = False
         self.roi_heads.engine = self._engine
-        self.roi_heads.track.tracker.engine = self._engine
+        if self.cfg.MODEL.TRACK_ON:
+            self.roi_heads.track.tracker.engine = self._engine
         return self._engine
 
     def load_state_dict(self, state_dict, strict=True):

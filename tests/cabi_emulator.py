@@ -430,7 +430,8 @@ def install(monkeypatch):
             self._engine.load_state_dict(self.state_dict())
             self._engine_stale = False
         self.roi_heads.engine = self._engine
-        self.roi_heads.track.tracker.engine = self._engine
+        if self.cfg.MODEL.TRACK_ON:
+            self.roi_heads.track.tracker.engine = self._engine
         return self._engine
 
     monkeypatch.setattr(rcnn.SiamMOT, "engine", host_engine)

@@ -280,3 +280,32 @@ def test_emulated_reset_between_videos_and_resolution_change(monkeypatch):
     assert torch.equal(r4.bbox, a[0].bbox) and torch.equal(rl.bbox, a[0].bbox)
     with pytest.raises(ValueError):
         model(torch.zeros(2, 3, 192, 320))
+
+
+@pytest.mark.parametrize("clip_api", [False, True])
+def test_emulated_detector_only_model(clip_api, monkeypatch):
+    """MODEL.TRACK_ON False (roi_heads.py:36,92): no track head, no solver -- the box head's detections with id -1, per frame and
+    through the clip API; the parameter tree has no roi_heads.track.* entries, like the reference's."""
+    from oracle import siammot_oracle as orc
+    from siammot_b200.modelling import build_siammot
+    cabi_emulator.install(monkeypatch)
+    cfg, sd, clip = scenario_inputs("emm_3class_192x320")
+    cfg.merge_from_list(["MODEL.TRACK_ON", False])
+    cfg.DTYPE = "float32"
+    model = build_siammot(cfg)
+    assert not any(k.startswith("roi_heads.track.") for k in model.state_dict())
+    assert "track" not in model.roi_heads and "solver" not in model.roi_heads
+    model.load_state_dict({k: v for k, v in sd.items() if not k.startswith("roi_heads.track.")}, strict=False)
+    model.eval()
+    model.reset_siammot_status()
+    frames = [clip[t] for t in range(3)]
+    results = model.forward_clip(frames) if clip_api else [model(f)[0] for f in frames]
+    o = orc.OracleSiamMOT(cfg, sd)
+    for f, r in zip(frames, results):
+        feats = o.features(f)
+        props, _ = orc.rpn_forward(o.P, cfg, feats, f.shape[2], f.shape[1])
+        ref = orc.box_head_forward(o.P, cfg, feats, props, f.shape[2], f.shape[1])
+        assert len(r) == ref["boxes"].shape[0] > 0
+        assert torch.equal(r.get_field("labels"), ref["labels"]) and bool((r.get_field("ids") == -1).all())
+        assert float((r.bbox - ref["boxes"]).abs().max()) <= BOX_TOL and float((r.get_field("scores") - ref["scores"]).abs().max()) <= SCORE_TOL
+    assert model.track_memory is None

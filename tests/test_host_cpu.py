@@ -211,3 +211,24 @@ def test_state_dict_layout_equals_the_reference_module_tree(name):
     ref = {k: tuple(v.shape) for k, v in build(rcfg).state_dict().items()}
     ours = {k: tuple(v.shape) for k, v in build_siammot(scenario_cfg(name)).state_dict().items()}
     assert ours == ref
+
+
+def test_detector_only_state_dict_layout_equals_the_reference():
+    """MODEL.TRACK_ON False: no roi_heads.track.* parameters on either side (roi_heads.py:87-100)."""
+    import sys
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from oracle import reference_loader
+    if not reference_loader.available():
+        pytest.skip("reference tree not present")
+    from helpers import scenario_cfg
+    from siammot_b200.modelling import build_siammot
+    cfg0, build = reference_loader.load()
+    rcfg = cfg0.clone()
+    rcfg.merge_from_file(os.path.join(reference_loader.REFERENCE_ROOT, "configs", "dla", "DLA_34_FPN_EMM.yaml"))
+    rcfg.merge_from_list(["MODEL.TRACK_ON", False])
+    rcfg.MODEL.DEVICE = "cpu"
+    ref = {k: tuple(v.shape) for k, v in build(rcfg).state_dict().items()}
+    cfg = scenario_cfg("emm_256x384")
+    cfg.merge_from_list(["MODEL.TRACK_ON", False])
+    ours = {k: tuple(v.shape) for k, v in build_siammot(cfg).state_dict().items()}
+    assert ours == ref and not any(k.startswith("roi_heads.track") for k in ours)
