@@ -392,6 +392,21 @@ class Engine(object):
             raise NotImplementedError("body %s: implemented are %s (dla.py:307-372; DLA-34-FPN is the SURVEY.md section 8 path) and "
                                       "%s (upstream resnet.py; R-50-FPN is BASELINE.json configs[4])"
                                       % (cfg.MODEL.BACKBONE.CONV_BODY, ", ".join(sorted(DLA_ARCHS)), ", ".join(sorted(RESNET_BLOCKS))))
+        # configuration switches whose alternatives are not built fail here, loudly, instead of silently computing the default
+        unsupported = [("MODEL.ROI_BOX_HEAD.FEATURE_EXTRACTOR", cfg.MODEL.ROI_BOX_HEAD.FEATURE_EXTRACTOR, "FPN2MLPFeatureExtractor"),
+                       ("MODEL.ROI_BOX_HEAD.PREDICTOR", cfg.MODEL.ROI_BOX_HEAD.PREDICTOR, "FPNPredictor"),
+                       ("MODEL.ROI_BOX_HEAD.USE_GN", cfg.MODEL.ROI_BOX_HEAD.USE_GN, False),
+                       ("MODEL.RPN.RPN_HEAD", cfg.MODEL.RPN.RPN_HEAD, "SingleConvRPNHead"),
+                       ("MODEL.RPN.USE_FPN", cfg.MODEL.RPN.USE_FPN, True), ("MODEL.ROI_HEADS.USE_FPN", cfg.MODEL.ROI_HEADS.USE_FPN, True),
+                       ("MODEL.FPN.USE_GN", cfg.MODEL.FPN.USE_GN, False), ("MODEL.FPN.USE_RELU", cfg.MODEL.FPN.USE_RELU, False),
+                       ("MODEL.RPN_ONLY", cfg.MODEL.RPN_ONLY, False), ("MODEL.MASK_ON", cfg.MODEL.MASK_ON, False),
+                       ("MODEL.KEYPOINT_ON", cfg.MODEL.KEYPOINT_ON, False), ("MODEL.RETINANET_ON", cfg.MODEL.RETINANET_ON, False)]
+        for key, value, supported in unsupported:
+            if value != supported:
+                raise NotImplementedError("%s = %r: the engine implements %r (the value of every shipped SiamMOT configuration)"
+                                          % (key, value, supported))
+        if len(cfg.MODEL.RPN.ANCHOR_STRIDE) != 5 or len(cfg.MODEL.RPN.ANCHOR_SIZES) != 5:
+            raise NotImplementedError("the FPN RPN runs on five levels (P2..P6): ANCHOR_STRIDE / ANCHOR_SIZES need five entries each")
         self.resnet = is_resnet(cfg)
         if self.resnet:
             R = cfg.MODEL.RESNETS

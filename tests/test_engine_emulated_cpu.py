@@ -309,3 +309,15 @@ def test_emulated_detector_only_model(clip_api, monkeypatch):
         assert torch.equal(r.get_field("labels"), ref["labels"]) and bool((r.get_field("ids") == -1).all())
         assert float((r.bbox - ref["boxes"]).abs().max()) <= BOX_TOL and float((r.get_field("scores") - ref["scores"]).abs().max()) <= SCORE_TOL
     assert model.track_memory is None
+
+
+@pytest.mark.parametrize("override", [["MODEL.ROI_BOX_HEAD.FEATURE_EXTRACTOR", "FPNXconv1fcFeatureExtractor"], ["MODEL.FPN.USE_GN", True],
+                                      ["MODEL.RPN.USE_FPN", False], ["MODEL.BACKBONE.CONV_BODY", "DLA-46-XC-FPN"],
+                                      ["MODEL.RPN.ANCHOR_STRIDE", (16,)]])
+def test_unsupported_configuration_alternatives_fail_loudly(override, monkeypatch):
+    from siammot_b200 import engine
+    cabi_emulator.install(monkeypatch)
+    cfg, sd, clip = scenario_inputs("emm_256x384")
+    cfg.merge_from_list(override)
+    with pytest.raises(NotImplementedError):
+        engine.Engine(cfg, device="cpu", use_graph=False)
