@@ -437,6 +437,7 @@ class Engine(object):
         self._tail = None
         # developer switches of SiamMOT.forward_clip: SMOT_CLIP_SPLIT=1 runs the detection tail of frame t
         # on a third stream under the backbone of frame t+1; SMOT_CLIP_SLOTS = number of static-plan copies (2 or 3)
+        self.body_branches = os.environ.get("SMOT_BODY_BRANCHES", "0") == "1"
         self.clip_split = os.environ.get("SMOT_CLIP_SPLIT", "0") == "1"
         self.clip_slots = max(2, min(4, int(os.environ.get("SMOT_CLIP_SLOTS", "2"))))
         self._pre = None
@@ -575,6 +576,12 @@ class Engine(object):
             else:
                 assert not level_root
             x2v, x1v = rootbuf[..., 0:cout], rootbuf[..., cout:2 * cout]
+            # developer switch SMOT_BODY_BRANCHES=1: the residual path (max-pool -> 1x1 project) and tree1.conv1 both read x and
+            # nothing of each other -- as two branches of the graph the two small kernels run under the 3x3 conv
+            side = self.body_branches and stride > 1 and cin != cout and P.branch is None
+            if side:
+                P.fork(1)
+                P.branch = 0
             if stride > 1:
                 bottom = rootbuf[..., 2 * cout:2 * cout + cin] if level_root else P.new(Ho, Wo, cin)
                 P.call(lib().smot_maxpool2x2, self._pool_args(x, bottom), "maxpool:" + name)
@@ -585,8 +592,12 @@ class Engine(object):
                 P.conv(bottom, "body." + name + ".project.0", residual)
             else:
                 residual = bottom
+            if side:
+                P.branch = None
             a = P.new(Ho, Wo, cout)
             P.conv(x, "body." + name + ".tree1.conv1", a, stride=stride, pad=1, relu=True)
+            if side:
+                P.join()
             P.conv(a, "body." + name + ".tree1.conv2", x1v, residual=residual, pad=1, relu=True)
             b = P.new(Ho, Wo, cout)
             P.conv(x1v, "body." + name + ".tree2.conv1", b, pad=1, relu=True)

@@ -141,3 +141,18 @@ def test_r101_wiring_matches_oracle(monkeypatch):
     for l, (got, want) in enumerate(zip(P.feats, OracleSiamMOT(cfg, sd).features(image))):
         err = float((got.permute(0, 3, 1, 2) - want).abs().max() / want.abs().max())
         assert err <= 1e-4, "R-101 FPN level %d: relative error %g" % (l, err)
+
+
+def test_body_branches_plan_has_the_forks_and_the_same_result(monkeypatch):
+    from oracle.siammot_oracle import OracleSiamMOT
+    monkeypatch.setenv("SMOT_BODY_BRANCHES", "1")
+    cfg, sd, clip = scenario_inputs("emm_amodal_expire_192x320")
+    cfg.DTYPE = "float32"
+    eng = build_engine_on_host(cfg, sd, monkeypatch)
+    assert eng.body_branches
+    P = eng.plan(clip[0].shape[1], clip[0].shape[2])
+    forks = [i for i, st in enumerate(P.steps) if st[0] == "fork"]
+    assert len(forks) == 2 + 4                       # FPN laterals, RPN chains + the four stride-2 trees with a project (levels 2..5)
+    assert run_backbone(P, clip[0]) >= 50
+    for got, want in zip(P.feats, OracleSiamMOT(cfg, sd).features(clip[0])):
+        assert float((got.permute(0, 3, 1, 2) - want).abs().max() / want.abs().max()) <= 1e-4

@@ -161,3 +161,13 @@ def test_device_resident_results_are_schedule_independent(policy, monkeypatch):
                 assert r.bbox.shape == g["boxes"].shape and torch.equal(r.get_field("ids"), g["ids"]), (mode, t)
                 if g["boxes"].numel():
                     assert float((r.bbox - g["boxes"]).abs().max()) <= 1e-3, (mode, t)
+
+
+@pytest.mark.parametrize("policy", ["lazy", "workers_eager", "default_eager", ("random", 7), ("random", 8)], ids=str)
+def test_body_branches_are_schedule_independent(policy, monkeypatch):
+    """SMOT_BODY_BRANCHES=1: inside the DLA trees the residual path (max-pool -> project) forks off tree1.conv1 and joins before
+    tree1.conv2 -- per-frame calls and the clip pipeline must not depend on how the branch is scheduled."""
+    gold = load_golden(NAME)["frames"]
+    env = {"SMOT_BODY_BRANCHES": "1"}
+    _compare(gold, _run_sim(monkeypatch, policy, "frame", env=env))
+    _compare(gold, _run_sim(monkeypatch, policy, "clip", env=dict(env, SMOT_CLIP_SPLIT="1", SMOT_CLIP_SLOTS="3")))
