@@ -214,6 +214,7 @@ class _TrackPlan(object):
         self.ncap, self.total = ncap, total
         self.keep, self.steps = [], []
         self.graph, self.warm = None, False
+        self.part_graphs, self.part_warm = [None, None], [False, False]
         self.det_is_static = det is None   # one-off plans over external detections are not worth capturing
         f32 = torch.float32
         # ---- inputs block: sr (4n) | boxes (4n) | labels (n, int32 bits) | active (n)
@@ -341,6 +342,44 @@ class _TrackPlan(object):
         self.host_res.copy_(self.res, non_blocking=True)
         self.host_det.copy_(self.det_block, non_blocking=True)
 
+    def _enqueue_part(self, part):
+        """part 0: inputs H2D .. box-head refinement (needs the frame's feature maps and the memory, not its detections);
+        part 1: candidate assembly, solver NMS, result block D2H (needs the detections)."""
+        st = _lib.stream_ptr()
+        k = next(i for i, stp in enumerate(self.steps) if stp[2] == "track_combine")
+        if part == 0:
+            if self.n:
+                self.inputs.copy_(self.inputs_host, non_blocking=True)
+            for fn, args, tag in self.steps[:k]:
+                check(fn(*args, st), tag)
+        else:
+            for fn, args, tag in self.steps[k:]:
+                check(fn(*args, st), tag)
+            self.host_res.copy_(self.res, non_blocking=True)
+            self.host_det.copy_(self.det_block, non_blocking=True)
+
+    def run_split(self, feat, between):
+        """The stage in two halves with ``between()`` called after the first is enqueued (SiamMOT.forward's overlap mode waits
+        there for the detection tail, which runs meanwhile on another stream).  One CUDA graph per half from the second use."""
+        eng = self.e
+        if self.n and feat.data_ptr() != self.tmpl.data_ptr():
+            self.tmpl.copy_(feat.view(self.tmpl.shape), non_blocking=True)
+        use_graph = eng.use_graph and self.det_is_static
+        for part in (0, 1):
+            if use_graph and self.part_graphs[part] is None and self.part_warm[part]:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_part(part)
+                self.part_graphs[part] = g
+            if use_graph and self.part_graphs[part] is not None:
+                self.part_graphs[part].replay()
+            else:
+                self._enqueue_part(part)
+                self.part_warm[part] = True
+            if part == 0:
+                between()
+        self.done.record()
+
     def run(self, feat, upload=True, wait=True):
         """Launch the stage and (wait=True) block on its result block: the frame's only device->host sync.
         The launch list is replayed as a CUDA graph from its second use on (the first use runs it eagerly, which also
@@ -438,6 +477,8 @@ class Engine(object):
         # developer switches of SiamMOT.forward_clip: SMOT_CLIP_SPLIT=1 runs the detection tail of frame t
         # on a third stream under the backbone of frame t+1; SMOT_CLIP_SLOTS = number of static-plan copies (2 or 3)
         self.body_branches = os.environ.get("SMOT_BODY_BRANCHES", "0") == "1"
+        # SiamMOT.forward: detection tail of the frame on a second stream under the EMM half of its track stage
+        self.frame_overlap = os.environ.get("SMOT_FRAME_OVERLAP", "0") == "1"
         self.clip_split = os.environ.get("SMOT_CLIP_SPLIT", "0") == "1"
         self.clip_slots = max(2, min(4, int(os.environ.get("SMOT_CLIP_SLOTS", "2"))))
         self._pre = None

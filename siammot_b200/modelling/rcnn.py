@@ -492,16 +492,52 @@ class SiamMOT(nn.Module):
         eng = self.engine()
         if hasattr(images, "tensors"):
             images = images.tensors
+        mem_in = self._mem
+        overlap = (eng.frame_overlap and given_detection is None and self.cfg.MODEL.TRACK_ON and mem_in is not None
+                   and mem_in.feat is not None and mem_in.feat.numel() > 0)
+        part = 0 if overlap else None
         if _is_raw_frame(images):
             # decoded RGB uint8 HWC frame: the test transform (demo_inference.py:74-82) runs on the device; boxes come
             # back in resized-frame pixels exactly as if the caller had applied the transform (demo_inference.py:108)
-            P = eng.run_static_raw(images)
+            P = eng.run_static_raw(images, part=part)
         else:
-            P = eng.run_static(images)
-        result, mem = self.roi_heads.run_frame(P, self._mem, given_detection)
+            P = eng.run_static(images, part=part)
+        if overlap:
+            result, mem = self._forward_overlapped(eng, P, mem_in)
+        else:
+            result, mem = self.roi_heads.run_frame(P, mem_in, given_detection)
         self._mem = mem
         self.track_memory = mem
         return [result]
+
+
+def _forward_overlapped(self, eng, P, mem):
+    """Per-frame latency mode (developer switch SMOT_FRAME_OVERLAP=1).  The track stage needs the frame's detections only for its
+    last two steps (candidate assembly, solver NMS); everything before -- search-region pooling, correlation, EMM heads, decode,
+    box-head refinement -- needs the feature maps and the memory.  So once the backbone half is enqueued on the caller's stream,
+    the detection tail goes to a second stream and runs under that EMM half; the caller's stream waits for it just before the
+    candidate assembly.  B + max(D, T_emm) + T_tail instead of B + D + T; results identical."""
+    cur = torch.cuda.current_stream(eng.device)
+    sD = eng.tail_stream()
+    if P.backbone_done is None:
+        P.backbone_done = torch.cuda.Event()
+    P.backbone_done.record(cur)
+    with torch.cuda.stream(sD):
+        sD.wait_event(P.backbone_done)
+        eng.run_tail(P)
+        if P.static_done is None:
+            P.static_done = torch.cuda.Event()
+        P.static_done.record(sD)
+    heads = self.roi_heads
+    tp = eng.track_plan(P, mem.n)
+    if tp.staged_mem is not mem:
+        mem.stage(tp)
+        tp.staged_mem = mem
+    tp.run_split(mem.feat, between=lambda: cur.wait_event(P.static_done))
+    return heads.finish_frame((P, tp, mem, mem.n))
+
+
+SiamMOT._forward_overlapped = _forward_overlapped
 
 
 def _is_raw_frame(x):

@@ -321,3 +321,10 @@ def test_unsupported_configuration_alternatives_fail_loudly(override, monkeypatc
     cfg.merge_from_list(override)
     with pytest.raises(NotImplementedError):
         engine.Engine(cfg, device="cpu", use_graph=False)
+
+
+def test_emulated_frame_overlap_equals_golden(monkeypatch):
+    """SMOT_FRAME_OVERLAP=1 (split static plan + split track plan in model(frame)): same results on two scenarios."""
+    for name in ("emm_amodal_expire_192x320", "emm_3class_192x320"):
+        got, fake = _run(name, monkeypatch, env={"SMOT_FRAME_OVERLAP": "1"})
+        _compare(load_golden(name)["frames"], got)

@@ -171,3 +171,28 @@ def test_body_branches_are_schedule_independent(policy, monkeypatch):
     env = {"SMOT_BODY_BRANCHES": "1"}
     _compare(gold, _run_sim(monkeypatch, policy, "frame", env=env))
     _compare(gold, _run_sim(monkeypatch, policy, "clip", env=dict(env, SMOT_CLIP_SPLIT="1", SMOT_CLIP_SLOTS="3")))
+
+
+@pytest.mark.parametrize("policy", POLICIES, ids=str)
+def test_frame_overlap_is_schedule_independent(policy, monkeypatch):
+    """SMOT_FRAME_OVERLAP=1: model(frame) with the detection tail on a second stream under the EMM half of the track stage."""
+    gold = load_golden(NAME)["frames"]
+    _compare(gold, _run_sim(monkeypatch, policy, "frame", env={"SMOT_FRAME_OVERLAP": "1"}))
+
+
+def test_frame_overlap_detector_detects_the_missing_wait(monkeypatch):
+    """Without the wait on the detection tail before the candidate assembly some schedule must break the results."""
+    gold = load_golden(NAME)["frames"]
+    from siammot_b200 import engine
+    broken = False
+    for policy in POLICIES:
+        with pytest.MonkeyPatch.context() as mp:
+            orig = engine._TrackPlan.run_split
+            mp.setattr(engine._TrackPlan, "run_split", lambda self, feat, between: orig(self, feat, lambda: None))
+            try:
+                broken = broken or _differs(gold, _run_sim(mp, policy, "frame", env={"SMOT_FRAME_OVERLAP": "1"}))
+            except Exception:
+                broken = True
+        if broken:
+            break
+    assert broken

@@ -231,6 +231,26 @@ def test_body_branches_change_nothing(dtype, monkeypatch):
         assert torch.equal(a.get_field("scores"), b.get_field("scores"))
 
 
+@pytest.mark.xfail(strict=False, reason="SMOT_FRAME_OVERLAP (detection tail under the EMM half of the track stage in model(frame)) "
+                                       "was added after this round's GPU budget was spent; results and ordering pinned on the CPU")
+def test_frame_overlap_changes_nothing(monkeypatch):
+    from test_e2e_gpu import build_model
+
+    def run(flag):
+        monkeypatch.setenv("SMOT_FRAME_OVERLAP", flag)
+        cfg, model, clip = build_model("emm_256x384", "float32")
+        assert model.engine().frame_overlap == (flag == "1")
+        outs = []
+        for _ in range(2):                                  # second pass: the per-half CUDA graphs are replayed
+            model.reset_siammot_status()
+            outs = [model(f.to("cuda"))[0] for f in clip]
+        return outs
+
+    for a, b in zip(run("0"), run("1")):
+        assert torch.equal(a.bbox, b.bbox) and torch.equal(a.get_field("ids"), b.get_field("ids"))
+        assert torch.equal(a.get_field("scores"), b.get_field("scores"))
+
+
 # (kept last: the only pending cases that launch a kernel with asynchronous copies for the first time)
 # ---- channel-planar search-window exchange (developer switch SMOT_XCORR_PLANAR) -------------------
 PENDING_PLANAR = pytest.mark.xfail(strict=False, reason="smot_roi_align_planar / smot_xcorr_planar were written after this round's "

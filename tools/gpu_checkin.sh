@@ -31,6 +31,7 @@ SMOT_XCORR_PLANAR=1 timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu
 SMOT_XCORR_PLANAR=2 timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --experimental off > "$OUT/bench_planar_trimmed.json" 2> "$OUT/bench_planar_trimmed.err"
 timeout 400 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --experimental off --workload 1080p80 > "$OUT/bench_1080p80.json" 2> "$OUT/bench_1080p80.err"
 timeout 400 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --experimental off --workload r50_720p30 > "$OUT/bench_r50.json" 2> "$OUT/bench_r50.err"
+SMOT_FRAME_OVERLAP=1 timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --experimental off > "$OUT/bench_frame_overlap.json" 2> "$OUT/bench_frame_overlap.err"
 SMOT_BODY_BRANCHES=1 timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --experimental off > "$OUT/bench_body_branches.json" 2> "$OUT/bench_body_branches.err"
 # launch lists (cold-cache, serialised: compare shares), default and planar
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file "$OUT/launches_default.csv" \
