@@ -51,6 +51,10 @@ WORKLOADS = {
                     yaml="dla34_emm.yaml",
                     metric="tracker FPS @1080p (DLA34-FPN+EMM, 80 tracks)",
                     text="1080p synthetic clip -> 3x1056x1920, DLA-34-FPN + EMM (search region r=2), 80 active tracks, 1 frame per step"),
+    # not a benchmark: a small frame for tests/test_bench_emulated_cpu.py, which runs this file's control flow on the CPU
+    "selftest": dict(src=(256, 384), net=(256, 384), tracks=8, opts=["INPUT.MIN_SIZE_TEST", 256, "INPUT.MAX_SIZE_TEST", 384],
+                     yaml="dla34_emm.yaml", metric="(self-test, not a measurement)",
+                     text="self-test clip -> 3x256x384, DLA-34-FPN + EMM, 8 active tracks, 1 frame per step"),
 }
 
 
@@ -75,9 +79,16 @@ def build_cfg(dtype):
 def track_table(n=None):
     """N_TRACKS pedestrian-like boxes spread over the frame (cx, cy, w, h), hitting FPN levels 0..2."""
     n = N_TRACKS if n is None else n
+    if (H_NET, W_NET) == (256, 384):      # the self-test frame: the 720p table scaled down
+        return _track_table_720p(n) * torch.tensor([384 / 1280., 256 / 704., 384 / 1280., 256 / 704.])
+    return _track_table_720p(n)
+
+
+def _track_table_720p(n):
     g = torch.Generator().manual_seed(123)
-    cx = torch.rand(n, generator=g) * (W_NET - 200) + 100
-    cy = torch.rand(n, generator=g) * (H_NET - 300) + 150
+    W, H = (1280, 704) if (H_NET, W_NET) == (256, 384) else (W_NET, H_NET)
+    cx = torch.rand(n, generator=g) * (W - 200) + 100
+    cy = torch.rand(n, generator=g) * (H - 300) + 150
     h = torch.rand(n, generator=g) * 260 + 60
     w = h * (0.3 + 0.2 * torch.rand(n, generator=g))
     return torch.stack((cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2), dim=1)

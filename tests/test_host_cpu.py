@@ -63,6 +63,10 @@ def test_bench_workloads_resolve_to_the_stated_network_sizes():
             assert get_size(wd, h, cfg.INPUT.MIN_SIZE_TEST, cfg.INPUT.MAX_SIZE_TEST, cfg.DATALOADER.SIZE_DIVISIBILITY) == w["net"]
             assert bench.track_table().shape == (w["tracks"], 4)
             assert "%dx%d" % w["net"] in w["text"] and str(w["tracks"]) in w["text"]
+        # the default workload's track table is the one every committed bench line was measured on
+        bench.select_workload("720p30")
+        t = bench.track_table()
+        assert t.shape == (30, 4) and abs(float(t.sum()) - 58072.671875) < 0.01
     finally:
         bench.select_workload("720p30")
 
