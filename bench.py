@@ -504,6 +504,27 @@ def experimental_arms(h, args, frames_dev, frames_u8, hook, ntrk_ref, tp, hbm_pe
             break
         finally:
             eng.clip_split, eng.clip_slots = False, 2
+    try:   # (3) model(frame) with the detection tail under the EMM half of the track stage (Engine.frame_overlap)
+        def per_frame(flag):
+            eng.frame_overlap = flag
+            for i in range(3):
+                h.step(frames_u8[i % N_FRAMES])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n = 0
+            for i in range(steps):
+                n += int((h.step(frames_u8[(args.warmup + i) % N_FRAMES]).get_field("ids") >= 0).sum())
+            torch.cuda.synchronize()
+            return steps / (time.perf_counter() - t0), n
+        fps0, n0 = per_frame(False)
+        fps1, n1 = per_frame(True)
+        fps1, n1 = per_frame(True)          # second pass: the per-half CUDA graphs exist
+        res["frame_overlap"] = {"per_frame_call": round(fps1, 2), "per_frame_call_default": round(fps0, 2), "unit": "frames/s",
+                                "steps": steps, "same_tracks_as_default": bool(n0 == n1)}
+    except Exception as exc:
+        res["frame_overlap"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    finally:
+        eng.frame_overlap = False
     try:
         T = h.cfg.MODEL.TRACK_HEAD
         P = tp.P

@@ -69,3 +69,4 @@ def test_bench_experimental_child_mode(monkeypatch):
     ex = json.loads(buf.getvalue().strip().splitlines()[-1])
     assert ex["three_stage_clip_k2"]["same_tracks_as_two_stream"] is True and ex["three_stage_clip_k3"]["same_tracks_as_two_stream"] is True
     assert "xcorr_planar" in ex        # fp32 here: the wrapper refuses (TypeError recorded), fp16 on the GPU
+    assert ex["frame_overlap"].get("same_tracks_as_default") is True, ex["frame_overlap"]
