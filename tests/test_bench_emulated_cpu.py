@@ -70,3 +70,17 @@ def test_bench_experimental_child_mode(monkeypatch):
     assert ex["three_stage_clip_k2"]["same_tracks_as_two_stream"] is True and ex["three_stage_clip_k3"]["same_tracks_as_two_stream"] is True
     assert "xcorr_planar" in ex        # fp32 here: the wrapper refuses (TypeError recorded), fp16 on the GPU
     assert ex["frame_overlap"].get("same_tracks_as_default") is True, ex["frame_overlap"]
+
+
+def test_demo_clip_tool_end_to_end(monkeypatch, tmp_path):
+    """tools/demo_clip.py (the engine's demos/demo.py): raw frames -> forward_clip -> egress -> JSON, over the emulation."""
+    import os
+    cabi_emulator.install_for_bench(monkeypatch)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import demo_clip
+    out = tmp_path / "tracks.json"
+    kept = demo_clip.main(["--synthetic", "6", "--size", "192x320", "--dtype", "float32", "--track-len", "2", "--track-conf", "0.0",
+                           "--out", str(out)])
+    recs = json.loads(out.read_text())
+    assert len(recs) == len(kept) and all(set(r) == {"frame_num", "id", "label", "confidence", "bbox"} for r in recs)
+    assert all(r["id"] >= 0 and len(r["bbox"]) == 4 for r in recs)
