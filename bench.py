@@ -66,6 +66,49 @@ def select_workload(name):
     METRIC, WORKLOAD, CFG_OVERRIDES = w["metric"], w["text"], w["opts"]
 
 
+def config_dict(world=1):
+    """The `config` object of the JSON line: identical for both arms (ours / --impl reference), so the driver compares like with
+    like.  Arm-specific notes (API used, graphs, baseline note) live in `notes`, outside it."""
+    return {"workload": WORKLOAD, "net_input": [3, H_NET, W_NET], "source_frame": [H_SRC, W_SRC, 3], "frames_resident": N_FRAMES,
+            "l2": "inputs (%d MB of frames + activations) exceed the 126 MB L2" % (N_FRAMES * 3 * H_NET * W_NET * 4 // 1000000),
+            "tracks_in_memory": N_TRACKS, "parallelism": "1 stream per GPU x %d" % world}
+
+
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would otherwise make the CPU legs
+    single-threaded)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def pin_to_gpu_numa_node(local):
+    """Bind this rank to the CPUs NVML reports as local to its GPU (on the 8-GPU box GPUs 0-3 sit on one socket, 4-7 on the
+    other): the host solver, the pinned staging buffers and the launch loop then stay on the GPU's own NUMA node.
+    Returns the number of CPUs bound, or None when NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def median(xs):
+    xs = sorted(xs)
+    n = len(xs)
+    return xs[n // 2] if n % 2 else 0.5 * (xs[n // 2 - 1] + xs[n // 2])
+
+
 def build_cfg(dtype):
     from siammot_b200.config import get_cfg
     cfg = get_cfg()
@@ -209,6 +252,9 @@ def kernels_per_frame(h):
     return n
 
 
+REPEATS = 5   # timed regions per arm: the line reports the median (a 20-step region is ~20 ms; one region cannot resolve 5 %)
+
+
 def run_ours(args):
     distributed = args.gpus > 1 and "RANK" in os.environ
     rank = int(os.environ.get("RANK", 0))
@@ -216,9 +262,18 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", 1)) if distributed else 1
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa_cpus = pin_to_gpu_numa_node(local) if distributed else None
     if distributed:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+        # SMOT_BENCH_BACKEND=gloo: the CPU test of this branch (tests/test_bench_distributed_cpu.py); production is NCCL
+        backend = os.environ.get("SMOT_BENCH_BACKEND", "nccl")
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=device)
+        else:
+            dist.init_process_group(backend)
+        from siammot_b200.parallel import exchange_device
+        xdev = exchange_device()           # where tensors handed to a collective must live (the rank's GPU under NCCL)
+    torch.set_num_threads(max(1, min(8, host_threads() // max(world, 1))))   # the host side is one Python thread + small numpy ops
     h = Harness(args.dtype, device)
     h.model.results_on_host = True   # results are consumed on the host (as demo / inferencer do): CPU BoxLists straight from the solver
     frames_u8 = make_frames_u8(N_FRAMES, h.cfg).pin_memory()                   # host, pinned: the e2e arm's input
@@ -233,24 +288,28 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm: `value` (clip API: the detection stage of frame t+1 overlaps the host solver of frame t)
+    # ---- device-resident arm: `value` (clip API: the detection stage of frame t+1 overlaps the host solver of frame t).
+    # No event timers in this arm (they are on only in the per-frame arm below); REPEATS timed regions of exactly K steps.
     hook = lambda t: h.restore()
     h.model.forward_clip([frames_dev[i % N_FRAMES] for i in range(max(args.warmup, 4))], before_frame=hook)
     seq = [frames_dev[(args.warmup + i) % N_FRAMES] for i in range(args.steps)]
-    h.eng.timers = {}
+    h.eng.timers = None
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    results = h.model.forward_clip(seq, before_frame=hook)
-    e1.record()
-    barrier()
+    value_ms = []
+    for rep in range(REPEATS):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        results = h.model.forward_clip(seq, before_frame=hook)
+        e1.record()
+        barrier()
+        value_ms.append(e0.elapsed_time(e1))
     ntrk = sum(int((r.get_field("ids") >= 0).sum()) for r in results)
     r = results[-1]
-    ms = e0.elapsed_time(e1)
-    h.eng.timers = None
+    ms = median(value_ms)
 
     # ---- end-to-end arm through the public API with HOST frames: `e2e`.  The call a user makes per decoded frame:
     # model(uint8 HWC frame) -> H2D of the frame, test transform on the device, the whole hot path, D2H of the result.
@@ -273,17 +332,20 @@ def run_ours(args):
     def e2e_clip_loop(src):
         h.model.forward_clip([src[i % N_FRAMES] for i in range(max(args.warmup, 4))], before_frame=hook)
         seq_h = [src[(args.warmup + i) % N_FRAMES] for i in range(args.steps)]
-        barrier()
-        t0 = time.perf_counter()
-        res = h.model.forward_clip(seq_h, before_frame=hook)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        assert len(res) == args.steps and all(r.bbox.device.type == "cpu" for r in res)
-        return dt, sum(int((r.get_field("ids") >= 0).sum()) for r in res)
+        dts = []
+        for rep in range(REPEATS):
+            barrier()
+            t0 = time.perf_counter()
+            res = h.model.forward_clip(seq_h, before_frame=hook)
+            torch.cuda.synchronize()
+            dts.append(time.perf_counter() - t0)
+            assert len(res) == args.steps and all(r.bbox.device.type == "cpu" for r in res)
+        return dts, sum(int((r.get_field("ids") >= 0).sum()) for r in res)
 
-    e2e_clip_s, e2e_clip_err = None, None
+    e2e_clip_s, e2e_clip_err, e2e_clip_all = None, None, []
     try:
-        e2e_clip_s, ntrk_clip = e2e_clip_loop(frames_u8)
+        e2e_clip_all, ntrk_clip = e2e_clip_loop(frames_u8)
+        e2e_clip_s = median(e2e_clip_all)
         if ntrk_clip != ntrk:   # same frames, same restored memory: the from-host clip must track exactly what `value` tracked
             e2e_clip_err = "clip-from-host tracked %d boxes, device-resident clip %d" % (ntrk_clip, ntrk)
     except Exception as exc:   # keep the per-frame number as the headline rather than lose the line
@@ -299,38 +361,40 @@ def run_ours(args):
     prep = [a.elapsed_time(b) for a, b in timers.get("preprocess", [])][min(args.warmup, 3):]
     e2e_float_s, _ = e2e_loop(frames_pin)   # the reference's calling convention: normalised float32 CHW host tensor
     clocks = sampler.stop() if rank == 0 else None   # sampled across both timed arms
-    # roofline kernel: the frame's own smot_xcorr launch (same buffers: 30 search windows / templates of the last frame,
-    # L2-resident as in the pipeline), bracketed with CUDA events on its stream, right after the timed region
+    # roofline kernel: the frame's own correlation launch (same buffers: the search windows / templates of the last frame,
+    # L2-resident as in the pipeline), bracketed with CUDA events on its stream, right after the timed region.  Measured both
+    # ways: eagerly (20 back-to-back launches from the Python/ctypes loop) and as a 20-launch CUDA-graph replay, which is how
+    # the product issues it (the track stage is a graph; a ~4 us kernel launched eagerly is paced by the ~8 us launch loop).
     from siammot_b200._lib import check, stream_ptr
     tp = h.eng.track_plan(h.eng.plan(H_NET, W_NET), N_TRACKS)
     xfn, xargs, _ = tp.steps[tp.xcorr_slot]
-    XREP = 20   # launches per bracket: the kernels serialise in-stream, the bracket's own launch latency is amortised
-    xev = []
-    for i in range(13):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(XREP):
-            check(xfn(*xargs, stream_ptr()), "xcorr")
-        b.record()
-        xev.append((a, b))
-    torch.cuda.synchronize()
-    xc = [a.elapsed_time(b) / XREP for a, b in xev[3:]]
+    xc_t = time_launches(lambda: check(xfn(*xargs, stream_ptr()), "xcorr"))
 
     clip_ok = e2e_clip_s is not None and e2e_clip_err is None
+    static_ms = sum(static) / max(len(static), 1)
+    prep_ms = sum(prep) / max(len(prep), 1)
+    per_rank = None
     if distributed:
-        t = torch.tensor([ms, e2e_s * 1e3, e2e_float_s * 1e3, e2e_clip_s * 1e3 if clip_ok else float("inf")],
-                         device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = torch.tensor([ms, e2e_s * 1e3, e2e_float_s * 1e3, e2e_clip_s * 1e3 if clip_ok else float("inf"), static_ms, prep_ms],
+                         device=xdev, dtype=torch.float64)
+        allr = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        per_rank = [[round(float(v), 4) for v in x.tolist()] for x in allr]
+        t = torch.stack(allr).max(dim=0).values      # MAX over ranks of every time
         ms, e2e_ms, e2e_float_ms, e2e_clip_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
         clip_ok = e2e_clip_ms != float("inf")   # every rank's clip arm ran
-        # the one inference collective: per-clip gather of fixed-size track-state records
-        from siammot_b200.parallel import gather_track_states
-        gather_track_states(r, max_tracks=128)
+        # the one inference collective: per-clip gather of fixed-size track-state records, on the exchange device
+        from siammot_b200.parallel import gather_track_states, unpack_track_states
+        rec = gather_track_states(r, max_tracks=128)
+        assert rec.shape[0] == world and rec.device.type == xdev.type, (rec.shape, rec.device)
+        gathered = [int(s_["ids"].numel()) for s_ in unpack_track_states(rec.cpu())]
     else:
         e2e_ms, e2e_float_ms = e2e_s * 1e3, e2e_float_s * 1e3
         e2e_clip_ms = e2e_clip_s * 1e3 if clip_ok else float("inf")
+        gathered = None
     if rank != 0:
         if distributed:
+            dist.barrier()
             dist.destroy_process_group()
         return
     peaks = {}
@@ -340,56 +404,70 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     esz = 2 if args.dtype == "float16" else 4
-    xc_bytes = N_TRACKS * h.eng.C * (30 * 30 + 15 * 15 + 16 * 16) * esz      # N*C*1381*b
-    xc_ms = sum(xc) / max(len(xc), 1)
-    achieved = xc_bytes / (xc_ms * 1e-3) / 1e9 if xc_ms > 0 else 0.0
+    S_, T_ = h.eng.s_res, h.eng.t_res
+    xc_bytes = N_TRACKS * h.eng.C * (S_ * S_ + T_ * T_ + (S_ - T_ + 1) ** 2) * esz      # N*C*1381*b at S=30, T=15
+    xc_best = xc_t.get("graph") if "us_per_launch" in xc_t.get("graph", {}) else xc_t.get("eager", {})
+    xc_us = xc_best.get("us_per_launch", 0.0)
+    achieved = xc_bytes / (xc_us * 1e-6) / 1e9 if xc_us > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(REPO, "profiles", "xcorr_traffic.json"))).get(args.dtype)
+        traffic = json.load(open(os.path.join(REPO, "profiles", "xcorr_traffic.json"))).get(getattr(tp, "xcorr_kernel", "").split(" ")[0])
     except Exception:
         pass
     fps = world * args.steps / (ms * 1e-3)
+    e2e_fps = world * args.steps / ((e2e_clip_ms if clip_ok else e2e_ms) * 1e-3)
+    cfgd = config_dict(world)
+    cfgd["tracked_boxes_per_step"] = round(ntrk / args.steps, 1)
     out = {
         "metric": METRIC, "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": round(fps / world / 17.0, 2) if (world == 1 and args.workload == "720p30") else None,
         "dtype": "f16" if args.dtype == "float16" else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_resident": N_FRAMES, "l2": "inputs (%d MB of frames + activations) exceed the 126 MB L2" % (N_FRAMES * 3 * H_NET * W_NET * 4 // 1000000),
-                   "tracks_in_memory": N_TRACKS, "tracked_boxes_per_step": round(ntrk / args.steps, 1),
-                   "parallelism": "1 stream per GPU x %d" % world, "cuda_graph": True,
-                   "api": "value: model.forward_clip on normalised frames resident in HBM (frame t+1's detection stage runs on a "
-                          "side stream under frame t's track stage and host solver); e2e: the same clip API on decoded RGB uint8 "
-                          "720p frames in pinned host memory (per frame: 2.76 MB H2D + test transform resize 720->704 / ToTensor / "
-                          "Normalize on the device, packed result block D2H; all inside the wall-clock region); "
-                          "e2e.per_frame_call: model(frame) once per frame; "
-                          "model.results_on_host = True (CPU BoxLists from the packed result block the engine copies D2H)",
-                   "baseline_note": "17 FPS = README.md:22 'a single modern GPU', unnamed hardware"},
-        "e2e": {"value": round(world * args.steps / ((e2e_clip_ms if clip_ok else e2e_ms) * 1e-3), 2), "unit": "frames/s",
+        "config": cfgd,
+        "notes": {"cuda_graph": True, "pipeline": h.eng.clip_mode_name(),
+                  "api": "value: model.forward_clip on normalised frames resident in HBM; e2e: the same clip API on decoded RGB uint8 "
+                         "720p frames in pinned host memory (per frame: 2.76 MB H2D + test transform resize 720->704 / ToTensor / "
+                         "Normalize on the device, packed result block D2H; all inside the wall-clock region); "
+                         "e2e.per_frame_call: model(frame) once per frame; "
+                         "model.results_on_host = True (CPU BoxLists from the packed result block the engine copies D2H)",
+                  "baseline_note": "17 FPS = README.md:22 'a single modern GPU', unnamed hardware",
+                  "repeats": "%d timed regions of exactly %d steps per arm; value / e2e are the median region (max over ranks)" % (REPEATS, args.steps),
+                  "numa_cpus_bound": numa_cpus},
+        "spread": {"value_fps": [round(world * args.steps / (x * 1e-3), 1) for x in value_ms],
+                   "e2e_fps": [round(world * args.steps / x, 1) for x in e2e_clip_all],
+                   "note": "this rank's regions; e2e may exceed value by a few per cent: the device-resident arm reads 10.8 MB fp32 "
+                           "frames from HBM (image_to_nhwc), the host arm uploads 2.8 MB uint8 frames and resamples on the side stream"},
+        "e2e": {"value": round(e2e_fps, 2), "unit": "frames/s",
                 "api": "model.forward_clip(pinned uint8 host frames)" if clip_ok else "model(pinned uint8 host frame) per frame",
                 "h2d_bytes_per_step": 3 * H_SRC * W_SRC + tp.inputs.numel() * 4,
                 "d2h_bytes_per_step": (tp.host_res.numel() + tp.host_det.numel()) * 4,
                 "result_bytes_per_step": int(d2h / args.steps),
                 "per_frame_call": {"value": round(world * args.steps / (e2e_ms * 1e-3), 2), "unit": "frames/s",
-                                   "note": "model(frame) called once per decoded frame (demo.py's loop): H2D, transform, detection "
-                                           "stage, track stage, D2H and the host solver run back to back, nothing overlaps"},
+                                   "note": "model(frame) called once per decoded frame (demo.py's loop, the reference's own API)"},
                 "clip_error": e2e_clip_err,
                 "float32_chw_host_input": {"value": round(world * args.steps / (e2e_float_ms * 1e-3), 2), "unit": "frames/s",
                                            "h2d_bytes_per_step": 3 * H_NET * W_NET * 4,
-                                           "note": "same loop with the reference's calling convention (frame already resized + "
+                                           "note": "same per-frame loop with the reference's calling convention (frame already resized + "
                                                    "normalised on the host)"}},
         "gpu_launches": kernels_per_frame(h) * args.steps,
         "roofline": {"kernel": getattr(tp, "xcorr_kernel", "smot_xcorr"), "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak,
                      "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
-                     "algorithmic_bytes": xc_bytes, "us_per_launch": round(xc_ms * 1e3, 2),
-                     "timing": "10 CUDA-event brackets of 20 back-to-back launches of the frame's smot_xcorr call, right after the timed "
-                               "region (inside it the track stage replays as a CUDA graph, which events cannot bracket)",
+                     "algorithmic_bytes": xc_bytes, "us_per_launch": round(xc_us, 2),
+                     "us_per_launch_eager": xc_t.get("eager", {}).get("us_per_launch"),
+                     "us_per_launch_graph": xc_t.get("graph", {}).get("us_per_launch"),
+                     "timing": "10 CUDA-event brackets (after 3 warm-up ones) of 20 back-to-back launches of the frame's own correlation "
+                               "call on its buffers, right after the timed region; `us_per_launch` is the CUDA-graph replay of the 20 "
+                               "launches (the product issues the track stage as a graph), `us_per_launch_eager` the ctypes launch loop",
                      "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650 GB/s",
-                     "note": "fp16: banded-Toeplitz mma.sync form (bound by staging/latency); fp32: FMA form, 41.7 FLOP/B"},
-        "stage_ms": {"static_graph": round(sum(static) / max(len(static), 1), 4),
-                     "preprocess_incl_h2d": round(sum(prep) / max(len(prep), 1), 4),
-                     "note": "CUDA-event brackets in the e2e arm (single stream)"},
+                     "flops_per_launch": N_TRACKS * h.eng.C * 2 * (S_ - T_ + 1) ** 2 * T_ * T_,
+                     "note": getattr(tp, "xcorr_note", "")},
+        "stage_ms": {"static_graph": round(static_ms, 4), "preprocess_incl_h2d": round(prep_ms, 4),
+                     "note": "CUDA-event brackets in the per-frame e2e arm (single stream)"},
         "clocks": clocks,
     }
+    if per_rank is not None:
+        out["per_rank_ms"] = {"columns": ["value_region", "per_frame_region", "float_region", "e2e_clip_region", "static_graph", "preprocess"],
+                              "rows": per_rank, "gathered_tracks_per_rank": gathered}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_frames=2)
     if world == 1 and args.experimental == "subprocess":
@@ -417,6 +495,43 @@ def run_ours(args):
 
 
 EXPERIMENTAL_TIMEOUT_S = 150
+
+
+def time_launches(launch, reps=20):
+    """us per launch of `launch()` (one kernel on the current stream): CUDA-event brackets around `reps` back-to-back launches,
+    10 brackets after 3 warm-up ones; 'eager' = the Python/ctypes launch loop, 'graph' = the launches replayed as one CUDA graph."""
+    out = {}
+    for how in ("eager", "graph"):
+        try:
+            if how == "graph":
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    launch()                         # function attributes are set outside the capture
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(reps):
+                        launch()
+                run = g.replay
+            else:
+                def run():
+                    for _ in range(reps):
+                        launch()
+            ev = []
+            for i in range(13):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                run()
+                b.record()
+                ev.append((a, b))
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) / reps for a, b in ev[3:]) / max(len(ev) - 3, 1)
+            out[how] = {"us_per_launch": round(ms * 1e3, 2)}
+        except Exception as exc:
+            out[how] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    return out
 
 
 def experimental_subprocess(args):
@@ -624,6 +739,7 @@ def oracle_runner():
 
 
 def cpu_baseline(sample_frames=2):
+    torch.set_num_threads(host_threads())
     step = oracle_runner()
     step(0)
     t0 = time.perf_counter()
@@ -636,28 +752,38 @@ def cpu_baseline(sample_frames=2):
 
 
 def run_reference(args):
+    """--impl reference: the reference algorithm on the host CPU (oracle port), rank 0 only, on every host thread the process
+    may use (torchrun exports OMP_NUM_THREADS=1: overridden here), same workload / config keys / warm-up count as our arm."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    cores = host_threads()
+    torch.set_num_threads(cores)
     step = oracle_runner()
-    for i in range(min(args.warmup, 1)):
+    warm = max(args.warmup, 0)
+    for i in range(warm):
         step(i)
-    # bounded: at ~1 frame/s the whole run must end within a few minutes
+    # bounded: at ~1-2 frames/s the whole run must end within a few minutes
     steps = min(args.steps, 60)
+    ntrk = 0
     t0 = time.perf_counter()
     for i in range(steps):
-        step(i)
+        out = step(warm + i)
+        ntrk += int((out["ids"] >= 0).sum()) if isinstance(out, dict) else int((out.get_field("ids") >= 0).sum())
     dt = time.perf_counter() - t0
     fps = steps / dt
-    cores = torch.get_num_threads()
+    world = int(os.environ.get("WORLD_SIZE", 1)) if (args.gpus > 1 and "RANK" in os.environ) else 1
+    cfgd = config_dict(world)
+    cfgd["tracked_boxes_per_step"] = round(ntrk / steps, 1)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(fps, 4), "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference algorithm on the host CPU (oracle port; the reference itself needs "
-                                                 "maskrcnn_benchmark which is not installable offline); steps capped at 60"},
+        "config": cfgd,
+        "notes": {"what": "reference algorithm on the host CPU (oracle port, fp32; the reference itself needs maskrcnn_benchmark which "
+                          "is not installable offline); steps capped at 60; rank 0 only, %d torch threads" % cores},
         "cpu_baseline": {"value": round(fps, 4), "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d full frames (704x1280, 30 tracks)" % steps},
+                         "sample": "%d full frames (%dx%d, %d tracks) after %d warm-up frames" % (steps, H_NET, W_NET, N_TRACKS, warm)},
         "e2e": {"value": round(fps, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 

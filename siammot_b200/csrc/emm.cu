@@ -660,11 +660,11 @@ extern "C" int smot_xcorr(const void* x, const void* k, void* out, int n, int ch
   return SMOT_OK;
 }
 
-// developer switch: SMOT_XCORR_PLANAR=2 selects the trimmed MMA phase (read once)
+// the trimmed MMA phase is the default; developer switch SMOT_XCORR_PLANAR=1 selects the untrimmed one (read once)
 static bool xcorr_planar_trimmed() {
   static const bool on = [] {
     const char* e = getenv("SMOT_XCORR_PLANAR");
-    return e && e[0] == '2';
+    return !(e && e[0] == '1');
   }();
   return on;
 }

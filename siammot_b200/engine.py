@@ -200,7 +200,7 @@ class _TrackPlan(object):
     template features are views of the shared _TrackArena; the small per-track inputs (search regions,
     template boxes, labels, active flags) arrive in one host->device copy."""
 
-    def __init__(self, eng, P, n, arena, det=None):
+    def __init__(self, eng, P, n, arena, det=None, persistent=True):
         dev, dt, cfg = eng.device, eng.dtype, eng.cfg
         L = lib()
         self.e, self.P, self.n, self.arena = eng, P, n, arena
@@ -215,7 +215,7 @@ class _TrackPlan(object):
         self.keep, self.steps = [], []
         self.graph, self.warm = None, False
         self.part_graphs, self.part_warm = [None, None], [False, False]
-        self.det_is_static = det is None   # one-off plans over external detections are not worth capturing
+        self.det_is_static = det is None or persistent   # one-off plans over foreign detection arrays are not worth capturing
         f32 = torch.float32
         # ---- inputs block: sr (4n) | boxes (4n) | labels (n, int32 bits) | active (n)
         self.inputs = A.inputs[:max(10 * n, 1)]
@@ -478,9 +478,12 @@ class Engine(object):
         # on a third stream under the backbone of frame t+1; SMOT_CLIP_SLOTS = number of static-plan copies (2 or 3)
         self.body_branches = os.environ.get("SMOT_BODY_BRANCHES", "0") == "1"
         # SiamMOT.forward: detection tail of the frame on a second stream under the EMM half of its track stage
-        self.frame_overlap = os.environ.get("SMOT_FRAME_OVERLAP", "0") == "1"
-        self.clip_split = os.environ.get("SMOT_CLIP_SPLIT", "0") == "1"
-        self.clip_slots = max(2, min(4, int(os.environ.get("SMOT_CLIP_SLOTS", "2"))))
+        # (default since round 2: measured 639 vs 580 FPS per-frame on the driver's B200, identical tracks; =0 restores the serial order)
+        self.frame_overlap = os.environ.get("SMOT_FRAME_OVERLAP", "1") == "1"
+        # forward_clip: three-stage pipeline over 3 static-plan copies by default (round 2: measured 989 / 1071 FPS value / e2e
+        # against 900 / 946 for the two-stream pipeline on the driver's B200, identical tracks); SMOT_CLIP_SPLIT=0 = two-stream
+        self.clip_split = os.environ.get("SMOT_CLIP_SPLIT", "1") == "1"
+        self.clip_slots = max(2, min(4, int(os.environ.get("SMOT_CLIP_SLOTS", "3"))))
         self._pre = None
         self._branch_ws = []
         self._branch_streams = []
@@ -489,9 +492,15 @@ class Engine(object):
         # developer switch: exchange the EMM search windows channel-planar (smot_roi_align_planar ->
         # smot_xcorr_planar).  Off by default until it has been through the GPU tests.
         self.nvtx = os.environ.get("SMOT_NVTX", "0") == "1"
-        self.xcorr_planar = os.environ.get("SMOT_XCORR_PLANAR", "0") in ("1", "2")   # 2: + trimmed MMA phase (libsmot reads it)
+        # channel-planar search-window exchange (default since round 2: bit-equal windows, 1.5-2x faster correlation on the
+        # driver's B200); 0 = NHWC windows + xcorr_mma_kernel, 1 = planar with the untrimmed MMA phase, 2 = trimmed (libsmot reads it)
+        self.xcorr_planar = os.environ.get("SMOT_XCORR_PLANAR", "2") in ("1", "2")
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
         self.time_kernels = False  # also bracket single kernels of the track stage (forces its eager path)
+
+    def clip_mode_name(self):
+        return ("three-stage clip pipeline (backbone half / detection tail / track stage on three streams, %d static-plan copies)"
+                % self.clip_slots) if self.clip_split else "two-stream clip pipeline (static stage / track stage, 2 static-plan copies)"
 
     def xcorr_planar_ok(self):
         """The planar exchange applies to the fp16 correlation at the TAO geometry (S = 30, T = 15) with C % 16 == 0."""
@@ -1062,14 +1071,45 @@ class Engine(object):
             cap = 64 if A is None else A.cap
             while cap < n:
                 cap *= 2
+            old = A
             A = self._arenas[key] = _TrackArena(self, P, ncap, cap)
-            for k in [k for k in self._track_plans if k[:3] == (P.H, P.W, getattr(P, "slot", 0))]:
+            for k in [k for k, tp in self._track_plans.items() if tp.arena is old]:   # only the plans that were views of the old arena
                 self._track_plans.pop(k)
         return A
 
+    @staticmethod
+    def given_capacity(rows):
+        """Capacity class of an external-detection set: next power of two >= max(rows, 64).  Arenas, buffers and plans of the
+        public-detection path are keyed on the class, not on the frame's detection count (a MOT17 video has dozens of
+        distinct counts; one arena per count leaked ~30 MB each)."""
+        return max(64, 1 << (max(int(rows), 1) - 1).bit_length())
+
+    def given_buffers(self, P, rows):
+        """Persistent (det_boxes, det_scores, det_block) of static plan P for external detections, per capacity class."""
+        cap = self.given_capacity(rows)
+        bufs = getattr(P, "given_bufs", None)
+        if bufs is None:
+            bufs = P.given_bufs = {}
+        if cap not in bufs:
+            dev = self.device
+            bufs[cap] = (torch.zeros((cap, 4), dtype=torch.float32, device=dev),
+                         torch.full((cap,), -1.0, dtype=torch.float32, device=dev),
+                         torch.zeros((1 + cap,), dtype=torch.int32, device=dev))
+        return bufs[cap]
+
     def track_plan(self, P, n, det=None):
-        if det is not None:   # external detections: one-off plan over their arrays
-            return _TrackPlan(self, P, n, self.track_arena(P, n, det[0].shape[0]), det=det)
+        if det is not None:
+            # external detections: their arrays are the plan's persistent per-capacity buffers (given_buffers), so the plan is
+            # cached per (slot, n, capacity) and replayed as a graph like the default one; foreign arrays get a one-off plan
+            ncap = det[0].shape[0]
+            if getattr(P, "given_bufs", {}).get(ncap, (None,))[0] is not det[0]:
+                return _TrackPlan(self, P, n, self.track_arena(P, n, ncap), det=det, persistent=False)
+            A = self.track_arena(P, n, ncap)
+            key = (P.H, P.W, getattr(P, "slot", 0), n, "given", ncap)
+            tp = self._track_plans.get(key)
+            if tp is None:
+                tp = self._track_plans[key] = _TrackPlan(self, P, n, A, det=det, persistent=True)
+            return tp
         A = self.track_arena(P, n)
         key = (P.H, P.W, getattr(P, "slot", 0), n)
         tp = self._track_plans.get(key)

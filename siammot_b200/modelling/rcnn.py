@@ -194,10 +194,10 @@ class CombinedROIHeads(nn.ModuleDict):
         ncls = eng.ncls
         rois = given.convert("xyxy").bbox.to(dev, torch.float32).contiguous()
         n = rois.shape[0]
-        cap = max(n * (ncls - 1), 1)
-        det_boxes = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
-        det_scores = torch.full((cap,), -1.0, dtype=torch.float32, device=dev)
-        det_block = torch.zeros((1 + cap,), dtype=torch.int32, device=dev)
+        # persistent buffers per capacity class (power of two): one arena / plan per class, not per detection count
+        det_boxes, det_scores, det_block = eng.given_buffers(P, n * (ncls - 1))
+        det_scores.fill_(-1.0)
+        det_block.zero_()
         if n:
             dec_b, dec_s = eng.box_head_eager(P, rois)
             H = cfg.MODEL.ROI_HEADS

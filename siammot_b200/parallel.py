@@ -32,9 +32,22 @@ def pack_track_states(result, max_tracks, device=None):
     return rec
 
 
+def exchange_device(result=None, group=None):
+    """The device the records must live on for the process group's backend: NCCL moves device memory only (a CPU tensor
+    handed to it fails with "no backend for device cpu" -- results_on_host BoxLists are CPU tensors), gloo moves host memory."""
+    if dist.is_available() and dist.is_initialized():
+        backend = str(dist.get_backend(group)).lower()
+        if "nccl" in backend:
+            return torch.device("cuda", torch.cuda.current_device())
+        if "gloo" in backend:
+            return torch.device("cpu")
+    return result.bbox.device if result is not None else torch.device("cpu")
+
+
 def gather_track_states(result, max_tracks=128, group=None):
-    """All ranks receive every rank's records: returns a (world, max_tracks, 8) tensor."""
-    rec = pack_track_states(result, max_tracks)
+    """All ranks receive every rank's records: returns a (world, max_tracks, 8) tensor on the exchange device
+    (the rank's GPU under NCCL, the host under gloo), whatever device the BoxList itself lives on."""
+    rec = pack_track_states(result, max_tracks, device=exchange_device(result, group))
     if not (dist.is_available() and dist.is_initialized()):
         return rec[None]
     world = dist.get_world_size(group)
