@@ -490,7 +490,9 @@ def run_ours(args):
             out["experimental"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         dog.cancel()
     print(json.dumps(out))
+    sys.stdout.flush()
     if distributed:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -10,6 +10,16 @@ import copy
 import yaml
 
 
+def _literal(text):
+    """A Python literal written in a yaml value / command-line override ("(30000, 40000)", "0.5", "True"), as yacs decodes
+    them: ast.literal_eval -- never eval -- falling back to the raw string."""
+    import ast
+    try:
+        return ast.literal_eval(text)
+    except (ValueError, SyntaxError):
+        return text
+
+
 class CfgNode(dict):
     def __init__(self, init_dict=None):
         super().__init__()
@@ -51,7 +61,7 @@ class CfgNode(dict):
     @staticmethod
     def _coerce(old, new):
         if isinstance(new, str) and isinstance(old, (tuple, list)):
-            new = eval(new)  # yaml has no tuple syntax: "(30000, 40000)" arrives as a string
+            new = _literal(new)  # yaml has no tuple syntax: "(30000, 40000)" arrives as a string
         if isinstance(old, tuple) and isinstance(new, list):
             new = tuple(new)
         elif isinstance(old, list) and isinstance(new, tuple):
@@ -87,10 +97,7 @@ class CfgNode(dict):
             for p in parts[:-1]:
                 node = node[p]
             if isinstance(val, str):
-                try:
-                    val = eval(val)
-                except Exception:
-                    pass
+                val = _literal(val)
             node._merge({parts[-1]: val})
 
 

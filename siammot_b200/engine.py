@@ -138,7 +138,7 @@ class _Plan(object):
                 self.run_eager()  # warm-up: sets function attributes, surfaces argument errors
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=self.e.capture_stream(0)):
                     self.run_eager()
                 self.graph = g
             self.graph.replay()
@@ -157,7 +157,7 @@ class _Plan(object):
             self.run_eager(lo, hi)  # warm-up on live data (the other half has run): sets function attributes
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self.e.capture_stream(0 if part == 0 else -1)):
                 self.run_eager(lo, hi)
             self.part_graphs[part] = g
         self.part_graphs[part].replay()
@@ -368,7 +368,7 @@ class _TrackPlan(object):
         for part in (0, 1):
             if use_graph and self.part_graphs[part] is None and self.part_warm[part]:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=eng.capture_stream(-2)):
                     self._enqueue_part(part)
                 self.part_graphs[part] = g
             if use_graph and self.part_graphs[part] is not None:
@@ -392,7 +392,7 @@ class _TrackPlan(object):
         if eng.use_graph and not (eng.timers is not None and eng.time_kernels) and self.det_is_static:
             if self.graph is None and self.warm:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=eng.capture_stream(-2)):
                     self._enqueue()
                 self.graph = g
             if self.graph is not None:
@@ -474,6 +474,9 @@ class Engine(object):
         self.conv_ws_det = ops.conv_workspace(self.device)
         self._side = None
         self._tail = None
+        self._track = None
+        self._capture = {}
+        self.stream_priority = os.environ.get("SMOT_STREAM_PRIORITY", "1") == "1"
         # developer switches of SiamMOT.forward_clip: SMOT_CLIP_SPLIT=1 runs the detection tail of frame t
         # on a third stream under the backbone of frame t+1; SMOT_CLIP_SLOTS = number of static-plan copies (2 or 3)
         self.body_branches = os.environ.get("SMOT_BODY_BRANCHES", "0") == "1"
@@ -954,17 +957,35 @@ class Engine(object):
             self._branch_streams.append(torch.cuda.Stream(device=self.device))
         return self._branch_streams[:n]
 
+    # Stream priorities (SMOT_STREAM_PRIORITY=0 turns them off).  The pipelines overlap one stage whose kernels fill the GPU
+    # (the backbone half of frame t+1) with two latency-bound chains of small kernels (detection tail and track stage of frame
+    # t, ~60 dependent launches).  With equal priorities every link of a chain queues behind the backbone's pending CTAs; with
+    # the chains on higher-priority streams the block scheduler serves them first, and the backbone fills what they leave.
     def side_stream(self):
-        """The stream forward_clip runs the frame-independent stage on (created on first use)."""
+        """The stream forward_clip runs the frame-independent stage on (created on first use; lowest priority)."""
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            self._side = torch.cuda.Stream(device=self.device, priority=0)
         return self._side
 
     def tail_stream(self):
-        """Three-stage clip mode: the stream of the detection tail."""
+        """The stream of the detection tail (three-stage clip mode, per-frame overlap mode); above the backbone's priority."""
         if self._tail is None:
-            self._tail = torch.cuda.Stream(device=self.device)
+            self._tail = torch.cuda.Stream(device=self.device, priority=-1 if self.stream_priority else 0)
         return self._tail
+
+    def track_stream(self):
+        """forward_clip's track stage runs here instead of on the caller's stream when priorities are on (highest priority:
+        the track stage + host solver is the sequential part of a video)."""
+        if self._track is None:
+            self._track = torch.cuda.Stream(device=self.device, priority=-2 if self.stream_priority else 0)
+        return self._track
+
+    def capture_stream(self, level):
+        """Stream to capture a CUDA graph on: kernel nodes inherit the capturing stream's priority (level 0 / -1 / -2)."""
+        level = level if self.stream_priority else 0
+        if level not in self._capture:
+            self._capture[level] = torch.cuda.Stream(device=self.device, priority=level)
+        return self._capture[level]
 
     def run_static(self, image, slot=0, part=None):
         """image: (3,H,W) or (1,3,H,W) float tensor (any device).  Enqueues backbone..detections on the current stream.

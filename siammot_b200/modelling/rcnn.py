@@ -565,9 +565,12 @@ def _forward_clip(self, frames, before_frame=None, given_detections=None):
         raise ValueError("given_detections: %d entries for %d frames" % (len(given_detections), n_frames))
     if eng.clip_split:
         return _forward_clip_three_stage(self, eng, frames, before_frame, given_detections)
-    cur = torch.cuda.current_stream(eng.device)
+    caller = torch.cuda.current_stream(eng.device)
+    cur = eng.track_stream() if eng.stream_priority else caller     # the track stage's stream (high priority, see Engine.side_stream)
+    if cur is not caller:
+        cur.wait_stream(caller)
     side = eng.side_stream()
-    side.wait_stream(cur)          # the frames (and anything else already enqueued) are visible to the side stream
+    side.wait_stream(caller)       # the frames (and anything else already enqueued) are visible to the side stream
     slot_free = [None, None]       # event: every reader of the slot's buffers (track stage, template pooling) is enqueued-complete
 
     def static(t):
@@ -580,7 +583,7 @@ def _forward_clip(self, frames, before_frame=None, given_detections=None):
             P.static_done.record(side)
         return P
 
-    with torch.no_grad():
+    with torch.no_grad(), torch.cuda.stream(cur):
         P_next = static(0)
         for t in range(n_frames):
             P = P_next
@@ -598,7 +601,21 @@ def _forward_clip(self, frames, before_frame=None, given_detections=None):
             self.track_memory = mem
             results.append(result)
         cur.wait_stream(side)
+    if cur is not caller:
+        caller.wait_stream(cur)
+        for r in results:
+            _record_on(r, caller)
     return results
+
+
+def _record_on(boxlist, stream):
+    """A device BoxList allocated on the track stream is handed to the caller's stream: tell the caching allocator."""
+    if boxlist.bbox.is_cuda:
+        boxlist.bbox.record_stream(stream)
+        for f in boxlist.fields():
+            v = boxlist.get_field(f)
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(stream)
 
 
 def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detections=None):
@@ -616,10 +633,13 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detect
     n_frames = len(frames)
     K = eng.clip_slots
     results = []
-    cur = torch.cuda.current_stream(eng.device)
+    caller = torch.cuda.current_stream(eng.device)
+    cur = eng.track_stream() if eng.stream_priority else caller     # the track stage's stream (high priority, see Engine.side_stream)
+    if cur is not caller:
+        cur.wait_stream(caller)
     sA, sD = eng.side_stream(), eng.tail_stream()
-    sA.wait_stream(cur)            # the frames (and anything else already enqueued) are visible to the worker streams
-    sD.wait_stream(cur)
+    sA.wait_stream(caller)         # the frames (and anything else already enqueued) are visible to the worker streams
+    sD.wait_stream(caller)
     slot_free = [None] * K         # event: every reader of the slot's buffers (D, T, template pooling) is enqueued-complete
     plans = {}
 
@@ -643,7 +663,7 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detect
                 P.static_done = torch.cuda.Event()
             P.static_done.record(sD)
 
-    with torch.no_grad():
+    with torch.no_grad(), torch.cuda.stream(cur):
         for t in range(min(K - 1, n_frames)):
             backbone(t)
         detect(0)
@@ -666,6 +686,10 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detect
             results.append(result)
         cur.wait_stream(sA)
         cur.wait_stream(sD)
+    if cur is not caller:
+        caller.wait_stream(cur)
+        for r in results:
+            _record_on(r, caller)
     return results
 
 
