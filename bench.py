@@ -74,13 +74,51 @@ def config_dict(world=1):
             "tracks_in_memory": N_TRACKS, "parallelism": "1 stream per GPU x %d" % world}
 
 
+_HOST_THREADS = None
+
+
 def host_threads():
-    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would otherwise make the CPU legs
-    single-threaded)."""
+    """The torch thread count that makes the CPU legs fastest on this host, found by timing a small convolution at
+    4 / 8 / 16 / ... / all CPUs this process may use (bounded by the cgroup CPU quota when there is one).  "All the host
+    threads it can use" is not the affinity count on a shared box: on the round-2 GPU hosts 128 threads made the oracle 40x
+    SLOWER than 8 (quota + hyper-threads), which would have flattered the GPU/CPU ratio.  torchrun's OMP_NUM_THREADS=1 is
+    overridden by whoever calls torch.set_num_threads(host_threads())."""
+    global _HOST_THREADS
+    if _HOST_THREADS is not None:
+        return _HOST_THREADS
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        limit = max(1, len(os.sched_getaffinity(0)))
     except Exception:
-        return max(1, os.cpu_count() or 1)
+        limit = max(1, os.cpu_count() or 1)
+    try:   # cgroup v2 / v1 CPU quota
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            limit = max(1, min(limit, int(float(q[0]) / float(q[1]) + 0.5)))
+    except Exception:
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                limit = max(1, min(limit, (quota + period // 2) // period))
+        except Exception:
+            pass
+    cands = sorted({c for c in (4, 8, 16, 32, 64, 128, 256) if c < limit} | {limit})
+    keep = torch.get_num_threads()
+    x = torch.randn(1, 64, 176, 320)
+    w = torch.randn(64, 64, 3, 3)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.conv2d(x, w, padding=1)
+        dt = time.perf_counter() - t0
+        if dt < 0.95 * best_t:       # prefer fewer threads unless clearly faster
+            best, best_t = c, dt
+    torch.set_num_threads(keep)
+    _HOST_THREADS = best
+    return best
 
 
 def pin_to_gpu_numa_node(local):

@@ -41,6 +41,7 @@ struct TcArgs {
   int tiles_w, tiles_h, tile_w, tile_h;
   // split-K (gridDim.z > 1): fp32 partial tiles [z][tile][128][Cout], summed by splitk_reduce_kernel
   int splits, chunks_per_split, num_tiles;
+  int cluster_reduce;   // 1: the `splits` CTAs of a tile are one thread-block cluster and finish the tile themselves (no reduce kernel)
   float* partial;
   unsigned long long* dbg;  // developer timing probe (SMOT_TC_DEBUG): 8 timestamps of CTA (0,0,0), else null
 };
@@ -231,6 +232,51 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, uint32_t tmem_base,
     }
   }
 
+// ---- split-K finish inside the cluster (replaces splitk_reduce_kernel: 22 launches, ~6 us each, 10 % of a frame in round 1).
+// The `splits` CTAs of an output tile are launched as ONE thread-block cluster (1,1,splits): they are co-scheduled by the
+// hardware, so after parking their raw fp32 partial tiles in the L2-resident workspace they can meet at a cluster barrier and
+// each finish 128/splits rows of the tile: sum the partials in split order (deterministic, the same order and the same
+// fp32 operations as splitk_reduce_kernel, so the results are bit-identical to it), scale / bias / residual / ReLU, fp16 store.
+// Per CTA: 128 x BN x 4 B of partials read back from L2 (.cg: written by other SMs), ~1 us, instead of a kernel boundary.
+template <int BN>
+__device__ __forceinline__ void tc_splitk_finish(const TcArgs& a, const float* s_scale, const float* s_bias, int img, int h0, int w0,
+                                                 int n0) {
+  const int tid = (int)threadIdx.x - 64;                 // the four epilogue warps
+  const int rows_per = (TC_BM + a.splits - 1) / a.splits;
+  const int r_lo = (int)blockIdx.z * rows_per;
+  const int r_hi = min(TC_BM, r_lo + rows_per);
+  constexpr int C4 = BN / 4;
+  const size_t zstride = (size_t)a.num_tiles * TC_BM * a.Cout;
+  const float* tile = a.partial + (size_t)blockIdx.x * TC_BM * a.Cout + n0;
+  for (int idx = tid; idx < (r_hi - r_lo) * C4; idx += 128) {
+    const int row = r_lo + idx / C4, c = (idx % C4) * 4;
+    const int oh = h0 + row / a.tile_w, ow = w0 + row % a.tile_w;
+    if (oh >= a.H || ow >= a.W) continue;
+    const float* p = tile + (size_t)row * a.Cout + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < a.splits; ++z) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p + (size_t)z * zstride));
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (a.scale) v[j] = __fmul_rn(v[j], s_scale[c + j]);
+      if (a.bias) v[j] = __fadd_rn(v[j], s_bias[c + j]);
+    }
+    const size_t pix = ((size_t)img * a.H + oh) * a.W + ow;
+    if (a.res) {
+      const float4 r = ld4(a.res + pix * a.res_ld + n0 + c);
+      v[0] += r.x, v[1] += r.y, v[2] += r.z, v[3] += r.w;
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    st4(a.out + pix * a.out_ld + n0 + c, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
 template <int BN, int STAGES>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
@@ -327,6 +373,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     tc_epilogue<BN>(a, tmem_base, s_scale, s_bias, tmem_full, img, h0, w0, n0);
   }
   if (warp == 2 && lane == 0) TC_STAMP(4);
+  if (a.cluster_reduce) {
+    // every CTA of the tile's cluster has parked its partial: publish (gpu scope), meet, finish 128 / splits rows each
+    __threadfence();
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp >= 2) tc_splitk_finish<BN>(a, s_scale, s_bias, img, h0, w0, n0);
+  }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TC_STAMP(5);
@@ -563,14 +617,76 @@ bool conv2d_tc_supported(const smot_conv_desc* d) {
   return true;
 }
 
+// launch attributes: programmatic dependent launch always; a (1,1,cluster_z) thread-block cluster when the CTAs of a tile
+// finish their split-K sum themselves
+template <int BN, int STAGES>
+static cudaError_t launch_tc_ex(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, dim3 grid, int cluster_z,
+                                cudaStream_t st) {
+  using S = TcSmem<BN, STAGES>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = S::TOTAL, cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  if (cluster_z > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 1, attr[1].val.clusterDim.y = 1, attr[1].val.clusterDim.z = (unsigned)cluster_z;
+    cfg.numAttrs = 2;
+  }
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES>, tmA, tmB, a);
+}
+
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, dim3 grid, cudaStream_t st) {
   using S = TcSmem<BN, STAGES>;
   SMOT_ENSURE_SMEM((conv_tc_kernel<BN, STAGES>), S::TOTAL, "smot_conv2d(tcgen05)");
-  launch_pdl(conv_tc_kernel<BN, STAGES>, grid, dim3(TC_THREADS), S::TOTAL, st, tmA, tmB, a);
+  cudaError_t e = launch_tc_ex<BN, STAGES>(tmA, tmB, a, grid, a.cluster_reduce ? a.splits : 1, st);
+  if (e != cudaSuccess) {
+    set_error("smot_conv2d(tcgen05): launch failed: %s", cudaGetErrorString(e));
+    return SMOT_ERR_CUDA;
+  }
   SMOT_CHECK_LAUNCH("smot_conv2d(tcgen05)");
   return SMOT_OK;
 }
+
+// How many (1,1,cz) clusters of this kernel variant the device can hold at once (a cluster lives inside one GPC, so this is
+// NOT 148 / cz: 8-CTA clusters fit twice into a 16..20-SM GPC).  Queried once per (variant, cz); 0 = query failed.
+template <int BN, int STAGES>
+static int tc_max_clusters(int cz) {
+  static std::mutex mu;
+  static int cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+  if (cz < 2 || cz > 8) return 0;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache[cz] >= 0) return cache[cz];
+  using S = TcSmem<BN, STAGES>;
+  int n = 0;
+  if (cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1, 1, (unsigned)cz), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = S::TOTAL;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = (unsigned)cz;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, STAGES>, &cfg) != cudaSuccess) n = 0;
+  }
+  (void)cudaGetLastError();
+  cache[cz] = n;
+  return n;
+}
+
+// ring depth of the generic kernel for a given tile width / CTA population / K length (measured choices, see conv2d_tc)
+static int tc_stages(int BN, bool solo, bool shallow, int my_chunks, int forced) {
+  if (BN == 256) return (forced ? forced >= 4 : (solo && my_chunks >= 4)) ? 4 : 3;
+  const bool deep = forced ? forced >= 6 : (solo && my_chunks >= 6);
+  if (BN == 128) return shallow ? 2 : (deep ? 6 : 3);
+  return deep ? 8 : (shallow ? 2 : 4);
+}
+
+#define SMOT_TC_DISPATCH(BN_, ST_, EXPR)                                                       \
+  ((BN_) == 256 ? ((ST_) == 4 ? EXPR(256, 4) : EXPR(256, 3))                                    \
+   : (BN_) == 128 ? ((ST_) == 2 ? EXPR(128, 2) : ((ST_) == 6 ? EXPR(128, 6) : EXPR(128, 3)))   \
+                  : ((ST_) == 8 ? EXPR(64, 8) : ((ST_) == 2 ? EXPR(64, 2) : EXPR(64, 4))))
 
 template <int BN, int PW, int SB>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, dim3 grid, int bo_mode, cudaStream_t st) {
@@ -629,6 +745,7 @@ static int conv2d_tc_halo(const smot_conv_desc* d, int mode, cudaStream_t st) {
   a.chunks_per_split = (a.cin_chunks + splits - 1) / splits;
   a.splits = (a.cin_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
   a.num_tiles = (int)tiles;
+  a.cluster_reduce = 0;
   a.dbg = nullptr;
   a.partial = d->workspace ? (float*)((char*)d->workspace + SMOT_CONV_WS_COUNTER_BYTES) : nullptr;
   dim3 grid((unsigned)tiles, (unsigned)(d->Cout / BN), (unsigned)a.splits);
@@ -669,7 +786,10 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   int BN = 64;
   if (d->Cout % 256 == 0 && tiles * (d->Cout / 256) >= min_ctas) BN = 256;
   else if (d->Cout % 128 == 0 && tiles * (d->Cout / 128) >= min_ctas) BN = 128;
-  int splits = 1;
+  const char* force = getenv("SMOT_TC_STAGES");  // developer override: ring depth
+  const int fs = force ? atoi(force) : 0;
+  static const bool cluster_ok = !(getenv("SMOT_TC_CLUSTER") && atoi(getenv("SMOT_TC_CLUSTER")) == 0);   // developer A/B switch
+  int splits = 1, cluster_reduce = 0;
   {
     const int bw = d->Cout % 256 == 0 ? 256 : (d->Cout % 128 == 0 ? 128 : 64);
     const long long cw = tiles * (d->Cout / bw);
@@ -678,7 +798,25 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
       if (sp > 8) sp = 8;
       if (sp > all_chunks / 4) sp = all_chunks / 4;
       const size_t need = (size_t)SMOT_CONV_WS_COUNTER_BYTES + (size_t)sp * tiles * TC_BM * d->Cout * sizeof(float);
-      if (sp >= 2 && need <= d->workspace_bytes) splits = sp, BN = bw;
+      if (sp >= 2 && need <= d->workspace_bytes) {
+        // preferred: the split CTAs of a tile form a cluster and finish the tile themselves; take the widest split whose
+        // clusters are all resident at once (the cluster barrier needs co-residency only inside a cluster, but a second wave
+        // would double the layer's time)
+        for (int cz = cluster_ok ? sp : 0; cz >= 2; --cz) {
+          const int cps = (all_chunks + cz - 1) / cz;
+          const int real = (all_chunks + cps - 1) / cps;                       // no empty split
+          if (real != cz) continue;
+          const int stg = tc_stages(bw, true, false, cps, fs);
+#define SMOT_TC_MAXC(BN_, ST_) tc_max_clusters<BN_, ST_>(cz)
+          const int fit = SMOT_TC_DISPATCH(bw, stg, SMOT_TC_MAXC);
+#undef SMOT_TC_MAXC
+          if (fit >= cw) {
+            splits = cz, BN = bw, cluster_reduce = 1;
+            break;
+          }
+        }
+        if (!cluster_reduce) splits = sp, BN = bw;                             // fallback: partials + splitk_reduce_kernel
+      }
     }
   }
   CUtensorMap tmA, tmB;
@@ -700,6 +838,7 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   a.splits = splits;
   a.chunks_per_split = (all_chunks + splits - 1) / splits;
   a.splits = (all_chunks + a.chunks_per_split - 1) / a.chunks_per_split;  // no empty split
+  a.cluster_reduce = (cluster_reduce && a.splits == splits) ? 1 : 0;
   a.num_tiles = (int)tiles;
   {
     const char* dbg = getenv("SMOT_TC_DEBUG");  // hex device pointer to 8 x u64
@@ -709,25 +848,15 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   dim3 grid((unsigned)tiles, (unsigned)(d->Cout / BN), (unsigned)a.splits);
   // many short tiles: 2-stage rings let 4 CTAs share an SM, so one CTA's prologue / epilogue overlaps the
   // main loops of the others (same bytes in flight per SM as 2 CTAs x 4 stages)
-  const char* force = getenv("SMOT_TC_STAGES");  // developer override: ring depth
-  const int fs = force ? atoi(force) : 0;
-  const int my_chunks = a.chunks_per_split;
   const bool shallow = fs ? fs == 2 : (tiles * (d->Cout / BN) >= 296 && all_chunks <= 36);
   // at most one CTA per SM: nothing else hides the ~1 us TMA round trip (the loop then advances `ring depth` chunks
   // per round trip), so use the whole shared memory for the ring: 8 x 24 KB, 6 x 32 KB, 4 x 48 KB
   const bool solo = (long long)grid.x * grid.y * grid.z <= 148;
-  const bool deep = fs ? fs >= 6 : (solo && my_chunks >= 6);
-  int rc;
-  if (BN == 256)
-    rc = (fs ? fs >= 4 : (solo && my_chunks >= 4)) ? launch_tc<256, 4>(tmA, tmB, a, grid, st) : launch_tc<256, 3>(tmA, tmB, a, grid, st);
-  else if (BN == 128)
-    rc = shallow ? launch_tc<128, 2>(tmA, tmB, a, grid, st)
-                 : (deep ? launch_tc<128, 6>(tmA, tmB, a, grid, st) : launch_tc<128, 3>(tmA, tmB, a, grid, st));
-  else if (deep)
-    rc = launch_tc<64, 8>(tmA, tmB, a, grid, st);
-  else
-    rc = shallow ? launch_tc<64, 2>(tmA, tmB, a, grid, st) : launch_tc<64, 4>(tmA, tmB, a, grid, st);
-  if (rc != SMOT_OK || a.splits == 1) return rc;
+  const int stages = tc_stages(BN, solo, shallow, a.chunks_per_split, fs);
+#define SMOT_TC_LAUNCH(BN_, ST_) launch_tc<BN_, ST_>(tmA, tmB, a, grid, st)
+  const int rc = SMOT_TC_DISPATCH(BN, stages, SMOT_TC_LAUNCH);
+#undef SMOT_TC_LAUNCH
+  if (rc != SMOT_OK || a.splits == 1 || a.cluster_reduce) return rc;
   const size_t total_out = (size_t)a.num_tiles * TC_BM * (d->Cout / 4);
   launch_pdl(splitk_reduce_kernel, dim3((unsigned)((total_out + 255) / 256)), dim3(256), 0, st, a);
   SMOT_CHECK_LAUNCH("smot_conv2d(split-K reduce)");

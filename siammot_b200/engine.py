@@ -87,7 +87,7 @@ class _Plan(object):
 
     def conv(self, x, name, out, residual=None, stride=1, pad=0, relu=False):
         w, scale, bias = self.e.weights[name]
-        ws = self.ws if self.branch is None else self.e.branch_ws(self.branch)
+        ws = self.ws if self.branch is None else self.e.branch_ws(self.branch, getattr(self, "slot", 0))
         d = ops.conv_desc(x, w, out, scale, bias, residual, stride, pad, relu, workspace=ws)
         self.keep.append(d)
         self.steps.append((lib().smot_conv2d, (C.byref(d),), "conv:" + name, self.branch))
@@ -138,7 +138,7 @@ class _Plan(object):
                 self.run_eager()  # warm-up: sets function attributes, surfaces argument errors
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self.e.capture_stream(0)):
+                with torch.cuda.graph(g):
                     self.run_eager()
                 self.graph = g
             self.graph.replay()
@@ -157,7 +157,7 @@ class _Plan(object):
             self.run_eager(lo, hi)  # warm-up on live data (the other half has run): sets function attributes
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self.e.capture_stream(0 if part == 0 else -1)):
+            with torch.cuda.graph(g):
                 self.run_eager(lo, hi)
             self.part_graphs[part] = g
         self.part_graphs[part].replay()
@@ -368,7 +368,7 @@ class _TrackPlan(object):
         for part in (0, 1):
             if use_graph and self.part_graphs[part] is None and self.part_warm[part]:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=eng.capture_stream(-2)):
+                with torch.cuda.graph(g):
                     self._enqueue_part(part)
                 self.part_graphs[part] = g
             if use_graph and self.part_graphs[part] is not None:
@@ -392,7 +392,7 @@ class _TrackPlan(object):
         if eng.use_graph and not (eng.timers is not None and eng.time_kernels) and self.det_is_static:
             if self.graph is None and self.warm:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=eng.capture_stream(-2)):
+                with torch.cuda.graph(g):
                     self._enqueue()
                 self.graph = g
             if self.graph is not None:
@@ -474,9 +474,6 @@ class Engine(object):
         self.conv_ws_det = ops.conv_workspace(self.device)
         self._side = None
         self._tail = None
-        self._track = None
-        self._capture = {}
-        self.stream_priority = os.environ.get("SMOT_STREAM_PRIORITY", "1") == "1"
         # developer switches of SiamMOT.forward_clip: SMOT_CLIP_SPLIT=1 runs the detection tail of frame t
         # on a third stream under the backbone of frame t+1; SMOT_CLIP_SLOTS = number of static-plan copies (2 or 3)
         self.body_branches = os.environ.get("SMOT_BODY_BRANCHES", "0") == "1"
@@ -488,7 +485,12 @@ class Engine(object):
         self.clip_split = os.environ.get("SMOT_CLIP_SPLIT", "1") == "1"
         self.clip_slots = max(2, min(4, int(os.environ.get("SMOT_CLIP_SLOTS", "3"))))
         self._pre = None
-        self._branch_ws = []
+        self._branch_ws = {}
+        self._slot_ws = {}
+        self._bb_streams = []
+        # forward_clip (three-stage): number of streams the backbone halves of consecutive frames alternate over (needs
+        # SMOT_CLIP_SLOTS >= streams + 1 plan copies to matter)
+        self.clip_backbone_streams = max(1, min(3, int(os.environ.get("SMOT_CLIP_BACKBONE_STREAMS", "1"))))
         self._branch_streams = []
         self._track_plans = {}
         self._arenas = {}
@@ -815,6 +817,7 @@ class Engine(object):
         cfg, dev, dt = self.cfg, self.device, self.dtype
         P = _Plan(self, H, W)
         P.slot = slot
+        P.ws = self.backbone_ws(slot)
         L = lib()
         dc = _lib.dtype_code(dt)
         # ---- input
@@ -946,46 +949,48 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     # per-frame entry points
     # ------------------------------------------------------------------------------------------
-    def branch_ws(self, b):
-        """Split-K scratch of parallel branch b (concurrent convolutions must not share one)."""
-        while len(self._branch_ws) <= b:
-            self._branch_ws.append(ops.conv_workspace(self.device))
-        return self._branch_ws[b]
+    def branch_ws(self, b, slot=0):
+        """Split-K scratch of parallel branch b (concurrent convolutions must not share one).  With several backbone streams
+        (clip_backbone_streams > 1) the backbones of consecutive frames run concurrently: one set per plan slot."""
+        key = (slot if self.clip_backbone_streams > 1 else 0, b)
+        if key not in self._branch_ws:
+            self._branch_ws[key] = ops.conv_workspace(self.device)
+        return self._branch_ws[key]
+
+    def backbone_ws(self, slot):
+        """Split-K scratch of the backbone half of plan slot `slot` (shared by all slots while one stream runs them in turn)."""
+        if self.clip_backbone_streams <= 1 or slot == 0:
+            return self.conv_ws
+        if slot not in self._slot_ws:
+            self._slot_ws[slot] = ops.conv_workspace(self.device)
+        return self._slot_ws[slot]
+
+    def backbone_stream(self, t):
+        """The stream the backbone half of clip frame t runs on: frames alternate over clip_backbone_streams low-priority
+        streams, so the (GPU-underfilling, fixed-cost-dominated) layers of consecutive frames' backbones interleave."""
+        n = max(1, self.clip_backbone_streams)
+        if n == 1:
+            return self.side_stream()
+        while len(self._bb_streams) < n:
+            self._bb_streams.append(self.side_stream() if not self._bb_streams else torch.cuda.Stream(device=self.device))
+        return self._bb_streams[t % n]
 
     def branch_streams(self, n):
         while len(self._branch_streams) < n:
             self._branch_streams.append(torch.cuda.Stream(device=self.device))
         return self._branch_streams[:n]
 
-    # Stream priorities (SMOT_STREAM_PRIORITY=0 turns them off).  The pipelines overlap one stage whose kernels fill the GPU
-    # (the backbone half of frame t+1) with two latency-bound chains of small kernels (detection tail and track stage of frame
-    # t, ~60 dependent launches).  With equal priorities every link of a chain queues behind the backbone's pending CTAs; with
-    # the chains on higher-priority streams the block scheduler serves them first, and the backbone fills what they leave.
     def side_stream(self):
-        """The stream forward_clip runs the frame-independent stage on (created on first use; lowest priority)."""
+        """The stream forward_clip runs the frame-independent stage on (created on first use)."""
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device, priority=0)
+            self._side = torch.cuda.Stream(device=self.device)
         return self._side
 
     def tail_stream(self):
-        """The stream of the detection tail (three-stage clip mode, per-frame overlap mode); above the backbone's priority."""
+        """The stream of the detection tail (three-stage clip mode, per-frame overlap mode)."""
         if self._tail is None:
-            self._tail = torch.cuda.Stream(device=self.device, priority=-1 if self.stream_priority else 0)
+            self._tail = torch.cuda.Stream(device=self.device)
         return self._tail
-
-    def track_stream(self):
-        """forward_clip's track stage runs here instead of on the caller's stream when priorities are on (highest priority:
-        the track stage + host solver is the sequential part of a video)."""
-        if self._track is None:
-            self._track = torch.cuda.Stream(device=self.device, priority=-2 if self.stream_priority else 0)
-        return self._track
-
-    def capture_stream(self, level):
-        """Stream to capture a CUDA graph on: kernel nodes inherit the capturing stream's priority (level 0 / -1 / -2)."""
-        level = level if self.stream_priority else 0
-        if level not in self._capture:
-            self._capture[level] = torch.cuda.Stream(device=self.device, priority=level)
-        return self._capture[level]
 
     def run_static(self, image, slot=0, part=None):
         """image: (3,H,W) or (1,3,H,W) float tensor (any device).  Enqueues backbone..detections on the current stream.
@@ -1020,7 +1025,7 @@ class Engine(object):
         oh, ow = pre.output_size(frame.shape[0], frame.shape[1])
         P = self.plan(oh, ow, slot)
         with self.timed("preprocess"):
-            pre.into(frame, P.img_in)
+            pre.into(frame, P.img_in, slot if self.clip_backbone_streams > 1 else 0)
         with self.timed("static"):
             P.run() if part is None else P.run_part(part)
         return P

@@ -565,12 +565,9 @@ def _forward_clip(self, frames, before_frame=None, given_detections=None):
         raise ValueError("given_detections: %d entries for %d frames" % (len(given_detections), n_frames))
     if eng.clip_split:
         return _forward_clip_three_stage(self, eng, frames, before_frame, given_detections)
-    caller = torch.cuda.current_stream(eng.device)
-    cur = eng.track_stream() if eng.stream_priority else caller     # the track stage's stream (high priority, see Engine.side_stream)
-    if cur is not caller:
-        cur.wait_stream(caller)
+    cur = torch.cuda.current_stream(eng.device)
     side = eng.side_stream()
-    side.wait_stream(caller)       # the frames (and anything else already enqueued) are visible to the side stream
+    side.wait_stream(cur)          # the frames (and anything else already enqueued) are visible to the side stream
     slot_free = [None, None]       # event: every reader of the slot's buffers (track stage, template pooling) is enqueued-complete
 
     def static(t):
@@ -583,7 +580,7 @@ def _forward_clip(self, frames, before_frame=None, given_detections=None):
             P.static_done.record(side)
         return P
 
-    with torch.no_grad(), torch.cuda.stream(cur):
+    with torch.no_grad():
         P_next = static(0)
         for t in range(n_frames):
             P = P_next
@@ -601,21 +598,7 @@ def _forward_clip(self, frames, before_frame=None, given_detections=None):
             self.track_memory = mem
             results.append(result)
         cur.wait_stream(side)
-    if cur is not caller:
-        caller.wait_stream(cur)
-        for r in results:
-            _record_on(r, caller)
     return results
-
-
-def _record_on(boxlist, stream):
-    """A device BoxList allocated on the track stream is handed to the caller's stream: tell the caching allocator."""
-    if boxlist.bbox.is_cuda:
-        boxlist.bbox.record_stream(stream)
-        for f in boxlist.fields():
-            v = boxlist.get_field(f)
-            if torch.is_tensor(v) and v.is_cuda:
-                v.record_stream(stream)
 
 
 def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detections=None):
@@ -633,25 +616,27 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detect
     n_frames = len(frames)
     K = eng.clip_slots
     results = []
-    caller = torch.cuda.current_stream(eng.device)
-    cur = eng.track_stream() if eng.stream_priority else caller     # the track stage's stream (high priority, see Engine.side_stream)
-    if cur is not caller:
-        cur.wait_stream(caller)
+    cur = torch.cuda.current_stream(eng.device)
     sA, sD = eng.side_stream(), eng.tail_stream()
-    sA.wait_stream(caller)         # the frames (and anything else already enqueued) are visible to the worker streams
-    sD.wait_stream(caller)
+    sA.wait_stream(cur)            # the frames (and anything else already enqueued) are visible to the worker streams
+    sD.wait_stream(cur)
     slot_free = [None] * K         # event: every reader of the slot's buffers (D, T, template pooling) is enqueued-complete
     plans = {}
+    extra = []                     # further backbone streams in use (Engine.backbone_stream)
 
     def backbone(t):
         s = t % K
-        with torch.cuda.stream(sA):
+        sB = eng.backbone_stream(t)           # sA, or one of several alternating backbone streams
+        if sB is not sA and sB not in extra:
+            sB.wait_stream(cur)
+            extra.append(sB)
+        with torch.cuda.stream(sB):
             if slot_free[s] is not None:
-                sA.wait_event(slot_free[s])
+                sB.wait_event(slot_free[s])
             P = (eng.run_static_raw(frames[t], s, part=0) if _is_raw_frame(frames[t]) else eng.run_static(frames[t], s, part=0))
             if P.backbone_done is None:
                 P.backbone_done = torch.cuda.Event()
-            P.backbone_done.record(sA)
+            P.backbone_done.record(sB)
         plans[t] = P
 
     def detect(t):
@@ -663,7 +648,7 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detect
                 P.static_done = torch.cuda.Event()
             P.static_done.record(sD)
 
-    with torch.no_grad(), torch.cuda.stream(cur):
+    with torch.no_grad():
         for t in range(min(K - 1, n_frames)):
             backbone(t)
         detect(0)
@@ -686,10 +671,8 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detect
             results.append(result)
         cur.wait_stream(sA)
         cur.wait_stream(sD)
-    if cur is not caller:
-        caller.wait_stream(cur)
-        for r in results:
-            _record_on(r, caller)
+        for sB in extra:
+            cur.wait_stream(sB)
     return results
 
 

@@ -74,21 +74,23 @@ class FramePreprocessor(object):
     def output_size(self, h, w):
         return get_size(w, h, self.min_size, self.max_size, self.div)
 
-    def geometry(self, h, w):
-        g = self._geo.get((h, w))
+    def geometry(self, h, w, lane=0):
+        """Staging buffers + coefficient tables of one input size; ``lane`` selects an independent copy of the staging
+        buffers (callers that transform frames on several streams at once use one lane per stream)."""
+        g = self._geo.get((h, w, lane))
         if g is None:
             oh, ow = self.output_size(h, w)
-            g = self._geo[(h, w)] = _Geometry(h, w, oh, ow, self.device)
+            g = self._geo[(h, w, lane)] = _Geometry(h, w, oh, ow, self.device)
         return g
 
-    def into(self, frame, out):
+    def into(self, frame, out, lane=0):
         """frame: uint8 (H, W, 3) RGB tensor / numpy array (host -- ideally pinned -- or device); out: float32
         (3, oh, ow) contiguous CUDA tensor.  Enqueues the copy and the kernels on the current stream."""
         if isinstance(frame, np.ndarray):
             frame = torch.from_numpy(frame)
         if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3:
             raise ValueError("expected a uint8 (H, W, 3) RGB frame, got %s %s" % (frame.dtype, tuple(frame.shape)))
-        g = self.geometry(frame.shape[0], frame.shape[1])
+        g = self.geometry(frame.shape[0], frame.shape[1], lane)
         if tuple(out.shape) != (3, g.oh, g.ow) or out.dtype != torch.float32 or not out.is_contiguous():
             raise ValueError("output must be a contiguous float32 (3, %d, %d) tensor" % (g.oh, g.ow))
         g.frame.copy_(frame, non_blocking=True)

@@ -450,7 +450,7 @@ def install_for_bench(monkeypatch):
         orig_init(self, cfg, device)
         self._cfg = cfg
 
-    def into(self, frame, out):
+    def into(self, frame, out, lane=0):
         out.copy_(opp.preprocess(frame.numpy() if torch.is_tensor(frame) else frame, self._cfg))
         return out
 

@@ -22,7 +22,7 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
 from oracle import reference_loader  # noqa: E402
-from scenarios import GIVEN_SCENARIOS, ORACLE_SCENARIOS, SCENARIOS, given_boxes, golden_path, inject_boxes  # noqa: E402
+from scenarios import FULL_SCENARIOS, GIVEN_SCENARIOS, ORACLE_SCENARIOS, SCENARIOS, given_boxes, golden_path, inject_boxes  # noqa: E402
 from siammot_b200.synthetic import make_state_dict  # noqa: E402
 from siammot_b200.synth_clip import make_clip  # noqa: E402
 
@@ -35,13 +35,18 @@ def build_reference(sc):
     cfg.MODEL.DEVICE = "cpu"
     model = build(cfg).eval()
     sd = model.state_dict()
-    sd.update(make_state_dict(cfg, sc["weight_seed"]))
+    new = make_state_dict(cfg, sc["weight_seed"])
+    if sc.get("tweak"):
+        from fp16_scene import apply_tweak
+        new = apply_tweak(new, cfg, sc["tweak"])
+    sd.update(new)
     model.load_state_dict(sd)
     return cfg, model
 
 
 def run(name):
-    sc = SCENARIOS.get(name) or ORACLE_SCENARIOS[name]
+    sc = SCENARIOS.get(name) or ORACLE_SCENARIOS.get(name) or FULL_SCENARIOS[name]
+    full = name in FULL_SCENARIOS
     cfg, model = build_reference(sc)
     from maskrcnn_benchmark.structures.bounding_box import BoxList
     clip = make_clip(sc["frames"], sc["H"], sc["W"], sc["n_obj"], sc["clip_seed"])
@@ -53,12 +58,16 @@ def run(name):
     frames = []
     start = 0
     with torch.no_grad():
-        if sc["inject"] is not None:
-            # seed the track table directly: 4 active tracks whose templates come from frame 0
+        if full or sc["inject"] is not None:
+            # seed the track table directly: active tracks whose templates come from frame 0
             feats = model.backbone(clip[0][None])
             head = model.roi_heads.track
             head.track_pool.reset()
-            boxes = inject_boxes(sc["inject"])
+            if full:
+                from fp16_scene import track_table
+                boxes = track_table(sc["tracks"], sc["H"], sc["W"])
+            else:
+                boxes = inject_boxes(sc["inject"])
             det = BoxList(boxes, (sc["W"], sc["H"]), mode="xyxy")
             det.add_field("ids", torch.tensor([head.track_pool.start_track() for _ in range(len(boxes))]))
             det.add_field("labels", torch.ones(len(boxes), dtype=torch.int64))
@@ -86,7 +95,30 @@ def run(name):
             frames.append(rec)
             print(name, "frame", t, "boxes", len(out), "tracked", int((rec["ids"] >= 0).sum()),
                   "active", len(rec["active"]), "dormant", len(rec["dormant"]))
-    torch.save(dict(scenario=name, spec=sc, torch=torch.__version__, frames=frames), golden_path(name))
+    extra = {}
+    if full:
+        # the oracle's view of the same clip: its outputs must equal the reference's (checked here, so the fixture is only
+        # written when they do) and its decision margins are stored for the GPU test to assert on
+        from decisive import MarginOracle, min_margin
+        from fp16_scene import build_scene
+        scene = build_scene(sc["weight_seed"], sc["clip_seed"], sc["frames"] - 1, sc["tweak"], workload=sc["workload"], tracks=sc["tracks"],
+                            n_obj=sc["n_obj"])
+        mo = MarginOracle(scene["cfg"], scene["sd"])
+        mo.inject(scene["clip"][0], scene["boxes"])
+        margins = []
+        for t in range(1, sc["frames"]):
+            out, m = mo.step(scene["clip"][t])
+            m.pop("top_logit_diff", None)
+            margins.append(m)
+            ref = frames[t - 1]
+            assert torch.equal(out["ids"], ref["ids"]) and torch.equal(out["labels"], ref["labels"]), "oracle ids differ from the reference"
+            assert float((out["boxes"] - ref["boxes"]).abs().max()) <= 1e-3 and float((out["scores"] - ref["scores"]).abs().max()) <= 1e-4
+        extra = dict(margins=margins, min_margin=min_margin(margins))
+        for f in frames:           # keep the fixture small: final outputs + track boxes only
+            for k in ("feat_stats", "props", "objectness"):
+                f.pop(k, None)
+        print(name, "oracle == reference on every frame; min margin", extra["min_margin"])
+    torch.save(dict(scenario=name, spec=sc, torch=torch.__version__, frames=frames, **extra), golden_path(name))
 
 
 def run_given(name):

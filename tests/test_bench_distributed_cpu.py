@@ -138,6 +138,7 @@ def test_reference_arm_prints_the_same_config_keys(monkeypatch):
     monkeypatch.setenv("WORLD_SIZE", "2")
     calls = []
     monkeypatch.setattr(bench, "oracle_runner", lambda: (lambda i: calls.append(i) or {"ids": torch.tensor([0, -1, 2])}))
+    expected_threads = bench.host_threads()            # calibrated once (cached), before set_num_threads is intercepted
     threads = []
     monkeypatch.setattr(torch, "set_num_threads", lambda n: threads.append(n))
     monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "3", "--warmup", "2", "--workload", "selftest"])
@@ -150,7 +151,7 @@ def test_reference_arm_prints_the_same_config_keys(monkeypatch):
     finally:
         bench.select_workload("720p30")
     assert calls == [0, 1, 2, 3, 4] and line["warmup"] == 2 and line["steps"] == 3
-    assert threads and threads[0] == bench.host_threads() >= 1
+    assert threads and threads[0] == expected_threads >= 1
     assert line["impl"] == "reference" and line["cpu_baseline"]["cores"] == threads[0]
     assert set(line["config"]) == set(ours) | {"tracked_boxes_per_step"}
     assert {k: line["config"][k] for k in ours} == ours

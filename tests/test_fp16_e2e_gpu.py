@@ -1,0 +1,111 @@
+"""End-to-end parity of the BENCHMARKED arithmetic (DTYPE float16: tcgen05 / mma.sync convolutions, planar tensor-core
+correlation) at the benchmarked geometry: 3x704x1280 network input, 30 tracks injected into the memory, 8 consecutive frames
+(and the 1080p / 80-track and R-50 variants of BASELINE.json configs[2] / [4]).
+
+Expected outputs are the REFERENCE's own (tests/golden/full_*.pt, produced by /root/reference through tests/golden/make_golden.py,
+which also checks that the CPU oracle reproduces them and stores the oracle's decision margins).
+
+What can be demanded of fp16 storage through ~45 layers, and what this file asserts:
+  * the scene is DECISIVE: every id-deciding comparison of the clip (detection threshold 0.05, both NMS 0.5 tests and score
+    orders, the solver's 0.4 / 0.6 thresholds -- tests/decisive.py) keeps a margin far above the fp16 deviation measured on a
+    B200.  The margins come from the fixture and are asserted first, so a scene that stops being decisive fails as such;
+  * ids: on EVERY frame the engine returns exactly the reference's id set with the reference's labels, and the same number
+    of untracked detections.  Rows are paired by id, not by position: the reference orders rows by score, and 30 tracks whose
+    scores differ by less than the fp16 deviation have no reproducible order;
+  * boxes of paired rows within BOX_BOUND px, scores within SCORE_BOUND (measured on a B200 in round 2: 1.37 px / 0.021 on
+    full_720p30; the EMM arg-max sits on a smooth maximum of a 256x256 map, so an fp16 perturbation moves it by a grid step
+    or two = 0.4-1.4 px of the search region, and the confidence read at the new position moves with it);
+  * the float32 engine on the same clip stays at the north-star tolerance (ids in the reference's ORDER, boxes <= 1e-3 px).
+"""
+import pytest
+import torch
+
+import fp16_scene as fs
+from helpers import load_golden
+from scenarios import FULL_SCENARIOS
+
+pytestmark = pytest.mark.gpu
+
+BOX_BOUND = 2.5       # px, fp16 engine vs reference, rows paired by id
+SCORE_BOUND = 0.04
+# floors of the decision margins (units: probability for *_thr / *_gap / det_thresh, IoU for *_iou); measured fp16 deviations:
+# scores <= 0.021 (tracks), <= 2e-3 (detections near 0.05); IoU of 1.4-px box noise on >= 60-px boxes <= 0.03
+MARGIN_FLOOR = {"det_thresh": 0.01, "det_nms_iou": 0.035, "det_nms_gap": 0.05, "solver_nms_iou": 0.035, "solver_nms_gap": 0.05,
+                "solver_thr": 0.05}
+
+
+def _scene(name):
+    sc = FULL_SCENARIOS[name]
+    return fs.build_scene(sc["weight_seed"], sc["clip_seed"], sc["frames"] - 1, sc["tweak"], workload=sc["workload"], tracks=sc["tracks"],
+                          n_obj=sc["n_obj"])
+
+
+def _assert_decisive(gold):
+    worst = {}
+    for t, m in enumerate(gold["margins"]):
+        for k, floor in MARGIN_FLOOR.items():
+            if k not in worst or m[k] < worst[k][0]:
+                worst[k] = (m[k], t)
+    print("decision margins (min over the clip):", {k: ("%.4f @ frame %d" % v) for k, v in worst.items()})
+    for k, floor in MARGIN_FLOOR.items():
+        assert worst[k][0] >= floor, ("the scene is no longer decisive: %s margin %.5f at frame %d is below %.3f -- recalibrate it "
+                                      "(tools/parity_probe.py --calibrate), do not loosen the parity bounds" % (k, worst[k][0], worst[k][1], floor))
+
+
+def _pair_and_check(gold_frames, got, box_bound, score_bound, ordered):
+    worst_box = worst_score = 0.0
+    for t, (g, o) in enumerate(zip(gold_frames, got)):
+        gi, oi = g["ids"], o["ids"]
+        assert gi.numel() == oi.numel(), "frame %d: %d rows vs %d" % (t, oi.numel(), gi.numel())
+        if ordered:
+            assert torch.equal(gi, oi) and torch.equal(g["labels"], o["labels"]), "frame %d: ids / labels differ" % t
+            gb, ob, gs, os_ = g["boxes"], o["boxes"], g["scores"], o["scores"]
+        else:
+            gt, ot = gi[gi >= 0], oi[oi >= 0]
+            assert sorted(gt.tolist()) == sorted(ot.tolist()), ("frame %d: track ids differ: only reference %s, only engine %s"
+                                                                % (t, sorted(set(gt.tolist()) - set(ot.tolist())),
+                                                                   sorted(set(ot.tolist()) - set(gt.tolist()))))
+            assert len(set(ot.tolist())) == ot.numel(), "frame %d: an id is assigned twice" % t
+            ga = {int(i): k for k, i in enumerate(gi.tolist()) if i >= 0}
+            oa = {int(i): k for k, i in enumerate(oi.tolist()) if i >= 0}
+            ka = torch.tensor([ga[i] for i in sorted(ga)], dtype=torch.int64)
+            kb = torch.tensor([oa[i] for i in sorted(ga)], dtype=torch.int64)
+            assert torch.equal(g["labels"][ka], o["labels"][kb]), "frame %d: labels of paired tracks differ" % t
+            gb, ob, gs, os_ = g["boxes"][ka], o["boxes"][kb], g["scores"][ka], o["scores"][kb]
+            # untracked detections (id -1): pair each reference row with the nearest engine row
+            gu, ou = (gi < 0).nonzero().squeeze(1), (oi < 0).nonzero().squeeze(1)
+            assert gu.numel() == ou.numel(), "frame %d: %d untracked detections vs %d" % (t, ou.numel(), gu.numel())
+            for r in gu.tolist():
+                d = (o["boxes"][ou] - g["boxes"][r]).abs().max(dim=1)[0]
+                j = int(torch.argmin(d))
+                assert float(d[j]) <= box_bound, "frame %d: untracked detection without a counterpart (%.2f px)" % (t, float(d[j]))
+                assert abs(float(o["scores"][ou[j]] - g["scores"][r])) <= score_bound
+        if gb.numel():
+            worst_box = max(worst_box, float((gb - ob).abs().max()))
+            worst_score = max(worst_score, float((gs - os_).abs().max()))
+            assert float((gb - ob).abs().max()) <= box_bound, "frame %d: box error %.4f px" % (t, float((gb - ob).abs().max()))
+            assert float((gs - os_).abs().max()) <= score_bound, "frame %d: score error %.5f" % (t, float((gs - os_).abs().max()))
+    return worst_box, worst_score
+
+
+@pytest.mark.parametrize("name", list(FULL_SCENARIOS))
+def test_fp16_engine_tracks_the_reference_ids_on_the_benchmark_geometry(name):
+    gold = load_golden(name)
+    _assert_decisive(gold)
+    scene = _scene(name)
+    got = fs.run_engine(scene, "float16")
+    assert len(got) == len(gold["frames"]) >= 6
+    box, score = _pair_and_check(gold["frames"], got, BOX_BOUND, SCORE_BOUND, ordered=False)
+    print("%s float16: ids exact on %d frames, max box error %.3f px, max score error %.4f" % (name, len(got), box, score))
+    # the clip API (three-stage pipeline over the same kernels) must return exactly what the per-frame calls returned
+    clip = fs.run_engine(scene, "float16", clip_api=True)
+    for t, (a, b) in enumerate(zip(got, clip)):
+        assert torch.equal(a["ids"], b["ids"]) and torch.equal(a["boxes"], b["boxes"]) and torch.equal(a["scores"], b["scores"]), t
+
+
+@pytest.mark.parametrize("name", ["full_720p30"])
+def test_fp32_engine_matches_the_reference_on_the_benchmark_geometry(name):
+    gold = load_golden(name)
+    got = fs.run_engine(_scene(name), "float32")
+    box, score = _pair_and_check(gold["frames"], got, 2e-3, 1e-3, ordered=True)
+    print("%s float32: ids in reference order on %d frames, max box error %.2e px, max score error %.2e" % (name, len(got), box, score))

@@ -106,3 +106,30 @@ def test_oracle_matches_reference_golden_with_given_detections():
         assert sorted(orc.pool.active) == g["active"] and sorted(orc.pool.dormant.keys()) == g["dormant"]
         tracked += int((g["ids"] >= 0).sum())
     assert tracked >= 10
+
+
+def test_full_size_fixture_is_decisive_and_the_oracle_reproduces_it():
+    """tests/golden/full_720p30.pt (the reference on the benchmark geometry: 3x704x1280, 30 injected tracks, tweaked head weights):
+    the stored decision margins clear the floors the GPU test demands, and the CPU oracle reproduces the reference's first frames
+    (the generator checked all of them when it wrote the fixture)."""
+    import fp16_scene as fs
+    from decisive import MarginOracle
+    from scenarios import FULL_SCENARIOS
+    from test_fp16_e2e_gpu import MARGIN_FLOOR
+    name = "full_720p30"
+    sc = FULL_SCENARIOS[name]
+    gold = load_golden(name)
+    assert len(gold["frames"]) == sc["frames"] - 1 >= 8 and len(gold["margins"]) == len(gold["frames"])
+    for t, m in enumerate(gold["margins"]):
+        for k, floor in MARGIN_FLOOR.items():
+            assert m[k] >= floor, (t, k, m[k])
+    assert all(int((f["ids"] >= 0).sum()) >= sc["tracks"] for f in gold["frames"])       # the injected tracks live on, one is born
+    scene = fs.build_scene(sc["weight_seed"], sc["clip_seed"], 2, sc["tweak"], workload=sc["workload"], tracks=sc["tracks"], n_obj=sc["n_obj"])
+    mo = MarginOracle(scene["cfg"], scene["sd"])
+    mo.inject(scene["clip"][0], scene["boxes"])
+    for t in (1, 2):
+        out, m = mo.step(scene["clip"][t])
+        ref = gold["frames"][t - 1]
+        assert torch.equal(out["ids"], ref["ids"]) and torch.equal(out["labels"], ref["labels"])
+        assert float((out["boxes"] - ref["boxes"]).abs().max()) <= 1e-3
+        assert abs(m["det_thresh"] - gold["margins"][t - 1]["det_thresh"]) <= 1e-4

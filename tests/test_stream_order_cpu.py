@@ -61,6 +61,16 @@ def test_three_stage_clip_is_schedule_independent(policy, slots, monkeypatch):
     _compare(gold, _run_sim(monkeypatch, policy, "clip", env={"SMOT_CLIP_SPLIT": "1", "SMOT_CLIP_SLOTS": slots}))
 
 
+@pytest.mark.parametrize("slots,streams", [("3", "2"), ("4", "3"), ("4", "2")])
+@pytest.mark.parametrize("policy", POLICIES, ids=str)
+def test_three_stage_clip_with_several_backbone_streams_is_schedule_independent(policy, slots, streams, monkeypatch):
+    """SMOT_CLIP_BACKBONE_STREAMS > 1: the backbone halves of consecutive frames run on alternating streams (per-slot buffers,
+    split-K scratch and preprocessing lanes) -- the results must not depend on how those streams interleave."""
+    gold = load_golden(NAME)["frames"]
+    env = {"SMOT_CLIP_SPLIT": "1", "SMOT_CLIP_SLOTS": slots, "SMOT_CLIP_BACKBONE_STREAMS": streams}
+    _compare(gold, _run_sim(monkeypatch, policy, "clip", env=env))
+
+
 def _differs(gold, got):
     try:
         _compare(gold, got)

@@ -58,10 +58,8 @@ def main():
     args = ap.parse_args()
     import fp16_scene as fs
     from decisive import MarginOracle, min_margin
-    try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except Exception:
-        pass
+    import bench
+    torch.set_num_threads(bench.host_threads())
     report = []
     for v in args.variants.split(","):
         wseed, cseed, tweak = v.split(":")
