@@ -282,8 +282,11 @@ static bool smalln_mma_ok(const smot_conv_desc* d) {
 template <typename TO>
 static int launch_smalln_mma(const SmallNArgs& a, cudaStream_t st) {
   const int mtiles = ceil_div(a.M, 16), chunks = a.KH * a.KW * (a.Cin / 32);
+  // the K slicing (= the summation order) is chosen from the pixels of ONE image, so a batched pass rounds exactly like
+  // per-image passes (Engine.pair_plan: clip results must equal frame-by-frame results bit for bit)
+  const int mtiles_img = ceil_div(a.M / (a.batch > 0 ? a.batch : 1), 16);
   int WK = 1;
-  while (WK < 8 && (long long)mtiles * WK < 1184 && chunks / (WK * 2) >= 2) WK *= 2;   // ~8 warps per SM, >= 2 chunks per slice
+  while (WK < 8 && (long long)mtiles_img * WK < 1184 && chunks / (WK * 2) >= 2) WK *= 2;   // ~8 warps per SM, >= 2 chunks per slice
   const int WM = 8 / WK;
   const unsigned grid = (unsigned)ceil_div(mtiles, WM);
   if (a.Cout <= 8)
@@ -305,7 +308,7 @@ bool conv2d_smalln_supported(const smot_conv_desc* d) {
 template <typename TI, typename TO>
 static int launch_smalln(const SmallNArgs& a, cudaStream_t st) {
   const int cout_pad = a.Cout <= 4 ? 4 : (a.Cout <= 8 ? 8 : 16);
-  if (a.M <= 1024 && ((uintptr_t)a.wt & 15) == 0 && a.K % 4 == 0) {
+  if (a.M / (a.batch > 0 ? a.batch : 1) <= 1024 && ((uintptr_t)a.wt & 15) == 0 && a.K % 4 == 0) {   // per image (see launch_smalln_mma)
     const unsigned g = (unsigned)ceil_div(a.M, 4);
     if (cout_pad == 4)
       conv_smalln_direct_kernel<TI, TO, 4><<<g, 128, 0, st>>>(a);

@@ -241,39 +241,58 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, uint32_t tmem_base,
 template <int BN>
 __device__ __forceinline__ void tc_splitk_finish(const TcArgs& a, const float* s_scale, const float* s_bias, int img, int h0, int w0,
                                                  int n0) {
-  const int tid = (int)threadIdx.x - 64;                 // the four epilogue warps
+  // all six warps take part; every thread has FIN_ITEMS float4 positions x up to 8 partials in flight before it sums
+  // (the slice is 128 x BN x 4 B per CTA read back from L2 at ~1 us latency: bytes in flight are what bounds it)
+  constexpr int FIN_ITEMS = 3, MAXS = 8;
+  const int tid = (int)threadIdx.x;
   const int rows_per = (TC_BM + a.splits - 1) / a.splits;
   const int r_lo = (int)blockIdx.z * rows_per;
   const int r_hi = min(TC_BM, r_lo + rows_per);
   constexpr int C4 = BN / 4;
+  const int n_items = (r_hi - r_lo) * C4;
   const size_t zstride = (size_t)a.num_tiles * TC_BM * a.Cout;
   const float* tile = a.partial + (size_t)blockIdx.x * TC_BM * a.Cout + n0;
-  for (int idx = tid; idx < (r_hi - r_lo) * C4; idx += 128) {
-    const int row = r_lo + idx / C4, c = (idx % C4) * 4;
-    const int oh = h0 + row / a.tile_w, ow = w0 + row % a.tile_w;
-    if (oh >= a.H || ow >= a.W) continue;
-    const float* p = tile + (size_t)row * a.Cout + c;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int z = 0; z < a.splits; ++z) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(p + (size_t)z * zstride));
-      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
-    }
-    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+  for (int base = tid; base < n_items; base += TC_THREADS * FIN_ITEMS) {
+    float4 v[FIN_ITEMS][MAXS];
+    int row[FIN_ITEMS], col[FIN_ITEMS];
+    bool ok[FIN_ITEMS];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (a.scale) v[j] = __fmul_rn(v[j], s_scale[c + j]);
-      if (a.bias) v[j] = __fadd_rn(v[j], s_bias[c + j]);
-    }
-    const size_t pix = ((size_t)img * a.H + oh) * a.W + ow;
-    if (a.res) {
-      const float4 r = ld4(a.res + pix * a.res_ld + n0 + c);
-      v[0] += r.x, v[1] += r.y, v[2] += r.z, v[3] += r.w;
-    }
-    if (a.relu) {
+    for (int it = 0; it < FIN_ITEMS; ++it) {
+      const int idx = base + it * TC_THREADS;
+      row[it] = r_lo + idx / C4, col[it] = (idx % C4) * 4;
+      const int oh = h0 + row[it] / a.tile_w, ow = w0 + row[it] % a.tile_w;
+      ok[it] = idx < n_items && oh < a.H && ow < a.W;
+      const float* p = tile + (size_t)row[it] * a.Cout + col[it];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+      for (int z = 0; z < MAXS; ++z)
+        if (ok[it] && z < a.splits) v[it][z] = __ldcg(reinterpret_cast<const float4*>(p + (size_t)z * zstride));
     }
-    st4(a.out + pix * a.out_ld + n0 + c, make_float4(v[0], v[1], v[2], v[3]));
+#pragma unroll
+    for (int it = 0; it < FIN_ITEMS; ++it) {
+      if (!ok[it]) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int z = 0; z < MAXS; ++z)
+        if (z < a.splits) acc.x += v[it][z].x, acc.y += v[it][z].y, acc.z += v[it][z].z, acc.w += v[it][z].w;   // split order
+      float o[4] = {acc.x, acc.y, acc.z, acc.w};
+      const int c = col[it];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (a.scale) o[j] = __fmul_rn(o[j], s_scale[c + j]);
+        if (a.bias) o[j] = __fadd_rn(o[j], s_bias[c + j]);
+      }
+      const int oh = h0 + row[it] / a.tile_w, ow = w0 + row[it] % a.tile_w;
+      const size_t pix = ((size_t)img * a.H + oh) * a.W + ow;
+      if (a.res) {
+        const float4 r = ld4(a.res + pix * a.res_ld + n0 + c);
+        o[0] += r.x, o[1] += r.y, o[2] += r.z, o[3] += r.w;
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+      }
+      st4(a.out + pix * a.out_ld + n0 + c, make_float4(o[0], o[1], o[2], o[3]));
+    }
   }
 }
 
@@ -373,13 +392,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     tc_epilogue<BN>(a, tmem_base, s_scale, s_bias, tmem_full, img, h0, w0, n0);
   }
   if (warp == 2 && lane == 0) TC_STAMP(4);
+  if constexpr (STAGES > 2)   // the 2-stage variants run 4 CTAs per SM on full-GPU layers: they never split K, keep their registers low
   if (a.cluster_reduce) {
     // every CTA of the tile's cluster has parked its partial: publish (gpu scope), meet, finish 128 / splits rows each
     __threadfence();
     __syncwarp();
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    if (warp >= 2) tc_splitk_finish<BN>(a, s_scale, s_bias, img, h0, w0, n0);
+    tc_splitk_finish<BN>(a, s_scale, s_bias, img, h0, w0, n0);
   }
   tc_fence_before();
   __syncthreads();
@@ -792,7 +812,11 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   int splits = 1, cluster_reduce = 0;
   {
     const int bw = d->Cout % 256 == 0 ? 256 : (d->Cout % 128 == 0 ? 128 : 64);
-    const long long cw = tiles * (d->Cout / bw);
+    // The split factor is a function of the tiles of ONE image: a batch-2 backbone pass (Engine.pair_plan) must sum every
+    // output element in exactly the order a single-frame pass does, so that clip results equal frame-by-frame results bit
+    // for bit.  (With two images the split layers then run two half-length waves instead of one: the same time.)
+    const long long tiles_img = tiles / (d->batch > 0 ? d->batch : 1);
+    const long long cw = tiles_img * (d->Cout / bw);
     if (d->workspace && cw <= 40 && all_chunks >= 16 && !getenv("SMOT_TC_NOSPLIT")) {
       int sp = (int)(148 / cw);
       if (sp > 8) sp = 8;
@@ -810,7 +834,7 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
 #define SMOT_TC_MAXC(BN_, ST_) tc_max_clusters<BN_, ST_>(cz)
           const int fit = SMOT_TC_DISPATCH(bw, stg, SMOT_TC_MAXC);
 #undef SMOT_TC_MAXC
-          if (fit >= cw) {
+          if (fit >= cw) {   // (per image: a batch of two takes two waves of clusters)
             splits = cz, BN = bw, cluster_reduce = 1;
             break;
           }

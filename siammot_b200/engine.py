@@ -79,11 +79,32 @@ class _Plan(object):
         self.backbone_done = None     # three-stage clip mode: event after part 0
         self.part_graphs = [None, None]
         self.branch = None            # while building: steps appended go to this parallel branch (None = main line)
+        self.batch = 1                # images per backbone pass (2 = a frame PAIR of a clip, see Engine.pair_plan)
+        self.bufs = []                # activation buffers in allocation order
+        self.view_of, self.view_index, self._cursor = None, 0, 0
 
-    def new(self, H, W, Cc, dtype=None, B=1):
-        t = torch.zeros((B, H, W, Cc), dtype=dtype or self.dtype, device=self.dev)
+    def new(self, H, W, Cc, dtype=None):
+        """An activation buffer (batch, H, W, Cc).  A frame plan that belongs to a pair plan (view_of) does not allocate: it
+        takes image ``view_index`` of the pair plan's buffer with the same allocation number -- both plans are built by the
+        same code, so the k-th allocation of one is the k-th of the other."""
+        dtype = dtype or self.dtype
+        if self.view_of is not None:
+            src = self.view_of.bufs[self._cursor]
+            self._cursor += 1
+            t = src[self.view_index:self.view_index + 1]
+            if tuple(t.shape) != (1, H, W, Cc) or t.dtype != dtype:
+                raise RuntimeError("pair plan / frame plan allocation order diverged: %s %s vs (1, %d, %d, %d) %s"
+                                   % (tuple(t.shape), t.dtype, H, W, Cc, dtype))
+        else:
+            t = torch.zeros((self.batch, H, W, Cc), dtype=dtype, device=self.dev)
+        self.bufs.append(t)
         self.keep.append(t)
         return t
+
+    def per_image(self, fn, make_args, tag):
+        """Kernels without a batch argument run once per image of the batch (make_args(i) builds the call for image i)."""
+        for i in range(self.batch):
+            self.call(fn, make_args(i), tag)
 
     def conv(self, x, name, out, residual=None, stride=1, pad=0, relu=False):
         w, scale, bias = self.e.weights[name]
@@ -112,7 +133,7 @@ class _Plan(object):
         for i, (_fn, _args, tag, _branch) in enumerate(self.steps):
             if tag == "rpn_select":
                 return i
-        raise RuntimeError("static plan without an rpn_select step")
+        return len(self.steps)        # a backbone-only (pair) plan: everything is part 0
 
     def run_eager(self, lo=0, hi=None):
         main = torch.cuda.current_stream(self.dev)
@@ -261,8 +282,12 @@ class _TrackPlan(object):
                                                              S, T.POOLER_SAMPLING_RATIO, ops._ptr(self.srp), _lib.XCORR_ROW_PITCH,
                                                              _lib.XCORR_PLANE, dc), "sr_roi_align"))
                 self.xcorr_slot = len(self.steps)
-                self.steps.append((L.smot_xcorr_planar, (ops._ptr(self.srp), ops._ptr(self.tmpl), ops._ptr(self.resp), n, Cc), "xcorr"))
-                self.xcorr_kernel = "xcorr_planar_kernel (smot_xcorr_planar)"
+                self.steps.append((L.smot_xcorr_planar_mode, (ops._ptr(self.srp), ops._ptr(self.tmpl), ops._ptr(self.resp), n, Cc,
+                                                              eng.xcorr_planar_mode), "xcorr"))
+                self.xcorr_kernel = "xcorr_planar_kernel<%d> (smot_xcorr_planar_mode)" % eng.xcorr_planar_mode
+                self.xcorr_note = ("fp16 banded-Toeplitz mma.sync form on channel-planar windows staged with cp.async.bulk; mode 1 = "
+                                   "structurally-zero MMA halves dropped (45 instead of 60 k16-MMAs per plane); bound by shared-memory "
+                                   "wavefronts (ldmatrix + B-operand loads, ~150 per plane) and per-launch fixed cost at 3840 planes")
             else:
                 self.steps.append((L.smot_roi_align, (C.byref(pyr_pad), ops._ptr(self.sr), ops._ptr(self.boxes), None, n, Cc, S,
                                                       T.POOLER_SAMPLING_RATIO, ops._ptr(self.srf), dc), "sr_roi_align"))
@@ -491,6 +516,8 @@ class Engine(object):
         # forward_clip (three-stage): number of streams the backbone halves of consecutive frames alternate over (needs
         # SMOT_CLIP_SLOTS >= streams + 1 plan copies to matter)
         self.clip_backbone_streams = max(1, min(3, int(os.environ.get("SMOT_CLIP_BACKBONE_STREAMS", "1"))))
+        # forward_clip (three-stage): backbone half over frame pairs (Engine.pair_plan); SMOT_CLIP_PAIRS=0 = one frame per pass
+        self.clip_pairs = os.environ.get("SMOT_CLIP_PAIRS", "1") == "1"
         self._branch_streams = []
         self._track_plans = {}
         self._arenas = {}
@@ -500,6 +527,7 @@ class Engine(object):
         # channel-planar search-window exchange (default since round 2: bit-equal windows, 1.5-2x faster correlation on the
         # driver's B200); 0 = NHWC windows + xcorr_mma_kernel, 1 = planar with the untrimmed MMA phase, 2 = trimmed (libsmot reads it)
         self.xcorr_planar = os.environ.get("SMOT_XCORR_PLANAR", "2") in ("1", "2")
+        self.xcorr_planar_mode = 0 if os.environ.get("SMOT_XCORR_PLANAR", "2") == "1" else 1   # the engine passes it per call
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
         self.time_kernels = False  # also bracket single kernels of the track stage (forces its eager path)
 
@@ -787,7 +815,8 @@ class Engine(object):
                 xs = x
                 if stride == 2:   # the even pixels, once, for every strided 1x1 of the block
                     xs = P.new(ho, wo, cin)
-                    P.call(L.smot_subsample2, (ops._ptr(x), ops._ptr(xs), h, w, cin, ops._nhwc(x)[4], cin, dc), "sub2:" + name)
+                    P.per_image(L.smot_subsample2, lambda b, x=x, xs=xs, h=h, w=w, cin=cin: (ops._ptr(x[b:b + 1]), ops._ptr(xs[b:b + 1]), h, w,
+                                                                                              cin, ops._nhwc(x)[4], cin, dc), "sub2:" + name)
                 identity = x
                 if cin != cout:
                     identity = P.conv(xs, name + ".downsample.0", P.new(ho, wo, cout))
@@ -809,21 +838,69 @@ class Engine(object):
         key = (H, W, slot)
         if key in self.plans:
             return self.plans[key]
+        self._check_plan_size(H, W)
+        P = _Plan(self, H, W)
+        P.slot = slot
+        P.ws = self.backbone_ws(slot)
+        self._build_static(P)
+        self.plans[key] = P
+        return P
+
+    def pair_plan(self, H, W, pslot=0):
+        """Backbone plan over a PAIR of clip frames (batch 2) + the two per-frame plans that read its halves.
+
+        Below level 2 every DLA / FPN / RPN layer has at most 110..120 CTAs for 148 SMs and costs ~10 us whatever its size
+        (launch, barrier + TMEM setup, TMA round trips, epilogue -- profiles/): run over two frames at once those layers cost
+        the same and do twice the work, only the layers that already fill the GPU (stem, level 0-2, P2) double.
+        forward_clip's three-stage mode therefore runs the backbone half of frames (2k, 2k+1) as ONE batch-2 pass; the
+        detection tail and the track stage stay per frame and read image i of the batched buffers through the frame plans
+        ``pair.frames[i]`` (same launch lists as a standalone plan, activation buffers = views).  Results are identical: every
+        kernel treats the batch images independently."""
+        key = (H, W, "pair", pslot)
+        if key in self.plans:
+            return self.plans[key]
+        self._check_plan_size(H, W)
+        PP = _Plan(self, H, W)
+        PP.batch = 2
+        PP.slot = ("pair", pslot)
+        PP.ws = self.conv_ws
+        self._build_static(PP, backbone_only=True)
+        PP.frames = []
+        for i in range(PP.batch):
+            P = _Plan(self, H, W)
+            P.view_of, P.view_index = PP, i
+            P.slot = ("pair", pslot, i)
+            P.ws = self.conv_ws
+            self._build_static(P)
+            if P._cursor != len(PP.bufs):
+                raise RuntimeError("frame plan used %d of the pair plan's %d buffers" % (P._cursor, len(PP.bufs)))
+            P.pair = PP
+            PP.frames.append(P)
+        self.plans[key] = PP
+        return PP
+
+    def _check_plan_size(self, H, W):
         if not self.weights:
             raise RuntimeError("Engine.load_state_dict() must be called before the first frame")
         if H % 32 or W % 32:
             raise ValueError("DLA-34 needs an input divisible by 32 (got %dx%d); the reference resizes to such a size "
                              "(DATALOADER.SIZE_DIVISIBILITY 32) and fails in dla.py:54 otherwise" % (H, W))
+
+    def _build_static(self, P, backbone_only=False):
+        """Fill plan P with the launches of the frame-independent stage (P.batch images per pass); backbone_only: stop after
+        the RPN heads (part 0 of the plan)."""
+        H, W = P.H, P.W
         cfg, dev, dt = self.cfg, self.device, self.dtype
-        P = _Plan(self, H, W)
-        P.slot = slot
-        P.ws = self.backbone_ws(slot)
         L = lib()
         dc = _lib.dtype_code(dt)
-        # ---- input
-        P.img_in = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+        # ---- input: (batch, 3, H, W) fp32; a frame plan of a pair reads / is fed through its image of the pair's buffer
+        if P.view_of is not None:
+            P.img_batch = P.view_of.img_batch[P.view_index:P.view_index + 1]
+        else:
+            P.img_batch = torch.zeros((P.batch, 3, H, W), dtype=torch.float32, device=dev)
+        P.img_in = P.img_batch[0]
         img = P.new(H, W, 4)
-        P.call(L.smot_image_to_nhwc, (ops._ptr(P.img_in), ops._ptr(img), 3, H, W, 4, dc), "image_to_nhwc")
+        P.per_image(L.smot_image_to_nhwc, lambda i: (ops._ptr(P.img_batch[i]), ops._ptr(img[i:i + 1]), 3, H, W, 4, dc), "image_to_nhwc")
         if self.resnet:
             body = self._resnet_body(P, img)
         elif cfg.MODEL.BACKBONE.CONV_BODY != "DLA-34-FPN":
@@ -853,8 +930,9 @@ class Engine(object):
         P.join()
         for i in range(3, 0, -1):                   # top-down pathway: sequential
             last, cur = inner[i], inner[i - 1]
-            P.call(L.smot_upsample_add, (ops._ptr(last), last.shape[1], last.shape[2], Cc, ops._ptr(cur),
-                                         cur.shape[1], cur.shape[2], Cc, Cc, dc), "upsample_add%d" % (i + 1))
+            P.per_image(L.smot_upsample_add, lambda b, last=last, cur=cur: (ops._ptr(last[b:b + 1]), last.shape[1], last.shape[2], Cc,
+                                                                              ops._ptr(cur[b:b + 1]), cur.shape[1], cur.shape[2], Cc, Cc, dc),
+                        "upsample_add%d" % (i + 1))
 
         def rpn_head(l):
             f = feats[l]
@@ -870,10 +948,15 @@ class Engine(object):
             if l == 3:                              # P6 = stride-2 subsample of P5 (fpn_patch.py:57-59), same branch
                 p5 = feats[3]
                 feats[4] = P.new((p5.shape[1] - 1) // 2 + 1, (p5.shape[2] - 1) // 2 + 1, Cc)
-                P.call(L.smot_subsample2, (ops._ptr(p5), ops._ptr(feats[4]), p5.shape[1], p5.shape[2], Cc, Cc, Cc, dc), "p6")
+                P.per_image(L.smot_subsample2, lambda b, p5=p5: (ops._ptr(p5[b:b + 1]), ops._ptr(feats[4][b:b + 1]), p5.shape[1],
+                                                                  p5.shape[2], Cc, Cc, Cc, dc), "p6")
                 rpn_head(4)
         P.join()
         P.feats = feats
+        if backbone_only:
+            return
+        if P.batch != 1:
+            raise RuntimeError("the detection tail runs per frame: build it on a frame plan (Engine.pair_plan(...).frames[i])")
         # ---- RPN selection
         P.rpn_levels = ops.rpn_levels(heads, R.ANCHOR_STRIDE, self.cells)
         P.keep.append(P.rpn_levels)
@@ -908,8 +991,6 @@ class Engine(object):
                                      nprop, H_.SCORE_THRESH, H_.NMS, nprop, j, None, ops._ptr(P.det_boxes),
                                      ops._ptr(P.det_scores), ops._ptr(P.det_labels), ops._ptr(P.det_count), ops._ptr(nws),
                                      nws.numel()), "det_nms%d" % j)
-        self.plans[key] = P
-        return P
 
     def _fill_dets(self, P):
         P.det_scores.fill_(-1.0)
@@ -1005,6 +1086,38 @@ class Engine(object):
             P.run() if part is None else P.run_part(part)
         return P
 
+    def pair_ok(self, frames):
+        """Frame pairs need kernels that take a batch (everything but the DCN gather) and frames of one size and kind."""
+        if any(self.cfg.MODEL.DLA.STAGE_WITH_DCN) and not self.resnet and self.cfg.MODEL.BACKBONE.CONV_BODY != "DLA-34-FPN":
+            return False
+        f0 = frames[0]
+        raw = not torch.is_tensor(f0) or f0.dtype == torch.uint8
+        shape = tuple(f0.shape)
+        for f in frames:
+            if tuple(f.shape) != shape or (not torch.is_tensor(f) or f.dtype == torch.uint8) != raw:
+                return False
+        return raw or len(shape) == 3 or shape[0] == 1
+
+    def run_backbone_pair(self, f0, f1, pslot):
+        """Stage two clip frames (normalised (3,H,W) tensors or decoded uint8 frames) and enqueue ONE batch-2 backbone / FPN /
+        RPN-head pass on the current stream.  Returns the pair plan; its .frames[i] are the per-frame plans."""
+        raw = not torch.is_tensor(f0) or f0.dtype == torch.uint8
+        if raw:
+            pre = self.preprocessor()
+            H, W = pre.output_size(f0.shape[0], f0.shape[1])
+        else:
+            H, W = f0.shape[-2], f0.shape[-1]
+        PP = self.pair_plan(H, W, pslot)
+        for i, f in enumerate((f0, f1)):
+            if raw:
+                with self.timed("preprocess"):
+                    pre.into(f, PP.img_batch[i], 2 * pslot + i)
+            else:
+                PP.img_batch[i].copy_(f[0] if f.dim() == 4 else f, non_blocking=True)
+        with self.timed("static"):
+            PP.run_part(0)
+        return PP
+
     def run_tail(self, P):
         """The detection tail (proposal selection, box head, per-class NMS) of a plan whose part 0 has been enqueued."""
         with self.timed("static_tail"):
@@ -1054,7 +1167,7 @@ class Engine(object):
                 srp = ops.roi_align_planar(P.feats, mem_sr, T.POOLER_SCALES, self.s_res, T.POOLER_SAMPLING_RATIO,
                                            level_boxes=mem_boxes, pads=self.pads)
             with self.timed("xcorr"):
-                resp = ops.xcorr_planar(srp, mem_feat.contiguous())
+                resp = ops.xcorr_planar(srp, mem_feat.contiguous(), mma_mode=self.xcorr_planar_mode)
         else:
             with self.timed("sr_roi_align"):
                 srf = ops.roi_align(P.feats, mem_sr, T.POOLER_SCALES, self.s_res, T.POOLER_SAMPLING_RATIO,

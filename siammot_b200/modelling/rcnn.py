@@ -614,6 +614,8 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detect
     and per-slot buffers; every cross-stream edge is an event recorded BEFORE the wait on it is enqueued.
     Results are identical to frame-by-frame calls."""
     n_frames = len(frames)
+    if eng.clip_pairs and n_frames >= 2 and eng.pair_ok(frames):
+        return _forward_clip_pairs(self, eng, frames, before_frame, given_detections)
     K = eng.clip_slots
     results = []
     cur = torch.cuda.current_stream(eng.device)
@@ -673,6 +675,92 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detect
         cur.wait_stream(sD)
         for sB in extra:
             cur.wait_stream(sB)
+    return results
+
+
+def _forward_clip_pairs(self, eng, frames, before_frame=None, given_detections=None):
+    """The three-stage clip pipeline with the backbone half run over frame PAIRS (Engine.pair_plan: one batch-2 pass for
+    frames 2k, 2k+1 -- the layers below level 2 do not fill 148 SMs with one frame and cost the same for two).
+
+      stream A   B(2k, 2k+1): input copies / test transform of both frames, ONE batch-2 backbone + FPN + RPN-head pass
+      stream D   D(t): proposal selection, box head, per-class NMS of frame t (its image of the batched buffers)
+      caller's   T(t): track stage, host solver H(t), next-frame memory
+
+    Dependencies: D(t) after B(pair of t) and D(t-1) (stream order); T(t) after D(t) and H(t-1); B(pair p + 2) reuses the
+    buffers of pair p, i.e. runs after T / H of its second frame (two pair slots).  B(p+1) is enqueued while frame 2p is
+    in its track stage, so D(2p+1), T(2p), T(2p+1) run under it.  An odd last frame takes the single-frame plan.
+    Results are identical to frame-by-frame calls (every kernel treats the images of a batch independently)."""
+    n_frames = len(frames)
+    results = []
+    cur = torch.cuda.current_stream(eng.device)
+    sA, sD = eng.side_stream(), eng.tail_stream()
+    sA.wait_stream(cur)
+    sD.wait_stream(cur)
+    KP = 2                          # pair slots
+    slot_free = [None] * KP         # event: every reader of the pair slot's buffers is enqueued-complete
+    single_free = None
+    plans, launched = {}, set()
+
+    def backbone(p):
+        """Backbone half of pair p (frames 2p, 2p+1), or of the odd last frame alone."""
+        t0 = 2 * p
+        launched.add(p)
+        with torch.cuda.stream(sA):
+            if t0 + 1 < n_frames:
+                if slot_free[p % KP] is not None:
+                    sA.wait_event(slot_free[p % KP])
+                PP = eng.run_backbone_pair(frames[t0], frames[t0 + 1], p % KP)
+                if PP.backbone_done is None:
+                    PP.backbone_done = torch.cuda.Event()
+                PP.backbone_done.record(sA)
+                plans[t0], plans[t0 + 1] = PP.frames[0], PP.frames[1]
+                PP.frames[0].backbone_done = PP.frames[1].backbone_done = PP.backbone_done
+            else:
+                if single_free is not None:
+                    sA.wait_event(single_free)
+                P = (eng.run_static_raw(frames[t0], 0, part=0) if _is_raw_frame(frames[t0]) else eng.run_static(frames[t0], 0, part=0))
+                if P.backbone_done is None:
+                    P.backbone_done = torch.cuda.Event()
+                P.backbone_done.record(sA)
+                plans[t0] = P
+
+    def detect(t):
+        P = plans[t]
+        with torch.cuda.stream(sD):
+            sD.wait_event(P.backbone_done)
+            eng.run_tail(P)
+            if P.static_done is None:
+                P.static_done = torch.cuda.Event()
+            P.static_done.record(sD)
+
+    n_pairs = (n_frames + 1) // 2
+    with torch.no_grad():
+        backbone(0)
+        detect(0)
+        for t in range(n_frames):
+            P = plans.pop(t)
+            if before_frame is not None:
+                before_frame(t)
+            cur.wait_event(P.static_done)          # D(t) complete (hence B of its pair)
+            pending = self.roi_heads.launch_frame(P, self._mem, given_detections[t] if given_detections is not None else None)
+            p = t // 2
+            if t % 2 == 0 and p + 1 < n_pairs and (p + 1) not in launched:
+                backbone(p + 1)                    # its slot held pair p-1, whose last reader finished in iteration t-1
+            if t + 1 < n_frames:
+                detect(t + 1)
+            result, mem = self.roi_heads.finish_frame(pending, next_P=plans.get(t + 1))
+            if t % 2 == 1 or t + 1 == n_frames:    # the pair's (or the single plan's) buffers are free for the next user
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                if getattr(P, "pair", None) is not None:
+                    slot_free[p % KP] = ev
+                else:
+                    single_free = ev
+            self._mem = mem
+            self.track_memory = mem
+            results.append(result)
+        cur.wait_stream(sA)
+        cur.wait_stream(sD)
     return results
 
 

@@ -288,24 +288,25 @@ def test_xcorr_planar_equals_xcorr(n, C):
     xp.view(n, C, -1)[:, :, :30 * _lib.XCORR_ROW_PITCH].view(n, C, 30, _lib.XCORR_ROW_PITCH)[..., 32:] = 7.0   # nor columns 32..39
     ref = ops.xcorr(dx, dk)
     for _ in range(3):                                   # back-to-back launches chain through PDL
-        got = ops.xcorr_planar(xp, dk)
+        got = ops.xcorr_planar(xp, dk, mma_mode=0)       # the untrimmed MMA phase: xcorr_mma_kernel's, instruction for instruction
     torch.cuda.synchronize()
     assert torch.equal(got, ref)
     assert rel_err(nchw(got), orc.xcorr_depthwise(x, k)) <= tol(dt)
-    # trimmed MMA phase (SMOT_XCORR_PLANAR=2 / mma_mode 1): another accumulation order -> the oracle bar, not bit equality
+    # trimmed MMA phase (the default: SMOT_XCORR_PLANAR=2 / mma_mode 1): another accumulation order -> the oracle bar, not bit equality
     trim = ops.xcorr_planar(xp, dk, mma_mode=1)
     assert rel_err(nchw(trim), orc.xcorr_depthwise(x, k)) <= tol(dt)
     assert rel_err(trim.float(), ref.float()) <= 2e-3
 
 
 def test_engine_planar_switch_changes_nothing(monkeypatch):
-    """fp16 engine with SMOT_XCORR_PLANAR=1: same boxes / scores / ids as the default exchange, frame by frame and as a clip."""
+    """fp16 engine with the planar exchange and the untrimmed MMA phase (SMOT_XCORR_PLANAR=1): same boxes / scores / ids as the
+    NHWC exchange (SMOT_XCORR_PLANAR=0), frame by frame and as a clip; the default (=2, trimmed MMA phase) tracks the same ids."""
     from test_e2e_gpu import build_model
 
     def run(flag, clip_api):
         monkeypatch.setenv("SMOT_XCORR_PLANAR", flag)
         cfg, model, clip = build_model("emm_256x384", "float16")
-        assert model.engine().xcorr_planar_ok() == (flag == "1")
+        assert model.engine().xcorr_planar_ok() == (flag != "0") and model.engine().xcorr_planar_mode == (0 if flag == "1" else 1)
         model.reset_siammot_status()
         frames = [f.to("cuda") for f in clip]
         return model.forward_clip(frames) if clip_api else [model(f)[0] for f in frames]
@@ -317,3 +318,6 @@ def test_engine_planar_switch_changes_nothing(monkeypatch):
         for a, b in zip(ref, got):
             assert torch.equal(a.bbox, b.bbox) and torch.equal(a.get_field("scores"), b.get_field("scores"))
             assert torch.equal(a.get_field("ids"), b.get_field("ids"))
+    got = run("2", False)                                    # the default: fp32 accumulation in another order (fp16 ulp of the response)
+    for a, b in zip(ref[:2], got[:2]):
+        assert a.bbox.shape == b.bbox.shape and float((a.bbox - b.bbox).abs().max()) <= 0.5

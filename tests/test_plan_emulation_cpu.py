@@ -52,7 +52,7 @@ def test_concurrent_stages_use_disjoint_split_k_scratch(monkeypatch):
     backbone, tail = scratch(P.steps[:k]), scratch(P.steps[k:])
     tp = eng.track_plan(P, 5)
     track = scratch(tp.steps)
-    allowed_backbone = {eng.conv_ws.data_ptr()} | {w.data_ptr() for w in eng._branch_ws}
+    allowed_backbone = {eng.conv_ws.data_ptr()} | {w.data_ptr() for w in eng._branch_ws.values()}
     assert backbone <= allowed_backbone and len(backbone) >= 2      # main line + parallel branches
     assert tail == {eng.conv_ws_det.data_ptr()}
     assert track == {eng.conv_ws_track.data_ptr()}
@@ -65,6 +65,12 @@ def test_concurrent_stages_use_disjoint_split_k_scratch(monkeypatch):
     assert all(len(v) == 1 for v in per_branch.values())
     assert len({next(iter(v)) for v in per_branch.values()}) == len(per_branch)
     assert eng.conv_ws.data_ptr() not in {next(iter(v)) for v in per_branch.values()}
+    # a frame PAIR's backbone pass (batch 2) and the detection tails of its two frame plans keep the same separation
+    PP = eng.pair_plan(clip[0].shape[1], clip[0].shape[2], 0)
+    assert scratch(PP.steps) <= allowed_backbone and PP.split_index() == len(PP.steps)
+    for F in PP.frames:
+        assert scratch(F.steps[F.split_index():]) == {eng.conv_ws_det.data_ptr()}
+        assert all(a.data_ptr() == b[F.view_index:F.view_index + 1].data_ptr() for a, b in zip(F.bufs, PP.bufs))
 
 
 DLA_FAMILY = {"DLA-46-C-FPN": (64, 64, 128, 256), "DLA-60-FPN": (128, 256, 512, 1024), "DLA-102-FPN": (128, 256, 512, 1024),
