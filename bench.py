@@ -337,6 +337,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     value_ms = []
+    h.eng.host_timers = {}
+    t_loop0 = time.perf_counter()
     for rep in range(REPEATS):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -345,6 +347,7 @@ def run_ours(args):
         e1.record()
         barrier()
         value_ms.append(e0.elapsed_time(e1))
+    host_t, h.eng.host_timers = h.eng.host_timers, None
     ntrk = sum(int((r.get_field("ids") >= 0).sum()) for r in results)
     r = results[-1]
     ms = median(value_ms)
@@ -500,7 +503,12 @@ def run_ours(args):
                      "flops_per_launch": N_TRACKS * h.eng.C * 2 * (S_ - T_ + 1) ** 2 * T_ * T_,
                      "note": getattr(tp, "xcorr_note", "")},
         "stage_ms": {"static_graph": round(static_ms, 4), "preprocess_incl_h2d": round(prep_ms, 4),
-                     "note": "CUDA-event brackets in the per-frame e2e arm (single stream)"},
+                     "note": "CUDA-event brackets in the per-frame e2e arm (single stream)",
+                     "host_per_frame_ms": {k: round(v / max(host_t.get("frames", 1), 1) * 1e3, 4) for k, v in host_t.items() if k != "frames"},
+                     "host_note": "wall clock inside finish_frame during the `value` arm: track_wait = blocking on the track "
+                                  "stage's result block (its GPU latency under the overlapped backbone), solver = unpack + id "
+                                  "resolution, next_memory = staging + template pooling launch, boxlist = result object; their "
+                                  "sum + the launch code is the sequential chain of a video"},
         "clocks": clocks,
     }
     if per_rank is not None:

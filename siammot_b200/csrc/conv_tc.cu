@@ -808,7 +808,11 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   else if (d->Cout % 128 == 0 && tiles * (d->Cout / 128) >= min_ctas) BN = 128;
   const char* force = getenv("SMOT_TC_STAGES");  // developer override: ring depth
   const int fs = force ? atoi(force) : 0;
-  static const bool cluster_ok = !(getenv("SMOT_TC_CLUSTER") && atoi(getenv("SMOT_TC_CLUSTER")) == 0);   // developer A/B switch
+  // developer switch SMOT_TC_CLUSTER=1: the split CTAs of a tile form a cluster and finish the tile themselves (tc_splitk_finish).
+  // Measured on B200 (profiles/bench_r02c_*): correct (bit-identical to the reduce kernel) but SLOWER -- 18.7-25.9 us per
+  // level-4 layer against 13.7 us + a 6 us reduce launch that overlaps the next layer's prologue through PDL; the serial
+  // store -> fence -> cluster barrier -> 128 KB read-back of one CTA cannot match a reduce grid that spreads over all SMs.
+  static const bool cluster_ok = getenv("SMOT_TC_CLUSTER") && atoi(getenv("SMOT_TC_CLUSTER")) == 1;
   int splits = 1, cluster_reduce = 0;
   {
     const int bw = d->Cout % 256 == 0 ? 256 : (d->Cout % 128 == 0 ? 128 : 64);

@@ -8,6 +8,8 @@
 //   * TrackUtils.pad_feature (track_utils.py:87-107), 170 MB of zero-padded copies per frame at 720p --
 //     emulated: coordinates are evaluated in the padded frame exactly as the reference does, and
 //     corner reads that fall into the padding return 0.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace smot {
@@ -184,6 +186,147 @@ __global__ void __launch_bounds__(256) roi_align_planar_kernel(const RoiArgs a, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row-wise ROIAlign with separable sample tables (round 2).
+//
+// ncu on the kernels above (profiles/ncu_roi_align_planar_r02.txt): 27 M warp instructions for 27 000 bins, issue slots 75 %
+// busy, L1 hit rate 80 %, DRAM 2 % -- they are INSTRUCTION bound: every warp re-derives the level (log2 / sqrt / IEEE
+// division), the bin geometry (4 divisions) and, per sample, two IEEE divisions plus ~40 instructions of clamping and
+// bounds logic, ~1000 instructions per bin of which ~150 are loads and multiply-adds.
+// The sample coordinates are separable (x depends on (pw, ix) only, y on (ph, iy) only), as are the clamps, the corner
+// indices, the interpolation weights and the "inside the padded map / inside the real map" predicates.  So: grid (bin row,
+// roi); the CTA derives the roi's geometry once, thread j fills entry j of a shared-memory table of the row's res * gw x-samples
+// (and the first gh threads the y-samples) with EXACTLY the operations of roi_align_kernel; the warps then walk the bins
+// reading two table entries per sample: what is left per sample is 4 weight products, 4 vector loads and the 16
+// multiply-add pairs, in the same order and rounding as before -- the outputs are bit-identical to roi_align_kernel's
+// (tests/test_kernels_on_cpu.py runs both sources on the host; tests/test_ops_gpu.py on the GPU).
+// PLANAR: results leave through the [C][res] shared-memory tile as one contiguous run per channel (see above); otherwise
+// NHWC rows (roi, ph, pw, C).
+// ---------------------------------------------------------------------------------------------
+constexpr int RAR_MAX_SAMPLES = 512;   // res * gw entries per row
+
+struct RarSample {   // one axis of one sample
+  int lo, hi;        // corner indices in the REAL (unpadded) map
+  float l, h;        // interpolation weights (l towards hi, h = 1 - l towards lo)
+  int flags;         // bit 0: sample inside the padded map (else skipped); bit 1 / 2: lo / hi inside the real map
+};
+
+__device__ __forceinline__ RarSample rar_sample(float v, int size_padded, int size_real, int pad) {
+  RarSample s;
+  s.flags = (v < -1.f || v > (float)size_padded) ? 0 : 1;
+  float vv = v <= 0.f ? 0.f : v;
+  int lo = (int)vv, hi;
+  if (lo >= size_padded - 1) { hi = lo = size_padded - 1; vv = (float)lo; } else hi = lo + 1;
+  s.l = vv - (float)lo;
+  s.h = 1.f - s.l;
+  s.lo = lo - pad, s.hi = hi - pad;
+  if (s.lo >= 0 && s.lo < size_real) s.flags |= 2;
+  if (s.hi >= 0 && s.hi < size_real) s.flags |= 4;
+  return s;
+}
+
+template <typename T, bool PLANAR>
+__global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T* __restrict__ out, int row_pitch, int plane_pitch) {
+  extern __shared__ __align__(16) unsigned char rar_raw[];
+  __shared__ RarSample xs[RAR_MAX_SAMPLES];
+  __shared__ RarSample ys[16];
+  T* tile = reinterpret_cast<T*>(rar_raw);  // PLANAR only: [channels][RAP_TP]
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ph = blockIdx.x, r = blockIdx.y;
+  const int n = a.count ? min(*a.count, a.max_rois) : a.max_rois;
+  if (r >= n) {   // rows past the count are zero
+    if (PLANAR) {
+      T* dst = out + (size_t)r * a.channels * plane_pitch + (size_t)ph * row_pitch;
+      for (int i = threadIdx.x; i < a.channels * a.res; i += blockDim.x) {
+        const int c = i / a.res, pw = i - c * a.res;
+        dst[(size_t)c * plane_pitch + pw] = from_f<T>(0.f);
+      }
+    } else {
+      T* dst = out + ((size_t)r * a.res + ph) * a.res * a.channels;
+      for (int i = threadIdx.x * 4; i < a.res * a.channels; i += blockDim.x * 4) st4(dst + i, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    return;
+  }
+  // ---- the roi's geometry: the operations of roi_align_kernel, once per thread instead of once per sample
+  const float* lb = (a.level_boxes ? a.level_boxes : a.rois) + 4 * r;
+  const float area = (lb[2] - lb[0] + 1.f) * (lb[3] - lb[1] + 1.f);
+  float lv = floorf(4.f + log2f(__fdiv_rn(__fsqrt_rn(area), 224.f) + 1e-6f));
+  const float kmin = (float)a.pyr.k_min, kmax = (float)(a.pyr.k_min + a.pyr.num_levels - 1);
+  lv = fminf(fmaxf(lv, kmin), kmax);
+  const int l = (int)lv - a.pyr.k_min;
+  const T* __restrict__ feat = reinterpret_cast<const T*>(a.pyr.feat[l]);
+  const int H = a.pyr.H[l], W = a.pyr.W[l], ld = a.pyr.ld[l], pad = a.pyr.pad[l];
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const float sc = a.pyr.scale[l];
+  const float* roi = a.rois + 4 * r;
+  const float x1 = roi[0] * sc, y1 = roi[1] * sc, x2 = roi[2] * sc, y2 = roi[3] * sc;
+  const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
+  const float bin_h = __fdiv_rn(rh, (float)a.res), bin_w = __fdiv_rn(rw, (float)a.res);
+  const int gh = a.sampling, gw = a.sampling;    // the host routes adaptive sampling (<= 0) to roi_align_kernel
+  const float cnt = (float)(gh * gw);
+  for (int j = threadIdx.x; j < a.res * gw; j += blockDim.x) {
+    const int pw = j / gw, ix = j - pw * gw;
+    const float x = x1 + (float)pw * bin_w + __fdiv_rn(((float)ix + .5f) * bin_w, (float)gw);
+    xs[j] = rar_sample(x, Wp, W, pad);
+  }
+  if ((int)threadIdx.x < gh) {
+    const float y = y1 + (float)ph * bin_h + __fdiv_rn(((float)threadIdx.x + .5f) * bin_h, (float)gh);
+    ys[threadIdx.x] = rar_sample(y, Hp, H, pad);
+  }
+  __syncthreads();
+  for (int pw = wid; pw < a.res; pw += 8) {
+    for (int c = lane * 4; c < a.channels; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int iy = 0; iy < gh; ++iy) {
+        const RarSample sy = ys[iy];
+        for (int ix = 0; ix < gw; ++ix) {
+          const RarSample sx = xs[pw * gw + ix];
+          if (!(sy.flags & sx.flags & 1)) continue;
+          const float w1 = sy.h * sx.h, w2 = sy.h * sx.l, w3 = sy.l * sx.h, w4 = sy.l * sx.l;
+          const bool oyl = sy.flags & 2, oyh = sy.flags & 4, oxl = sx.flags & 2, oxh = sx.flags & 4;
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 v1 = (oyl && oxl) ? ld4(feat + ((size_t)sy.lo * W + sx.lo) * ld + c) : z;
+          float4 v2 = (oyl && oxh) ? ld4(feat + ((size_t)sy.lo * W + sx.hi) * ld + c) : z;
+          float4 v3 = (oyh && oxl) ? ld4(feat + ((size_t)sy.hi * W + sx.lo) * ld + c) : z;
+          float4 v4 = (oyh && oxh) ? ld4(feat + ((size_t)sy.hi * W + sx.hi) * ld + c) : z;
+          acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+          acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+          acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+          acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+        }
+      }
+      acc.x = __fdiv_rn(acc.x, cnt), acc.y = __fdiv_rn(acc.y, cnt), acc.z = __fdiv_rn(acc.z, cnt), acc.w = __fdiv_rn(acc.w, cnt);
+      if (PLANAR) {
+        T* tp = tile + (size_t)c * RAP_TP + pw;
+        tp[0] = from_f<T>(acc.x);
+        tp[RAP_TP] = from_f<T>(acc.y);
+        tp[2 * RAP_TP] = from_f<T>(acc.z);
+        tp[3 * RAP_TP] = from_f<T>(acc.w);
+      } else {
+        st4(out + (((size_t)r * a.res + ph) * a.res + pw) * a.channels + c, acc);
+      }
+    }
+  }
+  if (PLANAR) {
+    __syncthreads();
+    T* dst = out + (size_t)r * a.channels * plane_pitch + (size_t)ph * row_pitch;
+    for (int i = threadIdx.x; i < a.channels * a.res; i += blockDim.x) {
+      const int c = i / a.res, pw = i - c * a.res;
+      dst[(size_t)c * plane_pitch + pw] = tile[(size_t)c * RAP_TP + pw];
+    }
+  }
+}
+
+// developer switch SMOT_ROI_ROWS=0: the one-warp-per-bin kernels (A/B; results are bit-identical)
+static bool roi_rows_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SMOT_ROI_ROWS");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 }  // namespace smot
 
 using namespace smot;
@@ -206,14 +349,25 @@ extern "C" int smot_roi_align_planar(const smot_pyramid* pyr, const float* rois,
   a.max_rois = max_rois, a.channels = channels, a.res = res, a.sampling = sampling_ratio;
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid((unsigned)res, (unsigned)max_rois);
+  const bool rows = roi_rows_enabled() && sampling_ratio > 0 && sampling_ratio <= 16 && res * sampling_ratio <= RAR_MAX_SAMPLES;
   if (dtype == SMOT_F32) {
     const size_t smem = (size_t)channels * RAP_TP * sizeof(float);
-    SMOT_ENSURE_SMEM(roi_align_planar_kernel<float>, smem, "smot_roi_align_planar");
-    roi_align_planar_kernel<float><<<grid, 256, smem, st>>>(a, (float*)out, row_pitch, plane_pitch);
+    if (rows) {
+      SMOT_ENSURE_SMEM((roi_align_rows_kernel<float, true>), smem, "smot_roi_align_planar");
+      roi_align_rows_kernel<float, true><<<grid, 256, smem, st>>>(a, (float*)out, row_pitch, plane_pitch);
+    } else {
+      SMOT_ENSURE_SMEM(roi_align_planar_kernel<float>, smem, "smot_roi_align_planar");
+      roi_align_planar_kernel<float><<<grid, 256, smem, st>>>(a, (float*)out, row_pitch, plane_pitch);
+    }
   } else if (dtype == SMOT_F16) {
     const size_t smem = (size_t)channels * RAP_TP * sizeof(__half);
-    SMOT_ENSURE_SMEM(roi_align_planar_kernel<__half>, smem, "smot_roi_align_planar");
-    roi_align_planar_kernel<__half><<<grid, 256, smem, st>>>(a, (__half*)out, row_pitch, plane_pitch);
+    if (rows) {
+      SMOT_ENSURE_SMEM((roi_align_rows_kernel<__half, true>), smem, "smot_roi_align_planar");
+      roi_align_rows_kernel<__half, true><<<grid, 256, smem, st>>>(a, (__half*)out, row_pitch, plane_pitch);
+    } else {
+      SMOT_ENSURE_SMEM(roi_align_planar_kernel<__half>, smem, "smot_roi_align_planar");
+      roi_align_planar_kernel<__half><<<grid, 256, smem, st>>>(a, (__half*)out, row_pitch, plane_pitch);
+    }
   } else {
     SMOT_CHECK_ARG(false, "smot_roi_align_planar: bad dtype %d", dtype);
   }
@@ -237,7 +391,13 @@ extern "C" int smot_roi_align(const smot_pyramid* pyr, const float* rois, const 
   const long long warps = (long long)max_rois * res * res;
   const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == SMOT_F32)
+  const bool rows = roi_rows_enabled() && sampling_ratio > 0 && sampling_ratio <= 16 && res * sampling_ratio <= RAR_MAX_SAMPLES;
+  const dim3 grid((unsigned)res, (unsigned)max_rois);
+  if (dtype == SMOT_F32 && rows)
+    roi_align_rows_kernel<float, false><<<grid, 256, 0, st>>>(a, (float*)out, 0, 0);
+  else if (dtype == SMOT_F16 && rows)
+    roi_align_rows_kernel<__half, false><<<grid, 256, 0, st>>>(a, (__half*)out, 0, 0);
+  else if (dtype == SMOT_F32)
     roi_align_kernel<float><<<blocks, 256, 0, st>>>(a, (float*)out);
   else if (dtype == SMOT_F16)
     roi_align_kernel<__half><<<blocks, 256, 0, st>>>(a, (__half*)out);

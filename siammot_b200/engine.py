@@ -517,7 +517,9 @@ class Engine(object):
         # SMOT_CLIP_SLOTS >= streams + 1 plan copies to matter)
         self.clip_backbone_streams = max(1, min(3, int(os.environ.get("SMOT_CLIP_BACKBONE_STREAMS", "1"))))
         # forward_clip (three-stage): backbone half over frame pairs (Engine.pair_plan); SMOT_CLIP_PAIRS=0 = one frame per pass
-        self.clip_pairs = os.environ.get("SMOT_CLIP_PAIRS", "1") == "1"
+        # (measured on B200, profiles/bench_r02c_*: no gain -- the clip's period is the sequential chain track stage -> host
+        # solver -> next memory, not the backbone -- so it stays a switch until that chain is shorter than a backbone pass)
+        self.clip_pairs = os.environ.get("SMOT_CLIP_PAIRS", "0") == "1"
         self._branch_streams = []
         self._track_plans = {}
         self._arenas = {}
@@ -529,6 +531,7 @@ class Engine(object):
         self.xcorr_planar = os.environ.get("SMOT_XCORR_PLANAR", "2") in ("1", "2")
         self.xcorr_planar_mode = 0 if os.environ.get("SMOT_XCORR_PLANAR", "2") == "1" else 1   # the engine passes it per call
         self.timers = None  # optional dict name -> list of (start_event, end_event), see timed()
+        self.host_timers = None   # optional dict: host-side seconds per phase of CombinedROIHeads.finish_frame (bench.py)
         self.time_kernels = False  # also bracket single kernels of the track stage (forces its eager path)
 
     def clip_mode_name(self):

@@ -10,6 +10,8 @@ through :class:`siammot_b200.engine.Engine`; this file is host control flow only
 TrackHead.get_track_memory track_head.py:54-110), restructured so that a frame costs one
 device->host copy.
 """
+import time
+
 import numpy as np
 import torch
 from torch import nn
@@ -267,7 +269,10 @@ class CombinedROIHeads(nn.ModuleDict):
         if pending[1] is None:
             return self._finish_detections_only(pending)
         P, tp, mem, n = pending
+        ht = self.engine.host_timers
+        t0 = time.perf_counter() if ht is not None else 0.0
         tp.wait()
+        t1 = time.perf_counter() if ht is not None else 0.0
         # ---- host: unpack the result block
         total, ncap = tp.total, tp.ncap
         t = max(total, 1)
@@ -307,9 +312,17 @@ class CombinedROIHeads(nn.ModuleDict):
         else:
             scores, ids = self.solver.resolve(kscores, ids, all_track_ids)
         boxes = np.array(kboxes, dtype=np.float32, copy=True)
+        t2 = time.perf_counter() if ht is not None else 0.0
         with self.engine.timed("next_memory"):
             new_mem = self._build_memory(P, boxes, ids, labels, next_P)
-        return self._to_boxlist(boxes, scores, ids, labels, (P.W, P.H)), new_mem
+        t3 = time.perf_counter() if ht is not None else 0.0
+        out = self._to_boxlist(boxes, scores, ids, labels, (P.W, P.H))
+        if ht is not None:   # where the sequential part of a video goes (bench.py stage_ms): wait = the track stage as the host sees it
+            t4 = time.perf_counter()
+            for k, v in (("track_wait", t1 - t0), ("solver", t2 - t1), ("next_memory", t3 - t2), ("boxlist", t4 - t3)):
+                ht[k] = ht.get(k, 0.0) + v
+            ht["frames"] = ht.get("frames", 0) + 1
+        return out, new_mem
 
     def _to_boxlist(self, boxes, scores, ids, labels, size):
         """One packed pinned buffer -> one H2D copy; the BoxList fields are views of the device copy.

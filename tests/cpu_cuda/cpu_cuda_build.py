@@ -23,6 +23,17 @@ def _function_text(src, signature_regex):
     return src[start:end]
 
 
+def _rows_kernel_text(roi):
+    """roi_align_rows_kernel + its helpers (sample struct / function) for the host build: the dynamic shared memory is the
+    shim's buffer, the static __shared__ tables become per-block arrays (the shim runs one block at a time)."""
+    helpers = roi[roi.index("constexpr int RAR_MAX_SAMPLES"):roi.index("template <typename T, bool PLANAR>")]
+    k = _function_text(roi, r"__global__ void __launch_bounds__\(256\) roi_align_rows_kernel")
+    k = k.replace("extern __shared__ __align__(16) unsigned char rar_raw[];", "unsigned char* rar_raw = cpu_dynamic_smem;")
+    k = k.replace("__shared__ RarSample xs[RAR_MAX_SAMPLES];", "static RarSample xs[RAR_MAX_SAMPLES];")
+    k = k.replace("__shared__ RarSample ys[16];", "static RarSample ys[16];")
+    return helpers + k
+
+
 def generate():
     roi = open(os.path.join(CSRC, "roi_align.cu")).read()
     elt = open(os.path.join(CSRC, "elementwise.cu")).read()
@@ -36,6 +47,7 @@ def generate():
              # the kernel declares its dynamic shared memory as an extern array: bind that name to the shim's buffer
              _function_text(roi, r"__global__ void __launch_bounds__\(256\) roi_align_planar_kernel")
              .replace("extern __shared__ __align__(16) unsigned char rap_raw[];", "unsigned char* rap_raw = cpu_dynamic_smem;"),
+             _rows_kernel_text(roi),
              _function_text(elt, r"__global__ void maxpool3x3s2_kernel"),
              _function_text(elt, r"__global__ void deform_im2col3x3_kernel"),
              _function_text(sel, r"__global__ void track_combine_grouped_kernel"),
@@ -47,6 +59,16 @@ extern "C" void cpu_roi_align_planar(const smot_pyramid* pyr, const float* rois,
   a.pyr = *pyr, a.rois = rois, a.level_boxes = level_boxes, a.count = count;
   a.max_rois = max_rois, a.channels = channels, a.res = res, a.sampling = sampling;
   cpu_launch(dim3(res, max_rois), dim3(256), [&] { roi_align_planar_kernel<float>(a, out, row_pitch, plane_pitch); });
+}
+extern "C" void cpu_roi_align_rows(const smot_pyramid* pyr, const float* rois, const float* level_boxes, const int* count, int max_rois,
+                                   int channels, int res, int sampling, float* out, int row_pitch, int plane_pitch, int planar) {
+  RoiArgs a;
+  a.pyr = *pyr, a.rois = rois, a.level_boxes = level_boxes, a.count = count;
+  a.max_rois = max_rois, a.channels = channels, a.res = res, a.sampling = sampling;
+  if (planar)
+    cpu_launch(dim3(res, max_rois), dim3(256), [&] { roi_align_rows_kernel<float, true>(a, out, row_pitch, plane_pitch); });
+  else
+    cpu_launch(dim3(res, max_rois), dim3(256), [&] { roi_align_rows_kernel<float, false>(a, out, 0, 0); });
 }
 extern "C" void cpu_roi_align(const smot_pyramid* pyr, const float* rois, const float* level_boxes, const int* count, int max_rois,
                               int channels, int res, int sampling, float* out) {
@@ -124,8 +146,19 @@ def generate_xcorr():
               _function_text(roi, r"__global__ void roi_align_kernel"),
               _function_text(roi, r"__global__ void __launch_bounds__\(256\) roi_align_planar_kernel")
               .replace("extern __shared__ __align__(16) unsigned char rap_raw[];", "unsigned char* rap_raw = cpu_dynamic_smem;"),
+              _rows_kernel_text(roi),
               _function_text(elt, r"__global__ void maxpool3x3s2_kernel"),
               _function_text(elt, r"__global__ void deform_im2col3x3_kernel"), "}  // namespace smot", """
+extern "C" void cpu_roi_align_rows_h(const smot_pyramid* pyr, const float* rois, const float* level_boxes, const int* count, int max_rois,
+                                     int channels, int res, int sampling, void* out, int row_pitch, int plane_pitch, int planar) {
+  smot::RoiArgs a;
+  a.pyr = *pyr, a.rois = rois, a.level_boxes = level_boxes, a.count = count;
+  a.max_rois = max_rois, a.channels = channels, a.res = res, a.sampling = sampling;
+  if (planar)
+    cpu_launch(dim3(res, max_rois), dim3(256), [&] { smot::roi_align_rows_kernel<__half, true>(a, (__half*)out, row_pitch, plane_pitch); });
+  else
+    cpu_launch(dim3(res, max_rois), dim3(256), [&] { smot::roi_align_rows_kernel<__half, false>(a, (__half*)out, 0, 0); });
+}
 extern "C" void cpu_deform_im2col3x3_h(const void* in, const float* off, void* cols, int H, int W, int C, int in_ld, int off_ld,
                                        int OH, int OW, int out_ld, int stride) {
   const size_t total = (size_t)OH * OW * 9 * (C / 4);

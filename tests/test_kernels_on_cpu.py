@@ -59,6 +59,20 @@ def test_roi_align_planar_kernel_source_matches_oracle(cpu_kernels, res, row_pit
     assert float(got[4].abs().max()) == 0.0                                   # past the count
     assert float((rows[..., res:] - 7.0).abs().max()) == 0.0                  # pad columns never written
     assert float((out[:, :, res * row_pitch:] - 7.0).abs().max()) == 0.0 if plane > res * row_pitch else True
+    # the row-wise kernel with separable sample tables (round 2, the default): bit-identical to both, NHWC and planar
+    rows_nhwc = torch.full((n, res, res, Cc), 7.0)
+    cpu_kernels.cpu_roi_align_rows(C.byref(pyr), p(sr), p(boxes), p(count), n, Cc, res, 2, p(rows_nhwc), 0, 0, 0)
+    assert torch.equal(rows_nhwc, nhwc_out)
+    rows_planar = torch.full((n, Cc, plane), 7.0)
+    cpu_kernels.cpu_roi_align_rows(C.byref(pyr), p(sr), p(boxes), p(count), n, Cc, res, 2, p(rows_planar), row_pitch, plane, 1)
+    assert torch.equal(rows_planar, out)
+    # ... and without the padded frame (the box head's / template pooler's use: pads 0, rois = level boxes)
+    for l in range(4):
+        pyr.pad[l] = 0
+    a1, a2 = torch.full((n, res, res, Cc), 7.0), torch.full((n, res, res, Cc), 7.0)
+    cpu_kernels.cpu_roi_align(C.byref(pyr), p(boxes), None, None, n, Cc, res, 2, p(a1))
+    cpu_kernels.cpu_roi_align_rows(C.byref(pyr), p(boxes), None, None, n, Cc, res, 2, p(a2), 0, 0, 0)
+    assert torch.equal(a1, a2)
 
 
 def test_maxpool3x3s2_kernel_source_matches_torch(cpu_kernels):
@@ -174,6 +188,13 @@ def test_fp16_instantiations_of_the_simple_kernels(cpu_xcorr):
     rows = planes[:, :, :res * RP].view(n, Cc, res, RP)
     assert torch.equal(rows[..., :res], ref.permute(0, 3, 1, 2))
     assert float(rows[..., res:].abs().max()) == 0.0 and float(planes[:, :, res * RP:].abs().max()) == 0.0
+    # the row-wise kernel (separable sample tables), fp16 instantiation: bit-identical to both
+    r_nhwc = torch.zeros(n, res, res, Cc, dtype=torch.float16)
+    cpu_xcorr.cpu_roi_align_rows_h(C.byref(pyr), p(sr), p(boxes), None, n, Cc, res, 2, p(r_nhwc), 0, 0, 0)
+    assert torch.equal(r_nhwc, ref)
+    r_planes = torch.zeros(n, Cc, PL, dtype=torch.float16)
+    cpu_xcorr.cpu_roi_align_rows_h(C.byref(pyr), p(sr), p(boxes), None, n, Cc, res, 2, p(r_planes), RP, PL, 1)
+    assert torch.equal(r_planes, planes)
     x = torch.randn(1, 8, 9, 14, generator=g).half()
     out = torch.zeros(1, 5, 7, 8, dtype=torch.float16)
     x_nhwc = x.permute(0, 2, 3, 1).contiguous()       # keep it alive across the call
