@@ -520,6 +520,9 @@ class Engine(object):
         # (measured on B200, profiles/bench_r02c_*: no gain -- the clip's period is the sequential chain track stage -> host
         # solver -> next memory, not the backbone -- so it stays a switch until that chain is shorter than a backbone pass)
         self.clip_pairs = os.environ.get("SMOT_CLIP_PAIRS", "0") == "1"
+        # forward_clip: the host work nothing waits for (result BoxList, per-id cache update) runs under the NEXT frame's track
+        # stage instead of in front of it (SMOT_CLIP_DEFER=0: in line, as model(frame) does)
+        self.clip_defer = os.environ.get("SMOT_CLIP_DEFER", "1") == "1"
         self._branch_streams = []
         self._track_plans = {}
         self._arenas = {}

@@ -263,9 +263,12 @@ class CombinedROIHeads(nn.ModuleDict):
         ids = np.full((k,), -1, dtype=np.int64)                         # inference.py:90: detections carry id -1
         return self._to_boxlist(boxes, scores, ids, labels, (P.W, P.H)), None
 
-    def finish_frame(self, pending, next_P=None):
+    def finish_frame(self, pending, next_P=None, defer=None):
         """Wait for the frame's result block, resolve ids on the host, build the next-frame memory.
-        next_P: the static plan the NEXT frame will run on (clip pipelining); defaults to this frame's."""
+        next_P: the static plan the NEXT frame will run on (clip pipelining); defaults to this frame's.
+        defer: a list -> the host work nothing downstream waits for (the result BoxList, the per-id cache update) is appended
+        to it as a callable returning the BoxList instead of being done here; the clip pipelines run it right after the NEXT
+        frame's track stage has been enqueued, i.e. under that stage instead of in front of it."""
         if pending[1] is None:
             return self._finish_detections_only(pending)
         P, tp, mem, n = pending
@@ -313,10 +316,24 @@ class CombinedROIHeads(nn.ModuleDict):
             scores, ids = self.solver.resolve(kscores, ids, all_track_ids)
         boxes = np.array(kboxes, dtype=np.float32, copy=True)
         t2 = time.perf_counter() if ht is not None else 0.0
+        late = [] if defer is not None else None
         with self.engine.timed("next_memory"):
-            new_mem = self._build_memory(P, boxes, ids, labels, next_P)
+            new_mem = self._build_memory(P, boxes, ids, labels, next_P, late)
         t3 = time.perf_counter() if ht is not None else 0.0
-        out = self._to_boxlist(boxes, scores, ids, labels, (P.W, P.H))
+        size = (P.W, P.H)
+        if defer is not None:
+            def finish_late():
+                tl = time.perf_counter() if ht is not None else 0.0
+                for fn in late:
+                    fn()
+                res = self._to_boxlist(boxes, scores, ids, labels, size)
+                if ht is not None:
+                    ht["deferred"] = ht.get("deferred", 0.0) + time.perf_counter() - tl
+                return res
+            defer.append(finish_late)
+            out = None
+        else:
+            out = self._to_boxlist(boxes, scores, ids, labels, size)
         if ht is not None:   # where the sequential part of a video goes (bench.py stage_ms): wait = the track stage as the host sees it
             t4 = time.perf_counter()
             for k, v in (("track_wait", t1 - t0), ("solver", t2 - t1), ("next_memory", t3 - t2), ("boxlist", t4 - t3)):
@@ -338,24 +355,38 @@ class CombinedROIHeads(nn.ModuleDict):
             out.add_field("labels", torch.from_numpy(np.array(labels, dtype=np.int64, copy=True)))
             return out
         nbytes = 36 * k
-        if self._out_host is None or self._out_host.numel() < nbytes:
-            self._out_host = torch.zeros((max(nbytes, 36 * 256),), dtype=torch.uint8).pin_memory()
-        h = self._out_host.numpy()
+        # pinned staging ring: the H2D copy below is asynchronous and (in the clip pipelines) enqueued behind the next frame's
+        # track stage, so a staging block is reused only once the copy that read it has completed (event per block)
+        if self._out_host is None:
+            self._out_host = [[None, None] for _ in range(3)]
+            self._out_next = 0
+        slot = self._out_host[self._out_next]
+        self._out_next = (self._out_next + 1) % len(self._out_host)
+        if slot[1] is not None:
+            slot[1].synchronize()
+        if slot[0] is None or slot[0].numel() < nbytes:
+            slot[0] = torch.zeros((max(nbytes, 36 * 256),), dtype=torch.uint8).pin_memory()
+        out_host = slot[0]
+        h = out_host.numpy()
         h[0:8 * k].view(np.int64)[:] = ids
         h[8 * k:16 * k].view(np.int64)[:] = labels
         h[16 * k:32 * k].view(np.float32)[:] = boxes.reshape(-1)
         h[32 * k:36 * k].view(np.float32)[:] = scores
         d = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=dev)
-        d[:nbytes].copy_(self._out_host[:nbytes], non_blocking=True)
+        d[:nbytes].copy_(out_host[:nbytes], non_blocking=True)
+        if slot[1] is None:
+            slot[1] = torch.cuda.Event()
+        slot[1].record()
         out = BoxList(d[16 * k:32 * k].view(torch.float32).view(k, 4), size, mode="xyxy")
         out.add_field("scores", d[32 * k:36 * k].view(torch.float32))
         out.add_field("ids", d[0:8 * k].view(torch.int64))
         out.add_field("labels", d[8 * k:16 * k].view(torch.int64))
         return out
 
-    def _build_memory(self, P, boxes, ids, labels, next_P=None):
+    def _build_memory(self, P, boxes, ids, labels, next_P=None, late=None):
         """TrackHead.get_track_memory (track_head.py:54-110) + EMM.extract_cache (track_core.py:81-98).
-        boxes/ids/labels: numpy, solver output order."""
+        boxes/ids/labels: numpy, solver output order.  late: list -> the per-id cache update (needed by the NEXT frame's
+        memory construction, not by its track stage) is appended to it instead of being done here."""
         eng, dev = self.engine, self.engine.device
         pool = self.track.track_pool
         tu = self.track.track_utils
@@ -391,8 +422,14 @@ class CombinedROIHeads(nn.ModuleDict):
         if dormant:
             eng.gather_templates(feat, n_act, [(d[0], d[1]) for d in dormant])
         mem.feat = feat
-        pool.update_cache({int(m_ids[r]): (feat, r, m_sr[r].copy(), m_boxes[r].copy(), int(m_ids[r]), int(m_labels[r]))
-                           for r in range(n)})
+
+        def update_cache():
+            pool.update_cache({int(m_ids[r]): (feat, r, m_sr[r].copy(), m_boxes[r].copy(), int(m_ids[r]), int(m_labels[r]))
+                               for r in range(n)})
+        if late is None:
+            update_cache()
+        else:
+            late.append(update_cache)
         return mem
 
 
@@ -593,6 +630,7 @@ def _forward_clip(self, frames, before_frame=None, given_detections=None):
             P.static_done.record(side)
         return P
 
+    deferred = []
     with torch.no_grad():
         P_next = static(0)
         for t in range(n_frames):
@@ -601,17 +639,27 @@ def _forward_clip(self, frames, before_frame=None, given_detections=None):
                 before_frame(t)
             cur.wait_event(P.static_done)
             pending = self.roi_heads.launch_frame(P, self._mem, given_detections[t] if given_detections is not None else None)
+            _run_deferred(deferred, results)       # frame t-1's result object / cache update, under frame t's track stage
             if t + 1 < n_frames:
                 P_next = static(t + 1)
-            result, mem = self.roi_heads.finish_frame(pending, next_P=P_next)
+            result, mem = self.roi_heads.finish_frame(pending, next_P=P_next, defer=deferred if eng.clip_defer else None)
             ev = torch.cuda.Event()
             ev.record(cur)
             slot_free[t & 1] = ev
             self._mem = mem
             self.track_memory = mem
             results.append(result)
+        _run_deferred(deferred, results)
         cur.wait_stream(side)
     return results
+
+
+def _run_deferred(deferred, results):
+    """Run the host work the previous frame put off (CombinedROIHeads.finish_frame(defer=...)): its callable returns the frame's
+    BoxList, which replaces the placeholder at the end of ``results``."""
+    for fn in deferred:
+        results[-1] = fn()
+    del deferred[:]
 
 
 def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detections=None):
@@ -663,6 +711,7 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detect
                 P.static_done = torch.cuda.Event()
             P.static_done.record(sD)
 
+    deferred = []
     with torch.no_grad():
         for t in range(min(K - 1, n_frames)):
             backbone(t)
@@ -673,17 +722,19 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detect
                 before_frame(t)
             cur.wait_event(P.static_done)          # D(t) complete (hence B(t))
             pending = self.roi_heads.launch_frame(P, self._mem, given_detections[t] if given_detections is not None else None)
+            _run_deferred(deferred, results)       # frame t-1's result object / cache update, under frame t's track stage
             if t + K - 1 < n_frames:
                 backbone(t + K - 1)                # slot of frame t-1: its slot_free event was recorded in iteration t-1
             if t + 1 < n_frames:
                 detect(t + 1)
-            result, mem = self.roi_heads.finish_frame(pending, next_P=plans.get(t + 1))
+            result, mem = self.roi_heads.finish_frame(pending, next_P=plans.get(t + 1), defer=deferred if eng.clip_defer else None)
             ev = torch.cuda.Event()
             ev.record(cur)
             slot_free[t % K] = ev
             self._mem = mem
             self.track_memory = mem
             results.append(result)
+        _run_deferred(deferred, results)
         cur.wait_stream(sA)
         cur.wait_stream(sD)
         for sB in extra:
@@ -747,6 +798,7 @@ def _forward_clip_pairs(self, eng, frames, before_frame=None, given_detections=N
             P.static_done.record(sD)
 
     n_pairs = (n_frames + 1) // 2
+    deferred = []
     with torch.no_grad():
         backbone(0)
         detect(0)
@@ -756,12 +808,13 @@ def _forward_clip_pairs(self, eng, frames, before_frame=None, given_detections=N
                 before_frame(t)
             cur.wait_event(P.static_done)          # D(t) complete (hence B of its pair)
             pending = self.roi_heads.launch_frame(P, self._mem, given_detections[t] if given_detections is not None else None)
+            _run_deferred(deferred, results)
             p = t // 2
             if t % 2 == 0 and p + 1 < n_pairs and (p + 1) not in launched:
                 backbone(p + 1)                    # its slot held pair p-1, whose last reader finished in iteration t-1
             if t + 1 < n_frames:
                 detect(t + 1)
-            result, mem = self.roi_heads.finish_frame(pending, next_P=plans.get(t + 1))
+            result, mem = self.roi_heads.finish_frame(pending, next_P=plans.get(t + 1), defer=deferred if eng.clip_defer else None)
             if t % 2 == 1 or t + 1 == n_frames:    # the pair's (or the single plan's) buffers are free for the next user
                 ev = torch.cuda.Event()
                 ev.record(cur)
@@ -772,6 +825,7 @@ def _forward_clip_pairs(self, eng, frames, before_frame=None, given_detections=N
             self._mem = mem
             self.track_memory = mem
             results.append(result)
+        _run_deferred(deferred, results)
         cur.wait_stream(sA)
         cur.wait_stream(sD)
     return results

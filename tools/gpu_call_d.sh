@@ -9,6 +9,7 @@ B="--steps 100 --warmup 10 --experimental off --no-cpu-baseline"
 timeout 300 python bench.py $B > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
 SMOT_ROI_ROWS=0 timeout 300 python bench.py $B > "$OUT/bench_noroirows.json" 2> "$OUT/bench_noroirows.err"
 SMOT_CLIP_PAIRS=1 timeout 300 python bench.py $B > "$OUT/bench_pairs.json" 2> "$OUT/bench_pairs.err"
+SMOT_CLIP_DEFER=0 timeout 300 python bench.py $B > "$OUT/bench_nodefer.json" 2> "$OUT/bench_nodefer.err"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file "$OUT/launches_720p30.csv" \
     python tools/run_frames.py --frames 3 --eager > "$OUT/ncu_launches.log" 2>&1
 python tools/launch_report.py "$OUT/launches_720p30.csv" > "$OUT/launches_720p30_summary.txt" 2>&1
