@@ -225,7 +225,26 @@ __device__ __forceinline__ RarSample rar_sample(float v, int size_padded, int si
   return s;
 }
 
-template <typename T, bool PLANAR>
+// four channels as they sit in memory (fp16: 8 bytes = 2 registers), converted only when they are consumed
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { float4 v; };
+template <> struct Raw4<__half> { uint2 v; };
+__device__ __forceinline__ Raw4<float> ld4raw(const float* p) { Raw4<float> r; r.v = *reinterpret_cast<const float4*>(p); return r; }
+__device__ __forceinline__ Raw4<__half> ld4raw(const __half* p) { Raw4<__half> r; r.v = *reinterpret_cast<const uint2*>(p); return r; }
+__device__ __forceinline__ float4 raw_to_f4(const Raw4<float>& r) { return r.v; }
+__device__ __forceinline__ float4 raw_to_f4(const Raw4<__half>& r) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.v.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.v.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ Raw4<T> raw_zero();
+template <> __device__ __forceinline__ Raw4<float> raw_zero<float>() { Raw4<float> r; r.v = make_float4(0.f, 0.f, 0.f, 0.f); return r; }
+template <> __device__ __forceinline__ Raw4<__half> raw_zero<__half>() { Raw4<__half> r; r.v = make_uint2(0u, 0u); return r; }
+
+// SAMP: compile-time sampling ratio (2 = every shipped configuration) or 0 = run time.  With SAMP the sample loops are
+// unrolled and the 4 * SAMP^2 corner loads of a bin are issued before the first multiply-add: the kernel was latency bound
+// after the instruction diet (a warp had one sample's 4 loads in flight at a time).
+template <typename T, bool PLANAR, int SAMP>
 __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T* __restrict__ out, int row_pitch, int plane_pitch) {
   extern __shared__ __align__(16) unsigned char rar_raw[];
   __shared__ RarSample xs[RAR_MAX_SAMPLES];
@@ -278,6 +297,35 @@ __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T*
   for (int pw = wid; pw < a.res; pw += 8) {
     for (int c = lane * 4; c < a.channels; c += 128) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (SAMP > 0) {
+        constexpr int NS = SAMP * SAMP;
+        Raw4<T> v[NS][4];
+        bool use[NS];
+        const Raw4<T> z = raw_zero<T>();
+#pragma unroll
+        for (int sidx = 0; sidx < NS; ++sidx) {       // all corner loads of the bin first (kept as loaded: 2 registers each in fp16)
+          const RarSample sy = ys[sidx / SAMP];
+          const RarSample sx = xs[pw * SAMP + sidx % SAMP];
+          use[sidx] = (sy.flags & sx.flags & 1) != 0;
+          const bool oyl = sy.flags & 2, oyh = sy.flags & 4, oxl = sx.flags & 2, oxh = sx.flags & 4;
+          v[sidx][0] = (use[sidx] && oyl && oxl) ? ld4raw(feat + ((size_t)sy.lo * W + sx.lo) * ld + c) : z;
+          v[sidx][1] = (use[sidx] && oyl && oxh) ? ld4raw(feat + ((size_t)sy.lo * W + sx.hi) * ld + c) : z;
+          v[sidx][2] = (use[sidx] && oyh && oxl) ? ld4raw(feat + ((size_t)sy.hi * W + sx.lo) * ld + c) : z;
+          v[sidx][3] = (use[sidx] && oyh && oxh) ? ld4raw(feat + ((size_t)sy.hi * W + sx.hi) * ld + c) : z;
+        }
+#pragma unroll
+        for (int sidx = 0; sidx < NS; ++sidx) {       // then the sums, in roi_align_kernel's order (iy outer, ix inner)
+          if (!use[sidx]) continue;
+          const RarSample sy = ys[sidx / SAMP];
+          const RarSample sx = xs[pw * SAMP + sidx % SAMP];
+          const float w1 = sy.h * sx.h, w2 = sy.h * sx.l, w3 = sy.l * sx.h, w4 = sy.l * sx.l;
+          const float4 v1 = raw_to_f4(v[sidx][0]), v2 = raw_to_f4(v[sidx][1]), v3 = raw_to_f4(v[sidx][2]), v4 = raw_to_f4(v[sidx][3]);
+          acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+          acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+          acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+          acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+        }
+      } else {
       for (int iy = 0; iy < gh; ++iy) {
         const RarSample sy = ys[iy];
         for (int ix = 0; ix < gw; ++ix) {
@@ -295,6 +343,7 @@ __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T*
           acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
           acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
         }
+      }
       }
       acc.x = __fdiv_rn(acc.x, cnt), acc.y = __fdiv_rn(acc.y, cnt), acc.z = __fdiv_rn(acc.z, cnt), acc.w = __fdiv_rn(acc.w, cnt);
       if (PLANAR) {
@@ -352,18 +401,24 @@ extern "C" int smot_roi_align_planar(const smot_pyramid* pyr, const float* rois,
   const bool rows = roi_rows_enabled() && sampling_ratio > 0 && sampling_ratio <= 16 && res * sampling_ratio <= RAR_MAX_SAMPLES;
   if (dtype == SMOT_F32) {
     const size_t smem = (size_t)channels * RAP_TP * sizeof(float);
-    if (rows) {
-      SMOT_ENSURE_SMEM((roi_align_rows_kernel<float, true>), smem, "smot_roi_align_planar");
-      roi_align_rows_kernel<float, true><<<grid, 256, smem, st>>>(a, (float*)out, row_pitch, plane_pitch);
+    if (rows && sampling_ratio == 2) {
+      SMOT_ENSURE_SMEM((roi_align_rows_kernel<float, true, 2>), smem, "smot_roi_align_planar");
+      roi_align_rows_kernel<float, true, 2><<<grid, 256, smem, st>>>(a, (float*)out, row_pitch, plane_pitch);
+    } else if (rows) {
+      SMOT_ENSURE_SMEM((roi_align_rows_kernel<float, true, 0>), smem, "smot_roi_align_planar");
+      roi_align_rows_kernel<float, true, 0><<<grid, 256, smem, st>>>(a, (float*)out, row_pitch, plane_pitch);
     } else {
       SMOT_ENSURE_SMEM(roi_align_planar_kernel<float>, smem, "smot_roi_align_planar");
       roi_align_planar_kernel<float><<<grid, 256, smem, st>>>(a, (float*)out, row_pitch, plane_pitch);
     }
   } else if (dtype == SMOT_F16) {
     const size_t smem = (size_t)channels * RAP_TP * sizeof(__half);
-    if (rows) {
-      SMOT_ENSURE_SMEM((roi_align_rows_kernel<__half, true>), smem, "smot_roi_align_planar");
-      roi_align_rows_kernel<__half, true><<<grid, 256, smem, st>>>(a, (__half*)out, row_pitch, plane_pitch);
+    if (rows && sampling_ratio == 2) {
+      SMOT_ENSURE_SMEM((roi_align_rows_kernel<__half, true, 2>), smem, "smot_roi_align_planar");
+      roi_align_rows_kernel<__half, true, 2><<<grid, 256, smem, st>>>(a, (__half*)out, row_pitch, plane_pitch);
+    } else if (rows) {
+      SMOT_ENSURE_SMEM((roi_align_rows_kernel<__half, true, 0>), smem, "smot_roi_align_planar");
+      roi_align_rows_kernel<__half, true, 0><<<grid, 256, smem, st>>>(a, (__half*)out, row_pitch, plane_pitch);
     } else {
       SMOT_ENSURE_SMEM(roi_align_planar_kernel<__half>, smem, "smot_roi_align_planar");
       roi_align_planar_kernel<__half><<<grid, 256, smem, st>>>(a, (__half*)out, row_pitch, plane_pitch);
@@ -393,10 +448,14 @@ extern "C" int smot_roi_align(const smot_pyramid* pyr, const float* rois, const 
   cudaStream_t st = (cudaStream_t)stream;
   const bool rows = roi_rows_enabled() && sampling_ratio > 0 && sampling_ratio <= 16 && res * sampling_ratio <= RAR_MAX_SAMPLES;
   const dim3 grid((unsigned)res, (unsigned)max_rois);
-  if (dtype == SMOT_F32 && rows)
-    roi_align_rows_kernel<float, false><<<grid, 256, 0, st>>>(a, (float*)out, 0, 0);
+  if (dtype == SMOT_F32 && rows && sampling_ratio == 2)
+    roi_align_rows_kernel<float, false, 2><<<grid, 256, 0, st>>>(a, (float*)out, 0, 0);
+  else if (dtype == SMOT_F16 && rows && sampling_ratio == 2)
+    roi_align_rows_kernel<__half, false, 2><<<grid, 256, 0, st>>>(a, (__half*)out, 0, 0);
+  else if (dtype == SMOT_F32 && rows)
+    roi_align_rows_kernel<float, false, 0><<<grid, 256, 0, st>>>(a, (float*)out, 0, 0);
   else if (dtype == SMOT_F16 && rows)
-    roi_align_rows_kernel<__half, false><<<grid, 256, 0, st>>>(a, (__half*)out, 0, 0);
+    roi_align_rows_kernel<__half, false, 0><<<grid, 256, 0, st>>>(a, (__half*)out, 0, 0);
   else if (dtype == SMOT_F32)
     roi_align_kernel<float><<<blocks, 256, 0, st>>>(a, (float*)out);
   else if (dtype == SMOT_F16)

@@ -388,6 +388,8 @@ class CombinedROIHeads(nn.ModuleDict):
         boxes/ids/labels: numpy, solver output order.  late: list -> the per-id cache update (needed by the NEXT frame's
         memory construction, not by its track stage) is appended to it instead of being done here."""
         eng, dev = self.engine, self.engine.device
+        ht = eng.host_timers
+        ta = time.perf_counter() if ht is not None else 0.0
         pool = self.track.track_pool
         tu = self.track.track_utils
         active_ids = pool.get_active_ids()
@@ -411,17 +413,26 @@ class CombinedROIHeads(nn.ModuleDict):
         if n == 0:
             return Memory(None, m_sr, m_boxes, m_ids, m_labels, 0, dev)
         # next frame's plan: stage its inputs now (the boxes are needed on the device anyway)
+        tb = time.perf_counter() if ht is not None else 0.0
         tp = eng.track_plan(next_P if next_P is not None else P, n)
+        tc = time.perf_counter() if ht is not None else 0.0
         mem = Memory(None, m_sr, m_boxes, m_ids, m_labels, n_act, dev)
         mem.stage(tp)
         tp.staged_mem = mem
         tp.inputs.copy_(tp.inputs_host, non_blocking=True)
+        td = time.perf_counter() if ht is not None else 0.0
         feat = torch.empty((n, eng.t_res, eng.t_res, eng.C), dtype=eng.dtype, device=dev)
+        te = time.perf_counter() if ht is not None else 0.0
         if n_act:
             eng.templates(P, tp.boxes[:n_act], out=feat[:n_act])
         if dormant:
             eng.gather_templates(feat, n_act, [(d[0], d[1]) for d in dormant])
         mem.feat = feat
+        if ht is not None:
+            tf = time.perf_counter()
+            for k, v in (("mem_numpy", tb - ta), ("mem_track_plan", tc - tb), ("mem_stage_h2d", td - tc), ("mem_alloc", te - td),
+                         ("mem_templates", tf - te)):
+                ht[k] = ht.get(k, 0.0) + v
 
         def update_cache():
             pool.update_cache({int(m_ids[r]): (feat, r, m_sr[r].copy(), m_boxes[r].copy(), int(m_ids[r]), int(m_labels[r]))

@@ -23,10 +23,15 @@ def _function_text(src, signature_regex):
     return src[start:end]
 
 
-def _rows_kernel_text(roi):
+def _rows_kernel_text(roi, fp16=False):
     """roi_align_rows_kernel + its helpers (sample struct / function) for the host build: the dynamic shared memory is the
     shim's buffer, the static __shared__ tables become per-block arrays (the shim runs one block at a time)."""
-    helpers = roi[roi.index("constexpr int RAR_MAX_SAMPLES"):roi.index("template <typename T, bool PLANAR>")]
+    helpers = roi[roi.index("constexpr int RAR_MAX_SAMPLES"):roi.index("// SAMP: compile-time sampling ratio")]
+    if not fp16:
+        helpers = re.sub(r"template <> struct Raw4<__half>.*?\n", "", helpers)
+        helpers = re.sub(r"__device__ __forceinline__ Raw4<__half> ld4raw.*?\n", "", helpers)
+        helpers = re.sub(r"__device__ __forceinline__ float4 raw_to_f4\(const Raw4<__half>& r\) \{.*?\n\}\n", "", helpers, flags=re.S)
+        helpers = re.sub(r"template <> __device__ __forceinline__ Raw4<__half> raw_zero<__half>\(\).*?\n", "", helpers)
     k = _function_text(roi, r"__global__ void __launch_bounds__\(256\) roi_align_rows_kernel")
     k = k.replace("extern __shared__ __align__(16) unsigned char rar_raw[];", "unsigned char* rar_raw = cpu_dynamic_smem;")
     k = k.replace("__shared__ RarSample xs[RAR_MAX_SAMPLES];", "static RarSample xs[RAR_MAX_SAMPLES];")
@@ -66,9 +71,9 @@ extern "C" void cpu_roi_align_rows(const smot_pyramid* pyr, const float* rois, c
   a.pyr = *pyr, a.rois = rois, a.level_boxes = level_boxes, a.count = count;
   a.max_rois = max_rois, a.channels = channels, a.res = res, a.sampling = sampling;
   if (planar)
-    cpu_launch(dim3(res, max_rois), dim3(256), [&] { roi_align_rows_kernel<float, true>(a, out, row_pitch, plane_pitch); });
+    cpu_launch(dim3(res, max_rois), dim3(256), [&] { (sampling == 2 ? roi_align_rows_kernel<float, true, 2>(a, out, row_pitch, plane_pitch) : roi_align_rows_kernel<float, true, 0>(a, out, row_pitch, plane_pitch)); });
   else
-    cpu_launch(dim3(res, max_rois), dim3(256), [&] { roi_align_rows_kernel<float, false>(a, out, 0, 0); });
+    cpu_launch(dim3(res, max_rois), dim3(256), [&] { (sampling == 2 ? roi_align_rows_kernel<float, false, 2>(a, out, 0, 0) : roi_align_rows_kernel<float, false, 0>(a, out, 0, 0)); });
 }
 extern "C" void cpu_roi_align(const smot_pyramid* pyr, const float* rois, const float* level_boxes, const int* count, int max_rois,
                               int channels, int res, int sampling, float* out) {
@@ -146,7 +151,7 @@ def generate_xcorr():
               _function_text(roi, r"__global__ void roi_align_kernel"),
               _function_text(roi, r"__global__ void __launch_bounds__\(256\) roi_align_planar_kernel")
               .replace("extern __shared__ __align__(16) unsigned char rap_raw[];", "unsigned char* rap_raw = cpu_dynamic_smem;"),
-              _rows_kernel_text(roi),
+              _rows_kernel_text(roi, fp16=True),
               _function_text(elt, r"__global__ void maxpool3x3s2_kernel"),
               _function_text(elt, r"__global__ void deform_im2col3x3_kernel"), "}  // namespace smot", """
 extern "C" void cpu_roi_align_rows_h(const smot_pyramid* pyr, const float* rois, const float* level_boxes, const int* count, int max_rois,
@@ -155,9 +160,9 @@ extern "C" void cpu_roi_align_rows_h(const smot_pyramid* pyr, const float* rois,
   a.pyr = *pyr, a.rois = rois, a.level_boxes = level_boxes, a.count = count;
   a.max_rois = max_rois, a.channels = channels, a.res = res, a.sampling = sampling;
   if (planar)
-    cpu_launch(dim3(res, max_rois), dim3(256), [&] { smot::roi_align_rows_kernel<__half, true>(a, (__half*)out, row_pitch, plane_pitch); });
+    cpu_launch(dim3(res, max_rois), dim3(256), [&] { (sampling == 2 ? smot::roi_align_rows_kernel<__half, true, 2>(a, (__half*)out, row_pitch, plane_pitch) : smot::roi_align_rows_kernel<__half, true, 0>(a, (__half*)out, row_pitch, plane_pitch)); });
   else
-    cpu_launch(dim3(res, max_rois), dim3(256), [&] { smot::roi_align_rows_kernel<__half, false>(a, (__half*)out, 0, 0); });
+    cpu_launch(dim3(res, max_rois), dim3(256), [&] { (sampling == 2 ? smot::roi_align_rows_kernel<__half, false, 2>(a, (__half*)out, 0, 0) : smot::roi_align_rows_kernel<__half, false, 0>(a, (__half*)out, 0, 0)); });
 }
 extern "C" void cpu_deform_im2col3x3_h(const void* in, const float* off, void* cols, int H, int W, int C, int in_ld, int off_ld,
                                        int OH, int OW, int out_ld, int stride) {
