@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(256) roi_align_planar_kernel(const RoiArgs a, 
 // PLANAR: results leave through the [C][res] shared-memory tile as one contiguous run per channel (see above); otherwise
 // NHWC rows (roi, ph, pw, C).
 // ---------------------------------------------------------------------------------------------
-constexpr int RAR_MAX_SAMPLES = 512;   // res * gw entries per row
+constexpr int RAR_MAX_SAMPLES = 512;   // res * gw x-entries per CTA
+constexpr int RAR_MAX_YS = 128;        // rows_per_cta * gh y-entries per CTA
 
 struct RarSample {   // one axis of one sample
   int lo, hi;        // corner indices in the REAL (unpadded) map
@@ -248,22 +249,25 @@ template <typename T, bool PLANAR, int SAMP>
 __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T* __restrict__ out, int row_pitch, int plane_pitch) {
   extern __shared__ __align__(16) unsigned char rar_raw[];
   __shared__ RarSample xs[RAR_MAX_SAMPLES];
-  __shared__ RarSample ys[16];
+  __shared__ RarSample ys[RAR_MAX_YS];
   T* tile = reinterpret_cast<T*>(rar_raw);  // PLANAR only: [channels][RAP_TP]
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int ph = blockIdx.x, r = blockIdx.y;
+  // the CTA owns bin rows [ph0, ph1) of roi r (PLANAR: exactly one row, the tile holds one row; NHWC: rows_per_cta rows, so
+  // that the roi's geometry and the sample tables are amortised over ~64+ bins even at 7 x 7)
+  const int ph0 = PLANAR ? (int)blockIdx.x : (int)blockIdx.x * row_pitch, r = blockIdx.y;
+  const int ph1 = PLANAR ? ph0 + 1 : min(a.res, ph0 + row_pitch);
   const int n = a.count ? min(*a.count, a.max_rois) : a.max_rois;
   if (r >= n) {   // rows past the count are zero
     if (PLANAR) {
-      T* dst = out + (size_t)r * a.channels * plane_pitch + (size_t)ph * row_pitch;
+      T* dst = out + (size_t)r * a.channels * plane_pitch + (size_t)ph0 * row_pitch;
       for (int i = threadIdx.x; i < a.channels * a.res; i += blockDim.x) {
         const int c = i / a.res, pw = i - c * a.res;
         dst[(size_t)c * plane_pitch + pw] = from_f<T>(0.f);
       }
     } else {
-      T* dst = out + ((size_t)r * a.res + ph) * a.res * a.channels;
-      for (int i = threadIdx.x * 4; i < a.res * a.channels; i += blockDim.x * 4) st4(dst + i, make_float4(0.f, 0.f, 0.f, 0.f));
+      T* dst = out + ((size_t)r * a.res + ph0) * a.res * a.channels;
+      for (int i = threadIdx.x * 4; i < (ph1 - ph0) * a.res * a.channels; i += blockDim.x * 4) st4(dst + i, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     return;
   }
@@ -289,12 +293,14 @@ __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T*
     const float x = x1 + (float)pw * bin_w + __fdiv_rn(((float)ix + .5f) * bin_w, (float)gw);
     xs[j] = rar_sample(x, Wp, W, pad);
   }
-  if ((int)threadIdx.x < gh) {
-    const float y = y1 + (float)ph * bin_h + __fdiv_rn(((float)threadIdx.x + .5f) * bin_h, (float)gh);
+  if ((int)threadIdx.x < (ph1 - ph0) * gh) {
+    const int pr = (int)threadIdx.x / gh, iy = (int)threadIdx.x - pr * gh;
+    const float y = y1 + (float)(ph0 + pr) * bin_h + __fdiv_rn(((float)iy + .5f) * bin_h, (float)gh);
     ys[threadIdx.x] = rar_sample(y, Hp, H, pad);
   }
   __syncthreads();
-  for (int pw = wid; pw < a.res; pw += 8) {
+  for (int bin = wid; bin < (ph1 - ph0) * a.res; bin += 8) {
+    const int pr = bin / a.res, pw = bin - pr * a.res, ph = ph0 + pr;
     for (int c = lane * 4; c < a.channels; c += 128) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (SAMP > 0) {
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T*
         const Raw4<T> z = raw_zero<T>();
 #pragma unroll
         for (int sidx = 0; sidx < NS; ++sidx) {       // all corner loads of the bin first (kept as loaded: 2 registers each in fp16)
-          const RarSample sy = ys[sidx / SAMP];
+          const RarSample sy = ys[pr * SAMP + sidx / SAMP];
           const RarSample sx = xs[pw * SAMP + sidx % SAMP];
           use[sidx] = (sy.flags & sx.flags & 1) != 0;
           const bool oyl = sy.flags & 2, oyh = sy.flags & 4, oxl = sx.flags & 2, oxh = sx.flags & 4;
@@ -316,7 +322,7 @@ __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T*
 #pragma unroll
         for (int sidx = 0; sidx < NS; ++sidx) {       // then the sums, in roi_align_kernel's order (iy outer, ix inner)
           if (!use[sidx]) continue;
-          const RarSample sy = ys[sidx / SAMP];
+          const RarSample sy = ys[pr * SAMP + sidx / SAMP];
           const RarSample sx = xs[pw * SAMP + sidx % SAMP];
           const float w1 = sy.h * sx.h, w2 = sy.h * sx.l, w3 = sy.l * sx.h, w4 = sy.l * sx.l;
           const float4 v1 = raw_to_f4(v[sidx][0]), v2 = raw_to_f4(v[sidx][1]), v3 = raw_to_f4(v[sidx][2]), v4 = raw_to_f4(v[sidx][3]);
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T*
         }
       } else {
       for (int iy = 0; iy < gh; ++iy) {
-        const RarSample sy = ys[iy];
+        const RarSample sy = ys[pr * gh + iy];
         for (int ix = 0; ix < gw; ++ix) {
           const RarSample sx = xs[pw * gw + ix];
           if (!(sy.flags & sx.flags & 1)) continue;
@@ -359,7 +365,7 @@ __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T*
   }
   if (PLANAR) {
     __syncthreads();
-    T* dst = out + (size_t)r * a.channels * plane_pitch + (size_t)ph * row_pitch;
+    T* dst = out + (size_t)r * a.channels * plane_pitch + (size_t)ph0 * row_pitch;
     for (int i = threadIdx.x; i < a.channels * a.res; i += blockDim.x) {
       const int c = i / a.res, pw = i - c * a.res;
       dst[(size_t)c * plane_pitch + pw] = tile[(size_t)c * RAP_TP + pw];
@@ -372,6 +378,17 @@ static bool roi_rows_enabled() {
   static const bool on = [] {
     const char* e = getenv("SMOT_ROI_ROWS");
     return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// developer switch SMOT_ROI_UNROLL=1: the sampling-2 specialisation that issues all 16 corner loads of a bin before the
+// first multiply-add (96 registers, 2 CTAs per SM).  Measured on B200: SLOWER (41.6 vs 33.0 us on the search windows) -- the
+// rolled form keeps 4x the warps resident, which hides the load latency better than the deeper per-warp queue.
+static bool roi_unroll_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SMOT_ROI_UNROLL");
+    return e && e[0] == '1';
   }();
   return on;
 }
@@ -401,7 +418,7 @@ extern "C" int smot_roi_align_planar(const smot_pyramid* pyr, const float* rois,
   const bool rows = roi_rows_enabled() && sampling_ratio > 0 && sampling_ratio <= 16 && res * sampling_ratio <= RAR_MAX_SAMPLES;
   if (dtype == SMOT_F32) {
     const size_t smem = (size_t)channels * RAP_TP * sizeof(float);
-    if (rows && sampling_ratio == 2) {
+    if (rows && sampling_ratio == 2 && roi_unroll_enabled()) {
       SMOT_ENSURE_SMEM((roi_align_rows_kernel<float, true, 2>), smem, "smot_roi_align_planar");
       roi_align_rows_kernel<float, true, 2><<<grid, 256, smem, st>>>(a, (float*)out, row_pitch, plane_pitch);
     } else if (rows) {
@@ -413,7 +430,7 @@ extern "C" int smot_roi_align_planar(const smot_pyramid* pyr, const float* rois,
     }
   } else if (dtype == SMOT_F16) {
     const size_t smem = (size_t)channels * RAP_TP * sizeof(__half);
-    if (rows && sampling_ratio == 2) {
+    if (rows && sampling_ratio == 2 && roi_unroll_enabled()) {
       SMOT_ENSURE_SMEM((roi_align_rows_kernel<__half, true, 2>), smem, "smot_roi_align_planar");
       roi_align_rows_kernel<__half, true, 2><<<grid, 256, smem, st>>>(a, (__half*)out, row_pitch, plane_pitch);
     } else if (rows) {
@@ -447,15 +464,20 @@ extern "C" int smot_roi_align(const smot_pyramid* pyr, const float* rois, const 
   const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   const bool rows = roi_rows_enabled() && sampling_ratio > 0 && sampling_ratio <= 16 && res * sampling_ratio <= RAR_MAX_SAMPLES;
-  const dim3 grid((unsigned)res, (unsigned)max_rois);
-  if (dtype == SMOT_F32 && rows && sampling_ratio == 2)
-    roi_align_rows_kernel<float, false, 2><<<grid, 256, 0, st>>>(a, (float*)out, 0, 0);
-  else if (dtype == SMOT_F16 && rows && sampling_ratio == 2)
-    roi_align_rows_kernel<__half, false, 2><<<grid, 256, 0, st>>>(a, (__half*)out, 0, 0);
+  // rows of bins per CTA: ~64+ bins, so that the per-CTA geometry + tables are amortised (7 x 7 -> the whole roi)
+  int rpc = (64 + res - 1) / res;
+  if (rpc > res) rpc = res;
+  if (rpc * sampling_ratio > RAR_MAX_YS) rpc = RAR_MAX_YS / (sampling_ratio > 0 ? sampling_ratio : 1);
+  const dim3 grid((unsigned)((res + rpc - 1) / rpc), (unsigned)max_rois);
+  const bool unroll = roi_unroll_enabled() && sampling_ratio == 2;
+  if (dtype == SMOT_F32 && rows && unroll)
+    roi_align_rows_kernel<float, false, 2><<<grid, 256, 0, st>>>(a, (float*)out, rpc, 0);
+  else if (dtype == SMOT_F16 && rows && unroll)
+    roi_align_rows_kernel<__half, false, 2><<<grid, 256, 0, st>>>(a, (__half*)out, rpc, 0);
   else if (dtype == SMOT_F32 && rows)
-    roi_align_rows_kernel<float, false, 0><<<grid, 256, 0, st>>>(a, (float*)out, 0, 0);
+    roi_align_rows_kernel<float, false, 0><<<grid, 256, 0, st>>>(a, (float*)out, rpc, 0);
   else if (dtype == SMOT_F16 && rows)
-    roi_align_rows_kernel<__half, false, 0><<<grid, 256, 0, st>>>(a, (__half*)out, 0, 0);
+    roi_align_rows_kernel<__half, false, 0><<<grid, 256, 0, st>>>(a, (__half*)out, rpc, 0);
   else if (dtype == SMOT_F32)
     roi_align_kernel<float><<<blocks, 256, 0, st>>>(a, (float*)out);
   else if (dtype == SMOT_F16)

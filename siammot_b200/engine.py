@@ -22,6 +22,8 @@ a few single-element glue ops on tiny tensors.  No CPU fallback exists.
 import ctypes as C
 import math
 import os
+import queue
+import threading
 
 import torch
 
@@ -61,6 +63,72 @@ def cell_anchors(stride, sizes, aspect_ratios):
         w, h, xc, yc = whctr(ra)
         rows.append(mk(w * scales, h * scales, xc, yc))
     return torch.from_numpy(np.vstack(rows)).float()
+
+
+class _Enqueuer(threading.Thread):
+    """Daemon thread that runs the clip pipeline's enqueue jobs in submission order.  A job is a callable; `done` (a
+    threading.Event) is set when it has run.  An exception is kept and re-raised on the submitting thread by check()."""
+
+    def __init__(self):
+        super().__init__(name="smot-enqueue", daemon=True)
+        self.q = queue.SimpleQueue()
+        self.error = None
+
+    def run(self):
+        while True:
+            fn, done = self.q.get()
+            try:
+                if fn is not None and self.error is None:
+                    fn()
+            except BaseException as exc:   # noqa: B902 -- handed to the caller's thread
+                self.error = exc
+            finally:
+                if done is not None:
+                    done.set()
+
+    def submit(self, fn, done=None):
+        self.q.put((fn, done))
+
+    def check(self):
+        if self.error is not None:
+            exc, self.error = self.error, None
+            raise exc
+
+
+class _NoTimer(object):
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_TIMER = _NoTimer()
+
+
+class _Timed(object):
+    """Engine.timed(): CUDA-event bracket (+ optional NVTX range) around the enclosed launches."""
+
+    def __init__(self, eng, name):
+        self.eng, self.name = eng, name
+
+    def __enter__(self):
+        eng = self.eng
+        if eng.nvtx:
+            torch.cuda.nvtx.range_push("smot/" + self.name)
+        if eng.timers is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        eng = self.eng
+        if eng.timers is not None:
+            self.e1.record()
+            eng.timers.setdefault(self.name, []).append((self.e0, self.e1))
+        if eng.nvtx:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 class _Plan(object):
@@ -523,6 +591,12 @@ class Engine(object):
         # forward_clip: the host work nothing waits for (result BoxList, per-id cache update) runs under the NEXT frame's track
         # stage instead of in front of it (SMOT_CLIP_DEFER=0: in line, as model(frame) does)
         self.clip_defer = os.environ.get("SMOT_CLIP_DEFER", "1") == "1"
+        # forward_clip (three-stage): the backbone / detection-tail enqueues (graph launches, input copies) and the deferred
+        # host work run on a helper thread, so the caller's thread only carries the sequential chain of a video
+        # (track stage launch -> wait -> solver -> next memory).  SMOT_CLIP_THREAD=0: everything on the caller's thread.
+        self.clip_thread = os.environ.get("SMOT_CLIP_THREAD", "1") == "1"
+        self._enqueuer = None
+        self.clip_thread_force = False   # tests: use the helper thread although the launch lists are not CUDA graphs
         self._branch_streams = []
         self._track_plans = {}
         self._arenas = {}
@@ -550,25 +624,9 @@ class Engine(object):
         """Context manager: when self.timers is a dict, brackets the enclosed launches with CUDA events on
         the launching stream (bench.py's live per-kernel timing); with SMOT_NVTX=1 also an NVTX range "smot/<name>"
         (stages: preprocess, static, static_tail, track_stage, next_memory) for `ncu --nvtx --nvtx-include`."""
-        eng = self
-
-        class _T(object):
-            def __enter__(self_inner):
-                if eng.nvtx:
-                    torch.cuda.nvtx.range_push("smot/" + name)
-                if eng.timers is not None:
-                    self_inner.e0 = torch.cuda.Event(enable_timing=True)
-                    self_inner.e1 = torch.cuda.Event(enable_timing=True)
-                    self_inner.e0.record()
-
-            def __exit__(self_inner, *exc):
-                if eng.timers is not None:
-                    self_inner.e1.record()
-                    eng.timers.setdefault(name, []).append((self_inner.e0, self_inner.e1))
-                if eng.nvtx:
-                    torch.cuda.nvtx.range_pop()
-                return False
-        return _T()
+        if self.timers is None and not self.nvtx:
+            return _NO_TIMER          # the common case costs one attribute test, not a class creation per call
+        return _Timed(self, name)
 
     # ------------------------------------------------------------------------------------------
     # weights
@@ -1067,6 +1125,13 @@ class Engine(object):
             self._branch_streams.append(torch.cuda.Stream(device=self.device))
         return self._branch_streams[:n]
 
+    def enqueuer(self):
+        """The helper thread of the clip pipeline (started on first use)."""
+        if self._enqueuer is None or not self._enqueuer.is_alive():
+            self._enqueuer = _Enqueuer()
+            self._enqueuer.start()
+        return self._enqueuer
+
     def side_stream(self):
         """The stream forward_clip runs the frame-independent stage on (created on first use)."""
         if self._side is None:
@@ -1091,6 +1156,25 @@ class Engine(object):
         with self.timed("static"):
             P.run() if part is None else P.run_part(part)
         return P
+
+    def static_key(self, frame, slot):
+        """Key of the static plan a clip frame (normalised tensor or decoded uint8 frame) runs on."""
+        if not torch.is_tensor(frame) or frame.dtype == torch.uint8:
+            H, W = self.preprocessor().output_size(frame.shape[0], frame.shape[1])
+        else:
+            H, W = frame.shape[-2], frame.shape[-1]
+        return (H, W, slot)
+
+    def static_ready(self, frame, slot):
+        """True when the frame's static plan exists with both halves captured as CUDA graphs (and, for a decoded frame, its
+        preprocessing buffers exist): replaying it needs no allocation and no capture, so any thread may enqueue it."""
+        P = self.plans.get(self.static_key(frame, slot))
+        if P is None or ((P.part_graphs[0] is None or P.part_graphs[1] is None) and not self.clip_thread_force):
+            return False
+        if not torch.is_tensor(frame) or frame.dtype == torch.uint8:
+            lane = slot if self.clip_backbone_streams > 1 else 0
+            return (frame.shape[0], frame.shape[1], lane) in self.preprocessor()._geo
+        return True
 
     def pair_ok(self, frames):
         """Frame pairs need kernels that take a batch (everything but the DCN gather) and frames of one size and kind."""
@@ -1194,18 +1278,41 @@ class Engine(object):
         return ops.emm_decode(maps, mem_sr, mem_boxes, self.hann, self.up, self.t_res, T.PAD_PIXELS,
                               T.EMM.USE_CENTERNESS, T.EMM.COSINE_WINDOW_WEIGHT, P.W, P.H, cfg.INPUT.AMODAL)
 
+    def templates_into(self, P, tp, n_act, feat):
+        """templates() for the clip / per-frame hot path: the first n_act boxes of track plan tp (already on the device at a
+        fixed address) -> feat[:n_act], one ctypes call without the generic wrapper's checks and views."""
+        T = self.cfg.MODEL.TRACK_HEAD
+        if getattr(P, "pyr_plain", None) is None:
+            P.pyr_plain = ops.make_pyramid(P.feats, T.POOLER_SCALES)
+            P.pyr_plain_ref = C.byref(P.pyr_plain)
+        bp = getattr(tp, "boxes_ptr", None)
+        if bp is None:
+            bp = tp.boxes_ptr = C.c_void_p(tp.boxes.data_ptr())
+        check(lib().smot_roi_align(P.pyr_plain_ref, bp, None, None, n_act, self.C, self.t_res, T.POOLER_SAMPLING_RATIO,
+                                   C.c_void_p(feat.data_ptr()), _lib.dtype_code(self.dtype), _lib.stream_ptr()), "smot_roi_align")
+
     def templates(self, P, boxes_dev, out=None):
         """EMM.extract_cache feature part (track_core.py:92): ROIAlign T x T on the unpadded pyramid."""
         T = self.cfg.MODEL.TRACK_HEAD
         if getattr(P, "pyr_plain", None) is None:
             P.pyr_plain = ops.make_pyramid(P.feats, T.POOLER_SCALES)
+            P.pyr_plain_ref = C.byref(P.pyr_plain)
         return ops.roi_align(P.feats, boxes_dev, T.POOLER_SCALES, self.t_res, T.POOLER_SAMPLING_RATIO, out=out,
                              pyramid=P.pyr_plain)
 
     def gather_templates(self, feat, first, sources):
         """feat[first + j] = sources[j][0][sources[j][1]]: the cached templates of dormant tracks (rows of earlier frames'
-        template tensors, track_head.py:77-97) appended behind the active tracks' templates.  Device-side, current stream."""
-        feat[first:] = torch.stack([t[r] for t, r in sources])
+        template tensors, track_head.py:77-97) appended behind the active tracks' templates.  Device-side, current stream.
+        Consecutive rows of one source tensor move as one slice copy (in steady state the dormant tracks of a video sit in
+        the previous memory in the same order: a single copy instead of one indexing op per track)."""
+        j, m = 0, len(sources)
+        while j < m:
+            t, r = sources[j]
+            k = j + 1
+            while k < m and sources[k][0] is t and sources[k][1] == r + (k - j):
+                k += 1
+            feat[first + j:first + k].copy_(t[r:r + (k - j)], non_blocking=True)
+            j = k
 
     def track_arena(self, P, n, ncap=None):
         """The shared buffer arena of static plan P, grown (x2) when n exceeds its capacity."""

@@ -10,6 +10,7 @@ through :class:`siammot_b200.engine.Engine`; this file is host control flow only
 TrackHead.get_track_memory track_head.py:54-110), restructured so that a frame costs one
 device->host copy.
 """
+import threading
 import time
 
 import numpy as np
@@ -263,7 +264,7 @@ class CombinedROIHeads(nn.ModuleDict):
         ids = np.full((k,), -1, dtype=np.int64)                         # inference.py:90: detections carry id -1
         return self._to_boxlist(boxes, scores, ids, labels, (P.W, P.H)), None
 
-    def finish_frame(self, pending, next_P=None, defer=None):
+    def finish_frame(self, pending, next_P=None, defer=None, before_solver=None):
         """Wait for the frame's result block, resolve ids on the host, build the next-frame memory.
         next_P: the static plan the NEXT frame will run on (clip pipelining); defaults to this frame's.
         defer: a list -> the host work nothing downstream waits for (the result BoxList, the per-id cache update) is appended
@@ -275,6 +276,8 @@ class CombinedROIHeads(nn.ModuleDict):
         ht = self.engine.host_timers
         t0 = time.perf_counter() if ht is not None else 0.0
         tp.wait()
+        if before_solver is not None:     # (clip pipeline with a helper thread: the previous frame's cache update must be in)
+            before_solver()
         t1 = time.perf_counter() if ht is not None else 0.0
         # ---- host: unpack the result block
         total, ncap = tp.total, tp.ncap
@@ -394,7 +397,7 @@ class CombinedROIHeads(nn.ModuleDict):
         tu = self.track.track_utils
         active_ids = pool.get_active_ids()
         ids_l = ids.tolist()
-        sel = np.fromiter((i in active_ids for i in ids_l), dtype=bool, count=len(ids_l))
+        sel = np.array([i in active_ids for i in ids_l], dtype=bool)
         a_boxes, a_ids, a_labels = boxes[sel], ids[sel], labels[sel]
         n_act = int(a_ids.shape[0])
         cache = pool.get_cache()
@@ -409,7 +412,7 @@ class CombinedROIHeads(nn.ModuleDict):
             m_sr[:n_act] = tu.search_region_np(a_boxes)
         for j, d in enumerate(dormant):
             r = n_act + j
-            m_boxes[r], m_sr[r], m_ids[r], m_labels[r] = d[3], d[2], d[4], d[5]
+            m_boxes[r], m_sr[r], m_ids[r], m_labels[r] = d[3][d[1]], d[2][d[1]], d[4], d[5]
         if n == 0:
             return Memory(None, m_sr, m_boxes, m_ids, m_labels, 0, dev)
         # next frame's plan: stage its inputs now (the boxes are needed on the device anyway)
@@ -424,7 +427,7 @@ class CombinedROIHeads(nn.ModuleDict):
         feat = torch.empty((n, eng.t_res, eng.t_res, eng.C), dtype=eng.dtype, device=dev)
         te = time.perf_counter() if ht is not None else 0.0
         if n_act:
-            eng.templates(P, tp.boxes[:n_act], out=feat[:n_act])
+            eng.templates_into(P, tp, n_act, feat)
         if dormant:
             eng.gather_templates(feat, n_act, [(d[0], d[1]) for d in dormant])
         mem.feat = feat
@@ -435,8 +438,10 @@ class CombinedROIHeads(nn.ModuleDict):
                 ht[k] = ht.get(k, 0.0) + v
 
         def update_cache():
-            pool.update_cache({int(m_ids[r]): (feat, r, m_sr[r].copy(), m_boxes[r].copy(), int(m_ids[r]), int(m_labels[r]))
-                               for r in range(n)})
+            # per id: (template tensor, row, search regions, boxes, id, label) -- the arrays of this memory are never written
+            # again, so the rows are read from them when a dormant track is revived instead of being copied out for every track
+            ids_py, labels_py = m_ids.tolist(), m_labels.tolist()
+            pool.update_cache({i: (feat, r, m_sr, m_boxes, i, labels_py[r]) for r, i in enumerate(ids_py)})
         if late is None:
             update_cache()
         else:
@@ -657,8 +662,7 @@ def _forward_clip(self, frames, before_frame=None, given_detections=None):
             ev = torch.cuda.Event()
             ev.record(cur)
             slot_free[t & 1] = ev
-            self._mem = mem
-            self.track_memory = mem
+            self.__dict__["_mem"] = self.__dict__["track_memory"] = mem      # (plain attributes: bypass nn.Module.__setattr__)
             results.append(result)
         _run_deferred(deferred, results)
         cur.wait_stream(side)
@@ -723,34 +727,91 @@ def _forward_clip_three_stage(self, eng, frames, before_frame=None, given_detect
             P.static_done.record(sD)
 
     deferred = []
+    enq = eng.enqueuer() if eng.clip_thread else None
+    det_ready = {}                 # frame -> threading.Event set once its detect() has been ENQUEUED by the helper thread
+    pending_jobs = []              # threading.Events of helper jobs the caller's thread must not run ahead of
+
+    def threaded(t):
+        """The helper thread takes over once every launch it will issue is a captured CUDA graph (a capture on one thread
+        while another issues CUDA calls would be invalidated) and the staging buffers exist: i.e. after a warm first clip."""
+        if enq is None or not (eng.use_graph or eng.clip_thread_force):
+            return False
+        for tt in (t + 1, t + K - 1):
+            if tt < n_frames and not eng.static_ready(frames[tt], tt % K):
+                return False
+        return True
+
     with torch.no_grad():
         for t in range(min(K - 1, n_frames)):
             backbone(t)
         detect(0)
         for t in range(n_frames):
+            ev = det_ready.pop(t, None)
+            if ev is not None:                     # the helper thread enqueued D(t): wait (host side) until it has
+                ev.wait()
+                enq.check()
             P = plans.pop(t)
             if before_frame is not None:
                 before_frame(t)
             cur.wait_event(P.static_done)          # D(t) complete (hence B(t))
             pending = self.roi_heads.launch_frame(P, self._mem, given_detections[t] if given_detections is not None else None)
-            _run_deferred(deferred, results)       # frame t-1's result object / cache update, under frame t's track stage
-            if t + K - 1 < n_frames:
-                backbone(t + K - 1)                # slot of frame t-1: its slot_free event was recorded in iteration t-1
-            if t + 1 < n_frames:
-                detect(t + 1)
-            result, mem = self.roi_heads.finish_frame(pending, next_P=plans.get(t + 1), defer=deferred if eng.clip_defer else None)
+            if threaded(t):
+                # helper thread, in this order: D(t+1) (the caller needs it first), frame t-1's deferred host work (its cache
+                # update must be in before this frame's solver), B(t+K-1)
+                if K == 2 and t + 1 < n_frames:
+                    enq.submit(lambda tt=t + 1: backbone(tt))     # two slots: B(t+1) is this iteration's, and D(t+1) follows it
+                if t + 1 < n_frames:
+                    det_ready[t + 1] = threading.Event()
+                    enq.submit(lambda tt=t + 1: detect(tt), det_ready[t + 1])
+                if deferred:
+                    fns, idx = list(deferred), len(results) - 1
+                    del deferred[:]
+                    done = threading.Event()
+                    pending_jobs.append(done)
+
+                    def late(fns=fns, idx=idx):
+                        with torch.cuda.stream(cur):        # a device-resident result is copied on the caller's stream
+                            for fn in fns:
+                                results[idx] = fn()
+                    enq.submit(late, done)
+                if K > 2 and t + K - 1 < n_frames:
+                    enq.submit(lambda tt=t + K - 1: backbone(tt))
+                nxt = None                          # next frame's plan: known without waiting (slot (t+1) % K)
+                if t + 1 < n_frames:
+                    nxt = eng.plans.get(eng.static_key(frames[t + 1], (t + 1) % K))
+                result, mem = self.roi_heads.finish_frame(pending, next_P=nxt, defer=deferred if eng.clip_defer else None,
+                                                          before_solver=lambda: _join(pending_jobs, enq))
+            else:
+                _run_deferred(deferred, results)   # frame t-1's result object / cache update, under frame t's track stage
+                if t + K - 1 < n_frames:
+                    backbone(t + K - 1)            # slot of frame t-1: its slot_free event was recorded in iteration t-1
+                if t + 1 < n_frames:
+                    detect(t + 1)
+                result, mem = self.roi_heads.finish_frame(pending, next_P=plans.get(t + 1), defer=deferred if eng.clip_defer else None)
             ev = torch.cuda.Event()
             ev.record(cur)
             slot_free[t % K] = ev
-            self._mem = mem
-            self.track_memory = mem
+            self.__dict__["_mem"] = self.__dict__["track_memory"] = mem      # (plain attributes: bypass nn.Module.__setattr__)
             results.append(result)
+        if enq is not None:
+            done = threading.Event()
+            enq.submit(None, done)                 # drain the helper thread
+            done.wait()
+            enq.check()
         _run_deferred(deferred, results)
         cur.wait_stream(sA)
         cur.wait_stream(sD)
         for sB in extra:
             cur.wait_stream(sB)
     return results
+
+
+def _join(events, enq):
+    """Wait for the helper-thread jobs the caller must not overtake; surface a helper-thread exception."""
+    for ev in events:
+        ev.wait()
+    del events[:]
+    enq.check()
 
 
 def _forward_clip_pairs(self, eng, frames, before_frame=None, given_detections=None):
@@ -833,8 +894,7 @@ def _forward_clip_pairs(self, eng, frames, before_frame=None, given_detections=N
                     slot_free[p % KP] = ev
                 else:
                     single_free = ev
-            self._mem = mem
-            self.track_memory = mem
+            self.__dict__["_mem"] = self.__dict__["track_memory"] = mem      # (plain attributes: bypass nn.Module.__setattr__)
             results.append(result)
         _run_deferred(deferred, results)
         cur.wait_stream(sA)

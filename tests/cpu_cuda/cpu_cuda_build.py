@@ -35,7 +35,7 @@ def _rows_kernel_text(roi, fp16=False):
     k = _function_text(roi, r"__global__ void __launch_bounds__\(256\) roi_align_rows_kernel")
     k = k.replace("extern __shared__ __align__(16) unsigned char rar_raw[];", "unsigned char* rar_raw = cpu_dynamic_smem;")
     k = k.replace("__shared__ RarSample xs[RAR_MAX_SAMPLES];", "static RarSample xs[RAR_MAX_SAMPLES];")
-    k = k.replace("__shared__ RarSample ys[16];", "static RarSample ys[16];")
+    k = k.replace("__shared__ RarSample ys[RAR_MAX_YS];", "static RarSample ys[RAR_MAX_YS];")
     return helpers + k
 
 
@@ -70,10 +70,15 @@ extern "C" void cpu_roi_align_rows(const smot_pyramid* pyr, const float* rois, c
   RoiArgs a;
   a.pyr = *pyr, a.rois = rois, a.level_boxes = level_boxes, a.count = count;
   a.max_rois = max_rois, a.channels = channels, a.res = res, a.sampling = sampling;
-  if (planar)
-    cpu_launch(dim3(res, max_rois), dim3(256), [&] { (sampling == 2 ? roi_align_rows_kernel<float, true, 2>(a, out, row_pitch, plane_pitch) : roi_align_rows_kernel<float, true, 0>(a, out, row_pitch, plane_pitch)); });
+  // `planar`: 1 = planar rows; 0 = NHWC with the product's rows-per-CTA rule; 2 = NHWC, unrolled sampling-2 specialisation
+  int rpc = (64 + res - 1) / res;
+  if (rpc > res) rpc = res;
+  if (planar == 1)
+    cpu_launch(dim3(res, max_rois), dim3(256), [&] { roi_align_rows_kernel<float, true, 0>(a, out, row_pitch, plane_pitch); });
+  else if (planar == 2)
+    cpu_launch(dim3((res + rpc - 1) / rpc, max_rois), dim3(256), [&] { roi_align_rows_kernel<float, false, 2>(a, out, rpc, 0); });
   else
-    cpu_launch(dim3(res, max_rois), dim3(256), [&] { (sampling == 2 ? roi_align_rows_kernel<float, false, 2>(a, out, 0, 0) : roi_align_rows_kernel<float, false, 0>(a, out, 0, 0)); });
+    cpu_launch(dim3((res + rpc - 1) / rpc, max_rois), dim3(256), [&] { roi_align_rows_kernel<float, false, 0>(a, out, rpc, 0); });
 }
 extern "C" void cpu_roi_align(const smot_pyramid* pyr, const float* rois, const float* level_boxes, const int* count, int max_rois,
                               int channels, int res, int sampling, float* out) {
@@ -159,10 +164,14 @@ extern "C" void cpu_roi_align_rows_h(const smot_pyramid* pyr, const float* rois,
   smot::RoiArgs a;
   a.pyr = *pyr, a.rois = rois, a.level_boxes = level_boxes, a.count = count;
   a.max_rois = max_rois, a.channels = channels, a.res = res, a.sampling = sampling;
-  if (planar)
-    cpu_launch(dim3(res, max_rois), dim3(256), [&] { (sampling == 2 ? smot::roi_align_rows_kernel<__half, true, 2>(a, (__half*)out, row_pitch, plane_pitch) : smot::roi_align_rows_kernel<__half, true, 0>(a, (__half*)out, row_pitch, plane_pitch)); });
+  int rpc = (64 + res - 1) / res;
+  if (rpc > res) rpc = res;
+  if (planar == 1)
+    cpu_launch(dim3(res, max_rois), dim3(256), [&] { smot::roi_align_rows_kernel<__half, true, 0>(a, (__half*)out, row_pitch, plane_pitch); });
+  else if (planar == 2)
+    cpu_launch(dim3((res + rpc - 1) / rpc, max_rois), dim3(256), [&] { smot::roi_align_rows_kernel<__half, false, 2>(a, (__half*)out, rpc, 0); });
   else
-    cpu_launch(dim3(res, max_rois), dim3(256), [&] { (sampling == 2 ? smot::roi_align_rows_kernel<__half, false, 2>(a, (__half*)out, 0, 0) : smot::roi_align_rows_kernel<__half, false, 0>(a, (__half*)out, 0, 0)); });
+    cpu_launch(dim3((res + rpc - 1) / rpc, max_rois), dim3(256), [&] { smot::roi_align_rows_kernel<__half, false, 0>(a, (__half*)out, rpc, 0); });
 }
 extern "C" void cpu_deform_im2col3x3_h(const void* in, const float* off, void* cols, int H, int W, int C, int in_ld, int off_ld,
                                        int OH, int OW, int out_ld, int stride) {

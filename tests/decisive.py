@@ -164,6 +164,7 @@ class MarginOracle(object):
         if with_emm_gap and mem_in is not None and mem_in["feat"].numel() > 0:
             g = emm_argmax_gap(orc, cfg, feats, mem_in)
             m["emm_argmax_gap"] = min(g) if g else float("inf")
+            m["emm_gap_by_id"] = {int(i): float(v) for i, v in zip(mem_in["ids"].tolist(), g)}
         return out, m
 
 

@@ -107,7 +107,7 @@ def run(name):
         mo.inject(scene["clip"][0], scene["boxes"])
         margins = []
         for t in range(1, sc["frames"]):
-            out, m = mo.step(scene["clip"][t])
+            out, m = mo.step(scene["clip"][t], with_emm_gap=True)
             m.pop("top_logit_diff", None)
             margins.append(m)
             ref = frames[t - 1]

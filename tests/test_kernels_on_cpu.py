@@ -73,6 +73,14 @@ def test_roi_align_planar_kernel_source_matches_oracle(cpu_kernels, res, row_pit
     cpu_kernels.cpu_roi_align(C.byref(pyr), p(boxes), None, None, n, Cc, res, 2, p(a1))
     cpu_kernels.cpu_roi_align_rows(C.byref(pyr), p(boxes), None, None, n, Cc, res, 2, p(a2), 0, 0, 0)
     assert torch.equal(a1, a2)
+    a3 = torch.full((n, res, res, Cc), 7.0)
+    cpu_kernels.cpu_roi_align_rows(C.byref(pyr), p(boxes), None, None, n, Cc, res, 2, p(a3), 0, 0, 2)   # unrolled specialisation
+    assert torch.equal(a1, a3)
+    for small in (7, 3):                                  # several bin rows per CTA (the box head's 7 x 7: the whole roi)
+        b1, b2 = torch.full((n, small, small, Cc), 7.0), torch.full((n, small, small, Cc), 7.0)
+        cpu_kernels.cpu_roi_align(C.byref(pyr), p(boxes), None, p(count), n, Cc, small, 2, p(b1))
+        cpu_kernels.cpu_roi_align_rows(C.byref(pyr), p(boxes), None, p(count), n, Cc, small, 2, p(b2), 0, 0, 0)
+        assert torch.equal(b1, b2)
 
 
 def test_maxpool3x3s2_kernel_source_matches_torch(cpu_kernels):
