@@ -585,16 +585,18 @@ class Engine(object):
         # SMOT_CLIP_SLOTS >= streams + 1 plan copies to matter)
         self.clip_backbone_streams = max(1, min(3, int(os.environ.get("SMOT_CLIP_BACKBONE_STREAMS", "1"))))
         # forward_clip (three-stage): backbone half over frame pairs (Engine.pair_plan); SMOT_CLIP_PAIRS=0 = one frame per pass
-        # (measured on B200, profiles/bench_r02c_*: no gain -- the clip's period is the sequential chain track stage -> host
-        # solver -> next memory, not the backbone -- so it stays a switch until that chain is shorter than a backbone pass)
-        self.clip_pairs = os.environ.get("SMOT_CLIP_PAIRS", "0") == "1"
+        # (measured on B200, profiles/bench_r02f_*: 1204 vs 1168 FPS device-resident, 1171 vs 1126 from host frames)
+        self.clip_pairs = os.environ.get("SMOT_CLIP_PAIRS", "1") == "1"
         # forward_clip: the host work nothing waits for (result BoxList, per-id cache update) runs under the NEXT frame's track
         # stage instead of in front of it (SMOT_CLIP_DEFER=0: in line, as model(frame) does)
         self.clip_defer = os.environ.get("SMOT_CLIP_DEFER", "1") == "1"
         # forward_clip (three-stage): the backbone / detection-tail enqueues (graph launches, input copies) and the deferred
         # host work run on a helper thread, so the caller's thread only carries the sequential chain of a video
         # (track stage launch -> wait -> solver -> next memory).  SMOT_CLIP_THREAD=0: everything on the caller's thread.
-        self.clip_thread = os.environ.get("SMOT_CLIP_THREAD", "1") == "1"
+        # Measured on B200 (profiles/bench_r02f_*): SLOWER and noisier (1082 +- 70 vs 1168 FPS) -- the clip is bound by the GPU
+        # (backbone + detection tail + track stage co-scheduled: 0.86 ms per frame), the time the caller's thread saves only
+        # moves into its wait for the track stage, and two Python threads contend for the GIL.  Off by default.
+        self.clip_thread = os.environ.get("SMOT_CLIP_THREAD", "0") == "1"
         self._enqueuer = None
         self.clip_thread_force = False   # tests: use the helper thread although the launch lists are not CUDA graphs
         self._branch_streams = []

@@ -92,6 +92,38 @@ class Memory(object):
                 torch.from_numpy(self.labels.astype(np.int32)).to(dev))
 
 
+class FeaturesView(object):
+    """The ``features`` argument of the tracker plugin contract (track_core.py:28,81-98: a tuple of NCHW feature maps, P2..P6)
+    over the engine's per-frame plan: ``features[i]`` is a zero-copy NCHW view (``permute`` of the plan's NHWC buffer, in the
+    engine's storage dtype) created on first access, ``len(features)`` the number of FPN levels; ``features.plan`` is the plan
+    itself, which the built-in EMM uses to run its fused kernels.  A tracker written against the reference -- pooling
+    ``features`` with its own ops -- therefore runs unchanged; only the maps' dtype (fp16 when DTYPE is float16) differs."""
+
+    def __init__(self, plan):
+        self.plan = plan
+        self._views = {}
+
+    def __len__(self):
+        return len(self.plan.feats)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return tuple(self[j] for j in range(*i.indices(len(self))))
+        if i < 0:
+            i += len(self)
+        v = self._views.get(i)
+        if v is None:
+            v = self._views[i] = self.plan.feats[i].permute(0, 3, 1, 2)
+        return v
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def _plan_of(features):
+    return features.plan if isinstance(features, FeaturesView) else features
+
+
 @registry.SIAMESE_TRACKER.register("EMM")
 class EMM(nn.Module):
     """The Explicit Motion Model tracker (track_core.py:14-98) on the engine.  ``SiamMOT.forward`` runs it
@@ -107,10 +139,12 @@ class EMM(nn.Module):
 
     def forward(self, features, boxes, sr, targets=None, template_features=None):
         """Reference contract: ({}, [BoxList], {}) with clipped, non-empty track boxes.
-        ``features`` is the engine plan of the current frame."""
+        ``features``: a FeaturesView (NCHW maps + the engine plan) or the plan itself."""
         dev = self.engine.device
         b, s = boxes[0], sr[0]
-        tb, conf, valid = self.engine.emm_track(features, template_features, s.bbox.to(dev).contiguous(),
+        if template_features.dim() == 4 and template_features.shape[1] == self.engine.C and template_features.shape[3] != self.engine.C:
+            template_features = template_features.permute(0, 2, 3, 1).contiguous()     # the reference's NCHW templates
+        tb, conf, valid = self.engine.emm_track(_plan_of(features), template_features, s.bbox.to(dev).contiguous(),
                                                 b.bbox.to(dev).contiguous())
         keep = valid.bool()
         out = BoxList(tb[keep], b.size, mode="xyxy")
@@ -121,7 +155,7 @@ class EMM(nn.Module):
 
     def extract_cache(self, features, detection):
         dev = self.engine.device
-        x = self.engine.templates(features, detection.bbox.to(dev).contiguous())
+        x = self.engine.templates(_plan_of(features), detection.bbox.to(dev).contiguous())
         sr = self.track_utils.extend_bbox(self.track_utils.update_boxes_in_pad_images([detection.to("cpu")]))
         return x, sr, [detection]
 
@@ -462,6 +496,14 @@ class SiamMOT(nn.Module):
         if cfg.MODEL.TRACK_ON:                        # build_roi_heads (roi_heads.py:87-100): track head + solver only when tracking
             track_utils, track_pool = build_track_utils(cfg)
             tracker = registry.SIAMESE_TRACKER[cfg.MODEL.TRACK_HEAD.MODEL](cfg, track_utils)
+            if not isinstance(tracker, EMM):
+                # SiamMOT.forward runs the track head as ONE fused launch list built around the EMM (engine._TrackPlan); a
+                # tracker registered by someone else can be constructed and driven through its own forward / extract_cache
+                # on FeaturesView(plan) (NCHW maps, the reference's contract), but it is not what forward() would execute:
+                # refuse loudly instead of silently tracking with the EMM
+                raise NotImplementedError("MODEL.TRACK_HEAD.MODEL = %r: SiamMOT.forward executes the built-in EMM track stage; drive "
+                                          "a third-party SIAMESE_TRACKER through tracker.forward(FeaturesView(plan), ...) yourself"
+                                          % cfg.MODEL.TRACK_HEAD.MODEL)
             sampler = registry.TRACKER_SAMPLER.get(cfg.MODEL.TRACK_HEAD.MODEL, lambda c, t: None)(cfg, track_utils)
             T = cfg.MODEL.TRACK_HEAD
             heads += [("track", TrackHead(tracker, sampler, track_utils, track_pool)),

@@ -132,6 +132,9 @@ def _plugin_contract_check(model, cfg, sd, clip, to_dev=lambda t: t):
     assert float((x.permute(0, 3, 1, 2).float().cpu() - ref_x).abs().max()) <= 2e-5 * float(ref_x.abs().max())
     assert len(sr) == 1 and torch.equal(sr[0].bbox.cpu(), ref_sr) and tuple(sr[0].size) == (W + 2 * T.PAD_PIXELS, H + 2 * T.PAD_PIXELS)
     assert dets[0] is det
+    from siammot_b200.modelling.rcnn import FeaturesView
+    x2, sr2, _ = tracker.extract_cache(FeaturesView(P0), det)          # the reference's argument form: a sequence of NCHW maps
+    assert torch.equal(x2, x) and torch.equal(sr2[0].bbox, sr[0].bbox)
     # next frame: propagate the four tracks
     P1 = eng.run_static(to_dev(clip[1]))
     extra, out, losses = tracker(P1, [det], sr, template_features=x)
@@ -141,6 +144,19 @@ def _plugin_contract_check(model, cfg, sd, clip, to_dev=lambda t: t):
     assert torch.equal(got.get_field("ids").cpu(), ref["ids"]) and torch.equal(got.get_field("labels").cpu(), ref["labels"])
     assert float((got.bbox.cpu() - ref["boxes"]).abs().max()) <= BOX_TOL
     assert float((got.get_field("scores").cpu() - ref["scores"]).abs().max()) <= SCORE_TOL
+    # the reference's argument forms (track_core.py:28,81-98): `features` a sequence of NCHW maps, templates NCHW
+    fv = FeaturesView(P1)
+    ref_feats = o.features(clip[1])
+    assert len(fv) == len(ref_feats) == 5 and len(fv[1:3]) == 2
+    for l, (a, b) in enumerate(zip(fv, ref_feats)):
+        assert tuple(a.shape) == tuple(b.shape), l                      # (1, C, H_l, W_l): what a reference-style tracker indexes
+        assert float((a.float().cpu() - b).abs().max()) <= 1e-4 * float(b.abs().max())
+    import torchvision
+    third_party = torchvision.ops.roi_align(fv[0].float(), [det.bbox.float()], 7, 0.25, 2, False)    # any torch op takes the view
+    want = torchvision.ops.roi_align(ref_feats[0], [boxes], 7, 0.25, 2, False)
+    assert float((third_party.cpu() - want).abs().max()) <= 1e-4 * float(want.abs().max())
+    _, out2, _ = tracker(fv, [det], sr, template_features=x.permute(0, 3, 1, 2))
+    assert torch.equal(out2[0].bbox, got.bbox) and torch.equal(out2[0].get_field("scores"), got.get_field("scores"))
 
 
 def test_emulated_tracker_plugin_contract(monkeypatch):
@@ -339,6 +355,7 @@ def test_emulated_clip_with_the_helper_thread_equals_golden(slots, monkeypatch):
     monkeypatch.setenv("SMOT_CLIP_SPLIT", "1")
     monkeypatch.setenv("SMOT_CLIP_SLOTS", slots)
     monkeypatch.setenv("SMOT_CLIP_THREAD", "1")
+    monkeypatch.setenv("SMOT_CLIP_PAIRS", "0")          # (the frame-pair variant of the pipeline has no helper-thread mode)
     cabi_emulator.install(monkeypatch)
     import threading
     from siammot_b200.modelling import build_siammot

@@ -54,11 +54,14 @@ def test_per_frame_and_two_stream_clip_are_schedule_independent(policy, monkeypa
     _compare(gold, _run_sim(monkeypatch, policy, "clip"))
 
 
+@pytest.mark.parametrize("pairs", ["0", "1"])
 @pytest.mark.parametrize("slots", ["2", "3"])
 @pytest.mark.parametrize("policy", POLICIES, ids=str)
-def test_three_stage_clip_is_schedule_independent(policy, slots, monkeypatch):
+def test_three_stage_clip_is_schedule_independent(policy, slots, pairs, monkeypatch):
+    """pairs = 1 (the default): the backbone half runs over frame pairs (batch-2 plan, two pair slots); 0: one frame per pass."""
     gold = load_golden(NAME)["frames"]
-    _compare(gold, _run_sim(monkeypatch, policy, "clip", env={"SMOT_CLIP_SPLIT": "1", "SMOT_CLIP_SLOTS": slots}))
+    env = {"SMOT_CLIP_SPLIT": "1", "SMOT_CLIP_SLOTS": slots, "SMOT_CLIP_PAIRS": pairs}
+    _compare(gold, _run_sim(monkeypatch, policy, "clip", env=env))
 
 
 @pytest.mark.parametrize("slots,streams", [("3", "2"), ("4", "3"), ("4", "2")])
