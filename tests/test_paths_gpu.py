@@ -149,3 +149,39 @@ def test_all_tracks_lost_raises_like_the_reference():
     pool.increment_frame()
     with pytest.raises(TypeError):
         model(clip[1].to("cuda"))
+
+
+def test_integration_md_operator_stubs_run_as_written():
+    """INTEGRATION.md section B shows the ctypes stubs a maintainer would put behind maskrcnn_benchmark's `_C.nms` /
+    `_C.roi_align_forward`.  Execute that code block VERBATIM and compare with independent implementations."""
+    import os
+    import re
+    import torchvision
+    from oracle import prims
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(repo, "INTEGRATION.md")).read()
+    block = [b for b in re.findall(r"```python\n(.*?)```", md, re.S) if "def nms(" in b and "def roi_align_forward(" in b]
+    assert len(block) == 1
+    code = block[0].replace('"siammot_b200/libsmot.so"', repr(os.path.join(repo, "siammot_b200", "libsmot.so")))
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    g = torch.Generator().manual_seed(0)
+    # ---- nms: score-descending keep list, IoU with +1 widths, suppress on IoU > thresh
+    for n in (1, 57, 700):
+        xy = torch.rand(n, 2, generator=g) * 300
+        wh = torch.rand(n, 2, generator=g) * 80 + 4
+        dets, scores = torch.cat([xy, xy + wh], 1), torch.rand(n, generator=g)
+        keep = ns["nms"](dets.cuda(), scores.cuda(), 0.5)
+        assert keep.dtype == torch.int64 and torch.equal(keep.cpu(), prims.nms_legacy(dets, scores, 0.5))
+    assert ns["nms"](torch.zeros((0, 4), device="cuda"), torch.zeros((0,), device="cuda"), 0.5).numel() == 0
+    # ---- roi_align_forward: NCHW in, (K, C, ph, pw) out, legacy alignment, rois carry the batch index
+    for dt, tol in ((torch.float32, 2e-5), (torch.float16, 2e-3)):
+        x = torch.randn(2, 24, 40, 56, generator=g)
+        b = torch.randint(0, 2, (19,), generator=g).float()
+        xy = torch.rand(19, 2, generator=g) * torch.tensor([150., 100.])
+        wh = torch.rand(19, 2, generator=g) * 80 + 2
+        rois = torch.cat([b[:, None], xy, xy + wh], 1)
+        got = ns["roi_align_forward"](x.to("cuda", dt), rois.cuda(), 0.25, 7, 7, 2)
+        ref = torchvision.ops.roi_align(x.to(dt).float(), rois, (7, 7), 0.25, 2, False)
+        assert tuple(got.shape) == (19, 24, 7, 7)
+        assert float((got.float().cpu() - ref).abs().max()) <= tol * float(ref.abs().max())
