@@ -208,6 +208,10 @@ int smot_xcorr_planar(const void* x_planar, const void* k, void* out, int n, int
  * the live operand halves, fragments shared between template rows u and u+8; equal to fp16 rounding).  smot_xcorr_planar
  * takes 1 when the environment has SMOT_XCORR_PLANAR=2, else 0. */
 int smot_xcorr_planar_mode(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode, void* stream);
+/* ... and the channel group of a CTA (2, 4, 8 or 16 planes = MMA warps; channels % channel_group == 0): the planes are independent,
+ * the results do not depend on it.  smot_xcorr_planar / _mode use 4 (SMOT_XCORR_CG overrides). */
+int smot_xcorr_planar_cfg(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode, int channel_group,
+                          void* stream);
 
 /* smot_emm_decode: fused bicubic x`up` upsampling (track_core.py:69-71) + get_locations (:184-225) +
  * decode_response (:101-135) + clip/validity of wrap_results_to_boxlist (:165-181).

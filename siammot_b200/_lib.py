@@ -43,7 +43,7 @@ _lib = None
 KERNELS_PER_CALL = {"smot_conv2d": 1, "smot_image_to_nhwc": 1, "smot_maxpool2x2": 1, "smot_maxpool3x3s2": 1, "smot_deform_im2col3x3": 1, "smot_upsample_add": 1,
                     "smot_subsample2": 1, "smot_groupnorm_relu": 1, "smot_roi_align": 1, "smot_rpn_select": 6,
                     "smot_sort_nms": 3, "smot_box_decode": 1, "smot_track_combine": 1, "smot_track_combine_grouped": 1, "smot_xcorr": 1, "smot_emm_decode": 2,
-                    "smot_roi_align_planar": 1, "smot_xcorr_planar": 1, "smot_xcorr_planar_mode": 1,
+                    "smot_roi_align_planar": 1, "smot_xcorr_planar": 1, "smot_xcorr_planar_mode": 1, "smot_xcorr_planar_cfg": 1,
                     "smot_resample_h_u8": 1, "smot_resample_v_normalize": 1}
 
 
@@ -71,6 +71,7 @@ def _declare(lib):
         "smot_roi_align_planar": [C.POINTER(Pyramid), vp, vp, vp, i, i, i, i, vp, i, i, i, vp],
         "smot_xcorr_planar": [vp, vp, vp, i, i, vp],
         "smot_xcorr_planar_mode": [vp, vp, vp, i, i, i, vp],
+        "smot_xcorr_planar_cfg": [vp, vp, vp, i, i, i, i, vp],
         "smot_emm_decode": [vp, i, i, i, i, i, vp, vp, vp, f, i, d, i, i, i, vp, vp, vp, vp, vp],
         "smot_resample_coeffs": [i, i, vp, vp],
         "smot_resample_h_u8": [vp, i, i, i, vp, vp, i, i, vp, i, vp],

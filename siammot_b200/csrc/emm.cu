@@ -240,12 +240,32 @@ __device__ __forceinline__ void xm_mma_k8(float* c, uint32_t a0, uint32_t a1, ui
 // overlaps the tail of the ROIAlign; the copy warp waits, then issues the bulk copies.  The MMA phase and the result
 // path are those of xcorr_mma_kernel, instruction for instruction, so the outputs are bit-identical.
 // ---------------------------------------------------------------------------------------------
-constexpr int XP_THREADS = (XM_WARPS + 1) * 32;                 // 16 MMA warps + 1 copy warp
-constexpr int XP_BAR_OFF = XM_SMEM;                             // mbarrier behind the two staging areas
-constexpr int XP_SMEM = XM_SMEM + 16;
-constexpr int XP_COPIES = 4;                                    // bulk copies per CTA (4 channel planes each)
-static_assert(XM_SMEM % 8 == 0, "mbarrier alignment");
-static_assert(XM_CG % XP_COPIES == 0 && ((XM_CG / XP_COPIES) * XM_CSTRIDE * 2) % 16 == 0, "bulk copy size must be a 16-byte multiple");
+// The channel group of a CTA is a template parameter (CG planes = CG MMA warps + 1 copy warp): the (track, channel) planes are
+// independent, so CG only sets the granularity of the grid.  30 tracks x 128 channels are 240 CTAs of 16 planes -- 1.6 per SM,
+// i.e. 92 SMs run 32 planes and 56 run 16 -- or 960 CTAs of 4 planes, at most 7 per SM = 28 planes (see DESIGN.md section 5.2
+// for the measured ladder).  Template vectors are CG halves wide (at most 16 B), result vectors likewise.
+template <int CG>
+struct XpGeom {
+  static_assert(CG == 2 || CG == 4 || CG == 8 || CG == 16, "channel group");
+  static constexpr int WARPS = CG;                              // MMA warps (one plane each)
+  static constexpr int THREADS = (CG + 1) * 32;                 // + 1 copy warp
+  static constexpr int MMA_THREADS = CG * 32;
+  static constexpr int X_HALVES = CG * XM_CSTRIDE, K_HALVES = CG * XM_KPLANE;
+  static constexpr int BAR_OFF = (X_HALVES + K_HALVES) * 2;     // mbarrier behind the two staging areas
+  static constexpr int SMEM = BAR_OFF + 16;
+  static constexpr int COPIES = CG >= 4 ? 4 : CG;               // bulk copies per CTA
+  static constexpr int VH = CG < 8 ? CG : 8;                    // halves per template / result vector
+  static constexpr int NCH = CG / VH;                           // vectors per position
+  static constexpr int K_ITEMS = 15 * 15 * NCH;                 // template vectors per CTA
+  static constexpr int K_ITERS = (K_ITEMS + MMA_THREADS - 1) / MMA_THREADS;
+  static_assert(BAR_OFF % 8 == 0, "mbarrier alignment");
+  static_assert(CG % COPIES == 0 && ((CG / COPIES) * XM_CSTRIDE * 2) % 16 == 0, "bulk copy size must be a 16-byte multiple");
+};
+template <int VH> struct XpVec;
+template <> struct XpVec<2> { using type = uint32_t; };
+template <> struct XpVec<4> { using type = uint2; };
+template <> struct XpVec<8> { using type = uint4; };
+constexpr int XP_THREADS = XpGeom<XM_CG>::THREADS, XP_SMEM = XpGeom<XM_CG>::SMEM;   // the 16-plane form (tests/cpu_cuda)
 
 __device__ __forceinline__ void xp_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -270,74 +290,101 @@ __device__ __forceinline__ void xp_bulk_g2s(uint32_t dst, const void* src, uint3
                : "memory");
 }
 
+#ifdef SMOT_XCORR_TRACE
+// developer build only (tools/xcorr_lab.py): per-warp phase stamps, [cta][warp][8] x (globaltimer, clock64 | smid << 48)
+__device__ unsigned long long* g_xp_trace = nullptr;
+extern "C" int smot_xcorr_trace_buffer(void* buf) { return cudaMemcpyToSymbol(g_xp_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1; }
+#define XP_STAMP(slot)                                                                                                    \
+  do {                                                                                                                    \
+    if (g_xp_trace && (threadIdx.x & 31) == 0) {                                                                          \
+      unsigned long long gt__;                                                                                            \
+      unsigned sm__;                                                                                                      \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt__));                                                             \
+      asm volatile("mov.u32 %0, %smid;" : "=r"(sm__));                                                                    \
+      unsigned long long* t__ = g_xp_trace + ((((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + (slot)) * 2; \
+      t__[0] = gt__, t__[1] = ((unsigned long long)clock64() & 0xffffffffffffull) | ((unsigned long long)sm__ << 48);    \
+    }                                                                                                                     \
+  } while (0)
+#else
+#define XP_STAMP(slot) do { } while (0)
+#endif
+
 // MMA_MODE 0: the MMA phase of xcorr_mma_kernel, instruction for instruction (bit-identical results).
-// MMA_MODE 1 (SMOT_XCORR_PLANAR=2): the same contraction with the structurally-zero work removed --
+// MMA_MODE 1 (default): the same contraction with the structurally-zero work removed --
 //   * of the four m16n8k16 per template row, two have an all-zero B half (taps d0-8 and d0+24 do not exist): they become
 //     m16n8k8 on the live half (window columns 8..15 for output columns 8..15, 16..23 for output columns 0..7): 3 instead of
 //     4 k16-equivalents per row, -25 % tensor work;
 //   * template rows u and u+8 read window rows u..u+15 and u+8..u+23: the second block of the first is the first block of
 //     the second, so the pair costs ldmatrix x4 + x2 per column half instead of 2 x4 (-25 % shared-memory wavefronts).
 //   The accumulation order differs from mode 0 (fp32 rounding), so the results agree to fp16 rounding, not bit for bit.
-template <int MMA_MODE>
-__global__ void __launch_bounds__(XP_THREADS) xcorr_planar_kernel(const __half* __restrict__ xp, const __half* __restrict__ k,
-                                                                  __half* __restrict__ out, int C) {
+// The results do not depend on CG (the planes are independent and each is computed by one warp in a fixed order).
+template <int MMA_MODE, int CG>
+__global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const __half* __restrict__ xp, const __half* __restrict__ k,
+                                                                          __half* __restrict__ out, int C) {
+  using G = XpGeom<CG>;
+  using KVec = typename XpVec<G::VH>::type;
   constexpr int S = 30, TT = 15, O = 16;
-  constexpr int KSTEPS = (TT * 2 + XM_WARPS - 1) / XM_WARPS;   // (template row, channel half) pairs per warp
   static_assert(S * XM_PITCH + 8 == XM_CSTRIDE, "plane = 30 rows of XM_PITCH halves + 8");
   extern __shared__ __align__(128) unsigned char xp_raw[];
   __half* xT = reinterpret_cast<__half*>(xp_raw);     // [CG][CSTRIDE]: filled by the bulk copies
-  __half* kz = xT + XM_CG * XM_CSTRIDE;             // [CG][TT][2][KROW]
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(xp_raw + XP_BAR_OFF);
-  const int n = blockIdx.y, c0 = blockIdx.x * XM_CG;
+  __half* kz = xT + G::X_HALVES;                      // [CG][TT][2][KROW]
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(xp_raw + G::BAR_OFF);
+  const int n = blockIdx.y, c0 = blockIdx.x * CG;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool copy_warp = warp == XM_WARPS;
+  const bool copy_warp = warp == G::WARPS;
   pdl_launch_dependents();
-  // ---- prologue (independent of the predecessor's output)
+  XP_STAMP(0);
+  // ---- prologue (independent of the predecessor's output): template vectors to registers, zero fill of the padded copies
   const __half* kb = k + (size_t)n * TT * TT * C + c0;
-  uint4 kv[KSTEPS];
+  KVec kv[G::K_ITERS];
   if (!copy_warp) {
 #pragma unroll
-    for (int it = 0; it < KSTEPS; ++it) {
-      const int idx = it * XM_WARPS + warp, u = idx >> 1, q = idx & 1;
-      if (idx < TT * 2 && lane < TT) kv[it] = *reinterpret_cast<const uint4*>(kb + (size_t)(u * TT + lane) * C + q * 8);
+    for (int it = 0; it < G::K_ITERS; ++it) {
+      const int i = it * G::MMA_THREADS + tid;
+      if (i < G::K_ITEMS) kv[it] = *reinterpret_cast<const KVec*>(kb + (size_t)(i / G::NCH) * C + (i % G::NCH) * 8);
     }
     uint4* kz4 = reinterpret_cast<uint4*>(kz);
-    for (int i = tid; i < XM_CG * XM_KPLANE / 8; i += XM_WARPS * 32) kz4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < G::K_HALVES / 8; i += G::MMA_THREADS) kz4[i] = make_uint4(0u, 0u, 0u, 0u);
   } else if (lane == 0) {
     xp_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();  // template zero fill complete; the mbarrier is initialised for every thread
+  XP_STAMP(1);
   if (copy_warp) {
-    // ---- window: wait for the producer of the planes, then 4 bulk copies onto one mbarrier
+    // ---- window: wait for the producer of the planes, then the bulk copies onto one mbarrier
     pdl_wait();
+    XP_STAMP(2);
     if (lane == 0) {
-      constexpr uint32_t BYTES = (XM_CG / XP_COPIES) * XM_CSTRIDE * 2;
+      constexpr uint32_t BYTES = (CG / G::COPIES) * XM_CSTRIDE * 2;
       const __half* src = xp + ((size_t)n * C + c0) * XM_CSTRIDE;
-      xp_mbar_expect_tx(bar, BYTES * XP_COPIES);
+      xp_mbar_expect_tx(bar, BYTES * G::COPIES);
 #pragma unroll
-      for (int i = 0; i < XP_COPIES; ++i)
+      for (int i = 0; i < G::COPIES; ++i)
         xp_bulk_g2s((uint32_t)__cvta_generic_to_shared(xT) + i * BYTES, reinterpret_cast<const unsigned char*>(src) + (size_t)i * BYTES,
                     BYTES, bar);
     }
   } else {
 #pragma unroll
-    for (int it = 0; it < KSTEPS; ++it) {
-      const int idx = it * XM_WARPS + warp, u = idx >> 1, q = idx & 1;
-      if (idx < TT * 2 && lane < TT) {
+    for (int it = 0; it < G::K_ITERS; ++it) {
+      const int i = it * G::MMA_THREADS + tid;
+      if (i < G::K_ITEMS) {
+        const int p = i / G::NCH, q = i % G::NCH, u = p / TT, v = p % TT;
         const __half* h = reinterpret_cast<const __half*>(&kv[it]);
-        __half* dst = kz + (q * 8) * XM_KPLANE + u * 2 * XM_KROW + 8 + lane;
+        __half* dst = kz + (q * 8) * XM_KPLANE + u * 2 * XM_KROW + 8 + v;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < G::VH; ++e) {
           dst[e * XM_KPLANE] = h[e];                  // copy 0: K[u][v] at half 8 + v
           dst[e * XM_KPLANE + XM_KROW - 1] = h[e];    // copy 1: K[u][v] at half 7 + v
         }
       }
     }
+    XP_STAMP(2);
     pdl_wait();  // the result stores below must not pass the predecessor either (back-to-back launches share `out`)
   }
   __syncthreads();  // templates staged
+  XP_STAMP(3);
   float acc[2][4];
   const int g = lane >> 2, t = lane & 3;
   const int c = warp;
@@ -355,6 +402,7 @@ __global__ void __launch_bounds__(XP_THREADS) xcorr_planar_kernel(const __half* 
         }
       }
     }
+    XP_STAMP(4);
     // ---- MMA phase: warp = channel (identical to xcorr_mma_kernel)
     const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
     const int par = g & 1;
@@ -406,6 +454,7 @@ __global__ void __launch_bounds__(XP_THREADS) xcorr_planar_kernel(const __half* 
         row_step(lo, hi, 7);
       }
     }
+    XP_STAMP(5);
     // ---- D fragments -> the warp's own (now dead) window plane as [O*O] halves
     __syncwarp();
     __half2* ost = reinterpret_cast<__half2*>(xT + c * XM_CSTRIDE);
@@ -416,14 +465,20 @@ __global__ void __launch_bounds__(XP_THREADS) xcorr_planar_kernel(const __half* 
     }
   }
   __syncthreads();
+  XP_STAMP(6);
   if (!copy_warp) {
-    const int q = warp & 1, pos = (warp >> 1) * 32 + lane;   // 256 positions x 2 channel halves = 512 threads
-    const __half* src = xT + (q * 8) * XM_CSTRIDE + pos;
-    __align__(16) __half h[8];
+    // O*O positions x NCH result vectors: a warp takes 32 consecutive positions of one vector column
 #pragma unroll
-    for (int e = 0; e < 8; ++e) h[e] = src[e * XM_CSTRIDE];
-    *reinterpret_cast<uint4*>(out + ((size_t)n * O * O + pos) * C + c0 + q * 8) = *reinterpret_cast<const uint4*>(h);
+    for (int i = tid; i < O * O * G::NCH; i += G::MMA_THREADS) {
+      const int q = i / (O * O), pos = i % (O * O);
+      const __half* src = xT + (q * 8) * XM_CSTRIDE + pos;
+      __align__(16) __half h[G::VH];
+#pragma unroll
+      for (int e = 0; e < G::VH; ++e) h[e] = src[e * XM_CSTRIDE];
+      *reinterpret_cast<KVec*>(out + ((size_t)n * O * O + pos) * C + c0 + q * 8) = *reinterpret_cast<const KVec*>(h);
+    }
   }
+  XP_STAMP(7);
 }
 
 // generic fallback for unusual geometries: one thread per output element
@@ -669,29 +724,65 @@ static bool xcorr_planar_trimmed() {
   return on;
 }
 
+// channels per CTA: 4 by default (measured ladder in DESIGN.md section 5.2); developer switch SMOT_XCORR_CG (read once)
+static int xcorr_planar_cg() {
+  static const int cg = [] {
+    const char* e = getenv("SMOT_XCORR_CG");
+    const int v = e ? atoi(e) : 0;
+    return (v == 2 || v == 4 || v == 8 || v == 16) ? v : 4;
+  }();
+  return cg;
+}
+
 extern "C" int smot_xcorr_planar(const void* x_planar, const void* k, void* out, int n, int channels, void* stream) {
   return smot_xcorr_planar_mode(x_planar, k, out, n, channels, xcorr_planar_trimmed() ? 1 : 0, stream);
 }
 
 extern "C" int smot_xcorr_planar_mode(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode,
                                       void* stream) {
+  int cg = xcorr_planar_cg();
+  while (cg > 2 && channels % cg) cg >>= 1;
+  return smot_xcorr_planar_cfg(x_planar, k, out, n, channels, mma_mode, cg, stream);
+}
+
+template <int MODE, int CG>
+static cudaError_t launch_xcorr_planar(const void* x, const void* k, void* out, int n, int C, cudaStream_t st) {
+  using G = XpGeom<CG>;
+  if (G::SMEM > 48 * 1024) {
+    static bool granted[::smot::SMOT_MAX_DEVICES];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < ::smot::SMOT_MAX_DEVICES && !granted[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(xcorr_planar_kernel<MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+      if (e != cudaSuccess) return e;
+      granted[dev] = true;
+    }
+  }
+  return launch_pdl(xcorr_planar_kernel<MODE, CG>, dim3(C / CG, n), dim3(G::THREADS), G::SMEM, st, (const __half*)x, (const __half*)k,
+                    (__half*)out, C);
+}
+
+extern "C" int smot_xcorr_planar_cfg(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode,
+                                     int channel_group, void* stream) {
+  const int cg = channel_group;
   SMOT_CHECK_ARG(mma_mode == 0 || mma_mode == 1, "smot_xcorr_planar: mma_mode %d", mma_mode);
-  SMOT_CHECK_ARG(n >= 0 && channels > 0 && channels % XM_CG == 0, "smot_xcorr_planar: bad geometry n=%d C=%d (C must be a multiple of %d)",
-                 n, channels, XM_CG);
+  SMOT_CHECK_ARG(cg == 2 || cg == 4 || cg == 8 || cg == 16, "smot_xcorr_planar: channel group %d (2, 4, 8 or 16)", cg);
+  SMOT_CHECK_ARG(n >= 0 && channels > 0 && channels % cg == 0, "smot_xcorr_planar: bad geometry n=%d C=%d (C must be a multiple of %d)",
+                 n, channels, cg);
   if (n == 0) return SMOT_OK;
   SMOT_CHECK_ARG(x_planar && k && out, "smot_xcorr_planar: null argument");
   SMOT_CHECK_ARG((((uintptr_t)x_planar | (uintptr_t)k | (uintptr_t)out) & 15) == 0, "smot_xcorr_planar: operands must be 16-byte aligned");
   static_assert(XM_CSTRIDE == SMOT_XCORR_PLANE && XM_PITCH == SMOT_XCORR_ROW_PITCH, "smot.h states the plane layout");
+  cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  if (mma_mode == 1) {
-    SMOT_ENSURE_SMEM(xcorr_planar_kernel<1>, XP_SMEM, "smot_xcorr_planar");
-    e = launch_pdl(xcorr_planar_kernel<1>, dim3(channels / XM_CG, n), dim3(XP_THREADS), XP_SMEM, (cudaStream_t)stream,
-                   (const __half*)x_planar, (const __half*)k, (__half*)out, channels);
-  } else {
-    SMOT_ENSURE_SMEM(xcorr_planar_kernel<0>, XP_SMEM, "smot_xcorr_planar");
-    e = launch_pdl(xcorr_planar_kernel<0>, dim3(channels / XM_CG, n), dim3(XP_THREADS), XP_SMEM, (cudaStream_t)stream,
-                   (const __half*)x_planar, (const __half*)k, (__half*)out, channels);
+#define SMOT_XP_CASE(MODE, CGV) \
+  case (MODE) * 32 + (CGV): e = launch_xcorr_planar<MODE, CGV>(x_planar, k, out, n, channels, st); break
+  switch (mma_mode * 32 + cg) {
+    SMOT_XP_CASE(0, 2); SMOT_XP_CASE(0, 4); SMOT_XP_CASE(0, 8); SMOT_XP_CASE(0, 16);
+    SMOT_XP_CASE(1, 2); SMOT_XP_CASE(1, 4); SMOT_XP_CASE(1, 8); SMOT_XP_CASE(1, 16);
+    default: e = cudaErrorInvalidValue;
   }
+#undef SMOT_XP_CASE
   if (e != cudaSuccess) {
     set_error("smot_xcorr_planar: launch failed: %s", cudaGetErrorString(e));
     return SMOT_ERR_CUDA;

@@ -288,7 +288,7 @@ def roi_align_planar(feats, rois, scales, res, sampling, level_boxes=None, pads=
     return out
 
 
-def xcorr_planar(x_planar, k, out=None, mma_mode=None):
+def xcorr_planar(x_planar, k, out=None, mma_mode=None, channel_group=None):
     """x_planar (n, C, XCORR_PLANE) fp16 channel-planar 30x30 windows (row pitch XCORR_ROW_PITCH, columns 30/31 zero),
     k (n,15,15,C) NHWC fp16 -> (n,16,16,C) NHWC: the output of xcorr() on the same windows, bit for bit."""
     _require_cuda(x_planar, k)
@@ -299,7 +299,10 @@ def xcorr_planar(x_planar, k, out=None, mma_mode=None):
     assert x_planar.is_contiguous() and k.is_contiguous() and tuple(k.shape) == (n, 15, 15, Cc)
     if out is None:
         out = torch.empty((n, 16, 16, Cc), dtype=torch.float16, device=k.device)
-    if mma_mode is None:   # the library's default (environment SMOT_XCORR_PLANAR=2 selects the trimmed MMA phase)
+    if channel_group is not None:   # planes per CTA (2 / 4 / 8 / 16): same results, another grid
+        check(lib().smot_xcorr_planar_cfg(_ptr(x_planar), _ptr(k), _ptr(out), n, Cc, 1 if mma_mode is None else int(mma_mode),
+                                          int(channel_group), stream_ptr()), "smot_xcorr_planar")
+    elif mma_mode is None:   # the library's default: trimmed MMA phase (SMOT_XCORR_PLANAR=1 selects the untrimmed one)
         check(lib().smot_xcorr_planar(_ptr(x_planar), _ptr(k), _ptr(out), n, Cc, stream_ptr()), "smot_xcorr_planar")
     else:
         check(lib().smot_xcorr_planar_mode(_ptr(x_planar), _ptr(k), _ptr(out), n, Cc, int(mma_mode), stream_ptr()), "smot_xcorr_planar")

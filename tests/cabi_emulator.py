@@ -346,6 +346,10 @@ class FakeLib(object):
     def smot_xcorr_planar_mode(self, xp, k, out, n, Cc, mma_mode, st):
         return self.smot_xcorr_planar(xp, k, out, n, Cc, st)
 
+    def smot_xcorr_planar_cfg(self, xp, k, out, n, Cc, mma_mode, cg, st):
+        assert cg in (2, 4, 8, 16) and Cc % cg == 0
+        return self.smot_xcorr_planar(xp, k, out, n, Cc, st)
+
     def smot_emm_decode(self, maps, map_ld, n, O, up, T, sr, tboxes, hann, pad, use_centerness, sigma, img_w, img_h, amodal,
                         out_boxes, out_conf, out_valid, scratch, st):
         self._count("smot_emm_decode")

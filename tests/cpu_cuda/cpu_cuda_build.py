@@ -137,10 +137,11 @@ def generate_xcorr():
     %globaltimer read of the bounded wait) have no host meaning and are dropped."""
     emm = open(os.path.join(CSRC, "emm.cu")).read()
     consts_mma = emm[emm.index("constexpr int XM_CG = 16;"):emm.index("__device__ __forceinline__ void xm_ldmatrix_x4")]
-    consts_planar = emm[emm.index("constexpr int XP_THREADS"):emm.index("__device__ __forceinline__ void xp_mbar_init")]
+    consts_planar = emm[emm.index("template <int CG>\nstruct XpGeom"):emm.index("__device__ __forceinline__ void xp_mbar_init")]
     k_mma = _function_text(emm, r"__global__ void __launch_bounds__\(XM_WARPS \* 32\) xcorr_mma_kernel")
-    k_planar = _function_text(emm, r"__global__ void __launch_bounds__\(XP_THREADS\) xcorr_planar_kernel")
-    assert k_planar.lstrip().startswith("template <int MMA_MODE>")
+    k_planar = _function_text(emm, r"__global__ void __launch_bounds__\(XpGeom<CG>::THREADS\) xcorr_planar_kernel")
+    assert k_planar.lstrip().startswith("template <int MMA_MODE, int CG>")
+    k_planar = re.sub(r"XP_STAMP\(\d\);", ";", k_planar)
     k_mma = k_mma.replace("extern __shared__ __align__(16) unsigned char xm_raw[];", "unsigned char* xm_raw = cpu_dynamic_smem;")
     k_planar = k_planar.replace("extern __shared__ __align__(128) unsigned char xp_raw[];", "unsigned char* xp_raw = cpu_dynamic_smem;")
     k_planar = re.sub(r'asm volatile\("fence[^"]*" ::: "memory"\);', ";", k_planar)
@@ -206,11 +207,26 @@ using namespace smot;
 extern "C" void cpu_xcorr_mma(const void* x, const void* k, void* out, int n, int C) {
   cpu_launch_warps(dim3(C / XM_CG, n), dim3(XM_WARPS * 32), [&] { xcorr_mma_kernel((const __half*)x, (const __half*)k, (__half*)out, C); });
 }
+template <int MODE, int CG>
+static void cpu_xcorr_planar_launch(const void* xp, const void* k, void* out, int n, int C) {
+  cpu_launch_warps(dim3(C / CG, n), dim3(XpGeom<CG>::THREADS), [&] { xcorr_planar_kernel<MODE, CG>((const __half*)xp, (const __half*)k, (__half*)out, C); });
+}
+extern "C" int cpu_xcorr_planar_cfg(const void* xp, const void* k, void* out, int n, int C, int mode, int cg) {
+  switch (mode * 32 + cg) {
+    case 2: cpu_xcorr_planar_launch<0, 2>(xp, k, out, n, C); break;
+    case 4: cpu_xcorr_planar_launch<0, 4>(xp, k, out, n, C); break;
+    case 8: cpu_xcorr_planar_launch<0, 8>(xp, k, out, n, C); break;
+    case 16: cpu_xcorr_planar_launch<0, 16>(xp, k, out, n, C); break;
+    case 34: cpu_xcorr_planar_launch<1, 2>(xp, k, out, n, C); break;
+    case 36: cpu_xcorr_planar_launch<1, 4>(xp, k, out, n, C); break;
+    case 40: cpu_xcorr_planar_launch<1, 8>(xp, k, out, n, C); break;
+    case 48: cpu_xcorr_planar_launch<1, 16>(xp, k, out, n, C); break;
+    default: return 1;
+  }
+  return 0;
+}
 extern "C" void cpu_xcorr_planar(const void* xp, const void* k, void* out, int n, int C, int mode) {
-  if (mode == 0)
-    cpu_launch_warps(dim3(C / XM_CG, n), dim3(XP_THREADS), [&] { xcorr_planar_kernel<0>((const __half*)xp, (const __half*)k, (__half*)out, C); });
-  else
-    cpu_launch_warps(dim3(C / XM_CG, n), dim3(XP_THREADS), [&] { xcorr_planar_kernel<1>((const __half*)xp, (const __half*)k, (__half*)out, C); });
+  cpu_xcorr_planar_cfg(xp, k, out, n, C, mode, 16);
 }
 extern "C" int cpu_xcorr_plane_halves() { return XM_CSTRIDE; }
 """]

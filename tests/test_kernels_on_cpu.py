@@ -166,6 +166,12 @@ def test_xcorr_kernels_source_under_ptx_emulation(cpu_xcorr, n, Cc):
     d = (out_trim.float() - out_mma.float()).abs()
     assert float((d / out_mma.float().abs().clamp_min(2e-2)).max()) <= 1.1e-3      # one fp16 ulp (2^-10) of the larger values
     assert float((d > 0).float().mean()) < 0.05                                    # and rare
+    # the channel group of a CTA (planes = MMA warps: 2 / 4 / 8 / 16) only sets the grid: the results are the same bits
+    for cg in (2, 4, 8):
+        for mode, want in ((0, out_mma), (1, out_trim)):
+            got = torch.full((n, 16, 16, Cc), float("nan"), dtype=torch.float16)
+            assert cpu_xcorr.cpu_xcorr_planar_cfg(p(xp), p(k_nhwc), p(got), n, Cc, mode, cg) == 0
+            assert torch.equal(got, want), "channel group %d, mode %d" % (cg, mode)
 
 
 def test_fp16_instantiations_of_the_simple_kernels(cpu_xcorr):

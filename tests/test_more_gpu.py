@@ -296,6 +296,13 @@ def test_xcorr_planar_equals_xcorr(n, C):
     trim = ops.xcorr_planar(xp, dk, mma_mode=1)
     assert rel_err(nchw(trim), orc.xcorr_depthwise(x, k)) <= tol(dt)
     assert rel_err(trim.float(), ref.float()) <= 2e-3
+    # planes per CTA (the grid's granularity) never change the bits: every plane is one warp's work in a fixed order
+    for cg in (2, 4, 8, 16):
+        for mode, want in ((0, ref), (1, trim)):
+            out = torch.full_like(ref, float("nan"))
+            for _ in range(2):
+                ops.xcorr_planar(xp, dk, out=out, mma_mode=mode, channel_group=cg)
+            assert torch.equal(out, want), "channel group %d, mma_mode %d" % (cg, mode)
 
 
 def test_engine_planar_switch_changes_nothing(monkeypatch):
