@@ -265,7 +265,6 @@ template <int VH> struct XpVec;
 template <> struct XpVec<2> { using type = uint32_t; };
 template <> struct XpVec<4> { using type = uint2; };
 template <> struct XpVec<8> { using type = uint4; };
-constexpr int XP_THREADS = XpGeom<XM_CG>::THREADS, XP_SMEM = XpGeom<XM_CG>::SMEM;   // the 16-plane form (tests/cpu_cuda)
 
 __device__ __forceinline__ void xp_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
