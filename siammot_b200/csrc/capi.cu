@@ -30,6 +30,18 @@ bool conv2d_smalln_supported(const smot_conv_desc* d);
 using namespace smot;
 
 namespace smot {
+int sm_count() {
+  static int cached[SMOT_MAX_DEVICES];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= SMOT_MAX_DEVICES) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cached[dev];
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("SMOT_PDL");

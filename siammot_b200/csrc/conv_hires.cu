@@ -254,6 +254,249 @@ __global__ void __launch_bounds__(256) stem7x7_hires_kernel(const HiresArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent forms of the two stride-1 layers (stem 7x7 3->16, level0 3x3 16->16), the widest maps of the network.
+//
+// The kernels above re-stage the weights in every one of 3520 CTAs and fetch every A fragment once per filter row it meets:
+// per warp-tile 170 (stem) / 27 (level0) shared-memory instructions for 56 / 36 MMAs, which is what bounds them (ncu, round 2:
+// 58.6 / 32.3 us against MMA floors of 11 / 7 us and HBM floors of 5.5 / 8.9 us).  Here
+//   * one CTA per SM walks 32x32-pixel output tiles; the input halo of tile i+1 arrives by cp.async under the MMAs of tile i
+//     (two halo buffers, one block barrier per tile);
+//   * the weights live in REGISTERS as ready-made B fragments for the whole kernel (56 / 36 registers), scale / bias likewise;
+//   * a warp owns FOUR output rows: the fragments of input row y are loaded once and meet every (output row, filter row) pair
+//     they belong to -- 10 / 6 row loads instead of 28 / 12;
+//   * the result leaves through a per-warp staging row (no block barrier): 16-byte stores, one output row = one contiguous KB.
+// Every output accumulates its taps in the order of the kernels above (filter row, then k chunk / tap), so the results are
+// bit-identical to theirs.
+// ---------------------------------------------------------------------------------------------
+constexpr int HP_TW = 32, HP_TH = 32, HP_ROWS = 4;     // tile, output rows per warp (8 warps)
+constexpr int HP_OPITCH = 24;                          // halves per staged output pixel (16 + 8: conflict-free fragment stores)
+
+// fragment (16 pixels x 16 channels as two n8 halves) -> warp-private staging row -> 16-byte global stores
+__device__ __forceinline__ void hp_store_row(__half* ost_w, const float (*acc)[2][4], const float* sc, const float* bi, int relu,
+                                             __half* out_row, int out_ld, int ox0, int OW, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v0 = __fadd_rn(__fmul_rn(acc[m][j][2 * h], sc[j * 2]), bi[j * 2]);
+        float v1 = __fadd_rn(__fmul_rn(acc[m][j][2 * h + 1], sc[j * 2 + 1]), bi[j * 2 + 1]);
+        if (relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+        *reinterpret_cast<__half2*>(ost_w + (m * 16 + g + h * 8) * HP_OPITCH + j * 8 + 2 * t) = __floats2half2_rn(v0, v1);
+      }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = i * 32 + lane, px = c >> 1, q = c & 1;
+    if (ox0 + px < OW)
+      *reinterpret_cast<uint4*>(out_row + (size_t)px * out_ld + q * 8) = *reinterpret_cast<const uint4*>(ost_w + px * HP_OPITCH + q * 8);
+  }
+  __syncwarp();
+}
+
+// stem: halo = (32 + 6) rows x 40 pixels x 4 halves, origin (oy0 - 3, ox0 - 4) so that every 16-byte chunk (2 pixels) is
+// aligned and lies entirely inside or outside the image (W even)
+constexpr int SP_IH = HP_TH + 6, SP_IW = 40;
+constexpr int SP_HALO = SP_IH * SP_IW * 4;             // halves per buffer
+constexpr int SP_SMEM = (2 * SP_HALO + 8 * 32 * HP_OPITCH) * 2;
+
+__global__ void __launch_bounds__(256, 1) stem7x7_persist_kernel(const HiresArgs a, int tiles_x, int tiles_y, int ntiles) {
+  extern __shared__ __align__(128) unsigned char hp_raw[];
+  __half* halo = reinterpret_cast<__half*>(hp_raw);                 // [2][SP_IH][SP_IW][4]
+  __half* ost = halo + 2 * SP_HALO;                                 // [8 warps][32][HP_OPITCH]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  pdl_launch_dependents();
+  // ---- constants to registers: B fragments of all 7 filter rows x 2 k-chunks x 2 channel halves
+  // k = s * 4 + c (filter column s, input channel c); s = 7 and c = 3 meet zeros
+  uint32_t bw[7][2][2][2];
+#pragma unroll
+  for (int r = 0; r < 7; ++r)
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int k = kb * 16 + hh * 8 + 2 * t, sx = k >> 2, c = k & 3, n = j * 8 + g;   // (k, k+1) = channels (c, c+1) of column sx
+          const __half* w = a.wt + ((size_t)n * 49 + r * 7 + sx) * 3;
+          const __half z = __float2half(0.f);
+          const __half lo = sx < 7 ? w[c] : z, hi = (sx < 7 && c == 0) ? w[1] : z;        // c is 0 or 2; channel 3 does not exist
+          bw[r][kb][j][hh] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+        }
+  float sc[4], bi[4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int n = j * 8 + 2 * t + e;
+      sc[j * 2 + e] = a.scale ? a.scale[n] : 1.f, bi[j * 2 + e] = a.bias ? a.bias[n] : 0.f;
+    }
+  pdl_wait();  // the weights are constants; the input belongs to the previous kernel
+  const int per_img = tiles_x * tiles_y;
+  auto load_halo = [&](int tile, int buf) {
+    const int img = tile / per_img, rem = tile - img * per_img, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const __half* in = a.in + (size_t)img * a.H * a.W * 4;
+    const int iy0 = ty * HP_TH - 3, ix0 = tx * HP_TW - 4;
+    __half* dst = halo + buf * SP_HALO;
+    for (int i = tid; i < SP_IH * (SP_IW / 2); i += 256) {
+      const int py = i / (SP_IW / 2), pc = i - py * (SP_IW / 2);
+      const int gy = iy0 + py, gx = ix0 + pc * 2;
+      const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      cp_async16(dst + (py * SP_IW + pc * 2) * 4, ok ? in + ((size_t)gy * a.W + gx) * 4 : in, ok);
+    }
+  };
+  int tile = blockIdx.x, cur = 0;
+  if (tile < ntiles) load_halo(tile, 0);
+  for (; tile < ntiles; tile += gridDim.x, cur ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();  // this tile's halo is complete for every thread; everyone is done with the other buffer
+    if (tile + (int)gridDim.x < ntiles) load_halo(tile + gridDim.x, cur ^ 1);
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(halo + cur * SP_HALO);  // 2 words per pixel
+    float acc[HP_ROWS][2][2][4];
+#pragma unroll
+    for (int y = 0; y < HP_ROWS; ++y)
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[y][m][j][e] = 0.f;
+#pragma unroll
+    for (int rho = 0; rho < HP_ROWS + 6; ++rho)      // input row warp*4 + rho of the halo
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        uint32_t af[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          // A(row i, k) = halo[row][pixel 1 + m*16 + i + k/4][k%4]: word = pixel * 2 + k / 2   (+1: the halo starts at ox0 - 4)
+          const int base = ((warp * HP_ROWS + rho) * SP_IW + 1 + m * 16) * 2 + kb * 8 + t;
+          af[m][0] = hw[base + g * 2];
+          af[m][1] = hw[base + (g + 8) * 2];
+          af[m][2] = hw[base + g * 2 + 4];
+          af[m][3] = hw[base + (g + 8) * 2 + 4];
+        }
+#pragma unroll
+        for (int y = 0; y < HP_ROWS; ++y) {
+          const int r = rho - y;
+          if (r >= 0 && r < 7) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              mma_16816(acc[y][m][0], af[m], bw[r][kb][0][0], bw[r][kb][0][1]);
+              mma_16816(acc[y][m][1], af[m], bw[r][kb][1][0], bw[r][kb][1][1]);
+            }
+          }
+        }
+      }
+    const int img = tile / per_img, rem = tile - img * per_img, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    __half* out = a.out + (size_t)img * a.OH * a.OW * a.out_ld;
+#pragma unroll
+    for (int y = 0; y < HP_ROWS; ++y) {
+      const int oy = ty * HP_TH + warp * HP_ROWS + y;
+      if (oy < a.OH)
+        hp_store_row(ost + warp * 32 * HP_OPITCH, acc[y], sc, bi, a.relu, out + ((size_t)oy * a.OW + tx * HP_TW) * a.out_ld, a.out_ld,
+                     tx * HP_TW, a.OW, lane);
+    }
+  }
+}
+
+// level0: 3x3, pad 1, stride 1, 16 -> 16.  Halo = 34 x 34 pixels, 48 B per pixel (32 + 16 pad: conflict-free ldmatrix).
+constexpr int L0_IH = HP_TH + 2, L0_IW = HP_TW + 2, L0_PITCH = 48;
+constexpr int L0_HALO = L0_IH * L0_IW * L0_PITCH;      // bytes per buffer
+constexpr int L0_SMEM = 2 * L0_HALO + 8 * 32 * HP_OPITCH * 2;
+
+__global__ void __launch_bounds__(256, 1) conv3x3_c16_persist_kernel(const HiresArgs a, int tiles_x, int tiles_y, int ntiles) {
+  extern __shared__ __align__(128) unsigned char hp_raw[];
+  unsigned char* halo = hp_raw;                                                  // [2][L0_IH][L0_IW][L0_PITCH]
+  __half* ost = reinterpret_cast<__half*>(hp_raw + 2 * L0_HALO);                 // [8 warps][32][HP_OPITCH]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  pdl_launch_dependents();
+  // B fragments of the 9 taps: b0 = W[n = j*8 + g][tap][2t, 2t+1], b1 = ...[2t+8, 2t+9]   (weights [16][3][3][16])
+  uint32_t bw[9][2][2];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+        bw[tap][j][hh] = *reinterpret_cast<const uint32_t*>(a.wt + ((size_t)(j * 8 + g) * 9 + tap) * 16 + hh * 8 + 2 * t);
+  float sc[4], bi[4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int n = j * 8 + 2 * t + e;
+      sc[j * 2 + e] = a.scale ? a.scale[n] : 1.f, bi[j * 2 + e] = a.bias ? a.bias[n] : 0.f;
+    }
+  pdl_wait();
+  const int per_img = tiles_x * tiles_y;
+  auto load_halo = [&](int tile, int buf) {
+    const int img = tile / per_img, rem = tile - img * per_img, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const __half* in = a.in + (size_t)img * a.H * a.W * a.in_ld;
+    const int iy0 = ty * HP_TH - 1, ix0 = tx * HP_TW - 1;
+    unsigned char* dst = halo + buf * L0_HALO;
+    for (int i = tid; i < L0_IH * L0_IW * 2; i += 256) {
+      const int p = i >> 1, q = i & 1;
+      const int py = p / L0_IW, px = p - py * L0_IW;
+      const int gy = iy0 + py, gx = ix0 + px;
+      const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      cp_async16(dst + p * L0_PITCH + q * 16, ok ? in + ((size_t)gy * a.W + gx) * a.in_ld + q * 8 : in, ok);
+    }
+  };
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
+  int tile = blockIdx.x, cur = 0;
+  if (tile < ntiles) load_halo(tile, 0);
+  for (; tile < ntiles; tile += gridDim.x, cur ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) load_halo(tile + gridDim.x, cur ^ 1);
+    const uint32_t halo_s = hs_smem(halo + cur * L0_HALO);
+    float acc[HP_ROWS][2][2][4];
+#pragma unroll
+    for (int y = 0; y < HP_ROWS; ++y)
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[y][m][j][e] = 0.f;
+#pragma unroll
+    for (int rho = 0; rho < HP_ROWS + 2; ++rho)
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx) {
+        uint32_t af[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+          ldmatrix_x4(halo_s + (((warp * HP_ROWS + rho) * L0_IW + m * 16 + a_row + sx) * L0_PITCH) + a_kh * 16, af[m][0], af[m][1], af[m][2],
+                      af[m][3]);
+#pragma unroll
+        for (int y = 0; y < HP_ROWS; ++y) {
+          const int r = rho - y;
+          if (r >= 0 && r < 3) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              mma_16816(acc[y][m][0], af[m], bw[r * 3 + sx][0][0], bw[r * 3 + sx][0][1]);
+              mma_16816(acc[y][m][1], af[m], bw[r * 3 + sx][1][0], bw[r * 3 + sx][1][1]);
+            }
+          }
+        }
+      }
+    const int img = tile / per_img, rem = tile - img * per_img, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    __half* out = a.out + (size_t)img * a.OH * a.OW * a.out_ld;
+#pragma unroll
+    for (int y = 0; y < HP_ROWS; ++y) {
+      const int oy = ty * HP_TH + warp * HP_ROWS + y;
+      if (oy < a.OH)
+        hp_store_row(ost + warp * 32 * HP_OPITCH, acc[y], sc, bi, a.relu, out + ((size_t)oy * a.OW + tx * HP_TW) * a.out_ld, a.out_ld,
+                     tx * HP_TW, a.OW, lane);
+    }
+  }
+}
+
 // ---- dispatch ---------------------------------------------------------------------------------
 static bool common_ok(const smot_conv_desc* d) {
   return d->in_dtype == SMOT_F16 && d->out_dtype == SMOT_F16 && !d->residual && d->out_ld % 8 == 0 &&
@@ -286,6 +529,25 @@ int conv2d_hires(const smot_conv_desc* d, cudaStream_t st) {
   a.in = (const __half*)d->in, a.wt = (const __half*)d->weight, a.scale = d->scale, a.bias = d->bias, a.out = (__half*)d->out;
   a.H = d->H, a.W = d->W, a.in_ld = d->in_ld, a.OH = d->OH, a.OW = d->OW, a.out_ld = d->out_ld, a.relu = d->relu;
   if (d->batch == 0) return SMOT_OK;
+  // persistent forms (stride-1 layers): when there is at least one 32x32 tile per SM.  SMOT_HIRES_PERSIST=0 keeps the
+  // per-tile kernels (A/B; the results are the same bits), =2 takes the persistent ones whatever the size (tests).
+  const bool stem = d->KH == 7, c16 = d->KH == 3 && d->stride == 1 && d->Cin == 16 && d->Cout == 16;
+  if (stem || c16) {
+    const char* e = getenv("SMOT_HIRES_PERSIST");
+    const int mode = e ? atoi(e) : 1;
+    const int tx = ceil_div(a.OW, HP_TW), ty = ceil_div(a.OH, HP_TH), ntiles = tx * ty * d->batch, sms = sm_count();
+    if (mode != 0 && (mode == 2 || ntiles >= sms) && (!stem || a.W % 2 == 0)) {
+      const int grid = ntiles < sms ? ntiles : sms;
+      if (stem) {
+        launch_pdl(stem7x7_persist_kernel, dim3(grid), dim3(256), SP_SMEM, st, a, tx, ty, ntiles);
+      } else {
+        SMOT_ENSURE_SMEM(conv3x3_c16_persist_kernel, L0_SMEM, "smot_conv2d(hires)");
+        launch_pdl(conv3x3_c16_persist_kernel, dim3(grid), dim3(256), L0_SMEM, st, a, tx, ty, ntiles);
+      }
+      SMOT_CHECK_LAUNCH("smot_conv2d(hires, persistent)");
+      return SMOT_OK;
+    }
+  }
   if (d->KH == 7) {
     dim3 grid(ceil_div(a.OW, ST_TW), ceil_div(a.OH, ST_TH), d->batch);
     launch_pdl(stem7x7_hires_kernel, grid, dim3(256), 0, st, a);

@@ -250,16 +250,19 @@ struct XpGeom {
   static constexpr int WARPS = CG;                              // MMA warps (one plane each)
   static constexpr int THREADS = (CG + 1) * 32;                 // + 1 copy warp
   static constexpr int MMA_THREADS = CG * 32;
-  static constexpr int X_HALVES = CG * XM_CSTRIDE, K_HALVES = CG * XM_KPLANE;
-  static constexpr int BAR_OFF = (X_HALVES + K_HALVES) * 2;     // mbarrier behind the two staging areas
-  static constexpr int SMEM = BAR_OFF + 16;
-  static constexpr int COPIES = CG >= 4 ? 4 : CG;               // bulk copies per CTA
+  static constexpr int KPLANE_I = 8 * 2 * 16 * 4;               // halves per channel of the pair-interleaved template image (mode 1)
+  static constexpr int X_HALVES = CG * XM_CSTRIDE, K_HALVES = CG * KPLANE_I;   // the staging area fits either template image
+  static constexpr int BAR_OFF = (X_HALVES + K_HALVES) * 2;     // mbarriers behind the two staging areas
+  static constexpr int COPIES = CG >= 4 ? CG / 2 : CG;          // bulk copies per CTA (2 planes each), one mbarrier per copy
+  static constexpr int PLANES_PER_COPY = CG / COPIES;
+  static constexpr int SMEM = BAR_OFF + 8 * COPIES;
   static constexpr int VH = CG < 8 ? CG : 8;                    // halves per template / result vector
   static constexpr int NCH = CG / VH;                           // vectors per position
   static constexpr int K_ITEMS = 15 * 15 * NCH;                 // template vectors per CTA
   static constexpr int K_ITERS = (K_ITEMS + MMA_THREADS - 1) / MMA_THREADS;
+  static_assert(KPLANE_I >= XM_KPLANE, "staging area");
   static_assert(BAR_OFF % 8 == 0, "mbarrier alignment");
-  static_assert(CG % COPIES == 0 && ((CG / COPIES) * XM_CSTRIDE * 2) % 16 == 0, "bulk copy size must be a 16-byte multiple");
+  static_assert(CG % COPIES == 0 && (PLANES_PER_COPY * XM_CSTRIDE * 2) % 16 == 0, "bulk copy size must be a 16-byte multiple");
 };
 template <int VH> struct XpVec;
 template <> struct XpVec<2> { using type = uint32_t; };
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
   extern __shared__ __align__(128) unsigned char xp_raw[];
   __half* xT = reinterpret_cast<__half*>(xp_raw);     // [CG][CSTRIDE]: filled by the bulk copies
   __half* kz = xT + G::X_HALVES;                      // [CG][TT][2][KROW]
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(xp_raw + G::BAR_OFF);
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(xp_raw + G::BAR_OFF);   // COPIES mbarriers, 8 bytes apart
   const int n = blockIdx.y, c0 = blockIdx.x * CG;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool copy_warp = warp == G::WARPS;
@@ -345,24 +348,27 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
     uint4* kz4 = reinterpret_cast<uint4*>(kz);
     for (int i = tid; i < G::K_HALVES / 8; i += G::MMA_THREADS) kz4[i] = make_uint4(0u, 0u, 0u, 0u);
   } else if (lane == 0) {
-    xp_mbar_init(bar, 1);
+#pragma unroll
+    for (int i = 0; i < G::COPIES; ++i) xp_mbar_init(bar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  __syncthreads();  // template zero fill complete; the mbarrier is initialised for every thread
+  __syncthreads();  // template zero fill complete; the mbarriers are initialised for every thread
   XP_STAMP(1);
   if (copy_warp) {
-    // ---- window: wait for the producer of the planes, then the bulk copies onto one mbarrier
+    // ---- window: wait for the producer of the planes, then one bulk copy per plane pair, each onto its own mbarrier:
+    // a warp starts as soon as ITS plane is there, the tensor pipe is busy from the first arrival on
     pdl_wait();
     XP_STAMP(2);
     if (lane == 0) {
-      constexpr uint32_t BYTES = (CG / G::COPIES) * XM_CSTRIDE * 2;
+      constexpr uint32_t BYTES = G::PLANES_PER_COPY * XM_CSTRIDE * 2;
       const __half* src = xp + ((size_t)n * C + c0) * XM_CSTRIDE;
-      xp_mbar_expect_tx(bar, BYTES * G::COPIES);
 #pragma unroll
-      for (int i = 0; i < G::COPIES; ++i)
+      for (int i = 0; i < G::COPIES; ++i) {
+        xp_mbar_expect_tx(bar + 8 * i, BYTES);
         xp_bulk_g2s((uint32_t)__cvta_generic_to_shared(xT) + i * BYTES, reinterpret_cast<const unsigned char*>(src) + (size_t)i * BYTES,
-                    BYTES, bar);
+                    BYTES, bar + 8 * i);
+      }
     }
   } else {
 #pragma unroll
@@ -371,18 +377,29 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
       if (i < G::K_ITEMS) {
         const int p = i / G::NCH, q = i % G::NCH, u = p / TT, v = p % TT;
         const __half* h = reinterpret_cast<const __half*>(&kv[it]);
-        __half* dst = kz + (q * 8) * XM_KPLANE + u * 2 * XM_KROW + 8 + v;
+        if constexpr (MMA_MODE == 0) {
+          __half* dst = kz + (q * 8) * XM_KPLANE + u * 2 * XM_KROW + 8 + v;
 #pragma unroll
-        for (int e = 0; e < G::VH; ++e) {
-          dst[e * XM_KPLANE] = h[e];                  // copy 0: K[u][v] at half 8 + v
-          dst[e * XM_KPLANE + XM_KROW - 1] = h[e];    // copy 1: K[u][v] at half 7 + v
+          for (int e = 0; e < G::VH; ++e) {
+            dst[e * XM_KPLANE] = h[e];                  // copy 0: K[u][v] at half 8 + v
+            dst[e * XM_KPLANE + XM_KROW - 1] = h[e];    // copy 1: K[u][v] at half 7 + v
+          }
+        } else {
+          // pair-interleaved image [pair = u & 7][copy][word 0..15][row u < 8 | row u >= 8][2 halves]: the B words of template
+          // rows u and u + 8 (processed together) are the two halves of ONE 64-bit shared-memory word
+          const int slot = u >> 3, h0 = 8 + v, h1 = 7 + v;
+          __half* dst = kz + (q * 8) * G::KPLANE_I + (u & 7) * 128 + slot * 2;
+#pragma unroll
+          for (int e = 0; e < G::VH; ++e) {
+            dst[e * G::KPLANE_I + (h0 >> 1) * 4 + (h0 & 1)] = h[e];         // copy 0
+            dst[e * G::KPLANE_I + 64 + (h1 >> 1) * 4 + (h1 & 1)] = h[e];    // copy 1
+          }
         }
       }
     }
     XP_STAMP(2);
-    pdl_wait();  // the result stores below must not pass the predecessor either (back-to-back launches share `out`)
   }
-  __syncthreads();  // templates staged
+  __syncthreads();  // templates staged (nothing so far depends on the predecessor: under PDL this all ran beside its tail)
   XP_STAMP(3);
   float acc[2][4];
   const int g = lane >> 2, t = lane & 3;
@@ -390,7 +407,8 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
   if (!copy_warp) {
     // bounded wait for the windows (wall clock, 2 s): a mis-programmed copy must fail the launch, never hang the GPU
     unsigned long long t_start = 0;
-    for (uint32_t spin = 0; !xp_mbar_try_wait(bar, 0); ++spin) {
+    const uint32_t my_bar = bar + 8 * (warp / G::PLANES_PER_COPY);
+    for (uint32_t spin = 0; !xp_mbar_try_wait(my_bar, 0); ++spin) {
       if ((spin & 255u) == 255u) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
@@ -406,12 +424,12 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
     const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
     const int par = g & 1;
     const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(xT + c * XM_CSTRIDE + a_row * XM_PITCH + a_kh * 8);
-    const uint32_t* kzw = reinterpret_cast<const uint32_t*>(kz + c * XM_KPLANE + par * XM_KROW) + ((8 + 2 * t - g - par) >> 1);
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
     if constexpr (MMA_MODE == 0) {
+      const uint32_t* kzw = reinterpret_cast<const uint32_t*>(kz + c * XM_KPLANE + par * XM_KROW) + ((8 + 2 * t - g - par) >> 1);
 #pragma unroll 5
       for (int u = 0; u < TT; ++u) {
         const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
@@ -424,9 +442,10 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
         xm_mma(acc[1], af, k8, k16);
       }
     } else {
+      // B words of a row pair: three 64-bit loads (word W0, W0 + 4, W0 + 8 of the lane's copy; .x = row u, .y = row u + 8)
+      const uint2* kzp = reinterpret_cast<const uint2*>(kz + c * G::KPLANE_I + par * 64) + ((8 + 2 * t - g - par) >> 1);
       // one template row: window rows [u, u+16) as fragments lo (cols 0..15) / hi (cols 16..31)
-      auto row_step = [&](const uint32_t* lo, const uint32_t* hi, int u) {
-        const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
+      auto row_step = [&](const uint32_t* lo, const uint32_t* hi, uint32_t k0, uint32_t k8, uint32_t k16) {
         xm_mma(acc[0], lo, k0, k8);              // out cols 0..7  <- window cols 0..15
         xm_mma_k8(acc[1], lo[2], lo[3], k0);     // out cols 8..15 <- window cols 8..15   (cols 0..7 meet no tap)
         xm_mma_k8(acc[0], hi[0], hi[1], k16);    // out cols 0..7  <- window cols 16..23  (cols 24..31 meet no tap)
@@ -443,14 +462,16 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
         lo2[0] = lo[1], lo2[2] = lo[3], hi2[0] = hi[1], hi2[2] = hi[3];
         xm_ldmatrix_x2(a_x2 + (uint32_t)(u * XM_PITCH * 2), lo2[1], lo2[3]);
         xm_ldmatrix_x2(a_x2 + (uint32_t)(u * XM_PITCH * 2 + 32), hi2[1], hi2[3]);
-        row_step(lo, hi, u);
-        row_step(lo2, hi2, u + 8);
+        const uint2 k0 = kzp[u * 32], k8 = kzp[u * 32 + 4], k16 = kzp[u * 32 + 8];
+        row_step(lo, hi, k0.x, k8.x, k16.x);
+        row_step(lo2, hi2, k0.y, k8.y, k16.y);
       }
       {
         uint32_t lo[4], hi[4];
         xm_ldmatrix_x4(a_s + (uint32_t)(7 * XM_PITCH * 2), lo[0], lo[1], lo[2], lo[3]);
         xm_ldmatrix_x4(a_s + (uint32_t)(7 * XM_PITCH * 2 + 32), hi[0], hi[1], hi[2], hi[3]);
-        row_step(lo, hi, 7);
+        const uint2 k0 = kzp[7 * 32], k8 = kzp[7 * 32 + 4], k16 = kzp[7 * 32 + 8];
+        row_step(lo, hi, k0.x, k8.x, k16.x);
       }
     }
     XP_STAMP(5);
@@ -466,6 +487,7 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
   __syncthreads();
   XP_STAMP(6);
   if (!copy_warp) {
+    pdl_wait();  // the result stores must not pass the predecessor (back-to-back launches share `out`); long returned by now
     // O*O positions x NCH result vectors: a warp takes 32 consecutive positions of one vector column
 #pragma unroll
     for (int i = tid; i < O * O * G::NCH; i += G::MMA_THREADS) {
@@ -723,14 +745,18 @@ static bool xcorr_planar_trimmed() {
   return on;
 }
 
-// channels per CTA: 4 by default (measured ladder in DESIGN.md section 5.2); developer switch SMOT_XCORR_CG (read once)
-static int xcorr_planar_cg() {
-  static const int cg = [] {
+// planes per CTA.  Measured ladder (B200, CUDA-graph replay, us per launch; profiles/xcorr_lab_r02h.json):
+//   30 tracks x 128 ch (3840 planes):  16: 6.15   8: 7.55   4: 7.93   2: 9.71
+//   80 tracks x 128 ch (10240 planes): 16: 14.31  8: 13.33  4: 15.91  2: 22.18       30 x 256 ch: 16: 11.60  8: 10.65
+// i.e. 16 while all CTAs are resident at once (two per SM), 8 beyond that.  Developer switch SMOT_XCORR_CG (read once).
+static int xcorr_planar_cg(int planes) {
+  static const int forced = [] {
     const char* e = getenv("SMOT_XCORR_CG");
     const int v = e ? atoi(e) : 0;
-    return (v == 2 || v == 4 || v == 8 || v == 16) ? v : 4;
+    return (v == 2 || v == 4 || v == 8 || v == 16) ? v : 0;
   }();
-  return cg;
+  if (forced) return forced;
+  return planes <= 16 * 2 * sm_count() ? 16 : 8;
 }
 
 extern "C" int smot_xcorr_planar(const void* x_planar, const void* k, void* out, int n, int channels, void* stream) {
@@ -739,7 +765,7 @@ extern "C" int smot_xcorr_planar(const void* x_planar, const void* k, void* out,
 
 extern "C" int smot_xcorr_planar_mode(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode,
                                       void* stream) {
-  int cg = xcorr_planar_cg();
+  int cg = xcorr_planar_cg(n * channels);
   while (cg > 2 && channels % cg) cg >>= 1;
   return smot_xcorr_planar_cfg(x_planar, k, out, n, channels, mma_mode, cg, stream);
 }

@@ -242,3 +242,67 @@ def build_xcorr():
 
 if __name__ == "__main__":
     print(build())
+
+
+OUT_HIRES = os.path.join(HERE, "_hires_cpu.so")
+
+
+def generate_hires():
+    """csrc/conv_hires.cu: the per-tile kernels of the stem / level0 (validated on the B200 against the oracle) and their
+    persistent forms, over shim_tc.h (cp.async = immediate copy or zero fill, ldmatrix / mma.sync emulated).  The persistent
+    kernels must reproduce the per-tile ones bit for bit."""
+    src = open(os.path.join(CSRC, "conv_hires.cu")).read()
+    body = src[src.index("template <int CIN, int COUT, int STRIDE>\nstruct Hires3"):src.index("// ---- dispatch")]
+    args = re.search(r"struct HiresArgs \{.*?\};", src, re.S).group(0)
+    body = body.replace("extern __shared__ __align__(128) unsigned char hs_raw[];", "unsigned char* hs_raw = cpu_dynamic_smem;")
+    body = body.replace("extern __shared__ __align__(128) unsigned char hp_raw[];", "unsigned char* hp_raw = cpu_dynamic_smem;")
+    body = body.replace("__shared__ __align__(16) __half ", "alignas(16) static __half ")
+    assert "asm" not in body and "extern __shared__" not in body
+    parts = ['#include "shim_tc.h"', "namespace smot {", args, """
+inline float __fadd_rn(float a, float b) { return a + b; }   // -ffp-contract=off: plain IEEE operations
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline uint32_t hs_smem(const void* p) { return cpu_smem_offset(p); }
+inline void cp_async16(void* dst, const void* src, bool valid) { if (valid) std::memcpy(dst, src, 16); else std::memset(dst, 0, 16); }
+inline void cp_async8(void* dst, const void* src, bool valid) { if (valid) std::memcpy(dst, src, 8); else std::memset(dst, 0, 8); }
+inline void cp_async_wait_all() {}
+inline void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) { xm_ldmatrix_x4(addr, r0, r1, r2, r3); }
+inline void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) { xm_mma(c, a, b0, b1); }
+""", body, "}  // namespace smot", """
+using namespace smot;
+static HiresArgs hires_args(const void* in, const void* wt, const float* scale, const float* bias, void* out, int H, int W, int in_ld,
+                            int out_ld, int relu) {
+  HiresArgs a;
+  a.in = (const __half*)in, a.wt = (const __half*)wt, a.scale = scale, a.bias = bias, a.out = (__half*)out;
+  a.H = H, a.W = W, a.in_ld = in_ld, a.OH = H, a.OW = W, a.out_ld = out_ld, a.relu = relu;
+  return a;
+}
+extern "C" void cpu_stem(const void* in, const void* wt, const float* scale, const float* bias, void* out, int batch, int H, int W,
+                         int out_ld, int relu, int persistent_ctas) {
+  const HiresArgs a = hires_args(in, wt, scale, bias, out, H, W, 4, out_ld, relu);
+  if (persistent_ctas > 0) {
+    const int tx = (W + HP_TW - 1) / HP_TW, ty = (H + HP_TH - 1) / HP_TH;
+    cpu_launch_warps(dim3(persistent_ctas), dim3(256), [&] { stem7x7_persist_kernel(a, tx, ty, tx * ty * batch); });
+  } else {
+    cpu_launch_warps(dim3((W + ST_TW - 1) / ST_TW, (H + ST_TH - 1) / ST_TH, batch), dim3(256), [&] { stem7x7_hires_kernel(a); });
+  }
+}
+extern "C" void cpu_conv3x3_c16(const void* in, const void* wt, const float* scale, const float* bias, void* out, int batch, int H,
+                                int W, int in_ld, int out_ld, int relu, int persistent_ctas) {
+  const HiresArgs a = hires_args(in, wt, scale, bias, out, H, W, in_ld, out_ld, relu);
+  if (persistent_ctas > 0) {
+    const int tx = (W + HP_TW - 1) / HP_TW, ty = (H + HP_TH - 1) / HP_TH;
+    cpu_launch_warps(dim3(persistent_ctas), dim3(256), [&] { conv3x3_c16_persist_kernel(a, tx, ty, tx * ty * batch); });
+  } else {
+    using C = Hires3<16, 16, 1>;
+    cpu_launch_warps(dim3((W + C::TW - 1) / C::TW, (H + C::TH - 1) / C::TH, batch), dim3(256), [&] { conv3x3_hires_kernel<16, 16, 1>(a); });
+  }
+}
+"""]
+    path = os.path.join(HERE, "_hires_cpu.cpp")
+    with open(path, "w") as f:
+        f.write("// GENERATED by tests/cpu_cuda/cpu_cuda_build.py from siammot_b200/csrc/conv_hires.cu -- do not edit\n" + "\n".join(parts) + "\n")
+    return path
+
+
+def build_hires():
+    return _compile(generate_hires(), OUT_HIRES, ["-I", CUDA_INCLUDE])

@@ -57,7 +57,7 @@ using std::max;
 using std::min;
 
 // dynamic shared memory of the block that is running (blocks are sequential)
-alignas(128) unsigned char cpu_dynamic_smem[96 * 1024];
+alignas(128) unsigned char cpu_dynamic_smem[160 * 1024];
 
 namespace smot {
 // csrc/common.cuh, host restatement of what the simple kernels use

@@ -101,16 +101,18 @@ inline void xm_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   for (int e = 0; e < 4; ++e) c[e] = d[e];
 }
 
-// one mbarrier phase: `pending` transaction bytes after the arming arrive
-static std::atomic<long> cpu_mbar_pending{0};
-static std::atomic<int> cpu_mbar_armed{0};
-inline void xp_mbar_init(uint32_t, uint32_t) { cpu_mbar_pending = 0, cpu_mbar_armed = 0; }
-inline void xp_mbar_expect_tx(uint32_t, uint32_t bytes) { cpu_mbar_pending += (long)bytes, cpu_mbar_armed = 1; }
-inline bool xp_mbar_try_wait(uint32_t, uint32_t) { return cpu_mbar_armed.load() == 1 && cpu_mbar_pending.load() == 0; }
-inline void xp_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t) {
+// mbarriers (one phase each), keyed by their shared-memory address: `pending` transaction bytes after the arming arrive
+struct CpuMbar { std::atomic<long> pending{0}; std::atomic<int> armed{0}; };
+static CpuMbar cpu_mbars[64];
+static inline CpuMbar& cpu_mbar(uint32_t bar) { return cpu_mbars[(bar >> 3) & 63u]; }
+inline void xp_mbar_init(uint32_t bar, uint32_t) { cpu_mbar(bar).pending = 0, cpu_mbar(bar).armed = 0; }
+inline void xp_mbar_expect_tx(uint32_t bar, uint32_t bytes) { cpu_mbar(bar).pending += (long)bytes, cpu_mbar(bar).armed = 1; }
+inline bool xp_mbar_try_wait(uint32_t bar, uint32_t) { return cpu_mbar(bar).armed.load() == 1 && cpu_mbar(bar).pending.load() == 0; }
+inline void xp_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   if ((dst & 15u) || ((uintptr_t)src & 15u) || (bytes & 15u)) { std::fprintf(stderr, "cp.async.bulk: misaligned operand\n"); std::abort(); }
+  if (bar & 7u) { std::fprintf(stderr, "mbarrier: misaligned\n"); std::abort(); }
   std::memcpy(cpu_dynamic_smem + dst, src, bytes);
-  cpu_mbar_pending -= (long)bytes;
+  cpu_mbar(bar).pending -= (long)bytes;
 }
 
 }  // namespace smot

@@ -240,3 +240,51 @@ def test_deform_im2col_kernel_source_matches_torchvision(cpu_kernels, cpu_xcorr,
         got = torch.einsum("hwk,ok->ohw", cols[0, :, :, :9 * Cc].float(), wq)[None]
         want = ref if dtype == torch.float32 else deform_conv2d(x.half().float(), off, w.half().float(), None, stride=stride, padding=1)
         assert float((got - want).abs().max()) <= tol_ * float(want.abs().max())
+
+
+@pytest.fixture(scope="module")
+def cpu_hires():
+    import cpu_cuda_build as cpu_build
+    if not os.path.exists(os.path.join(cpu_build.CUDA_INCLUDE, "cuda_fp16.h")):
+        pytest.skip("CUDA headers not found (cuda_fp16.h is compiled in host mode)")
+    return C.CDLL(cpu_build.build_hires())
+
+
+@pytest.mark.parametrize("H,W,batch,ctas", [(64, 96, 1, 4), (40, 70, 2, 3)])
+def test_persistent_hires_kernels_reproduce_the_per_tile_kernels(cpu_hires, H, W, batch, ctas):
+    """csrc/conv_hires.cu: stem 7x7 3->16 and level0 3x3 16->16.  The per-tile kernels are validated on the B200 (oracle bar);
+    here they also meet torch's convolution, which validates the emulation, and the persistent forms (weights as register-resident
+    B fragments, a warp owns four output rows, double-buffered halo, several tiles per CTA, ragged right / bottom tiles, two
+    images) must equal them bit for bit -- garbage in the output pitch's unused channels stays untouched."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(H * W + batch)
+    # ---- stem
+    x = torch.randn(batch, 3, H, W, generator=g).half()
+    w = (torch.randn(16, 3, 7, 7, generator=g) / 12.).half()
+    scale, bias = torch.rand(16, generator=g) + 0.5, torch.randn(16, generator=g) * 0.1
+    x_nhwc = torch.zeros(batch, H, W, 4, dtype=torch.float16)
+    x_nhwc[..., :3] = x.permute(0, 2, 3, 1)
+    w_k = w.permute(0, 2, 3, 1).contiguous()                                  # [Cout][KH][KW][Cin]
+    ref = F.relu(F.conv2d(x.float(), w.float(), padding=3) * scale[None, :, None, None] + bias[None, :, None, None])
+    outs = []
+    for persistent in (0, ctas):
+        out = torch.full((batch, H, W, 24), 5.0, dtype=torch.float16)          # channel pitch 24: 8 foreign channels per pixel
+        cpu_hires.cpu_stem(p(x_nhwc), p(w_k), p(scale), p(bias), p(out), batch, H, W, 24, 1, persistent)
+        assert float((out[..., 16:] - 5.0).abs().max()) == 0.0
+        outs.append(out[..., :16].clone())
+    err = float((outs[0].permute(0, 3, 1, 2).float() - ref).abs().max() / ref.abs().max())
+    assert err <= 2e-3, "emulated per-tile stem vs torch: %g" % err
+    assert torch.equal(outs[0], outs[1])
+    # ---- level0 on the stem's output (input pitch 24, output pitch 16)
+    w0 = (torch.randn(16, 16, 3, 3, generator=g) / 12.).half()
+    x0 = torch.full((batch, H, W, 24), 7.0, dtype=torch.float16)
+    x0[..., :16] = outs[0]
+    ref0 = F.conv2d(outs[0].permute(0, 3, 1, 2).float(), w0.float(), padding=1) * scale[None, :, None, None] + bias[None, :, None, None]
+    res, w0_k = [], w0.permute(0, 2, 3, 1).contiguous()
+    for persistent in (0, ctas):
+        out = torch.zeros((batch, H, W, 16), dtype=torch.float16)
+        cpu_hires.cpu_conv3x3_c16(p(x0), p(w0_k), p(scale), p(bias), p(out), batch, H, W, 24, 16, 0, persistent)
+        res.append(out)
+    err = float((res[0].permute(0, 3, 1, 2).float() - ref0).abs().max() / ref0.abs().max())
+    assert err <= 2e-3, "emulated per-tile level0 vs torch: %g" % err
+    assert torch.equal(res[0], res[1])

@@ -503,6 +503,38 @@ def test_conv2d_hires_kernels(case):
     assert rel_err(nchw(got), nchw(got_simt)) <= 1e-3
 
 
+@pytest.mark.parametrize("case", [("stem", 3, 16, 7, 2, 704, 1280), ("level0", 16, 16, 3, 1, 352, 640), ("stem", 3, 16, 7, 1, 100, 70),
+                                  ("level0", 16, 16, 3, 2, 75, 130)])
+def test_conv2d_hires_persistent_kernels(case, monkeypatch):
+    """Persistent forms of the stem / level0 kernels (one CTA per SM walks 32x32 tiles, weights as register-resident B fragments,
+    four output rows per warp, double-buffered halo): taken when there is a tile per SM, forced here for the ragged small
+    shapes.  Bit-identical to the per-tile kernels (SMOT_HIRES_PERSIST=0); torch fp32 within the fp16 bar."""
+    name, Cin, Cout, k, batch, H, W = case
+    g = torch.Generator().manual_seed(len(name) + H)
+    dt = torch.float16
+    x = q(torch.randn(batch, Cin, H, W, generator=g), dt)
+    w = q(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k), dt)
+    scale, bias = 0.5 + torch.rand(Cout, generator=g), torch.randn(Cout, generator=g)
+    ref = F.relu(F.conv2d(x, w, None, 1, k // 2) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    if Cin == 3:
+        buf = torch.zeros(batch, H, W, 4, dtype=dt, device=DEV)
+        buf[..., :3] = nhwc(x, dt)
+        dx = buf[..., :3]
+    else:
+        dx = nhwc(x, dt)
+    args = (dx, ohwi(w, dt), scale.to(DEV), bias.to(DEV), None, 1, k // 2, True)
+    monkeypatch.setenv("SMOT_HIRES_PERSIST", "0")
+    per_tile = ops().conv2d(*args)
+    monkeypatch.setenv("SMOT_HIRES_PERSIST", "2")
+    for _ in range(2):                               # back-to-back launches chain through PDL
+        got = ops().conv2d(*args)
+    torch.cuda.synchronize()
+    assert torch.equal(got, per_tile)
+    assert rel_err(nchw(got), ref) <= 2e-3
+    monkeypatch.delenv("SMOT_HIRES_PERSIST")
+    assert torch.equal(ops().conv2d(*args), per_tile)   # the default rule, whichever kernel it picks
+
+
 @pytest.mark.parametrize("mode", ["16", "10"])
 def test_conv2d_tcgen05_halo_variant(mode, monkeypatch):
     """Developer variant of the 3x3 tcgen05 kernel (SMOT_TC_HALO): the input halo of an 8x16 tile stays in shared
