@@ -452,7 +452,9 @@ def run_ours(args):
     achieved = xc_bytes / (xc_us * 1e-6) / 1e9 if xc_us > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(REPO, "profiles", "xcorr_traffic.json"))).get(getattr(tp, "xcorr_kernel", "").split(" ")[0])
+        # per launch, from one `ncu --set full` capture of the named kernel at this (tracks x channels); null when none is committed
+        table = json.load(open(os.path.join(REPO, "profiles", "xcorr_traffic.json")))
+        traffic = table.get(getattr(tp, "xcorr_kernel", "").split("<")[0].split(" ")[0], {}).get("%dx%d" % (N_TRACKS, h.eng.C))
     except Exception:
         pass
     fps = world * args.steps / (ms * 1e-3)

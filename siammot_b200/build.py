@@ -45,10 +45,12 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, out))
         if verbose:
             print(out)
-    cmd = [NVCC, "-shared", "-cudart", "shared", "-o", OUT] + objs
+    tmp = OUT + ".tmp"   # link beside the target, then rename: a reader (or a repository snapshot) never sees a half-written library
+    cmd = [NVCC, "-shared", "-cudart", "shared", "-o", tmp] + objs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout)
+    os.replace(tmp, OUT)
     return OUT
 
 

@@ -497,6 +497,128 @@ __global__ void __launch_bounds__(256, 1) conv3x3_c16_persist_kernel(const Hires
   }
 }
 
+// level1 (16 -> 32) and level2.tree1.conv1 (32 -> 64): 3x3, pad 1, STRIDE 2.  Adjacent output rows share one input row in
+// three, so there is no fragment reuse to gain; what the persistent form removes is the per-CTA weight staging and the B-operand
+// ldmatrix traffic (2 of the 3 shared-memory instructions per MMA pair): weights as register-resident B fragments (72 / 144
+// registers; for 64 output channels two warps split them), double-buffered halo, per-warp result staging.  Tile = (8 / NW) output
+// rows x 32 columns, warp = (row, 32-channel slice).  Same accumulation order as conv3x3_hires_kernel: bit-identical.
+template <int CIN, int COUT>
+struct S2Persist {
+  static constexpr int NW = COUT / 32;                 // warps along the output channels
+  static constexpr int TH = 8 / NW, TW = 32;
+  static constexpr int IH = (TH - 1) * 2 + 3, IW = (TW - 1) * 2 + 3;
+  static constexpr int PITCH = CIN * 2 + 16;           // bytes per halo pixel
+  static constexpr int HALO = ((IH * IW * PITCH + 127) / 128) * 128;
+  static constexpr int OPITCH = 40;                    // halves per staged pixel of a warp's 32-channel slice
+  static constexpr int SMEM = 2 * HALO + 8 * 32 * OPITCH * 2;
+  static constexpr int KC = CIN / 16;
+  static_assert(COUT == 32 || COUT == 64, "32-channel slices");
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256, 1) conv3x3_s2_persist_kernel(const HiresArgs a, int tiles_x, int tiles_y, int ntiles) {
+  using C = S2Persist<CIN, COUT>;
+  extern __shared__ __align__(128) unsigned char hp_raw[];
+  unsigned char* halo = hp_raw;
+  __half* ost = reinterpret_cast<__half*>(hp_raw + 2 * C::HALO);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int oy_l = warp / C::NW, nw = warp % C::NW;   // output row of the tile, 32-channel slice
+  pdl_launch_dependents();
+  uint32_t bw[9][C::KC][4][2];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int kc = 0; kc < C::KC; ++kc)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+          bw[tap][kc][j][hh] =
+              *reinterpret_cast<const uint32_t*>(a.wt + ((size_t)(nw * 32 + j * 8 + g) * 9 + tap) * CIN + kc * 16 + hh * 8 + 2 * t);
+  float sc[8], bi[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int n = nw * 32 + j * 8 + 2 * t + e;
+      sc[j * 2 + e] = a.scale ? a.scale[n] : 1.f, bi[j * 2 + e] = a.bias ? a.bias[n] : 0.f;
+    }
+  pdl_wait();
+  const int per_img = tiles_x * tiles_y;
+  auto load_halo = [&](int tile, int buf) {
+    const int img = tile / per_img, rem = tile - img * per_img, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const __half* in = a.in + (size_t)img * a.H * a.W * a.in_ld;
+    const int iy0 = ty * C::TH * 2 - 1, ix0 = tx * C::TW * 2 - 1;
+    unsigned char* dst = halo + buf * C::HALO;
+    constexpr int PCH = CIN / 8;
+    for (int i = tid; i < C::IH * C::IW * PCH; i += 256) {
+      const int p = i / PCH, q = i - p * PCH;
+      const int py = p / C::IW, px = p - py * C::IW;
+      const int gy = iy0 + py, gx = ix0 + px;
+      const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      cp_async16(dst + p * C::PITCH + q * 16, ok ? in + ((size_t)gy * a.W + gx) * a.in_ld + q * 8 : in, ok);
+    }
+  };
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
+  __half* ost_w = ost + warp * 32 * C::OPITCH;
+  int tile = blockIdx.x, cur = 0;
+  if (tile < ntiles) load_halo(tile, 0);
+  for (; tile < ntiles; tile += gridDim.x, cur ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) load_halo(tile + gridDim.x, cur ^ 1);
+    const uint32_t halo_s = hs_smem(halo + cur * C::HALO);
+    float acc[2][4][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx)
+#pragma unroll
+        for (int kc = 0; kc < C::KC; ++kc) {
+          uint32_t af[2][4];
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+            ldmatrix_x4(halo_s + ((oy_l * 2 + r) * C::IW + (m * 16 + a_row) * 2 + sx) * C::PITCH + kc * 32 + a_kh * 16, af[m][0], af[m][1],
+                        af[m][2], af[m][3]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int m = 0; m < 2; ++m) mma_16816(acc[m][j], af[m], bw[r * 3 + sx][kc][j][0], bw[r * 3 + sx][kc][j][1]);
+        }
+    const int img = tile / per_img, rem = tile - img * per_img, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const int oy = ty * C::TH + oy_l, ox0 = tx * C::TW;
+    if (oy < a.OH) {
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float v0 = __fadd_rn(__fmul_rn(acc[m][j][2 * h], sc[j * 2]), bi[j * 2]);
+            float v1 = __fadd_rn(__fmul_rn(acc[m][j][2 * h + 1], sc[j * 2 + 1]), bi[j * 2 + 1]);
+            if (a.relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+            *reinterpret_cast<__half2*>(ost_w + (m * 16 + g + h * 8) * C::OPITCH + j * 8 + 2 * t) = __floats2half2_rn(v0, v1);
+          }
+      __syncwarp();
+      __half* out_row = a.out + (((size_t)img * a.OH + oy) * a.OW + ox0) * a.out_ld + nw * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = i * 32 + lane, px = c >> 2, q = c & 3;
+        if (ox0 + px < a.OW)
+          *reinterpret_cast<uint4*>(out_row + (size_t)px * a.out_ld + q * 8) = *reinterpret_cast<const uint4*>(ost_w + px * C::OPITCH + q * 8);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // ---- dispatch ---------------------------------------------------------------------------------
 static bool common_ok(const smot_conv_desc* d) {
   return d->in_dtype == SMOT_F16 && d->out_dtype == SMOT_F16 && !d->residual && d->out_ld % 8 == 0 &&
@@ -543,6 +665,25 @@ int conv2d_hires(const smot_conv_desc* d, cudaStream_t st) {
       } else {
         SMOT_ENSURE_SMEM(conv3x3_c16_persist_kernel, L0_SMEM, "smot_conv2d(hires)");
         launch_pdl(conv3x3_c16_persist_kernel, dim3(grid), dim3(256), L0_SMEM, st, a, tx, ty, ntiles);
+      }
+      SMOT_CHECK_LAUNCH("smot_conv2d(hires, persistent)");
+      return SMOT_OK;
+    }
+  }
+  if (d->KH == 3 && d->stride == 2) {
+    const char* e = getenv("SMOT_HIRES_PERSIST");
+    const int mode = e ? atoi(e) : 1;
+    const bool small = d->Cin == 16;   // 16 -> 32, else 32 -> 64
+    const int th = small ? S2Persist<16, 32>::TH : S2Persist<32, 64>::TH;
+    const int tx = ceil_div(a.OW, 32), ty = ceil_div(a.OH, th), ntiles = tx * ty * d->batch, sms = sm_count();
+    if (mode != 0 && (mode == 2 || ntiles >= sms)) {
+      const int grid = ntiles < sms ? ntiles : sms;
+      if (small) {
+        SMOT_ENSURE_SMEM((conv3x3_s2_persist_kernel<16, 32>), (S2Persist<16, 32>::SMEM), "smot_conv2d(hires)");
+        launch_pdl(conv3x3_s2_persist_kernel<16, 32>, dim3(grid), dim3(256), S2Persist<16, 32>::SMEM, st, a, tx, ty, ntiles);
+      } else {
+        SMOT_ENSURE_SMEM((conv3x3_s2_persist_kernel<32, 64>), (S2Persist<32, 64>::SMEM), "smot_conv2d(hires)");
+        launch_pdl(conv3x3_s2_persist_kernel<32, 64>, dim3(grid), dim3(256), S2Persist<32, 64>::SMEM, st, a, tx, ty, ntiles);
       }
       SMOT_CHECK_LAUNCH("smot_conv2d(hires, persistent)");
       return SMOT_OK;

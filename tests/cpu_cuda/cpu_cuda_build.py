@@ -297,6 +297,28 @@ extern "C" void cpu_conv3x3_c16(const void* in, const void* wt, const float* sca
     cpu_launch_warps(dim3((W + C::TW - 1) / C::TW, (H + C::TH - 1) / C::TH, batch), dim3(256), [&] { conv3x3_hires_kernel<16, 16, 1>(a); });
   }
 }
+extern "C" void cpu_conv3x3_s2(const void* in, const void* wt, const float* scale, const float* bias, void* out, int batch, int H,
+                               int W, int cin, int in_ld, int out_ld, int relu, int persistent_ctas) {
+  HiresArgs a = hires_args(in, wt, scale, bias, out, H, W, in_ld, out_ld, relu);
+  a.OH = H / 2, a.OW = W / 2;
+  if (persistent_ctas > 0) {
+    if (cin == 16) {
+      using P = S2Persist<16, 32>;
+      const int tx = (a.OW + 31) / 32, ty = (a.OH + P::TH - 1) / P::TH;
+      cpu_launch_warps(dim3(persistent_ctas), dim3(256), [&] { conv3x3_s2_persist_kernel<16, 32>(a, tx, ty, tx * ty * batch); });
+    } else {
+      using P = S2Persist<32, 64>;
+      const int tx = (a.OW + 31) / 32, ty = (a.OH + P::TH - 1) / P::TH;
+      cpu_launch_warps(dim3(persistent_ctas), dim3(256), [&] { conv3x3_s2_persist_kernel<32, 64>(a, tx, ty, tx * ty * batch); });
+    }
+  } else if (cin == 16) {
+    using C = Hires3<16, 32, 2>;
+    cpu_launch_warps(dim3((a.OW + C::TW - 1) / C::TW, (a.OH + C::TH - 1) / C::TH, batch), dim3(256), [&] { conv3x3_hires_kernel<16, 32, 2>(a); });
+  } else {
+    using C = Hires3<32, 64, 2>;
+    cpu_launch_warps(dim3((a.OW + C::TW - 1) / C::TW, (a.OH + C::TH - 1) / C::TH, batch), dim3(256), [&] { conv3x3_hires_kernel<32, 64, 2>(a); });
+  }
+}
 """]
     path = os.path.join(HERE, "_hires_cpu.cpp")
     with open(path, "w") as f:

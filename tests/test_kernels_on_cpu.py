@@ -288,3 +288,29 @@ def test_persistent_hires_kernels_reproduce_the_per_tile_kernels(cpu_hires, H, W
     err = float((res[0].permute(0, 3, 1, 2).float() - ref0).abs().max() / ref0.abs().max())
     assert err <= 2e-3, "emulated per-tile level0 vs torch: %g" % err
     assert torch.equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("cin,cout,H,W,batch,ctas", [(16, 32, 36, 140, 1, 2), (32, 64, 20, 70, 2, 3)])
+def test_persistent_stride2_hires_kernels_reproduce_the_per_tile_kernels(cpu_hires, cin, cout, H, W, batch, ctas):
+    """level1 (16 -> 32) / level2.tree1.conv1 (32 -> 64), 3x3 stride 2: persistent forms (weights as register-resident B fragments,
+    for 64 output channels two warps per row, ragged tiles, several tiles per CTA) against the per-tile kernel -- bit for bit --
+    and both against torch."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(cin + H)
+    x = torch.randn(batch, cin, H, W, generator=g).half()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3. * cin ** 0.5)).half()
+    scale, bias = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ld_in, ld_out = cin + 8, cout + 16
+    x_nhwc = torch.full((batch, H, W, ld_in), 3.0, dtype=torch.float16)
+    x_nhwc[..., :cin] = x.permute(0, 2, 3, 1)
+    w_k = w.permute(0, 2, 3, 1).contiguous()
+    ref = F.relu(F.conv2d(x.float(), w.float(), stride=2, padding=1) * scale[None, :, None, None] + bias[None, :, None, None])
+    outs = []
+    for persistent in (0, ctas):
+        out = torch.full((batch, H // 2, W // 2, ld_out), 5.0, dtype=torch.float16)
+        cpu_hires.cpu_conv3x3_s2(p(x_nhwc), p(w_k), p(scale), p(bias), p(out), batch, H, W, cin, ld_in, ld_out, 1, persistent)
+        assert float((out[..., cout:] - 5.0).abs().max()) == 0.0
+        outs.append(out[..., :cout].clone())
+    err = float((outs[0].permute(0, 3, 1, 2).float() - ref).abs().max() / ref.abs().max())
+    assert err <= 2e-3, "emulated per-tile kernel vs torch: %g" % err
+    assert torch.equal(outs[0], outs[1])

@@ -503,26 +503,28 @@ def test_conv2d_hires_kernels(case):
     assert rel_err(nchw(got), nchw(got_simt)) <= 1e-3
 
 
-@pytest.mark.parametrize("case", [("stem", 3, 16, 7, 2, 704, 1280), ("level0", 16, 16, 3, 1, 352, 640), ("stem", 3, 16, 7, 1, 100, 70),
-                                  ("level0", 16, 16, 3, 2, 75, 130)])
+@pytest.mark.parametrize("case", [("stem", 3, 16, 7, 1, 2, 704, 1280), ("level0", 16, 16, 3, 1, 1, 352, 640), ("stem", 3, 16, 7, 1, 1, 100, 70),
+                                  ("level0", 16, 16, 3, 1, 2, 75, 130), ("level1", 16, 32, 3, 2, 2, 704, 1280), ("level1", 16, 32, 3, 2, 1, 70, 132),
+                                  ("level2.tree1.conv1", 32, 64, 3, 2, 2, 352, 640), ("level2.tree1.conv1", 32, 64, 3, 2, 1, 38, 76)])
 def test_conv2d_hires_persistent_kernels(case, monkeypatch):
-    """Persistent forms of the stem / level0 kernels (one CTA per SM walks 32x32 tiles, weights as register-resident B fragments,
-    four output rows per warp, double-buffered halo): taken when there is a tile per SM, forced here for the ragged small
-    shapes.  Bit-identical to the per-tile kernels (SMOT_HIRES_PERSIST=0); torch fp32 within the fp16 bar."""
-    name, Cin, Cout, k, batch, H, W = case
+    """Persistent forms of the stem / level0 / level1 / level2.tree1.conv1 kernels (one CTA per SM walks output tiles, weights as
+    register-resident B fragments, double-buffered halo; stride 1: four output rows per warp): taken when there is a tile per SM,
+    forced here for the ragged small shapes.  Bit-identical to the per-tile kernels (SMOT_HIRES_PERSIST=0); torch fp32 within the
+    fp16 bar."""
+    name, Cin, Cout, k, stride, batch, H, W = case
     g = torch.Generator().manual_seed(len(name) + H)
     dt = torch.float16
     x = q(torch.randn(batch, Cin, H, W, generator=g), dt)
     w = q(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k), dt)
     scale, bias = 0.5 + torch.rand(Cout, generator=g), torch.randn(Cout, generator=g)
-    ref = F.relu(F.conv2d(x, w, None, 1, k // 2) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    ref = F.relu(F.conv2d(x, w, None, stride, k // 2) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
     if Cin == 3:
         buf = torch.zeros(batch, H, W, 4, dtype=dt, device=DEV)
         buf[..., :3] = nhwc(x, dt)
         dx = buf[..., :3]
     else:
         dx = nhwc(x, dt)
-    args = (dx, ohwi(w, dt), scale.to(DEV), bias.to(DEV), None, 1, k // 2, True)
+    args = (dx, ohwi(w, dt), scale.to(DEV), bias.to(DEV), None, stride, k // 2, True)
     monkeypatch.setenv("SMOT_HIRES_PERSIST", "0")
     per_tile = ops().conv2d(*args)
     monkeypatch.setenv("SMOT_HIRES_PERSIST", "2")
