@@ -250,8 +250,7 @@ struct XpGeom {
   static constexpr int WARPS = CG;                              // MMA warps (one plane each)
   static constexpr int THREADS = (CG + 1) * 32;                 // + 1 copy warp
   static constexpr int MMA_THREADS = CG * 32;
-  static constexpr int KPLANE_I = 8 * 2 * 16 * 4;               // halves per channel of the pair-interleaved template image (mode 1)
-  static constexpr int X_HALVES = CG * XM_CSTRIDE, K_HALVES = CG * KPLANE_I;   // the staging area fits either template image
+  static constexpr int X_HALVES = CG * XM_CSTRIDE, K_HALVES = CG * XM_KPLANE;
   static constexpr int BAR_OFF = (X_HALVES + K_HALVES) * 2;     // mbarriers behind the two staging areas
   static constexpr int COPIES = CG >= 4 ? CG / 2 : CG;          // bulk copies per CTA (2 planes each), one mbarrier per copy
   static constexpr int PLANES_PER_COPY = CG / COPIES;
@@ -260,7 +259,6 @@ struct XpGeom {
   static constexpr int NCH = CG / VH;                           // vectors per position
   static constexpr int K_ITEMS = 15 * 15 * NCH;                 // template vectors per CTA
   static constexpr int K_ITERS = (K_ITEMS + MMA_THREADS - 1) / MMA_THREADS;
-  static_assert(KPLANE_I >= XM_KPLANE, "staging area");
   static_assert(BAR_OFF % 8 == 0, "mbarrier alignment");
   static_assert(CG % COPIES == 0 && (PLANES_PER_COPY * XM_CSTRIDE * 2) % 16 == 0, "bulk copy size must be a 16-byte multiple");
 };
@@ -377,23 +375,11 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
       if (i < G::K_ITEMS) {
         const int p = i / G::NCH, q = i % G::NCH, u = p / TT, v = p % TT;
         const __half* h = reinterpret_cast<const __half*>(&kv[it]);
-        if constexpr (MMA_MODE == 0) {
-          __half* dst = kz + (q * 8) * XM_KPLANE + u * 2 * XM_KROW + 8 + v;
+        __half* dst = kz + (q * 8) * XM_KPLANE + u * 2 * XM_KROW + 8 + v;
 #pragma unroll
-          for (int e = 0; e < G::VH; ++e) {
-            dst[e * XM_KPLANE] = h[e];                  // copy 0: K[u][v] at half 8 + v
-            dst[e * XM_KPLANE + XM_KROW - 1] = h[e];    // copy 1: K[u][v] at half 7 + v
-          }
-        } else {
-          // pair-interleaved image [pair = u & 7][copy][word 0..15][row u < 8 | row u >= 8][2 halves]: the B words of template
-          // rows u and u + 8 (processed together) are the two halves of ONE 64-bit shared-memory word
-          const int slot = u >> 3, h0 = 8 + v, h1 = 7 + v;
-          __half* dst = kz + (q * 8) * G::KPLANE_I + (u & 7) * 128 + slot * 2;
-#pragma unroll
-          for (int e = 0; e < G::VH; ++e) {
-            dst[e * G::KPLANE_I + (h0 >> 1) * 4 + (h0 & 1)] = h[e];         // copy 0
-            dst[e * G::KPLANE_I + 64 + (h1 >> 1) * 4 + (h1 & 1)] = h[e];    // copy 1
-          }
+        for (int e = 0; e < G::VH; ++e) {
+          dst[e * XM_KPLANE] = h[e];                  // copy 0: K[u][v] at half 8 + v
+          dst[e * XM_KPLANE + XM_KROW - 1] = h[e];    // copy 1: K[u][v] at half 7 + v
         }
       }
     }
@@ -424,12 +410,14 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
     const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
     const int par = g & 1;
     const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(xT + c * XM_CSTRIDE + a_row * XM_PITCH + a_kh * 8);
+    // the two copies of a template row sit 64 B apart: lanes with par = 0 / 1 read disjoint bank halves (conflict-free; a
+    // pair-interleaved image with 64-bit loads was measured SLOWER: both copies then alias the same banks, profiles/xcorr_lab_r02i_*)
+    const uint32_t* kzw = reinterpret_cast<const uint32_t*>(kz + c * XM_KPLANE + par * XM_KROW) + ((8 + 2 * t - g - par) >> 1);
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
     if constexpr (MMA_MODE == 0) {
-      const uint32_t* kzw = reinterpret_cast<const uint32_t*>(kz + c * XM_KPLANE + par * XM_KROW) + ((8 + 2 * t - g - par) >> 1);
 #pragma unroll 5
       for (int u = 0; u < TT; ++u) {
         const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
@@ -442,10 +430,9 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
         xm_mma(acc[1], af, k8, k16);
       }
     } else {
-      // B words of a row pair: three 64-bit loads (word W0, W0 + 4, W0 + 8 of the lane's copy; .x = row u, .y = row u + 8)
-      const uint2* kzp = reinterpret_cast<const uint2*>(kz + c * G::KPLANE_I + par * 64) + ((8 + 2 * t - g - par) >> 1);
       // one template row: window rows [u, u+16) as fragments lo (cols 0..15) / hi (cols 16..31)
-      auto row_step = [&](const uint32_t* lo, const uint32_t* hi, uint32_t k0, uint32_t k8, uint32_t k16) {
+      auto row_step = [&](const uint32_t* lo, const uint32_t* hi, int u) {
+        const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
         xm_mma(acc[0], lo, k0, k8);              // out cols 0..7  <- window cols 0..15
         xm_mma_k8(acc[1], lo[2], lo[3], k0);     // out cols 8..15 <- window cols 8..15   (cols 0..7 meet no tap)
         xm_mma_k8(acc[0], hi[0], hi[1], k16);    // out cols 0..7  <- window cols 16..23  (cols 24..31 meet no tap)
@@ -462,16 +449,14 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
         lo2[0] = lo[1], lo2[2] = lo[3], hi2[0] = hi[1], hi2[2] = hi[3];
         xm_ldmatrix_x2(a_x2 + (uint32_t)(u * XM_PITCH * 2), lo2[1], lo2[3]);
         xm_ldmatrix_x2(a_x2 + (uint32_t)(u * XM_PITCH * 2 + 32), hi2[1], hi2[3]);
-        const uint2 k0 = kzp[u * 32], k8 = kzp[u * 32 + 4], k16 = kzp[u * 32 + 8];
-        row_step(lo, hi, k0.x, k8.x, k16.x);
-        row_step(lo2, hi2, k0.y, k8.y, k16.y);
+        row_step(lo, hi, u);
+        row_step(lo2, hi2, u + 8);
       }
       {
         uint32_t lo[4], hi[4];
         xm_ldmatrix_x4(a_s + (uint32_t)(7 * XM_PITCH * 2), lo[0], lo[1], lo[2], lo[3]);
         xm_ldmatrix_x4(a_s + (uint32_t)(7 * XM_PITCH * 2 + 32), hi[0], hi[1], hi[2], hi[3]);
-        const uint2 k0 = kzp[7 * 32], k8 = kzp[7 * 32 + 4], k16 = kzp[7 * 32 + 8];
-        row_step(lo, hi, k0.x, k8.x, k16.x);
+        row_step(lo, hi, 7);
       }
     }
     XP_STAMP(5);

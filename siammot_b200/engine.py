@@ -356,7 +356,7 @@ class _TrackPlan(object):
                 self.xcorr_note = ("fp16 banded-Toeplitz mma.sync form on channel-planar windows staged with cp.async.bulk (one mbarrier "
                                    "per plane pair); mode 1 = structurally-zero MMA halves dropped (45 instead of 60 k16-MMAs per plane); "
                                    "CG = 16 planes per CTA while all CTAs are co-resident, else 8; bound by shared-memory wavefronts "
-                                   "(~116 per plane) and the launch -> dependency wait -> L2 round trip -> drain chain (DESIGN.md 5.2)")
+                                   "(~137 per plane) and the launch -> dependency wait -> L2 round trip -> drain chain (DESIGN.md 5.2)")
             else:
                 self.steps.append((L.smot_roi_align, (C.byref(pyr_pad), ops._ptr(self.sr), ops._ptr(self.boxes), None, n, Cc, S,
                                                       T.POOLER_SAMPLING_RATIO, ops._ptr(self.srf), dc), "sr_roi_align"))

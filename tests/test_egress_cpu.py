@@ -80,7 +80,7 @@ def test_postprocess_tracks_equals_the_reference_filter():
         _track_len, _track_conf = 5, 0.7
     results = _random_results(7, n_frames=40)
     tracks = egress.clip_to_tracks(results, 1280, 720)
-    sample = DataSample("v", egress.to_entities(tracks, ["person", "vehicle"]))
+    sample = DataSample("v", entities=egress.to_entities(tracks, ["person", "vehicle"]))
     ref = fn(Self(), sample).entities
     got = egress.to_entities(egress.postprocess_tracks(tracks, 5, 0.7), ["person", "vehicle"])
     key = lambda e: (e.id, e.frame_num, tuple(e.bbox))
