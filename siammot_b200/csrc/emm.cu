@@ -341,7 +341,9 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
 #pragma unroll
     for (int it = 0; it < G::K_ITERS; ++it) {
       const int i = it * G::MMA_THREADS + tid;
-      if (i < G::K_ITEMS) kv[it] = *reinterpret_cast<const KVec*>(kb + (size_t)(i / G::NCH) * C + (i % G::NCH) * 8);
+      // item = (vector column q, tap p), q-major: the lanes of a warp hold consecutive taps of ONE column, so the 2-byte
+      // scatter below lands in consecutive halves (a tap-major order put neighbouring lanes 15 KB apart = on one bank)
+      if (i < G::K_ITEMS) kv[it] = *reinterpret_cast<const KVec*>(kb + (size_t)(i % (TT * TT)) * C + (i / (TT * TT)) * 8);
     }
     uint4* kz4 = reinterpret_cast<uint4*>(kz);
     for (int i = tid; i < G::K_HALVES / 8; i += G::MMA_THREADS) kz4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
     for (int it = 0; it < G::K_ITERS; ++it) {
       const int i = it * G::MMA_THREADS + tid;
       if (i < G::K_ITEMS) {
-        const int p = i / G::NCH, q = i % G::NCH, u = p / TT, v = p % TT;
+        const int p = i % (TT * TT), q = i / (TT * TT), u = p / TT, v = p % TT;
         const __half* h = reinterpret_cast<const __half*>(&kv[it]);
         __half* dst = kz + (q * 8) * XM_KPLANE + u * 2 * XM_KROW + 8 + v;
 #pragma unroll
