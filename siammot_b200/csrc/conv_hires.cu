@@ -268,6 +268,9 @@ __global__ void __launch_bounds__(256) stem7x7_hires_kernel(const HiresArgs a) {
 //   * the result leaves through a per-warp staging row (no block barrier): 16-byte stores, one output row = one contiguous KB.
 // Every output accumulates its taps in the order of the kernels above (filter row, then k chunk / tap), so the results are
 // bit-identical to theirs.
+// Measured and dropped: hoisting the per-thread halo offsets out of the tile loop (one register per copy, interior tiles
+// without bounds tests).  Fewer instructions, but the enumeration that makes the shared-memory offset implicit leaves every
+// third lane idle, so a warp's cp.async covers fewer contiguous bytes: level0 26.0 -> 28.5 us, level1 18.7 -> 20.6 us.
 // ---------------------------------------------------------------------------------------------
 constexpr int HP_TW = 32, HP_TH = 32, HP_ROWS = 4;     // tile, output rows per warp (8 warps)
 constexpr int HP_OPITCH = 24;                          // halves per staged output pixel (16 + 8: conflict-free fragment stores)
@@ -296,48 +299,6 @@ __device__ __forceinline__ void hp_store_row(__half* ost_w, const float (*acc)[2
   }
   __syncwarp();
 }
-
-// Halo loads of the persistent 3x3 kernels.  The (row, pixel, chunk) a thread copies does not depend on the tile, so its offset
-// from the halo origin is computed ONCE (one register per copy); tiles whose halo lies inside the image -- 86 % of a 704x1280 frame
-// -- then cost an address add and a cp.async per 16 bytes (the generic loop with its divisions and bounds tests took ~40 % of the
-// issue slots of the per-tile kernels).  The staging area is enumerated in 16-byte units including the pad chunk of every pixel
-// (which nobody copies), so the shared-memory offset of copy k is simply (k * 256 + tid) * 16.
-template <int IH, int IW, int PCH>
-struct HaloPlan {
-  static constexpr int UNITS = IH * IW * (PCH + 1), ITERS = (UNITS + 255) / 256;
-  int goff[ITERS];   // halves from the halo origin pixel, or -1: pad chunk / beyond the staging area
-  __device__ __forceinline__ void init(int tid, int W, int in_ld) {
-#pragma unroll
-    for (int k = 0; k < ITERS; ++k) {
-      const int i = k * 256 + tid, p = i / (PCH + 1), q = i - p * (PCH + 1);
-      const int py = p / IW, px = p - py * IW;
-      goff[k] = (i < UNITS && q < PCH) ? (py * W + px) * in_ld + q * 8 : -1;
-    }
-  }
-  // interior tile: every pixel of the halo exists
-  __device__ __forceinline__ void load_interior(unsigned char* dst, const __half* origin, int tid) const {
-#pragma unroll
-    for (int k = 0; k < ITERS; ++k)
-      if (goff[k] >= 0) cp_async16(dst + (k * 256 + tid) * 16, origin + goff[k], true);
-  }
-  // border tile: zero fill outside the image (the conv padding)
-  __device__ __forceinline__ void load_border(unsigned char* dst, const __half* in, int iy0, int ix0, int H, int W, int in_ld, int tid) const {
-    for (int i = tid; i < UNITS; i += 256) {
-      const int p = i / (PCH + 1), q = i - p * (PCH + 1);
-      if (q >= PCH) continue;
-      const int py = p / IW, px = p - py * IW;
-      const int gy = iy0 + py, gx = ix0 + px;
-      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-      cp_async16(dst + i * 16, ok ? in + ((size_t)gy * W + gx) * in_ld + q * 8 : in, ok);
-    }
-  }
-  __device__ __forceinline__ void load(unsigned char* dst, const __half* in, int iy0, int ix0, int H, int W, int in_ld, int tid) const {
-    if (iy0 >= 0 && ix0 >= 0 && iy0 + IH <= H && ix0 + IW <= W)
-      load_interior(dst, in + ((ptrdiff_t)iy0 * W + ix0) * in_ld, tid);
-    else
-      load_border(dst, in, iy0, ix0, H, W, in_ld, tid);
-  }
-};
 
 // stem: halo = (32 + 6) rows x 40 pixels x 4 halves, origin (oy0 - 3, ox0 - 4) so that every 16-byte chunk (2 pixels) is
 // aligned and lies entirely inside or outside the image (W even)
@@ -476,12 +437,18 @@ __global__ void __launch_bounds__(256, 1) conv3x3_c16_persist_kernel(const Hires
     }
   pdl_wait();
   const int per_img = tiles_x * tiles_y;
-  HaloPlan<L0_IH, L0_IW, 2> plan;
-  static_assert(L0_PITCH == 3 * 16, "HaloPlan enumerates PCH + 1 sixteen-byte units per pixel");
-  plan.init(tid, a.W, a.in_ld);
   auto load_halo = [&](int tile, int buf) {
     const int img = tile / per_img, rem = tile - img * per_img, ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    plan.load(halo + buf * L0_HALO, a.in + (size_t)img * a.H * a.W * a.in_ld, ty * HP_TH - 1, tx * HP_TW - 1, a.H, a.W, a.in_ld, tid);
+    const __half* in = a.in + (size_t)img * a.H * a.W * a.in_ld;
+    const int iy0 = ty * HP_TH - 1, ix0 = tx * HP_TW - 1;
+    unsigned char* dst = halo + buf * L0_HALO;
+    for (int i = tid; i < L0_IH * L0_IW * 2; i += 256) {
+      const int p = i >> 1, q = i & 1;
+      const int py = p / L0_IW, px = p - py * L0_IW;
+      const int gy = iy0 + py, gx = ix0 + px;
+      const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      cp_async16(dst + p * L0_PITCH + q * 16, ok ? in + ((size_t)gy * a.W + gx) * a.in_ld + q * 8 : in, ok);
+    }
   };
   const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
   int tile = blockIdx.x, cur = 0;
@@ -582,12 +549,19 @@ __global__ void __launch_bounds__(256, 1) conv3x3_s2_persist_kernel(const HiresA
     }
   pdl_wait();
   const int per_img = tiles_x * tiles_y;
-  HaloPlan<C::IH, C::IW, CIN / 8> plan;
-  static_assert(C::PITCH == (CIN / 8 + 1) * 16, "HaloPlan enumerates PCH + 1 sixteen-byte units per pixel");
-  plan.init(tid, a.W, a.in_ld);
   auto load_halo = [&](int tile, int buf) {
     const int img = tile / per_img, rem = tile - img * per_img, ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    plan.load(halo + buf * C::HALO, a.in + (size_t)img * a.H * a.W * a.in_ld, ty * C::TH * 2 - 1, tx * C::TW * 2 - 1, a.H, a.W, a.in_ld, tid);
+    const __half* in = a.in + (size_t)img * a.H * a.W * a.in_ld;
+    const int iy0 = ty * C::TH * 2 - 1, ix0 = tx * C::TW * 2 - 1;
+    unsigned char* dst = halo + buf * C::HALO;
+    constexpr int PCH = CIN / 8;
+    for (int i = tid; i < C::IH * C::IW * PCH; i += 256) {
+      const int p = i / PCH, q = i - p * PCH;
+      const int py = p / C::IW, px = p - py * C::IW;
+      const int gy = iy0 + py, gx = ix0 + px;
+      const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      cp_async16(dst + p * C::PITCH + q * 16, ok ? in + ((size_t)gy * a.W + gx) * a.in_ld + q * 8 : in, ok);
+    }
   };
   const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
   __half* ost_w = ost + warp * 32 * C::OPITCH;
