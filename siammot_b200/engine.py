@@ -474,7 +474,7 @@ class _TrackPlan(object):
                 between()
         self.done.record()
 
-    def run(self, feat, upload=True, wait=True):
+    def run(self, feat, wait=True):
         """Launch the stage and (wait=True) block on its result block: the frame's only device->host sync.
         The launch list is replayed as a CUDA graph from its second use on (the first use runs it eagerly, which also
         sets kernel attributes); the template features are copied to the plan's fixed buffer first."""

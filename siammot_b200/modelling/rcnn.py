@@ -53,7 +53,9 @@ class Memory(object):
     """Track memory for the next frame: N = active tracks (first) + dormant tracks.
     Host-side arrays are numpy fp32 / int64 (same IEEE arithmetic as the reference's torch ops)."""
 
-    def __init__(self, feat, sr, boxes, ids, labels, n_active, device):
+    def __init__(self, feat, sr, boxes, ids, labels, n_active, device, frame_size=None, pad_pixels=0):
+        self.frame_size = frame_size      # (W, H) of the network input the boxes live in: makes the object read as the reference's tuple
+        self.pad_pixels = pad_pixels
         self.feat = feat                  # device (N,T,T,C) activation dtype
         self.sr = sr                      # np (N,4) fp32, padded frame
         self.boxes = boxes                # np (N,4) fp32
@@ -72,6 +74,21 @@ class Memory(object):
         h[8 * n:9 * n].view(np.int32)[:] = self.labels
         h[9 * n:9 * n + self.n_active] = 1.0
         h[9 * n + self.n_active:10 * n] = 0.0
+
+    # ``model.track_memory`` read the reference way -- ``feats, sr, boxes = model.track_memory`` / ``model.track_memory[0]`` --
+    # yields TrackHead.get_track_memory's tuple (track_head.py:54-110), built on demand
+    def __len__(self):
+        return 3
+
+    def __getitem__(self, i):
+        if self.frame_size is None:
+            raise TypeError("this Memory does not know its frame size: use as_reference_tuple(image_size, pad_pixels)")
+        return self.as_reference_tuple(self.frame_size, self.pad_pixels)[i]
+
+    def __iter__(self):
+        if self.frame_size is None:
+            raise TypeError("this Memory does not know its frame size: use as_reference_tuple(image_size, pad_pixels)")
+        return iter(self.as_reference_tuple(self.frame_size, self.pad_pixels))
 
     def as_reference_tuple(self, image_size, pad_pixels):
         """The same memory in the reference's form -- (template_features (N,C,T,T), [sr BoxList], [boxes BoxList with ids /
@@ -263,11 +280,10 @@ class CombinedROIHeads(nn.ModuleDict):
         else:
             # external detections replace the RPN/box-head ones: a one-off plan bound to their arrays
             tp = eng.track_plan(P, n, det=self._given_detections(P, given_detection[0]))
-        upload = bool(n) and tp.staged_mem is not mem
-        if upload:
+        if n and tp.staged_mem is not mem:      # normally staged by the previous frame's finish; a flushed-in memory is staged here
             mem.stage(tp)
             tp.staged_mem = mem
-        tp.run(mem.feat if n else None, upload=upload, wait=False)
+        tp.run(mem.feat if n else None, wait=False)
         return (P, tp, mem, n)
 
     # -- MODEL.TRACK_ON False: the model is the detector alone (roi_heads.py:36 skips track head and solver; rcnn.py:57-61)
@@ -448,12 +464,12 @@ class CombinedROIHeads(nn.ModuleDict):
             r = n_act + j
             m_boxes[r], m_sr[r], m_ids[r], m_labels[r] = d[3][d[1]], d[2][d[1]], d[4], d[5]
         if n == 0:
-            return Memory(None, m_sr, m_boxes, m_ids, m_labels, 0, dev)
+            return Memory(None, m_sr, m_boxes, m_ids, m_labels, 0, dev, (P.W, P.H), tu.pad_pixels)
         # next frame's plan: stage its inputs now (the boxes are needed on the device anyway)
         tb = time.perf_counter() if ht is not None else 0.0
         tp = eng.track_plan(next_P if next_P is not None else P, n)
         tc = time.perf_counter() if ht is not None else 0.0
-        mem = Memory(None, m_sr, m_boxes, m_ids, m_labels, n_act, dev)
+        mem = Memory(None, m_sr, m_boxes, m_ids, m_labels, n_act, dev, (P.W, P.H), tu.pad_pixels)
         mem.stage(tp)
         tp.staged_mem = mem
         tp.inputs.copy_(tp.inputs_host, non_blocking=True)
@@ -591,7 +607,8 @@ class SiamMOT(nn.Module):
         else:
             feats = None
         return Memory(feats, sr[0].bbox.to("cpu").float().numpy(), b.bbox.float().numpy(),
-                      ids, b.get_field("labels").to(torch.int64).numpy(), n_act, dev)
+                      ids, b.get_field("labels").to(torch.int64).numpy(), n_act, dev, tuple(b.size),
+                      self.roi_heads.track.track_utils.pad_pixels)
 
     @torch.no_grad()
     def forward(self, images, targets=None, given_detection=None):

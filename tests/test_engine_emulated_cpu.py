@@ -196,6 +196,11 @@ def test_emulated_flush_memory_accepts_the_reference_memory_tuple(layout, monkey
     mem = model.track_memory                       # the engine's own memory after frame 1
     W, H = clip[0].shape[2], clip[0].shape[1]
     feats, sr_l, boxes_l = mem.as_reference_tuple((W, H), cfg.MODEL.TRACK_HEAD.PAD_PIXELS)
+    # ... which is also what unpacking ``model.track_memory`` the reference way (track_head.py:54-110) yields
+    f2, s2, b2 = model.track_memory
+    assert len(model.track_memory) == 3 and torch.equal(f2, feats) and torch.equal(s2[0].bbox, sr_l[0].bbox) and tuple(s2[0].size) == tuple(sr_l[0].size)
+    assert torch.equal(b2[0].bbox, boxes_l[0].bbox) and torch.equal(b2[0].get_field("ids"), boxes_l[0].get_field("ids")) and tuple(b2[0].size) == (W, H)
+    assert torch.equal(model.track_memory[2][0].get_field("labels"), boxes_l[0].get_field("labels"))
     sr, boxes = sr_l[0], boxes_l[0]
     assert tuple(feats.shape[1:]) == (128, 15, 15) and tuple(sr.size) == (W + 1024, H + 1024)
     if layout == "nhwc":
