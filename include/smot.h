@@ -208,8 +208,10 @@ int smot_xcorr_planar(const void* x_planar, const void* k, void* out, int n, int
  * the live operand halves, fragments shared between template rows u and u+8; equal to fp16 rounding).  smot_xcorr_planar
  * takes 1 when the environment has SMOT_XCORR_PLANAR=2, else 0. */
 int smot_xcorr_planar_mode(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode, void* stream);
-/* ... and the channel group of a CTA (2, 4, 8 or 16 planes = MMA warps; channels % channel_group == 0): the planes are independent,
- * the results do not depend on it.  smot_xcorr_planar / _mode take 16 while n * channels <= 32 planes per SM, else 8
+/* ... and the channel group of a CTA (2, 4, 8 or 16 planes = MMA warps; channels % channel_group == 0; 0 = the flat form: one CTA per
+ * SM, the plane list dealt in 4-plane units, for n * channels <= 28 planes per SM): the planes are independent,
+ * the results do not depend on it.  smot_xcorr_planar / _mode take the flat form while it fits (SMOT_XCORR_FLAT=0: never), else 16 while n * channels <= 32 planes
+ * per SM, else 8
  * (SMOT_XCORR_CG overrides). */
 int smot_xcorr_planar_cfg(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode, int channel_group,
                           void* stream);

@@ -309,6 +309,66 @@ extern "C" int smot_xcorr_trace_buffer(void* buf) { return cudaMemcpyToSymbol(g_
 #define XP_STAMP(slot) do { } while (0)
 #endif
 
+// One plane: Out(16x16) = sum_u X[u:u+16, :32] * B_u on mma.sync from the plane's window image xw (shared memory, rows XM_PITCH
+// apart) and its zero-padded template image kw; acc = the warp's D fragments (two n8 tiles).  Shared by the planar kernels.
+template <int MMA_MODE>
+__device__ __forceinline__ void xp_plane_mma(const __half* xw, const __half* kw, int lane, float (&acc)[2][4]) {
+  constexpr int TT = 15;
+  const int g = lane >> 2, t = lane & 3;
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
+  const int par = g & 1;
+  const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(xw + a_row * XM_PITCH + a_kh * 8);
+  // the two copies of a template row sit 64 B apart: lanes with par = 0 / 1 read disjoint bank halves (conflict-free; a
+  // pair-interleaved image with 64-bit loads was measured SLOWER: both copies then alias the same banks, profiles/xcorr_lab_r02i_*)
+  const uint32_t* kzw = reinterpret_cast<const uint32_t*>(kw + par * XM_KROW) + ((8 + 2 * t - g - par) >> 1);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  if constexpr (MMA_MODE == 0) {
+#pragma unroll 5
+    for (int u = 0; u < TT; ++u) {
+      const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
+      uint32_t af[4];
+      xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2), af[0], af[1], af[2], af[3]);
+      xm_mma(acc[0], af, k0, k8);
+      xm_mma(acc[1], af, 0u, k0);
+      xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2 + 32), af[0], af[1], af[2], af[3]);
+      xm_mma(acc[0], af, k16, 0u);
+      xm_mma(acc[1], af, k8, k16);
+    }
+  } else {
+    // one template row: window rows [u, u+16) as fragments lo (cols 0..15) / hi (cols 16..31)
+    auto row_step = [&](const uint32_t* lo, const uint32_t* hi, int u) {
+      const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
+      xm_mma(acc[0], lo, k0, k8);              // out cols 0..7  <- window cols 0..15
+      xm_mma_k8(acc[1], lo[2], lo[3], k0);     // out cols 8..15 <- window cols 8..15   (cols 0..7 meet no tap)
+      xm_mma_k8(acc[0], hi[0], hi[1], k16);    // out cols 0..7  <- window cols 16..23  (cols 24..31 meet no tap)
+      xm_mma(acc[1], hi, k8, k16);             // out cols 8..15 <- window cols 16..31
+    };
+    // lanes 0..15 address the x2 loads: rows (lane & 7) + 16 of the pair's 24-row span, column half (lane >> 3) & 1
+    const uint32_t a_x2 = (uint32_t)__cvta_generic_to_shared(xw + ((lane & 7) + 16) * XM_PITCH + ((lane >> 3) & 1) * 8);
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+      uint32_t lo[4], hi[4], lo2[4], hi2[4];
+      xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2), lo[0], lo[1], lo[2], lo[3]);
+      xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2 + 32), hi[0], hi[1], hi[2], hi[3]);
+      // rows u+8..u+15 are the second row block of the fragments above; rows u+16..u+23 are new
+      lo2[0] = lo[1], lo2[2] = lo[3], hi2[0] = hi[1], hi2[2] = hi[3];
+      xm_ldmatrix_x2(a_x2 + (uint32_t)(u * XM_PITCH * 2), lo2[1], lo2[3]);
+      xm_ldmatrix_x2(a_x2 + (uint32_t)(u * XM_PITCH * 2 + 32), hi2[1], hi2[3]);
+      row_step(lo, hi, u);
+      row_step(lo2, hi2, u + 8);
+    }
+    {
+      uint32_t lo[4], hi[4];
+      xm_ldmatrix_x4(a_s + (uint32_t)(7 * XM_PITCH * 2), lo[0], lo[1], lo[2], lo[3]);
+      xm_ldmatrix_x4(a_s + (uint32_t)(7 * XM_PITCH * 2 + 32), hi[0], hi[1], hi[2], hi[3]);
+      row_step(lo, hi, 7);
+    }
+  }
+}
+
 // MMA_MODE 0: the MMA phase of xcorr_mma_kernel, instruction for instruction (bit-identical results).
 // MMA_MODE 1 (default): the same contraction with the structurally-zero work removed --
 //   * of the four m16n8k16 per template row, two have an all-zero B half (taps d0-8 and d0+24 do not exist): they become
@@ -408,59 +468,8 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
       }
     }
     XP_STAMP(4);
-    // ---- MMA phase: warp = channel (identical to xcorr_mma_kernel)
-    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
-    const int par = g & 1;
-    const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(xT + c * XM_CSTRIDE + a_row * XM_PITCH + a_kh * 8);
-    // the two copies of a template row sit 64 B apart: lanes with par = 0 / 1 read disjoint bank halves (conflict-free; a
-    // pair-interleaved image with 64-bit loads was measured SLOWER: both copies then alias the same banks, profiles/xcorr_lab_r02i_*)
-    const uint32_t* kzw = reinterpret_cast<const uint32_t*>(kz + c * XM_KPLANE + par * XM_KROW) + ((8 + 2 * t - g - par) >> 1);
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-    if constexpr (MMA_MODE == 0) {
-#pragma unroll 5
-      for (int u = 0; u < TT; ++u) {
-        const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
-        uint32_t af[4];
-        xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2), af[0], af[1], af[2], af[3]);
-        xm_mma(acc[0], af, k0, k8);
-        xm_mma(acc[1], af, 0u, k0);
-        xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2 + 32), af[0], af[1], af[2], af[3]);
-        xm_mma(acc[0], af, k16, 0u);
-        xm_mma(acc[1], af, k8, k16);
-      }
-    } else {
-      // one template row: window rows [u, u+16) as fragments lo (cols 0..15) / hi (cols 16..31)
-      auto row_step = [&](const uint32_t* lo, const uint32_t* hi, int u) {
-        const uint32_t k0 = kzw[u * XM_KROW], k8 = kzw[u * XM_KROW + 4], k16 = kzw[u * XM_KROW + 8];
-        xm_mma(acc[0], lo, k0, k8);              // out cols 0..7  <- window cols 0..15
-        xm_mma_k8(acc[1], lo[2], lo[3], k0);     // out cols 8..15 <- window cols 8..15   (cols 0..7 meet no tap)
-        xm_mma_k8(acc[0], hi[0], hi[1], k16);    // out cols 0..7  <- window cols 16..23  (cols 24..31 meet no tap)
-        xm_mma(acc[1], hi, k8, k16);             // out cols 8..15 <- window cols 16..31
-      };
-      // lanes 0..15 address the x2 loads: rows (lane & 7) + 16 of the pair's 24-row span, column half (lane >> 3) & 1
-      const uint32_t a_x2 = (uint32_t)__cvta_generic_to_shared(xT + c * XM_CSTRIDE + ((lane & 7) + 16) * XM_PITCH + ((lane >> 3) & 1) * 8);
-#pragma unroll
-      for (int u = 0; u < 7; ++u) {
-        uint32_t lo[4], hi[4], lo2[4], hi2[4];
-        xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2), lo[0], lo[1], lo[2], lo[3]);
-        xm_ldmatrix_x4(a_s + (uint32_t)(u * XM_PITCH * 2 + 32), hi[0], hi[1], hi[2], hi[3]);
-        // rows u+8..u+15 are the second row block of the fragments above; rows u+16..u+23 are new
-        lo2[0] = lo[1], lo2[2] = lo[3], hi2[0] = hi[1], hi2[2] = hi[3];
-        xm_ldmatrix_x2(a_x2 + (uint32_t)(u * XM_PITCH * 2), lo2[1], lo2[3]);
-        xm_ldmatrix_x2(a_x2 + (uint32_t)(u * XM_PITCH * 2 + 32), hi2[1], hi2[3]);
-        row_step(lo, hi, u);
-        row_step(lo2, hi2, u + 8);
-      }
-      {
-        uint32_t lo[4], hi[4];
-        xm_ldmatrix_x4(a_s + (uint32_t)(7 * XM_PITCH * 2), lo[0], lo[1], lo[2], lo[3]);
-        xm_ldmatrix_x4(a_s + (uint32_t)(7 * XM_PITCH * 2 + 32), hi[0], hi[1], hi[2], hi[3]);
-        row_step(lo, hi, 7);
-      }
-    }
+    // ---- MMA phase: warp = channel (identical to xcorr_mma_kernel) + D fragments -> the warp's own (now dead) window plane
+    xp_plane_mma<MMA_MODE>(xT + c * XM_CSTRIDE, kz + c * XM_KPLANE, lane, acc);
     XP_STAMP(5);
     // ---- D fragments -> the warp's own (now dead) window plane as [O*O] halves
     __syncwarp();
@@ -487,6 +496,123 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
     }
   }
   XP_STAMP(7);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Flat form of the planar kernel for launches that fit ONE wave (n * C <= 28 planes per SM; 30 tracks x 128 channels = 25.9).
+// With 16 planes per CTA, 3840 planes are 240 CTAs on 148 SMs: 92 SMs run 32 planes, 56 run 16, and the launch ends with the
+// loaded ones (trace: MMA phase 1.2 us on the light SMs, up to 3.3 us on the others).  Here the plane list is cut into 4-plane
+// units (a unit never straddles a track or an 8-byte channel vector) and CTA b of gridDim.x takes units
+// [b * U / grid, (b + 1) * U / grid): 24 or 28 planes on EVERY SM, one CTA per SM, one MMA warp per plane (up to 28 + the copy
+// warp).  Templates and results move as 8-byte vectors (a unit's four channels).  Per-plane arithmetic is xp_plane_mma's, so the
+// results are the same bits as xcorr_planar_kernel's.
+// ---------------------------------------------------------------------------------------------
+constexpr int XF_MAX_UNITS = 7, XF_MAX_PLANES = 4 * XF_MAX_UNITS;
+constexpr int XF_THREADS = (XF_MAX_PLANES + 1) * 32, XF_MMA_THREADS = XF_MAX_PLANES * 32;
+constexpr int XF_BAR_OFF = XF_MAX_PLANES * (XM_CSTRIDE + XM_KPLANE) * 2;
+constexpr int XF_SMEM = XF_BAR_OFF + 8 * (XF_MAX_PLANES / 2);
+constexpr int XF_K_ITERS = (15 * 15 * XF_MAX_UNITS + XF_MMA_THREADS - 1) / XF_MMA_THREADS;
+static_assert(XF_BAR_OFF % 8 == 0 && XF_THREADS <= 1024, "flat kernel geometry");
+
+template <int MMA_MODE>
+__global__ void __launch_bounds__(XF_THREADS, 1) xcorr_flat_kernel(const __half* __restrict__ xp, const __half* __restrict__ k,
+                                                                   __half* __restrict__ out, int C, int units_total) {
+  constexpr int TT = 15, O = 16;
+  extern __shared__ __align__(128) unsigned char xp_raw[];
+  __half* xT = reinterpret_cast<__half*>(xp_raw);                   // [28][CSTRIDE]
+  __half* kz = xT + XF_MAX_PLANES * XM_CSTRIDE;                     // [28][TT][2][KROW]
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(xp_raw + XF_BAR_OFF);   // one mbarrier per plane pair
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool copy_warp = warp == XF_MAX_PLANES;
+  const int u0 = (int)(((long long)blockIdx.x * units_total) / gridDim.x);
+  const int u1 = (int)(((long long)(blockIdx.x + 1) * units_total) / gridDim.x);
+  const int units = u1 - u0, planes = 4 * units, p0 = 4 * u0;      // units <= XF_MAX_UNITS (checked by the launcher)
+  pdl_launch_dependents();
+  // ---- prologue (independent of the predecessor): this CTA's templates to registers (8 bytes = a unit's channels of one tap),
+  // unit-major so that a warp's scatter below lands in consecutive halves; zero fill of the padded copies
+  uint2 kv[XF_K_ITERS];
+  if (!copy_warp) {
+#pragma unroll
+    for (int it = 0; it < XF_K_ITERS; ++it) {
+      const int i = it * XF_MMA_THREADS + tid, unit = i / (TT * TT), tap = i - unit * (TT * TT);
+      if (unit < units) {
+        const int plane = p0 + 4 * unit, n = plane / C, c = plane - n * C;
+        kv[it] = *reinterpret_cast<const uint2*>(k + ((size_t)n * TT * TT + tap) * C + c);
+      }
+    }
+    uint4* kz4 = reinterpret_cast<uint4*>(kz);
+    for (int i = tid; i < planes * XM_KPLANE / 8; i += XF_MMA_THREADS) kz4[i] = make_uint4(0u, 0u, 0u, 0u);
+  } else if (lane == 0) {
+    for (int i = 0; i < XF_MAX_PLANES / 2; ++i) xp_mbar_init(bar + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (copy_warp) {
+    pdl_wait();
+    if (lane == 0) {
+      constexpr uint32_t BYTES = 2 * XM_CSTRIDE * 2;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(xp + (size_t)p0 * XM_CSTRIDE);
+      for (int i = 0; i < planes / 2; ++i) {
+        xp_mbar_expect_tx(bar + 8 * i, BYTES);
+        xp_bulk_g2s((uint32_t)__cvta_generic_to_shared(xT) + i * BYTES, src + (size_t)i * BYTES, BYTES, bar + 8 * i);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < XF_K_ITERS; ++it) {
+      const int i = it * XF_MMA_THREADS + tid, unit = i / (TT * TT), tap = i - unit * (TT * TT);
+      if (unit < units) {
+        const int u = tap / TT, v = tap - u * TT;
+        const __half* h = reinterpret_cast<const __half*>(&kv[it]);
+        __half* dst = kz + (unit * 4) * XM_KPLANE + u * 2 * XM_KROW + 8 + v;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          dst[e * XM_KPLANE] = h[e];                  // copy 0: K[u][v] at half 8 + v
+          dst[e * XM_KPLANE + XM_KROW - 1] = h[e];    // copy 1: K[u][v] at half 7 + v
+        }
+      }
+    }
+  }
+  __syncthreads();  // templates staged
+  if (!copy_warp && warp < planes) {
+    unsigned long long t_start = 0;
+    const uint32_t my_bar = bar + 8 * (warp >> 1);
+    for (uint32_t spin = 0; !xp_mbar_try_wait(my_bar, 0); ++spin) {
+      if ((spin & 255u) == 255u) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t_start == 0) t_start = now;
+        if (now - t_start > 2000000000ull) {
+          printf("smot xcorr_flat: bulk copy wait timed out (block %d thread %d)\n", blockIdx.x, tid);
+          __trap();
+        }
+      }
+    }
+    float acc[2][4];
+    xp_plane_mma<MMA_MODE>(xT + warp * XM_CSTRIDE, kz + warp * XM_KPLANE, lane, acc);
+    __syncwarp();
+    const int g = lane >> 2, t = lane & 3;
+    __half2* ost = reinterpret_cast<__half2*>(xT + warp * XM_CSTRIDE);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      ost[g * 8 + nt * 4 + t] = __floats2half2_rn(acc[nt][0], acc[nt][1]);
+      ost[(g + 8) * 8 + nt * 4 + t] = __floats2half2_rn(acc[nt][2], acc[nt][3]);
+    }
+  }
+  __syncthreads();
+  if (!copy_warp) {
+    pdl_wait();  // the result stores must not pass the predecessor
+    for (int i = tid; i < O * O * units; i += XF_MMA_THREADS) {
+      const int unit = i / (O * O), pos = i - unit * (O * O);
+      const int plane = p0 + 4 * unit, n = plane / C, c = plane - n * C;
+      const __half* src = xT + (unit * 4) * XM_CSTRIDE + pos;
+      __align__(8) __half h[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = src[e * XM_CSTRIDE];
+      *reinterpret_cast<uint2*>(out + ((size_t)n * O * O + pos) * C + c) = *reinterpret_cast<const uint2*>(h);
+    }
+  }
 }
 
 // generic fallback for unusual geometries: one thread per output element
@@ -750,8 +876,19 @@ extern "C" int smot_xcorr_planar(const void* x_planar, const void* k, void* out,
   return smot_xcorr_planar_mode(x_planar, k, out, n, channels, xcorr_planar_trimmed() ? 1 : 0, stream);
 }
 
+// 0: never; 1 (default): whenever the planes fit one wave of 28 per SM; developer switch SMOT_XCORR_FLAT (read once)
+static bool xcorr_flat_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SMOT_XCORR_FLAT");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 extern "C" int smot_xcorr_planar_mode(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode,
                                       void* stream) {
+  if (xcorr_flat_enabled() && channels % 4 == 0 && (long long)n * channels <= (long long)XF_MAX_PLANES * sm_count())
+    return smot_xcorr_planar_cfg(x_planar, k, out, n, channels, mma_mode, 0, stream);
   int cg = xcorr_planar_cg(n * channels);
   while (cg > 2 && channels % cg) cg >>= 1;
   return smot_xcorr_planar_cfg(x_planar, k, out, n, channels, mma_mode, cg, stream);
@@ -778,15 +915,36 @@ extern "C" int smot_xcorr_planar_cfg(const void* x_planar, const void* k, void* 
                                      int channel_group, void* stream) {
   const int cg = channel_group;
   SMOT_CHECK_ARG(mma_mode == 0 || mma_mode == 1, "smot_xcorr_planar: mma_mode %d", mma_mode);
-  SMOT_CHECK_ARG(cg == 2 || cg == 4 || cg == 8 || cg == 16, "smot_xcorr_planar: channel group %d (2, 4, 8 or 16)", cg);
-  SMOT_CHECK_ARG(n >= 0 && channels > 0 && channels % cg == 0, "smot_xcorr_planar: bad geometry n=%d C=%d (C must be a multiple of %d)",
-                 n, channels, cg);
+  SMOT_CHECK_ARG(cg == 0 || cg == 2 || cg == 4 || cg == 8 || cg == 16, "smot_xcorr_planar: channel group %d (0 = flat, 2, 4, 8 or 16)", cg);
+  SMOT_CHECK_ARG(n >= 0 && channels > 0 && channels % (cg ? cg : 4) == 0,
+                 "smot_xcorr_planar: bad geometry n=%d C=%d (C must be a multiple of %d)", n, channels, cg ? cg : 4);
   if (n == 0) return SMOT_OK;
   SMOT_CHECK_ARG(x_planar && k && out, "smot_xcorr_planar: null argument");
   SMOT_CHECK_ARG((((uintptr_t)x_planar | (uintptr_t)k | (uintptr_t)out) & 15) == 0, "smot_xcorr_planar: operands must be 16-byte aligned");
   static_assert(XM_CSTRIDE == SMOT_XCORR_PLANE && XM_PITCH == SMOT_XCORR_ROW_PITCH, "smot.h states the plane layout");
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
+  if (cg == 0) {   // flat form: one CTA per SM, 4-plane units dealt evenly
+    const int units = n * channels / 4, sms = sm_count();
+    SMOT_CHECK_ARG(units <= XF_MAX_UNITS * sms, "smot_xcorr_planar: %d planes do not fit one wave of the flat form (%d SMs x %d)",
+                   n * channels, sms, XF_MAX_PLANES);
+    const int grid = units < sms ? units : sms;
+    if (mma_mode == 1) {
+      SMOT_ENSURE_SMEM(xcorr_flat_kernel<1>, XF_SMEM, "smot_xcorr_planar");
+      e = launch_pdl(xcorr_flat_kernel<1>, dim3(grid), dim3(XF_THREADS), XF_SMEM, st, (const __half*)x_planar, (const __half*)k,
+                     (__half*)out, channels, units);
+    } else {
+      SMOT_ENSURE_SMEM(xcorr_flat_kernel<0>, XF_SMEM, "smot_xcorr_planar");
+      e = launch_pdl(xcorr_flat_kernel<0>, dim3(grid), dim3(XF_THREADS), XF_SMEM, st, (const __half*)x_planar, (const __half*)k,
+                     (__half*)out, channels, units);
+    }
+    if (e != cudaSuccess) {
+      set_error("smot_xcorr_planar: launch failed: %s", cudaGetErrorString(e));
+      return SMOT_ERR_CUDA;
+    }
+    SMOT_CHECK_LAUNCH("smot_xcorr_planar(flat)");
+    return SMOT_OK;
+  }
 #define SMOT_XP_CASE(MODE, CGV) \
   case (MODE) * 32 + (CGV): e = launch_xcorr_planar<MODE, CGV>(x_planar, k, out, n, channels, st); break
   switch (mma_mode * 32 + cg) {

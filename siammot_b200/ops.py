@@ -299,7 +299,7 @@ def xcorr_planar(x_planar, k, out=None, mma_mode=None, channel_group=None):
     assert x_planar.is_contiguous() and k.is_contiguous() and tuple(k.shape) == (n, 15, 15, Cc)
     if out is None:
         out = torch.empty((n, 16, 16, Cc), dtype=torch.float16, device=k.device)
-    if channel_group is not None:   # planes per CTA (2 / 4 / 8 / 16): same results, another grid
+    if channel_group is not None:   # planes per CTA (2 / 4 / 8 / 16; 0 = flat form, one CTA per SM): same results, another grid
         check(lib().smot_xcorr_planar_cfg(_ptr(x_planar), _ptr(k), _ptr(out), n, Cc, 1 if mma_mode is None else int(mma_mode),
                                           int(channel_group), stream_ptr()), "smot_xcorr_planar")
     elif mma_mode is None:   # the library's default: trimmed MMA phase (SMOT_XCORR_PLANAR=1 selects the untrimmed one)

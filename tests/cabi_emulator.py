@@ -347,7 +347,7 @@ class FakeLib(object):
         return self.smot_xcorr_planar(xp, k, out, n, Cc, st)
 
     def smot_xcorr_planar_cfg(self, xp, k, out, n, Cc, mma_mode, cg, st):
-        assert cg in (2, 4, 8, 16) and Cc % cg == 0
+        assert cg in (0, 2, 4, 8, 16) and Cc % (cg or 4) == 0
         return self.smot_xcorr_planar(xp, k, out, n, Cc, st)
 
     def smot_emm_decode(self, maps, map_ld, n, O, up, T, sr, tboxes, hann, pad, use_centerness, sigma, img_w, img_h, amodal,

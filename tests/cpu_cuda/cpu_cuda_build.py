@@ -141,6 +141,10 @@ def generate_xcorr():
     k_mma = _function_text(emm, r"__global__ void __launch_bounds__\(XM_WARPS \* 32\) xcorr_mma_kernel")
     k_planar = _function_text(emm, r"__global__ void __launch_bounds__\(XpGeom<CG>::THREADS\) xcorr_planar_kernel")
     assert k_planar.lstrip().startswith("template <int MMA_MODE, int CG>")
+    k_planar = _function_text(emm, r"__device__ __forceinline__ void xp_plane_mma") + k_planar
+    consts_flat = emm[emm.index("constexpr int XF_MAX_UNITS"):emm.index("template <int MMA_MODE>\n__global__ void __launch_bounds__(XF_THREADS, 1) xcorr_flat_kernel")]
+    k_flat = _function_text(emm, r"__global__ void __launch_bounds__\(XF_THREADS, 1\) xcorr_flat_kernel")
+    k_planar += consts_flat + k_flat
     k_planar = re.sub(r"XP_STAMP\(\d\);", ";", k_planar)
     k_mma = k_mma.replace("extern __shared__ __align__(16) unsigned char xm_raw[];", "unsigned char* xm_raw = cpu_dynamic_smem;")
     k_planar = k_planar.replace("extern __shared__ __align__(128) unsigned char xp_raw[];", "unsigned char* xp_raw = cpu_dynamic_smem;")
@@ -227,6 +231,15 @@ extern "C" int cpu_xcorr_planar_cfg(const void* xp, const void* k, void* out, in
 }
 extern "C" void cpu_xcorr_planar(const void* xp, const void* k, void* out, int n, int C, int mode) {
   cpu_xcorr_planar_cfg(xp, k, out, n, C, mode, 16);
+}
+extern "C" int cpu_xcorr_flat(const void* xp, const void* k, void* out, int n, int C, int mode, int grid) {
+  const int units = n * C / 4;
+  if (C % 4 || (units + grid - 1) / grid > XF_MAX_UNITS) return 1;
+  if (mode == 0)
+    cpu_launch_warps(dim3(grid), dim3(XF_THREADS), [&] { xcorr_flat_kernel<0>((const __half*)xp, (const __half*)k, (__half*)out, C, units); });
+  else
+    cpu_launch_warps(dim3(grid), dim3(XF_THREADS), [&] { xcorr_flat_kernel<1>((const __half*)xp, (const __half*)k, (__half*)out, C, units); });
+  return 0;
 }
 extern "C" int cpu_xcorr_plane_halves() { return XM_CSTRIDE; }
 """]

@@ -130,7 +130,7 @@ def cpu_xcorr():
     return C.CDLL(cpu_build.build_xcorr())
 
 
-@pytest.mark.parametrize("n,Cc", [(2, 32), (1, 16)])
+@pytest.mark.parametrize("n,Cc", [(2, 32), (1, 16), (3, 48)])
 def test_xcorr_kernels_source_under_ptx_emulation(cpu_xcorr, n, Cc):
     """csrc/emm.cu's tensor-core correlation kernels, source text, with ldmatrix / mma.sync / mbarrier / cp.async.bulk emulated
     on the host (tests/cpu_cuda/shim_tc.h).  xcorr_mma_kernel is validated on the B200: its agreement with the oracle here
@@ -172,6 +172,13 @@ def test_xcorr_kernels_source_under_ptx_emulation(cpu_xcorr, n, Cc):
             got = torch.full((n, 16, 16, Cc), float("nan"), dtype=torch.float16)
             assert cpu_xcorr.cpu_xcorr_planar_cfg(p(xp), p(k_nhwc), p(got), n, Cc, mode, cg) == 0
             assert torch.equal(got, want), "channel group %d, mode %d" % (cg, mode)
+    # flat form (one CTA per SM, the plane list dealt in 4-plane units): CTAs of 4-5 units, some straddling a track boundary, a
+    # single CTA, and one unit per CTA -- the same bits again
+    for grid in sorted({(n * Cc // 4 + 4) // 5, n * Cc // 4} | ({1} if n * Cc <= 28 else set())):
+        for mode, want in ((0, out_mma), (1, out_trim)):
+            got = torch.full((n, 16, 16, Cc), float("nan"), dtype=torch.float16)
+            assert cpu_xcorr.cpu_xcorr_flat(p(xp), p(k_nhwc), p(got), n, Cc, mode, grid) == 0
+            assert torch.equal(got, want), "flat form, grid %d, mode %d" % (grid, mode)
 
 
 def test_fp16_instantiations_of_the_simple_kernels(cpu_xcorr):

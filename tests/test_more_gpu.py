@@ -297,7 +297,9 @@ def test_xcorr_planar_equals_xcorr(n, C):
     assert rel_err(nchw(trim), orc.xcorr_depthwise(x, k)) <= tol(dt)
     assert rel_err(trim.float(), ref.float()) <= 2e-3
     # planes per CTA (the grid's granularity) never change the bits: every plane is one warp's work in a fixed order
-    for cg in (2, 4, 8, 16):
+    # (0 = the flat form: one CTA per SM, 4-plane units dealt evenly; only while the planes fit one wave of 28 per SM)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for cg in (2, 4, 8, 16) + ((0,) if n * C <= 28 * sms else ()):
         for mode, want in ((0, ref), (1, trim)):
             out = torch.full_like(ref, float("nan"))
             for _ in range(2):
