@@ -849,9 +849,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="float16", choices=["float16", "float32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--experimental", default="subprocess", choices=["subprocess", "inproc", "off", "child"],
-                    help="information-only arms for paths that have not had a GPU run yet: in a child process after the line is "
-                         "final (default), in this process under a watchdog (tests), or not at all; 'child' is the child's mode")
+    ap.add_argument("--experimental", default="off", choices=["subprocess", "inproc", "off", "child"],
+                    help="information-only A/B arms of the pipeline switches (all of them are measured defaults since round 2, so "
+                         "this is off unless asked for): in a child process after the line is final, in this process under a "
+                         "watchdog (tests), or not at all (default); 'child' is the child's mode")
     ap.add_argument("--workload", default="720p30", choices=sorted(WORKLOADS),
                     help="720p30 = BASELINE.json configs[1] (the metric's configuration, default); 1080p80 = configs[2]; "
                          "r50_720p30 = configs[4]")
