@@ -210,8 +210,8 @@ int smot_xcorr_planar(const void* x_planar, const void* k, void* out, int n, int
 int smot_xcorr_planar_mode(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode, void* stream);
 /* ... and the channel group of a CTA (2, 4, 8 or 16 planes = MMA warps; channels % channel_group == 0; 0 = the flat form: one CTA per
  * SM, the plane list dealt in 4-plane units, for n * channels <= 28 planes per SM): the planes are independent,
- * the results do not depend on it.  smot_xcorr_planar / _mode take the flat form while it fits (SMOT_XCORR_FLAT=0: never), else 16 while n * channels <= 32 planes
- * per SM, else 8
+ * the results do not depend on it.  smot_xcorr_planar / _mode take 16 while n * channels <= 32 planes per SM, else 8 (SMOT_XCORR_FLAT=1: the flat form while it
+ * fits -- measured slower)
  * (SMOT_XCORR_CG overrides). */
 int smot_xcorr_planar_cfg(const void* x_planar, const void* k, void* out, int n, int channels, int mma_mode, int channel_group,
                           void* stream);

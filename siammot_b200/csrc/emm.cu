@@ -500,6 +500,7 @@ __global__ void __launch_bounds__(XpGeom<CG>::THREADS) xcorr_planar_kernel(const
 
 // ---------------------------------------------------------------------------------------------
 // Flat form of the planar kernel for launches that fit ONE wave (n * C <= 28 planes per SM; 30 tracks x 128 channels = 25.9).
+// (Developer variant, measured SLOWER than the 16-plane CTAs -- see xcorr_flat_enabled() -- and therefore not the default.)
 // With 16 planes per CTA, 3840 planes are 240 CTAs on 148 SMs: 92 SMs run 32 planes, 56 run 16, and the launch ends with the
 // loaded ones (trace: MMA phase 1.2 us on the light SMs, up to 3.3 us on the others).  Here the plane list is cut into 4-plane
 // units (a unit never straddles a track or an 8-byte channel vector) and CTA b of gridDim.x takes units
@@ -876,11 +877,15 @@ extern "C" int smot_xcorr_planar(const void* x_planar, const void* k, void* out,
   return smot_xcorr_planar_mode(x_planar, k, out, n, channels, xcorr_planar_trimmed() ? 1 : 0, stream);
 }
 
-// 0: never; 1 (default): whenever the planes fit one wave of 28 per SM; developer switch SMOT_XCORR_FLAT (read once)
+// developer switch SMOT_XCORR_FLAT=1 (read once): the flat form whenever the planes fit one wave of 28 per SM.  OFF by default:
+// measured 7.34 us against 5.80 us for 16-plane CTAs at 30 x 128 (profiles/bench_r02l_*.json) -- the balance it buys (28 instead
+// of 32 planes on the busiest SM) is worth less than what one 29-warp CTA per SM loses: its phases (template staging, wait for
+// the windows, MMA, result path) cannot overlap with those of a second CTA, its block barriers span 928 threads, and templates /
+// results move as 8-byte instead of 16-byte vectors.
 static bool xcorr_flat_enabled() {
   static const bool on = [] {
     const char* e = getenv("SMOT_XCORR_FLAT");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }

@@ -352,13 +352,13 @@ class _TrackPlan(object):
                 self.xcorr_slot = len(self.steps)
                 self.steps.append((L.smot_xcorr_planar_mode, (ops._ptr(self.srp), ops._ptr(self.tmpl), ops._ptr(self.resp), n, Cc,
                                                               eng.xcorr_planar_mode), "xcorr"))
-                # the library's rule (csrc/emm.cu smot_xcorr_planar_mode): flat form while the planes fit one wave of 28 per SM
-                flat = os.environ.get("SMOT_XCORR_FLAT", "1") != "0" and n * Cc <= 28 * eng.sm_count()
+                # the library's rule (csrc/emm.cu smot_xcorr_planar_mode): the flat form only under its developer switch
+                flat = os.environ.get("SMOT_XCORR_FLAT", "0") == "1" and n * Cc <= 28 * eng.sm_count()
                 self.xcorr_kernel = ("xcorr_flat_kernel<%d> (smot_xcorr_planar_mode)" if flat
                                      else "xcorr_planar_kernel<%d,CG> (smot_xcorr_planar_mode)") % eng.xcorr_planar_mode
                 self.xcorr_note = ("fp16 banded-Toeplitz mma.sync form on channel-planar windows staged with cp.async.bulk (one mbarrier "
                                    "per plane pair); mode 1 = structurally-zero MMA halves dropped (45 instead of 60 k16-MMAs per plane); "
-                                   "one CTA per SM with the planes dealt in 4-plane units while they fit one wave, else CG = 16 / 8 planes per CTA; bound by shared-memory wavefronts "
+                                   "CG = 16 planes per CTA while all CTAs are co-resident, else 8; bound by shared-memory wavefronts "
                                    "(~137 per plane) and the launch -> dependency wait -> L2 round trip -> drain chain (DESIGN.md 5.2)")
             else:
                 self.steps.append((L.smot_roi_align, (C.byref(pyr_pad), ops._ptr(self.sr), ops._ptr(self.boxes), None, n, Cc, S,

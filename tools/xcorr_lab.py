@@ -45,7 +45,7 @@ def ladder(res):
                 t = bench.time_launches(fn)
                 same = bool(torch.equal(out, ref)) if mode == 1 else None
                 us = t.get("graph", {}).get("us_per_launch")
-                res.append({"n": n, "C": Cc, "mma_mode": mode, "channel_group": cg, "ctas": n * Cc // cg, "graph_us": us,
+                res.append({"n": n, "C": Cc, "mma_mode": mode, "channel_group": cg, "ctas": (n * Cc // cg) if cg else min(n * Cc // 4, torch.cuda.get_device_properties(0).multi_processor_count), "graph_us": us,
                             "eager_us": t.get("eager", {}).get("us_per_launch"), "gbs": round(nbytes / (us * 1e-6) / 1e9, 1) if us else None,
                             "equal_to_cg16": same})
                 print(res[-1], flush=True)
