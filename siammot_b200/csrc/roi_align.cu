@@ -226,6 +226,26 @@ __device__ __forceinline__ RarSample rar_sample(float v, int size_padded, int si
   return s;
 }
 
+// One axis of one sample as the inner loop wants it (16 bytes = one shared-memory load): ELEMENT OFFSETS of the two corners and
+// their weights.  A corner outside the real map (the virtual zero padding) or a sample outside the padded map gets weight 0 and
+// the offset of a corner that exists, so the loop has no predicates, no flags and no 64-bit index arithmetic: 0 * value adds
+// +-0 where roi_align_kernel adds w * 0 or skips the sample -- the same sums, bit for bit (feature maps are finite).
+struct __align__(16) RarTap {
+  int lo, hi;        // element offsets (index * stride) of the corners
+  float h, l;        // weight of the lo / hi corner
+};
+
+__device__ __forceinline__ RarTap rar_tap(float v, int size_padded, int size_real, int pad, int stride) {
+  const RarSample s = rar_sample(v, size_padded, size_real, pad);
+  const bool valid = s.flags & 1, in_lo = s.flags & 2, in_hi = s.flags & 4;
+  RarTap t;
+  t.h = (valid && in_lo) ? s.h : 0.f;
+  t.l = (valid && in_hi) ? s.l : 0.f;
+  t.lo = in_lo ? s.lo * stride : (in_hi ? s.hi * stride : 0);
+  t.hi = in_hi ? s.hi * stride : t.lo;
+  return t;
+}
+
 // four channels as they sit in memory (fp16: 8 bytes = 2 registers), converted only when they are consumed
 template <typename T> struct Raw4;
 template <> struct Raw4<float> { float4 v; };
@@ -238,18 +258,17 @@ __device__ __forceinline__ float4 raw_to_f4(const Raw4<__half>& r) {
   const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.v.y));
   return make_float4(a.x, a.y, b.x, b.y);
 }
-template <typename T> __device__ __forceinline__ Raw4<T> raw_zero();
-template <> __device__ __forceinline__ Raw4<float> raw_zero<float>() { Raw4<float> r; r.v = make_float4(0.f, 0.f, 0.f, 0.f); return r; }
-template <> __device__ __forceinline__ Raw4<__half> raw_zero<__half>() { Raw4<__half> r; r.v = make_uint2(0u, 0u); return r; }
 
-// SAMP: compile-time sampling ratio (2 = every shipped configuration) or 0 = run time.  With SAMP the sample loops are
-// unrolled and the 4 * SAMP^2 corner loads of a bin are issued before the first multiply-add: the kernel was latency bound
-// after the instruction diet (a warp had one sample's 4 loads in flight at a time).
+// SAMP: compile-time sampling ratio (2 = every shipped configuration; the sample loops unroll and the 16 corner loads of a bin
+// are independent) or 0 = run time.
+// Round-2 instruction diet: ncu counted 818 warp instructions per bin (4 samples) in the previous form -- 64-bit index products
+// per corner, five-word table entries, per-corner predicates.  Now per sample: one 16-byte table load, 4 weight products, 4 adds +
+// 4 address computations + 4 loads, the conversions and the 32 multiply / add of the reference's summation order.
 template <typename T, bool PLANAR, int SAMP>
 __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T* __restrict__ out, int row_pitch, int plane_pitch) {
   extern __shared__ __align__(16) unsigned char rar_raw[];
-  __shared__ RarSample xs[RAR_MAX_SAMPLES];
-  __shared__ RarSample ys[RAR_MAX_YS];
+  __shared__ RarTap xs[RAR_MAX_SAMPLES];
+  __shared__ RarTap ys[RAR_MAX_YS];
   T* tile = reinterpret_cast<T*>(rar_raw);  // PLANAR only: [channels][RAP_TP]
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -286,70 +305,42 @@ __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T*
   const float x1 = roi[0] * sc, y1 = roi[1] * sc, x2 = roi[2] * sc, y2 = roi[3] * sc;
   const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
   const float bin_h = __fdiv_rn(rh, (float)a.res), bin_w = __fdiv_rn(rw, (float)a.res);
-  const int gh = a.sampling, gw = a.sampling;    // the host routes adaptive sampling (<= 0) to roi_align_kernel
+  const int gh = SAMP > 0 ? SAMP : a.sampling, gw = gh;    // the host routes adaptive sampling (<= 0) to roi_align_kernel
   const float cnt = (float)(gh * gw);
   for (int j = threadIdx.x; j < a.res * gw; j += blockDim.x) {
     const int pw = j / gw, ix = j - pw * gw;
     const float x = x1 + (float)pw * bin_w + __fdiv_rn(((float)ix + .5f) * bin_w, (float)gw);
-    xs[j] = rar_sample(x, Wp, W, pad);
+    xs[j] = rar_tap(x, Wp, W, pad, ld);
   }
   if ((int)threadIdx.x < (ph1 - ph0) * gh) {
     const int pr = (int)threadIdx.x / gh, iy = (int)threadIdx.x - pr * gh;
     const float y = y1 + (float)(ph0 + pr) * bin_h + __fdiv_rn(((float)iy + .5f) * bin_h, (float)gh);
-    ys[threadIdx.x] = rar_sample(y, Hp, H, pad);
+    ys[threadIdx.x] = rar_tap(y, Hp, H, pad, W * ld);
   }
   __syncthreads();
+  const int4* xs4 = reinterpret_cast<const int4*>(xs);
+  const int4* ys4 = reinterpret_cast<const int4*>(ys);
   for (int bin = wid; bin < (ph1 - ph0) * a.res; bin += 8) {
     const int pr = bin / a.res, pw = bin - pr * a.res, ph = ph0 + pr;
     for (int c = lane * 4; c < a.channels; c += 128) {
+      const T* __restrict__ base = feat + c;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (SAMP > 0) {
-        constexpr int NS = SAMP * SAMP;
-        Raw4<T> v[NS][4];
-        bool use[NS];
-        const Raw4<T> z = raw_zero<T>();
 #pragma unroll
-        for (int sidx = 0; sidx < NS; ++sidx) {       // all corner loads of the bin first (kept as loaded: 2 registers each in fp16)
-          const RarSample sy = ys[pr * SAMP + sidx / SAMP];
-          const RarSample sx = xs[pw * SAMP + sidx % SAMP];
-          use[sidx] = (sy.flags & sx.flags & 1) != 0;
-          const bool oyl = sy.flags & 2, oyh = sy.flags & 4, oxl = sx.flags & 2, oxh = sx.flags & 4;
-          v[sidx][0] = (use[sidx] && oyl && oxl) ? ld4raw(feat + ((size_t)sy.lo * W + sx.lo) * ld + c) : z;
-          v[sidx][1] = (use[sidx] && oyl && oxh) ? ld4raw(feat + ((size_t)sy.lo * W + sx.hi) * ld + c) : z;
-          v[sidx][2] = (use[sidx] && oyh && oxl) ? ld4raw(feat + ((size_t)sy.hi * W + sx.lo) * ld + c) : z;
-          v[sidx][3] = (use[sidx] && oyh && oxh) ? ld4raw(feat + ((size_t)sy.hi * W + sx.hi) * ld + c) : z;
-        }
-#pragma unroll
-        for (int sidx = 0; sidx < NS; ++sidx) {       // then the sums, in roi_align_kernel's order (iy outer, ix inner)
-          if (!use[sidx]) continue;
-          const RarSample sy = ys[pr * SAMP + sidx / SAMP];
-          const RarSample sx = xs[pw * SAMP + sidx % SAMP];
-          const float w1 = sy.h * sx.h, w2 = sy.h * sx.l, w3 = sy.l * sx.h, w4 = sy.l * sx.l;
-          const float4 v1 = raw_to_f4(v[sidx][0]), v2 = raw_to_f4(v[sidx][1]), v3 = raw_to_f4(v[sidx][2]), v4 = raw_to_f4(v[sidx][3]);
-          acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
-          acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
-          acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
-          acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
-        }
-      } else {
       for (int iy = 0; iy < gh; ++iy) {
-        const RarSample sy = ys[pr * gh + iy];
+        const int4 ty = ys4[pr * gh + iy];
+        const float yh = __int_as_float(ty.z), yl = __int_as_float(ty.w);
+#pragma unroll
         for (int ix = 0; ix < gw; ++ix) {
-          const RarSample sx = xs[pw * gw + ix];
-          if (!(sy.flags & sx.flags & 1)) continue;
-          const float w1 = sy.h * sx.h, w2 = sy.h * sx.l, w3 = sy.l * sx.h, w4 = sy.l * sx.l;
-          const bool oyl = sy.flags & 2, oyh = sy.flags & 4, oxl = sx.flags & 2, oxh = sx.flags & 4;
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 v1 = (oyl && oxl) ? ld4(feat + ((size_t)sy.lo * W + sx.lo) * ld + c) : z;
-          float4 v2 = (oyl && oxh) ? ld4(feat + ((size_t)sy.lo * W + sx.hi) * ld + c) : z;
-          float4 v3 = (oyh && oxl) ? ld4(feat + ((size_t)sy.hi * W + sx.lo) * ld + c) : z;
-          float4 v4 = (oyh && oxh) ? ld4(feat + ((size_t)sy.hi * W + sx.hi) * ld + c) : z;
+          const int4 tx = xs4[pw * gw + ix];
+          const float xh = __int_as_float(tx.z), xl = __int_as_float(tx.w);
+          const float w1 = yh * xh, w2 = yh * xl, w3 = yl * xh, w4 = yl * xl;
+          const float4 v1 = raw_to_f4(ld4raw(base + (ty.x + tx.x))), v2 = raw_to_f4(ld4raw(base + (ty.x + tx.y)));
+          const float4 v3 = raw_to_f4(ld4raw(base + (ty.y + tx.x))), v4 = raw_to_f4(ld4raw(base + (ty.y + tx.y)));
           acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
           acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
           acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
           acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
         }
-      }
       }
       acc.x = __fdiv_rn(acc.x, cnt), acc.y = __fdiv_rn(acc.y, cnt), acc.z = __fdiv_rn(acc.z, cnt), acc.w = __fdiv_rn(acc.w, cnt);
       if (PLANAR) {
@@ -382,9 +373,8 @@ static bool roi_rows_enabled() {
   return on;
 }
 
-// developer switch SMOT_ROI_UNROLL=1: the sampling-2 specialisation that issues all 16 corner loads of a bin before the
-// first multiply-add (96 registers, 2 CTAs per SM).  Measured on B200: SLOWER (41.6 vs 33.0 us on the search windows) -- the
-// rolled form keeps 4x the warps resident, which hides the load latency better than the deeper per-warp queue.
+// developer switch SMOT_ROI_UNROLL=1: the sampling-2 specialisation (sample loops unrolled at compile time).  With the round-2
+// table format the body is the same either way; the earlier, heavier unrolled form (96 registers) measured slower (41.6 vs 33.0 us).
 static bool roi_unroll_enabled() {
   static const bool on = [] {
     const char* e = getenv("SMOT_ROI_UNROLL");

@@ -34,8 +34,8 @@ def _rows_kernel_text(roi, fp16=False):
         helpers = re.sub(r"template <> __device__ __forceinline__ Raw4<__half> raw_zero<__half>\(\).*?\n", "", helpers)
     k = _function_text(roi, r"__global__ void __launch_bounds__\(256\) roi_align_rows_kernel")
     k = k.replace("extern __shared__ __align__(16) unsigned char rar_raw[];", "unsigned char* rar_raw = cpu_dynamic_smem;")
-    k = k.replace("__shared__ RarSample xs[RAR_MAX_SAMPLES];", "static RarSample xs[RAR_MAX_SAMPLES];")
-    k = k.replace("__shared__ RarSample ys[RAR_MAX_YS];", "static RarSample ys[RAR_MAX_YS];")
+    k = k.replace("__shared__ RarTap xs[RAR_MAX_SAMPLES];", "static RarTap xs[RAR_MAX_SAMPLES];")
+    k = k.replace("__shared__ RarTap ys[RAR_MAX_YS];", "static RarTap ys[RAR_MAX_YS];")
     return helpers + k
 
 
