@@ -592,6 +592,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcArgs a) {
 }
 
 // ---- host side ------------------------------------------------------------------------------
+constexpr int SMOT_TC_DEFAULT_MAXSPLIT = 8;
 static PFN_cuTensorMapEncodeTiled get_encode() {
   static PFN_cuTensorMapEncodeTiled fn = nullptr;
   static bool tried = false;
@@ -623,6 +624,21 @@ static bool encode_map(CUtensorMap* tm, const void* base, int rank, const uint64
     return false;
   }
   return true;
+}
+
+// Widest split of the K loop of a few-tile layer (levels 4 / 5, FC layers), finished by splitk_reduce_kernel.
+// SMOT_TC_MAXSPLIT=1..8 (SMOT_TC_NOSPLIT=1 is MAXSPLIT=1).  Measured on B200 in the clip pipeline (profiles/bench_r02m_*.json):
+// splitting 8 ways makes the static stage ALONE faster (0.646 vs 0.658 ms) but the pipeline slower (1228 vs 1277 frames/s):
+// 8 CTAs per tile plus a 960-CTA reduce kernel per layer occupy SMs that the detection tail and the track stage of the
+// neighbouring frames would otherwise use.
+static int tc_max_split() {
+  static const int v = [] {
+    if (getenv("SMOT_TC_NOSPLIT")) return 1;
+    const char* e = getenv("SMOT_TC_MAXSPLIT");
+    const int m = e ? atoi(e) : SMOT_TC_DEFAULT_MAXSPLIT;
+    return m < 1 ? 1 : (m > 8 ? 8 : m);
+  }();
+  return v;
 }
 
 bool conv2d_tc_supported(const smot_conv_desc* d) {
@@ -740,9 +756,9 @@ static int conv2d_tc_halo(const smot_conv_desc* d, int mode, cudaStream_t st) {
   {
     const int bw = d->Cout % 256 == 0 ? 256 : (d->Cout % 128 == 0 ? 128 : 64);
     const long long cw = tiles * (d->Cout / bw);
-    if (d->workspace && cw <= 40 && a.cin_chunks >= 2 && !getenv("SMOT_TC_NOSPLIT")) {
+    if (d->workspace && cw <= 40 && a.cin_chunks >= 2 && tc_max_split() > 1) {
       int sp = (int)(148 / cw);
-      if (sp > 8) sp = 8;
+      if (sp > tc_max_split()) sp = tc_max_split();
       if (sp > a.cin_chunks) sp = a.cin_chunks;
       const size_t need = (size_t)SMOT_CONV_WS_COUNTER_BYTES + (size_t)sp * tiles * TC_BM * d->Cout * sizeof(float);
       if (sp >= 2 && need <= d->workspace_bytes) splits = sp, BN = bw;
@@ -821,9 +837,9 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
     // for bit.  (With two images the split layers then run two half-length waves instead of one: the same time.)
     const long long tiles_img = tiles / (d->batch > 0 ? d->batch : 1);
     const long long cw = tiles_img * (d->Cout / bw);
-    if (d->workspace && cw <= 40 && all_chunks >= 16 && !getenv("SMOT_TC_NOSPLIT")) {
+    if (d->workspace && cw <= 40 && all_chunks >= 16 && tc_max_split() > 1) {
       int sp = (int)(148 / cw);
-      if (sp > 8) sp = 8;
+      if (sp > tc_max_split()) sp = tc_max_split();
       if (sp > all_chunks / 4) sp = all_chunks / 4;
       const size_t need = (size_t)SMOT_CONV_WS_COUNTER_BYTES + (size_t)sp * tiles * TC_BM * d->Cout * sizeof(float);
       if (sp >= 2 && need <= d->workspace_bytes) {
