@@ -42,6 +42,10 @@ struct TcArgs {
   // split-K (gridDim.z > 1): fp32 partial tiles [z][tile][128][Cout], summed by splitk_reduce_kernel
   int splits, chunks_per_split, num_tiles;
   int cluster_reduce;   // 1: the `splits` CTAs of a tile are one thread-block cluster and finish the tile themselves (no reduce kernel)
+  // in-CTA K slices (splits == 1, slices > 1): ONE CTA runs all `slices` K ranges of `chunks_per_split` chunks, each into its own
+  // TMEM accumulator (BN columns apart), and sums them in slice order in the epilogue -- the bits of the split-K path without
+  // its partial tiles, its reduce kernel and its 8x CTA count
+  int slices, tmem_cols;
   float* partial;
   unsigned long long* dbg;  // developer timing probe (SMOT_TC_DEBUG): 8 timestamps of CTA (0,0,0), else null
 };
@@ -147,7 +151,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 // ---- epilogue warps 2..5: TMEM -> scale / bias (+residual) (+ReLU) -> fp16 NHWC, or the raw fp32 partial tile when K is split
-template <int BN>
+template <int BN, bool SLICES_OK>
 __device__ __forceinline__ void tc_epilogue(const TcArgs& a, uint32_t tmem_base, float* s_scale, float* s_bias, uint64_t* tmem_full,
                                             int img, int h0, int w0, int n0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -211,7 +215,23 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, uint32_t tmem_base,
     mbar_wait(tmem_full, 0u);
     if (warp == 2 && lane == 0) TC_STAMP(3);
     tc_fence_after();
-    if (a.splits == 1) {
+    if (SLICES_OK && a.slices > 1) {
+      // the accumulators of the K slices, summed in slice order from 0.f: splitk_reduce_kernel's operations on the same values
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll 1
+        for (int z = 0; z < a.slices; ++z) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(z * BN + c0), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += v[j];
+        }
+        if (valid) finish(acc, c0);
+      }
+    } else if (a.splits == 1) {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
@@ -333,8 +353,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const int w0 = tw * a.tile_w, h0 = th * a.tile_h;
   const int n0 = blockIdx.y * BN;
   const int all_chunks = a.taps * a.cin_chunks;
-  const int it0 = (int)blockIdx.z * a.chunks_per_split;                 // this CTA's K range [it0, it0 + total)
-  const int total = min(a.chunks_per_split, all_chunks - it0);
+  const bool sliced = STAGES > 2 && a.slices > 1;                        // all K slices in this CTA, one accumulator each
+  const int it0 = sliced ? 0 : (int)blockIdx.z * a.chunks_per_split;    // this CTA's K range [it0, it0 + total)
+  const int total = sliced ? all_chunks : min(a.chunks_per_split, all_chunks - it0);
+  const uint32_t tmem_cols = sliced ? (uint32_t)a.tmem_cols : (uint32_t)BN;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -345,8 +367,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM allocation (whole warp), BN fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN)
+  if (warp == 1) {  // TMEM allocation (whole warp), BN fp32 columns per accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -381,15 +403,17 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         tc_fence_after();
         const uint64_t ad = umma_desc_sw128(sA + s * S::A_BYTES);
         const uint64_t bd = umma_desc_sw128(sB + s * S::B_BYTES);
+        const int sl = sliced ? it / a.chunks_per_split : 0, itl = it - sl * a.chunks_per_split;   // slice, chunk inside it
+        const uint32_t d_tmem = tmem_base + (uint32_t)(sl * BN);
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k)  // +32 bytes (2 x 16B units) per K=16 step inside the swizzle atom
-          umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)((it | k) != 0));
+          umma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)((itl | k) != 0));
         umma_commit(&empty[s]);  // slot reusable once these MMAs have read it
       }
-      umma_commit(tmem_full);    // accumulator complete
+      umma_commit(tmem_full);    // accumulator(s) complete
     }
   } else {  // ===== epilogue warps 2..5 =====
-    tc_epilogue<BN>(a, tmem_base, s_scale, s_bias, tmem_full, img, h0, w0, n0);
+    tc_epilogue<BN, (STAGES > 2)>(a, tmem_base, s_scale, s_bias, tmem_full, img, h0, w0, n0);
   }
   if (warp == 2 && lane == 0) TC_STAMP(4);
   if constexpr (STAGES > 2)   // the 2-stage variants run 4 CTAs per SM on full-GPU layers: they never split K, keep their registers low
@@ -406,7 +430,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   if (threadIdx.x == 0) TC_STAMP(5);
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -539,7 +563,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_halo_kernel(const __grid_c
       umma_commit(tmem_full);
     }
   } else {
-    tc_epilogue<BN>(a, tmem_base, s_scale, s_bias, tmem_full, img, h0, w0, n0);
+    tc_epilogue<BN, false>(a, tmem_base, s_scale, s_bias, tmem_full, img, h0, w0, n0);
   }
   tc_fence_before();
   __syncthreads();
@@ -782,6 +806,7 @@ static int conv2d_tc_halo(const smot_conv_desc* d, int mode, cudaStream_t st) {
   a.splits = (a.cin_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
   a.num_tiles = (int)tiles;
   a.cluster_reduce = 0;
+  a.slices = 1, a.tmem_cols = 0;
   a.dbg = nullptr;
   a.partial = d->workspace ? (float*)((char*)d->workspace + SMOT_CONV_WS_COUNTER_BYTES) : nullptr;
   dim3 grid((unsigned)tiles, (unsigned)(d->Cout / BN), (unsigned)a.splits);
@@ -863,6 +888,19 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
       }
     }
   }
+  // In-CTA K slices (default; SMOT_TC_SLICED=0 keeps the split CTAs + reduce kernel): the SAME K ranges, summed in the SAME order
+  // -- bit-identical results -- but by one CTA with one TMEM accumulator per range (BN x slices <= 512 columns).  Measured
+  // (profiles/bench_r02m_*, r02o_*): what the split costs the pipeline is SM-time -- 8 CTAs per tile and a 960-CTA reduce kernel
+  // per layer crowd out the detection tail and the track stage of the neighbouring frames -- not latency.
+  bool sliced = false;
+  if (splits > 1 && !cluster_reduce) {
+    const char* e = getenv("SMOT_TC_SLICED");
+    if (!(e && e[0] == '0')) {
+      int bn = 512 / splits;                       // splits <= 8 -> >= 64
+      if (bn > BN) bn = BN;
+      if (bn >= 64) sliced = true, BN = bn >= 256 ? 256 : (bn >= 128 ? 128 : 64);
+    }
+  }
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
@@ -883,6 +921,13 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   a.chunks_per_split = (all_chunks + splits - 1) / splits;
   a.splits = (all_chunks + a.chunks_per_split - 1) / a.chunks_per_split;  // no empty split
   a.cluster_reduce = (cluster_reduce && a.splits == splits) ? 1 : 0;
+  a.slices = 1, a.tmem_cols = 0;
+  if (sliced) {
+    a.slices = a.splits, a.splits = 1;
+    int cols = 32;
+    while (cols < a.slices * BN) cols <<= 1;
+    a.tmem_cols = cols;
+  }
   a.num_tiles = (int)tiles;
   {
     const char* dbg = getenv("SMOT_TC_DEBUG");  // hex device pointer to 8 x u64
@@ -896,7 +941,8 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   // at most one CTA per SM: nothing else hides the ~1 us TMA round trip (the loop then advances `ring depth` chunks
   // per round trip), so use the whole shared memory for the ring: 8 x 24 KB, 6 x 32 KB, 4 x 48 KB
   const bool solo = (long long)grid.x * grid.y * grid.z <= 148;
-  const int stages = tc_stages(BN, solo, shallow, a.chunks_per_split, fs);
+  int stages = tc_stages(BN, solo, shallow, sliced ? all_chunks : a.chunks_per_split, fs);
+  if (sliced && stages == 2) stages = BN == 128 ? 3 : 4;   // the 2-stage variants carry no slice code
 #define SMOT_TC_LAUNCH(BN_, ST_) launch_tc<BN_, ST_>(tmA, tmB, a, grid, st)
   const int rc = SMOT_TC_DISPATCH(BN, stages, SMOT_TC_LAUNCH);
 #undef SMOT_TC_LAUNCH

@@ -589,3 +589,31 @@ def test_conv2d_tcgen05_split_k():
         assert rel_err(gotfc.view(rows, 1024).float().cpu(), reffc) <= 2e-3
     torch.cuda.synchronize()
     assert int(ws[:_lib.CONV_WS_COUNTER_BYTES].view(torch.int32).abs().sum()) == 0
+
+
+@pytest.mark.parametrize("case", [(1, 512, 22, 40, 512, 3), (1, 256, 44, 80, 256, 3), (2, 256, 44, 80, 256, 3), (1, 1280, 22, 40, 512, 1),
+                                  (1, 6272, 1, 300, 1024, 1), (1, 256, 22, 40, 512, 3), (1, 128, 16, 16, 256, 3)])
+def test_conv2d_tcgen05_k_slices_equal_split_k(case, monkeypatch):
+    """Few-tile layers: one CTA with one TMEM accumulator per K range (default) against the split CTAs + reduce kernel
+    (SMOT_TC_SLICED=0): the same K ranges summed in the same order -- the same bits -- for levels 4 / 5, a root 1x1, fc6 and a
+    batch of two (frame-pair plans)."""
+    from siammot_b200 import _lib
+    B, Cin, H, W, Cout, k = case
+    g = torch.Generator().manual_seed(Cin + W)
+    dt = torch.float16
+    ws = ops().conv_workspace(DEV)
+    x = q(torch.randn(B, Cin, H, W, generator=g), dt)
+    w = q(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k), dt)
+    res = q(torch.randn(B, Cout, H, W, generator=g), dt)
+    scale, bias = 0.5 + torch.rand(Cout, generator=g), torch.randn(Cout, generator=g)
+    ref = F.relu(F.conv2d(x, w, None, 1, k // 2) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1) + res)
+    args = (nhwc(x, dt), ohwi(w, dt), scale.to(DEV), bias.to(DEV), nhwc(res, dt), 1, k // 2, True)
+    monkeypatch.setenv("SMOT_TC_SLICED", "0")
+    split = ops().conv2d(*args, algo=_lib.CONV_TCGEN05, workspace=ws)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("SMOT_TC_SLICED", "1")
+    for _ in range(2):
+        sliced = ops().conv2d(*args, algo=_lib.CONV_TCGEN05, workspace=ws)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(sliced), ref) <= 2e-3
+    assert torch.equal(sliced, split)
