@@ -896,8 +896,13 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   if (splits > 1 && !cluster_reduce) {
     const char* e = getenv("SMOT_TC_SLICED");
     if (!(e && e[0] == '0')) {
+      // N tile: 64 by default (as many CTAs as the layer has 64-channel tiles: the shortest chain per CTA; 4 accumulators of
+      // 128 columns measured slower at 1080p: 776 vs 793 frames/s); SMOT_TC_SLICED=128 / 256 take wider tiles where they fit
+      int want = e ? atoi(e) : 64;
+      if (want != 128 && want != 256) want = 64;
       int bn = 512 / splits;                       // splits <= 8 -> >= 64
       if (bn > BN) bn = BN;
+      if (bn > want) bn = want;
       if (bn >= 64) sliced = true, BN = bn >= 256 ? 256 : (bn >= 128 ? 128 : 64);
     }
   }
