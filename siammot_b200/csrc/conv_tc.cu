@@ -893,7 +893,11 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
   // (profiles/bench_r02m_*, r02o_*): what the split costs the pipeline is SM-time -- 8 CTAs per tile and a 960-CTA reduce kernel
   // per layer crowd out the detection tail and the track stage of the neighbouring frames -- not latency.
   bool sliced = false;
-  if (splits > 1 && !cluster_reduce) {
+  // ... where the split is widest (8 ranges = at most 18 tiles): measured on one box (profiles/bench_r02s_*.json), slicing EVERY split
+  // layer gives 720p30 1243 -> 1261 (`value`), 1221 -> 1262 (`e2e`) but 1080p80 801 -> 785 and R-50 e2e 608 -> 582: with 4 ranges
+  // (19-37 tiles) the split's 4x CTAs are what fills the GPU; with 8 they crowd it.  SMOT_TC_SLICED_MIN sets the threshold.
+  static const int slice_min = getenv("SMOT_TC_SLICED_MIN") ? atoi(getenv("SMOT_TC_SLICED_MIN")) : 8;
+  if (splits >= slice_min && splits > 1 && !cluster_reduce) {
     const char* e = getenv("SMOT_TC_SLICED");
     if (!(e && e[0] == '0')) {
       // N tile: 64 by default (as many CTAs as the layer has 64-channel tiles: the shortest chain per CTA; 4 accumulators of
