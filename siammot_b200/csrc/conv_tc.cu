@@ -888,21 +888,19 @@ int conv2d_tc(const smot_conv_desc* d, cudaStream_t st) {
       }
     }
   }
-  // In-CTA K slices (default; SMOT_TC_SLICED=0 keeps the split CTAs + reduce kernel): the SAME K ranges, summed in the SAME order
-  // -- bit-identical results -- but by one CTA with one TMEM accumulator per range (BN x slices <= 512 columns).  Measured
-  // (profiles/bench_r02m_*, r02o_*): what the split costs the pipeline is SM-time -- 8 CTAs per tile and a 960-CTA reduce kernel
-  // per layer crowd out the detection tail and the track stage of the neighbouring frames -- not latency.
+  // In-CTA K slices (developer switch SMOT_TC_SLICED=1 | 128 | 256 = N tile; default off): the SAME K ranges, summed in the SAME
+  // order -- bit-identical results (test_conv2d_tcgen05_k_slices_equal_split_k) -- but by one CTA with one TMEM accumulator per
+  // range (BN x slices <= 512 columns), no partial tiles, no reduce kernel.  Measured pairwise on the same boxes
+  // (profiles/bench_r02{r,s,t}_*.json; value / e2e frames/s, split -> sliced): 720p30 1243 / 1221 -> 1261 / 1262 (+1.5 / +3.4 %),
+  // but 1080p80 801 / 785 -> 785 / 770, R-50 570 / 608 -> 572 / 582, model(frame) 687 -> 663; slicing only the 8-wide splits
+  // (SMOT_TC_SLICED_MIN=8) lost on all three.  The split's extra CTAs fill the GPU where the neighbouring stages leave room and
+  // crowd it where they do not; with no rule that holds across the three workloads, the validated split path stays the default.
   bool sliced = false;
-  // ... where the split is widest (8 ranges = at most 18 tiles): measured on one box (profiles/bench_r02s_*.json), slicing EVERY split
-  // layer gives 720p30 1243 -> 1261 (`value`), 1221 -> 1262 (`e2e`) but 1080p80 801 -> 785 and R-50 e2e 608 -> 582: with 4 ranges
-  // (19-37 tiles) the split's 4x CTAs are what fills the GPU; with 8 they crowd it.  SMOT_TC_SLICED_MIN sets the threshold.
-  static const int slice_min = getenv("SMOT_TC_SLICED_MIN") ? atoi(getenv("SMOT_TC_SLICED_MIN")) : 8;
+  static const int slice_min = getenv("SMOT_TC_SLICED_MIN") ? atoi(getenv("SMOT_TC_SLICED_MIN")) : 2;
   if (splits >= slice_min && splits > 1 && !cluster_reduce) {
     const char* e = getenv("SMOT_TC_SLICED");
-    if (!(e && e[0] == '0')) {
-      // N tile: 64 by default (as many CTAs as the layer has 64-channel tiles: the shortest chain per CTA; 4 accumulators of
-      // 128 columns measured slower at 1080p: 776 vs 793 frames/s); SMOT_TC_SLICED=128 / 256 take wider tiles where they fit
-      int want = e ? atoi(e) : 64;
+    if (e && e[0] != '0') {
+      int want = atoi(e);
       if (want != 128 && want != 256) want = 64;
       int bn = 512 / splits;                       // splits <= 8 -> >= 64
       if (bn > BN) bn = BN;

@@ -594,9 +594,9 @@ def test_conv2d_tcgen05_split_k():
 @pytest.mark.parametrize("case", [(1, 512, 22, 40, 512, 3), (1, 256, 44, 80, 256, 3), (2, 256, 44, 80, 256, 3), (1, 1280, 22, 40, 512, 1),
                                   (1, 6272, 1, 300, 1024, 1), (1, 256, 22, 40, 512, 3), (1, 128, 16, 16, 256, 3)])
 def test_conv2d_tcgen05_k_slices_equal_split_k(case, monkeypatch):
-    """Few-tile layers: one CTA with one TMEM accumulator per K range (default) against the split CTAs + reduce kernel
-    (SMOT_TC_SLICED=0): the same K ranges summed in the same order -- the same bits -- for levels 4 / 5, a root 1x1, fc6 and a
-    batch of two (frame-pair plans)."""
+    """Few-tile layers: one CTA with one TMEM accumulator per K range (SMOT_TC_SLICED=1) against the split CTAs + reduce kernel
+    (the default): the same K ranges summed in the same order -- the same bits -- for levels 4 / 5, a root 1x1, fc6 and a batch
+    of two (frame-pair plans)."""
     from siammot_b200 import _lib
     B, Cin, H, W, Cout, k = case
     g = torch.Generator().manual_seed(Cin + W)
