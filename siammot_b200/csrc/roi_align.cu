@@ -356,11 +356,10 @@ __global__ void __launch_bounds__(256) roi_align_rows_kernel(const RoiArgs a, T*
   }
   if (PLANAR) {
     __syncthreads();
+    // a warp per channel, a lane per bin of the row (res <= 32): no division per element, one contiguous run per store
     T* dst = out + (size_t)r * a.channels * plane_pitch + (size_t)ph0 * row_pitch;
-    for (int i = threadIdx.x; i < a.channels * a.res; i += blockDim.x) {
-      const int c = i / a.res, pw = i - c * a.res;
-      dst[(size_t)c * plane_pitch + pw] = tile[(size_t)c * RAP_TP + pw];
-    }
+    for (int c = wid; c < a.channels; c += 8)
+      if (lane < a.res) dst[(size_t)c * plane_pitch + lane] = tile[(size_t)c * RAP_TP + lane];
   }
 }
 
