@@ -649,6 +649,7 @@ static int launch_xcorr(const void* x, const void* k, void* out, int n, int C, c
 // =============================================================================================
 constexpr int EMM_CH = 7;
 
+constexpr int EMM_MAX_BAND = 64;   // rows of the upsampled map per CTA (= the upsampling factor, 16 in every shipped configuration)
 struct CubicTap {
   int idx[4];
   float w[4];
@@ -732,6 +733,16 @@ __global__ void __launch_bounds__(256) emm_score_kernel(const DecodeArgs a) {
   const float* mp = a.maps + (size_t)n * O * O * a.map_ld;
   for (int i = threadIdx.x + r_lo * O * EMM_CH; i < (r_hi + 1) * O * EMM_CH; i += blockDim.x)
     maps_s[i] = mp[(size_t)(i / EMM_CH) * a.map_ld + (i % EMM_CH)];
+  // the vertical taps and the window weight of the band's rows: once per CTA instead of once per pixel (same values)
+  __shared__ CubicTap ty_s[EMM_MAX_BAND];
+  __shared__ float hann_y[EMM_MAX_BAND];
+  if ((int)threadIdx.x < y1 - y0) {
+    CubicTap t = cubic_taps(y0 + (int)threadIdx.x, scale, O);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t.idx[j] = (t.idx[j] - r_lo) * OW;   // element offset of the tap's row inside a channel of `tmp`
+    ty_s[threadIdx.x] = t;
+    hann_y[threadIdx.x] = a.hann[y0 + threadIdx.x];
+  }
   __syncthreads();
   for (int x = threadIdx.x; x < OW; x += blockDim.x) {
     const CubicTap tx = cubic_taps(x, scale, O);
@@ -750,17 +761,19 @@ __global__ void __launch_bounds__(256) emm_score_kernel(const DecodeArgs a) {
   unsigned long long best = 0ull;
   for (int x = threadIdx.x; x < OW; x += blockDim.x) {
     const float wx = a.hann[x];
+    const float* tcol = tmp + x;
+    const int ch_stride = a.rows_max * OW;
     for (int y = y0; y < y1; ++y) {
-      const CubicTap ty = cubic_taps(y, scale, O);
+      const CubicTap ty = ty_s[y - y0];
       float c[EMM_CH];
 #pragma unroll
       for (int ch = 0; ch < EMM_CH; ++ch) {
         float v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = tmp[(ch * a.rows_max + (ty.idx[j] - r_lo)) * OW + x];
+        for (int j = 0; j < 4; ++j) v[j] = tcol[ch * ch_stride + ty.idx[j]];
         c[ch] = hsum4(v, ty.w);
       }
-      const PixelEval e = eval_pixel(c, box_w, box_h, a.hann[y] * wx, a.use_centerness, a.sigma, a.one_minus_sigma);
+      const PixelEval e = eval_pixel(c, box_w, box_h, hann_y[y - y0] * wx, a.use_centerness, a.sigma, a.one_minus_sigma);
       // scores are >= 0 here (conf, pen, window >= 0), so the raw float bits order like the floats
       const unsigned idx = (unsigned)(y * OW + x);
       const unsigned long long key = ((unsigned long long)__float_as_uint(fmaxf(e.score, 0.f)) << 32) |
@@ -974,6 +987,7 @@ extern "C" int smot_emm_decode(const float* maps, int map_ld, int n, int O, int 
   if (n == 0) return SMOT_OK;
   SMOT_CHECK_ARG(maps && sr && tboxes && hann && out_boxes && out_conf && out_valid && scratch, "smot_emm_decode: null argument");
   const int OW = O * up;
+  SMOT_CHECK_ARG(up <= EMM_MAX_BAND, "smot_emm_decode: upsampling factor %d > %d", up, EMM_MAX_BAND);
   const int rows_per_cta = up;                        // one source-row period per band
   const int rows_max = min(O, rows_per_cta / up + 4);  // source rows a band can touch (4 taps)
   const size_t smem = ((size_t)O * O * EMM_CH + (size_t)EMM_CH * rows_max * OW) * sizeof(float);
