@@ -294,7 +294,13 @@ def kernels_per_frame(h):
     return n
 
 
-REPEATS = 5   # timed regions per arm: the line reports the median (a 20-step region is ~20 ms; one region cannot resolve 5 %)
+REPEATS = 5   # least number of timed regions per arm: the line reports the median region
+
+
+def repeats(steps):
+    """Timed regions per arm: at least REPEATS, and enough short ones to cover ~0.4 s (a 20-step region is 16 ms: one scheduler
+    hiccup on a shared host is 10 % of it, and 5 such regions do not make a stable median; 20 do and still cost < 1 s)."""
+    return REPEATS if REPEATS < 5 else max(REPEATS, min(25, -(-400 // max(int(steps), 1))))
 
 
 def run_ours(args):
@@ -343,7 +349,7 @@ def run_ours(args):
     value_ms = []
     h.eng.host_timers = {}
     t_loop0 = time.perf_counter()
-    for rep in range(REPEATS):
+    for rep in range(repeats(args.steps)):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -378,7 +384,7 @@ def run_ours(args):
         h.model.forward_clip([src[i % N_FRAMES] for i in range(max(args.warmup, 4))], before_frame=hook)
         seq_h = [src[(args.warmup + i) % N_FRAMES] for i in range(args.steps)]
         dts = []
-        for rep in range(REPEATS):
+        for rep in range(repeats(args.steps)):
             barrier()
             t0 = time.perf_counter()
             res = h.model.forward_clip(seq_h, before_frame=hook)
@@ -478,7 +484,7 @@ def run_ours(args):
                          "e2e.per_frame_call: model(frame) once per frame; "
                          "model.results_on_host = True (CPU BoxLists from the packed result block the engine copies D2H)",
                   "baseline_note": "17 FPS = README.md:22 'a single modern GPU', unnamed hardware",
-                  "repeats": "%d timed regions of exactly %d steps per arm; value / e2e are the median region (max over ranks)" % (REPEATS, args.steps),
+                  "repeats": "%d timed regions of exactly %d steps per arm; value / e2e are the median region (max over ranks)" % (repeats(args.steps), args.steps),
                   "numa_cpus_bound": numa_cpus},
         "spread": {"value_fps": [round(world * args.steps / (x * 1e-3), 1) for x in value_ms],
                    "e2e_fps": [round(world * args.steps / x, 1) for x in e2e_clip_all],

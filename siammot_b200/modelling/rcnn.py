@@ -893,26 +893,39 @@ def _forward_clip_pairs(self, eng, frames, before_frame=None, given_detections=N
     sD.wait_stream(cur)
     KP = 2                          # pair slots
     slot_free = [None] * KP         # event: every reader of the pair slot's buffers is enqueued-complete
-    single_free = None
-    plans, launched = {}, set()
+    single_free = [None]
+    plans = {}
+    # Backbone units: frame 0 ALONE (the first result then waits for one backbone pass, not two: 0.55 ms less pipeline fill per
+    # clip, 3 % of a 20-frame clip), then pairs, then an odd last frame alone.  unit = (first frame, frames, pair slot | None)
+    units, t = [], 0
+    if n_frames >= 3:
+        units.append((0, 1, None))
+        t = 1
+    while t < n_frames:
+        c = 2 if t + 1 < n_frames else 1
+        units.append((t, c, (sum(1 for u in units if u[1] == 2) % KP) if c == 2 else None))
+        t += c
+    unit_of = {}
+    for u, (f, c, _) in enumerate(units):
+        for i in range(c):
+            unit_of[f + i] = u
 
-    def backbone(p):
-        """Backbone half of pair p (frames 2p, 2p+1), or of the odd last frame alone."""
-        t0 = 2 * p
-        launched.add(p)
+    def backbone(u):
+        """Backbone half of unit u."""
+        t0, count, pslot = units[u]
         with torch.cuda.stream(sA):
-            if t0 + 1 < n_frames:
-                if slot_free[p % KP] is not None:
-                    sA.wait_event(slot_free[p % KP])
-                PP = eng.run_backbone_pair(frames[t0], frames[t0 + 1], p % KP)
+            if count == 2:
+                if slot_free[pslot] is not None:
+                    sA.wait_event(slot_free[pslot])
+                PP = eng.run_backbone_pair(frames[t0], frames[t0 + 1], pslot)
                 if PP.backbone_done is None:
                     PP.backbone_done = torch.cuda.Event()
                 PP.backbone_done.record(sA)
                 plans[t0], plans[t0 + 1] = PP.frames[0], PP.frames[1]
                 PP.frames[0].backbone_done = PP.frames[1].backbone_done = PP.backbone_done
             else:
-                if single_free is not None:
-                    sA.wait_event(single_free)
+                if single_free[0] is not None:
+                    sA.wait_event(single_free[0])
                 P = (eng.run_static_raw(frames[t0], 0, part=0) if _is_raw_frame(frames[t0]) else eng.run_static(frames[t0], 0, part=0))
                 if P.backbone_done is None:
                     P.backbone_done = torch.cuda.Event()
@@ -928,7 +941,6 @@ def _forward_clip_pairs(self, eng, frames, before_frame=None, given_detections=N
                 P.static_done = torch.cuda.Event()
             P.static_done.record(sD)
 
-    n_pairs = (n_frames + 1) // 2
     deferred = []
     with torch.no_grad():
         backbone(0)
@@ -937,22 +949,23 @@ def _forward_clip_pairs(self, eng, frames, before_frame=None, given_detections=N
             P = plans.pop(t)
             if before_frame is not None:
                 before_frame(t)
-            cur.wait_event(P.static_done)          # D(t) complete (hence B of its pair)
+            cur.wait_event(P.static_done)          # D(t) complete (hence B of its unit)
             pending = self.roi_heads.launch_frame(P, self._mem, given_detections[t] if given_detections is not None else None)
             _run_deferred(deferred, results)
-            p = t // 2
-            if t % 2 == 0 and p + 1 < n_pairs and (p + 1) not in launched:
-                backbone(p + 1)                    # its slot held pair p-1, whose last reader finished in iteration t-1
+            u = unit_of[t]
+            t0, count, pslot = units[u]
+            if t == t0 and u + 1 < len(units):
+                backbone(u + 1)                    # its buffers held the unit before u (or nothing), whose last reader finished in iteration t-1
             if t + 1 < n_frames:
                 detect(t + 1)
             result, mem = self.roi_heads.finish_frame(pending, next_P=plans.get(t + 1), defer=deferred if eng.clip_defer else None)
-            if t % 2 == 1 or t + 1 == n_frames:    # the pair's (or the single plan's) buffers are free for the next user
+            if t == t0 + count - 1:                # the unit's buffers are free for their next user
                 ev = torch.cuda.Event()
                 ev.record(cur)
-                if getattr(P, "pair", None) is not None:
-                    slot_free[p % KP] = ev
+                if pslot is not None:
+                    slot_free[pslot] = ev
                 else:
-                    single_free = ev
+                    single_free[0] = ev
             self.__dict__["_mem"] = self.__dict__["track_memory"] = mem      # (plain attributes: bypass nn.Module.__setattr__)
             results.append(result)
         _run_deferred(deferred, results)
