@@ -12,7 +12,7 @@ POLICIES = ["lazy", "eager", "workers_eager", "default_eager", ("random", 1), ("
 NAME = "emm_amodal_expire_192x320"
 
 
-def _run_sim(monkeypatch, policy, mode, env=None, sabotage=None):
+def _run_sim(monkeypatch, policy, mode, env=None, sabotage=None, n_frames=None):
     from siammot_b200.modelling import build_siammot
     for k, v in (env or {}).items():
         monkeypatch.setenv(k, v)
@@ -28,6 +28,8 @@ def _run_sim(monkeypatch, policy, mode, env=None, sabotage=None):
     model.reset_siammot_status()
     pool = model.roi_heads.track.track_pool
     frames = list(clip)
+    if n_frames is not None:      # a longer clip: the scenario's frames over and over (the tracks persist, slots get reused)
+        frames = [frames[i % len(frames)] for i in range(n_frames)]
     states = []
     sim.active = True
     try:
@@ -209,3 +211,19 @@ def test_frame_overlap_detector_detects_the_missing_wait(monkeypatch):
         if broken:
             break
     assert broken
+
+
+@pytest.mark.parametrize("n_frames", [7, 8])
+@pytest.mark.parametrize("policy", ["lazy", "workers_eager", "default_eager", ("random", 1), ("random", 4)], ids=str)
+def test_long_pair_clip_reuses_its_slots_safely(policy, n_frames, monkeypatch):
+    """Frame 0 alone, then pairs on two alternating pair slots, then (8 frames) an odd last frame on the single-frame plan
+    again: 7 / 8 frames reuse every buffer set at least once.  The adversarial schedule must give what per-frame calls give
+    (same emulated kernels, no overlap), row for row and bit for bit."""
+    ref = _run_sim(monkeypatch, "eager", "frame", n_frames=n_frames)
+    got = _run_sim(monkeypatch, policy, "clip", env={"SMOT_CLIP_SPLIT": "1", "SMOT_CLIP_SLOTS": "3", "SMOT_CLIP_PAIRS": "1"}, n_frames=n_frames)
+    assert len(ref) == len(got) == n_frames
+    assert sum(int((r["ids"] >= 0).sum()) for r in ref) > 0
+    for t, (a, b) in enumerate(zip(ref, got)):
+        assert torch.equal(a["ids"], b["ids"]) and torch.equal(a["labels"], b["labels"]), t
+        assert torch.equal(a["boxes"], b["boxes"]) and torch.equal(a["scores"], b["scores"]), t
+        assert a["active"] == b["active"] and a["dormant"] == b["dormant"], t
